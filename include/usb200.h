@@ -1,0 +1,175 @@
+/*
+ * usb200.h -- C ABI of the B200-native USEARCH/UCLUST hot path (libusb200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch
+ * types, no exceptions.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/src).  All functions return 0 on success or a negative
+ * USB_E* code; usb_last_error() returns the message of the last failure on the calling thread.
+ * The reference's own error convention is Die() = message + exit(1) (myutils.cpp:867); the host
+ * shim (usearch12_b200/csrc/host) maps non-zero returns to that behaviour.
+ *
+ * There is NO CPU fallback behind this interface: every compute entry point runs CUDA kernels
+ * built for sm_100a and fails with USB_ECUDA when no device is usable.
+ */
+#ifndef USB200_H
+#define USB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USB_OK 0
+#define USB_EINVAL (-1)   /* bad argument / unsupported option combination (fails loudly) */
+#define USB_ECUDA (-2)    /* CUDA runtime error or no device */
+#define USB_ENOMEM (-3)
+#define USB_ELIMIT (-4)   /* an internal capacity was exceeded (message says which) */
+
+/* POD snapshot of the options the path reads.  Float options stay `float`
+ * because the reference stores them as float and widens on read (opts.cpp:8-15,80-88); the
+ * accept test compares double(ids)/double(cols) with (double)(float)id (accepter.cpp:36-38). */
+typedef struct usb_params {
+	uint32_t struct_size;   /* = sizeof(usb_params), ABI check */
+	int32_t is_nucleo;      /* 1 = nucleotide DB (amino: usearch_local row, not built yet) */
+	float id;               /* -id */
+	uint32_t maxaccepts;    /* -maxaccepts (terminator.cpp:23-31), default 1 */
+	uint32_t maxrejects;    /* -maxrejects, default 32 (8 for cluster_fast) */
+	int32_t strand_both;    /* -strand both (searcher.cpp:144-158) */
+	uint32_t word_length;   /* UDB word length, nt 8 (udbparams.cpp:246-250) */
+	uint32_t big;           /* -big, 100000 (o_defaults.inc:25) */
+	uint32_t bump;          /* -bump, 50 (udbusortedsearcher.cpp:269-282) */
+	uint32_t stepwords;     /* -stepwords, 8 (wordparams.cpp:167-192) */
+	uint32_t band;          /* -band, 16 (alnheuristics.cpp:33) */
+	uint32_t minhsp;        /* -minhsp, 16 */
+	uint32_t hspw;          /* HSP finder word length, nt 5 (alnheuristics.cpp:37) */
+	float xdrop_nw;         /* -xdrop_nw, 8 */
+	float match;            /* -match, 1 */
+	float mismatch;         /* -mismatch, -2 */
+	float gap_open;         /* internal gap open, nt -10 (alnparams.cpp:378-384) */
+	float gap_ext;          /* internal gap extend, -1 */
+	float term_gap_open;    /* terminal gap open, -0.5 */
+	float term_gap_ext;     /* terminal gap extend, -0.5 */
+	int32_t dbmask;         /* 1 = fastnucleo soft-masking of the DB (makeudb.cpp:11-25) */
+	int32_t cluster_mode;   /* 1 = cluster_fast semantics: raw un-masked centroids, growing DB */
+} usb_params;
+
+/* Defaults of -usearch_global (cluster_fast=0) or -cluster_fast (=1). */
+void usb_default_params(usb_params *p, int cluster_fast);
+
+/* One accepted hit == the statistics the reference derives lazily from an AlignResult
+ * (alignresult.h:17-245, arscorer.cpp:201-296 FillLo).  Coordinates are 0-based. */
+typedef struct usb_hit {
+	uint32_t query;        /* query index within the batch */
+	uint32_t target;       /* DB target index (SeqDB index, m_Target->m_Index) */
+	uint32_t strand;       /* 0 = plus, 1 = query reverse-complemented */
+	uint32_t rank;         /* position of the target in the U-sorted candidate order */
+	uint32_t ids, mism, intgaps, opens;
+	uint32_t first_mq, first_mt, last_mq, last_mt; /* first / last M column positions */
+	uint32_t first_mcol, alnlen;                   /* alnlen = cols between first and last M */
+	uint32_t ql, tl;
+	uint32_t run_off, run_cnt; /* path as runs in the run arena: (length << 2) | op, op 0=M 1=D 2=I */
+} usb_hit;
+
+/* Per (query,strand) search counters (diagnostics; the reference has no equivalent object). */
+typedef struct usb_qstat {
+	uint32_t n_cand;     /* TopOrder.Size (udbusortedsearcher.cpp:109-120) */
+	uint32_t n_tried;    /* Align() calls made before the Terminator fired */
+	uint32_t n_hspfail;  /* attempts rejected by the HSP identity gate (globalalignmem.cpp:171) */
+	uint32_t n_dp;       /* banded Viterbi calls */
+	uint32_t dp_cells;   /* DP cells computed */
+	uint32_t n_accept;
+	uint32_t seq_bytes;  /* sum over attempts of (query + target) letters read */
+} usb_qstat;
+
+typedef struct usb_index usb_index;       /* UDBData + SeqDB on one device (udbdata.h:15-31) */
+typedef struct usb_searcher usb_searcher; /* UDBUsortedSearcher + GlobalAligner + Accepter + Terminator */
+typedef struct usb_result usb_result;     /* what HitMgr holds after a batch (hitmgr.cpp:120-161) */
+
+const char *usb_last_error(void);
+/* Number of usable CUDA devices (0 when none); never fails. */
+int usb_device_count(void);
+
+/* ---- index: replaces LoadDB/LoadUDB (loaddb.cpp:100-127) = MaskDB (makeudb.cpp:11-25) +
+ * UDBParams::FromCmdLine (udbparams.cpp:58) + UDBData::FromSeqDB (udbbuild.cpp:303-398).
+ * seqs = concatenated target letters, seq_off[n_seq+1] byte offsets.  Sequences are copied. */
+int usb_index_create(int device, const usb_params *p, const uint8_t *seqs, const uint64_t *seq_off,
+  uint32_t n_seq, usb_index **out);
+void usb_index_free(usb_index *ix);
+uint32_t usb_index_seq_count(const usb_index *ix);
+uint64_t usb_index_posting_count(const usb_index *ix);
+/* Host-side introspection for parity tests: one UDB row (m_UDBRows[word], m_Sizes[word]). */
+int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size);
+/* Masked target sequence as indexed (SeqDB::GetSeq after SeqDB::Mask, seqdb.cpp:415). */
+int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t **seq, uint32_t *len);
+
+/* ---- searcher: replaces MakeDBSearcher (makedbsearcher.cpp:75) wiring for one device. */
+int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searcher **out);
+void usb_searcher_free(usb_searcher *s);
+
+/* ---- the hot path.  Replaces the per-query loop of Thread() (search.cpp:51-87):
+ * Searcher::Search (searcher.cpp:122) -> UDBUsortedSearcher::SearchImpl
+ * (udbusortedsearcher.cpp:122) -> GlobalAligner::Align (globalaligner.cpp:37) -> Searcher::OnAR
+ * (searcher.cpp:52), for a whole batch of queries.  Host buffers in, host result out. */
+int usb_search_batch(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  usb_result **out);
+
+/* Staged form of the same call (bench.py times the middle step with inputs resident in HBM). */
+int usb_batch_upload(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q);
+/* Runs all kernels on the uploaded batch.  ms[0]=U-sort kernel, ms[1]=align kernel, ms[2]=total
+ * device time (CUDA events on the searcher's stream); ms may be NULL. */
+int usb_batch_run(usb_searcher *s, float *ms);
+int usb_batch_download(usb_searcher *s, usb_result **out);
+/* Counters of the last usb_batch_run: out[0] = UDB postings read by the U-sort kernel,
+ * out[1] = hits, out[2] = path runs, out[3] = (query,strand) jobs. */
+int usb_batch_counters(const usb_searcher *s, uint64_t out[4]);
+/* Number of kernel launches issued by this searcher so far. */
+uint64_t usb_searcher_launch_count(const usb_searcher *s);
+/* Device-resident packed hit records of the last usb_batch_run (for the NCCL gather of
+ * section 8e): copies min(n_hits, cap_hits) usb_hit records into a caller-owned DEVICE buffer. */
+int usb_batch_export_hits_device(usb_searcher *s, void *dev_dst, uint64_t cap_hits, uint64_t *n_hits);
+
+/* Result accessors.  Hits are grouped by query (ascending) and, within a query, in the
+ * reference's output order (HitMgr::Sort, hitmgr.cpp:477; sort.h:63-102). */
+uint64_t usb_result_hit_count(const usb_result *r);
+const usb_hit *usb_result_hits(const usb_result *r);
+const uint32_t *usb_result_runs(const usb_result *r, uint64_t *n_runs);
+/* first_hit[q] .. first_hit[q+1] = hit range of query q (n_q+1 entries). */
+const uint64_t *usb_result_query_offsets(const usb_result *r);
+/* qstat[2*q + strand] */
+const usb_qstat *usb_result_qstats(const usb_result *r);
+void usb_result_free(usb_result *r);
+/* Expands a hit's path to the reference's M/D/I string (PathInfo::GetPath, pathinfo.cpp:37-214);
+ * buf must hold ql+tl+1 bytes.  Returns the length. */
+uint32_t usb_result_path(const usb_result *r, const usb_hit *h, char *buf);
+
+/* ---- stage-level entry points (each is one kernel; used by the parity tests and by bench.py's
+ * per-kernel roofline).  All take host buffers.
+ *
+ * a1..a6: U-sort candidate ranking (udbusortedsearcher.cpp:109-120 SetTargetOrder).
+ * For each query writes up to k_max candidates (target, U) in TopOrder order into
+ * cand_t/cand_u[q*k_max ..] and TopOrder.Size into n_cand[q].  u_out (may be NULL) receives the
+ * full U vector of each query (n_q * n_seq entries). */
+int usb_rank_batch(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  uint32_t k_max, uint32_t *cand_t, uint32_t *cand_u, uint32_t *n_cand, uint32_t *u_out);
+
+/* a9..a15: GlobalAligner::Align for explicit (query, target) pairs (globalaligner.cpp:37-61).
+ * aligned[i] = 0 when the HSP gate rejected the pair; otherwise hits[i] is filled (rank = i) and
+ * the path goes to the result's run arena.  hsp_out (may be NULL): per pair 1 + 4*max_hsp words:
+ * chained HSP count then {Loi, Loj, Len, 2*Score}. */
+int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_pairs, uint8_t *aligned,
+  usb_result **out, uint32_t *hsp_out, uint32_t max_hsp);
+
+/* a14/a15: banded Viterbi + traceback on explicit rectangles (viterbifastbandmem.cpp:232-253
+ * ViterbiFastMainDiagMem).  flags bit0..3 = left_a, left_b, right_a, right_b terminal sides.
+ * paths receives NUL-terminated M/D/I strings at path_off[i] (capacity la+lb+1 each);
+ * score2[i] = 2 * alignment score. */
+int usb_viterbi_batch(usb_searcher *s, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+  const uint64_t *b_off, const uint8_t *flags, uint32_t n, char *paths, const uint64_t *path_off,
+  int32_t *score2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,70 @@
+"""CPU-only: the oracle restatement against the golden files written by the UNMODIFIED reference
+binary (tools/make_golden.py), plus host-logic checks that need no GPU."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import uso_py as O
+from tests import util
+
+
+@pytest.mark.parametrize("variant", ["plus97", "both80_ma0"])
+def test_oracle_matches_reference_golden(golden, variant):
+    kw = util.VARIANTS[variant]
+    p = O.default_params(**kw)
+    db = O.DB(golden.db, p, golden.db_labels)
+    s = O.Searcher(db, p)
+    # a slice that covers every edge-case block of tools/make_golden.py (the tail) plus regular reads
+    idx = list(range(0, 300)) + list(range(2400, len(golden.q)))
+    want = {k: golden.lines(variant, k) for k in ("user", "uc", "b6")}
+    labels = [golden.q_labels[i] for i in idx]
+    seqs = [golden.q[i] for i in idx]
+    user, uc, b6 = util.oracle_lines(s, labels, seqs, golden.db_labels)
+    keep = set(labels)
+    for got, kind, col in ((user, "user", 0), (uc, "uc", 8), (b6, "b6", 0)):
+        ref = [l for l in want[kind] if l.split("\t")[col] in keep]
+        assert util.first_diff(got, ref) is None, kind
+
+
+def test_known_answer_compress_path():
+    assert O.compress_path("I" * 610 + "M" * 250 + "I" * 638) == "610I250M638I"
+    assert O.compress_path("I" * 847 + "M" * 12 + "D" + "M" * 238 + "I" * 408) == "847I12MD238M408I"
+
+
+def test_capi_library_exports_every_symbol():
+    from usearch12_b200 import capi
+    L = capi.lib()
+    for name in capi.SYMBOLS:
+        assert hasattr(L, name), name
+    # header and binding agree on the struct sizes
+    p = capi.default_params()
+    assert p.struct_size == C.sizeof(capi.Params)
+    assert capi.HIT_DTYPE.itemsize == 72 and capi.QSTAT_DTYPE.itemsize == 28
+
+
+def test_header_declares_bound_symbols():
+    import os
+    import re
+    hdr = open(os.path.join(util.ROOT, "include", "usb200.h")).read()
+    from usearch12_b200 import capi
+    declared = set(re.findall(r"\b(usb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+
+
+def test_no_gpu_fails_loudly():
+    from usearch12_b200 import capi
+    if capi.lib().usb_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(capi.UsbError):
+        capi.Index(["ACGTACGTACGTACGT"])
+
+
+def test_product_never_imports_oracle():
+    import os
+    for root, _, files in os.walk(os.path.join(util.ROOT, "usearch12_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, fn), errors="ignore").read()
+                assert "uso_" not in txt and "liboracle" not in txt, fn

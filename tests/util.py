@@ -1,0 +1,131 @@
+"""Test helpers: golden fixture access, FASTA reading, and the reference's output line formats
+(re-stated here only to compare product hits with the golden files; formats follow
+userout.cpp:150-215, blast6out.cpp:27-80, outputuc.cpp:19-69)."""
+import gzip
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+VARIANTS = {
+    "plus97": dict(id=0.97, strand_both=0),
+    "both97": dict(id=0.97, strand_both=1),
+    "plus90_ma4": dict(id=0.9, strand_both=0, maxaccepts=4, maxrejects=64),
+    "both80_ma0": dict(id=0.8, strand_both=1, maxaccepts=3, maxrejects=16),
+}
+
+
+def read_fasta(path):
+    op = gzip.open if path.endswith(".gz") else open
+    labels, seqs, cur = [], [], None
+    with op(path, "rt") as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                if cur is not None and cur[1]:
+                    labels.append(cur[0])
+                    seqs.append("".join(cur[1]))
+                cur = (line[1:], [])
+            elif cur is not None:
+                cur[1].append("".join(c for c in line if c.isalpha()))
+    if cur is not None and cur[1]:
+        labels.append(cur[0])
+        seqs.append("".join(cur[1]))
+    seqs = [s for s in seqs]
+    return labels, seqs
+
+
+class Golden:
+    def __init__(self):
+        self.db_labels, self.db = read_fasta(os.path.join(GOLDEN, "db.fa.gz"))
+        self.q_labels, self.q = read_fasta(os.path.join(GOLDEN, "q.fa.gz"))
+
+    def lines(self, variant, kind):
+        with gzip.open(os.path.join(GOLDEN, "%s.%s.gz" % (variant, kind)), "rt") as f:
+            return f.read().splitlines()
+
+
+def pct(ids, alnlen):
+    return 100.0 * (float(ids) / float(alnlen) if alnlen else 0.0)
+
+
+def fmt_user(h, cigar, ql, tl):
+    return "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
+        ql, tl, pct(h["ids"], h["alnlen"]), h["alnlen"], h["mism"], h["opens"], 1, h["ql"], 1, h["tl"], cigar,
+        "-" if h["strand"] else "+")
+
+
+def fmt_b6(h, ql, tl):
+    tlo, thi = (h["tl"], 1) if h["strand"] else (1, h["tl"])
+    return "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t*\t*" % (
+        ql, tl, pct(h["ids"], h["alnlen"]), h["alnlen"], h["mism"], h["opens"], 1, h["ql"], tlo, thi)
+
+
+def fmt_uc_hit(h, cigar, ql, tl):
+    return "H\t%d\t%d\t%.1f\t%s\t0\t0\t%s\t%s\t%s" % (
+        h["target"], h["ql"], pct(h["ids"], h["alnlen"]), "-" if h["strand"] else "+", cigar, ql, tl)
+
+
+def fmt_uc_nohit(qlen, ql):
+    return "N\t*\t%d\t*\t.\t*\t*\t*\t%s\t*" % (qlen, ql)
+
+
+def product_lines(res, q_labels, q_seqs, db_labels):
+    """usb200 Result -> (user, uc, b6) line lists in query input order."""
+    user, uc, b6 = [], [], []
+    for qi in range(len(q_seqs)):
+        b, e = int(res.qoff[qi]), int(res.qoff[qi + 1])
+        for k in range(b, e):
+            h = res.hits[k]
+            cig = res.cigar(h)
+            tl = db_labels[int(h["target"])]
+            user.append(fmt_user(h, cig, q_labels[qi], tl))
+            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl))
+            b6.append(fmt_b6(h, q_labels[qi], tl))
+        if b == e:
+            uc.append(fmt_uc_nohit(len(q_seqs[qi]), q_labels[qi]))
+    return user, uc, b6
+
+
+def oracle_lines(searcher, q_labels, q_seqs, db_labels):
+    from oracle import uso_py as O
+    user, uc, b6 = [], [], []
+    for qi, s in enumerate(q_seqs):
+        hits = searcher.search(s, qi)
+        for h in hits:
+            cig = O.compress_path(h["path"])
+            tl = db_labels[h["target"]]
+            user.append(fmt_user(h, cig, q_labels[qi], tl))
+            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl))
+            b6.append(fmt_b6(h, q_labels[qi], tl))
+        if not hits:
+            uc.append(fmt_uc_nohit(len(s), q_labels[qi]))
+    return user, uc, b6
+
+
+def first_diff(a, b):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            return "line %d:\n  got  %s\n  want %s" % (i, x, y)
+    if len(a) != len(b):
+        return "length %d vs %d" % (len(a), len(b))
+    return None
+
+
+def mutate(s, rate, rng, alphabet="ACGT"):
+    out = []
+    for c in s:
+        if rng.random() < rate:
+            k = rng.random()
+            if k < 0.1:
+                continue
+            elif k < 0.2:
+                out.append(c)
+                out.append(rng.choice(alphabet))
+            else:
+                out.append(rng.choice([x for x in alphabet if x != c]))
+        else:
+            out.append(c)
+    return "".join(out)

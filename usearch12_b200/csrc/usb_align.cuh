@@ -1,0 +1,1045 @@
+// usb_align.cuh -- kernel K2: per-(query,strand) candidate loop, one WARP per job.
+//
+// A warp walks its query's U-sorted candidates strictly in order, exactly like
+// UDBUsortedSearcher::SearchImpl (udbusortedsearcher.cpp:138-151) does, so Accepter/Terminator
+// semantics need no speculation; the parallelism inside one attempt is the 32 lanes, the
+// parallelism across queries is thousands of resident warps pulling jobs from a global cursor.
+//
+// Reference behaviour reproduced:
+//   a10 HSPFinder::SetA / SeqToWords            hspfinder.cpp:226-270,304-331
+//   a11 HSPFinder::UngappedBlast, IsGlobalHSP   ungappedblast.cpp:8-211, hspfinder.cpp:594-636
+//   a12 Chain + IsStaggered + HSP %id gate      chainer.cpp:352-500, hsp.h:102-126, getglobalhsps.cpp:22-60
+//   a9/a13 GlobalAlign_AllOpts, GetHole, AlignHSPMem   globalalignmem.cpp:25-236
+//   a14 ViterbiFastMainDiagMem / ViterbiFastBandMem   viterbifastbandmem.cpp:12-253, diagbox.h:150-171
+//   a15 TraceBackBitMem                          tracebackbitmem.cpp:8-73
+//   a17 AlignResult::FillLo statistics           arscorer.cpp:201-296
+//   a7  Accepter::IsAccept (-id) + Terminator    accepter.cpp:27-38, terminator.cpp:64-100
+//
+// Arithmetic: the reference DP is float with every default score a multiple of 0.5; here all
+// scores are doubled integers, which is exact.
+//
+// Lane mapping: seed search = one target word position per lane; DP = one band column per lane
+// with the horizontal-gap state resolved by a max-plus warp scan; path statistics = one
+// alignment column per lane with ballot/popc prefix counts.
+#pragma once
+#include "usb_dev.cuh"
+
+namespace usb {
+
+struct AlignArgs {
+	DevParams P;
+	const uint8_t *q;
+	const uint64_t *q_off;
+	uint32_t n_jobs, strands;
+	const uint32_t *cand_t;   // n_jobs * k_max, from k_rank
+	const uint32_t *n_emit;
+	uint32_t k_max;
+	const uint32_t *pair_q;   // pairs mode (usb_align_pairs) when non-null: job i = pair i
+	const uint32_t *pair_t;
+	const uint8_t *db_seq;    // 16-byte aligned targets
+	const uint64_t *db_off;
+	const uint32_t *db_len;
+	usb_hit *hits;
+	uint32_t hits_cap;
+	uint32_t *runs;
+	uint32_t runs_cap;
+	usb_qstat *qstat;         // per job
+	uint8_t *aligned;         // pairs mode
+	uint32_t *hsp_out;        // pairs mode, optional
+	uint32_t max_hsp;
+	uint8_t *slab;            // per-warp global workspace
+	uint64_t slab_stride;
+	uint32_t ql_cap, tl_cap;  // padded capacities of the per-warp sequence buffers
+	uint32_t hsp_cap;
+	uint32_t fast_bytes;      // per-warp bytes of the "fast" arrays
+	uint32_t fast_in_smem;    // 1: fast arrays in shared memory, 0: in the slab
+	DevCounters *ctr;
+};
+
+// Per-warp workspace.  "fast" arrays live in shared memory when they fit, else in the slab
+// (generic pointers: the code is the same).
+struct WarpWs {
+	uint8_t *A, *Ac;          // query letters (strand-adjusted) and their nt codes
+	uint8_t *B, *Bc;          // current target
+	uint8_t *cnt, *fil;       // seed table: words' occurrence counts (capped at 8), fill cursors
+	uint16_t *start, *pos;    // seed table CSR
+	int *Mrow, *Drow;         // DP rows; Mrow[-1] is addressable
+	// slab-only
+	uint8_t *TB;              // trace bytes, (LA+1) x (LB+1)
+	char *path, *rev;
+	HspRec *ung;
+	uint32_t *order, *prev, *chain;
+	int *cscore;
+	uint32_t LA, LB, nwordsA;
+};
+
+inline __host__ __device__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
+
+inline __host__ __device__ uint32_t align_fast_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_words)
+{
+	return 2 * ql_cap + 2 * tl_cap + 2 * pad16(hsp_words) + pad16(2 * hsp_words) + pad16(2 * ql_cap) +
+	  2 * pad16(4 * (tl_cap + 8));
+}
+
+inline __host__ __device__ uint64_t align_slab_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_cap)
+{
+	uint64_t tb = ((uint64_t)(ql_cap + 1) * (tl_cap + 1) + 15) & ~(uint64_t)15;
+	uint64_t path = pad16(ql_cap + tl_cap + 16);
+	return tb + 2 * path + (uint64_t)hsp_cap * (sizeof(HspRec) + 16);
+}
+
+__device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t *fast, uint8_t *slab)
+{
+	uint8_t *p = fast;
+	w.A = p; p += a.ql_cap;
+	w.Ac = p; p += a.ql_cap;
+	w.B = p; p += a.tl_cap;
+	w.Bc = p; p += a.tl_cap;
+	w.cnt = p; p += pad16(a.P.hsp_words);
+	w.fil = p; p += pad16(a.P.hsp_words);
+	w.start = (uint16_t *)p; p += pad16(2 * a.P.hsp_words);
+	w.pos = (uint16_t *)p; p += pad16(2 * a.ql_cap);
+	w.Mrow = (int *)p + 4; p += pad16(4 * (a.tl_cap + 8));
+	w.Drow = (int *)p; p += pad16(4 * (a.tl_cap + 8));
+	uint8_t *s = slab;
+	w.TB = s; s += ((uint64_t)(a.ql_cap + 1) * (a.tl_cap + 1) + 15) & ~(uint64_t)15;
+	w.path = (char *)s; s += pad16(a.ql_cap + a.tl_cap + 16);
+	w.rev = (char *)s; s += pad16(a.ql_cap + a.tl_cap + 16);
+	w.ung = (HspRec *)s; s += (uint64_t)a.hsp_cap * sizeof(HspRec);
+	w.order = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
+	w.prev = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
+	w.chain = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
+	w.cscore = (int *)s;
+}
+
+// ------------------------------------------------------------------ sequence staging
+__device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const uint8_t *Q, uint32_t L, uint32_t strand)
+{
+	const uint32_t lane = lane_id();
+	for (uint32_t i = lane; i < L; i += 32) {
+		uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
+		w.A[i] = (uint8_t)c;
+		w.Ac[i] = (uint8_t)nt_code(c);
+	}
+	w.LA = L;
+	__syncwarp();
+}
+
+__device__ __forceinline__ void load_target(const AlignArgs &a, WarpWs &w, uint32_t t)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t L = a.db_len[t];
+	const uint4 *src = (const uint4 *)(a.db_seq + a.db_off[t]);
+	uint4 *dB = (uint4 *)w.B, *dC = (uint4 *)w.Bc;
+	const uint32_t n16 = (L + 15) / 16;
+	for (uint32_t i = lane; i < n16; i += 32) {
+		uint4 v = __ldg(src + i);
+		uint32_t in[4] = {v.x, v.y, v.z, v.w}, out[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			uint32_t x = in[k];
+			out[k] = nt_code(x & 0xff) | (nt_code((x >> 8) & 0xff) << 8) | (nt_code((x >> 16) & 0xff) << 16) |
+			  (nt_code(x >> 24) << 24);
+		}
+		dB[i] = v;
+		dC[i] = make_uint4(out[0], out[1], out[2], out[3]);
+	}
+	w.LB = L;
+	__syncwarp();
+}
+
+// ------------------------------------------------------------------ a10: seed table of the query
+// HSP words treat wildcards as letter 0 and are never dropped (hspfinder.cpp:238-240).
+__device__ __forceinline__ uint32_t hsp_word_at(const uint8_t *codes, uint32_t p, uint32_t w)
+{
+	uint32_t word = 0;
+	for (uint32_t i = 0; i < w; ++i) {
+		uint32_t c = codes[p + i];
+		word = (word << 2) | (c & 4 ? 0u : c);
+	}
+	return word;
+}
+
+// Builds cnt[word] = min(8, occurrences) and, per word, the first 8 query positions in query
+// order (hspfinder.cpp:304-323), as a CSR (start, pos).  Query order inside a word is kept by
+// processing positions in chunks of 32 and ranking equal words inside a chunk with match_any.
+__device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t hw = a.P.hspw, HW = a.P.hsp_words;
+	uint32_t *cnt32 = (uint32_t *)w.cnt, *fil32 = (uint32_t *)w.fil;
+	for (uint32_t i = lane; i < HW / 4; i += 32) {
+		cnt32[i] = 0;
+		fil32[i] = 0;
+	}
+	const uint32_t nw = w.LA >= hw ? w.LA - hw + 1 : 0;
+	w.nwordsA = nw;
+	__syncwarp();
+	for (uint32_t base = 0; base < nw; base += 32) {
+		const uint32_t p = base + lane;
+		const bool valid = p < nw;
+		const uint32_t word = valid ? hsp_word_at(w.Ac, p, hw) : (0x80000000u | lane);
+		const uint32_t peers = __match_any_sync(USB_FULL, word);
+		if (valid && (peers & lanemask_lt()) == 0) {
+			uint32_t c = w.cnt[word] + __popc(peers);
+			w.cnt[word] = (uint8_t)min(c, 8u);
+		}
+		__syncwarp();
+	}
+	// exclusive scan of cnt -> start
+	{
+		const uint32_t per = HW / 32;
+		uint32_t sum = 0;
+		for (uint32_t i = 0; i < per; ++i)
+			sum += w.cnt[lane * per + i];
+		uint32_t inc = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t t = __shfl_up_sync(USB_FULL, inc, d);
+			if (lane >= (uint32_t)d)
+				inc += t;
+		}
+		uint32_t run = inc - sum;
+		for (uint32_t i = 0; i < per; ++i) {
+			w.start[lane * per + i] = (uint16_t)run;
+			run += w.cnt[lane * per + i];
+		}
+	}
+	__syncwarp();
+	for (uint32_t base = 0; base < nw; base += 32) {
+		const uint32_t p = base + lane;
+		const bool valid = p < nw;
+		const uint32_t word = valid ? hsp_word_at(w.Ac, p, hw) : (0x80000000u | lane);
+		const uint32_t peers = __match_any_sync(USB_FULL, word);
+		uint32_t before = 0;
+		if (valid)
+			before = w.fil[word];
+		__syncwarp();
+		if (valid) {
+			uint32_t slot = before + __popc(peers & lanemask_lt());
+			if (slot < 8)
+				w.pos[w.start[word] + slot] = (uint16_t)p;
+			if ((peers & lanemask_lt()) == 0)
+				w.fil[word] = (uint8_t)min(before + __popc(peers), 8u);
+		}
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------ a11: ungapped seeds + X-drop
+// hspfinder.cpp:594-636
+__device__ __forceinline__ bool is_global_hsp(uint32_t ALo, uint32_t BLo, uint32_t LA, uint32_t LB)
+{
+	const uint32_t AR = LA - ALo, BR = LB - BLo;
+	if (LA <= LB) {
+		const uint32_t MaxGap = LA / 4 + 1;
+		if (ALo > BLo && ALo - BLo > MaxGap)
+			return false;
+		if (AR > BR && AR - BR > MaxGap)
+			return false;
+	} else {
+		const uint32_t MaxGap = LB / 4 + 1;
+		if (BLo > ALo && BLo - ALo > MaxGap)
+			return false;
+		if (BR > AR && BR - AR > MaxGap)
+			return false;
+	}
+	return true;
+}
+
+// One lane extends one seed (ungappedblast.cpp:76-193): right from the seed's last letter, then
+// left from its first letter starting at the best right-extended score.  Scores are doubled.
+__device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
+  uint32_t MinLength, HspRec &out, uint32_t &Bhi_out)
+{
+	const DevParams &P = a.P;
+	const uint32_t LA = w.LA, LB = w.LB, hw = P.hspw;
+	const uint8_t *Ac = w.Ac, *Bc = w.Bc;
+	int score = 0;
+	for (uint32_t j = 0; j < hw; ++j)
+		score += subst2(P, Ac[APos + j], Bc[BPos + j]);
+	int best = score;
+	uint32_t bp = BPos + hw - 1, ap = APos + hw - 1, best_hi = bp;
+	for (;;) {
+		++bp;
+		if (bp >= LB)
+			break;
+		++ap;
+		if (ap >= LA)
+			break;
+		score += subst2(P, Ac[ap], Bc[bp]);
+		if (score > best) {
+			best = score;
+			best_hi = bp;
+		} else if ((float)(best - score) > P.xdrop2)
+			break;
+	}
+	bp = BPos;
+	ap = APos;
+	uint32_t best_lo = BPos;
+	score = best;
+	for (;;) {
+		if (bp == 0 || ap == 0)
+			break;
+		--bp;
+		--ap;
+		score += subst2(P, Ac[ap], Bc[bp]);
+		if (score > best) {
+			best = score;
+			best_lo = bp;
+		} else if ((float)(best - score) > P.xdrop2)
+			break;
+	}
+	const uint32_t Length = best_hi - best_lo + 1;
+	const uint32_t Alo = best_lo - (BPos - APos) /* same diagonal */;
+	if (Length < MinLength || (float)best < P.minscore2)
+		return false;
+	// Alo computed with wrap-around arithmetic is exact: the diagonal is fixed
+	if (!is_global_hsp(Alo, best_lo, LA, LB))
+		return false;
+	out.Loi = Alo;
+	out.Loj = best_lo;
+	out.Len = Length;
+	out.score2 = best;
+	Bhi_out = best_hi;
+	return true;
+}
+
+// Returns the number of ungapped HSPs written to w.ung (ungappedblast.cpp:45-210): target word
+// positions ascending; the first seed at a position that yields an acceptable HSP wins and the
+// scan jumps past that HSP.  32 positions are examined speculatively per step; the lowest lane
+// with an accepted HSP is the one the sequential scan would have reached first.
+__device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLength)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t hw = a.P.hspw;
+	const uint32_t LB = w.LB;
+	if (LB < 2 * hw)
+		return 0;
+	const uint32_t nwordsB = LB - hw + 1;
+	uint32_t nung = 0;
+	uint32_t base = 0;
+	while (base < nwordsB) {
+		const uint32_t bpos = base + lane;
+		uint32_t na = 0, word = 0;
+		if (bpos < nwordsB) {
+			word = hsp_word_at(w.Bc, bpos, hw);
+			na = w.cnt[word];
+		}
+		if (!__any_sync(USB_FULL, na != 0)) {
+			base += 32;
+			continue;
+		}
+		HspRec h;
+		uint32_t bhi = 0;
+		bool ok = false;
+		const uint32_t st = na ? w.start[word] : 0;
+		for (uint32_t i = 0; i < na && !ok; ++i)
+			ok = extend_seed(a, w, w.pos[st + i], bpos, MinLength, h, bhi);
+		const uint32_t okmask = __ballot_sync(USB_FULL, ok);
+		if (okmask == 0) {
+			base += 32;
+			continue;
+		}
+		const int src = __ffs(okmask) - 1;
+		h.Loi = __shfl_sync(USB_FULL, h.Loi, src);
+		h.Loj = __shfl_sync(USB_FULL, h.Loj, src);
+		h.Len = __shfl_sync(USB_FULL, h.Len, src);
+		h.score2 = __shfl_sync(USB_FULL, h.score2, src);
+		bhi = __shfl_sync(USB_FULL, bhi, src);
+		if (nung < a.hsp_cap) {
+			if (lane == 0)
+				w.ung[nung] = h;
+		} else if (lane == 0)
+			atomicOr(&a.ctr->err, ERR_HSP_FULL);
+		if (nung < a.hsp_cap)
+			++nung;
+		base = bhi + 1;
+	}
+	__syncwarp();
+	return nung;
+}
+
+// ------------------------------------------------------------------ a12: chaining
+// hsp.h:102-126 (three of the four terminal-gap terms are clamped, as in the reference)
+__device__ __forceinline__ bool is_staggered(const HspRec &h, uint32_t LA, uint32_t LB)
+{
+	int Hii = (int)(h.Loi + h.Len - 1), Hij = (int)(h.Loj + h.Len - 1);
+	int gla = (int)h.Loi - (int)h.Loj;
+	int glb = (int)h.Loj - (int)h.Loi;
+	int gra = ((int)LA - Hii - 1) - ((int)LB - Hij - 1);
+	int grb = ((int)LB - Hij - 1) - ((int)LA - Hii - 1);
+	if (gla < 0) gla = 0;
+	if (glb < 0) glb = 0;
+	if (grb < 0) grb = 0;
+	int GapA = gla + gra, GapB = glb + grb;
+	if (GapA == 0 || GapB == 0)
+		return false;
+	double r = LA < LB ? (double)GapA / (double)LA : (double)GapB / (double)LB;
+	return r > 0.5;
+}
+
+// Best colinear chain (chainer.cpp:352-500; the "dominated chain" pruning there never fires, so
+// this is the plain O(K^2) recurrence over HSPs ordered by query start, stable).  K is small
+// (mean 2.9): lane 0 does it.  Returns the chain length; indices into w.ung in w.chain.
+__device__ uint32_t chain_hsps(const AlignArgs &a, WarpWs &w, uint32_t n)
+{
+	uint32_t len = 0;
+	if (lane_id() == 0 && n > 0) {
+		const HspRec *H = w.ung;
+		uint32_t *order = w.order, *prev = w.prev;
+		int *cs = w.cscore;
+		for (uint32_t i = 0; i < n; ++i) {
+			uint32_t j = i;
+			const uint32_t key = H[i].Loi;
+			while (j > 0 && H[order[j - 1]].Loi > key) {
+				order[j] = order[j - 1];
+				--j;
+			}
+			order[j] = i;
+		}
+		for (uint32_t oi = 0; oi < n; ++oi) {
+			const uint32_t k = order[oi];
+			const HspRec h = H[k];
+			int best = 0;
+			uint32_t bestc = 0xffffffffu;
+			for (uint32_t oj = 0; oj < oi; ++oj) {
+				const uint32_t c = order[oj];
+				const HspRec g = H[c];
+				if (g.Loi + g.Len - 1 < h.Loi && g.Loj + g.Len - 1 < h.Loj && (bestc == 0xffffffffu || cs[c] > best)) {
+					bestc = c;
+					best = cs[c];
+				}
+			}
+			prev[k] = bestc;
+			cs[k] = bestc == 0xffffffffu ? h.score2 : cs[bestc] + h.score2;
+		}
+		uint32_t opt = 0;
+		for (uint32_t k = 1; k < n; ++k)
+			if (cs[k] > cs[opt])
+				opt = k;
+		for (uint32_t k = opt; k != 0xffffffffu; k = prev[k])
+			++len;
+		uint32_t i = len;
+		for (uint32_t k = opt; k != 0xffffffffu; k = prev[k])
+			w.chain[--i] = k;
+		for (uint32_t c = 0; c < len; ++c) // hspfinder.cpp:537-553
+			if (is_staggered(H[w.chain[c]], w.LA, w.LB)) {
+				len = 0;
+				break;
+			}
+	}
+	len = __shfl_sync(USB_FULL, len, 0);
+	__syncwarp();
+	return len;
+}
+
+// ------------------------------------------------------------------ a14/a15: banded Viterbi
+struct GapCosts { // doubled; "L"/"R" = left/right terminal variants (alnparams.cpp:100-152)
+	int OpenA, ExtA, OpenB, ExtB, LOpenA, LExtA, LOpenB, LExtB, ROpenA, RExtA, ROpenB, RExtB;
+};
+
+__device__ __forceinline__ GapCosts hole_costs(const DevParams &P, bool leftA, bool leftB, bool rightA, bool rightB)
+{
+	GapCosts g;
+	g.OpenA = g.OpenB = P.open2;
+	g.ExtA = g.ExtB = P.ext2;
+	g.LOpenA = leftA ? P.topen2 : P.open2;   g.LExtA = leftA ? P.text2 : P.ext2;
+	g.LOpenB = leftB ? P.topen2 : P.open2;   g.LExtB = leftB ? P.text2 : P.ext2;
+	g.ROpenA = rightA ? P.topen2 : P.open2;  g.RExtA = rightA ? P.text2 : P.ext2;
+	g.ROpenB = rightB ? P.topen2 : P.open2;  g.RExtB = rightB ? P.text2 : P.ext2;
+	return g;
+}
+
+// diagbox.h:150-171
+__device__ __forceinline__ void band_range(uint32_t LA, uint32_t LB, uint32_t dlo, uint32_t dhi, uint32_t i,
+  uint32_t &sj, uint32_t &ej)
+{
+	sj = (dlo + i >= LA) ? dlo + i - LA : 0;
+	if (sj >= LB)
+		sj = LB - 1;
+	ej = (dhi + i + 1 >= LA) ? dhi + i + 1 - LA : 0;
+	if (ej > LB)
+		ej = LB;
+}
+
+// max-plus inclusive warp scan: R[l] = max_{k<=l} (v[k] + (l-k)*ext)
+__device__ __forceinline__ int scan_gap(int v, int ext)
+{
+	const uint32_t lane = lane_id();
+	int R = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		int t = __shfl_up_sync(USB_FULL, R, d);
+		if (lane >= (uint32_t)d)
+			R = max(R, t + d * ext);
+	}
+	return R;
+}
+
+// Global alignment of Ac[0..LA) x Bc[0..LB) restricted to the main-diagonal band
+// (viterbifastbandmem.cpp:232-253), LA, LB >= 1.  Appends the path at out[0..) and returns its
+// length; *score2 receives the doubled score.  Rows are swept in order; within a row each lane
+// owns one column: M and D depend only on the previous row, the I state is a prefix max-plus scan.
+__device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *Ac, uint32_t LA, const uint8_t *Bc,
+  uint32_t LB, const GapCosts &G, char *out, int *score2, uint32_t *cells)
+{
+	const uint32_t lane = lane_id();
+	const DevParams &P = a.P;
+	uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
+	dlo = dlo > P.band ? dlo - P.band : 1;
+	dhi += P.band;
+	dhi = min(dhi, LA + LB - 1);
+	const uint64_t W = (uint64_t)LB + 1;
+	int *Mrow = w.Mrow, *Drow = w.Drow;
+	uint8_t *TB = w.TB;
+	for (uint32_t j = lane; j <= LB + 1; j += 32) {
+		Mrow[(int)j - 1] = USB_NEG;
+		if (j <= LB)
+			Drow[j] = USB_NEG;
+	}
+	__syncwarp();
+	int OpenA = G.LOpenA, ExtA = G.LExtA;
+	uint32_t ncell = 0;
+	for (uint32_t i = 0; i < LA; ++i) {
+		uint32_t sj, ej;
+		band_range(LA, LB, dlo, dhi, i, sj, ej);
+		if (ej == 0)
+			continue;
+		ncell += ej - sj;
+		const uint32_t ca = Ac[i];
+		uint8_t *TBrow = TB + (uint64_t)i * W;
+		int Mcarry = (i == 0) ? 0 : (sj == 0 ? USB_NEG : Mrow[(int)sj - 1]);
+		if (sj > 0 && lane == 0)
+			TBrow[sj - 1] = TB_IM;
+		int Icarry = USB_NEG;
+		int lastMold = Mcarry;
+		for (uint32_t base = sj; base < ej; base += 32) {
+			const uint32_t j = base + lane;
+			const bool act = j < ej;
+			const int mold = act ? Mrow[j] : USB_NEG;
+			const int dold = act ? Drow[j] : USB_NEG;
+			int saved = __shfl_up_sync(USB_FULL, mold, 1);
+			if (lane == 0)
+				saved = Mcarry;
+			// I state: I(j+1) = max(saved(j) + OpenA, I(j) + ExtA)
+			const int g = saved + OpenA;
+			const int R = scan_gap(g, ExtA);
+			const int Iincl = max(R, Icarry + (int)(lane + 1) * ExtA);
+			int Iexcl = __shfl_up_sync(USB_FULL, Iincl, 1);
+			if (lane == 0)
+				Iexcl = Icarry;
+			uint32_t bits = 0;
+			int xM = saved;
+			if (dold > xM) {
+				xM = dold;
+				bits = TB_DM;
+			}
+			if (Iexcl > xM) {
+				xM = Iexcl;
+				bits = TB_IM;
+			}
+			const int mnew = xM + (act ? subst2(P, ca, Bc[j]) : 0);
+			const int ob = (j == 0) ? G.LOpenB : G.OpenB, eb = (j == 0) ? G.LExtB : G.ExtB;
+			const int md = saved + ob;
+			int dnew = dold + eb;
+			if (md >= dnew) {
+				dnew = md;
+				bits |= TB_MD;
+			}
+			if (g >= Iexcl + ExtA)
+				bits |= TB_MI;
+			const uint32_t last_lane = min(31u, ej - 1 - base);
+			lastMold = __shfl_sync(USB_FULL, mold, last_lane);
+			Mcarry = __shfl_sync(USB_FULL, mold, 31);
+			Icarry = __shfl_sync(USB_FULL, Iincl, 31);
+			if (act) {
+				Mrow[j] = mnew;
+				Drow[j] = dnew;
+				TBrow[j] = (uint8_t)bits;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) { // right-edge column, every row (viterbifastbandmem.cpp:165-179)
+			uint32_t tb = 0;
+			const int md = lastMold + G.ROpenB;
+			int d = Drow[LB] + G.RExtB;
+			if (md >= d) {
+				d = md;
+				tb = TB_MD;
+			}
+			Drow[LB] = d;
+			TBrow[LB] = (uint8_t)tb;
+		}
+		__syncwarp();
+		OpenA = G.OpenA;
+		ExtA = G.ExtA;
+	}
+	// bottom row: horizontal gaps after the last query letter (:186-206), strict '>'
+	uint32_t sj, ej;
+	band_range(LA, LB, dlo, dhi, LA - 1, sj, ej);
+	int FinalI = USB_NEG;
+	{
+		uint8_t *TBrow = TB + (uint64_t)LA * W;
+		if (lane == 0)
+			Mrow[(int)sj - 1] = USB_NEG;
+		__syncwarp();
+		int Icarry = USB_NEG;
+		for (uint32_t base = sj; base < ej; base += 32) {
+			const uint32_t j = base + lane;
+			const bool act = j < ej;
+			const int g = (act ? Mrow[(int)j - 1] : USB_NEG) + G.ROpenA;
+			const int R = scan_gap(g, G.RExtA);
+			const int Iincl = max(R, Icarry + (int)(lane + 1) * G.RExtA);
+			int Iexcl = __shfl_up_sync(USB_FULL, Iincl, 1);
+			if (lane == 0)
+				Iexcl = Icarry;
+			if (act)
+				TBrow[j] = (g > Iexcl + G.RExtA) ? TB_MI : 0;
+			const uint32_t last_lane = min(31u, ej - 1 - base);
+			FinalI = __shfl_sync(USB_FULL, Iincl, last_lane);
+			Icarry = __shfl_sync(USB_FULL, Iincl, 31);
+		}
+	}
+	__syncwarp();
+	const int FinalM = Mrow[(int)LB - 1], FinalD = Drow[LB];
+	int Score = FinalM;
+	char State = 'M';
+	if (FinalD > Score) {
+		Score = FinalD;
+		State = 'D';
+	}
+	if (FinalI > Score) {
+		Score = FinalI;
+		State = 'I';
+	}
+	if (score2)
+		*score2 = Score;
+	if (cells)
+		*cells += ncell;
+
+	// traceback (tracebackbitmem.cpp:8-73), lane 0, reversed into w.rev
+	uint32_t n = 0;
+	if (lane == 0) {
+		uint32_t i = LA, j = LB;
+		char *rev = w.rev;
+		const uint32_t limit = LA + LB;
+		while ((i != 0 || j != 0) && n < limit) {
+			rev[n++] = State;
+			if (State == 'M') {
+				if (i == 0 || j == 0) {
+					atomicOr(&a.ctr->err, ERR_TRACE);
+					break;
+				}
+				const uint32_t t = TB[(uint64_t)(i - 1) * W + (j - 1)];
+				State = (t & TB_DM) ? 'D' : (t & TB_IM) ? 'I' : 'M';
+				--i;
+				--j;
+			} else if (State == 'D') {
+				if (i == 0) {
+					atomicOr(&a.ctr->err, ERR_TRACE);
+					break;
+				}
+				const uint32_t t = TB[(uint64_t)(i - 1) * W + j];
+				State = (t & TB_MD) ? 'M' : 'D';
+				--i;
+			} else {
+				if (j == 0) {
+					atomicOr(&a.ctr->err, ERR_TRACE);
+					break;
+				}
+				const uint32_t t = TB[(uint64_t)i * W + (j - 1)];
+				State = (t & TB_MI) ? 'M' : 'I';
+				--j;
+			}
+		}
+		if (i != 0 || j != 0)
+			atomicOr(&a.ctr->err, ERR_TRACE);
+	}
+	n = __shfl_sync(USB_FULL, n, 0);
+	__syncwarp();
+	for (uint32_t k = lane; k < n; k += 32)
+		out[k] = w.rev[n - 1 - k];
+	__syncwarp();
+	return n;
+}
+
+// ------------------------------------------------------------------ a9/a13: whole pair
+__device__ __forceinline__ uint32_t fill_run(char *out, char c, uint32_t n)
+{
+	for (uint32_t k = lane_id(); k < n; k += 32)
+		out[k] = c;
+	return n;
+}
+
+// globalalignmem.cpp:70-112 AlignHSPMem
+__device__ uint32_t align_hole(const AlignArgs &a, WarpWs &w, uint32_t Loi, uint32_t Loj, uint32_t Leni, uint32_t Lenj,
+  char *out, usb_qstat &st)
+{
+	if (Leni == 0)
+		return fill_run(out, 'I', Lenj);
+	if (Lenj == 0)
+		return fill_run(out, 'D', Leni);
+	const GapCosts G = hole_costs(a.P, Loi == 0, Loj == 0, Loi + Leni == w.LA, Loj + Lenj == w.LB);
+	++st.n_dp;
+	return viterbi_band(a, w, w.Ac + Loi, Leni, w.Bc + Loj, Lenj, G, out, nullptr, &st.dp_cells);
+}
+
+// GlobalAlign_AllOpts (globalalignmem.cpp:129-236).  Returns path length, 0 = rejected (no AR).
+// The seed table of the query must be current.
+__device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, uint32_t *n_chain_out)
+{
+	const DevParams &P = a.P;
+	const uint32_t lane = lane_id();
+	const uint32_t LA = w.LA, LB = w.LB;
+	uint32_t MinHSPLength = P.min_hsp_len == 0 ? 32 : P.min_hsp_len;
+	MinHSPLength = min(MinHSPLength, LA / 4);
+	MinHSPLength = max(MinHSPLength, 16u);
+	const uint32_t nung = ungapped_blast(a, w, MinHSPLength);
+	const uint32_t nchain = chain_hsps(a, w, nung);
+	if (n_chain_out)
+		*n_chain_out = nchain;
+	// HSP identity gate (getglobalhsps.cpp:22-60, globalalignmem.cpp:171)
+	uint32_t TotalLength = 0, TotalSame = 0;
+	for (uint32_t c = 0; c < nchain; ++c) {
+		const HspRec h = w.ung[w.chain[c]];
+		TotalLength += h.Len;
+		for (uint32_t base = 0; base < h.Len; base += 32) {
+			const uint32_t k = base + lane;
+			bool same = false;
+			if (k < h.Len)
+				same = chars_match_dev(w.A[h.Loi + k], w.B[h.Loj + k], w.Ac[h.Loi + k], w.Bc[h.Loj + k]);
+			TotalSame += __popc(__ballot_sync(USB_FULL, same));
+		}
+	}
+	const float HSPFractId = TotalLength == 0 ? 0.0f : (float)TotalSame / (float)TotalLength;
+	if (HSPFractId < P.min_hsp_fract_id)
+		return 0;
+	char *path = w.path;
+	uint32_t n = 0;
+	if (nchain == 0) {
+		if (P.min_hsp_len > 0 && LA > 64)
+			return 0;
+		if (LA == 0 || LB == 0)
+			return 0;
+		const GapCosts G = hole_costs(P, true, true, true, true);
+		++st.n_dp;
+		return viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, path, nullptr, &st.dp_cells);
+	}
+	uint32_t Loi = 0, Loj = 0;
+	for (uint32_t c = 0; c < nchain; ++c) {
+		const HspRec h = w.ung[w.chain[c]];
+		n += align_hole(a, w, Loi, Loj, h.Loi - Loi, h.Loj - Loj, path + n, st);
+		n += fill_run(path + n, 'M', h.Len);
+		Loi = h.Loi + h.Len;
+		Loj = h.Loj + h.Len;
+	}
+	n += align_hole(a, w, Loi, Loj, LA - Loi, LB - Loj, path + n, st);
+	__syncwarp();
+	return n;
+}
+
+// ------------------------------------------------------------------ a17: statistics + hit record
+// arscorer.cpp:201-296 FillLo over the path between the first and last M column.
+__device__ bool path_stats(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_hit &h)
+{
+	const uint32_t lane = lane_id();
+	const char *path = w.path;
+	uint32_t first = 0xffffffffu, last = 0, qpos = 0, tpos = 0;
+	// first M column and the letters consumed before it
+	for (uint32_t base = 0; base < n && first == 0xffffffffu; base += 32) {
+		const uint32_t c = base + lane;
+		const char ch = c < n ? path[c] : 0;
+		const uint32_t mm = __ballot_sync(USB_FULL, ch == 'M');
+		const uint32_t dm = __ballot_sync(USB_FULL, ch == 'D');
+		const uint32_t im = __ballot_sync(USB_FULL, ch == 'I');
+		if (mm) {
+			const uint32_t f = __ffs(mm) - 1;
+			first = base + f;
+			qpos += __popc(dm & ((1u << f) - 1));
+			tpos += __popc(im & ((1u << f) - 1));
+		} else {
+			qpos += __popc(dm);
+			tpos += __popc(im);
+		}
+	}
+	if (first == 0xffffffffu)
+		return false;
+	for (uint32_t base = (n - 1) & ~31u;; base -= 32) {
+		const uint32_t c = base + lane;
+		const char ch = c < n ? path[c] : 0;
+		const uint32_t mm = __ballot_sync(USB_FULL, ch == 'M');
+		if (mm) {
+			last = base + 31 - __clz(mm);
+			break;
+		}
+		if (base == 0)
+			break;
+	}
+	h.first_mq = qpos;
+	h.first_mt = tpos;
+	h.first_mcol = first;
+	h.alnlen = last - first + 1;
+	uint32_t ids = 0, mism = 0, gaps = 0, opens = 0;
+	uint32_t prev_carry = 'M';
+	for (uint32_t base = first; base <= last; base += 32) {
+		const uint32_t c = base + lane;
+		const bool in = c <= last;
+		const uint32_t ch = in ? (uint32_t)path[c] : 0u;
+		const bool isM = ch == 'M', isD = ch == 'D', isI = ch == 'I';
+		const uint32_t qm = __ballot_sync(USB_FULL, isM || isD);
+		const uint32_t tm = __ballot_sync(USB_FULL, isM || isI);
+		const uint32_t qp = qpos + __popc(qm & lanemask_lt());
+		const uint32_t tp = tpos + __popc(tm & lanemask_lt());
+		bool same = false;
+		if (isM)
+			same = chars_match_dev(w.A[qp], w.B[tp], w.Ac[qp], w.Bc[tp]);
+		uint32_t prev = __shfl_up_sync(USB_FULL, ch, 1);
+		if (lane == 0)
+			prev = prev_carry;
+		ids += __popc(__ballot_sync(USB_FULL, same));
+		mism += __popc(__ballot_sync(USB_FULL, isM && !same));
+		gaps += __popc(__ballot_sync(USB_FULL, isD || isI));
+		opens += __popc(__ballot_sync(USB_FULL, (isD || isI) && prev == 'M'));
+		prev_carry = __shfl_sync(USB_FULL, ch, 31);
+		qpos += __popc(qm);
+		tpos += __popc(tm);
+	}
+	h.ids = ids;
+	h.mism = mism;
+	h.intgaps = gaps;
+	h.opens = opens;
+	h.last_mq = qpos - 1;
+	h.last_mt = tpos - 1;
+	return true;
+}
+
+// Appends the path as runs (length << 2 | op) to the run arena; returns false when full.
+__device__ bool emit_runs(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_hit &h)
+{
+	const uint32_t lane = lane_id();
+	const char *path = w.path;
+	uint32_t nruns = 0;
+	uint32_t carry = 0;
+	for (uint32_t base = 0; base < n; base += 32) {
+		const uint32_t c = base + lane;
+		const uint32_t ch = c < n ? (uint32_t)path[c] : 0u;
+		uint32_t prev = __shfl_up_sync(USB_FULL, ch, 1);
+		if (lane == 0)
+			prev = carry;
+		nruns += __popc(__ballot_sync(USB_FULL, c < n && ch != prev));
+		carry = __shfl_sync(USB_FULL, ch, 31);
+	}
+	uint32_t off = 0;
+	if (lane == 0)
+		off = atomicAdd(&a.ctr->n_runs, nruns);
+	off = __shfl_sync(USB_FULL, off, 0);
+	if ((uint64_t)off + nruns > a.runs_cap) {
+		if (lane == 0)
+			atomicOr(&a.ctr->err, ERR_RUNS_FULL);
+		return false;
+	}
+	uint32_t *runs = a.runs + off;
+	uint32_t k = 0;
+	carry = 0;
+	for (uint32_t base = 0; base < n; base += 32) {
+		const uint32_t c = base + lane;
+		const uint32_t ch = c < n ? (uint32_t)path[c] : 0u;
+		uint32_t prev = __shfl_up_sync(USB_FULL, ch, 1);
+		if (lane == 0)
+			prev = carry;
+		const bool startrun = c < n && ch != prev;
+		const uint32_t sm = __ballot_sync(USB_FULL, startrun);
+		if (startrun) {
+			const uint32_t op = ch == 'M' ? 0u : ch == 'D' ? 1u : 2u;
+			runs[k + __popc(sm & lanemask_lt())] = (c << 2) | op; // start column for now
+		}
+		k += __popc(sm);
+		carry = __shfl_sync(USB_FULL, ch, 31);
+	}
+	__syncwarp();
+	// start columns -> lengths
+	for (uint32_t base = 0; base < nruns; base += 32) {
+		const uint32_t r = base + lane;
+		uint32_t v = 0, nxt = 0;
+		if (r < nruns) {
+			v = runs[r];
+			nxt = (r + 1 < nruns) ? (runs[r + 1] >> 2) : n;
+		}
+		__syncwarp();
+		if (r < nruns)
+			runs[r] = ((nxt - (v >> 2)) << 2) | (v & 3);
+		__syncwarp();
+	}
+	h.run_off = off;
+	h.run_cnt = nruns;
+	return true;
+}
+
+// ------------------------------------------------------------------ the job loop
+__device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
+{
+	const uint32_t lane = lane_id();
+	const bool pairs = a.pair_q != nullptr;
+	const uint32_t qi = pairs ? a.pair_q[job] : job / a.strands;
+	const uint32_t strand = pairs ? 0u : job % a.strands;
+	const uint32_t ncand = pairs ? 1u : a.n_emit[job];
+	usb_qstat st;
+	st.n_cand = 0; st.n_tried = 0; st.n_hspfail = 0; st.n_dp = 0; st.dp_cells = 0; st.n_accept = 0; st.seq_bytes = 0;
+	if (ncand != 0) {
+		const uint64_t q0 = a.q_off[qi];
+		const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
+		load_query(a, w, a.q + q0, L, strand);
+		build_seed_table(a, w);
+		uint32_t acc = 0, rej = 0;
+		for (uint32_t k = 0; k < ncand; ++k) {
+			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			load_target(a, w, t);
+			++st.n_tried;
+			st.seq_bytes += w.LA + w.LB;
+			uint32_t nchain = 0;
+			const uint32_t n = global_align(a, w, st, &nchain);
+			if (pairs && a.hsp_out) {
+				uint32_t *ho = a.hsp_out + (uint64_t)job * (1 + 4 * a.max_hsp);
+				if (lane == 0) {
+					ho[0] = nchain;
+					for (uint32_t c = 0; c < nchain && c < a.max_hsp; ++c) {
+						const HspRec h = w.ung[w.chain[c]];
+						ho[1 + 4 * c] = h.Loi;
+						ho[2 + 4 * c] = h.Loj;
+						ho[3 + 4 * c] = h.Len;
+						ho[4 + 4 * c] = (uint32_t)h.score2;
+					}
+				}
+			}
+			bool accept = false;
+			if (n == 0)
+				++st.n_hspfail;
+			else {
+				usb_hit h;
+				h.query = qi; h.target = t; h.strand = strand; h.rank = pairs ? job : k;
+				h.ql = w.LA; h.tl = w.LB; h.run_off = 0; h.run_cnt = 0;
+				if (!path_stats(a, w, n, h)) {
+					if (lane == 0)
+						atomicOr(&a.ctr->err, ERR_NO_M);
+				} else {
+					// accepter.cpp:27-38: reject iff double(ids)/double(cols) < (double)(float)id
+					const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
+					accept = pairs || !(fid < a.P.id_d);
+					if (accept) {
+						if (emit_runs(a, w, n, h)) {
+							uint32_t slot = 0;
+							if (lane == 0)
+								slot = atomicAdd(&a.ctr->n_hits, 1u);
+							slot = __shfl_sync(USB_FULL, slot, 0);
+							if (slot < a.hits_cap) {
+								if (lane == 0)
+									a.hits[slot] = h;
+							} else if (lane == 0)
+								atomicOr(&a.ctr->err, ERR_HITS_FULL);
+						}
+						++st.n_accept;
+					}
+				}
+			}
+			if (pairs) {
+				if (lane == 0)
+					a.aligned[job] = n != 0;
+				break;
+			}
+			// terminator.cpp:64-100
+			if (accept)
+				++acc;
+			else
+				++rej;
+			if (a.P.maxaccepts > 0 && acc == a.P.maxaccepts)
+				break;
+			if (a.P.maxrejects > 0 && rej == a.P.maxrejects)
+				break;
+		}
+	}
+	if (lane == 0 && a.qstat) {
+		usb_qstat *o = a.qstat + job;
+		*o = st; // n_cand is filled in by the host from k_rank's output
+	}
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 1) k_align(const AlignArgs a)
+{
+	extern __shared__ __align__(16) uint8_t align_smem[];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t gw = blockIdx.x * WPB + warp;
+	uint8_t *slab = a.slab + (uint64_t)gw * a.slab_stride;
+	uint8_t *fast = a.fast_in_smem ? align_smem + (size_t)warp * a.fast_bytes : slab;
+	if (!a.fast_in_smem)
+		slab += a.fast_bytes;
+	WarpWs w;
+	ws_setup(a, w, fast, slab);
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0)
+			job = atomicAdd(&a.ctr->job, 1u);
+		job = __shfl_sync(USB_FULL, job, 0);
+		if (job >= a.n_jobs)
+			break;
+		align_job(a, w, job);
+	}
+}
+
+// ------------------------------------------------------------------ stage kernel: Viterbi only
+struct ViterbiArgs {
+	AlignArgs base;          // P, slab, caps, ctr
+	const uint8_t *a_seq; const uint64_t *a_off;
+	const uint8_t *b_seq; const uint64_t *b_off;
+	const uint8_t *flags;
+	uint32_t n;
+	char *paths; const uint64_t *path_off;
+	int *score2;
+};
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 1) k_viterbi(const ViterbiArgs v)
+{
+	extern __shared__ __align__(16) uint8_t align_smem[];
+	const AlignArgs &a = v.base;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t gw = blockIdx.x * WPB + warp;
+	uint8_t *slab = a.slab + (uint64_t)gw * a.slab_stride;
+	uint8_t *fast = a.fast_in_smem ? align_smem + (size_t)warp * a.fast_bytes : slab;
+	if (!a.fast_in_smem)
+		slab += a.fast_bytes;
+	WarpWs w;
+	ws_setup(a, w, fast, slab);
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0)
+			job = atomicAdd(&a.ctr->job, 1u);
+		job = __shfl_sync(USB_FULL, job, 0);
+		if (job >= v.n)
+			break;
+		const uint32_t LA = (uint32_t)(v.a_off[job + 1] - v.a_off[job]);
+		const uint32_t LB = (uint32_t)(v.b_off[job + 1] - v.b_off[job]);
+		const uint8_t *A = v.a_seq + v.a_off[job], *B = v.b_seq + v.b_off[job];
+		for (uint32_t i = lane; i < LA; i += 32)
+			w.Ac[i] = (uint8_t)nt_code(A[i]);
+		for (uint32_t i = lane; i < LB; i += 32)
+			w.Bc[i] = (uint8_t)nt_code(B[i]);
+		w.LA = LA;
+		w.LB = LB;
+		__syncwarp();
+		const uint32_t f = v.flags[job];
+		const GapCosts G = hole_costs(a.P, f & 1, f & 2, f & 4, f & 8);
+		char *out = v.paths + v.path_off[job];
+		int sc = 0;
+		uint32_t cells = 0;
+		const uint32_t n = viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, out, &sc, &cells);
+		if (lane == 0) {
+			out[n] = 0;
+			v.score2[job] = sc;
+		}
+		__syncwarp();
+	}
+}
+
+} // namespace usb

@@ -1,0 +1,955 @@
+// usb_api.cu -- C ABI (include/usb200.h) over the CUDA kernels.  No CPU fallback: every compute
+// entry point needs a CUDA device and fails with USB_ECUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "usb_align.cuh"
+#include "usb_hostindex.h"
+#include "usb_rank.cuh"
+
+using namespace usb;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                     \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(USB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+extern "C" const char *usb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int usb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" void usb_default_params(usb_params *p, int cluster_fast)
+{
+	memset(p, 0, sizeof *p);
+	p->struct_size = sizeof(usb_params);
+	p->is_nucleo = 1;
+	p->id = 0.97f;
+	p->maxaccepts = 1;
+	p->maxrejects = cluster_fast ? 8 : 32;
+	p->strand_both = 0;
+	p->word_length = 8;
+	p->big = 100000;
+	p->bump = 50;
+	p->stepwords = 8;
+	p->band = 16;
+	p->minhsp = 16;
+	p->hspw = 5;
+	p->xdrop_nw = 8.0f;
+	p->match = 1.0f;
+	p->mismatch = -2.0f;
+	p->gap_open = -10.0f;
+	p->gap_ext = -1.0f;
+	p->term_gap_open = -0.5f;
+	p->term_gap_ext = -0.5f;
+	p->dbmask = cluster_fast ? 0 : 1;
+	p->cluster_mode = cluster_fast;
+}
+
+// ------------------------------------------------------------------ objects
+template <class T> struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return fail(USB_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+		}
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct usb_index {
+	int device = 0;
+	usb_params P;
+	HostIndex H;
+	DevBuf<uint8_t> d_seqs;
+	DevBuf<uint64_t> d_seq_off, d_row_off;
+	DevBuf<uint32_t> d_seq_len, d_postings;
+};
+
+struct usb_result {
+	std::vector<usb_hit> hits;
+	std::vector<uint32_t> runs;
+	std::vector<uint64_t> qoff;
+	std::vector<usb_qstat> qstat;
+};
+
+struct usb_searcher {
+	usb_index *ix = nullptr;
+	usb_params P;
+	DevParams D;
+	int num_sms = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	uint64_t launches = 0;
+	// current batch
+	uint32_t n_q = 0, n_jobs = 0, strands = 1, k_max = 0, max_ql = 0;
+	bool ran = false;
+	uint32_t last_hits = 0, last_runs = 0;
+	uint64_t last_postings = 0;
+	DevBuf<uint8_t> d_q;
+	DevBuf<uint64_t> d_qoff;
+	DevBuf<uint32_t> d_cand_t, d_cand_u, d_ncand, d_nemit, d_runs, d_uout;
+	DevBuf<usb_hit> d_hits;
+	DevBuf<usb_qstat> d_qstat;
+	DevBuf<DevCounters> d_ctr;
+	DevBuf<uint8_t> d_slab;
+	size_t rank_smem_set = 0;
+};
+
+static bool is_int2(float x) { return std::floor(2.0 * (double)x) == 2.0 * (double)x; }
+
+// Validates the option snapshot and derives the device constants (alnheuristics.cpp:26-69).
+static int make_dev_params(const usb_params *p, DevParams &D)
+{
+	if (!p || p->struct_size != sizeof(usb_params))
+		return fail(USB_EINVAL, "usb_params.struct_size mismatch (header/library version skew)");
+	if (!p->is_nucleo)
+		return fail(USB_EINVAL, "amino-acid databases (usearch_local row) are not built yet");
+	if (p->word_length < 2 || p->word_length > 8)
+		return fail(USB_EINVAL, "word_length %u unsupported (2..8)", p->word_length);
+	if (p->hspw < 3 || p->hspw > 6)
+		return fail(USB_EINVAL, "hspw %u unsupported (3..6)", p->hspw);
+	const float sc[] = {p->match, p->mismatch, p->gap_open, p->gap_ext, p->term_gap_open, p->term_gap_ext};
+	for (float v : sc)
+		if (!is_int2(v) || std::fabs(v) > 1000)
+			return fail(USB_EINVAL, "score %g is not a multiple of 0.5: the integer DP cannot reproduce it", (double)v);
+	if (!(p->id >= 0.0f && p->id <= 1.0f))
+		return fail(USB_EINVAL, "-id %g out of range", (double)p->id);
+	D.match2 = (int)std::lround(2.0 * p->match);
+	D.mismatch2 = (int)std::lround(2.0 * p->mismatch);
+	D.open2 = (int)std::lround(2.0 * p->gap_open);
+	D.ext2 = (int)std::lround(2.0 * p->gap_ext);
+	D.topen2 = (int)std::lround(2.0 * p->term_gap_open);
+	D.text2 = (int)std::lround(2.0 * p->term_gap_ext);
+	D.xdrop2 = 2.0f * p->xdrop_nw;
+	D.min_hsp_fract_id = p->id > 0.75f ? p->id : 0.75f;
+	D.min_hsp_len = p->minhsp;
+	// MinGlobalHSPScore = FractId * Length * match, evaluated in float like the reference
+	float minscore = D.min_hsp_fract_id * (float)p->minhsp * p->match;
+	D.minscore2 = 2.0f * minscore;
+	D.band = p->band;
+	D.hspw = p->hspw;
+	D.hsp_words = 1u << (2 * p->hspw);
+	D.hsp_hi = D.hsp_words / 4;
+	D.word_length = p->word_length;
+	D.slots = 1u << (2 * p->word_length);
+	D.maxaccepts = p->maxaccepts;
+	D.maxrejects = p->maxrejects;
+	D.bump = p->bump;
+	D.id_d = (double)p->id;
+	return 0;
+}
+
+static bool g_tables_uploaded[64];
+
+static int upload_tables(int device)
+{
+	if (device < 0 || device >= 64)
+		return fail(USB_EINVAL, "device %d out of range", device);
+	if (g_tables_uploaded[device])
+		return 0;
+	CharTables T;
+	build_char_tables(T);
+	CK(cudaMemcpyToSymbol(c_cls, T.cls, sizeof T.cls));
+	CK(cudaMemcpyToSymbol(c_upper, T.upper, sizeof T.upper));
+	CK(cudaMemcpyToSymbol(c_comp, T.comp, sizeof T.comp));
+	g_tables_uploaded[device] = true;
+	return 0;
+}
+
+// ------------------------------------------------------------------ index
+extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *seqs, const uint64_t *seq_off,
+  uint32_t n_seq, usb_index **out)
+{
+	if (!out || (!seqs && n_seq) || !seq_off)
+		return fail(USB_EINVAL, "usb_index_create: null argument");
+	DevParams D;
+	int rc = make_dev_params(p, D);
+	if (rc)
+		return rc;
+	if (usb_device_count() <= device)
+		return fail(USB_ECUDA, "CUDA device %d not available (no CPU fallback exists)", device);
+	CK(cudaSetDevice(device));
+	rc = upload_tables(device);
+	if (rc)
+		return rc;
+	usb_index *ix = new usb_index;
+	ix->device = device;
+	ix->P = *p;
+	build_host_index(seqs, seq_off, n_seq, p->word_length, p->dbmask && !p->cluster_mode, 0, ix->H);
+	const HostIndex &H = ix->H;
+	if ((rc = ix->d_seqs.reserve(H.seqs.size())) || (rc = ix->d_seq_off.reserve(H.seq_off.size())) ||
+	    (rc = ix->d_seq_len.reserve(H.seq_len.size() + 1)) || (rc = ix->d_row_off.reserve(H.row_off.size())) ||
+	    (rc = ix->d_postings.reserve(H.postings.size()))) {
+		usb_index_free(ix);
+		return rc;
+	}
+	CK(cudaMemcpy(ix->d_seqs.p, H.seqs.data(), H.seqs.size(), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_seq_off.p, H.seq_off.data(), H.seq_off.size() * 8, cudaMemcpyHostToDevice));
+	if (n_seq)
+		CK(cudaMemcpy(ix->d_seq_len.p, H.seq_len.data(), H.seq_len.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
+	*out = ix;
+	return 0;
+}
+
+extern "C" void usb_index_free(usb_index *ix)
+{
+	if (!ix)
+		return;
+	cudaSetDevice(ix->device);
+	ix->d_seqs.release();
+	ix->d_seq_off.release();
+	ix->d_seq_len.release();
+	ix->d_row_off.release();
+	ix->d_postings.release();
+	delete ix;
+}
+
+extern "C" uint32_t usb_index_seq_count(const usb_index *ix) { return ix ? ix->H.n_seq : 0; }
+extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->H.row_off[ix->H.slots] : 0; }
+
+extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size)
+{
+	if (!ix || word >= ix->H.slots)
+		return fail(USB_EINVAL, "usb_index_row: bad word %u", word);
+	*row = ix->H.postings.data() + ix->H.row_off[word];
+	*size = (uint32_t)(ix->H.row_off[word + 1] - ix->H.row_off[word]);
+	return 0;
+}
+
+extern "C" int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t **seq, uint32_t *len)
+{
+	if (!ix || target >= ix->H.n_seq)
+		return fail(USB_EINVAL, "usb_index_seq: bad target %u", target);
+	*seq = ix->H.seqs.data() + ix->H.seq_off[target];
+	*len = ix->H.seq_len[target];
+	return 0;
+}
+
+// ------------------------------------------------------------------ searcher
+extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searcher **out)
+{
+	if (!ix || !out)
+		return fail(USB_EINVAL, "usb_searcher_create: null argument");
+	DevParams D;
+	int rc = make_dev_params(p, D);
+	if (rc)
+		return rc;
+	if (p->word_length != ix->P.word_length)
+		return fail(USB_EINVAL, "searcher word_length %u != index word_length %u", p->word_length, ix->P.word_length);
+	if (ix->H.n_seq > p->big)
+		return fail(USB_EINVAL,
+		  "DB has %u sequences > -big %u: the UDBSearchBig path (udbusortedsearcherbig.cpp) is not built yet",
+		  ix->H.n_seq, p->big);
+	CK(cudaSetDevice(ix->device));
+	usb_searcher *s = new usb_searcher;
+	s->ix = ix;
+	s->P = *p;
+	s->D = D;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, ix->device));
+	s->num_sms = prop.multiProcessorCount;
+	s->smem_optin = prop.sharedMemPerBlockOptin;
+	CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	for (auto &e : s->ev)
+		CK(cudaEventCreate(&e));
+	if ((rc = s->d_ctr.reserve(1))) {
+		usb_searcher_free(s);
+		return rc;
+	}
+	*out = s;
+	return 0;
+}
+
+extern "C" void usb_searcher_free(usb_searcher *s)
+{
+	if (!s)
+		return;
+	cudaSetDevice(s->ix->device);
+	if (s->stream)
+		cudaStreamSynchronize(s->stream);
+	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
+	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release();
+	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release();
+	for (auto &e : s->ev)
+		if (e)
+			cudaEventDestroy(e);
+	if (s->stream)
+		cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+extern "C" uint64_t usb_searcher_launch_count(const usb_searcher *s) { return s ? s->launches : 0; }
+
+extern "C" int usb_batch_counters(const usb_searcher *s, uint64_t out[4])
+{
+	if (!s || !out || !s->ran)
+		return fail(USB_EINVAL, "usb_batch_counters: no completed batch");
+	out[0] = s->last_postings;
+	out[1] = s->last_hits;
+	out[2] = s->last_runs;
+	out[3] = s->n_jobs;
+	return 0;
+}
+
+// ------------------------------------------------------------------ launches
+static int upload_queries(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q)
+{
+	if (!s || !q_off || (!qseqs && n_q))
+		return fail(USB_EINVAL, "null query buffers");
+	CK(cudaSetDevice(s->ix->device));
+	uint32_t max_ql = 0;
+	for (uint32_t i = 0; i < n_q; ++i) {
+		if (q_off[i + 1] < q_off[i])
+			return fail(USB_EINVAL, "q_off not ascending at %u", i);
+		uint64_t L = q_off[i + 1] - q_off[i];
+		if (L > 65000)
+			return fail(USB_ELIMIT, "query %u has %llu letters; the seed table supports up to 65000", i,
+			  (unsigned long long)L);
+		max_ql = std::max<uint32_t>(max_ql, (uint32_t)L);
+	}
+	const uint64_t base = n_q ? q_off[0] : 0, total = n_q ? q_off[n_q] - base : 0;
+	int rc;
+	if ((rc = s->d_q.reserve(total + 16)) || (rc = s->d_qoff.reserve((size_t)n_q + 1)))
+		return rc;
+	if (total)
+		CK(cudaMemcpyAsync(s->d_q.p, qseqs + base, total, cudaMemcpyHostToDevice, s->stream));
+	if (base == 0)
+		CK(cudaMemcpyAsync(s->d_qoff.p, q_off, ((size_t)n_q + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+	else {
+		std::vector<uint64_t> rel((size_t)n_q + 1);
+		for (uint32_t i = 0; i <= n_q; ++i)
+			rel[i] = q_off[i] - base;
+		CK(cudaMemcpyAsync(s->d_qoff.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+	}
+	s->n_q = n_q;
+	s->max_ql = max_ql;
+	s->ran = false;
+	return 0;
+}
+
+static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
+{
+	const usb_index *ix = s->ix;
+	const uint32_t N = ix->H.n_seq;
+	int rc;
+	if ((rc = s->d_cand_t.reserve((size_t)n_jobs * k_max)) || (rc = s->d_cand_u.reserve((size_t)n_jobs * k_max)) ||
+	    (rc = s->d_ncand.reserve(n_jobs)) || (rc = s->d_nemit.reserve(n_jobs)))
+		return rc;
+	if (want_u && (rc = s->d_uout.reserve((size_t)n_jobs * N)))
+		return rc;
+	if (n_jobs == 0)
+		return 0;
+	RankArgs a;
+	memset(&a, 0, sizeof a);
+	a.P = s->D;
+	a.q = s->d_q.p;
+	a.q_off = s->d_qoff.p;
+	a.n_jobs = n_jobs;
+	a.strands = strands;
+	a.row_off = ix->d_row_off.p;
+	a.postings = ix->d_postings.p;
+	a.n_seq = N;
+	a.k_max = k_max;
+	a.cand_t = s->d_cand_t.p;
+	a.cand_u = s->d_cand_u.p;
+	a.n_cand = s->d_ncand.p;
+	a.n_emit = s->d_nemit.p;
+	a.u_out = want_u ? s->d_uout.p : nullptr;
+	const bool wide = s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > 255;
+	a.seg_narrow = rank_segment(N, false);
+	a.seg_wide = rank_segment(N, true);
+	a.rec_cap = wide ? RANK_REC_WIDE : RANK_REC_NARROW;
+	a.bump_d = s->P.bump / 100.0;
+	a.ctr = s->d_ctr.p;
+	const size_t smem = rank_smem_bytes(N, wide, s->D.slots, a.rec_cap, &a.u_bytes);
+	if (smem > s->smem_optin)
+		return fail(USB_ELIMIT,
+		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
+		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
+	if (smem > s->rank_smem_set) {
+		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		s->rank_smem_set = smem;
+	}
+	k_rank<<<n_jobs, RANK_THREADS, smem, s->stream>>>(a);
+	CK(cudaGetLastError());
+	++s->launches;
+	return 0;
+}
+
+struct AlignGeom {
+	int wpb;
+	uint32_t ql_cap, tl_cap, fast_bytes, fast_in_smem;
+	size_t smem;
+	uint64_t slab_stride;
+	uint32_t n_warps, grid;
+};
+
+static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uint32_t hsp_cap, AlignGeom &g)
+{
+	g.ql_cap = pad16(max_ql + 16);
+	g.tl_cap = pad16(max_tl + 16);
+	g.fast_bytes = align_fast_bytes(g.ql_cap, g.tl_cap, s->D.hsp_words);
+	const size_t budget = s->smem_optin > 1024 ? s->smem_optin - 1024 : 0;
+	const int choices[] = {16, 12, 8, 6, 4, 2, 1};
+	g.wpb = 0;
+	for (int c : choices)
+		if ((size_t)c * g.fast_bytes <= budget) {
+			g.wpb = c;
+			break;
+		}
+	g.fast_in_smem = g.wpb != 0;
+	if (!g.fast_in_smem)
+		g.wpb = 8;
+	g.smem = g.fast_in_smem ? (size_t)g.wpb * g.fast_bytes : 0;
+	g.slab_stride = align_slab_bytes(g.ql_cap, g.tl_cap, hsp_cap) + (g.fast_in_smem ? 0 : g.fast_bytes);
+	g.slab_stride = (g.slab_stride + 255) & ~(uint64_t)255;
+	g.grid = (uint32_t)s->num_sms;
+	g.n_warps = g.grid * g.wpb;
+	// keep the workspace under ~1/3 of device memory
+	size_t free_b = 0, total_b = 0;
+	CK(cudaMemGetInfo(&free_b, &total_b));
+	const uint64_t limit = std::max<uint64_t>(total_b / 3, (uint64_t)256 << 20);
+	while ((uint64_t)g.n_warps * g.slab_stride > limit && g.grid > 1) {
+		g.grid = std::max(1u, g.grid / 2);
+		g.n_warps = g.grid * g.wpb;
+	}
+	if ((uint64_t)g.n_warps * g.slab_stride > limit)
+		return fail(USB_ELIMIT, "alignment workspace of %llu bytes per warp (query %u x target %u letters) does not fit",
+		  (unsigned long long)g.slab_stride, max_ql, max_tl);
+	return 0;
+}
+
+template <int WPB> static cudaError_t launch_align_t(const AlignArgs &a, const AlignGeom &g, cudaStream_t st)
+{
+	cudaError_t e = cudaFuncSetAttribute(k_align<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+	if (e != cudaSuccess)
+		return e;
+	k_align<WPB><<<g.grid, WPB * 32, g.smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+template <int WPB> static cudaError_t launch_viterbi_t(const ViterbiArgs &v, const AlignGeom &g, cudaStream_t st)
+{
+	cudaError_t e = cudaFuncSetAttribute(k_viterbi<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+	if (e != cudaSuccess)
+		return e;
+	k_viterbi<WPB><<<g.grid, WPB * 32, g.smem, st>>>(v);
+	return cudaGetLastError();
+}
+
+#define DISPATCH_WPB(fn, wpb, ...)                                                                  \
+	((wpb) == 16 ? fn<16>(__VA_ARGS__) : (wpb) == 12 ? fn<12>(__VA_ARGS__) : (wpb) == 8 ? fn<8>(__VA_ARGS__) \
+	 : (wpb) == 6 ? fn<6>(__VA_ARGS__) : (wpb) == 4 ? fn<4>(__VA_ARGS__) : (wpb) == 2 ? fn<2>(__VA_ARGS__)   \
+	                                                                                 : fn<1>(__VA_ARGS__))
+
+static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_cap, AlignArgs &a)
+{
+	memset(&a, 0, sizeof a);
+	const usb_index *ix = s->ix;
+	a.P = s->D;
+	a.q = s->d_q.p;
+	a.q_off = s->d_qoff.p;
+	a.db_seq = ix->d_seqs.p;
+	a.db_off = ix->d_seq_off.p;
+	a.db_len = ix->d_seq_len.p;
+	a.slab = s->d_slab.p;
+	a.slab_stride = g.slab_stride;
+	a.ql_cap = g.ql_cap;
+	a.tl_cap = g.tl_cap;
+	a.hsp_cap = hsp_cap;
+	a.fast_bytes = g.fast_bytes;
+	a.fast_in_smem = g.fast_in_smem;
+	a.ctr = s->d_ctr.p;
+}
+
+static const char *err_text(uint32_t e)
+{
+	static thread_local char buf[256];
+	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s", e, e & ERR_HITS_FULL ? " hit buffer full" : "",
+	  e & ERR_RUNS_FULL ? " run arena full" : "", e & ERR_HSP_FULL ? " HSP list full" : "",
+	  e & ERR_TRACE ? " traceback left the band" : "", e & ERR_RECORDS_FULL ? " U-sort record list full" : "",
+	  e & ERR_NO_M ? " alignment path without M" : "");
+	return buf;
+}
+
+extern "C" int usb_batch_upload(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q)
+{
+	int rc = upload_queries(s, qseqs, q_off, n_q);
+	if (rc)
+		return rc;
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int usb_batch_run(usb_searcher *s, float *ms)
+{
+	if (!s)
+		return fail(USB_EINVAL, "null searcher");
+	CK(cudaSetDevice(s->ix->device));
+	const usb_index *ix = s->ix;
+	const uint32_t N = ix->H.n_seq;
+	s->strands = s->P.strand_both ? 2 : 1;
+	s->n_jobs = s->n_q * s->strands;
+	uint32_t k_max = N;
+	if (s->P.maxaccepts > 0 && s->P.maxrejects > 0)
+		k_max = std::min<uint64_t>(N, (uint64_t)s->P.maxaccepts + s->P.maxrejects - 1);
+	if (k_max == 0)
+		k_max = 1;
+	if (k_max > RANK_KCAP)
+		return fail(USB_ELIMIT,
+		  "maxaccepts/maxrejects allow up to %u candidates per query; this build materialises at most %u (set both > 0)",
+		  k_max, RANK_KCAP);
+	s->k_max = k_max;
+	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->H.max_len / 8 + 16);
+	AlignGeom g;
+	int rc = align_geometry(s, s->max_ql, ix->H.max_len, hsp_cap, g);
+	if (rc)
+		return rc;
+	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : k_max;
+	const uint64_t hits_cap = std::max<uint64_t>(1, (uint64_t)s->n_jobs * per_job_hits);
+	if (hits_cap > 0xfffffff0ull)
+		return fail(USB_ELIMIT, "hit buffer of %llu records too large; use smaller batches", (unsigned long long)hits_cap);
+	uint64_t runs_cap = std::max<uint64_t>(s->d_runs.cap, std::max<uint64_t>((uint64_t)1 << 20, hits_cap * 24));
+	if ((rc = s->d_hits.reserve(hits_cap)) || (rc = s->d_qstat.reserve(std::max(1u, s->n_jobs))) ||
+	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride)))
+		return rc;
+	for (int attempt = 0;; ++attempt) {
+		if ((rc = s->d_runs.reserve(runs_cap)))
+			return rc;
+		CK(cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream));
+		CK(cudaEventRecord(s->ev[0], s->stream));
+		if ((rc = launch_rank(s, s->n_jobs, s->strands, k_max, false)))
+			return rc;
+		CK(cudaEventRecord(s->ev[1], s->stream));
+		if (s->n_jobs) {
+			AlignArgs a;
+			fill_align_args(s, g, hsp_cap, a);
+			a.n_jobs = s->n_jobs;
+			a.strands = s->strands;
+			a.cand_t = s->d_cand_t.p;
+			a.n_emit = s->d_nemit.p;
+			a.k_max = k_max;
+			a.hits = s->d_hits.p;
+			a.hits_cap = (uint32_t)hits_cap;
+			a.runs = s->d_runs.p;
+			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
+			a.qstat = s->d_qstat.p;
+			CK(DISPATCH_WPB(launch_align_t, g.wpb, a, g, s->stream));
+			++s->launches;
+		}
+		CK(cudaEventRecord(s->ev[2], s->stream));
+		DevCounters c;
+		CK(cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		if (c.err == ERR_RUNS_FULL && attempt < 4) {
+			runs_cap = std::max<uint64_t>(runs_cap * 4, (uint64_t)c.n_runs + 1024);
+			continue;
+		}
+		if (c.err)
+			return fail(USB_ELIMIT, "%s", err_text(c.err));
+		s->last_hits = c.n_hits;
+		s->last_runs = c.n_runs;
+		s->last_postings = c.postings;
+		break;
+	}
+	if (ms) {
+		CK(cudaEventElapsedTime(&ms[0], s->ev[0], s->ev[1]));
+		CK(cudaEventElapsedTime(&ms[1], s->ev[1], s->ev[2]));
+		CK(cudaEventElapsedTime(&ms[2], s->ev[0], s->ev[2]));
+	}
+	s->ran = true;
+	return 0;
+}
+
+// HitMgr::Sort (hitmgr.cpp:477) orders a query's hits with the reference's own quicksort on
+// float scores (sort.h:63-102): middle pivot, Hoare partition, descending, not stable.
+static void quicksort_desc(const float *v, uint32_t *ord, int lo, int hi)
+{
+	int i = lo, j = hi;
+	const float pivot = v[ord[(lo + hi) / 2]];
+	while (i <= j) {
+		while (v[ord[i]] > pivot)
+			++i;
+		while (v[ord[j]] < pivot)
+			--j;
+		if (i <= j) {
+			std::swap(ord[i], ord[j]);
+			++i;
+			--j;
+		}
+	}
+	if (lo < j)
+		quicksort_desc(v, ord, lo, j);
+	if (i < hi)
+		quicksort_desc(v, ord, i, hi);
+}
+
+static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector<uint64_t> &qoff)
+{
+	std::vector<float> sc;
+	std::vector<uint32_t> ord;
+	std::vector<usb_hit> tmp;
+	for (size_t q = 0; q + 1 < qoff.size(); ++q) {
+		const uint64_t b = qoff[q], e = qoff[q + 1];
+		const uint32_t n = (uint32_t)(e - b);
+		if (n < 2)
+			continue;
+		// Searcher::Search appends plus-strand hits, then minus-strand hits (searcher.cpp:144-158)
+		std::sort(hits.begin() + b, hits.begin() + e, [](const usb_hit &x, const usb_hit &y) {
+			return x.strand != y.strand ? x.strand < y.strand : x.rank < y.rank;
+		});
+		sc.resize(n);
+		ord.resize(n);
+		tmp.assign(hits.begin() + b, hits.begin() + e);
+		for (uint32_t i = 0; i < n; ++i) {
+			const usb_hit &h = tmp[i];
+			sc[i] = (float)(h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen); // arscorer.cpp:818
+			ord[i] = i;
+		}
+		quicksort_desc(sc.data(), ord.data(), 0, (int)n - 1);
+		for (uint32_t i = 0; i < n; ++i)
+			hits[b + i] = tmp[ord[i]];
+	}
+}
+
+static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result **out)
+{
+	usb_result *r = new usb_result;
+	const uint32_t nh = s->last_hits, nr = s->last_runs;
+	std::vector<usb_hit> raw(nh);
+	r->runs.resize(nr);
+	r->qstat.resize(s->n_jobs);
+	std::vector<uint32_t> ncand(s->n_jobs);
+	cudaError_t e = cudaSuccess;
+	if (nh)
+		e = cudaMemcpyAsync(raw.data(), s->d_hits.p, (size_t)nh * sizeof(usb_hit), cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess && nr)
+		e = cudaMemcpyAsync(r->runs.data(), s->d_runs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess && s->n_jobs && group) {
+		e = cudaMemcpyAsync(r->qstat.data(), s->d_qstat.p, (size_t)s->n_jobs * sizeof(usb_qstat), cudaMemcpyDeviceToHost,
+		  s->stream);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(ncand.data(), s->d_ncand.p, (size_t)s->n_jobs * 4, cudaMemcpyDeviceToHost, s->stream);
+	}
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s->stream);
+	if (e != cudaSuccess) {
+		delete r;
+		return fail(USB_ECUDA, "result download failed: %s", cudaGetErrorString(e));
+	}
+	if (group)
+		for (uint32_t j = 0; j < s->n_jobs; ++j)
+			r->qstat[j].n_cand = ncand[j];
+	// group by query (counting sort), then the reference's per-query order
+	r->qoff.assign((size_t)n_q + 1, 0);
+	for (const usb_hit &h : raw)
+		++r->qoff[(size_t)(group ? h.query : h.rank) + 1];
+	for (uint32_t q = 0; q < n_q; ++q)
+		r->qoff[q + 1] += r->qoff[q];
+	r->hits.resize(nh);
+	std::vector<uint64_t> cur(r->qoff.begin(), r->qoff.end() - 1);
+	for (const usb_hit &h : raw)
+		r->hits[cur[group ? h.query : h.rank]++] = h;
+	if (group)
+		order_hits_like_hitmgr(r->hits, r->qoff);
+	*out = r;
+	return 0;
+}
+
+extern "C" int usb_batch_download(usb_searcher *s, usb_result **out)
+{
+	if (!s || !out)
+		return fail(USB_EINVAL, "null argument");
+	if (!s->ran)
+		return fail(USB_EINVAL, "usb_batch_download before usb_batch_run");
+	CK(cudaSetDevice(s->ix->device));
+	return download_result(s, s->n_q, true, out);
+}
+
+extern "C" int usb_search_batch(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  usb_result **out)
+{
+	int rc = upload_queries(s, qseqs, q_off, n_q);
+	if (rc)
+		return rc;
+	if ((rc = usb_batch_run(s, nullptr)))
+		return rc;
+	return usb_batch_download(s, out);
+}
+
+extern "C" int usb_batch_export_hits_device(usb_searcher *s, void *dev_dst, uint64_t cap_hits, uint64_t *n_hits)
+{
+	if (!s || !s->ran || !n_hits)
+		return fail(USB_EINVAL, "usb_batch_export_hits_device: no completed batch");
+	CK(cudaSetDevice(s->ix->device));
+	*n_hits = s->last_hits;
+	const uint64_t n = std::min<uint64_t>(cap_hits, s->last_hits);
+	if (n && dev_dst) {
+		CK(cudaMemcpyAsync(dev_dst, s->d_hits.p, n * sizeof(usb_hit), cudaMemcpyDeviceToDevice, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------ result accessors
+extern "C" uint64_t usb_result_hit_count(const usb_result *r) { return r ? r->hits.size() : 0; }
+extern "C" const usb_hit *usb_result_hits(const usb_result *r) { return r ? r->hits.data() : nullptr; }
+extern "C" const uint32_t *usb_result_runs(const usb_result *r, uint64_t *n_runs)
+{
+	if (n_runs)
+		*n_runs = r ? r->runs.size() : 0;
+	return r ? r->runs.data() : nullptr;
+}
+extern "C" const uint64_t *usb_result_query_offsets(const usb_result *r) { return r ? r->qoff.data() : nullptr; }
+extern "C" const usb_qstat *usb_result_qstats(const usb_result *r) { return r ? r->qstat.data() : nullptr; }
+extern "C" void usb_result_free(usb_result *r) { delete r; }
+
+extern "C" uint32_t usb_result_path(const usb_result *r, const usb_hit *h, char *buf)
+{
+	static const char ops[4] = {'M', 'D', 'I', '?'};
+	uint32_t n = 0;
+	for (uint32_t k = 0; k < h->run_cnt; ++k) {
+		const uint32_t v = r->runs[(size_t)h->run_off + k];
+		const uint32_t len = v >> 2;
+		memset(buf + n, ops[v & 3], len);
+		n += len;
+	}
+	buf[n] = 0;
+	return n;
+}
+
+// ------------------------------------------------------------------ stage-level entry points
+extern "C" int usb_rank_batch(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  uint32_t k_max, uint32_t *cand_t, uint32_t *cand_u, uint32_t *n_cand, uint32_t *u_out)
+{
+	if (k_max == 0 || k_max > RANK_KCAP)
+		return fail(USB_EINVAL, "k_max must be 1..%u", RANK_KCAP);
+	int rc = upload_queries(s, qseqs, q_off, n_q);
+	if (rc)
+		return rc;
+	const uint32_t strands = s->P.strand_both ? 2 : 1, n_jobs = n_q * strands;
+	const uint32_t N = s->ix->H.n_seq;
+	CK(cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream));
+	if ((rc = launch_rank(s, n_jobs, strands, k_max, u_out != nullptr)))
+		return rc;
+	DevCounters c;
+	CK(cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+	std::vector<uint32_t> nemit(n_jobs);
+	if (n_jobs) {
+		CK(cudaMemcpyAsync(cand_t, s->d_cand_t.p, (size_t)n_jobs * k_max * 4, cudaMemcpyDeviceToHost, s->stream));
+		if (cand_u)
+			CK(cudaMemcpyAsync(cand_u, s->d_cand_u.p, (size_t)n_jobs * k_max * 4, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(n_cand, s->d_ncand.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, s->stream));
+		if (u_out)
+			CK(cudaMemcpyAsync(u_out, s->d_uout.p, (size_t)n_jobs * N * 4, cudaMemcpyDeviceToHost, s->stream));
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	if (c.err)
+		return fail(USB_ELIMIT, "%s", err_text(c.err));
+	return 0;
+}
+
+extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_pairs, uint8_t *aligned, usb_result **out,
+  uint32_t *hsp_out, uint32_t max_hsp)
+{
+	if (!pair_q || !pair_t || !aligned || !out)
+		return fail(USB_EINVAL, "usb_align_pairs: null argument");
+	const usb_index *ix = s->ix;
+	for (uint32_t i = 0; i < n_pairs; ++i)
+		if (pair_q[i] >= n_q || pair_t[i] >= ix->H.n_seq)
+			return fail(USB_EINVAL, "pair %u out of range", i);
+	int rc = upload_queries(s, qseqs, q_off, n_q);
+	if (rc)
+		return rc;
+	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->H.max_len / 8 + 16);
+	AlignGeom g;
+	if ((rc = align_geometry(s, s->max_ql, ix->H.max_len, hsp_cap, g)))
+		return rc;
+	DevBuf<uint32_t> d_pq, d_pt, d_hsp;
+	DevBuf<uint8_t> d_al;
+	const size_t hsp_words = hsp_out ? (size_t)n_pairs * (1 + 4 * max_hsp) : 0;
+	uint64_t runs_cap = std::max<uint64_t>((uint64_t)1 << 20, (uint64_t)n_pairs * 64);
+	auto cleanup = [&]() { d_pq.release(); d_pt.release(); d_hsp.release(); d_al.release(); };
+	if ((rc = d_pq.reserve(n_pairs + 1)) || (rc = d_pt.reserve(n_pairs + 1)) || (rc = d_al.reserve(n_pairs + 1)) ||
+	    (rc = d_hsp.reserve(hsp_words + 1)) || (rc = s->d_hits.reserve(n_pairs + 1)) ||
+	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride))) {
+		cleanup();
+		return rc;
+	}
+	cudaMemcpyAsync(d_pq.p, pair_q, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_pt.p, pair_t, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s->stream);
+	DevCounters c;
+	memset(&c, 0, sizeof c);
+	for (int attempt = 0; n_pairs; ++attempt) {
+		if ((rc = s->d_runs.reserve(runs_cap))) {
+			cleanup();
+			return rc;
+		}
+		cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream);
+		cudaMemsetAsync(d_al.p, 0, n_pairs, s->stream);
+		AlignArgs a;
+		fill_align_args(s, g, hsp_cap, a);
+		a.n_jobs = n_pairs;
+		a.strands = 1;
+		a.pair_q = d_pq.p;
+		a.pair_t = d_pt.p;
+		a.hits = s->d_hits.p;
+		a.hits_cap = n_pairs;
+		a.runs = s->d_runs.p;
+		a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
+		a.aligned = d_al.p;
+		a.hsp_out = hsp_out ? d_hsp.p : nullptr;
+		a.max_hsp = max_hsp;
+		cudaError_t e = DISPATCH_WPB(launch_align_t, g.wpb, a, g, s->stream);
+		++s->launches;
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s->stream);
+		if (e != cudaSuccess) {
+			cleanup();
+			return fail(USB_ECUDA, "align kernel failed: %s", cudaGetErrorString(e));
+		}
+		if (c.err == ERR_RUNS_FULL && attempt < 4) {
+			runs_cap *= 4;
+			continue;
+		}
+		break;
+	}
+	if (c.err) {
+		cleanup();
+		return fail(USB_ELIMIT, "%s", err_text(c.err));
+	}
+	cudaMemcpyAsync(aligned, d_al.p, n_pairs, cudaMemcpyDeviceToHost, s->stream);
+	if (hsp_out)
+		cudaMemcpyAsync(hsp_out, d_hsp.p, hsp_words * 4, cudaMemcpyDeviceToHost, s->stream);
+	s->last_hits = c.n_hits;
+	s->last_runs = c.n_runs;
+	s->n_jobs = 0;
+	rc = download_result(s, n_pairs, false, out); // grouped by pair index (hit.rank)
+	cleanup();
+	return rc;
+}
+
+extern "C" int usb_viterbi_batch(usb_searcher *s, const uint8_t *a_seq, const uint64_t *a_off, const uint8_t *b_seq,
+  const uint64_t *b_off, const uint8_t *flags, uint32_t n, char *paths, const uint64_t *path_off, int32_t *score2)
+{
+	if (!s || !a_off || !b_off || !flags || !paths || !path_off || !score2)
+		return fail(USB_EINVAL, "usb_viterbi_batch: null argument");
+	if (n == 0)
+		return 0;
+	CK(cudaSetDevice(s->ix->device));
+	uint32_t max_a = 0, max_b = 0;
+	uint64_t path_total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+		if (la == 0 || lb == 0 || la > 65000 || lb > (1u << 24))
+			return fail(USB_EINVAL, "rectangle %u: side lengths %llu x %llu unsupported", i, (unsigned long long)la,
+			  (unsigned long long)lb);
+		max_a = std::max<uint32_t>(max_a, (uint32_t)la);
+		max_b = std::max<uint32_t>(max_b, (uint32_t)lb);
+		path_total = std::max<uint64_t>(path_total, path_off[i] + la + lb + 1);
+	}
+	AlignGeom g;
+	int rc = align_geometry(s, max_a, max_b, 64, g);
+	if (rc)
+		return rc;
+	DevBuf<uint8_t> d_a, d_b, d_f;
+	DevBuf<uint64_t> d_ao, d_bo, d_po;
+	DevBuf<char> d_paths;
+	DevBuf<int> d_sc;
+	auto cleanup = [&]() {
+		d_a.release(); d_b.release(); d_f.release(); d_ao.release(); d_bo.release(); d_po.release();
+		d_paths.release(); d_sc.release();
+	};
+	if ((rc = d_a.reserve(a_off[n] + 1)) || (rc = d_b.reserve(b_off[n] + 1)) || (rc = d_f.reserve(n)) ||
+	    (rc = d_ao.reserve(n + 1)) || (rc = d_bo.reserve(n + 1)) || (rc = d_po.reserve(n)) ||
+	    (rc = d_paths.reserve(path_total)) || (rc = d_sc.reserve(n)) ||
+	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride))) {
+		cleanup();
+		return rc;
+	}
+	cudaMemcpyAsync(d_a.p, a_seq, a_off[n], cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_b.p, b_seq, b_off[n], cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_f.p, flags, n, cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_ao.p, a_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_bo.p, b_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_po.p, path_off, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream);
+	cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream);
+	ViterbiArgs v;
+	memset(&v, 0, sizeof v);
+	fill_align_args(s, g, 64, v.base);
+	v.a_seq = d_a.p; v.a_off = d_ao.p; v.b_seq = d_b.p; v.b_off = d_bo.p; v.flags = d_f.p;
+	v.n = n; v.paths = d_paths.p; v.path_off = d_po.p; v.score2 = d_sc.p;
+	cudaError_t e = DISPATCH_WPB(launch_viterbi_t, g.wpb, v, g, s->stream);
+	++s->launches;
+	DevCounters c;
+	memset(&c, 0, sizeof c);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(paths, d_paths.p, path_total, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(score2, d_sc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s->stream);
+	cleanup();
+	if (e != cudaSuccess)
+		return fail(USB_ECUDA, "viterbi kernel failed: %s", cudaGetErrorString(e));
+	if (c.err)
+		return fail(USB_ELIMIT, "%s", err_text(c.err));
+	return 0;
+}

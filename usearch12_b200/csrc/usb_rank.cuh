@@ -1,0 +1,464 @@
+// usb_rank.cuh -- kernel K1: UDB posting walk + U-sort candidate ranking, one CTA per
+// (query, strand).
+//
+// Reference behaviour reproduced (results identical, algorithm re-designed for one CTA):
+//   a1  query words, bad words dropped      udbsearcher.cpp:128-151, udbparams.cpp:540-555
+//   a2  unique words                        udbsearcher.cpp:161-194 (order irrelevant for U)
+//   a4  U[t] = #unique query words in t     udbusortedsearcher.cpp:375-410 SetU_NonCoded
+//   a5  SetTopBump rising-threshold filter  udbusortedsearcher.cpp:230-267
+//   a6  CountSortOrderDesc + NextValue/2    countsort.cpp:6-108
+//
+// Design: the per-target counters live in shared memory (1 byte per target when the query has
+// <= 255 word positions, 2 bytes otherwise), so U never touches HBM; posting rows are streamed
+// with coalesced 128-byte warp loads and counted with shared-memory atomics on packed 32-bit
+// words.  The two order-dependent filters are evaluated exactly from the strict prefix maxima of
+// U ("records"): records are few, so one thread replays the
+// threshold evolution over them and every other thread filters its own contiguous target
+// segment against the threshold in force at that position.  Only the first k_max candidates of
+// the descending stable order are materialised (the Terminator can never look further than
+// maxaccepts+maxrejects-1 candidates): a radix-select on U finds the cut value, ties at the cut
+// are taken in ascending target order with a block scan, and the <= k_max keys are bitonic-sorted.
+#pragma once
+#include "usb_dev.cuh"
+
+namespace usb {
+
+#define RANK_THREADS 1024
+#define RANK_KCAP 1024         // max candidates materialised per query
+#define RANK_REC_NARROW 256
+#define RANK_REC_WIDE 2048
+
+struct RankArgs {
+	DevParams P;
+	const uint8_t *q;          // concatenated query letters
+	const uint64_t *q_off;     // n_q + 1
+	uint32_t n_jobs;           // n_q * strands
+	uint32_t strands;          // 1 or 2
+	const uint64_t *row_off;   // slots + 1
+	const uint32_t *postings;
+	uint32_t n_seq;
+	uint32_t k_max;            // <= RANK_KCAP
+	uint32_t *cand_t;          // n_jobs * k_max
+	uint32_t *cand_u;          // n_jobs * k_max (may be null)
+	uint32_t *n_cand;          // TopOrder.Size per job
+	uint32_t *n_emit;          // min(TopOrder.Size, k_max) per job
+	uint32_t *u_out;           // optional: n_jobs * n_seq
+	uint32_t seg_narrow, seg_wide; // targets per thread segment (bank-conflict-free strides)
+	uint32_t u_bytes;          // shared bytes reserved for the counters
+	uint32_t rec_cap;
+	double bump_d;             // BumpPct / 100.0 ; 0 = no bump
+	DevCounters *ctr;
+};
+
+struct RankShared {
+	uint32_t n_rows, row_cur, n_rec, n_chg;
+	uint32_t maxv, minv, total, vstar, m_eq, n_sel, bstar, above;
+	uint32_t take_all, n_post, pad1, pad2;
+	uint32_t warp_tmp[32];
+	uint32_t hist[256];
+	uint32_t rows[RANK_THREADS];
+	unsigned long long sel[RANK_KCAP];
+};
+
+// exclusive prefix maximum over the CTA in thread order
+__device__ __forceinline__ uint32_t block_excl_scan_max(uint32_t v, uint32_t *warp_tmp)
+{
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t t = __shfl_up_sync(USB_FULL, inc, d);
+		if (lane >= (uint32_t)d)
+			inc = max(inc, t);
+	}
+	if (lane == 31)
+		warp_tmp[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t xi = warp_tmp[lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t t = __shfl_up_sync(USB_FULL, xi, d);
+			if (lane >= (uint32_t)d)
+				xi = max(xi, t);
+		}
+		uint32_t ex = __shfl_up_sync(USB_FULL, xi, 1);
+		warp_tmp[lane] = lane == 0 ? 0u : ex;
+	}
+	__syncthreads();
+	uint32_t ex = __shfl_up_sync(USB_FULL, inc, 1);
+	ex = lane == 0 ? 0u : ex;
+	uint32_t r = max(ex, warp_tmp[w]);
+	__syncthreads();
+	return r;
+}
+
+// exclusive prefix sum over the CTA in thread order
+__device__ __forceinline__ uint32_t block_excl_scan_sum(uint32_t v, uint32_t *warp_tmp)
+{
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t t = __shfl_up_sync(USB_FULL, inc, d);
+		if (lane >= (uint32_t)d)
+			inc += t;
+	}
+	if (lane == 31)
+		warp_tmp[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t x = warp_tmp[lane];
+		uint32_t xi = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t t = __shfl_up_sync(USB_FULL, xi, d);
+			if (lane >= (uint32_t)d)
+				xi += t;
+		}
+		warp_tmp[lane] = xi - x;
+	}
+	__syncthreads();
+	uint32_t r = inc - v + warp_tmp[w];
+	__syncthreads();
+	return r;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ uint32_t u_get(const uint8_t *U, uint32_t t)
+{
+	return WIDE ? (uint32_t)((const uint16_t *)U)[t] : (uint32_t)U[t];
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void u_inc(uint32_t *U32, uint32_t t)
+{
+	if (WIDE)
+		atomicAdd(&U32[t >> 1], 1u << ((t & 1) * 16));
+	else
+		atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
+}
+
+// Survivor test for target t with count u (u > 0): SetTopBump threshold in force at t (changes
+// take effect after the record position that caused them) and the counting-sort cut-off.
+struct KeepCursor {
+	const uint32_t *chg_pos, *chg_minu;
+	uint32_t n_chg, minv, cur;
+	__device__ __forceinline__ bool keep(uint32_t t, uint32_t u)
+	{
+		while (cur < n_chg && chg_pos[cur] < t)
+			++cur;
+		uint32_t mu = cur == 0 ? 1u : chg_minu[cur - 1];
+		return u >= mu && u >= minv;
+	}
+};
+
+template <bool WIDE>
+__device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t *U, uint32_t *bitmap,
+  uint32_t *rec_pos, uint32_t *rec_val, uint32_t *chg_pos, uint32_t *chg_minu)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t N = a.n_seq;
+	const uint32_t WLEN = a.P.word_length;
+	const uint32_t qi = job / a.strands, strand = job % a.strands;
+	const uint64_t q0 = a.q_off[qi];
+	const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
+	const uint8_t *Q = a.q + q0;
+	uint32_t *U32 = (uint32_t *)U;
+
+	// ---- zero shared state
+	{
+		const uint32_t u_words = ((WIDE ? 2 * N : N) + 3) / 4;
+		for (uint32_t i = tid; i < u_words; i += RANK_THREADS)
+			U32[i] = 0;
+		for (uint32_t i = tid; i < a.P.slots / 32; i += RANK_THREADS)
+			bitmap[i] = 0;
+		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+			S.hist[i] = 0;
+		if (tid == 0) {
+			S.n_rows = 0; S.row_cur = 0; S.n_rec = 0; S.n_chg = 0; S.n_sel = 0; S.n_post = 0;
+		}
+	}
+	__syncthreads();
+
+	// ---- a1/a2/a4: words -> unique rows -> posting walk
+	const uint32_t npos = L >= WLEN ? L - WLEN + 1 : 0;
+	for (uint32_t base = 0; base < npos; base += RANK_THREADS) {
+		const uint32_t p = base + tid;
+		if (p < npos) {
+			uint32_t word = 0, bad = 0;
+			for (uint32_t i = 0; i < WLEN; ++i) {
+				uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - (p + i)]] : (uint32_t)Q[p + i];
+				uint32_t l = udb_letter(c);
+				bad |= l >> 2;
+				word = (word << 2) | (l & 3);
+			}
+			if (!bad) {
+				uint32_t bit = 1u << (word & 31);
+				uint32_t old = atomicOr(&bitmap[word >> 5], bit);
+				if (!(old & bit))
+					S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+			}
+		}
+		__syncthreads();
+		const uint32_t n_rows = S.n_rows;
+		for (;;) {
+			uint32_t r = 0;
+			if (lane == 0)
+				r = atomicAdd(&S.row_cur, 1u);
+			r = __shfl_sync(USB_FULL, r, 0);
+			if (r >= n_rows)
+				break;
+			const uint32_t word = S.rows[r];
+			const uint64_t beg = a.row_off[word], end = a.row_off[word + 1];
+			if (lane == 0)
+				atomicAdd(&S.n_post, (uint32_t)(end - beg));
+			const uint32_t *pp = a.postings;
+			uint64_t i = beg + lane;
+			for (; i + 96 < end; i += 128) {
+				uint32_t t0 = __ldg(pp + i), t1 = __ldg(pp + i + 32), t2 = __ldg(pp + i + 64), t3 = __ldg(pp + i + 96);
+				u_inc<WIDE>(U32, t0); u_inc<WIDE>(U32, t1); u_inc<WIDE>(U32, t2); u_inc<WIDE>(U32, t3);
+			}
+			for (; i < end; i += 32)
+				u_inc<WIDE>(U32, __ldg(pp + i));
+		}
+		__syncthreads();
+		if (tid == 0) {
+			S.n_rows = 0;
+			S.row_cur = 0;
+		}
+		__syncthreads();
+	}
+
+	if (a.u_out)
+		for (uint32_t t = tid; t < N; t += RANK_THREADS)
+			a.u_out[(uint64_t)job * N + t] = u_get<WIDE>(U, t);
+
+	// ---- strict prefix maxima ("records") of U in target order
+	const uint32_t seg = WIDE ? a.seg_wide : a.seg_narrow;
+	const uint32_t t0 = min(N, tid * seg), t1 = min(N, t0 + seg);
+	uint32_t m = 0;
+	for (uint32_t t = t0; t < t1; ++t)
+		m = max(m, u_get<WIDE>(U, t));
+	uint32_t run = block_excl_scan_max(m, S.warp_tmp);
+	if (m > run)
+		for (uint32_t t = t0; t < t1; ++t) {
+			uint32_t u = u_get<WIDE>(U, t);
+			if (u > run) {
+				uint32_t idx = atomicAdd(&S.n_rec, 1u);
+				if (idx < a.rec_cap) {
+					rec_pos[idx] = t;
+					rec_val[idx] = u;
+				}
+				run = u;
+			}
+		}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t n = S.n_rec;
+		if (n > a.rec_cap) {
+			atomicOr(&a.ctr->err, ERR_RECORDS_FULL);
+			n = a.rec_cap;
+		}
+		for (uint32_t i = 1; i < n; ++i) { // few records: insertion sort by position
+			uint32_t p = rec_pos[i], v = rec_val[i];
+			uint32_t j = i;
+			while (j > 0 && rec_pos[j - 1] > p) {
+				rec_pos[j] = rec_pos[j - 1];
+				rec_val[j] = rec_val[j - 1];
+				--j;
+			}
+			rec_pos[j] = p;
+			rec_val[j] = v;
+		}
+		// SetTopBump replayed over the records (udbusortedsearcher.cpp:247-263)
+		uint32_t MinU = 1, MaxCount = 0, nchg = 0;
+		for (uint32_t k = 0; k < n; ++k) {
+			uint32_t v = rec_val[k];
+			if (a.bump_d != 0.0) {
+				uint32_t NewMin = (uint32_t)((double)v * a.bump_d);
+				if (NewMin > MinU && NewMin < MaxCount) {
+					MinU = NewMin;
+					chg_pos[nchg] = rec_pos[k];
+					chg_minu[nchg] = MinU;
+					++nchg;
+				}
+			}
+			MaxCount = v;
+		}
+		S.n_chg = nchg;
+		S.maxv = n ? rec_val[n - 1] : 0;
+		// countsort.cpp:12-24: NextValue = running max before its last increase
+		S.minv = (n >= 2 ? rec_val[n - 2] : 0) / 2;
+	}
+	__syncthreads();
+
+	KeepCursor kc{chg_pos, chg_minu, S.n_chg, S.minv, 0};
+
+	// ---- radix select of the k_max-th largest surviving count
+	for (uint32_t t = t0; t < t1; ++t) {
+		uint32_t u = u_get<WIDE>(U, t);
+		if (u && kc.keep(t, u))
+			atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t total = 0;
+		for (int b = 0; b < 256; ++b)
+			total += S.hist[b];
+		S.total = total;
+		S.take_all = total <= a.k_max;
+		S.vstar = 0;
+		S.m_eq = 0;
+		if (!S.take_all) {
+			uint32_t cum = 0;
+			for (int b = 255; b >= 0; --b) {
+				cum += S.hist[b];
+				if (cum >= a.k_max) {
+					S.bstar = (uint32_t)b;
+					S.above = cum - S.hist[b];
+					break;
+				}
+			}
+			if (!WIDE) {
+				S.vstar = S.bstar;
+				S.m_eq = a.k_max - S.above;
+			}
+		}
+	}
+	__syncthreads();
+	if (WIDE && !S.take_all) {
+		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+			S.hist[i] = 0;
+		__syncthreads();
+		kc.cur = 0;
+		const uint32_t bstar = S.bstar;
+		for (uint32_t t = t0; t < t1; ++t) {
+			uint32_t u = u_get<WIDE>(U, t);
+			if (u && (u >> 8) == bstar && kc.keep(t, u))
+				atomicAdd(&S.hist[u & 255], 1u);
+		}
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t cum = S.above;
+			for (int b = 255; b >= 0; --b) {
+				cum += S.hist[b];
+				if (cum >= a.k_max) {
+					S.vstar = (S.bstar << 8) | (uint32_t)b;
+					S.m_eq = a.k_max - (cum - S.hist[b]);
+					break;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	const uint32_t vstar = S.vstar, m_eq = S.m_eq;
+	const bool take_all = S.take_all != 0;
+
+	// ---- ties at the cut value are taken in ascending target order
+	uint32_t c_eq = 0;
+	if (!take_all) {
+		kc.cur = 0;
+		for (uint32_t t = t0; t < t1; ++t) {
+			uint32_t u = u_get<WIDE>(U, t);
+			if (u == vstar && u && kc.keep(t, u))
+				++c_eq;
+		}
+	}
+	uint32_t eq_rank = block_excl_scan_sum(c_eq, S.warp_tmp);
+	kc.cur = 0;
+	for (uint32_t t = t0; t < t1; ++t) {
+		uint32_t u = u_get<WIDE>(U, t);
+		if (!u || !kc.keep(t, u))
+			continue;
+		bool take = u > vstar;
+		if (!take && u == vstar)
+			take = (eq_rank++ < m_eq);
+		if (take) {
+			uint32_t slot = atomicAdd(&S.n_sel, 1u);
+			if (slot < RANK_KCAP)
+				S.sel[slot] = ((unsigned long long)(0xFFFFu - u) << 32) | t;
+		}
+	}
+	__syncthreads();
+	const uint32_t nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
+
+	// ---- descending U, ascending target within ties == ascending key; bitonic sort
+	uint32_t P2 = 1;
+	while (P2 < nsel)
+		P2 <<= 1;
+	for (uint32_t i = nsel + tid; i < P2; i += RANK_THREADS)
+		S.sel[i] = ~0ull;
+	__syncthreads();
+	for (uint32_t k = 2; k <= P2; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			for (uint32_t i = tid; i < P2; i += RANK_THREADS) {
+				uint32_t x = i ^ j;
+				if (x > i) {
+					unsigned long long A = S.sel[i], B = S.sel[x];
+					bool up = (i & k) == 0;
+					if ((A > B) == up) {
+						S.sel[i] = B;
+						S.sel[x] = A;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	for (uint32_t i = tid; i < nsel; i += RANK_THREADS) {
+		unsigned long long key = S.sel[i];
+		a.cand_t[(uint64_t)job * a.k_max + i] = (uint32_t)key;
+		if (a.cand_u)
+			a.cand_u[(uint64_t)job * a.k_max + i] = 0xFFFFu - (uint32_t)(key >> 32);
+	}
+	if (tid == 0) {
+		a.n_cand[job] = S.total;
+		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
+		a.n_emit[job] = nsel;
+	}
+}
+
+__global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
+{
+	extern __shared__ __align__(16) uint8_t rank_smem[];
+	RankShared &S = *(RankShared *)rank_smem;
+	uint8_t *U = rank_smem + ((sizeof(RankShared) + 15) & ~(size_t)15);
+	uint32_t *bitmap = (uint32_t *)(U + a.u_bytes);
+	uint32_t *rec_pos = bitmap + a.P.slots / 32;
+	uint32_t *rec_val = rec_pos + a.rec_cap;
+	uint32_t *chg_pos = rec_val + a.rec_cap;
+	uint32_t *chg_minu = chg_pos + a.rec_cap;
+	const uint32_t job = blockIdx.x;
+	if (job >= a.n_jobs)
+		return;
+	const uint32_t qi = job / a.strands;
+	const uint32_t L = (uint32_t)(a.q_off[qi + 1] - a.q_off[qi]);
+	const uint32_t npos = L >= a.P.word_length ? L - a.P.word_length + 1 : 0;
+	if (npos > 255)
+		rank_job<true>(a, job, S, U, bitmap, rec_pos, rec_val, chg_pos, chg_minu);
+	else
+		rank_job<false>(a, job, S, U, bitmap, rec_pos, rec_val, chg_pos, chg_minu);
+}
+
+inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, uint32_t slots, uint32_t rec_cap, uint32_t *u_bytes)
+{
+	size_t ub = (((size_t)n_seq * (wide ? 2 : 1)) + 15) & ~(size_t)15;
+	*u_bytes = (uint32_t)ub;
+	return ((sizeof(RankShared) + 15) & ~(size_t)15) + ub + slots / 8 + (size_t)4 * rec_cap * 4;
+}
+
+// Per-thread segment length (in targets) such that consecutive threads start in different
+// shared-memory banks: seg * width / 4 must be odd.
+inline uint32_t rank_segment(uint32_t n_seq, bool wide)
+{
+	uint32_t per = (n_seq + RANK_THREADS - 1) / RANK_THREADS;
+	uint32_t unit = wide ? 2 : 4;
+	uint32_t m = (per + unit - 1) / unit;
+	if (m == 0)
+		m = 1;
+	if ((m & 1) == 0)
+		++m;
+	return m * unit;
+}
+
+} // namespace usb
