@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- usearch_global hot-path throughput on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--reads R] [--db D] [--no-cpu-baseline]
+
+Workload (BASELINE.json metric): usearch_global of R=1M synthetic 250 bp reads against a
+D=100k x 1500 bp synthetic 16S-like DB at -id 0.97 -strand plus.  One "step" = one pass of the hot
+path (U-sort rank kernel + align kernel) over the R reads of this rank.  N > 1: every rank holds
+a replica of the index and its own R reads (weak scaling); after each step the packed hit records
+are gathered on rank 0 with NCCL.
+
+value  = reads/s with the reads already resident in HBM (CUDA-event time of the kernels, plus the
+         NCCL gather for N>1; max over ranks).
+e2e    = reads/s through usb_search_batch with pinned HOST buffers: H2D of the reads, kernels,
+         D2H of hits/paths/counters and the host-side grouping into HitMgr order, wall clock.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "query-seqs/sec usearch_global 1Mx250bp vs 100k-seq DB @97%id"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "usearch12")
+ORACLE_CLI = os.path.join(ROOT, "oracle", "_build", "uso_cli")
+
+
+def workload_name(a):
+    return "usearch_global %dx250bp synthetic reads vs %dx1500bp synthetic DB, -id 0.97 -strand plus" % (a.reads, a.db)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def _write_sample_fastas(tmp, db, db_off, reads, r_off, n_sample):
+    import synth_np
+    dbfa = os.path.join(tmp, "db.fa")
+    qfa = os.path.join(tmp, "q.fa")
+    q1 = os.path.join(tmp, "q1.fa")
+    synth_np.write_fasta(dbfa, db, db_off, "db")
+    synth_np.write_fasta(qfa, reads, r_off, "q", 0, n_sample)
+    synth_np.write_fasta(q1, reads, r_off, "q", 0, 1)
+    return dbfa, qfa, q1
+
+
+def _run(cmd):
+    t = time.perf_counter()
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t
+
+
+class ReferenceRunner:
+    """Times the reference's own CPU implementation (oracle/_ref/usearch12, the unmodified
+    binary built by oracle/Makefile.ref) -- or, where that binary is absent, the oracle port --
+    on a bounded sample of the same workload.  Search time excludes DB load like the reference's
+    own "Search time" log line (search.cpp:128-134): a .udb is prebuilt once and the wall time
+    of a 1-query run (load only) is subtracted."""
+
+    def __init__(self, db, db_off, reads, r_off, n_sample):
+        self.tmp = tempfile.mkdtemp(prefix="usb_ref_")
+        self.n = n_sample
+        self.dbfa, self.qfa, self.q1 = _write_sample_fastas(self.tmp, db, db_off, reads, r_off, n_sample)
+        self.cores = os.cpu_count() or 1
+        if os.path.exists(REF_BIN):
+            self.kind = "reference"
+            self.udb = os.path.join(self.tmp, "db.udb")
+            _run([REF_BIN, "-makeudb_usearch", self.dbfa, "-output", self.udb, "-quiet"])
+            self.t_load = min(self._ref(self.q1) for _ in range(2))
+        else:
+            self.kind = "port"
+            self.cores = 1
+            self.t_load = self._port(self.q1)
+
+    def _ref(self, q):
+        return _run([REF_BIN, "-usearch_global", q, "-db", self.udb, "-id", "0.97", "-strand", "plus", "-threads",
+                     str(self.cores), "-uc", os.path.join(self.tmp, "o.uc"), "-quiet"])
+
+    def _port(self, q):
+        o = os.path.join(self.tmp, "o")
+        return _run([ORACLE_CLI, "usearch_global", q, self.dbfa, "0.97", "plus", o + ".user", o + ".uc", o + ".b6"])
+
+    def step(self):
+        """-> reads/s of one sample pass."""
+        t = self._ref(self.qfa) if self.kind == "reference" else self._port(self.qfa)
+        return self.n / max(t - self.t_load, 1e-3)
+
+    def describe(self):
+        return "%d reads of the workload vs the full DB, %s, %d threads, DB load (%.1fs) subtracted" % (
+            self.n, "oracle/_ref/usearch12 -usearch_global" if self.kind == "reference" else "oracle/uso_cli (1 thread)",
+            self.cores, self.t_load)
+
+    def close(self):
+        shutil.rmtree(self.tmp, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reads", type=int, default=1000000)
+    ap.add_argument("--db", type=int, default=100000)
+    ap.add_argument("--ref-sample", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import synth_np
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        db, db_off = synth_np.gen_db(a.db, 1500, seed=4)
+        reads, r_off, _ = synth_np.gen_reads(db, db_off, a.ref_sample, 250, seed=1000)
+        rr = ReferenceRunner(db, db_off, reads, r_off, a.ref_sample)
+        for _ in range(a.warmup):
+            rr.step()
+        t0 = time.perf_counter()
+        vals = [rr.step() for _ in range(a.steps)]
+        wall = time.perf_counter() - t0
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "query-seqs/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall / max(1, a.steps),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic", "config": {"workload": workload_name(a)},
+                "cpu_baseline": {"value": v, "unit": "query-seqs/s", "cores": rr.cores, "kind": rr.kind,
+                                 "sample": rr.describe()},
+                "e2e": {"value": v, "unit": "query-seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        rr.close()
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from usearch12_b200 import capi
+    if not torch.cuda.is_available() or capi.lib().usb_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the usb200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- synthetic workload: replicated DB, per-rank reads (weak scaling)
+    t_gen = time.perf_counter()
+    db, db_off = synth_np.gen_db(a.db, 1500, seed=4)
+    reads, r_off, _ = synth_np.gen_reads(db, db_off, a.reads, 250, seed=1000 + rank)
+    t_gen = time.perf_counter() - t_gen
+    p = capi.default_params()
+    t_ix = time.perf_counter()
+    ix = capi.Index.__new__(capi.Index)
+    ix.params, ix._data, ix._off, ix.n_seq = p, db, db_off, a.db
+    import ctypes as C
+    h = C.c_void_p()
+    capi.check(capi.lib().usb_index_create(local_rank, C.byref(p), db.ctypes.data_as(C.c_void_p),
+                                           db_off.ctypes.data_as(C.c_void_p), a.db, C.byref(h)))
+    ix.handle = h
+    t_ix = time.perf_counter() - t_ix
+    s = capi.Searcher(ix, p)
+
+    # pinned host copies of the inputs for the end-to-end leg
+    pin_reads = torch.empty(reads.size, dtype=torch.uint8, pin_memory=True)
+    pin_reads.numpy()[:] = reads
+    pin_off = torch.empty(r_off.size, dtype=torch.int64, pin_memory=True)
+    pin_off.numpy()[:] = r_off.astype(np.int64)
+    h_reads, h_off = pin_reads.numpy(), pin_off.numpy().view(np.uint64)
+
+    cap_hits = a.reads * max(1, p.maxaccepts)
+    gather_src = torch.zeros(cap_hits * capi.HIT_DTYPE.itemsize, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gather_dst = None
+    if world > 1 and rank == 0:
+        gather_dst = [torch.empty_like(gather_src) for _ in range(world)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def device_step():
+        """kernels on the library stream (+ NCCL gather of the hit records); returns device ms."""
+        ms = s.run()
+        g_ms = 0.0
+        if world > 1:
+            s.export_hits_device(gather_src.data_ptr(), cap_hits)
+            ev0.record()
+            dist.gather(gather_src, gather_dst, dst=0)
+            ev1.record()
+            ev1.synchronize()
+            g_ms = ev0.elapsed_time(ev1)
+        return ms, g_ms
+
+    s.upload(h_reads, h_off)
+    for _ in range(a.warmup):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    launches0 = s.launch_count
+    t0 = time.perf_counter()
+    k1 = k2 = tot = gat = 0.0
+    for _ in range(a.steps):
+        ms, g_ms = device_step()
+        k1 += ms[0]
+        k2 += ms[1]
+        tot += ms[2] + g_ms
+        gat += g_ms
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = s.launch_count - launches0
+    ctr = s.counters()
+    res = s.download()
+
+    # ---- end to end through the C ABI with host buffers
+    s.search_packed(h_reads, h_off)
+    sync_all()
+    t1 = time.perf_counter()
+    for _ in range(a.steps):
+        r2 = s.search_packed(h_reads, h_off)
+        if world > 1:
+            s.export_hits_device(gather_src.data_ptr(), cap_hits)
+            dist.gather(gather_src, gather_dst, dst=0)
+    sync_all()
+    e2e_wall = time.perf_counter() - t1
+    launches += 2 * a.steps
+    h2d = int(reads.size + r_off.size * 8)
+    d2h = int(r2.hits.nbytes + r2.runs.nbytes + r2.qstat.nbytes + 4 * len(r2.qstat) + 24)
+
+    times = torch.tensor([tot, wall * 1000.0, e2e_wall * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    tot_ms, wall_ms, e2e_ms = [float(x) for x in times.cpu()]
+    total_reads = a.reads * world
+    value = total_reads * a.steps / (tot_ms / 1000.0)
+    e2e = total_reads * a.steps / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        qs = res.qstat
+        hits = res.hits
+        # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
+        b_k1 = 4.0 * ctr["postings"] + 8.0 * float(np.minimum(qs["n_cand"], s_kmax(p, a.db)).sum()) + float(reads.size)
+        b_k2 = float(qs["seq_bytes"].sum()) + float(np.ceil(qs["dp_cells"] / 2.0).sum()) + \
+            float((hits["ql"] + hits["tl"]).sum()) + 72.0 * len(hits) + 4.0 * len(res.runs)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = "k_align" if k2 >= k1 else "k_rank"
+        dom_ms = (k2 if k2 >= k1 else k1) / a.steps
+        dom_bytes = b_k2 if k2 >= k1 else b_k1
+        achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            if prof.get("workload") == workload_name(a):
+                traffic = prof.get(dom)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "query-seqs/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_gpu": a.reads, "db_seqs": a.db,
+                       "postings": int(ix.posting_count), "l2": "inputs larger than L2 (reads %d MB + postings %d MB)" % (
+                           reads.size >> 20, (4 * ix.posting_count) >> 20),
+                       "hit_rate": float(len(hits)) / a.reads, "gen_s": round(t_gen, 1), "index_build_s": round(t_ix, 1)},
+            "kernels_ms_per_step": {"k_rank": k1 / a.steps, "k_align": k2 / a.steps, "nccl_gather": gat / a.steps,
+                                    "wall": wall_ms / a.steps},
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "other": {"k_rank_GBps": b_k1 / (k1 / a.steps / 1000.0) / 1e9 if k1 else None,
+                                   "k_align_GBps": b_k2 / (k2 / a.steps / 1000.0) / 1e9 if k2 else None}},
+            "e2e": {"value": e2e, "unit": "query-seqs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            rr = ReferenceRunner(db, db_off, reads, r_off, min(a.ref_sample, a.reads))
+            v = rr.step()
+            line["cpu_baseline"] = {"value": v, "unit": "query-seqs/s", "cores": rr.cores, "kind": rr.kind,
+                                    "sample": rr.describe()}
+            rr.close()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def s_kmax(p, n_db):
+    if p.maxaccepts > 0 and p.maxrejects > 0:
+        return min(n_db, p.maxaccepts + p.maxrejects - 1)
+    return n_db
+
+
+if __name__ == "__main__":
+    sys.exit(main())
