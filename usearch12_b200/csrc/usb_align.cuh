@@ -60,7 +60,10 @@ struct AlignArgs {
 // (generic pointers: the code is the same).
 struct WarpWs {
 	uint8_t *A, *Ac;          // query letters (strand-adjusted) and their nt codes
-	uint8_t *B, *Bc;          // current target
+	const uint8_t *B;         // current target letters (global memory; only read for wildcards)
+	uint8_t *Bc;              // current target nt codes
+	uint32_t *A2, *An2;       // query packed 2 bits/base (16 per word) and wildcard flags (bit 0 of each pair)
+	uint32_t *B2, *Bn2;       // same for the target
 	uint8_t *cnt, *fil;       // seed table: words' occurrence counts (capped at 8), fill cursors
 	uint16_t *start, *pos;    // seed table CSR
 	int *Mrow, *Drow;         // DP rows; Mrow[-1] is addressable
@@ -77,8 +80,8 @@ inline __host__ __device__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u;
 
 inline __host__ __device__ uint32_t align_fast_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_words)
 {
-	return 2 * ql_cap + 2 * tl_cap + 2 * pad16(hsp_words) + pad16(2 * hsp_words) + pad16(2 * ql_cap) +
-	  2 * pad16(4 * (tl_cap + 8));
+	return 2 * ql_cap + tl_cap + 2 * pad16(ql_cap / 4 + 8) + 2 * pad16(tl_cap / 4 + 8) + 2 * pad16(hsp_words) +
+	  pad16(2 * hsp_words) + pad16(2 * ql_cap) + 2 * pad16(4 * (tl_cap + 8));
 }
 
 inline __host__ __device__ uint64_t align_slab_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_cap)
@@ -93,8 +96,11 @@ __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t 
 	uint8_t *p = fast;
 	w.A = p; p += a.ql_cap;
 	w.Ac = p; p += a.ql_cap;
-	w.B = p; p += a.tl_cap;
 	w.Bc = p; p += a.tl_cap;
+	w.A2 = (uint32_t *)p; p += pad16(a.ql_cap / 4 + 8);
+	w.An2 = (uint32_t *)p; p += pad16(a.ql_cap / 4 + 8);
+	w.B2 = (uint32_t *)p; p += pad16(a.tl_cap / 4 + 8);
+	w.Bn2 = (uint32_t *)p; p += pad16(a.tl_cap / 4 + 8);
 	w.cnt = p; p += pad16(a.P.hsp_words);
 	w.fil = p; p += pad16(a.P.hsp_words);
 	w.start = (uint16_t *)p; p += pad16(2 * a.P.hsp_words);
@@ -112,6 +118,16 @@ __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t 
 	w.cscore = (int *)s;
 }
 
+// %id identity of query position qp vs target position tp; raw letters are only needed (and the
+// target's only fetched from global memory) when a wildcard is involved.
+__device__ __forceinline__ bool pos_match(const WarpWs &w, uint32_t qp, uint32_t tp)
+{
+	const uint32_t ca = w.Ac[qp], cb = w.Bc[tp];
+	if ((ca | cb) < 4)
+		return ca == cb;
+	return chars_match_dev(w.A[qp], w.B[tp], ca, cb);
+}
+
 // ------------------------------------------------------------------ sequence staging
 __device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const uint8_t *Q, uint32_t L, uint32_t strand)
 {
@@ -123,26 +139,49 @@ __device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const 
 	}
 	w.LA = L;
 	__syncwarp();
+	const uint32_t nw16 = (L + 15) / 16;
+	for (uint32_t k = lane; k < nw16 + 2; k += 32) {
+		uint32_t v = 0, n = 0;
+		if (k < nw16)
+			for (uint32_t j = 0; j < 16 && 16 * k + j < L; ++j) {
+				const uint32_t c = w.Ac[16 * k + j];
+				v |= (c & 3) << (2 * j);
+				n |= (c >> 2) << (2 * j);
+			}
+		w.A2[k] = v & ~(n * 3);
+		w.An2[k] = n;
+	}
+	__syncwarp();
 }
 
 __device__ __forceinline__ void load_target(const AlignArgs &a, WarpWs &w, uint32_t t)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t L = a.db_len[t];
-	const uint4 *src = (const uint4 *)(a.db_seq + a.db_off[t]);
-	uint4 *dB = (uint4 *)w.B, *dC = (uint4 *)w.Bc;
+	w.B = a.db_seq + a.db_off[t];
+	const uint4 *src = (const uint4 *)w.B;
+	uint4 *dC = (uint4 *)w.Bc;
 	const uint32_t n16 = (L + 15) / 16;
-	for (uint32_t i = lane; i < n16; i += 32) {
-		uint4 v = __ldg(src + i);
-		uint32_t in[4] = {v.x, v.y, v.z, v.w}, out[4];
+	for (uint32_t i = lane; i < n16 + 2; i += 32) {
+		uint32_t p2 = 0, pn = 0;
+		if (i < n16) {
+			uint4 v = __ldg(src + i);
+			uint32_t in[4] = {v.x, v.y, v.z, v.w}, out[4];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			uint32_t x = in[k];
-			out[k] = nt_code(x & 0xff) | (nt_code((x >> 8) & 0xff) << 8) | (nt_code((x >> 16) & 0xff) << 16) |
-			  (nt_code(x >> 24) << 24);
+			for (int k = 0; k < 4; ++k) {
+				uint32_t x = in[k];
+#pragma unroll
+				for (int b = 0; b < 4; ++b) {
+					const uint32_t c = nt_code((x >> (8 * b)) & 0xff);
+					out[k] = b == 0 ? c : (out[k] | (c << (8 * b)));
+					p2 |= (c & 3) << (2 * (4 * k + b));
+					pn |= (c >> 2) << (2 * (4 * k + b));
+				}
+			}
+			dC[i] = make_uint4(out[0], out[1], out[2], out[3]);
 		}
-		dB[i] = v;
-		dC[i] = make_uint4(out[0], out[1], out[2], out[3]);
+		w.B2[i] = p2 & ~(pn * 3);
+		w.Bn2[i] = pn;
 	}
 	w.LB = L;
 	__syncwarp();
@@ -150,14 +189,18 @@ __device__ __forceinline__ void load_target(const AlignArgs &a, WarpWs &w, uint3
 
 // ------------------------------------------------------------------ a10: seed table of the query
 // HSP words treat wildcards as letter 0 and are never dropped (hspfinder.cpp:238-240).
-__device__ __forceinline__ uint32_t hsp_word_at(const uint8_t *codes, uint32_t p, uint32_t w)
+// 16 bases starting at position p of a packed array (two aligned word loads + funnel shift).
+__device__ __forceinline__ uint32_t ext16(const uint32_t *X, uint32_t p)
 {
-	uint32_t word = 0;
-	for (uint32_t i = 0; i < w; ++i) {
-		uint32_t c = codes[p + i];
-		word = (word << 2) | (c & 4 ? 0u : c);
-	}
-	return word;
+	const uint32_t k = p >> 4;
+	return __funnelshift_r(X[k], X[k + 1], (p & 15) * 2);
+}
+
+// The word value is only a table key shared by query and target side (first base in the low
+// bits); wildcards are packed as letter 0, so they behave like 'A' exactly as in the reference.
+__device__ __forceinline__ uint32_t hsp_word_at(const uint32_t *X2, uint32_t p, uint32_t hsp_words)
+{
+	return ext16(X2, p) & (hsp_words - 1);
 }
 
 // Builds cnt[word] = min(8, occurrences) and, per word, the first 8 query positions in query
@@ -178,7 +221,7 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 	for (uint32_t base = 0; base < nw; base += 32) {
 		const uint32_t p = base + lane;
 		const bool valid = p < nw;
-		const uint32_t word = valid ? hsp_word_at(w.Ac, p, hw) : (0x80000000u | lane);
+		const uint32_t word = valid ? hsp_word_at(w.A2, p, HW) : (0x80000000u | lane);
 		const uint32_t peers = __match_any_sync(USB_FULL, word);
 		if (valid && (peers & lanemask_lt()) == 0) {
 			uint32_t c = w.cnt[word] + __popc(peers);
@@ -209,7 +252,7 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 	for (uint32_t base = 0; base < nw; base += 32) {
 		const uint32_t p = base + lane;
 		const bool valid = p < nw;
-		const uint32_t word = valid ? hsp_word_at(w.Ac, p, hw) : (0x80000000u | lane);
+		const uint32_t word = valid ? hsp_word_at(w.A2, p, HW) : (0x80000000u | lane);
 		const uint32_t peers = __match_any_sync(USB_FULL, word);
 		uint32_t before = 0;
 		if (valid)
@@ -247,10 +290,11 @@ __device__ __forceinline__ bool is_global_hsp(uint32_t ALo, uint32_t BLo, uint32
 	return true;
 }
 
-// One lane extends one seed (ungappedblast.cpp:76-193): right from the seed's last letter, then
-// left from its first letter starting at the best right-extended score.  Scores are doubled.
-__device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
-  uint32_t MinLength, HspRec &out, uint32_t &Bhi_out)
+// One lane extends one seed letter by letter (ungappedblast.cpp:76-193): right from the seed's
+// last letter, then left from its first letter starting at the best right-extended score.
+// Scores are doubled.  Generic form, used when the score signs do not allow the packed walk.
+__device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
+  int &best_out, uint32_t &best_lo_out, uint32_t &best_hi_out)
 {
 	const DevParams &P = a.P;
 	const uint32_t LA = w.LA, LB = w.LB, hw = P.hspw;
@@ -290,12 +334,164 @@ __device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w,
 		} else if ((float)(best - score) > P.xdrop2)
 			break;
 	}
-	const uint32_t Length = best_hi - best_lo + 1;
-	const uint32_t Alo = best_lo - (BPos - APos) /* same diagonal */;
-	if (Length < MinLength || (float)best < P.minscore2)
+	best_out = best;
+	best_lo_out = best_lo;
+	best_hi_out = best_hi;
+}
+
+#define M55 0x55555555u
+
+// Same walk on the 2-bit packed sequences, 16 letters per step (requires match > 0 > mismatch;
+// wildcard pairs score 0).  Inside a run of matches the score only rises, so the run can be
+// applied at once: it cannot trigger the X-drop test and, if it ends above the best score, its
+// last letter is the new best end.  A wildcard pair changes nothing.  A mismatch is the only
+// step that can terminate.  The result is identical to extend_seed_bytes.
+__device__ __forceinline__ void extend_seed_packed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
+  int seed2, int &best_out, uint32_t &best_lo_out, uint32_t &best_hi_out)
+{
+	const DevParams &P = a.P;
+	const uint32_t LA = w.LA, LB = w.LB, hw = P.hspw;
+	int score = seed2, best = seed2;
+	uint32_t best_hi = BPos + hw - 1;
+	{
+		uint32_t pa = APos + hw, pb = BPos + hw;
+		for (;;) {
+			const uint32_t k = min(16u, min(LA - pa, LB - pb));
+			if (k == 0)
+				break;
+			const uint32_t x = ext16(w.A2, pa) ^ ext16(w.B2, pb);
+			const uint32_t wl = (ext16(w.An2, pa) | ext16(w.Bn2, pb)) & M55;
+			uint32_t stop = ((x | (x >> 1)) & M55) | wl; // pairs that are not a definite match
+			uint32_t done = 0;
+			bool term = false;
+			while (done < k) {
+				const uint32_t nxt = min(k, stop ? (uint32_t)(__ffs(stop) - 1) >> 1 : 16u);
+				if (nxt > done) {
+					score += (int)(nxt - done) * P.match2;
+					if (score > best) {
+						best = score;
+						best_hi = pb + nxt - 1;
+					}
+				}
+				if (nxt >= k)
+					break;
+				if (!((wl >> (2 * nxt)) & 1)) {
+					score += P.mismatch2;
+					if ((float)(best - score) > P.xdrop2) {
+						term = true;
+						break;
+					}
+				}
+				done = nxt + 1;
+				stop &= stop - 1;
+			}
+			if (term || k < 16)
+				break;
+			pa += 16;
+			pb += 16;
+		}
+	}
+	uint32_t best_lo = BPos;
+	score = best;
+	{
+		uint32_t pa = APos, pb = BPos; // letters available to the left
+		for (;;) {
+			const uint32_t k = min(16u, min(pa, pb));
+			if (k == 0)
+				break;
+			const uint32_t sh = 32 - 2 * k;
+			const uint32_t x = ext16(w.A2, pa - k) ^ ext16(w.B2, pb - k);
+			const uint32_t wl = ((ext16(w.An2, pa - k) | ext16(w.Bn2, pb - k)) & M55) << sh;
+			uint32_t stop = (((x | (x >> 1)) & M55) << sh) | wl; // nearest letter at bit 30
+			uint32_t done = 0;
+			bool term = false;
+			while (done < k) {
+				const uint32_t nxt = min(k, (uint32_t)__clz(stop) >> 1);
+				if (nxt > done) {
+					score += (int)(nxt - done) * P.match2;
+					if (score > best) {
+						best = score;
+						best_lo = pb - nxt;
+					}
+				}
+				if (nxt >= k)
+					break;
+				const uint32_t bit = 0x40000000u >> (2 * nxt);
+				if (!(wl & bit)) {
+					score += P.mismatch2;
+					if ((float)(best - score) > P.xdrop2) {
+						term = true;
+						break;
+					}
+				}
+				done = nxt + 1;
+				stop &= ~bit;
+			}
+			if (term || k < 16)
+				break;
+			pa -= 16;
+			pb -= 16;
+		}
+	}
+	best_out = best;
+	best_lo_out = best_lo;
+	best_hi_out = best_hi;
+}
+
+// Cheap exact rejection of a seed before walking it.  (1) IsGlobalHSP only depends on the
+// diagonal, which the extension never leaves.  (2) Look at the 16 letter pairs on each side of
+// the seed: if a side has so few possible matches that the X-drop walk must stop inside the
+// window (or the sequence ends there), the gain on that side is at most its match count; when
+// both sides are bounded like that and seed + bounds < MinGlobalHSPScore the seed can never be
+// accepted.  About 85 % of random seeds end here.
+__device__ __forceinline__ bool seed_may_pass(const AlignArgs &a, const WarpWs &w, uint32_t ap, uint32_t bp, int &seed2)
+{
+	const DevParams &P = a.P;
+	const uint32_t LA = w.LA, LB = w.LB, hw = P.hspw;
+	if (!is_global_hsp(ap, bp, LA, LB))
 		return false;
-	// Alo computed with wrap-around arithmetic is exact: the diagonal is fixed
-	if (!is_global_hsp(Alo, best_lo, LA, LB))
+	const uint32_t seedmask = M55 & (P.hsp_words - 1);
+	const uint32_t wseed = (ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask;
+	seed2 = P.match2 * (int)(hw - __popc(wseed));
+	const uint32_t ra = ap + hw, rb = bp + hw;
+	const uint32_t kR = min(16u, min(LA - ra, LB - rb));
+	uint32_t mR = 0;
+	if (kR) {
+		const uint32_t x = ext16(w.A2, ra) ^ ext16(w.B2, rb);
+		const uint32_t wl = ext16(w.An2, ra) | ext16(w.Bn2, rb);
+		const uint32_t mis = ((x | (x >> 1)) & ~wl & M55) & (kR == 16 ? M55 : ((1u << (2 * kR)) - 1));
+		mR = kR - __popc(mis);
+	}
+	const uint32_t kL = min(16u, min(ap, bp));
+	uint32_t mL = 0;
+	if (kL) {
+		const uint32_t x = ext16(w.A2, ap - kL) ^ ext16(w.B2, bp - kL);
+		const uint32_t wl = ext16(w.An2, ap - kL) | ext16(w.Bn2, bp - kL);
+		const uint32_t mis = ((x | (x >> 1)) & ~wl & M55) & (kL == 16 ? M55 : ((1u << (2 * kL)) - 1));
+		mL = kL - __popc(mis);
+	}
+	const bool deadR = kR < 16 || (float)(-((int)mR * P.match2 + (int)(16 - mR) * P.mismatch2)) > P.xdrop2;
+	const bool deadL = kL < 16 || (float)(-((int)mL * P.match2 + (int)(16 - mL) * P.mismatch2)) > P.xdrop2;
+	if (deadR && deadL && (float)(seed2 + (int)(mR + mL) * P.match2) < P.minscore2)
+		return false;
+	return true;
+}
+
+// Acceptance test of an extended seed (ungappedblast.cpp:172-193).
+__device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
+  int seed2, bool packed, uint32_t MinLength, HspRec &out, uint32_t &Bhi_out)
+{
+	int best;
+	uint32_t best_lo, best_hi;
+	if (packed)
+		extend_seed_packed(a, w, APos, BPos, seed2, best, best_lo, best_hi);
+	else
+		extend_seed_bytes(a, w, APos, BPos, best, best_lo, best_hi);
+	const uint32_t Length = best_hi - best_lo + 1;
+	const uint32_t Alo = best_lo - (BPos - APos); // same diagonal; wrap-around arithmetic is exact
+	if (Length < MinLength || (float)best < a.P.minscore2)
+		return false;
+	if (!is_global_hsp(Alo, best_lo, w.LA, w.LB))
 		return false;
 	out.Loi = Alo;
 	out.Loj = best_lo;
@@ -305,56 +501,125 @@ __device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w,
 	return true;
 }
 
-// Returns the number of ungapped HSPs written to w.ung (ungappedblast.cpp:45-210): target word
-// positions ascending; the first seed at a position that yields an acceptable HSP wins and the
-// scan jumps past that HSP.  32 positions are examined speculatively per step; the lowest lane
-// with an accepted HSP is the one the sequential scan would have reached first.
+// Returns the number of ungapped HSPs written to w.ung (ungappedblast.cpp:45-210).  Reference
+// order: target word positions ascending; at each, the query positions of that word in query
+// order; the first seed that yields an acceptable HSP wins and the scan jumps past that HSP.
+// Here: (1) all seeds of a stretch of the target are queued in exactly that order (the queue
+// lives in the DP row buffers, which are idle now), (2) every lane pre-filters queued seeds, (3)
+// the survivors are extended 32 at a time; an extension does not depend on scan history, so the
+// sequential result is: walk the survivors in order, accept the first acceptable one at or after
+// the current scan position, move the scan position past it, continue.
 __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLength)
 {
 	const uint32_t lane = lane_id();
-	const uint32_t hw = a.P.hspw;
+	const DevParams &P = a.P;
+	const uint32_t hw = P.hspw, HW = P.hsp_words;
 	const uint32_t LB = w.LB;
 	if (LB < 2 * hw)
 		return 0;
+	const bool packed = P.match2 > 0 && P.mismatch2 < 0;
 	const uint32_t nwordsB = LB - hw + 1;
+	uint32_t *q_b = (uint32_t *)(w.Mrow - 4);         // seed queue: target positions
+	uint16_t *q_a = (uint16_t *)w.Drow;               // seed queue: query positions
+	const uint32_t QCAP = a.tl_cap + 8;
 	uint32_t nung = 0;
-	uint32_t base = 0;
-	while (base < nwordsB) {
-		const uint32_t bpos = base + lane;
-		uint32_t na = 0, word = 0;
-		if (bpos < nwordsB) {
-			word = hsp_word_at(w.Bc, bpos, hw);
-			na = w.cnt[word];
+	uint32_t scan = 0;     // next target word position to queue
+	uint32_t cur = 0;      // sequential scan position (seeds before it are never examined)
+	while (scan < nwordsB) {
+		// (1) queue seeds of [scan, ...) in order
+		uint32_t nq = 0;
+		while (scan < nwordsB && nq + 256 <= QCAP) {
+			const uint32_t bpos = scan + lane;
+			uint32_t na = 0, word = 0;
+			if (bpos < nwordsB) {
+				word = hsp_word_at(w.B2, bpos, HW);
+				na = w.cnt[word];
+			}
+			uint32_t inc = na;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				uint32_t t = __shfl_up_sync(USB_FULL, inc, d);
+				if (lane >= (uint32_t)d)
+					inc += t;
+			}
+			const uint32_t tot = __shfl_sync(USB_FULL, inc, 31);
+			if (na) {
+				const uint32_t st = w.start[word];
+				uint32_t dst = nq + inc - na;
+				for (uint32_t i = 0; i < na; ++i, ++dst) {
+					q_b[dst] = bpos;
+					q_a[dst] = w.pos[st + i];
+				}
+			}
+			nq += tot;
+			scan += 32;
 		}
-		if (!__any_sync(USB_FULL, na != 0)) {
-			base += 32;
-			continue;
+		__syncwarp();
+		// (2) pre-filter, compacting survivors in place (order kept)
+		uint32_t ns = 0;
+		for (uint32_t s0 = 0; s0 < nq; s0 += 32) {
+			const uint32_t s = s0 + lane;
+			uint32_t bp = 0, ap = 0;
+			int seed2 = 0;
+			bool keep = false;
+			if (s < nq) {
+				bp = q_b[s];
+				ap = q_a[s];
+				keep = bp >= cur && (!packed || seed_may_pass(a, w, ap, bp, seed2));
+			}
+			const uint32_t km = __ballot_sync(USB_FULL, keep);
+			__syncwarp();
+			if (keep) {
+				const uint32_t d = ns + __popc(km & lanemask_lt());
+				q_b[d] = bp;
+				q_a[d] = (uint16_t)ap;
+			}
+			ns += __popc(km);
+			__syncwarp();
 		}
-		HspRec h;
-		uint32_t bhi = 0;
-		bool ok = false;
-		const uint32_t st = na ? w.start[word] : 0;
-		for (uint32_t i = 0; i < na && !ok; ++i)
-			ok = extend_seed(a, w, w.pos[st + i], bpos, MinLength, h, bhi);
-		const uint32_t okmask = __ballot_sync(USB_FULL, ok);
-		if (okmask == 0) {
-			base += 32;
-			continue;
+		// (3) extend survivors, 32 at a time, accepting in order
+		for (uint32_t s0 = 0; s0 < ns; s0 += 32) {
+			const uint32_t s = s0 + lane;
+			HspRec h;
+			h.Loi = h.Loj = h.Len = 0;
+			h.score2 = 0;
+			uint32_t bhi = 0, bp = 0;
+			bool ok = false;
+			if (s < ns) {
+				bp = q_b[s];
+				const uint32_t ap = q_a[s];
+				if (bp >= cur) {
+					int seed2 = 0;
+					if (packed) {
+						const uint32_t seedmask = M55 & (HW - 1);
+						seed2 = P.match2 * (int)(hw - __popc((ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask));
+					}
+					ok = extend_seed(a, w, ap, bp, seed2, packed, MinLength, h, bhi);
+				}
+			}
+			uint32_t okmask = __ballot_sync(USB_FULL, ok);
+			while (okmask) {
+				const int src = __ffs(okmask) - 1;
+				okmask &= okmask - 1;
+				const uint32_t sbp = __shfl_sync(USB_FULL, bp, src);
+				if (sbp < cur)
+					continue; // inside an HSP accepted a moment ago: the scan never sees this seed
+				HspRec g;
+				g.Loi = __shfl_sync(USB_FULL, h.Loi, src);
+				g.Loj = __shfl_sync(USB_FULL, h.Loj, src);
+				g.Len = __shfl_sync(USB_FULL, h.Len, src);
+				g.score2 = __shfl_sync(USB_FULL, h.score2, src);
+				const uint32_t sbhi = __shfl_sync(USB_FULL, bhi, src);
+				if (nung < a.hsp_cap) {
+					if (lane == 0)
+						w.ung[nung] = g;
+					++nung;
+				} else if (lane == 0)
+					atomicOr(&a.ctr->err, ERR_HSP_FULL);
+				cur = sbhi + 1;
+			}
 		}
-		const int src = __ffs(okmask) - 1;
-		h.Loi = __shfl_sync(USB_FULL, h.Loi, src);
-		h.Loj = __shfl_sync(USB_FULL, h.Loj, src);
-		h.Len = __shfl_sync(USB_FULL, h.Len, src);
-		h.score2 = __shfl_sync(USB_FULL, h.score2, src);
-		bhi = __shfl_sync(USB_FULL, bhi, src);
-		if (nung < a.hsp_cap) {
-			if (lane == 0)
-				w.ung[nung] = h;
-		} else if (lane == 0)
-			atomicOr(&a.ctr->err, ERR_HSP_FULL);
-		if (nung < a.hsp_cap)
-			++nung;
-		base = bhi + 1;
+		scan = max(scan, cur);
 	}
 	__syncwarp();
 	return nung;
@@ -708,7 +973,7 @@ __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, u
 			const uint32_t k = base + lane;
 			bool same = false;
 			if (k < h.Len)
-				same = chars_match_dev(w.A[h.Loi + k], w.B[h.Loj + k], w.Ac[h.Loi + k], w.Bc[h.Loj + k]);
+				same = pos_match(w, h.Loi + k, h.Loj + k);
 			TotalSame += __popc(__ballot_sync(USB_FULL, same));
 		}
 	}
@@ -793,7 +1058,7 @@ __device__ bool path_stats(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_
 		const uint32_t tp = tpos + __popc(tm & lanemask_lt());
 		bool same = false;
 		if (isM)
-			same = chars_match_dev(w.A[qp], w.B[tp], w.Ac[qp], w.Bc[tp]);
+			same = pos_match(w, qp, tp);
 		uint32_t prev = __shfl_up_sync(USB_FULL, ch, 1);
 		if (lane == 0)
 			prev = prev_carry;
@@ -964,12 +1229,12 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 	}
 }
 
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 1) k_align(const AlignArgs a)
+#define ALIGN_MAX_WARPS 16
+__global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_align(const AlignArgs a)
 {
 	extern __shared__ __align__(16) uint8_t align_smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t gw = blockIdx.x * WPB + warp;
+	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
 	uint8_t *slab = a.slab + (uint64_t)gw * a.slab_stride;
 	uint8_t *fast = a.fast_in_smem ? align_smem + (size_t)warp * a.fast_bytes : slab;
 	if (!a.fast_in_smem)
@@ -998,13 +1263,12 @@ struct ViterbiArgs {
 	int *score2;
 };
 
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 1) k_viterbi(const ViterbiArgs v)
+__global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_viterbi(const ViterbiArgs v)
 {
 	extern __shared__ __align__(16) uint8_t align_smem[];
 	const AlignArgs &a = v.base;
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t gw = blockIdx.x * WPB + warp;
+	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
 	uint8_t *slab = a.slab + (uint64_t)gw * a.slab_stride;
 	uint8_t *fast = a.fast_in_smem ? align_smem + (size_t)warp * a.fast_bytes : slab;
 	if (!a.fast_in_smem)

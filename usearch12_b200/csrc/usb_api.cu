@@ -442,13 +442,7 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 	g.tl_cap = pad16(max_tl + 16);
 	g.fast_bytes = align_fast_bytes(g.ql_cap, g.tl_cap, s->D.hsp_words);
 	const size_t budget = s->smem_optin > 1024 ? s->smem_optin - 1024 : 0;
-	const int choices[] = {16, 12, 8, 6, 4, 2, 1};
-	g.wpb = 0;
-	for (int c : choices)
-		if ((size_t)c * g.fast_bytes <= budget) {
-			g.wpb = c;
-			break;
-		}
+	g.wpb = (int)std::min<size_t>(ALIGN_MAX_WARPS, budget / g.fast_bytes);
 	g.fast_in_smem = g.wpb != 0;
 	if (!g.fast_in_smem)
 		g.wpb = 8;
@@ -471,28 +465,23 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 	return 0;
 }
 
-template <int WPB> static cudaError_t launch_align_t(const AlignArgs &a, const AlignGeom &g, cudaStream_t st)
+static cudaError_t launch_align(const AlignArgs &a, const AlignGeom &g, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(k_align<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+	cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
 	if (e != cudaSuccess)
 		return e;
-	k_align<WPB><<<g.grid, WPB * 32, g.smem, st>>>(a);
+	k_align<<<g.grid, g.wpb * 32, g.smem, st>>>(a);
 	return cudaGetLastError();
 }
 
-template <int WPB> static cudaError_t launch_viterbi_t(const ViterbiArgs &v, const AlignGeom &g, cudaStream_t st)
+static cudaError_t launch_viterbi(const ViterbiArgs &v, const AlignGeom &g, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(k_viterbi<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+	cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
 	if (e != cudaSuccess)
 		return e;
-	k_viterbi<WPB><<<g.grid, WPB * 32, g.smem, st>>>(v);
+	k_viterbi<<<g.grid, g.wpb * 32, g.smem, st>>>(v);
 	return cudaGetLastError();
 }
-
-#define DISPATCH_WPB(fn, wpb, ...)                                                                  \
-	((wpb) == 16 ? fn<16>(__VA_ARGS__) : (wpb) == 12 ? fn<12>(__VA_ARGS__) : (wpb) == 8 ? fn<8>(__VA_ARGS__) \
-	 : (wpb) == 6 ? fn<6>(__VA_ARGS__) : (wpb) == 4 ? fn<4>(__VA_ARGS__) : (wpb) == 2 ? fn<2>(__VA_ARGS__)   \
-	                                                                                 : fn<1>(__VA_ARGS__))
 
 static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_cap, AlignArgs &a)
 {
@@ -586,7 +575,7 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			a.runs = s->d_runs.p;
 			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
 			a.qstat = s->d_qstat.p;
-			CK(DISPATCH_WPB(launch_align_t, g.wpb, a, g, s->stream));
+			CK(launch_align(a, g, s->stream));
 			++s->launches;
 		}
 		CK(cudaEventRecord(s->ev[2], s->stream));
@@ -853,7 +842,7 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 		a.aligned = d_al.p;
 		a.hsp_out = hsp_out ? d_hsp.p : nullptr;
 		a.max_hsp = max_hsp;
-		cudaError_t e = DISPATCH_WPB(launch_align_t, g.wpb, a, g, s->stream);
+		cudaError_t e = launch_align(a, g, s->stream);
 		++s->launches;
 		if (e == cudaSuccess)
 			e = cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream);
@@ -934,7 +923,7 @@ extern "C" int usb_viterbi_batch(usb_searcher *s, const uint8_t *a_seq, const ui
 	fill_align_args(s, g, 64, v.base);
 	v.a_seq = d_a.p; v.a_off = d_ao.p; v.b_seq = d_b.p; v.b_off = d_bo.p; v.flags = d_f.p;
 	v.n = n; v.paths = d_paths.p; v.path_off = d_po.p; v.score2 = d_sc.p;
-	cudaError_t e = DISPATCH_WPB(launch_viterbi_t, g.wpb, v, g, s->stream);
+	cudaError_t e = launch_viterbi(v, g, s->stream);
 	++s->launches;
 	DevCounters c;
 	memset(&c, 0, sizeof c);
