@@ -40,3 +40,12 @@ for l in sorted(lines, key=lambda x: -x[5])[:top]:
     thr = l[4] / l[3] if l[3] else 0
     print("%-18s %5d %6.2f %6.2f %5.1f %7.2f %6.0f %6.0f  %s" % (l[0][:18], l[1], 100 * l[3] / tot_i, 100 * l[5] / tot_s, thr,
                                                         (l[6] / l[7]) if l[7] else 0, l[8], l[9], l[2][:90]))
+
+# optional: per-function share (ranges given as name:lo-hi after the top-N argument)
+if len(sys.argv) > 3:
+    for spec in sys.argv[3:]:
+        name, rng = spec.split(":")
+        lo, hi = map(int, rng.split("-"))
+        sel = [l for l in lines if l[0].startswith("usb_align") and lo <= l[1] <= hi]
+        print("%-14s inst %.1f%%  samples %.1f%%  avg thr %.1f" % (name, 100 * sum(l[3] for l in sel) / tot_i,
+              100 * sum(l[5] for l in sel) / tot_s, sum(l[4] for l in sel) / max(1, sum(l[3] for l in sel))))

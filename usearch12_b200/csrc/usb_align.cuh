@@ -52,6 +52,7 @@ struct AlignArgs {
 	uint32_t ql_cap, tl_cap;  // padded capacities of the per-warp sequence buffers
 	uint32_t hsp_cap;
 	uint32_t fast_bytes;      // per-warp bytes of the "fast" arrays
+	uint32_t scratch_bytes;   // per-warp bytes of the scratch union inside the fast arrays
 	uint32_t fast_in_smem;    // 1: fast arrays in shared memory, 0: in the slab
 	DevCounters *ctr;
 };
@@ -64,9 +65,10 @@ struct WarpWs {
 	uint8_t *Bc;              // current target nt codes
 	uint32_t *A2, *An2;       // query packed 2 bits/base (16 per word) and wildcard flags (bit 0 of each pair)
 	uint32_t *B2, *Bn2;       // same for the target
-	uint8_t *cnt, *fil;       // seed table: words' occurrence counts (capped at 8), fill cursors
+	uint8_t *cnt;             // seed table: words' occurrence counts (capped at 8)
 	uint16_t *start, *pos;    // seed table CSR
-	int *Mrow, *Drow;         // DP rows; Mrow[-1] is addressable
+	uint8_t *scratch;         // union: seed-table fill cursors | seed queues | DP rows (when they fit)
+	int *rows_slab;           // DP rows for rectangles too wide for the scratch (global memory)
 	// slab-only
 	uint8_t *TB;              // trace bytes, (LA+1) x (LB+1)
 	char *path, *rev;
@@ -80,15 +82,15 @@ inline __host__ __device__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u;
 
 inline __host__ __device__ uint32_t align_fast_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_words)
 {
-	return 2 * ql_cap + tl_cap + 2 * pad16(ql_cap / 4 + 8) + 2 * pad16(tl_cap / 4 + 8) + 2 * pad16(hsp_words) +
-	  pad16(2 * hsp_words) + pad16(2 * ql_cap) + 2 * pad16(4 * (tl_cap + 8));
+	return 2 * ql_cap + tl_cap + 2 * pad16(ql_cap / 4 + 8) + 2 * pad16(tl_cap / 4 + 8) + pad16(hsp_words) +
+	  pad16(2 * hsp_words) + pad16(2 * ql_cap);
 }
 
 inline __host__ __device__ uint64_t align_slab_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t hsp_cap)
 {
 	uint64_t tb = ((uint64_t)(ql_cap + 1) * (tl_cap + 1) + 15) & ~(uint64_t)15;
 	uint64_t path = pad16(ql_cap + tl_cap + 16);
-	return tb + 2 * path + (uint64_t)hsp_cap * (sizeof(HspRec) + 16);
+	return tb + 2 * path + (uint64_t)hsp_cap * (sizeof(HspRec) + 16) + 2 * pad16(4 * (tl_cap + 8));
 }
 
 __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t *fast, uint8_t *slab)
@@ -102,11 +104,9 @@ __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t 
 	w.B2 = (uint32_t *)p; p += pad16(a.tl_cap / 4 + 8);
 	w.Bn2 = (uint32_t *)p; p += pad16(a.tl_cap / 4 + 8);
 	w.cnt = p; p += pad16(a.P.hsp_words);
-	w.fil = p; p += pad16(a.P.hsp_words);
 	w.start = (uint16_t *)p; p += pad16(2 * a.P.hsp_words);
 	w.pos = (uint16_t *)p; p += pad16(2 * a.ql_cap);
-	w.Mrow = (int *)p + 4; p += pad16(4 * (a.tl_cap + 8));
-	w.Drow = (int *)p; p += pad16(4 * (a.tl_cap + 8));
+	w.scratch = p;
 	uint8_t *s = slab;
 	w.TB = s; s += ((uint64_t)(a.ql_cap + 1) * (a.tl_cap + 1) + 15) & ~(uint64_t)15;
 	w.path = (char *)s; s += pad16(a.ql_cap + a.tl_cap + 16);
@@ -115,7 +115,8 @@ __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t 
 	w.order = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
 	w.prev = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
 	w.chain = (uint32_t *)s; s += (uint64_t)a.hsp_cap * 4;
-	w.cscore = (int *)s;
+	w.cscore = (int *)s; s += (uint64_t)a.hsp_cap * 4;
+	w.rows_slab = (int *)s;
 }
 
 // %id identity of query position qp vs target position tp; raw letters are only needed (and the
@@ -210,7 +211,8 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t hw = a.P.hspw, HW = a.P.hsp_words;
-	uint32_t *cnt32 = (uint32_t *)w.cnt, *fil32 = (uint32_t *)w.fil;
+	uint8_t *fil = w.scratch;
+	uint32_t *cnt32 = (uint32_t *)w.cnt, *fil32 = (uint32_t *)fil;
 	for (uint32_t i = lane; i < HW / 4; i += 32) {
 		cnt32[i] = 0;
 		fil32[i] = 0;
@@ -256,14 +258,14 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 		const uint32_t peers = __match_any_sync(USB_FULL, word);
 		uint32_t before = 0;
 		if (valid)
-			before = w.fil[word];
+			before = fil[word];
 		__syncwarp();
 		if (valid) {
 			uint32_t slot = before + __popc(peers & lanemask_lt());
 			if (slot < 8)
 				w.pos[w.start[word] + slot] = (uint16_t)p;
 			if ((peers & lanemask_lt()) == 0)
-				w.fil[word] = (uint8_t)min(before + __popc(peers), 8u);
+				fil[word] = (uint8_t)min(before + __popc(peers), 8u);
 		}
 		__syncwarp();
 	}
@@ -501,14 +503,71 @@ __device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w,
 	return true;
 }
 
+// Seed queues inside the per-warp scratch: q1 = target word positions that have seeds, q2 =
+// seeds that survived the pre-filter, both in reference scan order.
+#define SEEDQ1 384
+#define SEEDQ2 512
+#define SEED_SCRATCH_BYTES (8 * SEEDQ1 + 6 * SEEDQ2)
+
+// Extends the queued survivors 32 at a time and accepts in order (see ungapped_blast).
+__device__ __forceinline__ void extend_queued(const AlignArgs &a, WarpWs &w, const uint32_t *q2b, const uint16_t *q2a,
+  uint32_t n2, bool packed, uint32_t MinLength, uint32_t &cur, uint32_t &nung)
+{
+	const uint32_t lane = lane_id();
+	const DevParams &P = a.P;
+	for (uint32_t s0 = 0; s0 < n2; s0 += 32) {
+		const uint32_t s = s0 + lane;
+		HspRec h;
+		h.Loi = h.Loj = h.Len = 0;
+		h.score2 = 0;
+		uint32_t bhi = 0, bp = 0;
+		bool ok = false;
+		if (s < n2) {
+			bp = q2b[s];
+			const uint32_t ap = q2a[s];
+			if (bp >= cur) {
+				int seed2 = 0;
+				if (packed) {
+					const uint32_t seedmask = M55 & (P.hsp_words - 1);
+					seed2 = P.match2 * (int)(P.hspw - __popc((ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask));
+				}
+				ok = extend_seed(a, w, ap, bp, seed2, packed, MinLength, h, bhi);
+			}
+		}
+		uint32_t okmask = __ballot_sync(USB_FULL, ok);
+		while (okmask) {
+			const int src = __ffs(okmask) - 1;
+			okmask &= okmask - 1;
+			const uint32_t sbp = __shfl_sync(USB_FULL, bp, src);
+			if (sbp < cur)
+				continue; // inside an HSP accepted a moment ago: the scan never sees this seed
+			HspRec g;
+			g.Loi = __shfl_sync(USB_FULL, h.Loi, src);
+			g.Loj = __shfl_sync(USB_FULL, h.Loj, src);
+			g.Len = __shfl_sync(USB_FULL, h.Len, src);
+			g.score2 = __shfl_sync(USB_FULL, h.score2, src);
+			const uint32_t sbhi = __shfl_sync(USB_FULL, bhi, src);
+			if (nung < a.hsp_cap) {
+				if (lane == 0)
+					w.ung[nung] = g;
+				++nung;
+			} else if (lane == 0)
+				atomicOr(&a.ctr->err, ERR_HSP_FULL);
+			cur = sbhi + 1;
+		}
+	}
+	__syncwarp();
+}
+
 // Returns the number of ungapped HSPs written to w.ung (ungappedblast.cpp:45-210).  Reference
 // order: target word positions ascending; at each, the query positions of that word in query
 // order; the first seed that yields an acceptable HSP wins and the scan jumps past that HSP.
-// Here: (1) all seeds of a stretch of the target are queued in exactly that order (the queue
-// lives in the DP row buffers, which are idle now), (2) every lane pre-filters queued seeds, (3)
-// the survivors are extended 32 at a time; an extension does not depend on scan history, so the
-// sequential result is: walk the survivors in order, accept the first acceptable one at or after
-// the current scan position, move the scan position past it, continue.
+// Here: (1) the target positions whose word occurs in the query are queued in order (one ballot
+// per 32 positions), (2) every lane takes one queued position and pre-filters its seeds; the
+// survivors are queued in the same (position, query order) order, (3) survivors are extended 32
+// at a time.  An extension does not depend on scan history, so the sequential result is: walk
+// the survivors in order, accept the first acceptable one at or after the current scan
+// position, move the scan position past it, continue.
 __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLength)
 {
 	const uint32_t lane = lane_id();
@@ -519,106 +578,68 @@ __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLe
 		return 0;
 	const bool packed = P.match2 > 0 && P.mismatch2 < 0;
 	const uint32_t nwordsB = LB - hw + 1;
-	uint32_t *q_b = (uint32_t *)(w.Mrow - 4);         // seed queue: target positions
-	uint16_t *q_a = (uint16_t *)w.Drow;               // seed queue: query positions
-	const uint32_t QCAP = a.tl_cap + 8;
+	uint32_t *q1b = (uint32_t *)w.scratch;
+	uint32_t *q1s = q1b + SEEDQ1;
+	uint32_t *q2b = q1s + SEEDQ1;
+	uint16_t *q2a = (uint16_t *)(q2b + SEEDQ2);
 	uint32_t nung = 0;
-	uint32_t scan = 0;     // next target word position to queue
-	uint32_t cur = 0;      // sequential scan position (seeds before it are never examined)
+	uint32_t scan = 0; // next target word position to queue
+	uint32_t cur = 0;  // sequential scan position (seeds before it are never examined)
 	while (scan < nwordsB) {
-		// (1) queue seeds of [scan, ...) in order
-		uint32_t nq = 0;
-		while (scan < nwordsB && nq + 256 <= QCAP) {
+		uint32_t n1 = 0;
+		while (scan < nwordsB && n1 + 32 <= SEEDQ1) {
 			const uint32_t bpos = scan + lane;
 			uint32_t na = 0, word = 0;
 			if (bpos < nwordsB) {
 				word = hsp_word_at(w.B2, bpos, HW);
 				na = w.cnt[word];
 			}
-			uint32_t inc = na;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				uint32_t t = __shfl_up_sync(USB_FULL, inc, d);
-				if (lane >= (uint32_t)d)
-					inc += t;
-			}
-			const uint32_t tot = __shfl_sync(USB_FULL, inc, 31);
+			const uint32_t m = __ballot_sync(USB_FULL, na != 0);
 			if (na) {
-				const uint32_t st = w.start[word];
-				uint32_t dst = nq + inc - na;
-				for (uint32_t i = 0; i < na; ++i, ++dst) {
-					q_b[dst] = bpos;
-					q_a[dst] = w.pos[st + i];
-				}
+				const uint32_t d = n1 + __popc(m & lanemask_lt());
+				q1b[d] = bpos;
+				q1s[d] = (uint32_t)w.start[word] | (na << 16);
 			}
-			nq += tot;
+			n1 += __popc(m);
 			scan += 32;
 		}
 		__syncwarp();
-		// (2) pre-filter, compacting survivors in place (order kept)
-		uint32_t ns = 0;
-		for (uint32_t s0 = 0; s0 < nq; s0 += 32) {
-			const uint32_t s = s0 + lane;
-			uint32_t bp = 0, ap = 0;
-			int seed2 = 0;
-			bool keep = false;
-			if (s < nq) {
-				bp = q_b[s];
-				ap = q_a[s];
-				keep = bp >= cur && (!packed || seed_may_pass(a, w, ap, bp, seed2));
+		uint32_t n2 = 0;
+		for (uint32_t e0 = 0; e0 < n1; e0 += 32) {
+			if (n2 + 256 > SEEDQ2) {
+				extend_queued(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
+				n2 = 0;
 			}
-			const uint32_t km = __ballot_sync(USB_FULL, keep);
-			__syncwarp();
-			if (keep) {
-				const uint32_t d = ns + __popc(km & lanemask_lt());
-				q_b[d] = bp;
-				q_a[d] = (uint16_t)ap;
+			const uint32_t e = e0 + lane;
+			uint32_t bp = 0, st = 0, na = 0;
+			if (e < n1) {
+				bp = q1b[e];
+				const uint32_t v = q1s[e];
+				st = v & 0xffff;
+				na = bp >= cur ? v >> 16 : 0;
 			}
-			ns += __popc(km);
-			__syncwarp();
+			uint32_t keepbits = 0;
+			for (uint32_t i = 0; i < na; ++i) {
+				int seed2;
+				if (!packed || seed_may_pass(a, w, w.pos[st + i], bp, seed2))
+					keepbits |= 1u << i;
+			}
+			// exclusive prefix of the per-lane survivor counts (0..8) from four ballots
+			const uint32_t c = __popc(keepbits), lt = lanemask_lt();
+			const uint32_t b0 = __ballot_sync(USB_FULL, c & 1), b1 = __ballot_sync(USB_FULL, c & 2),
+			               b2 = __ballot_sync(USB_FULL, c & 4), b3 = __ballot_sync(USB_FULL, c & 8);
+			uint32_t d = n2 + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+			while (keepbits) {
+				const uint32_t i = __ffs(keepbits) - 1;
+				keepbits &= keepbits - 1;
+				q2b[d] = bp;
+				q2a[d] = w.pos[st + i];
+				++d;
+			}
+			n2 += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
 		}
-		// (3) extend survivors, 32 at a time, accepting in order
-		for (uint32_t s0 = 0; s0 < ns; s0 += 32) {
-			const uint32_t s = s0 + lane;
-			HspRec h;
-			h.Loi = h.Loj = h.Len = 0;
-			h.score2 = 0;
-			uint32_t bhi = 0, bp = 0;
-			bool ok = false;
-			if (s < ns) {
-				bp = q_b[s];
-				const uint32_t ap = q_a[s];
-				if (bp >= cur) {
-					int seed2 = 0;
-					if (packed) {
-						const uint32_t seedmask = M55 & (HW - 1);
-						seed2 = P.match2 * (int)(hw - __popc((ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask));
-					}
-					ok = extend_seed(a, w, ap, bp, seed2, packed, MinLength, h, bhi);
-				}
-			}
-			uint32_t okmask = __ballot_sync(USB_FULL, ok);
-			while (okmask) {
-				const int src = __ffs(okmask) - 1;
-				okmask &= okmask - 1;
-				const uint32_t sbp = __shfl_sync(USB_FULL, bp, src);
-				if (sbp < cur)
-					continue; // inside an HSP accepted a moment ago: the scan never sees this seed
-				HspRec g;
-				g.Loi = __shfl_sync(USB_FULL, h.Loi, src);
-				g.Loj = __shfl_sync(USB_FULL, h.Loj, src);
-				g.Len = __shfl_sync(USB_FULL, h.Len, src);
-				g.score2 = __shfl_sync(USB_FULL, h.score2, src);
-				const uint32_t sbhi = __shfl_sync(USB_FULL, bhi, src);
-				if (nung < a.hsp_cap) {
-					if (lane == 0)
-						w.ung[nung] = g;
-					++nung;
-				} else if (lane == 0)
-					atomicOr(&a.ctr->err, ERR_HSP_FULL);
-				cur = sbhi + 1;
-			}
-		}
+		__syncwarp();
+		extend_queued(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
 		scan = max(scan, cur);
 	}
 	__syncwarp();
@@ -756,7 +777,10 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 	dhi += P.band;
 	dhi = min(dhi, LA + LB - 1);
 	const uint64_t W = (uint64_t)LB + 1;
-	int *Mrow = w.Mrow, *Drow = w.Drow;
+	// rows in shared memory when the rectangle is narrow enough, else in the global slab
+	const bool rows_fit = 8u * (LB + 8) <= a.scratch_bytes;
+	int *Mrow = (rows_fit ? (int *)w.scratch : w.rows_slab) + 4;
+	int *Drow = Mrow + LB + 4;
 	uint8_t *TB = w.TB;
 	for (uint32_t j = lane; j <= LB + 1; j += 32) {
 		Mrow[(int)j - 1] = USB_NEG;

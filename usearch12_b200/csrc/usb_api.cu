@@ -430,7 +430,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 
 struct AlignGeom {
 	int wpb;
-	uint32_t ql_cap, tl_cap, fast_bytes, fast_in_smem;
+	uint32_t ql_cap, tl_cap, fast_bytes, scratch_bytes, fast_in_smem;
 	size_t smem;
 	uint64_t slab_stride;
 	uint32_t n_warps, grid;
@@ -440,8 +440,17 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 {
 	g.ql_cap = pad16(max_ql + 16);
 	g.tl_cap = pad16(max_tl + 16);
-	g.fast_bytes = align_fast_bytes(g.ql_cap, g.tl_cap, s->D.hsp_words);
+	// fixed per-warp arrays + a scratch union (seed-table fill cursors | seed queues | DP rows).
+	// The scratch gets whatever is left of a 1/16 share of shared memory, never less than the
+	// seed queues need; rectangles whose DP rows do not fit use the global slab.
+	const uint32_t fixed = align_fast_bytes(g.ql_cap, g.tl_cap, s->D.hsp_words);
 	const size_t budget = s->smem_optin > 1024 ? s->smem_optin - 1024 : 0;
+	const uint32_t min_scratch = std::max<uint32_t>(SEED_SCRATCH_BYTES, pad16(s->D.hsp_words));
+	uint32_t share = (uint32_t)((budget / ALIGN_MAX_WARPS) & ~(size_t)15);
+	g.scratch_bytes = share > fixed + min_scratch ? share - fixed : min_scratch;
+	g.scratch_bytes = std::min<uint32_t>(g.scratch_bytes, 8u * (g.tl_cap + 8));
+	g.scratch_bytes = std::max<uint32_t>(g.scratch_bytes, min_scratch);
+	g.fast_bytes = fixed + g.scratch_bytes;
 	g.wpb = (int)std::min<size_t>(ALIGN_MAX_WARPS, budget / g.fast_bytes);
 	g.fast_in_smem = g.wpb != 0;
 	if (!g.fast_in_smem)
@@ -499,6 +508,7 @@ static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_ca
 	a.tl_cap = g.tl_cap;
 	a.hsp_cap = hsp_cap;
 	a.fast_bytes = g.fast_bytes;
+	a.scratch_bytes = g.scratch_bytes;
 	a.fast_in_smem = g.fast_in_smem;
 	a.ctr = s->d_ctr.p;
 }
