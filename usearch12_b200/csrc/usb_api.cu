@@ -110,7 +110,7 @@ struct usb_index {
 	HostIndex H;
 	DevBuf<uint8_t> d_seqs;
 	DevBuf<uint64_t> d_seq_off, d_row_off;
-	DevBuf<uint32_t> d_seq_len, d_postings;
+	DevBuf<uint32_t> d_seq_len, d_postings, d_row_size;
 };
 
 struct usb_result {
@@ -228,7 +228,7 @@ extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *
 	const HostIndex &H = ix->H;
 	if ((rc = ix->d_seqs.reserve(H.seqs.size())) || (rc = ix->d_seq_off.reserve(H.seq_off.size())) ||
 	    (rc = ix->d_seq_len.reserve(H.seq_len.size() + 1)) || (rc = ix->d_row_off.reserve(H.row_off.size())) ||
-	    (rc = ix->d_postings.reserve(H.postings.size()))) {
+	    (rc = ix->d_postings.reserve(H.postings.size())) || (rc = ix->d_row_size.reserve(H.row_size.size()))) {
 		usb_index_free(ix);
 		return rc;
 	}
@@ -238,6 +238,7 @@ extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *
 		CK(cudaMemcpy(ix->d_seq_len.p, H.seq_len.data(), H.seq_len.size() * 4, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
 	*out = ix;
 	return 0;
 }
@@ -252,18 +253,19 @@ extern "C" void usb_index_free(usb_index *ix)
 	ix->d_seq_len.release();
 	ix->d_row_off.release();
 	ix->d_postings.release();
+	ix->d_row_size.release();
 	delete ix;
 }
 
 extern "C" uint32_t usb_index_seq_count(const usb_index *ix) { return ix ? ix->H.n_seq : 0; }
-extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->H.row_off[ix->H.slots] : 0; }
+extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->H.n_postings : 0; }
 
 extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size)
 {
 	if (!ix || word >= ix->H.slots)
 		return fail(USB_EINVAL, "usb_index_row: bad word %u", word);
 	*row = ix->H.postings.data() + ix->H.row_off[word];
-	*size = (uint32_t)(ix->H.row_off[word + 1] - ix->H.row_off[word]);
+	*size = ix->H.row_size[word];
 	return 0;
 }
 
@@ -400,6 +402,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	a.strands = strands;
 	a.row_off = ix->d_row_off.p;
 	a.postings = ix->d_postings.p;
+	a.row_size = ix->d_row_size.p;
 	a.n_seq = N;
 	a.k_max = k_max;
 	a.cand_t = s->d_cand_t.p;

@@ -149,7 +149,9 @@ void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_s
 	});
 	// row offsets; each worker's counts become its write cursor inside the row
 	ix.row_off.assign((size_t)ix.slots + 1, 0);
+	ix.row_size.assign(ix.slots, 0);
 	uint64_t total = 0;
+	ix.n_postings = 0;
 	for (uint32_t word = 0; word < ix.slots; ++word) {
 		ix.row_off[word] = total;
 		for (unsigned k = 0; k < T; ++k) {
@@ -157,9 +159,12 @@ void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_s
 			W[k].counts[word] = (uint32_t)(total - ix.row_off[word]);
 			total += c;
 		}
+		ix.row_size[word] = (uint32_t)(total - ix.row_off[word]);
+		ix.n_postings += ix.row_size[word];
+		total = (total + 3) & ~(uint64_t)3; // 16-byte aligned rows for vector loads
 	}
 	ix.row_off[ix.slots] = total;
-	ix.postings.assign(total + 4, 0);
+	ix.postings.assign(total + 4, 0xffffffffu);
 	// pass 2: fill (targets ascending within each row because workers own ascending ranges)
 	run([&](unsigned k) {
 		Worker &w = W[k];

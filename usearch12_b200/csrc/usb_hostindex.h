@@ -19,8 +19,10 @@ struct HostIndex {
 	std::vector<uint8_t> seqs;          // masked letters, each target padded to a 16-byte boundary
 	std::vector<uint64_t> seq_off;      // n_seq+1 padded offsets (multiples of 16)
 	std::vector<uint32_t> seq_len;      // n_seq true lengths
-	std::vector<uint64_t> row_off;      // slots+1
+	std::vector<uint64_t> row_off;      // slots+1; every row starts on a 16-byte boundary (multiple of 4 entries)
+	std::vector<uint32_t> row_size;     // slots; true row lengths (m_Sizes[word])
 	std::vector<uint32_t> postings;     // target indexes, ascending per row, each target once per row
+	uint64_t n_postings = 0;            // sum of row_size
 	uint32_t max_len = 0;
 };
 

@@ -9,15 +9,18 @@
 //   a6  CountSortOrderDesc + NextValue/2    countsort.cpp:6-108
 //
 // Design: the per-target counters live in shared memory (1 byte per target when the query has
-// <= 255 word positions, 2 bytes otherwise), so U never touches HBM; posting rows are streamed
-// with coalesced 128-byte warp loads and counted with shared-memory atomics on packed 32-bit
-// words.  The two order-dependent filters are evaluated exactly from the strict prefix maxima of
-// U ("records"): records are few, so one thread replays the
-// threshold evolution over them and every other thread filters its own contiguous target
-// segment against the threshold in force at that position.  Only the first k_max candidates of
-// the descending stable order are materialised (the Terminator can never look further than
-// maxaccepts+maxrejects-1 candidates): a radix-select on U finds the cut value, ties at the cut
-// are taken in ascending target order with a block scan, and the <= k_max keys are bitonic-sorted.
+// <= 255 word positions, 2 bytes otherwise), so U never touches HBM.  Posting rows start on
+// 16-byte boundaries and are streamed with 128-bit loads, four in flight per lane (64 KB in
+// flight per SM), and counted with shared-memory atomics on packed 32-bit words.
+// The two order-dependent filters are evaluated exactly from the strict prefix maxima of U
+// ("records"): records are few, so one thread replays the
+// threshold evolution over them; every thread then filters its own contiguous target segment
+// against the threshold in force there, four (two) counters per instruction with the byte
+// (halfword) SIMD compares.  Survivors (TopOrder) are usually a few hundred: they are collected
+// unordered and bitonic-sorted by (U descending, target ascending), which is the reference's
+// stable counting-sort order.  Only when more than RANK_KCAP targets survive does the kernel fall
+// back to a radix-select of the first k_max of that order (the Terminator can never look
+// further than maxaccepts+maxrejects-1 candidates).
 #pragma once
 #include "usb_dev.cuh"
 
@@ -34,7 +37,8 @@ struct RankArgs {
 	const uint64_t *q_off;     // n_q + 1
 	uint32_t n_jobs;           // n_q * strands
 	uint32_t strands;          // 1 or 2
-	const uint64_t *row_off;   // slots + 1
+	const uint64_t *row_off;   // slots + 1, multiples of 4
+	const uint32_t *row_size;  // slots
 	const uint32_t *postings;
 	uint32_t n_seq;
 	uint32_t k_max;            // <= RANK_KCAP
@@ -53,7 +57,7 @@ struct RankArgs {
 struct RankShared {
 	uint32_t n_rows, row_cur, n_rec, n_chg;
 	uint32_t maxv, minv, total, vstar, m_eq, n_sel, bstar, above;
-	uint32_t take_all, n_post, pad1, pad2;
+	uint32_t take_all, n_post, n_surv, pad2;
 	uint32_t warp_tmp[32];
 	uint32_t hist[256];
 	uint32_t rows[RANK_THREADS];
@@ -144,14 +148,131 @@ __device__ __forceinline__ void u_inc(uint32_t *U32, uint32_t t)
 struct KeepCursor {
 	const uint32_t *chg_pos, *chg_minu;
 	uint32_t n_chg, minv, cur;
-	__device__ __forceinline__ bool keep(uint32_t t, uint32_t u)
+	__device__ __forceinline__ uint32_t minu(uint32_t t)
 	{
 		while (cur < n_chg && chg_pos[cur] < t)
 			++cur;
-		uint32_t mu = cur == 0 ? 1u : chg_minu[cur - 1];
-		return u >= mu && u >= minv;
+		return cur == 0 ? 1u : chg_minu[cur - 1];
 	}
+	__device__ __forceinline__ bool keep(uint32_t t, uint32_t u) { return u >= minu(t) && u >= minv; }
 };
+
+__device__ __forceinline__ unsigned long long rank_key(uint32_t u, uint32_t t)
+{
+	return ((unsigned long long)(0xFFFFu - u) << 32) | t;
+}
+
+// ascending bitonic sort of sel[0..n) (n <= RANK_KCAP) by the whole CTA
+__device__ void block_sort_keys(unsigned long long *sel, uint32_t n)
+{
+	const uint32_t tid = threadIdx.x;
+	uint32_t P2 = 1;
+	while (P2 < n)
+		P2 <<= 1;
+	for (uint32_t i = n + tid; i < P2; i += RANK_THREADS)
+		sel[i] = ~0ull;
+	__syncthreads();
+	for (uint32_t k = 2; k <= P2; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			for (uint32_t i = tid; i < P2; i += RANK_THREADS) {
+				const uint32_t x = i ^ j;
+				if (x > i) {
+					const unsigned long long A = sel[i], B = sel[x];
+					if ((A > B) == ((i & k) == 0)) {
+						sel[i] = B;
+						sel[x] = A;
+					}
+				}
+			}
+			__syncthreads();
+		}
+}
+
+// Rare path: more than RANK_KCAP survivors.  Radix-select the k_max-th largest surviving count,
+// take ties at the cut in ascending target order (block scan), leave the selection in S.sel.
+template <bool WIDE>
+__device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const uint8_t *U, KeepCursor kc, uint32_t t0,
+  uint32_t t1)
+{
+	const uint32_t tid = threadIdx.x;
+	for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+		S.hist[i] = 0;
+	if (tid == 0)
+		S.n_sel = 0;
+	__syncthreads();
+	kc.cur = 0;
+	for (uint32_t t = t0; t < t1; ++t) {
+		const uint32_t u = u_get<WIDE>(U, t);
+		if (u && kc.keep(t, u))
+			atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t cum = 0;
+		for (int b = 255; b >= 0; --b) {
+			cum += S.hist[b];
+			if (cum >= a.k_max) {
+				S.bstar = (uint32_t)b;
+				S.above = cum - S.hist[b];
+				break;
+			}
+		}
+		if (!WIDE) {
+			S.vstar = S.bstar;
+			S.m_eq = a.k_max - S.above;
+		}
+	}
+	__syncthreads();
+	if (WIDE) {
+		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+			S.hist[i] = 0;
+		__syncthreads();
+		kc.cur = 0;
+		const uint32_t bstar = S.bstar;
+		for (uint32_t t = t0; t < t1; ++t) {
+			const uint32_t u = u_get<WIDE>(U, t);
+			if (u && (u >> 8) == bstar && kc.keep(t, u))
+				atomicAdd(&S.hist[u & 255], 1u);
+		}
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t cum = S.above;
+			for (int b = 255; b >= 0; --b) {
+				cum += S.hist[b];
+				if (cum >= a.k_max) {
+					S.vstar = (S.bstar << 8) | (uint32_t)b;
+					S.m_eq = a.k_max - (cum - S.hist[b]);
+					break;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	const uint32_t vstar = S.vstar, m_eq = S.m_eq;
+	uint32_t c_eq = 0;
+	kc.cur = 0;
+	for (uint32_t t = t0; t < t1; ++t) {
+		const uint32_t u = u_get<WIDE>(U, t);
+		if (u == vstar && u && kc.keep(t, u))
+			++c_eq;
+	}
+	uint32_t eq_rank = block_excl_scan_sum(c_eq, S.warp_tmp);
+	kc.cur = 0;
+	for (uint32_t t = t0; t < t1; ++t) {
+		const uint32_t u = u_get<WIDE>(U, t);
+		if (!u || !kc.keep(t, u))
+			continue;
+		bool take = u > vstar;
+		if (!take && u == vstar)
+			take = (eq_rank++ < m_eq);
+		if (take) {
+			const uint32_t slot = atomicAdd(&S.n_sel, 1u);
+			if (slot < RANK_KCAP)
+				S.sel[slot] = rank_key(u, t);
+		}
+	}
+	__syncthreads();
+}
 
 template <bool WIDE>
 __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t *U, uint32_t *bitmap,
@@ -166,17 +287,16 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	const uint8_t *Q = a.q + q0;
 	uint32_t *U32 = (uint32_t *)U;
 
-	// ---- zero shared state
+	// ---- zero shared state (u_bytes is a multiple of 16)
 	{
-		const uint32_t u_words = ((WIDE ? 2 * N : N) + 3) / 4;
-		for (uint32_t i = tid; i < u_words; i += RANK_THREADS)
-			U32[i] = 0;
+		uint4 *U128 = (uint4 *)U;
+		const uint32_t n128 = ((WIDE ? 2 * N : N) + 15) / 16;
+		for (uint32_t i = tid; i < n128; i += RANK_THREADS)
+			U128[i] = make_uint4(0, 0, 0, 0);
 		for (uint32_t i = tid; i < a.P.slots / 32; i += RANK_THREADS)
 			bitmap[i] = 0;
-		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
-			S.hist[i] = 0;
 		if (tid == 0) {
-			S.n_rows = 0; S.row_cur = 0; S.n_rec = 0; S.n_chg = 0; S.n_sel = 0; S.n_post = 0;
+			S.n_rows = 0; S.row_cur = 0; S.n_rec = 0; S.n_chg = 0; S.n_sel = 0; S.n_post = 0; S.n_surv = 0;
 		}
 	}
 	__syncthreads();
@@ -202,6 +322,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		}
 		__syncthreads();
 		const uint32_t n_rows = S.n_rows;
+		uint32_t my_post = 0;
 		for (;;) {
 			uint32_t r = 0;
 			if (lane == 0)
@@ -210,18 +331,28 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 			if (r >= n_rows)
 				break;
 			const uint32_t word = S.rows[r];
-			const uint64_t beg = a.row_off[word], end = a.row_off[word + 1];
-			if (lane == 0)
-				atomicAdd(&S.n_post, (uint32_t)(end - beg));
-			const uint32_t *pp = a.postings;
-			uint64_t i = beg + lane;
-			for (; i + 96 < end; i += 128) {
-				uint32_t t0 = __ldg(pp + i), t1 = __ldg(pp + i + 32), t2 = __ldg(pp + i + 64), t3 = __ldg(pp + i + 96);
-				u_inc<WIDE>(U32, t0); u_inc<WIDE>(U32, t1); u_inc<WIDE>(U32, t2); u_inc<WIDE>(U32, t3);
+			const uint32_t size = a.row_size[word];
+			const uint32_t *row = a.postings + a.row_off[word];
+			const uint4 *v4 = (const uint4 *)row;
+			const uint32_t nvec = size >> 2;
+			my_post += size;
+			uint32_t i = lane;
+			for (; i + 96 < nvec; i += 128) {
+				const uint4 x0 = __ldg(v4 + i), x1 = __ldg(v4 + i + 32), x2 = __ldg(v4 + i + 64), x3 = __ldg(v4 + i + 96);
+				u_inc<WIDE>(U32, x0.x); u_inc<WIDE>(U32, x0.y); u_inc<WIDE>(U32, x0.z); u_inc<WIDE>(U32, x0.w);
+				u_inc<WIDE>(U32, x1.x); u_inc<WIDE>(U32, x1.y); u_inc<WIDE>(U32, x1.z); u_inc<WIDE>(U32, x1.w);
+				u_inc<WIDE>(U32, x2.x); u_inc<WIDE>(U32, x2.y); u_inc<WIDE>(U32, x2.z); u_inc<WIDE>(U32, x2.w);
+				u_inc<WIDE>(U32, x3.x); u_inc<WIDE>(U32, x3.y); u_inc<WIDE>(U32, x3.z); u_inc<WIDE>(U32, x3.w);
 			}
-			for (; i < end; i += 32)
-				u_inc<WIDE>(U32, __ldg(pp + i));
+			for (; i < nvec; i += 32) {
+				const uint4 x = __ldg(v4 + i);
+				u_inc<WIDE>(U32, x.x); u_inc<WIDE>(U32, x.y); u_inc<WIDE>(U32, x.z); u_inc<WIDE>(U32, x.w);
+			}
+			if (lane < (size & 3))
+				u_inc<WIDE>(U32, __ldg(row + 4 * nvec + lane));
 		}
+		if (lane == 0 && my_post)
+			atomicAdd(&S.n_post, my_post);
 		__syncthreads();
 		if (tid == 0) {
 			S.n_rows = 0;
@@ -234,12 +365,22 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		for (uint32_t t = tid; t < N; t += RANK_THREADS)
 			a.u_out[(uint64_t)job * N + t] = u_get<WIDE>(U, t);
 
-	// ---- strict prefix maxima ("records") of U in target order
+	// ---- strict prefix maxima ("records") of U in target order; SIMD max over the segment
 	const uint32_t seg = WIDE ? a.seg_wide : a.seg_narrow;
 	const uint32_t t0 = min(N, tid * seg), t1 = min(N, t0 + seg);
+	const uint32_t PER = WIDE ? 2 : 4;   // counters per 32-bit word
+	// segment start is word aligned; threads past the end own nothing
+	const uint32_t w0 = t0 / PER, w1 = t0 < t1 ? (t1 + PER - 1) / PER : w0;
 	uint32_t m = 0;
-	for (uint32_t t = t0; t < t1; ++t)
-		m = max(m, u_get<WIDE>(U, t));
+	{
+		uint32_t acc = 0;
+		for (uint32_t k = w0; k < w1; ++k)
+			acc = WIDE ? __vmaxu2(acc, U32[k]) : __vmaxu4(acc, U32[k]);
+		if (WIDE)
+			m = max(acc & 0xffff, acc >> 16);
+		else
+			m = max(max(acc & 0xff, (acc >> 8) & 0xff), max((acc >> 16) & 0xff, acc >> 24));
+	}
 	uint32_t run = block_excl_scan_max(m, S.warp_tmp);
 	if (m > run)
 		for (uint32_t t = t0; t < t1; ++t) {
@@ -293,128 +434,64 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	}
 	__syncthreads();
 
+	// ---- survivors of both filters, collected unordered
 	KeepCursor kc{chg_pos, chg_minu, S.n_chg, S.minv, 0};
-
-	// ---- radix select of the k_max-th largest surviving count
-	for (uint32_t t = t0; t < t1; ++t) {
-		uint32_t u = u_get<WIDE>(U, t);
-		if (u && kc.keep(t, u))
-			atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
-	}
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t total = 0;
-		for (int b = 0; b < 256; ++b)
-			total += S.hist[b];
-		S.total = total;
-		S.take_all = total <= a.k_max;
-		S.vstar = 0;
-		S.m_eq = 0;
-		if (!S.take_all) {
-			uint32_t cum = 0;
-			for (int b = 255; b >= 0; --b) {
-				cum += S.hist[b];
-				if (cum >= a.k_max) {
-					S.bstar = (uint32_t)b;
-					S.above = cum - S.hist[b];
-					break;
-				}
-			}
-			if (!WIDE) {
-				S.vstar = S.bstar;
-				S.m_eq = a.k_max - S.above;
-			}
-		}
-	}
-	__syncthreads();
-	if (WIDE && !S.take_all) {
-		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
-			S.hist[i] = 0;
-		__syncthreads();
-		kc.cur = 0;
-		const uint32_t bstar = S.bstar;
-		for (uint32_t t = t0; t < t1; ++t) {
-			uint32_t u = u_get<WIDE>(U, t);
-			if (u && (u >> 8) == bstar && kc.keep(t, u))
-				atomicAdd(&S.hist[u & 255], 1u);
-		}
-		__syncthreads();
-		if (tid == 0) {
-			uint32_t cum = S.above;
-			for (int b = 255; b >= 0; --b) {
-				cum += S.hist[b];
-				if (cum >= a.k_max) {
-					S.vstar = (S.bstar << 8) | (uint32_t)b;
-					S.m_eq = a.k_max - (cum - S.hist[b]);
-					break;
-				}
-			}
-		}
-		__syncthreads();
-	}
-	const uint32_t vstar = S.vstar, m_eq = S.m_eq;
-	const bool take_all = S.take_all != 0;
-
-	// ---- ties at the cut value are taken in ascending target order
-	uint32_t c_eq = 0;
-	if (!take_all) {
-		kc.cur = 0;
-		for (uint32_t t = t0; t < t1; ++t) {
-			uint32_t u = u_get<WIDE>(U, t);
-			if (u == vstar && u && kc.keep(t, u))
-				++c_eq;
-		}
-	}
-	uint32_t eq_rank = block_excl_scan_sum(c_eq, S.warp_tmp);
-	kc.cur = 0;
-	for (uint32_t t = t0; t < t1; ++t) {
-		uint32_t u = u_get<WIDE>(U, t);
-		if (!u || !kc.keep(t, u))
-			continue;
-		bool take = u > vstar;
-		if (!take && u == vstar)
-			take = (eq_rank++ < m_eq);
-		if (take) {
-			uint32_t slot = atomicAdd(&S.n_sel, 1u);
-			if (slot < RANK_KCAP)
-				S.sel[slot] = ((unsigned long long)(0xFFFFu - u) << 32) | t;
-		}
-	}
-	__syncthreads();
-	const uint32_t nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
-
-	// ---- descending U, ascending target within ties == ascending key; bitonic sort
-	uint32_t P2 = 1;
-	while (P2 < nsel)
-		P2 <<= 1;
-	for (uint32_t i = nsel + tid; i < P2; i += RANK_THREADS)
-		S.sel[i] = ~0ull;
-	__syncthreads();
-	for (uint32_t k = 2; k <= P2; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = tid; i < P2; i += RANK_THREADS) {
-				uint32_t x = i ^ j;
-				if (x > i) {
-					unsigned long long A = S.sel[i], B = S.sel[x];
-					bool up = (i & k) == 0;
-					if ((A > B) == up) {
-						S.sel[i] = B;
-						S.sel[x] = A;
+	{
+		const uint32_t mu0 = kc.minu(t0);          // threshold at the segment start
+		const uint32_t cur0 = kc.cur;
+		// constant over the segment unless a change position lies in [t0, t1 - 1)
+		const bool constant = !(cur0 < kc.n_chg && chg_pos[cur0] + 1 < t1);
+		if (constant) {
+			const uint32_t thr = max(max(mu0, kc.minv), 1u);
+			if (thr <= (WIDE ? 0xffffu : 0xffu)) {
+				const uint32_t thr_v = WIDE ? thr * 0x00010001u : thr * 0x01010101u;
+				for (uint32_t k = w0; k < w1; ++k) {
+					const uint32_t word = U32[k];
+					uint32_t mask = WIDE ? __vcmpgeu2(word, thr_v) : __vcmpgeu4(word, thr_v);
+					while (mask) {
+						const uint32_t b = (uint32_t)(__ffs(mask) - 1) / (WIDE ? 16 : 8);
+						mask &= ~((WIDE ? 0xffffu : 0xffu) << (b * (WIDE ? 16 : 8)));
+						const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+						const uint32_t t = k * PER + b;
+						const uint32_t slot = atomicAdd(&S.n_surv, 1u);
+						if (slot < RANK_KCAP)
+							S.sel[slot] = rank_key(u, t);
 					}
 				}
 			}
-			__syncthreads();
+		} else {
+			kc.cur = 0;
+			for (uint32_t t = t0; t < t1; ++t) {
+				const uint32_t u = u_get<WIDE>(U, t);
+				if (u && kc.keep(t, u)) {
+					const uint32_t slot = atomicAdd(&S.n_surv, 1u);
+					if (slot < RANK_KCAP)
+						S.sel[slot] = rank_key(u, t);
+				}
+			}
 		}
+	}
+	__syncthreads();
+	const uint32_t total = S.n_surv;
+	uint32_t nsel;
+	if (total <= RANK_KCAP) {
+		nsel = min(total, a.k_max);
+		block_sort_keys(S.sel, total);
+	} else {
+		rank_select_fallback<WIDE>(a, S, U, kc, t0, t1);
+		nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
+		block_sort_keys(S.sel, nsel);
+	}
 	for (uint32_t i = tid; i < nsel; i += RANK_THREADS) {
-		unsigned long long key = S.sel[i];
+		const unsigned long long key = S.sel[i];
 		a.cand_t[(uint64_t)job * a.k_max + i] = (uint32_t)key;
 		if (a.cand_u)
 			a.cand_u[(uint64_t)job * a.k_max + i] = 0xFFFFu - (uint32_t)(key >> 32);
 	}
 	if (tid == 0) {
-		a.n_cand[job] = S.total;
-		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
+		a.n_cand[job] = total;
 		a.n_emit[job] = nsel;
+		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
 	}
 }
 
