@@ -76,3 +76,58 @@ def test_idempotent_and_batch_split_invariant(golden):
     c1, c2 = s.search(qs[:250]), s.search(qs[250:])
     tgt = np.concatenate([c1.hits["target"], c2.hits["target"]])
     assert np.array_equal(a.hits["target"], tgt)
+
+
+def _run_cli(tmp_path, golden, extra, outs):
+    """Runs the C++ host driver (Searcher/HitMgr/OutputSink mirror) on the golden FASTA inputs."""
+    import gzip
+    import os
+    import subprocess
+    from usearch12_b200 import build
+    cli = build.build_cli()
+    paths = {}
+    for name in ("q", "db"):
+        dst = os.path.join(tmp_path, name + ".fa")
+        with gzip.open(os.path.join(util.GOLDEN, name + ".fa.gz"), "rb") as fi, open(dst, "wb") as fo:
+            fo.write(fi.read())
+        paths[name] = dst
+    cmd = [cli, "-usearch_global", paths["q"], "-db", paths["db"], "-quiet"] + extra
+    for k in outs:
+        paths[k] = os.path.join(tmp_path, "o." + k)
+        cmd += [{"user": "-userout", "uc": "-uc", "b6": "-blast6out"}[k], paths[k]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return {k: open(paths[k]).read().splitlines() for k in outs}
+
+
+@pytest.mark.parametrize("variant", ["plus97", "both80_ma0"])
+def test_cli_output_files_byte_identical_to_reference(golden, variant, tmp_path):
+    kw = util.VARIANTS[variant]
+    extra = ["-id", str(kw["id"]), "-strand", "both" if kw["strand_both"] else "plus",
+             "-userfields", "query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand", "-batch", "1000"]
+    if "maxaccepts" in kw:
+        extra += ["-maxaccepts", str(kw["maxaccepts"]), "-maxrejects", str(kw["maxrejects"])]
+    got = _run_cli(str(tmp_path), golden, extra, ["user", "uc", "b6"])
+    for kind in ("user", "uc", "b6"):
+        d = util.first_diff(got[kind], golden.lines(variant, kind))
+        assert d is None, "%s %s\n%s" % (variant, kind, d)
+
+
+def test_cli_extended_userfields_match_reference(golden, tmp_path):
+    """tests/golden/both90x.user.gz: reference binary, -id 0.9 -strand both -maxaccepts 2
+    -maxrejects 16 with 25 userfields (first/last-M coordinates, gap counts, full path ...)."""
+    xf = ("query+target+id+fractid+dist+pairs+gaps+allgaps+qlot+qhit+qunt+tlot+thit+tunt+ql+tl+alnlen+opens+exts+"
+          "aln+tstrand+mism+ids+diffs+clusternr")
+    got = _run_cli(str(tmp_path), golden, ["-id", "0.9", "-strand", "both", "-maxaccepts", "2", "-maxrejects", "16",
+                                           "-userfields", xf], ["user"])
+    d = util.first_diff(got["user"], golden.lines("both90x", "user"))
+    assert d is None, d
+
+
+def test_cli_refuses_unsupported_options(tmp_path):
+    import subprocess
+    from usearch12_b200 import build
+    cli = build.build_cli()
+    r = subprocess.run([cli, "-usearch_global", "x.fa", "-db", "y.fa", "-id", "0.9", "-strand", "plus", "-fulldp", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "not supported" in r.stdout

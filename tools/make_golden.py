@@ -128,6 +128,16 @@ def main():
     for name, extra in variants.items():
         run(name, qfa, dfa, extra)
         print("golden", name)
+    # extended userfields (first/last-M coordinates, gap counts, full path): user file only
+    xf = ("query+target+id+fractid+dist+pairs+gaps+allgaps+qlot+qhit+qunt+tlot+thit+tunt+ql+tl+alnlen+opens+exts+"
+          "aln+tstrand+mism+ids+diffs+clusternr")
+    tmp = os.path.join(OUT, "_x.user")
+    subprocess.run([REF, "-usearch_global", qfa, "-db", dfa, "-id", "0.9", "-strand", "both", "-maxaccepts", "2",
+                    "-maxrejects", "16", "-threads", "1", "-quiet", "-userout", tmp, "-userfields", xf], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    with gzip.open(os.path.join(OUT, "both90x.user.gz"), "wt", compresslevel=9) as f:
+        f.write(open(tmp).read())
+    os.remove(tmp)
     os.remove(dfa)
     os.remove(qfa)
 

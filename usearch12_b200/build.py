@@ -46,5 +46,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+CLI = os.path.join(HERE, "usearch12_b200_cli")
+
+
+def build_cli(force=False):
+    """Host C++ driver (usearch12_b200/csrc/host) linked against libusb200.so."""
+    host = os.path.join(CSRC, "host")
+    srcs = [os.path.join(host, f) for f in ("usb_host.cpp", "usb_main.cpp")]
+    newest = max(os.path.getmtime(x) for x in srcs + [os.path.join(host, "usb_host.h")])
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= newest:
+        return CLI
+    build()
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", CLI] + srcs + [
+        "-L" + HERE, "-lusb200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building the host CLI")
+    return CLI
+
+
 if __name__ == "__main__":
+    build_cli(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose=True))

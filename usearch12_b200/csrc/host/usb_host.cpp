@@ -1,0 +1,427 @@
+// usb_host.cpp -- see usb_host.h
+#include "usb_host.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace usbhost {
+
+void Die(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	fprintf(stderr, "\n---Fatal error---\n");
+	vfprintf(stderr, fmt, ap);
+	fprintf(stderr, "\n");
+	va_end(ap);
+	exit(1);
+}
+
+void Warning(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	fprintf(stderr, "\nWARNING: ");
+	vfprintf(stderr, fmt, ap);
+	fprintf(stderr, "\n");
+	va_end(ap);
+}
+
+static void CheckUsb(int rc, const char *what)
+{
+	if (rc != 0)
+		Die("%s: %s (usb200 error %d)", what, usb_last_error(), rc);
+}
+
+// ------------------------------------------------------------------ SeqDB
+// fastaseqsource.cpp:25-124: label = everything after '>', letters = isalpha characters, white
+// space skipped, gap characters stripped, other bytes reported and skipped, empty sequences
+// dropped with a warning.
+void SeqDB::FromFasta(const std::string &FileName)
+{
+	FILE *f = fopen(FileName.c_str(), "rb");
+	if (!f)
+		Die("Cannot open %s", FileName.c_str());
+	fseek(f, 0, SEEK_END);
+	long sz = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	std::vector<char> buf((size_t)sz + 1);
+	if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz)
+		Die("Read error on %s", FileName.c_str());
+	fclose(f);
+	buf[sz] = '\n';
+	m_Letters.clear();
+	m_Letters.reserve((size_t)sz);
+	m_Offsets.assign(1, 0);
+	m_Labels.clear();
+	const char *p = buf.data(), *end = buf.data() + sz;
+	unsigned line_nr = 0, bad_bytes = 0;
+	bool have_label = false;
+	std::string label;
+	uint64_t start = 0;
+	auto close_record = [&]() {
+		if (!have_label)
+			return;
+		if (m_Letters.size() > start) {
+			m_Labels.push_back(label);
+			m_Offsets.push_back(m_Letters.size());
+		} else
+			Warning("Empty sequence at line %u in FASTA file %s, label >%s", line_nr, FileName.c_str(), label.c_str());
+		start = m_Letters.size();
+	};
+	while (p < end) {
+		const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p + 1));
+		const char *q = eol;
+		while (q > p && (q[-1] == '\r' || q[-1] == '\n'))
+			--q;
+		++line_nr;
+		if (q > p && *p == '>') {
+			close_record();
+			label.assign(p + 1, q);
+			have_label = true;
+		} else if (q > p) {
+			if (!have_label)
+				Die("Bad FASTA file %s, expected '>' in line %u", FileName.c_str(), line_nr);
+			for (const char *c = p; c < q; ++c) {
+				unsigned char ch = (unsigned char)*c;
+				if (isalpha(ch))
+					m_Letters.push_back(ch);
+				else if (isspace(ch) || ch == '-' || ch == '.')
+					continue;
+				else
+					++bad_bytes;
+			}
+		}
+		p = eol + 1;
+	}
+	close_record();
+	if (bad_bytes)
+		Warning("%u invalid bytes in FASTA file %s ignored", bad_bytes, FileName.c_str());
+}
+
+void SeqDB::GetSI(uint32_t Index, SeqInfo &SI) const
+{
+	SI.m_Label = m_Labels[Index].c_str();
+	SI.m_Seq = GetSeq(Index);
+	SI.m_L = GetSeqLength(Index);
+	SI.m_Index = Index;
+	SI.m_RevComp = false;
+}
+
+// ------------------------------------------------------------------ AlignResult
+unsigned AlignResult::GetPathLength() const
+{
+	unsigned n = 0;
+	for (uint32_t k = 0; k < m_Hit.run_cnt; ++k)
+		n += m_Runs[k] >> 2;
+	return n;
+}
+
+void AlignResult::GetPath(std::string &Path) const
+{
+	static const char ops[4] = {'M', 'D', 'I', '?'};
+	Path.clear();
+	for (uint32_t k = 0; k < m_Hit.run_cnt; ++k)
+		Path.append(m_Runs[k] >> 2, ops[m_Runs[k] & 3]);
+}
+
+void AlignResult::GetCompressedPath(std::string &CPath) const
+{
+	static const char ops[4] = {'M', 'D', 'I', '?'};
+	CPath.clear();
+	char tmp[16];
+	for (uint32_t k = 0; k < m_Hit.run_cnt; ++k) {
+		const unsigned n = m_Runs[k] >> 2;
+		if (n != 1) {
+			snprintf(tmp, sizeof tmp, "%u", n);
+			CPath += tmp;
+		}
+		CPath += ops[m_Runs[k] & 3];
+	}
+}
+
+// ------------------------------------------------------------------ OutputSink
+enum UserField {
+	UF_query, UF_target, UF_clusternr, UF_id, UF_fractid, UF_dist, UF_pairs, UF_gaps, UF_allgaps, UF_qlo, UF_qhi,
+	UF_tlo, UF_thi, UF_qlot, UF_qhit, UF_qunt, UF_tlot, UF_thit, UF_tunt, UF_ql, UF_tl, UF_alnlen, UF_opens,
+	UF_exts, UF_aln, UF_caln, UF_qstrand, UF_tstrand, UF_mism, UF_ids, UF_diffs, UF_COUNT
+};
+static const char *g_UserFieldNames[UF_COUNT] = {
+	"query", "target", "clusternr", "id", "fractid", "dist", "pairs", "gaps", "allgaps", "qlo", "qhi", "tlo",
+	"thi", "qlot", "qhit", "qunt", "tlot", "thit", "tunt", "ql", "tl", "alnlen", "opens", "exts", "aln", "caln",
+	"qstrand", "tstrand", "mism", "ids", "diffs"};
+
+OutputSink::OutputSink(const OutputOpts &O)
+{
+	auto open = [](const std::string &fn) -> FILE * {
+		if (fn.empty())
+			return nullptr;
+		FILE *f = fopen(fn.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", fn.c_str());
+		return f;
+	};
+	m_fUC = open(O.uc);
+	m_fB6 = open(O.blast6out);
+	m_fUser = open(O.userout);
+	if (O.output_no_hits)
+		Die("-output_no_hits is not supported by this build");
+	if (m_fUser) {
+		// userout.cpp:20-60: fields separated by '+'; default query+target+id
+		std::string spec = O.userfields.empty() ? "query+target+id" : O.userfields;
+		size_t pos = 0;
+		while (pos <= spec.size()) {
+			size_t e = spec.find('+', pos);
+			if (e == std::string::npos)
+				e = spec.size();
+			std::string name = spec.substr(pos, e - pos);
+			int idx = -1;
+			for (int i = 0; i < UF_COUNT; ++i)
+				if (name == g_UserFieldNames[i])
+					idx = i;
+			if (idx < 0)
+				Die("Invalid or unsupported userfield name '%s'", name.c_str());
+			m_UserFields.push_back(idx);
+			pos = e + 1;
+		}
+	}
+}
+
+OutputSink::~OutputSink() { OnAllDone(); }
+
+void OutputSink::Flush(FILE *f, std::string &buf, bool force)
+{
+	if (f && (force || buf.size() > (1u << 20))) {
+		fwrite(buf.data(), 1, buf.size(), f);
+		buf.clear();
+	}
+}
+
+void OutputSink::OnAllDone()
+{
+	Flush(m_fUC, m_bUC, true);
+	Flush(m_fB6, m_bB6, true);
+	Flush(m_fUser, m_bUser, true);
+	for (FILE **f : {&m_fUC, &m_fB6, &m_fUser})
+		if (*f) {
+			fclose(*f);
+			*f = nullptr;
+		}
+}
+
+static void appendf(std::string &s, const char *fmt, ...)
+{
+	char tmp[256];
+	va_list ap;
+	va_start(ap, fmt);
+	int n = vsnprintf(tmp, sizeof tmp, fmt, ap);
+	va_end(ap);
+	if (n > 0)
+		s.append(tmp, (size_t)std::min<int>(n, (int)sizeof tmp - 1));
+}
+
+// outputuc.cpp:19-22,45-69
+void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM)
+{
+	if (!m_fUC)
+		return;
+	std::string cp;
+	if (HM.m_Hits.empty()) {
+		appendf(m_bUC, "N\t*\t%u\t*\t.\t*\t*\t*\t", Query.m_L);
+		m_bUC += Query.m_Label;
+		m_bUC += "\t*\n";
+	}
+	for (const AlignResult &AR : HM.m_Hits) {
+		AR.GetCompressedPath(cp);
+		appendf(m_bUC, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t", AR.GetTargetIndex(), AR.GetIQL(), AR.GetPctId(),
+		  AR.GetQueryStrand(), 0u, 0u);
+		m_bUC += cp;
+		m_bUC += '\t';
+		m_bUC += AR.GetQueryLabel();
+		m_bUC += '\t';
+		m_bUC += AR.GetTargetLabel();
+		m_bUC += '\n';
+	}
+	Flush(m_fUC, m_bUC, false);
+}
+
+// blast6out.cpp:27-80 (global alignments: evalue and bit score print as '*')
+void OutputSink::OutputBlast6(const HitMgr &HM)
+{
+	if (!m_fB6)
+		return;
+	for (const AlignResult &AR : HM.m_Hits) {
+		m_bB6 += AR.GetQueryLabel();
+		m_bB6 += '\t';
+		m_bB6 += AR.GetTargetLabel();
+		appendf(m_bB6, "\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t*\t*\n", AR.GetPctId(), AR.GetAlnLength(),
+		  AR.GetMismatchCount(), AR.GetGapOpenCount(), AR.GetIQLo1(), AR.GetIQHi1(), AR.GetTLo6(), AR.GetTHi6());
+	}
+	Flush(m_fB6, m_bB6, false);
+}
+
+// userout.cpp:126-215
+void OutputSink::OutputUser(const HitMgr &HM)
+{
+	if (!m_fUser)
+		return;
+	std::string tmp;
+	for (const AlignResult &AR : HM.m_Hits) {
+		for (size_t i = 0; i < m_UserFields.size(); ++i) {
+			if (i)
+				m_bUser += '\t';
+			switch (m_UserFields[i]) {
+			case UF_query: m_bUser += AR.GetQueryLabel(); break;
+			case UF_target: m_bUser += AR.GetTargetLabel(); break;
+			case UF_clusternr: appendf(m_bUser, "%u", AR.GetTargetIndex()); break;
+			case UF_id: appendf(m_bUser, "%.1f", AR.GetPctId()); break;
+			case UF_fractid: appendf(m_bUser, "%.4f", AR.GetFractId()); break;
+			case UF_dist: appendf(m_bUser, "%.4f", 1.0 - AR.GetFractId()); break;
+			case UF_pairs: appendf(m_bUser, "%u", AR.GetLetterPairCount()); break;
+			case UF_gaps: appendf(m_bUser, "%u", AR.GetGapCount()); break;
+			case UF_allgaps: appendf(m_bUser, "%u", AR.GetAllGapCount()); break;
+			case UF_qlo: appendf(m_bUser, "%u", AR.GetIQLo1()); break;
+			case UF_qhi: appendf(m_bUser, "%u", AR.GetIQHi1()); break;
+			case UF_tlo: appendf(m_bUser, "%u", AR.GetITLo1()); break;
+			case UF_thi: appendf(m_bUser, "%u", AR.GetITHi1()); break;
+			case UF_qlot: appendf(m_bUser, "%u", AR.GetQLoT()); break;
+			case UF_qhit: appendf(m_bUser, "%u", AR.GetQHiT()); break;
+			case UF_qunt: appendf(m_bUser, "%u", AR.GetQUnT()); break;
+			case UF_tlot: appendf(m_bUser, "%u", AR.GetTLoT()); break;
+			case UF_thit: appendf(m_bUser, "%u", AR.GetTHiT()); break;
+			case UF_tunt: appendf(m_bUser, "%u", AR.GetTUnT()); break;
+			case UF_ql: appendf(m_bUser, "%u", AR.GetIQL()); break;
+			case UF_tl: appendf(m_bUser, "%u", AR.GetITL()); break;
+			case UF_alnlen: appendf(m_bUser, "%u", AR.GetAlnLength()); break;
+			case UF_opens: appendf(m_bUser, "%u", AR.GetGapOpenCount()); break;
+			case UF_exts: appendf(m_bUser, "%u", AR.GetGapExtCount()); break;
+			case UF_aln: AR.GetPath(tmp); m_bUser += tmp; break;
+			case UF_caln: AR.GetCompressedPath(tmp); m_bUser += tmp; break;
+			case UF_qstrand: m_bUser += AR.GetQueryStrand(); break;
+			case UF_tstrand: m_bUser += AR.GetTargetStrand(); break;
+			case UF_mism: appendf(m_bUser, "%u", AR.GetMismatchCount()); break;
+			case UF_ids: appendf(m_bUser, "%u", AR.GetIdCount()); break;
+			case UF_diffs: appendf(m_bUser, "%u", AR.GetDiffCount()); break;
+			}
+		}
+		m_bUser += '\n';
+	}
+	Flush(m_fUser, m_bUser, false);
+}
+
+void OutputSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
+{
+	OutputUC(Query, HM);
+	OutputBlast6(HM);
+	OutputUser(HM);
+}
+
+// ------------------------------------------------------------------ GpuSearcher
+GpuSearcher::GpuSearcher(int Device, const SeqDB &DB, const usb_params &P) : m_DB(DB)
+{
+	CheckUsb(usb_index_create(Device, &P, DB.Letters(), DB.Offsets(), DB.GetSeqCount(), &m_Index), "usb_index_create");
+	CheckUsb(usb_searcher_create(m_Index, &P, &m_Searcher), "usb_searcher_create");
+}
+
+GpuSearcher::~GpuSearcher()
+{
+	usb_searcher_free(m_Searcher);
+	usb_index_free(m_Index);
+}
+
+uint64_t GpuSearcher::GetLaunchCount() const { return usb_searcher_launch_count(m_Searcher); }
+
+// Replaces the loop "SS->GetNext(Query); searcher->Search(Query)" of Thread() (search.cpp:63-86)
+// for a batch: one C-ABI call, then one HitMgr per query holding AlignResults in output order.
+void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out)
+{
+	usb_result *R = nullptr;
+	CheckUsb(usb_search_batch(m_Searcher, Queries.Letters(), Queries.Offsets() + First, Count, &R), "usb_search_batch");
+	const usb_hit *hits = usb_result_hits(R);
+	const uint64_t *qoff = usb_result_query_offsets(R);
+	uint64_t n_runs = 0;
+	const uint32_t *runs = usb_result_runs(R, &n_runs);
+	// the run arena must outlive the result handle: keep a copy owned by the first HitMgr's vector
+	auto arena = std::make_shared<std::vector<uint32_t>>(runs, runs + n_runs);
+	m_Arenas.push_back(arena);
+	Out.resize(Count);
+	for (uint32_t q = 0; q < Count; ++q) {
+		HitMgr &HM = Out[q];
+		Queries.GetSI(First + q, HM.m_Query);
+		HM.m_Hits.clear();
+		for (uint64_t k = qoff[q]; k < qoff[q + 1]; ++k) {
+			AlignResult AR;
+			AR.m_Hit = hits[k];
+			AR.m_Query = HM.m_Query;
+			AR.m_Query.m_RevComp = hits[k].strand != 0;
+			m_DB.GetSI(hits[k].target, AR.m_Target);
+			AR.m_Runs = arena->data() + hits[k].run_off;
+			HM.m_Hits.push_back(AR);
+		}
+	}
+	usb_result_free(R);
+}
+
+void GpuSearcher::ReleaseArenas() { m_Arenas.clear(); }
+
+// ------------------------------------------------------------------ Search driver
+uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts)
+{
+	if (QueryFileName.empty())
+		Die("Query file name not set");
+	if (DBFileName.empty())
+		Die("Database file name not set");
+	const int ndev = usb_device_count();
+	if (ndev <= 0)
+		Die("No CUDA device available: this build has no CPU search path");
+	const int gpus = std::min(std::max(1, Opts.gpus), ndev);
+	SeqDB DB, Q;
+	DB.FromFasta(DBFileName);
+	Q.FromFasta(QueryFileName);
+	if (!Opts.quiet)
+		fprintf(stderr, "%u db seqs, %u query seqs, %d GPU(s)\n", DB.GetSeqCount(), Q.GetSeqCount(), gpus);
+	std::vector<GpuSearcher *> searchers(gpus, nullptr);
+	{
+		std::vector<std::thread> th;
+		for (int d = 0; d < gpus; ++d)
+			th.emplace_back([&, d]() { searchers[d] = new GpuSearcher(d, DB, Opts.P); });
+		for (auto &t : th)
+			t.join();
+	}
+	OutputSink Sink(Opts.Out);
+	const uint32_t NQ = Q.GetSeqCount();
+	const uint32_t nbatch = (NQ + Opts.batch - 1) / Opts.batch;
+	uint64_t queries_with_hits = 0;
+	// batches are dealt round-robin to the devices and drained in input order, so the output
+	// files are in query order for any GPU count (the reference guarantees that only for 1 thread)
+	for (uint32_t b0 = 0; b0 < nbatch; b0 += gpus) {
+		const uint32_t nb = std::min<uint32_t>(gpus, nbatch - b0);
+		std::vector<std::vector<HitMgr>> results(nb);
+		std::vector<std::thread> th;
+		for (uint32_t k = 0; k < nb; ++k)
+			th.emplace_back([&, k]() {
+				const uint32_t first = (b0 + k) * Opts.batch;
+				searchers[k]->SearchBatch(Q, first, std::min<uint32_t>(Opts.batch, NQ - first), results[k]);
+			});
+		for (auto &t : th)
+			t.join();
+		for (uint32_t k = 0; k < nb; ++k) {
+			for (const HitMgr &HM : results[k]) {
+				Sink.OnQueryDone(HM.m_Query, HM);
+				queries_with_hits += HM.GetHitCount() > 0;
+			}
+			searchers[k]->ReleaseArenas();
+		}
+	}
+	Sink.OnAllDone();
+	for (GpuSearcher *s : searchers)
+		delete s;
+	return queries_with_hits;
+}
+
+} // namespace usbhost

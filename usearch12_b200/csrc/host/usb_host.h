@@ -1,0 +1,170 @@
+// usb_host.h -- host-side mirror of the reference's search framework for the GPU hot path.
+//
+// Same names, argument meaning and error behaviour as the reference classes they stand in for
+// (SURVEY.md section 8b), re-implemented over the C ABI of include/usb200.h:
+//   SeqInfo / SeqDB            seqinfo.h, seqdb.cpp:256 (GetSI), fastaseqsource.cpp:25-124
+//   AlignResult                alignresult.h:17-245, arscorer.cpp:201-296 (FillLo)
+//   HitMgr                     hitmgr.cpp:120-161,400,477
+//   HitSink / OutputSink       hitsink.h:57, outputsink.cpp:358, outputuc.cpp, blast6out.cpp, userout.cpp
+//   Searcher / GpuSearcher     searcher.h:21-96 -- Search(Query) becomes SearchBatch(first,n)
+//   Search()                   search.cpp:89 (driver: load DB, fan out, sinks in input order)
+// Error convention: Die() prints to stderr and exits 1 (myutils.cpp:867).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/usb200.h"
+
+namespace usbhost {
+
+[[noreturn]] void Die(const char *fmt, ...);
+void Warning(const char *fmt, ...);
+
+struct SeqInfo {
+	const char *m_Label = nullptr;
+	const uint8_t *m_Seq = nullptr;
+	uint32_t m_L = 0;
+	uint32_t m_Index = 0;
+	bool m_RevComp = false;
+};
+
+// In-memory sequence set (seqdb.h); letters are kept exactly as read.
+class SeqDB {
+public:
+	void FromFasta(const std::string &FileName);
+	uint32_t GetSeqCount() const { return (uint32_t)m_Offsets.size() - 1; }
+	void GetSI(uint32_t Index, SeqInfo &SI) const;
+	const uint8_t *GetSeq(uint32_t i) const { return m_Letters.data() + m_Offsets[i]; }
+	uint32_t GetSeqLength(uint32_t i) const { return (uint32_t)(m_Offsets[i + 1] - m_Offsets[i]); }
+	const char *GetLabel(uint32_t i) const { return m_Labels[i].c_str(); }
+	const uint8_t *Letters() const { return m_Letters.data(); }
+	const uint64_t *Offsets() const { return m_Offsets.data(); }
+
+private:
+	std::vector<uint8_t> m_Letters;
+	std::vector<uint64_t> m_Offsets{0};
+	std::vector<std::string> m_Labels;
+};
+
+// One accepted alignment: the statistics the reference derives lazily from (Query, Target, Path).
+class AlignResult {
+public:
+	SeqInfo m_Query, m_Target;
+	usb_hit m_Hit;
+	const uint32_t *m_Runs = nullptr; // (length << 2) | op, op 0=M 1=D 2=I
+
+	double GetFractId() const { return m_Hit.alnlen == 0 ? 0.0 : double(m_Hit.ids) / double(m_Hit.alnlen); }
+	double GetPctId() const { return 100.0 * GetFractId(); }
+	const char *GetQueryLabel() const { return m_Query.m_Label; }
+	const char *GetTargetLabel() const { return m_Target.m_Label; }
+	unsigned GetTargetIndex() const { return m_Hit.target; }
+	unsigned GetIQL() const { return m_Hit.ql; }
+	unsigned GetITL() const { return m_Hit.tl; }
+	unsigned GetAlnLength() const { return m_Hit.alnlen; }
+	unsigned GetIdCount() const { return m_Hit.ids; }
+	unsigned GetMismatchCount() const { return m_Hit.mism; }
+	unsigned GetGapCount() const { return m_Hit.intgaps; }
+	unsigned GetGapOpenCount() const { return m_Hit.opens; }
+	unsigned GetGapExtCount() const { return m_Hit.intgaps - m_Hit.opens; }
+	unsigned GetLetterPairCount() const { return m_Hit.ids + m_Hit.mism; }
+	unsigned GetDiffCount() const { return m_Hit.mism + m_Hit.intgaps; }
+	unsigned GetPathLength() const;
+	unsigned GetAllGapCount() const { return m_Hit.intgaps + (GetPathLength() - m_Hit.alnlen); }
+	// global alignments: the HSP spans both sequences (alignresult.cpp:137-145)
+	unsigned GetIQLo1() const { return 1; }
+	unsigned GetIQHi1() const { return m_Hit.ql; }
+	unsigned GetITLo1() const { return 1; }
+	unsigned GetITHi1() const { return m_Hit.tl; }
+	unsigned GetTLo6() const { return m_Hit.strand ? GetITHi1() : GetITLo1(); } // arscorer.cpp:748-808
+	unsigned GetTHi6() const { return m_Hit.strand ? GetITLo1() : GetITHi1(); }
+	unsigned GetQLoT() const { return m_Hit.first_mq; }
+	unsigned GetQHiT() const { return m_Hit.last_mq; }
+	unsigned GetTLoT() const { return m_Hit.first_mt; }
+	unsigned GetTHiT() const { return m_Hit.last_mt; }
+	unsigned GetQUnT() const { return m_Hit.ql - m_Hit.last_mq - 1; }
+	unsigned GetTUnT() const { return m_Hit.tl - m_Hit.last_mt - 1; }
+	char GetQueryStrand() const { return m_Hit.strand ? '-' : '+'; }
+	char GetTargetStrand() const { return '+'; }
+	void GetPath(std::string &Path) const;           // pathinfo.cpp:37-214
+	void GetCompressedPath(std::string &CPath) const; // comppath.cpp:7-48
+};
+
+// Per-query hit list in output order (hitmgr.cpp).
+class HitMgr {
+public:
+	SeqInfo m_Query;
+	std::vector<AlignResult> m_Hits;
+	unsigned GetHitCount() const { return (unsigned)m_Hits.size(); }
+	const AlignResult *GetTopHit() const { return m_Hits.empty() ? nullptr : &m_Hits[0]; }
+};
+
+class HitSink {
+public:
+	virtual ~HitSink() {}
+	virtual void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) = 0;
+	virtual void OnAllDone() {}
+};
+
+struct OutputOpts {
+	std::string uc, blast6out, userout, userfields;
+	bool output_no_hits = false;
+};
+
+// outputsink.cpp:358-381; formats of outputuc.cpp:19-69, blast6out.cpp:27-80, userout.cpp:126-215
+class OutputSink : public HitSink {
+public:
+	explicit OutputSink(const OutputOpts &O);
+	~OutputSink() override;
+	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
+	void OnAllDone() override;
+
+private:
+	void Flush(FILE *f, std::string &buf, bool force);
+	void OutputUC(const SeqInfo &Query, const HitMgr &HM);
+	void OutputBlast6(const HitMgr &HM);
+	void OutputUser(const HitMgr &HM);
+	FILE *m_fUC = nullptr, *m_fB6 = nullptr, *m_fUser = nullptr;
+	std::string m_bUC, m_bB6, m_bUser;
+	std::vector<int> m_UserFields;
+};
+
+// Abstract searcher (searcher.h:21-96), batched.
+class Searcher {
+public:
+	virtual ~Searcher() {}
+	// Searches queries [First, First+Count) of Queries and appends one HitMgr per query to Out.
+	virtual void SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out) = 0;
+};
+
+// UDBUsortedSearcher + GlobalAligner + Accepter + Terminator on one GPU.
+class GpuSearcher : public Searcher {
+public:
+	GpuSearcher(int Device, const SeqDB &DB, const usb_params &P);
+	~GpuSearcher() override;
+	void SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out) override;
+	uint64_t GetLaunchCount() const;
+	// AlignResults of a batch point into a run arena owned here; release it once the sinks ran
+	void ReleaseArenas();
+
+private:
+	std::vector<std::shared_ptr<std::vector<uint32_t>>> m_Arenas;
+	const SeqDB &m_DB;
+	usb_index *m_Index = nullptr;
+	usb_searcher *m_Searcher = nullptr;
+};
+
+struct SearchOpts {
+	usb_params P;
+	OutputOpts Out;
+	int gpus = 1;
+	uint32_t batch = 1u << 18;
+	bool quiet = false;
+};
+
+// search.cpp:89 Search(): returns the number of queries with at least one hit.
+uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts);
+
+} // namespace usbhost
