@@ -144,3 +144,26 @@ def test_align_pairs_match_oracle(env):
             assert res.path(res.hits[b]) == opath, (k, idx[pq[k]], pt[k])
             n_al += 1
     assert n_al > 50
+
+
+@pytest.mark.parametrize("big,id_,stepwords", [(100, 0.97, 8), (100, 0.8, 8), (50, 0.97, 0)])
+def test_big_database_path_matches_oracle(env, big, id_, stepwords):
+    """UDBSearchBig (udbusortedsearcherbig.cpp): DB larger than -big; candidate order and whole
+    searches against the oracle, which is pinned on this path by tools/pin_oracle.sh with a
+    120 000-sequence DB."""
+    capi, O, g = env["capi"], env["O"], env["g"]
+    p = capi.default_params(big=big, id=id_, stepwords=stepwords)
+    ix = capi.Index(g.db, p)
+    s = capi.Searcher(ix, p)
+    op = O.default_params(big=big, id=id_, stepwords=stepwords)
+    odb = O.DB(g.db, op, g.db_labels)
+    osr = O.Searcher(odb, op)
+    idx = list(range(0, 150)) + list(range(2400, 2700, 3))
+    seqs = [q for q in (g.q[i] for i in idx) if len(q) <= 4000]
+    labels = ["q%d" % i for i in range(len(seqs))]
+    res = s.search(seqs)
+    got = util.product_lines(res, labels, seqs, g.db_labels)
+    want = util.oracle_lines(osr, labels, seqs, g.db_labels)
+    for a, b, kind in zip(got, want, ("user", "uc", "b6")):
+        assert util.first_diff(a, b) is None, kind
+    assert len(got[0]) > 50

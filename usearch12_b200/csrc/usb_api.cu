@@ -11,6 +11,7 @@
 #include "usb_align.cuh"
 #include "usb_hostindex.h"
 #include "usb_rank.cuh"
+#include "usb_rankbig.cuh"
 
 using namespace usb;
 
@@ -140,8 +141,10 @@ struct usb_searcher {
 	DevBuf<usb_hit> d_hits;
 	DevBuf<usb_qstat> d_qstat;
 	DevBuf<DevCounters> d_ctr;
-	DevBuf<uint8_t> d_slab;
+	DevBuf<uint8_t> d_slab, d_uarena;
 	size_t rank_smem_set = 0;
+	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
+	bool bigsmem_set = false;
 };
 
 static bool is_int2(float x) { return std::floor(2.0 * (double)x) == 2.0 * (double)x; }
@@ -289,13 +292,10 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 		return rc;
 	if (p->word_length != ix->P.word_length)
 		return fail(USB_EINVAL, "searcher word_length %u != index word_length %u", p->word_length, ix->P.word_length);
-	if (ix->H.n_seq > p->big)
-		return fail(USB_EINVAL,
-		  "DB has %u sequences > -big %u: the UDBSearchBig path (udbusortedsearcherbig.cpp) is not built yet",
-		  ix->H.n_seq, p->big);
 	CK(cudaSetDevice(ix->device));
 	usb_searcher *s = new usb_searcher;
 	s->ix = ix;
+	s->big = ix->H.n_seq > p->big;
 	s->P = *p;
 	s->D = D;
 	cudaDeviceProp prop;
@@ -322,7 +322,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 		cudaStreamSynchronize(s->stream);
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release();
-	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release();
+	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
 	for (auto &e : s->ev)
 		if (e)
 			cudaEventDestroy(e);
@@ -381,6 +381,50 @@ static int upload_queries(usb_searcher *s, const uint8_t *qseqs, const uint64_t 
 	return 0;
 }
 
+// K1b launch: persistent CTAs, each with its own counter array in global memory.
+static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
+{
+	const usb_index *ix = s->ix;
+	const uint32_t N = ix->H.n_seq;
+	if (s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > BIG_MAX_POS)
+		return fail(USB_ELIMIT, "big-database path supports queries up to %u letters (got %u)",
+		  BIG_MAX_POS + s->D.word_length - 1, s->max_ql);
+	RankBigArgs a;
+	memset(&a, 0, sizeof a);
+	a.P = s->D;
+	a.q = s->d_q.p;
+	a.q_off = s->d_qoff.p;
+	a.n_jobs = n_jobs;
+	a.strands = strands;
+	a.row_off = ix->d_row_off.p;
+	a.postings = ix->d_postings.p;
+	a.row_size = ix->d_row_size.p;
+	a.n_seq = N;
+	a.k_max = k_max;
+	a.cand_t = s->d_cand_t.p;
+	a.cand_u = s->d_cand_u.p;
+	a.n_cand = s->d_ncand.p;
+	a.n_emit = s->d_nemit.p;
+	a.u_out = want_u ? s->d_uout.p : nullptr;
+	a.stepwords = s->P.stepwords;
+	a.ctr = s->d_ctr.p;
+	a.u_stride = (((uint64_t)N * 2 + 64) + 255) & ~(uint64_t)255;
+	const uint32_t grid = std::min<uint32_t>(n_jobs, (uint32_t)s->num_sms * 2);
+	int rc = s->d_uarena.reserve((size_t)grid * a.u_stride);
+	if (rc)
+		return rc;
+	a.u_arena = s->d_uarena.p;
+	const size_t smem = sizeof(RankBigShared);
+	if (!s->bigsmem_set) {
+		CK(cudaFuncSetAttribute(k_rank_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		s->bigsmem_set = true;
+	}
+	k_rank_big<<<grid, RANK_THREADS, smem, s->stream>>>(a);
+	CK(cudaGetLastError());
+	++s->launches;
+	return 0;
+}
+
 static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
 {
 	const usb_index *ix = s->ix;
@@ -393,6 +437,8 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		return rc;
 	if (n_jobs == 0)
 		return 0;
+	if (s->big)
+		return launch_rank_big(s, n_jobs, strands, k_max, want_u);
 	RankArgs a;
 	memset(&a, 0, sizeof a);
 	a.P = s->D;

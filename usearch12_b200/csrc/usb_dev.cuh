@@ -47,6 +47,8 @@ struct DevCounters {
 	uint32_t n_runs;
 	uint32_t err;
 	unsigned long long postings; // UDB postings walked by k_rank
+	uint32_t job_rank;           // job cursor of k_rank_big
+	uint32_t pad;
 };
 
 struct HspRec {

@@ -1,0 +1,451 @@
+// usb_rankbig.cuh -- kernel K1b: candidate ranking for big databases (more than -big targets),
+// the counterpart of UDBUsortedSearcher::UDBSearchBig (udbusortedsearcherbig.cpp:31-135).
+//
+// Reference behaviour reproduced:
+//   a8  GetWordCountingParams: QueryStep from -id and -stepwords   wordparams.cpp:125-192
+//       unique query words in first-occurrence order, every QueryStep-th one is counted
+//       candidates = touched targets in first-touch order                udbusortedsearcherbig.cpp:82-100
+//       CountSortSubsetDesc: drop U < NextValue/2, stable descending       countsort.cpp:110-191
+//
+// Design: the counter array is too large for shared memory here (one byte or halfword per target,
+// millions of targets), so every resident CTA owns a counter array in global memory that stays in
+// L2; the few sampled posting rows (about 11 at -id 0.97 for 250 bp reads) are walked by all
+// warps with fire-and-forget packed atomic adds.  The reference's order-dependent parts are
+// derived without storing the touch order:
+//   * first-touch rank of a target = (first sampled row containing it, target index), because
+//     rows are walked in word order and are ascending;
+//   * NextValue (running max before its last increase, in first-touch order) = max U over the
+//     targets that precede p*, the first-touched target holding the global max; those are exactly
+//     the entries of the sampled rows before p*'s row plus the entries of that row below p*.
+// Survivors (U >= NextValue/2) are usually few: they get their first-row by binary search in the
+// sampled rows and are bitonic-sorted by (U desc, first row, target).  When more than 1024
+// survive, the first k_max of that order are selected instead (radix-select on U, ties at the
+// cut taken row by row in first-touch order).
+#pragma once
+#include "usb_rank.cuh"
+
+namespace usb {
+
+#define BIG_MAX_POS 4096   // query word positions supported by the big path
+#define BIG_MAX_ROWS BIG_MAX_POS // sampled rows per query (QueryStep can be 1)
+
+struct RankBigArgs {
+	DevParams P;
+	const uint8_t *q;
+	const uint64_t *q_off;
+	uint32_t n_jobs, strands;
+	const uint64_t *row_off;
+	const uint32_t *row_size;
+	const uint32_t *postings;
+	uint32_t n_seq;
+	uint32_t k_max;
+	uint32_t *cand_t, *cand_u, *n_cand, *n_emit;
+	uint32_t *u_out;           // optional: n_jobs * n_seq
+	uint8_t *u_arena;          // gridDim.x counter arrays of u_stride bytes
+	uint64_t u_stride;         // >= 2 * n_seq, multiple of 16
+	uint32_t stepwords;
+	DevCounters *ctr;
+};
+
+struct RankBigShared {
+	uint32_t n_uniq, n_rows, row_cur, n_surv, n_sel, found, gmax, kstar, tstar, nextv, vstar, above, m_eq, taken;
+	uint32_t n_post;
+	uint32_t warp_tmp[32];
+	uint32_t hist[256];
+	uint32_t words[BIG_MAX_POS];     // word per position (0xffffffff = bad)
+	uint32_t uniq[BIG_MAX_POS];      // unique words, first-occurrence order
+	uint32_t rows[BIG_MAX_ROWS];     // sampled words
+	unsigned long long sel[RANK_KCAP];
+};
+
+__device__ __forceinline__ uint32_t block_reduce_max(uint32_t v, uint32_t *warp_tmp)
+{
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	v = __reduce_max_sync(USB_FULL, v);
+	if (lane == 0)
+		warp_tmp[w] = v;
+	__syncthreads();
+	uint32_t r = warp_tmp[lane];
+	r = __reduce_max_sync(USB_FULL, r);
+	__syncthreads();
+	return r;
+}
+
+__device__ __forceinline__ uint32_t block_reduce_min(uint32_t v, uint32_t *warp_tmp)
+{
+	const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	v = __reduce_min_sync(USB_FULL, v);
+	if (lane == 0)
+		warp_tmp[w] = v;
+	__syncthreads();
+	uint32_t r = warp_tmp[lane];
+	r = __reduce_min_sync(USB_FULL, r);
+	__syncthreads();
+	return r;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ uint32_t ug_get(const uint8_t *U, uint32_t t)
+{
+	return WIDE ? (uint32_t)((const volatile uint16_t *)U)[t] : (uint32_t)((const volatile uint8_t *)U)[t];
+}
+
+// index of the first sampled row that contains target t (rows ascending), or n_rows
+__device__ __forceinline__ uint32_t first_row_of(const RankBigArgs &a, const RankBigShared &S, uint32_t t,
+  uint32_t row_limit)
+{
+	for (uint32_t k = 0; k < row_limit; ++k) {
+		const uint32_t word = S.rows[k];
+		const uint32_t *row = a.postings + a.row_off[word];
+		uint32_t lo = 0, hi = a.row_size[word];
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (__ldg(row + mid) < t)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		if (lo < a.row_size[word] && __ldg(row + lo) == t)
+			return k;
+	}
+	return row_limit;
+}
+
+__device__ __forceinline__ unsigned long long big_key(uint32_t u, uint32_t k, uint32_t t)
+{
+	return ((unsigned long long)(0xFFFFu - u) << 48) | ((unsigned long long)(k & 0xFFFFu) << 32) | t;
+}
+
+template <bool WIDE>
+__device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &S, uint8_t *U, uint32_t n_rows)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t N = a.n_seq;
+	uint32_t *U32 = (uint32_t *)U;
+	const uint32_t PER = WIDE ? 2 : 4;
+	const uint32_t n_words32 = (N + PER - 1) / PER;
+
+	// ---- zero the counters (global, L2 resident)
+	{
+		uint4 *U128 = (uint4 *)U;
+		const uint32_t n128 = (n_words32 + 3) / 4;
+		for (uint32_t i = tid; i < n128; i += RANK_THREADS)
+			U128[i] = make_uint4(0, 0, 0, 0);
+	}
+	__syncthreads();
+
+	// ---- count: warps take sampled rows from a shared cursor; packed fire-and-forget adds
+	{
+		uint32_t my_post = 0;
+		for (;;) {
+			uint32_t r = 0;
+			if (lane == 0)
+				r = atomicAdd(&S.row_cur, 1u);
+			r = __shfl_sync(USB_FULL, r, 0);
+			if (r >= n_rows)
+				break;
+			const uint32_t word = S.rows[r];
+			const uint32_t size = a.row_size[word];
+			const uint32_t *row = a.postings + a.row_off[word];
+			my_post += size;
+			for (uint32_t i = lane; i < size; i += 32) {
+				const uint32_t t = __ldg(row + i);
+				if (WIDE)
+					atomicAdd(&U32[t >> 1], 1u << ((t & 1) * 16));
+				else
+					atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
+			}
+		}
+		if (lane == 0 && my_post)
+			atomicAdd(&S.n_post, my_post);
+	}
+	__threadfence();
+	__syncthreads();
+
+	if (a.u_out)
+		for (uint32_t t = tid; t < N; t += RANK_THREADS)
+			a.u_out[(uint64_t)job * N + t] = ug_get<WIDE>(U, t);
+
+	// ---- global max of U
+	uint32_t m = 0;
+	{
+		uint32_t acc = 0;
+		const volatile uint32_t *V = (const volatile uint32_t *)U32;
+		for (uint32_t i = tid; i < n_words32; i += RANK_THREADS)
+			acc = WIDE ? __vmaxu2(acc, V[i]) : __vmaxu4(acc, V[i]);
+		m = WIDE ? max(acc & 0xffff, acc >> 16) : max(max(acc & 0xff, (acc >> 8) & 0xff), max((acc >> 16) & 0xff, acc >> 24));
+	}
+	const uint32_t gmax = block_reduce_max(m, S.warp_tmp);
+	uint32_t total = 0, nsel = 0;
+	if (gmax > 0) {
+		// ---- p* = first-touched target holding gmax: first sampled row with such a target, lowest t
+		uint32_t kstar = 0, tstar = 0xffffffffu;
+		for (uint32_t k = 0; k < n_rows; ++k) {
+			const uint32_t word = S.rows[k];
+			const uint32_t size = a.row_size[word];
+			const uint32_t *row = a.postings + a.row_off[word];
+			uint32_t best = 0xffffffffu;
+			for (uint32_t i = tid; i < size; i += RANK_THREADS) {
+				const uint32_t t = __ldg(row + i);
+				if (ug_get<WIDE>(U, t) == gmax)
+					best = min(best, t);
+			}
+			best = block_reduce_min(best, S.warp_tmp);
+			if (best != 0xffffffffu) {
+				kstar = k;
+				tstar = best;
+				break;
+			}
+		}
+		// ---- NextValue = max U over everything touched before p*
+		uint32_t nv = 0;
+		for (uint32_t k = 0; k <= kstar; ++k) {
+			const uint32_t word = S.rows[k];
+			const uint32_t size = a.row_size[word];
+			const uint32_t *row = a.postings + a.row_off[word];
+			for (uint32_t i = tid; i < size; i += RANK_THREADS) {
+				const uint32_t t = __ldg(row + i);
+				if (k == kstar && t >= tstar)
+					break; // ascending row: the rest of this thread's stride is beyond p* too
+				const uint32_t u = ug_get<WIDE>(U, t);
+				if (u != gmax || k < kstar) // (targets with U == gmax before p* cannot exist)
+					nv = max(nv, u);
+			}
+		}
+		const uint32_t nextv = block_reduce_max(nv, S.warp_tmp);
+		const uint32_t minv = max(nextv / 2, 1u);
+
+		// ---- survivors
+		{
+			const volatile uint32_t *V = (const volatile uint32_t *)U32;
+			const uint32_t thr_v = WIDE ? minv * 0x00010001u : minv * 0x01010101u;
+			const bool possible = minv <= (WIDE ? 0xffffu : 0xffu);
+			for (uint32_t i = tid; possible && i < n_words32; i += RANK_THREADS) {
+				const uint32_t word = V[i];
+				uint32_t mask = WIDE ? __vcmpgeu2(word, thr_v) : __vcmpgeu4(word, thr_v);
+				while (mask) {
+					const uint32_t b = (uint32_t)(__ffs(mask) - 1) / (WIDE ? 16 : 8);
+					mask &= ~((WIDE ? 0xffffu : 0xffu) << (b * (WIDE ? 16 : 8)));
+					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+					const uint32_t t = i * PER + b;
+					const uint32_t slot = atomicAdd(&S.n_surv, 1u);
+					if (slot < RANK_KCAP)
+						S.sel[slot] = ((unsigned long long)u << 32) | t;
+				}
+			}
+		}
+		__syncthreads();
+		total = S.n_surv;
+		if (total <= RANK_KCAP) {
+			for (uint32_t i = tid; i < total; i += RANK_THREADS) {
+				const unsigned long long e = S.sel[i];
+				const uint32_t t = (uint32_t)e, u = (uint32_t)(e >> 32);
+				S.sel[i] = big_key(u, first_row_of(a, S, t, n_rows), t);
+			}
+			__syncthreads();
+			block_sort_keys(S.sel, total);
+			nsel = min(total, a.k_max);
+		} else {
+			// ---- rare: select the first k_max of (U desc, first-touch order)
+			for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+				S.hist[i] = 0;
+			if (tid == 0) {
+				S.n_sel = 0;
+				S.taken = 0;
+			}
+			__syncthreads();
+			const volatile uint32_t *V = (const volatile uint32_t *)U32;
+			// radix select on U (two levels when WIDE)
+			for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
+				const uint32_t word = V[i];
+				for (uint32_t b = 0; b < PER; ++b) {
+					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+					if (u >= minv)
+						atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
+				}
+			}
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t cum = 0;
+				for (int b = 255; b >= 0; --b) {
+					cum += S.hist[b];
+					if (cum >= a.k_max) {
+						S.vstar = (uint32_t)b;
+						S.above = cum - S.hist[b];
+						break;
+					}
+				}
+				S.m_eq = a.k_max - S.above;
+			}
+			__syncthreads();
+			if (WIDE) {
+				const uint32_t bstar = S.vstar;
+				for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+					S.hist[i] = 0;
+				__syncthreads();
+				for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
+					const uint32_t word = V[i];
+					for (uint32_t b = 0; b < PER; ++b) {
+						const uint32_t u = (word >> (b * 16)) & 0xffffu;
+						if (u >= minv && (u >> 8) == bstar)
+							atomicAdd(&S.hist[u & 255], 1u);
+					}
+				}
+				__syncthreads();
+				if (tid == 0) {
+					uint32_t cum = S.above;
+					for (int b = 255; b >= 0; --b) {
+						cum += S.hist[b];
+						if (cum >= a.k_max) {
+							S.vstar = (bstar << 8) | (uint32_t)b;
+							S.above = cum - S.hist[b];
+							break;
+						}
+					}
+					S.m_eq = a.k_max - S.above;
+				}
+				__syncthreads();
+			}
+			const uint32_t vstar = S.vstar, m_eq = S.m_eq;
+			// everything above the cut value
+			for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
+				const uint32_t word = V[i];
+				for (uint32_t b = 0; b < PER; ++b) {
+					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+					if (u > vstar) {
+						const uint32_t t = i * PER + b;
+						const uint32_t slot = atomicAdd(&S.n_sel, 1u);
+						if (slot < RANK_KCAP)
+							S.sel[slot] = big_key(u, first_row_of(a, S, t, n_rows), t);
+					}
+				}
+			}
+			__syncthreads();
+			// ties at the cut: row by row in first-touch order until m_eq are taken
+			for (uint32_t k = 0; k < n_rows && S.taken < m_eq; ++k) {
+				const uint32_t word = S.rows[k];
+				const uint32_t size = a.row_size[word];
+				const uint32_t *row = a.postings + a.row_off[word];
+				for (uint32_t base = 0; base < size && S.taken < m_eq; base += RANK_THREADS) {
+					const uint32_t i = base + tid;
+					uint32_t t = 0;
+					bool hit = false;
+					if (i < size) {
+						t = __ldg(row + i);
+						hit = ug_get<WIDE>(U, t) == vstar && first_row_of(a, S, t, k) == k;
+					}
+					const uint32_t rank = block_excl_scan_sum(hit ? 1u : 0u, S.warp_tmp);
+					const uint32_t already = S.taken;
+					__syncthreads();
+					if (hit && already + rank < m_eq) {
+						const uint32_t slot = atomicAdd(&S.n_sel, 1u);
+						if (slot < RANK_KCAP)
+							S.sel[slot] = big_key(vstar, k, t);
+						atomicAdd(&S.taken, 1u);
+					}
+					__syncthreads();
+				}
+			}
+			__syncthreads();
+			nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
+			block_sort_keys(S.sel, nsel);
+		}
+	}
+	for (uint32_t i = tid; i < nsel; i += RANK_THREADS) {
+		const unsigned long long key = S.sel[i];
+		a.cand_t[(uint64_t)job * a.k_max + i] = (uint32_t)key;
+		if (a.cand_u)
+			a.cand_u[(uint64_t)job * a.k_max + i] = 0xFFFFu - (uint32_t)(key >> 48);
+	}
+	if (tid == 0) {
+		a.n_cand[job] = total;
+		a.n_emit[job] = nsel;
+		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(RANK_THREADS, 1) k_rank_big(const RankBigArgs a)
+{
+	extern __shared__ __align__(16) uint8_t rankbig_smem[];
+	RankBigShared &S = *(RankBigShared *)rankbig_smem;
+	const uint32_t tid = threadIdx.x;
+	uint8_t *U = a.u_arena + (uint64_t)blockIdx.x * a.u_stride;
+	const uint32_t WLEN = a.P.word_length;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0)
+			S.found = atomicAdd(&a.ctr->job_rank, 1u);
+		__syncthreads();
+		const uint32_t job = S.found;
+		if (job >= a.n_jobs)
+			break;
+		const uint32_t qi = job / a.strands, strand = job % a.strands;
+		const uint64_t q0 = a.q_off[qi];
+		const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
+		const uint8_t *Q = a.q + q0;
+		const uint32_t npos = L >= WLEN ? min(L - WLEN + 1, (uint32_t)BIG_MAX_POS) : 0;
+		// ---- words per position
+		for (uint32_t p = tid; p < npos; p += RANK_THREADS) {
+			uint32_t word = 0, bad = 0;
+			for (uint32_t i = 0; i < WLEN; ++i) {
+				uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - (p + i)]] : (uint32_t)Q[p + i];
+				uint32_t l = udb_letter(c);
+				bad |= l >> 2;
+				word = (word << 2) | (l & 3);
+			}
+			S.words[p] = bad ? 0xffffffffu : word;
+		}
+		if (tid == 0) {
+			S.n_uniq = 0; S.row_cur = 0; S.n_surv = 0; S.n_sel = 0; S.n_post = 0;
+		}
+		__syncthreads();
+		// ---- unique words in first-occurrence order (udbsearcher.cpp:161-194): ordered compaction
+		uint32_t base_cnt = 0;
+		for (uint32_t base = 0; base < npos; base += RANK_THREADS) {
+			const uint32_t p = base + tid;
+			bool first = false;
+			uint32_t w = 0xffffffffu;
+			if (p < npos) {
+				w = S.words[p];
+				first = w != 0xffffffffu;
+				for (uint32_t qpos = 0; first && qpos < p; ++qpos)
+					first = S.words[qpos] != w;
+			}
+			const uint32_t rank = block_excl_scan_sum(first ? 1u : 0u, S.warp_tmp);
+			if (first)
+				S.uniq[base_cnt + rank] = w;
+			// total of this chunk = rank + flag of the last thread
+			if (tid == RANK_THREADS - 1)
+				S.n_uniq = base_cnt + rank + (first ? 1u : 0u);
+			__syncthreads();
+			base_cnt = S.n_uniq;
+		}
+		const uint32_t nu = base_cnt;
+		// ---- QueryStep (wordparams.cpp:125-192), double arithmetic without fused multiply-add
+		uint32_t Thresh = 1;
+		{
+			const double WordFract = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, a.P.id_d), (double)WLEN));
+			if (!(WordFract < 0.0)) {
+				const double x = __dmul_rn(WordFract, (double)nu);
+				Thresh = x < 1.0 ? 1u : (uint32_t)x;
+			}
+		}
+		uint32_t Step = 1;
+		if (a.stepwords != 0) {
+			Step = Thresh / a.stepwords;
+			if (Step == 0)
+				Step = 1;
+		}
+		const uint32_t n_rows = min((nu + Step - 1) / Step, (uint32_t)BIG_MAX_ROWS);
+		for (uint32_t r = tid; r < n_rows; r += RANK_THREADS)
+			S.rows[r] = S.uniq[r * Step];
+		__syncthreads();
+		if (n_rows > 255)
+			rank_big_job<true>(a, job, S, U, n_rows);
+		else
+			rank_big_job<false>(a, job, S, U, n_rows);
+	}
+}
+
+} // namespace usb
