@@ -95,6 +95,10 @@ int usb_device_count(void);
  * seqs = concatenated target letters, seq_off[n_seq+1] byte offsets.  Sequences are copied. */
 int usb_index_create(int device, const usb_params *p, const uint8_t *seqs, const uint64_t *seq_off,
   uint32_t n_seq, usb_index **out);
+/* Appends n targets (indexes N..N+n-1) to a live index: UDBData::AddSIToDB_CopyData
+ * (udbbuild.cpp:286 -> AddSeqNoncoded :256 -> AddWord/GrowRow :111,:74), as cluster_fast does for
+ * every new centroid.  Searchers created on the index see the new targets on their next batch. */
+int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n);
 void usb_index_free(usb_index *ix);
 uint32_t usb_index_seq_count(const usb_index *ix);
 uint64_t usb_index_posting_count(const usb_index *ix);

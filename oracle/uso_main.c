@@ -62,8 +62,168 @@ static void read_fasta(const char *fn, fasta *F)
 	fclose(f);
 	}
 
+
+/* ------------------------------------------------------------------ cluster_fast
+ * clusterfast.cpp:81-133 with -threads 1: dereplicate (derepfull.cpp:130-212; equality is
+ * case-insensitive, seqhash.cpp:6-51; uniques in first-occurrence order), optional -sort, then the
+ * serial greedy loop: search the unique against the centroids so far (Terminator 1 accept /
+ * 8 rejects, terminator.cpp:10-14); no hit -> new centroid appended to the growing UDB
+ * (clustersink.cpp:306-330, udbbuild.cpp:286).  Output: .uc S/H records incl. the duplicate
+ * members (outputuc.cpp:9-92), C records (clustersink.cpp:477-492), centroids FASTA in decreasing
+ * cluster size order (clustersink.cpp:246-272, sort.h:63-102), 80 letters per line. */
+static int seq_eq_ci(const uint8_t *a, const uint8_t *b, uint32_t L)
+	{
+	for (uint32_t i = 0; i < L; ++i)
+		if (toupper(a[i]) != toupper(b[i]))
+			return 0;
+	return 1;
+	}
+
+static void qsort_order_desc_u(const unsigned *v, int left, int right, unsigned *order)
+	{
+	int i = left, j = right;
+	unsigned pivot = v[order[(left + right) / 2]];
+	while (i <= j)
+		{
+		while (v[order[i]] > pivot) i++;
+		while (v[order[j]] < pivot) j--;
+		if (i <= j)
+			{
+			unsigned t = order[i]; order[i] = order[j]; order[j] = t;
+			i++; j--;
+			}
+		}
+	if (left < j) qsort_order_desc_u(v, left, j, order);
+	if (i < right) qsort_order_desc_u(v, i, right, order);
+	}
+
+static int cluster_fast_main(int argc, char **argv)
+	{
+	/* uso_cli cluster_fast READS.fa ID UC CENTROIDS [sort: none|length|size] */
+	if (argc < 6)
+		{
+		fprintf(stderr, "usage: uso_cli cluster_fast READS.fa ID UC CENTROIDS [none|length|size]\n");
+		return 2;
+		}
+	uso_params P;
+	uso_default_params(&P, 1);
+	P.id = (float) atof(argv[3]);
+	const char *sortname = argc > 6 ? argv[6] : "none";
+	fasta R;
+	read_fasta(argv[2], &R);
+	/* dereplication: open hash on upper-cased letters */
+	unsigned nb = 1;
+	while (nb < 2 * R.n + 16) nb <<= 1;
+	int *bucket = malloc(nb * sizeof(int));
+	for (unsigned i = 0; i < nb; ++i) bucket[i] = -1;
+	unsigned *uniq_of = malloc((R.n + 1) * sizeof(unsigned));   /* read -> unique index */
+	unsigned *first = malloc((R.n + 1) * sizeof(unsigned));     /* unique -> first read */
+	unsigned *usize = calloc(R.n + 1, sizeof(unsigned));
+	unsigned nu = 0;
+	for (unsigned i = 0; i < R.n; ++i)
+		{
+		uint32_t h = 2166136261u;
+		for (uint32_t k = 0; k < R.lens[i]; ++k)
+			h = (h ^ (uint32_t) toupper(R.seqs[i][k])) * 16777619u;
+		unsigned b = h & (nb - 1);
+		for (;;)
+			{
+			if (bucket[b] < 0)
+				{
+				bucket[b] = (int) nu;
+				first[nu] = i;
+				uniq_of[i] = nu++;
+				break;
+				}
+			unsigned f = first[bucket[b]];
+			if (R.lens[f] == R.lens[i] && seq_eq_ci(R.seqs[f], R.seqs[i], R.lens[i]))
+				{
+				uniq_of[i] = (unsigned) bucket[b];
+				break;
+				}
+			b = (b + 1) & (nb - 1);
+			}
+		++usize[uniq_of[i]];
+		}
+	unsigned *order = malloc((nu + 1) * sizeof(unsigned));
+	for (unsigned u = 0; u < nu; ++u) order[u] = u;
+	if (strcmp(sortname, "length") == 0 || strcmp(sortname, "size") == 0)
+		{
+		unsigned *v = malloc((nu + 1) * sizeof(unsigned));
+		for (unsigned u = 0; u < nu; ++u)
+			v[u] = sortname[0] == 'l' ? R.lens[first[u]] : usize[u];
+		if (nu > 0)
+			qsort_order_desc_u(v, 0, (int) nu - 1, order);
+		free(v);
+		}
+	uso_db *db = uso_db_create(&P);
+	uso_searcher *s = uso_searcher_create(db, &P);
+	FILE *fc = fopen(argv[4], "w");
+	unsigned *csize = calloc(nu + 1, sizeof(unsigned));
+	unsigned *centroid_read = malloc((nu + 1) * sizeof(unsigned));
+	unsigned nclust = 0;
+	uso_hit *hits = 0; unsigned nh = 0, cap = 0;
+	char *cp = malloc(1 << 20);
+	for (unsigned k = 0; k < nu; ++k)
+		{
+		unsigned u = order[k];
+		unsigned r0 = first[u];
+		nh = 0;
+		unsigned n = uso_search(s, u, R.seqs[r0], R.lens[r0], &hits, &nh, &cap);
+		if (n == 0)
+			{
+			unsigned c = uso_db_add(db, R.seqs[r0], R.lens[r0], R.labels[r0]);
+			centroid_read[c] = r0;
+			csize[c] = usize[u];
+			nclust = c + 1;
+			fprintf(fc, "S\t%u\t%u\t*\t.\t*\t*\t*\t%s\t*\n", c, R.lens[r0], R.labels[r0]);
+			for (unsigned i = r0 + 1; i < R.n; ++i)
+				if (uniq_of[i] == u)
+					fprintf(fc, "H\t%u\t%u\t100.0\t.\t0\t%u\t=\t%s\t%s\n", c, R.lens[r0], R.lens[r0], R.labels[i], R.labels[r0]);
+			}
+		else
+			{
+			const uso_hit *h = &hits[0];
+			unsigned c = h->target;
+			csize[c] += usize[u];
+			uso_compress_path(h->path, cp);
+			double pct = 100.0 * (h->alnlen == 0 ? 0.0 : (double) h->ids / (double) h->alnlen);
+			for (unsigned i = r0; i < R.n; ++i)
+				if (uniq_of[i] == u)
+					fprintf(fc, "H\t%u\t%u\t%.1f\t%c\t0\t0\t%s\t%s\t%s\n", c, R.lens[r0], pct, h->strand ? '-' : '+', cp,
+					  R.labels[i], uso_db_label(db, c));
+			for (unsigned i = 0; i < n; ++i)
+				free(hits[i].path);
+			}
+		}
+	for (unsigned c = 0; c < nclust; ++c)
+		fprintf(fc, "C\t%u\t%u\t*\t*\t*\t*\t*\t%s\t*\n", c, csize[c], uso_db_label(db, c));
+	fclose(fc);
+	FILE *ff = fopen(argv[5], "w");
+	unsigned *corder = malloc((nclust + 1) * sizeof(unsigned));
+	for (unsigned c = 0; c < nclust; ++c) corder[c] = c;
+	if (nclust > 0)
+		qsort_order_desc_u(csize, 0, (int) nclust - 1, corder);
+	for (unsigned k = 0; k < nclust; ++k)
+		{
+		unsigned c = corder[k];
+		uint32_t L;
+		const uint8_t *seq = uso_db_seq(db, c, &L);
+		fprintf(ff, ">%s\n", uso_db_label(db, c));
+		for (uint32_t i = 0; i < L; i += 80)
+			{
+			fwrite(seq + i, 1, L - i < 80 ? L - i : 80, ff);
+			fputc('\n', ff);
+			}
+		}
+	fclose(ff);
+	return 0;
+	}
+
 int main(int argc, char **argv)
 	{
+	if (argc >= 2 && strcmp(argv[1], "cluster_fast") == 0)
+		return cluster_fast_main(argc, argv);
 	if (argc < 9 || strcmp(argv[1], "usearch_global") != 0)
 		{
 		fprintf(stderr, "usage: uso_cli usearch_global Q.fa DB.fa ID plus|both USEROUT UC B6 [maxaccepts maxrejects]\n");

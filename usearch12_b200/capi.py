@@ -44,7 +44,7 @@ QSTAT_DTYPE = np.dtype([
 
 # every symbol include/usb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_free",
+    "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
     "usb_index_seq_count", "usb_index_posting_count", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
     "usb_batch_download", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
@@ -68,6 +68,7 @@ def lib():
     L.usb_default_params.argtypes = [C.POINTER(Params), C.c_int]
     L.usb_default_params.restype = None
     L.usb_index_create.argtypes = [C.c_int, C.POINTER(Params), vp, vp, C.c_uint32, C.POINTER(vp)]
+    L.usb_index_append.argtypes = [vp, vp, vp, C.c_uint32]
     L.usb_index_free.argtypes = [vp]
     L.usb_index_free.restype = None
     L.usb_index_seq_count.argtypes = [vp]
@@ -181,6 +182,12 @@ class Index:
                                      C.byref(h)))
         self.handle = h
         self.n_seq = len(seqs)
+
+    def append(self, seqs):
+        """UDBData::AddSIToDB_CopyData for a block of new targets (cluster_fast centroids)."""
+        data, off = pack_seqs(seqs)
+        check(lib().usb_index_append(self.handle, _ptr(data), _ptr(off), len(seqs)))
+        self.n_seq += len(seqs)
 
     def row(self, word):
         p = C.POINTER(C.c_uint32)()

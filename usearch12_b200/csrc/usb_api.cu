@@ -96,6 +96,26 @@ template <class T> struct DevBuf {
 		cap = want;
 		return 0;
 	}
+	// grows to hold n elements, keeping the first `used` (device-to-device copy), doubling
+	int grow_keep(size_t n, size_t used)
+	{
+		if (n <= cap)
+			return 0;
+		size_t want = std::max(n + n / 8 + 64, cap * 2);
+		T *q = nullptr;
+		cudaError_t e = cudaMalloc((void **)&q, want * sizeof(T));
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return fail(USB_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+		}
+		if (p && used)
+			cudaMemcpy(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice);
+		if (p)
+			cudaFree(p);
+		p = q;
+		cap = want;
+		return 0;
+	}
 	void release()
 	{
 		if (p)
@@ -105,14 +125,57 @@ template <class T> struct DevBuf {
 	}
 };
 
+// One immutable CSR segment of the index on the host and on the device.
+struct IndexSegment {
+	HostCSR H;
+	DevBuf<uint64_t> d_row_off;
+	DevBuf<uint32_t> d_row_size, d_postings;
+	int upload()
+	{
+		int rc;
+		if ((rc = d_row_off.reserve(H.row_off.size())) || (rc = d_row_size.reserve(H.row_size.size())) ||
+		    (rc = d_postings.reserve(H.postings.size())))
+			return rc;
+		CK(cudaMemcpy(d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
+		return 0;
+	}
+	void release()
+	{
+		d_row_off.release();
+		d_row_size.release();
+		d_postings.release();
+	}
+};
+
 struct usb_index {
 	int device = 0;
 	usb_params P;
-	HostIndex H;
+	HostSeqs S;                          // masked SeqDB (host copy)
+	std::vector<IndexSegment *> segs;    // ascending target ranges covering [0, S.n())
+	uint32_t n_dev = 0;                  // targets whose letters are on the device
+	uint64_t n_postings = 0;
 	DevBuf<uint8_t> d_seqs;
-	DevBuf<uint64_t> d_seq_off, d_row_off;
-	DevBuf<uint32_t> d_seq_len, d_postings, d_row_size;
+	DevBuf<uint64_t> d_seq_off;
+	DevBuf<uint32_t> d_seq_len;
+	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
+
+static void fill_index_view(const usb_index *ix, IndexView &v)
+{
+	memset(&v, 0, sizeof v);
+	v.n_seg = (uint32_t)ix->segs.size();
+	v.n_seq = ix->S.n();
+	for (uint32_t i = 0; i < v.n_seg; ++i) {
+		const IndexSegment *g = ix->segs[i];
+		v.seg[i].row_off = g->d_row_off.p;
+		v.seg[i].row_size = g->d_row_size.p;
+		v.seg[i].postings = g->d_postings.p;
+		v.seg[i].base = g->H.base;
+		v.seg[i].count = g->H.count;
+	}
+}
 
 struct usb_result {
 	std::vector<usb_hit> hits;
@@ -227,22 +290,64 @@ extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *
 	usb_index *ix = new usb_index;
 	ix->device = device;
 	ix->P = *p;
-	build_host_index(seqs, seq_off, n_seq, p->word_length, p->dbmask && !p->cluster_mode, 0, ix->H);
-	const HostIndex &H = ix->H;
-	if ((rc = ix->d_seqs.reserve(H.seqs.size())) || (rc = ix->d_seq_off.reserve(H.seq_off.size())) ||
-	    (rc = ix->d_seq_len.reserve(H.seq_len.size() + 1)) || (rc = ix->d_row_off.reserve(H.row_off.size())) ||
-	    (rc = ix->d_postings.reserve(H.postings.size())) || (rc = ix->d_row_size.reserve(H.row_size.size()))) {
+	*out = ix;
+	if (n_seq && (rc = usb_index_append(ix, seqs, seq_off, n_seq))) {
 		usb_index_free(ix);
+		*out = nullptr;
 		return rc;
 	}
-	CK(cudaMemcpy(ix->d_seqs.p, H.seqs.data(), H.seqs.size(), cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(ix->d_seq_off.p, H.seq_off.data(), H.seq_off.size() * 8, cudaMemcpyHostToDevice));
-	if (n_seq)
-		CK(cudaMemcpy(ix->d_seq_len.p, H.seq_len.data(), H.seq_len.size() * 4, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(ix->d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(ix->d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(ix->d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
-	*out = ix;
+	return 0;
+}
+
+// Appends targets [N, N+n): UDBData::AddSIToDB_CopyData (udbbuild.cpp:286) for a whole block.
+// The new targets form a CSR segment; neighbouring segments of similar size are concatenated
+// (log-structured merge) so that the number of row fragments per word stays logarithmic.
+extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n)
+{
+	if (!ix || !seq_off || (!seqs && n))
+		return fail(USB_EINVAL, "usb_index_append: null argument");
+	if (n == 0)
+		return 0;
+	CK(cudaSetDevice(ix->device));
+	const uint32_t n0 = ix->S.n();
+	if ((uint64_t)n0 + n > 0xfffffff0ull)
+		return fail(USB_ELIMIT, "too many targets");
+	for (uint32_t i = 0; i < n; ++i)
+		if (seq_off[i + 1] < seq_off[i] || seq_off[i + 1] - seq_off[i] > (1u << 24))
+			return fail(USB_EINVAL, "usb_index_append: bad offsets at target %u", i);
+	HostSeqs &S = ix->S;
+	S.append(seqs, seq_off, n, ix->P.dbmask && !ix->P.cluster_mode, 0);
+	int rc;
+	// letters and lengths of the new targets
+	const uint64_t b0 = S.seq_off[n0], b1 = S.seq_off[n0 + n];
+	if ((rc = ix->d_seqs.grow_keep(b1 + 16, b0)) || (rc = ix->d_seq_off.grow_keep((size_t)n0 + n + 1, (size_t)n0 + 1)) ||
+	    (rc = ix->d_seq_len.grow_keep((size_t)n0 + n + 1, n0)))
+		return rc;
+	CK(cudaMemcpy(ix->d_seqs.p + b0, S.seqs.data() + b0, b1 - b0 + 16, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_seq_off.p + n0, S.seq_off.data() + n0, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
+	ix->n_dev = n0 + n;
+	// new segment, then merge while the last two are of similar size (or the list is full)
+	IndexSegment *g = new IndexSegment;
+	build_csr(S, n0, n, ix->P.word_length, 0, g->H);
+	ix->n_postings += g->H.n_postings;
+	ix->segs.push_back(g);
+	bool dirty = true;
+	while (ix->segs.size() >= 2) {
+		IndexSegment *a = ix->segs[ix->segs.size() - 2], *b = ix->segs.back();
+		if (!(b->H.count * 2 >= a->H.count || ix->segs.size() > USB_MAX_SEG - 2))
+			break;
+		IndexSegment *m = new IndexSegment;
+		merge_csr(a->H, b->H, m->H);
+		a->release();
+		b->release();
+		delete a;
+		delete b;
+		ix->segs.pop_back();
+		ix->segs.back() = m;
+	}
+	if (dirty && (rc = ix->segs.back()->upload()))
+		return rc;
 	return 0;
 }
 
@@ -254,30 +359,36 @@ extern "C" void usb_index_free(usb_index *ix)
 	ix->d_seqs.release();
 	ix->d_seq_off.release();
 	ix->d_seq_len.release();
-	ix->d_row_off.release();
-	ix->d_postings.release();
-	ix->d_row_size.release();
+	for (IndexSegment *g : ix->segs) {
+		g->release();
+		delete g;
+	}
 	delete ix;
 }
 
-extern "C" uint32_t usb_index_seq_count(const usb_index *ix) { return ix ? ix->H.n_seq : 0; }
-extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->H.n_postings : 0; }
+extern "C" uint32_t usb_index_seq_count(const usb_index *ix) { return ix ? ix->S.n() : 0; }
+extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->n_postings : 0; }
 
 extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size)
 {
-	if (!ix || word >= ix->H.slots)
+	if (!ix || word >= (1u << (2 * ix->P.word_length)))
 		return fail(USB_EINVAL, "usb_index_row: bad word %u", word);
-	*row = ix->H.postings.data() + ix->H.row_off[word];
-	*size = ix->H.row_size[word];
+	std::vector<uint32_t> &tmp = const_cast<usb_index *>(ix)->row_tmp;
+	tmp.clear();
+	for (const IndexSegment *g : ix->segs)
+		tmp.insert(tmp.end(), g->H.postings.begin() + g->H.row_off[word],
+		  g->H.postings.begin() + g->H.row_off[word] + g->H.row_size[word]);
+	*row = tmp.data();
+	*size = (uint32_t)tmp.size();
 	return 0;
 }
 
 extern "C" int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t **seq, uint32_t *len)
 {
-	if (!ix || target >= ix->H.n_seq)
+	if (!ix || target >= ix->S.n())
 		return fail(USB_EINVAL, "usb_index_seq: bad target %u", target);
-	*seq = ix->H.seqs.data() + ix->H.seq_off[target];
-	*len = ix->H.seq_len[target];
+	*seq = ix->S.seqs.data() + ix->S.seq_off[target];
+	*len = ix->S.seq_len[target];
 	return 0;
 }
 
@@ -295,7 +406,7 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 	CK(cudaSetDevice(ix->device));
 	usb_searcher *s = new usb_searcher;
 	s->ix = ix;
-	s->big = ix->H.n_seq > p->big;
+	s->big = ix->S.n() > p->big;
 	s->P = *p;
 	s->D = D;
 	cudaDeviceProp prop;
@@ -385,7 +496,7 @@ static int upload_queries(usb_searcher *s, const uint8_t *qseqs, const uint64_t 
 static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
 {
 	const usb_index *ix = s->ix;
-	const uint32_t N = ix->H.n_seq;
+	const uint32_t N = ix->S.n();
 	if (s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > BIG_MAX_POS)
 		return fail(USB_ELIMIT, "big-database path supports queries up to %u letters (got %u)",
 		  BIG_MAX_POS + s->D.word_length - 1, s->max_ql);
@@ -396,9 +507,7 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 	a.q_off = s->d_qoff.p;
 	a.n_jobs = n_jobs;
 	a.strands = strands;
-	a.row_off = ix->d_row_off.p;
-	a.postings = ix->d_postings.p;
-	a.row_size = ix->d_row_size.p;
+	fill_index_view(ix, a.ix);
 	a.n_seq = N;
 	a.k_max = k_max;
 	a.cand_t = s->d_cand_t.p;
@@ -428,7 +537,7 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
 {
 	const usb_index *ix = s->ix;
-	const uint32_t N = ix->H.n_seq;
+	const uint32_t N = ix->S.n();
 	int rc;
 	if ((rc = s->d_cand_t.reserve((size_t)n_jobs * k_max)) || (rc = s->d_cand_u.reserve((size_t)n_jobs * k_max)) ||
 	    (rc = s->d_ncand.reserve(n_jobs)) || (rc = s->d_nemit.reserve(n_jobs)))
@@ -437,6 +546,8 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		return rc;
 	if (n_jobs == 0)
 		return 0;
+	if (!s->big && N > s->P.big)
+		s->big = true; // sticky, like UDBUsortedSearcher::SetQueryImpl (udbusortedsearcher.cpp:39-58)
 	if (s->big)
 		return launch_rank_big(s, n_jobs, strands, k_max, want_u);
 	RankArgs a;
@@ -446,9 +557,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	a.q_off = s->d_qoff.p;
 	a.n_jobs = n_jobs;
 	a.strands = strands;
-	a.row_off = ix->d_row_off.p;
-	a.postings = ix->d_postings.p;
-	a.row_size = ix->d_row_size.p;
+	fill_index_view(ix, a.ix);
 	a.n_seq = N;
 	a.k_max = k_max;
 	a.cand_t = s->d_cand_t.p;
@@ -587,7 +696,7 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		return fail(USB_EINVAL, "null searcher");
 	CK(cudaSetDevice(s->ix->device));
 	const usb_index *ix = s->ix;
-	const uint32_t N = ix->H.n_seq;
+	const uint32_t N = ix->S.n();
 	s->strands = s->P.strand_both ? 2 : 1;
 	s->n_jobs = s->n_q * s->strands;
 	uint32_t k_max = N;
@@ -600,9 +709,9 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		  "maxaccepts/maxrejects allow up to %u candidates per query; this build materialises at most %u (set both > 0)",
 		  k_max, RANK_KCAP);
 	s->k_max = k_max;
-	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->H.max_len / 8 + 16);
+	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->S.max_len / 8 + 16);
 	AlignGeom g;
-	int rc = align_geometry(s, s->max_ql, ix->H.max_len, hsp_cap, g);
+	int rc = align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g);
 	if (rc)
 		return rc;
 	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : k_max;
@@ -828,7 +937,7 @@ extern "C" int usb_rank_batch(usb_searcher *s, const uint8_t *qseqs, const uint6
 	if (rc)
 		return rc;
 	const uint32_t strands = s->P.strand_both ? 2 : 1, n_jobs = n_q * strands;
-	const uint32_t N = s->ix->H.n_seq;
+	const uint32_t N = s->ix->S.n();
 	CK(cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream));
 	if ((rc = launch_rank(s, n_jobs, strands, k_max, u_out != nullptr)))
 		return rc;
@@ -857,14 +966,14 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 		return fail(USB_EINVAL, "usb_align_pairs: null argument");
 	const usb_index *ix = s->ix;
 	for (uint32_t i = 0; i < n_pairs; ++i)
-		if (pair_q[i] >= n_q || pair_t[i] >= ix->H.n_seq)
+		if (pair_q[i] >= n_q || pair_t[i] >= ix->S.n())
 			return fail(USB_EINVAL, "pair %u out of range", i);
 	int rc = upload_queries(s, qseqs, q_off, n_q);
 	if (rc)
 		return rc;
-	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->H.max_len / 8 + 16);
+	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->S.max_len / 8 + 16);
 	AlignGeom g;
-	if ((rc = align_geometry(s, s->max_ql, ix->H.max_len, hsp_cap, g)))
+	if ((rc = align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g)))
 		return rc;
 	DevBuf<uint32_t> d_pq, d_pt, d_hsp;
 	DevBuf<uint8_t> d_al;

@@ -51,6 +51,22 @@ struct DevCounters {
 	uint32_t pad;
 };
 
+// The UDB index as the kernels see it: a few CSR segments over consecutive target ranges
+// (usb_hostindex.h).  A word's posting row is the concatenation of its fragments in segment order,
+// which is ascending target order.
+#define USB_MAX_SEG 24
+struct SegDesc {
+	const uint64_t *row_off;   // slots + 1, multiples of 4
+	const uint32_t *row_size;  // slots
+	const uint32_t *postings;  // global target indexes
+	uint32_t base, count;
+};
+struct IndexView {
+	SegDesc seg[USB_MAX_SEG];
+	uint32_t n_seg;
+	uint32_t n_seq;
+};
+
 struct HspRec {
 	uint32_t Loi, Loj, Len;
 	int score2;

@@ -72,6 +72,52 @@ static inline uint32_t udb_word(const uint8_t *s, uint32_t w)
 	return word;
 }
 
+static unsigned pick_threads(int n_threads, uint32_t items)
+{
+	unsigned T = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
+	T = std::min<unsigned>(T, std::max<uint32_t>(1, items / 256));
+	return std::max(1u, std::min(T, 64u));
+}
+
+template <class F> static void run_threads(unsigned T, F fn)
+{
+	std::vector<std::thread> th;
+	for (unsigned k = 1; k < T; ++k)
+		th.emplace_back(fn, k);
+	fn(0u);
+	for (auto &t : th)
+		t.join();
+}
+
+void HostSeqs::append(const uint8_t *s, const uint64_t *off, uint32_t count, int dbmask, int n_threads)
+{
+	const uint32_t n0 = n();
+	uint64_t cur = seq_off.back();
+	seq_off.reserve(seq_off.size() + count);
+	seq_len.reserve(seq_len.size() + count);
+	for (uint32_t i = 0; i < count; ++i) {
+		const uint64_t L = off[i + 1] - off[i];
+		seq_len.push_back((uint32_t)L);
+		max_len = std::max(max_len, (uint32_t)L);
+		cur += (L + 15) & ~(uint64_t)15;
+		seq_off.push_back(cur);
+	}
+	seqs.resize(cur + 16, 0);
+	const unsigned T = pick_threads(n_threads, count);
+	run_threads(T, [&](unsigned k) {
+		const uint32_t a = (uint32_t)((uint64_t)count * k / T), b = (uint32_t)((uint64_t)count * (k + 1) / T);
+		for (uint32_t i = a; i < b; ++i) {
+			const uint8_t *src = s + off[i];
+			uint8_t *dst = seqs.data() + seq_off[n0 + i];
+			const uint32_t L = seq_len[n0 + i];
+			if (dbmask)
+				fastmask_nt(src, L, dst);
+			else if (L)
+				memcpy(dst, src, L);
+		}
+	});
+}
+
 namespace {
 struct Worker {
 	uint32_t t0, t1;
@@ -81,71 +127,40 @@ struct Worker {
 }
 
 template <class F>
-static void for_each_unique_word(const HostIndex &ix, uint32_t t, std::vector<uint32_t> &stamp, F f)
+static void for_each_unique_word(const HostSeqs &S, uint32_t word_length, uint32_t t, uint32_t stamp_id,
+  std::vector<uint32_t> &stamp, F f)
 {
-	const uint8_t *s = ix.seqs.data() + ix.seq_off[t];
-	uint32_t L = ix.seq_len[t], w = ix.word_length;
+	const uint8_t *s = S.seqs.data() + S.seq_off[t];
+	const uint32_t L = S.seq_len[t], w = word_length;
 	if (L < w)
 		return;
 	for (uint32_t p = 0; p + w <= L; ++p) {
-		uint32_t word = udb_word(s + p, w);
-		if (word == UINT32_MAX || stamp[word] == t + 1)
+		const uint32_t word = udb_word(s + p, w);
+		if (word == UINT32_MAX || stamp[word] == stamp_id)
 			continue;
-		stamp[word] = t + 1;
+		stamp[word] = stamp_id;
 		f(word);
 	}
 }
 
-void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_seq, uint32_t word_length,
-  int dbmask, int n_threads, HostIndex &ix)
+void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, int n_threads, HostCSR &ix)
 {
-	ix.n_seq = n_seq;
-	ix.word_length = word_length;
+	ix.base = first;
+	ix.count = count;
 	ix.slots = 1u << (2 * word_length);
-	ix.seq_off.assign((size_t)n_seq + 1, 0);
-	ix.seq_len.assign(n_seq, 0);
-	ix.max_len = 0;
-	uint64_t off = 0;
-	for (uint32_t t = 0; t < n_seq; ++t) {
-		uint64_t L = seq_off[t + 1] - seq_off[t];
-		ix.seq_off[t] = off;
-		ix.seq_len[t] = (uint32_t)L;
-		ix.max_len = std::max(ix.max_len, (uint32_t)L);
-		off += (L + 15) & ~(uint64_t)15;
-	}
-	ix.seq_off[n_seq] = off;
-	ix.seqs.assign(off + 16, 0);
-
-	unsigned T = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
-	T = std::min<unsigned>(T, std::max<uint32_t>(1, n_seq / 64));
-	T = std::max(1u, std::min(T, 64u));
+	const unsigned T = pick_threads(n_threads, count);
 	std::vector<Worker> W(T);
 	for (unsigned k = 0; k < T; ++k) {
-		W[k].t0 = (uint32_t)((uint64_t)n_seq * k / T);
-		W[k].t1 = (uint32_t)((uint64_t)n_seq * (k + 1) / T);
+		W[k].t0 = first + (uint32_t)((uint64_t)count * k / T);
+		W[k].t1 = first + (uint32_t)((uint64_t)count * (k + 1) / T);
 	}
-	auto run = [&](auto fn) {
-		std::vector<std::thread> th;
-		for (unsigned k = 1; k < T; ++k)
-			th.emplace_back(fn, k);
-		fn(0u);
-		for (auto &t : th)
-			t.join();
-	};
-	// pass 1: copy + mask, count unique words per worker
-	run([&](unsigned k) {
+	// pass 1: count unique words per worker
+	run_threads(T, [&](unsigned k) {
 		Worker &w = W[k];
 		w.counts.assign(ix.slots, 0);
 		w.stamp.assign(ix.slots, 0);
-		for (uint32_t t = w.t0; t < w.t1; ++t) {
-			const uint8_t *src = seqs + seq_off[t];
-			uint8_t *dst = ix.seqs.data() + ix.seq_off[t];
-			if (dbmask)
-				fastmask_nt(src, ix.seq_len[t], dst);
-			else if (ix.seq_len[t])
-				memcpy(dst, src, ix.seq_len[t]);
-			for_each_unique_word(ix, t, w.stamp, [&](uint32_t word) { ++w.counts[word]; });
-		}
+		for (uint32_t t = w.t0; t < w.t1; ++t)
+			for_each_unique_word(S, word_length, t, t - first + 1, w.stamp, [&](uint32_t word) { ++w.counts[word]; });
 	});
 	// row offsets; each worker's counts become its write cursor inside the row
 	ix.row_off.assign((size_t)ix.slots + 1, 0);
@@ -155,7 +170,7 @@ void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_s
 	for (uint32_t word = 0; word < ix.slots; ++word) {
 		ix.row_off[word] = total;
 		for (unsigned k = 0; k < T; ++k) {
-			uint32_t c = W[k].counts[word];
+			const uint32_t c = W[k].counts[word];
 			W[k].counts[word] = (uint32_t)(total - ix.row_off[word]);
 			total += c;
 		}
@@ -166,14 +181,38 @@ void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_s
 	ix.row_off[ix.slots] = total;
 	ix.postings.assign(total + 4, 0xffffffffu);
 	// pass 2: fill (targets ascending within each row because workers own ascending ranges)
-	run([&](unsigned k) {
+	run_threads(T, [&](unsigned k) {
 		Worker &w = W[k];
 		std::fill(w.stamp.begin(), w.stamp.end(), 0u);
 		for (uint32_t t = w.t0; t < w.t1; ++t)
-			for_each_unique_word(ix, t, w.stamp, [&](uint32_t word) {
-				ix.postings[ix.row_off[word] + w.counts[word]++] = t;
-			});
+			for_each_unique_word(S, word_length, t, t - first + 1, w.stamp,
+			  [&](uint32_t word) { ix.postings[ix.row_off[word] + w.counts[word]++] = t; });
 	});
+}
+
+void merge_csr(const HostCSR &a, const HostCSR &b, HostCSR &out)
+{
+	out.base = a.base;
+	out.count = a.count + b.count;
+	out.slots = a.slots;
+	out.row_off.assign((size_t)a.slots + 1, 0);
+	out.row_size.assign(a.slots, 0);
+	uint64_t total = 0;
+	for (uint32_t w = 0; w < a.slots; ++w) {
+		out.row_off[w] = total;
+		out.row_size[w] = a.row_size[w] + b.row_size[w];
+		total = (total + out.row_size[w] + 3) & ~(uint64_t)3;
+	}
+	out.row_off[a.slots] = total;
+	out.n_postings = a.n_postings + b.n_postings;
+	out.postings.assign(total + 4, 0xffffffffu);
+	for (uint32_t w = 0; w < a.slots; ++w) {
+		uint32_t *dst = out.postings.data() + out.row_off[w];
+		if (a.row_size[w])
+			memcpy(dst, a.postings.data() + a.row_off[w], (size_t)a.row_size[w] * 4);
+		if (b.row_size[w])
+			memcpy(dst + a.row_size[w], b.postings.data() + b.row_off[w], (size_t)b.row_size[w] * 4);
+	}
 }
 
 } // namespace usb

@@ -1,10 +1,14 @@
 // usb_hostindex.h -- host-side construction of the UDB index (CSR postings) and masked SeqDB.
 //
 // Replaces, for the in-memory layout: MaskDB (makeudb.cpp:11-25) -> FastMaskSeq
-// (fastmask.cpp:88-158), UDBParams::SetTargetWords/SetTargetUniqueWords (udbparams.cpp:644-711)
-// and UDBData::FromSeqDB (udbbuild.cpp:303-398).  The reference keeps one heap row per word
-// (m_UDBRows[word], m_Sizes[word]); here the rows are one CSR array so that a posting row is a
-// contiguous, coalesced HBM range.
+// (fastmask.cpp:88-158), UDBParams::SetTargetWords/SetTargetUniqueWords (udbparams.cpp:644-711),
+// UDBData::FromSeqDB (udbbuild.cpp:303-398) and, for the growing cluster_fast database,
+// UDBData::AddSIToDB_CopyData / AddWord / GrowRow (udbbuild.cpp:74-130,286).
+// The reference keeps one heap row per word (m_UDBRows[word], m_Sizes[word]) and grows rows in
+// place; here the index is a short list of immutable CSR segments over consecutive target ranges
+// (a log-structured merge: appended targets form a new small segment, neighbouring segments of
+// similar size are concatenated), so that every posting row fragment stays a contiguous, 16-byte
+// aligned HBM range and an append never rewrites more than an amortised O(log N) share.
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -12,26 +16,34 @@
 
 namespace usb {
 
-struct HostIndex {
-	uint32_t n_seq = 0;
-	uint32_t word_length = 8;
-	uint32_t slots = 0;                 // 4^word_length
-	std::vector<uint8_t> seqs;          // masked letters, each target padded to a 16-byte boundary
-	std::vector<uint64_t> seq_off;      // n_seq+1 padded offsets (multiples of 16)
-	std::vector<uint32_t> seq_len;      // n_seq true lengths
-	std::vector<uint64_t> row_off;      // slots+1; every row starts on a 16-byte boundary (multiple of 4 entries)
-	std::vector<uint32_t> row_size;     // slots; true row lengths (m_Sizes[word])
-	std::vector<uint32_t> postings;     // target indexes, ascending per row, each target once per row
-	uint64_t n_postings = 0;            // sum of row_size
+// Masked target letters; each target padded to a 16-byte boundary.
+struct HostSeqs {
+	std::vector<uint8_t> seqs;
+	std::vector<uint64_t> seq_off{0};   // n+1 padded offsets (multiples of 16)
+	std::vector<uint32_t> seq_len;      // true lengths
 	uint32_t max_len = 0;
+	uint32_t n() const { return (uint32_t)seq_len.size(); }
+	// dbmask: 1 = fastnucleo soft-masking, 0 = letters taken verbatim (cluster_fast)
+	void append(const uint8_t *s, const uint64_t *off, uint32_t count, int dbmask, int n_threads);
+};
+
+// Postings of the targets [base, base+count): row_off[slots+1] (multiples of 4 entries),
+// row_size[slots] true lengths, postings = global target indexes ascending per row, every target
+// at most once per row; padding entries are 0xffffffff.
+struct HostCSR {
+	uint32_t base = 0, count = 0, slots = 0;
+	std::vector<uint64_t> row_off;
+	std::vector<uint32_t> row_size;
+	std::vector<uint32_t> postings;
+	uint64_t n_postings = 0;
 };
 
 // FastMaskSeq soft-masking (fastmask.cpp:88-158); in == out allowed.
 void fastmask_nt(const uint8_t *in, uint32_t L, uint8_t *out);
 
-// Builds the masked SeqDB + CSR index.  dbmask: 1 = fastnucleo, 0 = sequences taken verbatim
-// (cluster_fast indexes raw reads, clusterfast.cpp:88-103).  n_threads <= 0: hardware concurrency.
-void build_host_index(const uint8_t *seqs, const uint64_t *seq_off, uint32_t n_seq, uint32_t word_length,
-  int dbmask, int n_threads, HostIndex &out);
+// n_threads <= 0: hardware concurrency.
+void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, int n_threads, HostCSR &out);
+// a covers [x, y), b covers [y, z): out covers [x, z) with rows = a's row followed by b's row.
+void merge_csr(const HostCSR &a, const HostCSR &b, HostCSR &out);
 
 } // namespace usb

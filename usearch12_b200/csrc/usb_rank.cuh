@@ -37,11 +37,10 @@ struct RankArgs {
 	const uint64_t *q_off;     // n_q + 1
 	uint32_t n_jobs;           // n_q * strands
 	uint32_t strands;          // 1 or 2
-	const uint64_t *row_off;   // slots + 1, multiples of 4
-	const uint32_t *row_size;  // slots
-	const uint32_t *postings;
+	IndexView ix;              // CSR segments of the UDB index
 	uint32_t n_seq;
 	uint32_t k_max;            // <= RANK_KCAP
+	uint32_t *aux;             // optional, 4 per job: final SetTopBump MinU, NextValue/2, max U, 0
 	uint32_t *cand_t;          // n_jobs * k_max
 	uint32_t *cand_u;          // n_jobs * k_max (may be null)
 	uint32_t *n_cand;          // TopOrder.Size per job
@@ -331,25 +330,30 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 			if (r >= n_rows)
 				break;
 			const uint32_t word = S.rows[r];
-			const uint32_t size = a.row_size[word];
-			const uint32_t *row = a.postings + a.row_off[word];
-			const uint4 *v4 = (const uint4 *)row;
-			const uint32_t nvec = size >> 2;
-			my_post += size;
-			uint32_t i = lane;
-			for (; i + 96 < nvec; i += 128) {
-				const uint4 x0 = __ldg(v4 + i), x1 = __ldg(v4 + i + 32), x2 = __ldg(v4 + i + 64), x3 = __ldg(v4 + i + 96);
-				u_inc<WIDE>(U32, x0.x); u_inc<WIDE>(U32, x0.y); u_inc<WIDE>(U32, x0.z); u_inc<WIDE>(U32, x0.w);
-				u_inc<WIDE>(U32, x1.x); u_inc<WIDE>(U32, x1.y); u_inc<WIDE>(U32, x1.z); u_inc<WIDE>(U32, x1.w);
-				u_inc<WIDE>(U32, x2.x); u_inc<WIDE>(U32, x2.y); u_inc<WIDE>(U32, x2.z); u_inc<WIDE>(U32, x2.w);
-				u_inc<WIDE>(U32, x3.x); u_inc<WIDE>(U32, x3.y); u_inc<WIDE>(U32, x3.z); u_inc<WIDE>(U32, x3.w);
+			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+				const SegDesc &seg = a.ix.seg[sg];
+				const uint32_t size = seg.row_size[word];
+				if (size == 0)
+					continue;
+				const uint32_t *row = seg.postings + seg.row_off[word];
+				const uint4 *v4 = (const uint4 *)row;
+				const uint32_t nvec = size >> 2;
+				my_post += size;
+				uint32_t i = lane;
+				for (; i + 96 < nvec; i += 128) {
+					const uint4 x0 = __ldg(v4 + i), x1 = __ldg(v4 + i + 32), x2 = __ldg(v4 + i + 64), x3 = __ldg(v4 + i + 96);
+					u_inc<WIDE>(U32, x0.x); u_inc<WIDE>(U32, x0.y); u_inc<WIDE>(U32, x0.z); u_inc<WIDE>(U32, x0.w);
+					u_inc<WIDE>(U32, x1.x); u_inc<WIDE>(U32, x1.y); u_inc<WIDE>(U32, x1.z); u_inc<WIDE>(U32, x1.w);
+					u_inc<WIDE>(U32, x2.x); u_inc<WIDE>(U32, x2.y); u_inc<WIDE>(U32, x2.z); u_inc<WIDE>(U32, x2.w);
+					u_inc<WIDE>(U32, x3.x); u_inc<WIDE>(U32, x3.y); u_inc<WIDE>(U32, x3.z); u_inc<WIDE>(U32, x3.w);
+				}
+				for (; i < nvec; i += 32) {
+					const uint4 x = __ldg(v4 + i);
+					u_inc<WIDE>(U32, x.x); u_inc<WIDE>(U32, x.y); u_inc<WIDE>(U32, x.z); u_inc<WIDE>(U32, x.w);
+				}
+				if (lane < (size & 3))
+					u_inc<WIDE>(U32, __ldg(row + 4 * nvec + lane));
 			}
-			for (; i < nvec; i += 32) {
-				const uint4 x = __ldg(v4 + i);
-				u_inc<WIDE>(U32, x.x); u_inc<WIDE>(U32, x.y); u_inc<WIDE>(U32, x.z); u_inc<WIDE>(U32, x.w);
-			}
-			if (lane < (size & 3))
-				u_inc<WIDE>(U32, __ldg(row + 4 * nvec + lane));
 		}
 		if (lane == 0 && my_post)
 			atomicAdd(&S.n_post, my_post);
@@ -428,6 +432,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 			MaxCount = v;
 		}
 		S.n_chg = nchg;
+		S.pad2 = MinU; // SetTopBump threshold in force after the last target
 		S.maxv = n ? rec_val[n - 1] : 0;
 		// countsort.cpp:12-24: NextValue = running max before its last increase
 		S.minv = (n >= 2 ? rec_val[n - 2] : 0) / 2;
@@ -491,6 +496,12 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	if (tid == 0) {
 		a.n_cand[job] = total;
 		a.n_emit[job] = nsel;
+		if (a.aux) {
+			a.aux[4 * job] = S.pad2;
+			a.aux[4 * job + 1] = S.minv;
+			a.aux[4 * job + 2] = S.maxv;
+			a.aux[4 * job + 3] = 0;
+		}
 		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
 	}
 }

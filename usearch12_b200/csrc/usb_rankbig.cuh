@@ -34,11 +34,10 @@ struct RankBigArgs {
 	const uint8_t *q;
 	const uint64_t *q_off;
 	uint32_t n_jobs, strands;
-	const uint64_t *row_off;
-	const uint32_t *row_size;
-	const uint32_t *postings;
+	IndexView ix;              // CSR segments; a row = its fragments in segment order
 	uint32_t n_seq;
 	uint32_t k_max;
+	uint32_t *aux;             // optional, 4 per job: 0, NextValue/2, max U, QueryStep
 	uint32_t *cand_t, *cand_u, *n_cand, *n_emit;
 	uint32_t *u_out;           // optional: n_jobs * n_seq
 	uint8_t *u_arena;          // gridDim.x counter arrays of u_stride bytes
@@ -94,10 +93,16 @@ __device__ __forceinline__ uint32_t ug_get(const uint8_t *U, uint32_t t)
 __device__ __forceinline__ uint32_t first_row_of(const RankBigArgs &a, const RankBigShared &S, uint32_t t,
   uint32_t row_limit)
 {
+	// only the segment whose target range holds t can contain it
+	uint32_t sg = 0;
+	while (sg + 1 < a.ix.n_seg && t >= a.ix.seg[sg].base + a.ix.seg[sg].count)
+		++sg;
+	const SegDesc &seg = a.ix.seg[sg];
 	for (uint32_t k = 0; k < row_limit; ++k) {
 		const uint32_t word = S.rows[k];
-		const uint32_t *row = a.postings + a.row_off[word];
-		uint32_t lo = 0, hi = a.row_size[word];
+		const uint32_t *row = seg.postings + seg.row_off[word];
+		const uint32_t size = seg.row_size[word];
+		uint32_t lo = 0, hi = size;
 		while (lo < hi) {
 			const uint32_t mid = (lo + hi) >> 1;
 			if (__ldg(row + mid) < t)
@@ -105,7 +110,7 @@ __device__ __forceinline__ uint32_t first_row_of(const RankBigArgs &a, const Ran
 			else
 				hi = mid;
 		}
-		if (lo < a.row_size[word] && __ldg(row + lo) == t)
+		if (lo < size && __ldg(row + lo) == t)
 			return k;
 	}
 	return row_limit;
@@ -117,8 +122,10 @@ __device__ __forceinline__ unsigned long long big_key(uint32_t u, uint32_t k, ui
 }
 
 template <bool WIDE>
-__device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &S, uint8_t *U, uint32_t n_rows)
+__device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &S, uint8_t *U, uint32_t n_rows,
+  uint32_t step)
 {
+	uint32_t minv_out = 1;
 	const uint32_t tid = threadIdx.x, lane = tid & 31;
 	const uint32_t N = a.n_seq;
 	uint32_t *U32 = (uint32_t *)U;
@@ -145,15 +152,18 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 			if (r >= n_rows)
 				break;
 			const uint32_t word = S.rows[r];
-			const uint32_t size = a.row_size[word];
-			const uint32_t *row = a.postings + a.row_off[word];
-			my_post += size;
-			for (uint32_t i = lane; i < size; i += 32) {
-				const uint32_t t = __ldg(row + i);
-				if (WIDE)
-					atomicAdd(&U32[t >> 1], 1u << ((t & 1) * 16));
-				else
-					atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
+			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+				const SegDesc &seg = a.ix.seg[sg];
+				const uint32_t size = seg.row_size[word];
+				const uint32_t *row = seg.postings + seg.row_off[word];
+				my_post += size;
+				for (uint32_t i = lane; i < size; i += 32) {
+					const uint32_t t = __ldg(row + i);
+					if (WIDE)
+						atomicAdd(&U32[t >> 1], 1u << ((t & 1) * 16));
+					else
+						atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
+				}
 			}
 		}
 		if (lane == 0 && my_post)
@@ -182,13 +192,16 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 		uint32_t kstar = 0, tstar = 0xffffffffu;
 		for (uint32_t k = 0; k < n_rows; ++k) {
 			const uint32_t word = S.rows[k];
-			const uint32_t size = a.row_size[word];
-			const uint32_t *row = a.postings + a.row_off[word];
 			uint32_t best = 0xffffffffu;
-			for (uint32_t i = tid; i < size; i += RANK_THREADS) {
-				const uint32_t t = __ldg(row + i);
-				if (ug_get<WIDE>(U, t) == gmax)
-					best = min(best, t);
+			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+				const SegDesc &seg = a.ix.seg[sg];
+				const uint32_t size = seg.row_size[word];
+				const uint32_t *row = seg.postings + seg.row_off[word];
+				for (uint32_t i = tid; i < size; i += RANK_THREADS) {
+					const uint32_t t = __ldg(row + i);
+					if (ug_get<WIDE>(U, t) == gmax)
+						best = min(best, t);
+				}
 			}
 			best = block_reduce_min(best, S.warp_tmp);
 			if (best != 0xffffffffu) {
@@ -201,19 +214,21 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 		uint32_t nv = 0;
 		for (uint32_t k = 0; k <= kstar; ++k) {
 			const uint32_t word = S.rows[k];
-			const uint32_t size = a.row_size[word];
-			const uint32_t *row = a.postings + a.row_off[word];
-			for (uint32_t i = tid; i < size; i += RANK_THREADS) {
-				const uint32_t t = __ldg(row + i);
-				if (k == kstar && t >= tstar)
-					break; // ascending row: the rest of this thread's stride is beyond p* too
-				const uint32_t u = ug_get<WIDE>(U, t);
-				if (u != gmax || k < kstar) // (targets with U == gmax before p* cannot exist)
-					nv = max(nv, u);
+			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+				const SegDesc &seg = a.ix.seg[sg];
+				const uint32_t size = seg.row_size[word];
+				const uint32_t *row = seg.postings + seg.row_off[word];
+				for (uint32_t i = tid; i < size; i += RANK_THREADS) {
+					const uint32_t t = __ldg(row + i);
+					if (k == kstar && t >= tstar)
+						break; // ascending row: the rest of this thread's stride is beyond p* too
+					nv = max(nv, ug_get<WIDE>(U, t)); // (no target before p* holds gmax)
+				}
 			}
 		}
 		const uint32_t nextv = block_reduce_max(nv, S.warp_tmp);
 		const uint32_t minv = max(nextv / 2, 1u);
+		minv_out = minv;
 
 		// ---- survivors
 		{
@@ -324,8 +339,10 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 			// ties at the cut: row by row in first-touch order until m_eq are taken
 			for (uint32_t k = 0; k < n_rows && S.taken < m_eq; ++k) {
 				const uint32_t word = S.rows[k];
-				const uint32_t size = a.row_size[word];
-				const uint32_t *row = a.postings + a.row_off[word];
+				for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+				const SegDesc &seg = a.ix.seg[sg];
+				const uint32_t size = seg.row_size[word];
+				const uint32_t *row = seg.postings + seg.row_off[word];
 				for (uint32_t base = 0; base < size && S.taken < m_eq; base += RANK_THREADS) {
 					const uint32_t i = base + tid;
 					uint32_t t = 0;
@@ -345,6 +362,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					}
 					__syncthreads();
 				}
+				}
 			}
 			__syncthreads();
 			nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
@@ -360,6 +378,12 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 	if (tid == 0) {
 		a.n_cand[job] = total;
 		a.n_emit[job] = nsel;
+		if (a.aux) {
+			a.aux[4 * job] = 0;
+			a.aux[4 * job + 1] = minv_out;
+			a.aux[4 * job + 2] = gmax;
+			a.aux[4 * job + 3] = step;
+		}
 		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
 	}
 	__syncthreads();
@@ -442,9 +466,9 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank_big(const RankBigArgs 
 			S.rows[r] = S.uniq[r * Step];
 		__syncthreads();
 		if (n_rows > 255)
-			rank_big_job<true>(a, job, S, U, n_rows);
+			rank_big_job<true>(a, job, S, U, n_rows, Step);
 		else
-			rank_big_job<false>(a, job, S, U, n_rows);
+			rank_big_job<false>(a, job, S, U, n_rows, Step);
 	}
 }
 
