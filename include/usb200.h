@@ -133,6 +133,18 @@ uint64_t usb_searcher_launch_count(const usb_searcher *s);
  * section 8e): copies min(n_hits, cap_hits) usb_hit records into a caller-owned DEVICE buffer. */
 int usb_batch_export_hits_device(usb_searcher *s, void *dev_dst, uint64_t cap_hits, uint64_t *n_hits);
 
+/* ---- cluster_fast: one round of the greedy centroid loop.  Replaces, for a block of queries
+ * in cluster order, the body of ClusterFast()'s loop (clusterfast.cpp:120-129): Searcher::Search
+ * against the centroids so far, then ClusterSink::OnQueryDone (clustersink.cpp:306-330), which
+ * appends a query without a hit to the database as a new centroid.  All n_q queries are searched
+ * against the database as it is on entry; the longest prefix whose results provably equal the
+ * sequential ones is committed (*n_committed >= 1 when n_q >= 1), its no-hit queries are appended
+ * to the index in order, and cluster_idx[q] (q < *n_committed) receives the centroid index the
+ * query belongs to (== its own new index when it became a centroid).  *out holds the hits of the
+ * committed queries.  Call again with the remaining queries.  Needs -maxaccepts 1, -strand plus. */
+int usb_cluster_round(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  uint32_t *n_committed, uint32_t *cluster_idx, usb_result **out);
+
 /* Result accessors.  Hits are grouped by query (ascending) and, within a query, in the
  * reference's output order (HitMgr::Sort, hitmgr.cpp:477; sort.h:63-102). */
 uint64_t usb_result_hit_count(const usb_result *r);

@@ -1,0 +1,97 @@
+"""GPU parity of the cluster_fast greedy centroid loop (usb_cluster_round) against the oracle's
+sequential loop (oracle/uso.c, pinned against the reference binary's -cluster_fast output by
+tools/pin_oracle.sh-style runs: byte-identical .uc and centroids on 25 715 reads, three -sort modes)."""
+import random
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def make_reads(seed, n_random, n_amp, n_db=300, n_amp_db=40):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    from gen_synth import generate
+    rng = random.Random(seed)
+    db, reads = generate(ndb=n_db, dblen=1000, nq=n_random, qlen=250, seed=seed, nroot=6)
+    out = [r[1] for r in reads]
+    for k in range(n_amp):
+        t = rng.randrange(n_amp_db)
+        L = rng.choice([250, 250, 240, 200, 251])
+        out.append(util.mutate(db[t][300:300 + L], rng.uniform(0, 0.03), rng))
+    out += ["ACGT", "N" * 60, out[3].lower(), "A" * 250]
+    rng.shuffle(out)
+    return out
+
+
+def oracle_cluster(reads, **kw):
+    from oracle import uso_py as O
+    p = O.default_params(cluster_fast=True, **kw)
+    db = O.DB([], p)
+    s = O.Searcher(db, p)
+    assign, paths = [], []
+    import ctypes as C
+    for i, r in enumerate(reads):
+        hits = s.search(r, i)
+        if hits:
+            assign.append(hits[0]["target"])
+            paths.append((hits[0]["ids"], hits[0]["alnlen"], hits[0]["path"]))
+        else:
+            b = r.encode()
+            assign.append(O.lib().uso_db_add(db.h, b, len(b), b""))
+            db.n += 1
+            paths.append(None)
+    return assign, paths
+
+
+def gpu_cluster(reads, block, **kw):
+    from usearch12_b200 import capi
+    p = capi.default_params(cluster_fast=True, **kw)
+    ix = capi.Index([], p)
+    s = capi.Searcher(ix, p)
+    data, off = capi.pack_seqs(reads)
+    assign, paths, rounds = [], [], 0
+    pos = 0
+    while pos < len(reads):
+        n = min(block, len(reads) - pos)
+        sub_off = off[pos:pos + n + 1]
+        ncom, cidx, res = s.cluster_round(data, sub_off)
+        assert ncom >= 1
+        for q in range(ncom):
+            assign.append(int(cidx[q]))
+            b, e = int(res.qoff[q]), int(res.qoff[q + 1])
+            if e > b:
+                h = res.hits[b]
+                paths.append((int(h["ids"]), int(h["alnlen"]), res.path(h)))
+            else:
+                paths.append(None)
+        pos += ncom
+        rounds += 1
+    return assign, paths, rounds
+
+
+@pytest.mark.parametrize("block", [1, 64, 4096])
+def test_cluster_rounds_equal_sequential_loop(block):
+    reads = make_reads(7, 500, 700)
+    want_a, want_p = oracle_cluster(reads)
+    got_a, got_p, rounds = gpu_cluster(reads, block)
+    assert got_a == want_a
+    assert got_p == want_p
+    assert len(set(want_a)) > 50
+    if block > 1:
+        assert rounds < len(reads)
+
+
+def test_cluster_crosses_big_threshold():
+    """-big 150: the database switches to the UDBSearchBig path in mid-run, like a 1M-read
+    cluster_fast crossing 100 000 centroids."""
+    reads = make_reads(11, 600, 300)
+    want_a, want_p = oracle_cluster(reads, big=150)
+    got_a, got_p, _ = gpu_cluster(reads, 512, big=150)
+    assert got_a == want_a
+    assert got_p == want_p
+    assert len(set(want_a)) > 200

@@ -23,7 +23,7 @@ def _newest_source_mtime():
     m = 0.0
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for fn in os.listdir(root):
-            if fn.endswith((".cu", ".cuh", ".cpp", ".h")):
+            if fn.endswith((".cu", ".cuh", ".cpp", ".h", ".inc")):
                 m = max(m, os.path.getmtime(os.path.join(root, fn)))
     return m
 

@@ -47,7 +47,7 @@ SYMBOLS = [
     "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
     "usb_index_seq_count", "usb_index_posting_count", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
-    "usb_batch_download", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
+    "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
     "usb_viterbi_batch",
@@ -85,6 +85,7 @@ def lib():
     L.usb_batch_run.argtypes = [vp, C.POINTER(C.c_float)]
     L.usb_batch_download.argtypes = [vp, C.POINTER(vp)]
     L.usb_batch_counters.argtypes = [vp, u64p]
+    L.usb_cluster_round.argtypes = [vp, vp, vp, C.c_uint32, u32p, vp, C.POINTER(vp)]
     L.usb_searcher_launch_count.argtypes = [vp]
     L.usb_searcher_launch_count.restype = C.c_uint64
     L.usb_batch_export_hits_device.argtypes = [vp, vp, C.c_uint64, u64p]
@@ -254,6 +255,16 @@ class Searcher:
         n = C.c_uint64()
         check(lib().usb_batch_export_hits_device(self.handle, C.c_void_p(dev_ptr), cap_hits, C.byref(n)))
         return n.value
+
+    def cluster_round(self, data, off):
+        """One round of the cluster_fast loop on packed queries -> (n_committed, cluster_idx, Result)."""
+        n = len(off) - 1
+        ncom = C.c_uint32()
+        cidx = np.zeros(max(n, 1), np.uint32)
+        h = C.c_void_p()
+        check(lib().usb_cluster_round(self.handle, _ptr(data), _ptr(off), n, C.byref(ncom), _ptr(cidx), C.byref(h)))
+        self.index.n_seq = lib().usb_index_seq_count(self.index.handle)
+        return ncom.value, cidx[:ncom.value], Result(h, ncom.value, ncom.value)
 
     def counters(self):
         out = (C.c_uint64 * 4)()

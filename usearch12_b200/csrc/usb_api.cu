@@ -200,7 +200,7 @@ struct usb_searcher {
 	uint64_t last_postings = 0;
 	DevBuf<uint8_t> d_q;
 	DevBuf<uint64_t> d_qoff;
-	DevBuf<uint32_t> d_cand_t, d_cand_u, d_ncand, d_nemit, d_runs, d_uout;
+	DevBuf<uint32_t> d_cand_t, d_cand_u, d_ncand, d_nemit, d_runs, d_uout, d_aux;
 	DevBuf<usb_hit> d_hits;
 	DevBuf<usb_qstat> d_qstat;
 	DevBuf<DevCounters> d_ctr;
@@ -432,7 +432,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 	if (s->stream)
 		cudaStreamSynchronize(s->stream);
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
-	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release();
+	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
 	for (auto &e : s->ev)
 		if (e)
@@ -515,6 +515,7 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 	a.n_cand = s->d_ncand.p;
 	a.n_emit = s->d_nemit.p;
 	a.u_out = want_u ? s->d_uout.p : nullptr;
+	a.aux = s->d_aux.p;
 	a.stepwords = s->P.stepwords;
 	a.ctr = s->d_ctr.p;
 	a.u_stride = (((uint64_t)N * 2 + 64) + 255) & ~(uint64_t)255;
@@ -540,7 +541,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	const uint32_t N = ix->S.n();
 	int rc;
 	if ((rc = s->d_cand_t.reserve((size_t)n_jobs * k_max)) || (rc = s->d_cand_u.reserve((size_t)n_jobs * k_max)) ||
-	    (rc = s->d_ncand.reserve(n_jobs)) || (rc = s->d_nemit.reserve(n_jobs)))
+	    (rc = s->d_ncand.reserve(n_jobs)) || (rc = s->d_nemit.reserve(n_jobs)) || (rc = s->d_aux.reserve((size_t)n_jobs * 4 + 4)))
 		return rc;
 	if (want_u && (rc = s->d_uout.reserve((size_t)n_jobs * N)))
 		return rc;
@@ -565,6 +566,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	a.n_cand = s->d_ncand.p;
 	a.n_emit = s->d_nemit.p;
 	a.u_out = want_u ? s->d_uout.p : nullptr;
+	a.aux = s->d_aux.p;
 	const bool wide = s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > 255;
 	a.seg_narrow = rank_segment(N, false);
 	a.seg_wide = rank_segment(N, true);
@@ -1110,3 +1112,5 @@ extern "C" int usb_viterbi_batch(usb_searcher *s, const uint8_t *a_seq, const ui
 		return fail(USB_ELIMIT, "%s", err_text(c.err));
 	return 0;
 }
+
+#include "usb_cluster.inc"
