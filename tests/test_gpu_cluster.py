@@ -95,3 +95,28 @@ def test_cluster_crosses_big_threshold():
     assert got_a == want_a
     assert got_p == want_p
     assert len(set(want_a)) > 200
+
+
+@pytest.mark.parametrize("sort", ["none", "length", "size"])
+def test_cluster_fast_cli_byte_identical_to_reference(sort, tmp_path):
+    """C++ driver (-cluster_fast): .uc and centroids FASTA byte-identical to the reference binary's
+    (tests/golden/cluster_*.gz, made with oracle/_ref/usearch12 -cluster_fast -id 0.97 -threads 1)."""
+    import gzip
+    import os
+    import subprocess
+    from usearch12_b200 import build
+    cli = build.build_cli()
+    reads = os.path.join(str(tmp_path), "g.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "cluster_reads.fa.gz"), "rb") as fi, open(reads, "wb") as fo:
+        fo.write(fi.read())
+    uc, cen = os.path.join(str(tmp_path), "o.uc"), os.path.join(str(tmp_path), "o.fa")
+    cmd = [cli, "-cluster_fast", reads, "-id", "0.97", "-uc", uc, "-centroids", cen, "-quiet"]
+    if sort != "none":
+        cmd += ["-sort", sort]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for got, name in ((uc, "cluster_%s.uc.gz" % sort), (cen, "cluster_%s.centroids.fa.gz" % sort)):
+        with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+            want = f.read().splitlines()
+        d = util.first_diff(open(got).read().splitlines(), want)
+        assert d is None, "%s\n%s" % (name, d)

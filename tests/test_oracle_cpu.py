@@ -68,3 +68,21 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, fn), errors="ignore").read()
                 assert "uso_" not in txt and "liboracle" not in txt, fn
+
+
+def test_oracle_cluster_fast_matches_reference_golden(tmp_path):
+    """oracle/uso_cli cluster_fast vs the reference binary's .uc / centroids (tests/golden/cluster_*)."""
+    import gzip
+    import os
+    import subprocess
+    O.lib()
+    cli = os.path.join(util.ROOT, "oracle", "_build", "uso_cli")
+    reads = os.path.join(str(tmp_path), "g.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "cluster_reads.fa.gz"), "rb") as fi, open(reads, "wb") as fo:
+        fo.write(fi.read())
+    for sort in ("none", "size"):
+        uc, cen = os.path.join(str(tmp_path), "o.uc"), os.path.join(str(tmp_path), "o.fa")
+        subprocess.run([cli, "cluster_fast", reads, "0.97", uc, cen, sort], check=True)
+        for got, name in ((uc, "cluster_%s.uc.gz" % sort), (cen, "cluster_%s.centroids.fa.gz" % sort)):
+            with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+                assert util.first_diff(open(got).read().splitlines(), f.read().splitlines()) is None, name

@@ -52,7 +52,7 @@ CLI = os.path.join(HERE, "usearch12_b200_cli")
 def build_cli(force=False):
     """Host C++ driver (usearch12_b200/csrc/host) linked against libusb200.so."""
     host = os.path.join(CSRC, "host")
-    srcs = [os.path.join(host, f) for f in ("usb_host.cpp", "usb_main.cpp")]
+    srcs = [os.path.join(host, f) for f in ("usb_host.cpp", "usb_cluster_host.cpp", "usb_main.cpp")]
     newest = max(os.path.getmtime(x) for x in srcs + [os.path.join(host, "usb_host.h")])
     if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= newest:
         return CLI

@@ -1,0 +1,276 @@
+// usb_cluster_host.cpp -- host driver of -cluster_fast over usb_cluster_round.
+//
+// Mirrors ClusterFast() (clusterfast.cpp:81-133) with -threads 1 semantics: dereplication
+// (derepfull.cpp:130-212; equality is case-insensitive, uniques in first-occurrence order),
+// optional -sort length|size (clusterfast.cpp:38-79, the reference's own quicksort sort.h:63-102),
+// the greedy centroid loop (batched: see usb_cluster.inc), ClusterSink bookkeeping
+// (clustersink.cpp:306-359), .uc S/H/C records including the dereplicated members
+// (outputuc.cpp:9-92, clustersink.cpp:477-492) and the centroids FASTA in decreasing cluster
+// size order, 80 letters per line (clustersink.cpp:246-272).
+#include <algorithm>
+#include <cctype>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "usb_host.h"
+
+namespace usbhost {
+
+static void CheckUsb2(int rc, const char *what)
+{
+	if (rc != 0)
+		Die("%s: %s (usb200 error %d)", what, usb_last_error(), rc);
+}
+
+// sort.h:63-102,132 QuickSortOrderDesc<unsigned>: middle pivot, Hoare partition, not stable
+static void QuickSortOrderDescRecurse(const unsigned *Values, int left, int right, unsigned *Order)
+{
+	int i = left, j = right;
+	const unsigned pivot = Values[Order[(left + right) / 2]];
+	while (i <= j) {
+		while (Values[Order[i]] > pivot)
+			++i;
+		while (Values[Order[j]] < pivot)
+			--j;
+		if (i <= j) {
+			std::swap(Order[i], Order[j]);
+			++i;
+			--j;
+		}
+	}
+	if (left < j)
+		QuickSortOrderDescRecurse(Values, left, j, Order);
+	if (i < right)
+		QuickSortOrderDescRecurse(Values, i, right, Order);
+}
+
+static void QuickSortOrderDesc(const std::vector<unsigned> &Values, std::vector<unsigned> &Order)
+{
+	Order.resize(Values.size());
+	for (unsigned i = 0; i < Order.size(); ++i)
+		Order[i] = i;
+	if (!Values.empty())
+		QuickSortOrderDescRecurse(Values.data(), 0, (int)Values.size() - 1, Order.data());
+}
+
+static void appendf2(std::string &s, const char *fmt, ...)
+{
+	char tmp[256];
+	va_list ap;
+	va_start(ap, fmt);
+	int n = vsnprintf(tmp, sizeof tmp, fmt, ap);
+	va_end(ap);
+	if (n > 0)
+		s.append(tmp, (size_t)std::min<int>(n, (int)sizeof tmp - 1));
+}
+
+uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
+{
+	if (usb_device_count() <= 0)
+		Die("No CUDA device available: this build has no CPU search path");
+	SeqDB Input;
+	Input.FromFasta(ReadsFileName);
+	const unsigned SeqCount = Input.GetSeqCount();
+	if (SeqCount == 0)
+		Die("No sequences in input file");
+
+	// ---- DerepFull: open-addressing hash over upper-cased letters
+	std::vector<unsigned> UniqOf(SeqCount), First, USize;
+	{
+		size_t nb = 16;
+		while (nb < 2 * (size_t)SeqCount + 16)
+			nb <<= 1;
+		std::vector<int> bucket(nb, -1);
+		for (unsigned i = 0; i < SeqCount; ++i) {
+			const uint8_t *s = Input.GetSeq(i);
+			const unsigned L = Input.GetSeqLength(i);
+			uint32_t h = 2166136261u;
+			for (unsigned k = 0; k < L; ++k)
+				h = (h ^ (uint32_t)toupper(s[k])) * 16777619u;
+			size_t b = h & (nb - 1);
+			for (;;) {
+				if (bucket[b] < 0) {
+					bucket[b] = (int)First.size();
+					UniqOf[i] = (unsigned)First.size();
+					First.push_back(i);
+					USize.push_back(0);
+					break;
+				}
+				const unsigned f = First[bucket[b]];
+				bool eq = Input.GetSeqLength(f) == L;
+				const uint8_t *t = Input.GetSeq(f);
+				for (unsigned k = 0; eq && k < L; ++k)
+					eq = toupper(s[k]) == toupper(t[k]);
+				if (eq) {
+					UniqOf[i] = (unsigned)bucket[b];
+					break;
+				}
+				b = (b + 1) & (nb - 1);
+			}
+			++USize[UniqOf[i]];
+		}
+	}
+	const unsigned UniqueCount = (unsigned)First.size();
+	// members of each unique in input order (CSR)
+	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(SeqCount);
+	for (unsigned i = 0; i < SeqCount; ++i)
+		++MemberOff[UniqOf[i] + 1];
+	for (unsigned u = 0; u < UniqueCount; ++u)
+		MemberOff[u + 1] += MemberOff[u];
+	{
+		std::vector<unsigned> cur(MemberOff.begin(), MemberOff.end() - 1);
+		for (unsigned i = 0; i < SeqCount; ++i)
+			Members[cur[UniqOf[i]]++] = i;
+	}
+	// ---- GetSeqOrder
+	std::vector<unsigned> Order(UniqueCount);
+	for (unsigned u = 0; u < UniqueCount; ++u)
+		Order[u] = u;
+	if (Opts.sort == "length" || Opts.sort == "size") {
+		std::vector<unsigned> v(UniqueCount);
+		for (unsigned u = 0; u < UniqueCount; ++u)
+			v[u] = Opts.sort == "length" ? Input.GetSeqLength(First[u]) : USize[u];
+		QuickSortOrderDesc(v, Order);
+	} else if (!Opts.sort.empty() && Opts.sort != "other" && Opts.sort != "user")
+		Die("Invalid sort name %s", Opts.sort.c_str());
+	if (Opts.sort == "other")
+		Die("-cluster_fast does not support -sort other, use -cluster_smallmem");
+
+	// uniques in cluster order, flattened
+	std::vector<uint8_t> Letters;
+	std::vector<uint64_t> Off(1, 0);
+	for (unsigned k = 0; k < UniqueCount; ++k) {
+		const unsigned r = First[Order[k]];
+		Letters.insert(Letters.end(), Input.GetSeq(r), Input.GetSeq(r) + Input.GetSeqLength(r));
+		Off.push_back(Letters.size());
+	}
+
+	usb_index *Index = nullptr;
+	usb_searcher *Srch = nullptr;
+	uint64_t zero_off[1] = {0};
+	CheckUsb2(usb_index_create(0, &Opts.P, Letters.data(), zero_off, 0, &Index), "usb_index_create");
+	CheckUsb2(usb_searcher_create(Index, &Opts.P, &Srch), "usb_searcher_create");
+
+	FILE *fUC = nullptr;
+	if (!Opts.uc.empty() && !(fUC = fopen(Opts.uc.c_str(), "wb")))
+		Die("Cannot create %s", Opts.uc.c_str());
+	std::string buf, cp;
+	std::vector<unsigned> ClusterSizes, CentroidRead;
+	std::vector<uint32_t> cidx;
+	unsigned pos = 0;
+	uint32_t B = 256;
+	uint64_t rounds = 0;
+	while (pos < UniqueCount) {
+		const uint32_t n = std::min<uint32_t>(B, UniqueCount - pos);
+		cidx.resize(n);
+		uint32_t ncom = 0;
+		usb_result *R = nullptr;
+		CheckUsb2(usb_cluster_round(Srch, Letters.data(), Off.data() + pos, n, &ncom, cidx.data(), &R), "usb_cluster_round");
+		++rounds;
+		const usb_hit *hits = usb_result_hits(R);
+		const uint64_t *qoff = usb_result_query_offsets(R);
+		uint64_t n_runs = 0;
+		const uint32_t *runs = usb_result_runs(R, &n_runs);
+		for (uint32_t q = 0; q < ncom; ++q) {
+			const unsigned u = Order[pos + q];
+			const unsigned r0 = First[u];
+			const unsigned L = Input.GetSeqLength(r0);
+			const unsigned c = cidx[q];
+			if (qoff[q + 1] == qoff[q]) {
+				// ClusterSink::OnQueryDone, no hit: new centroid (clustersink.cpp:318-329)
+				if (c != ClusterSizes.size())
+					Die("internal: centroid index %u != cluster count %zu", c, ClusterSizes.size());
+				ClusterSizes.push_back(USize[u]);
+				CentroidRead.push_back(r0);
+				if (fUC) {
+					appendf2(buf, "S\t%u\t%u\t*\t.\t*\t*\t*\t", c, L);
+					buf += Input.GetLabel(r0);
+					buf += "\t*\n";
+					for (unsigned m = MemberOff[u] + 1; m < MemberOff[u + 1]; ++m) {
+						appendf2(buf, "H\t%u\t%u\t100.0\t.\t0\t%u\t=\t", c, L, L);
+						buf += Input.GetLabel(Members[m]);
+						buf += '\t';
+						buf += Input.GetLabel(r0);
+						buf += '\n';
+					}
+				}
+			} else {
+				ClusterSizes[c] += USize[u];
+				if (fUC) {
+					AlignResult AR;
+					AR.m_Hit = hits[qoff[q]];
+					AR.m_Runs = runs + AR.m_Hit.run_off;
+					AR.GetCompressedPath(cp);
+					const char *tlabel = Input.GetLabel(CentroidRead[c]);
+					for (unsigned m = MemberOff[u]; m < MemberOff[u + 1]; ++m) {
+						appendf2(buf, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t", c, L, AR.GetPctId(), AR.GetQueryStrand(), 0u, 0u);
+						buf += cp;
+						buf += '\t';
+						buf += Input.GetLabel(Members[m]);
+						buf += '\t';
+						buf += tlabel;
+						buf += '\n';
+					}
+				}
+			}
+			if (fUC && buf.size() > (1u << 20)) {
+				fwrite(buf.data(), 1, buf.size(), fUC);
+				buf.clear();
+			}
+		}
+		usb_result_free(R);
+		pos += ncom;
+		// block size: grow while whole blocks commit, shrink towards the committed prefix otherwise
+		if (ncom == n)
+			B = std::min<uint32_t>(B * 2, Opts.max_block);
+		else
+			B = std::max<uint32_t>(64, std::min<uint32_t>(B, 2 * ncom));
+	}
+	const unsigned ClusterCount = (unsigned)ClusterSizes.size();
+	if (fUC) {
+		for (unsigned c = 0; c < ClusterCount; ++c) {
+			appendf2(buf, "C\t%u\t%u\t*\t*\t*\t*\t*\t", c, ClusterSizes[c]);
+			buf += Input.GetLabel(CentroidRead[c]);
+			buf += "\t*\n";
+		}
+		fwrite(buf.data(), 1, buf.size(), fUC);
+		fclose(fUC);
+	}
+	if (!Opts.centroids.empty()) {
+		FILE *f = fopen(Opts.centroids.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", Opts.centroids.c_str());
+		std::vector<unsigned> COrder;
+		QuickSortOrderDesc(ClusterSizes, COrder);
+		std::string out;
+		for (unsigned k = 0; k < ClusterCount; ++k) {
+			const unsigned r = CentroidRead[COrder[k]];
+			out += '>';
+			out += Input.GetLabel(r);
+			out += '\n';
+			const uint8_t *s = Input.GetSeq(r);
+			const unsigned L = Input.GetSeqLength(r);
+			for (unsigned i = 0; i < L; i += 80) {
+				out.append((const char *)s + i, std::min(80u, L - i));
+				out += '\n';
+			}
+			if (out.size() > (1u << 20)) {
+				fwrite(out.data(), 1, out.size(), f);
+				out.clear();
+			}
+		}
+		fwrite(out.data(), 1, out.size(), f);
+		fclose(f);
+	}
+	if (!Opts.quiet)
+		fprintf(stderr, "%u seqs, %u uniques, %u clusters, %llu rounds\n", SeqCount, UniqueCount, ClusterCount,
+		  (unsigned long long)rounds);
+	usb_searcher_free(Srch);
+	usb_index_free(Index);
+	return ClusterCount;
+}
+
+} // namespace usbhost

@@ -164,6 +164,16 @@ struct SearchOpts {
 	bool quiet = false;
 };
 
+struct ClusterOpts {
+	usb_params P;             // usb_default_params(&P, 1) + -id
+	std::string uc, centroids, sort;
+	uint32_t max_block = 1u << 16;
+	bool quiet = false;
+};
+
+// clusterfast.cpp:81 ClusterFast() with -threads 1 semantics; returns the number of clusters.
+uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
+
 // search.cpp:89 Search(): returns the number of queries with at least one hit.
 uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts);
 

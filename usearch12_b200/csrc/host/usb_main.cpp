@@ -43,11 +43,35 @@ int main(int argc, char **argv)
 		opt.erase(it);
 		return v;
 	};
+	const std::string reads = take("cluster_fast", nullptr);
+	if (!reads.empty()) {
+		// clusterfast.cpp:135 cmd_cluster_fast
+		ClusterOpts C;
+		usb_default_params(&C.P, 1);
+		const std::string cid = take("id", nullptr);
+		if (cid.empty())
+			Die("Must specify -id"); // makeclustersearcher.cpp:30-31
+		C.P.id = (float)atof(cid.c_str());
+		const std::string cstrand = take("strand", "plus");
+		if (cstrand != "plus")
+			Die("-cluster_fast -strand %s is not supported by this build", cstrand.c_str());
+		C.P.maxrejects = (uint32_t)atoi(take("maxrejects", "8").c_str());
+		C.uc = take("uc", nullptr);
+		C.centroids = take("centroids", nullptr);
+		C.sort = take("sort", nullptr);
+		C.max_block = (uint32_t)atoi(take("batch", "65536").c_str());
+		C.quiet = !take("quiet", nullptr).empty();
+		take("threads", nullptr); // derep/cluster order follow the reference's -threads 1 behaviour
+		if (!opt.empty())
+			Die("Option -%s is not supported by this build", opt.begin()->first.c_str());
+		ClusterFast(reads, C);
+		return 0;
+	}
 	SearchOpts O;
 	usb_default_params(&O.P, 0);
 	const std::string query = take("usearch_global", nullptr);
 	if (query.empty())
-		Die("No command: this build implements -usearch_global");
+		Die("No command: this build implements -usearch_global and -cluster_fast");
 	const std::string db = take("db", nullptr);
 	const std::string id = take("id", nullptr);
 	if (id.empty())
