@@ -151,11 +151,14 @@ struct IndexSegment {
 	}
 };
 
+#include "usb_dynseg.inc"
+
 struct usb_index {
 	int device = 0;
 	usb_params P;
 	HostSeqs S;                          // masked SeqDB (host copy)
-	std::vector<IndexSegment *> segs;    // ascending target ranges covering [0, S.n())
+	std::vector<IndexSegment *> segs;    // ascending target ranges covering [0, dyn ? dyn->base : S.n())
+	DynSegment *dyn = nullptr;           // growable tail segment for small appends (cluster_fast)
 	uint32_t n_dev = 0;                  // targets whose letters are on the device
 	uint64_t n_postings = 0;
 	DevBuf<uint8_t> d_seqs;
@@ -176,6 +179,14 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 		v.seg[i].postings = g->d_postings.p;
 		v.seg[i].base = g->H.base;
 		v.seg[i].count = g->H.count;
+	}
+	if (ix->dyn) {
+		SegDesc &d = v.seg[v.n_seg++];
+		d.row_off = ix->dyn->d_row_off.p;
+		d.row_size = ix->dyn->d_row_size.p;
+		d.postings = ix->dyn->d_pool.p;
+		d.base = ix->dyn->base;
+		d.count = ix->dyn->count;
 	}
 }
 
@@ -329,6 +340,19 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	CK(cudaMemcpy(ix->d_seq_off.p + n0, S.seq_off.data() + n0, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
 	ix->n_dev = n0 + n;
+	// small appends (and everything after the first one) go to the growable tail segment
+	if (ix->dyn || n < 8192) {
+		if (!ix->dyn) {
+			ix->dyn = new DynSegment;
+			if ((rc = ix->dyn->init(n0, ix->P.word_length)))
+				return rc;
+		}
+		const uint64_t before = ix->dyn->n_postings;
+		if ((rc = ix->dyn->append(S, n0, n, ix->P.word_length)))
+			return rc;
+		ix->n_postings += ix->dyn->n_postings - before;
+		return 0;
+	}
 	// new segment, then merge while the last two are of similar size (or the list is full)
 	IndexSegment *g = new IndexSegment;
 	build_csr(S, n0, n, ix->P.word_length, 0, g->H);
@@ -365,6 +389,10 @@ extern "C" void usb_index_free(usb_index *ix)
 		g->release();
 		delete g;
 	}
+	if (ix->dyn) {
+		ix->dyn->release();
+		delete ix->dyn;
+	}
 	delete ix;
 }
 
@@ -380,6 +408,12 @@ extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t 
 	for (const IndexSegment *g : ix->segs)
 		tmp.insert(tmp.end(), g->H.postings.begin() + g->H.row_off[word],
 		  g->H.postings.begin() + g->H.row_off[word] + g->H.row_size[word]);
+	if (ix->dyn && ix->dyn->row_size[word]) {
+		const size_t n0 = tmp.size(), n = ix->dyn->row_size[word];
+		tmp.resize(n0 + n);
+		cudaSetDevice(ix->device);
+		CK(cudaMemcpy(tmp.data() + n0, ix->dyn->d_pool.p + ix->dyn->row_off[word], n * 4, cudaMemcpyDeviceToHost));
+	}
 	*row = tmp.data();
 	*size = (uint32_t)tmp.size();
 	return 0;
@@ -623,8 +657,11 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 	g.grid = (uint32_t)s->num_sms;
 	g.n_warps = g.grid * g.wpb;
 	// keep the workspace under ~1/3 of device memory
-	size_t free_b = 0, total_b = 0;
-	CK(cudaMemGetInfo(&free_b, &total_b));
+	static thread_local size_t total_b = 0; // (same device class for every searcher of a process)
+	if (total_b == 0) {
+		size_t free_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+	}
 	const uint64_t limit = std::max<uint64_t>(total_b / 3, (uint64_t)256 << 20);
 	while ((uint64_t)g.n_warps * g.slab_stride > limit && g.grid > 1) {
 		g.grid = std::max(1u, g.grid / 2);
@@ -638,9 +675,17 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 
 static cudaError_t launch_align(const AlignArgs &a, const AlignGeom &g, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-	if (e != cudaSuccess)
-		return e;
+	static thread_local size_t smem_set = 0;
+	static thread_local int dev_set = -1;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (g.smem > smem_set || dev != dev_set) {
+		cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+		if (e != cudaSuccess)
+			return e;
+		smem_set = g.smem;
+		dev_set = dev;
+	}
 	k_align<<<g.grid, g.wpb * 32, g.smem, st>>>(a);
 	return cudaGetLastError();
 }

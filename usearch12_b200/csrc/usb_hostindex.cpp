@@ -93,8 +93,6 @@ void HostSeqs::append(const uint8_t *s, const uint64_t *off, uint32_t count, int
 {
 	const uint32_t n0 = n();
 	uint64_t cur = seq_off.back();
-	seq_off.reserve(seq_off.size() + count);
-	seq_len.reserve(seq_len.size() + count);
 	for (uint32_t i = 0; i < count; ++i) {
 		const uint64_t L = off[i + 1] - off[i];
 		seq_len.push_back((uint32_t)L);
