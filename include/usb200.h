@@ -52,6 +52,8 @@ typedef struct usb_params {
 	float term_gap_ext;     /* terminal gap extend, -0.5 */
 	int32_t dbmask;         /* 1 = fastnucleo soft-masking of the DB (makeudb.cpp:11-25) */
 	int32_t cluster_mode;   /* 1 = cluster_fast semantics: raw un-masked centroids, growing DB */
+	int32_t fulldp;         /* -fulldp: no HSPs, full Viterbi per candidate (globalalignmem.cpp:153-157);
+	                           band = 0 (-band 0) alone selects the full DP for holes only (:103-106) */
 } usb_params;
 
 /* Defaults of -usearch_global (cluster_fast=0) or -cluster_fast (=1). */

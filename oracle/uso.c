@@ -1116,6 +1116,12 @@ static float viterbi_main_diag(float (*Mx)[256], float *Mrow, float *Drow, uint8
 	{
 	unsigned DiagLo = LA < LB ? LA : LB;
 	unsigned DiagHi = LA > LB ? LA : LB;
+	if (BandRadius == 0)
+		{
+		/* -band 0: ViterbiFastMem (viterbifastmem.cpp:9-170) = the same recurrence over the full
+		 * rectangle; a band that covers every diagonal reproduces it cell for cell */
+		return viterbi_band(Mx, Mrow, Drow, TB, A, LA, B, LB, 1, LA + LB - 1, AP, path);
+		}
 	if (DiagLo > BandRadius)
 		DiagLo -= BandRadius;
 	else
@@ -1206,6 +1212,15 @@ static int global_align(uso_searcher *s, const uint8_t *A, unsigned LA, const ui
 		MinHSPLength = LA / 4;
 	if (MinHSPLength < 16)
 		MinHSPLength = 16;
+	if (s->P.fulldp)
+		{
+		/* globalalignmem.cpp:153-157: FullDPAlways */
+		alnp G;
+		global_ap(s, &G);
+		dp_alloc(s, LA, LB);
+		viterbi_main_diag(s->subst, s->Mrow, s->Drow, s->TB, A, LA, B, LB, 0, &G, path);
+		return 1;
+		}
 	float HSPFractId;
 	hsp_set_b(s, B, LB); /* Searcher::SetTarget -> GlobalAligner::SetTargetImpl globalaligner.cpp:69-74 */
 	unsigned HSPCount = get_global_hsps(s, A, LA, B, LB, MinHSPLength, &HSPFractId);

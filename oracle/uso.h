@@ -41,6 +41,7 @@ typedef struct uso_params {
 	float mismatch;      /* -mismatch -2 */
 	int dbmask_fast;     /* 1 = fastnucleo soft masking of the DB (makeudb.cpp:11-25) */
 	int cluster_mode;    /* 1 = cluster_fast semantics (no DB masking, growing DB) */
+	int fulldp;          /* -fulldp: no HSPs, full Viterbi on every candidate (globalalignmem.cpp:153-157) */
 } uso_params;
 
 void uso_default_params(uso_params *p, int cluster_fast);

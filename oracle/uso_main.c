@@ -238,6 +238,10 @@ int main(int argc, char **argv)
 		P.maxaccepts = (unsigned) atoi(argv[9]);
 		P.maxrejects = (unsigned) atoi(argv[10]);
 		}
+	if (argc > 11)
+		P.band = (unsigned) atoi(argv[11]);
+	if (argc > 12)
+		P.fulldp = atoi(argv[12]);
 	fasta Q, D;
 	read_fasta(argv[2], &Q);
 	read_fasta(argv[3], &D);

@@ -19,7 +19,7 @@ class Params(C.Structure):
         ("strand_both", C.c_int), ("word_length", C.c_uint), ("big", C.c_uint), ("bump", C.c_uint),
         ("stepwords", C.c_uint), ("band", C.c_uint), ("minhsp", C.c_uint), ("hspw", C.c_uint),
         ("xdrop_nw", C.c_float), ("match", C.c_float), ("mismatch", C.c_float), ("dbmask_fast", C.c_int),
-        ("cluster_mode", C.c_int),
+        ("cluster_mode", C.c_int), ("fulldp", C.c_int),
     ]
 
 

@@ -128,7 +128,7 @@ def test_cli_refuses_unsupported_options(tmp_path):
     import subprocess
     from usearch12_b200 import build
     cli = build.build_cli()
-    r = subprocess.run([cli, "-usearch_global", "x.fa", "-db", "y.fa", "-id", "0.9", "-strand", "plus", "-fulldp", "1"],
+    r = subprocess.run([cli, "-usearch_global", "x.fa", "-db", "y.fa", "-id", "0.9", "-strand", "plus", "-maxhits", "3"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "not supported" in r.stdout
 
@@ -151,3 +151,21 @@ def test_index_append_equals_one_shot_build(golden):
     r2 = capi.Searcher(grown, p).search(qs)
     assert np.array_equal(r1.hits[["query", "target", "ids", "alnlen", "rank"]], r2.hits[["query", "target", "ids", "alnlen", "rank"]])
     assert [r1.cigar(h) for h in r1.hits] == [r2.cigar(h) for h in r2.hits]
+
+
+@pytest.mark.parametrize("mode", ["band0", "fulldp"])
+def test_full_dp_variants_match_reference_golden(golden, mode):
+    """-band 0 (ViterbiFastMem for the holes, globalalignmem.cpp:103-106) and -fulldp (no HSPs,
+    full Viterbi per candidate, :153-157): reference-binary outputs on 800 golden reads."""
+    from usearch12_b200 import capi
+    kw = dict(band=0) if mode == "band0" else dict(fulldp=1)
+    p = capi.default_params(**kw)
+    ix = capi.Index(golden.db, p)
+    s = capi.Searcher(ix, p)
+    qs = golden.q[:600] + golden.q[-200:]
+    labels = golden.q_labels[:600] + golden.q_labels[-200:]
+    res = s.search(qs)
+    user, uc, _ = util.product_lines(res, labels, qs, golden.db_labels)
+    for got, kind in ((user, "user"), (uc, "uc")):
+        d = util.first_diff(got, golden.lines(mode + "_q600", kind))
+        assert d is None, "%s %s\n%s" % (mode, kind, d)

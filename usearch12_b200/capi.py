@@ -26,7 +26,7 @@ class Params(C.Structure):
         ("band", C.c_uint32), ("minhsp", C.c_uint32), ("hspw", C.c_uint32), ("xdrop_nw", C.c_float),
         ("match", C.c_float), ("mismatch", C.c_float), ("gap_open", C.c_float), ("gap_ext", C.c_float),
         ("term_gap_open", C.c_float), ("term_gap_ext", C.c_float), ("dbmask", C.c_int32),
-        ("cluster_mode", C.c_int32),
+        ("cluster_mode", C.c_int32), ("fulldp", C.c_int32),
     ]
 
 

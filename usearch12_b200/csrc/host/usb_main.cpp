@@ -17,7 +17,7 @@ using namespace usbhost;
 int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
-	static const char *flags[] = {"quiet", "output_no_hits", nullptr};
+	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", nullptr};
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
 		if (a[0] != '-')
@@ -83,6 +83,8 @@ int main(int argc, char **argv)
 	O.P.strand_both = strand == "both";
 	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", "1").c_str());
 	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", "32").c_str());
+	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
+	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
 	const std::string dbmask = take("dbmask", "fastnucleo");
 	if (dbmask != "fastnucleo" && dbmask != "none")
 		Die("-dbmask %s not supported (fastnucleo|none)", dbmask.c_str());

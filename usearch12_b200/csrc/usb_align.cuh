@@ -776,6 +776,10 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 	dlo = dlo > P.band ? dlo - P.band : 1;
 	dhi += P.band;
 	dhi = min(dhi, LA + LB - 1);
+	if (P.band == 0) { // -band 0: ViterbiFastMem (viterbifastmem.cpp:9-170) == a band over every diagonal
+		dlo = 1;
+		dhi = LA + LB - 1;
+	}
 	const uint64_t W = (uint64_t)LB + 1;
 	// rows in shared memory when the rectangle is narrow enough, else in the global slab
 	const bool rows_fit = 8u * (LB + 8) <= a.scratch_bytes;
@@ -981,6 +985,15 @@ __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, u
 	const DevParams &P = a.P;
 	const uint32_t lane = lane_id();
 	const uint32_t LA = w.LA, LB = w.LB;
+	if (P.fulldp) { // globalalignmem.cpp:153-157 FullDPAlways: no HSPs, no identity gate
+		if (n_chain_out)
+			*n_chain_out = 0;
+		if (LA == 0 || LB == 0)
+			return 0;
+		const GapCosts G = hole_costs(P, true, true, true, true);
+		++st.n_dp;
+		return viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, w.path, nullptr, &st.dp_cells);
+	}
 	uint32_t MinHSPLength = P.min_hsp_len == 0 ? 32 : P.min_hsp_len;
 	MinHSPLength = min(MinHSPLength, LA / 4);
 	MinHSPLength = max(MinHSPLength, 16u);

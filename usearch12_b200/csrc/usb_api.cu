@@ -263,6 +263,7 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 	D.maxaccepts = p->maxaccepts;
 	D.maxrejects = p->maxrejects;
 	D.bump = p->bump;
+	D.fulldp = p->fulldp != 0;
 	D.id_d = (double)p->id;
 	return 0;
 }

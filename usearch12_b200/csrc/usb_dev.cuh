@@ -38,6 +38,7 @@ struct DevParams {
 	uint32_t word_length, slots;         // UDB
 	uint32_t maxaccepts, maxrejects;
 	uint32_t bump;
+	uint32_t fulldp;                     // -fulldp (FullDPAlways)
 	double id_d;                         // (double)(float)id (accepter.cpp:36-38)
 };
 
