@@ -9,6 +9,7 @@
 #include "uso.h"
 #include <ctype.h>
 #include <limits.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -25,6 +26,13 @@ static uint8_t g_c2l[256];       /* alpha.cpp g_CharToLetterNucleo: ACGTU/acgtu 
 static uint8_t g_match[256][256];/* alpha2.cpp:220-264 g_MatchMxNucleo */
 static uint8_t g_comp[256];      /* alpha.cpp g_CharToCompChar ('?' = invalid -> keep char) */
 static int g_tables_done;
+/* current alphabet (set on every API entry from the params): nt or aa */
+static uint8_t g_c2l_aa[256];      /* alpha.cpp g_CharToLetterAmino: ACDEFGHIKLMNPQRSTVWY both cases -> 0..19 */
+static uint8_t g_match_aa[256][256];/* alpha2.cpp:220-279 g_MatchMxAmino */
+static float g_blosum[256][256];   /* blosum62.cpp:17-96 */
+static const uint8_t *g_cur_c2l = 0;
+static unsigned g_cur_A = 4;
+static uint8_t (*g_cur_match)[256] = 0;
 
 static void init_tables(void)
 	{
@@ -90,7 +98,91 @@ static void init_tables(void)
 			g_comp[(uint8_t) tolower(from[i])] = (uint8_t) tolower(to[i]);
 		}
 	g_comp[0] = 0;
+
+	/* amino acid tables */
+	memset(g_c2l_aa, 0xff, sizeof g_c2l_aa);
+	const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+	for (int i = 0; i < 20; ++i)
+		{
+		g_c2l_aa[(uint8_t) aa[i]] = (uint8_t) i;
+		g_c2l_aa[(uint8_t) tolower(aa[i])] = (uint8_t) i;
+		}
+	for (unsigned i = 0; i < 256; ++i)
+		for (unsigned j = 0; j < 256; ++j)
+			{
+			int ai = isalpha((int) i) != 0, aj = isalpha((int) j) != 0;
+			uint8_t m;
+			if (!ai || !aj)
+				m = (uint8_t) ((i == '-' || i == '.') && (j == '-' || j == '.'));
+			else if (toupper((int) i) == toupper((int) j))
+				m = 1;
+			else
+				m = (uint8_t) (toupper((int) i) == 'X' || toupper((int) j) == 'X');
+			g_match_aa[i][j] = m;
+			}
+	g_match_aa['B']['N'] = g_match_aa['N']['B'] = g_match_aa['B']['D'] = g_match_aa['D']['B'] = 1;
+	g_match_aa['Z']['Q'] = g_match_aa['Q']['Z'] = g_match_aa['Z']['E'] = g_match_aa['E']['Z'] = 1;
+	/* BLOSUM62 in NCBI order, 1/2-bit units; both cases; everything else 0 (blosum62.cpp:48-80) */
+	static const char *bl_alpha = "ARNDCQEGHILKMFPSTWYVBZX*";
+	static const signed char bl[24][24] = {
+		{ 4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0,-2,-1, 0,-4},
+		{-1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3,-1, 0,-1,-4},
+		{-2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3, 3, 0,-1,-4},
+		{-2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3, 4, 1,-1,-4},
+		{ 0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1,-3,-3,-2,-4},
+		{-1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2, 0, 3,-1,-4},
+		{-1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,-4},
+		{ 0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3,-1,-2,-1,-4},
+		{-2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3, 0, 0,-1,-4},
+		{-1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3,-3,-3,-1,-4},
+		{-1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1,-4,-3,-1,-4},
+		{-1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2, 0, 1,-1,-4},
+		{-1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1,-3,-1,-1,-4},
+		{-2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1,-3,-3,-1,-4},
+		{-1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2,-2,-1,-2,-4},
+		{ 1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2, 0, 0, 0,-4},
+		{ 0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0,-1,-1, 0,-4},
+		{-3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3,-4,-3,-2,-4},
+		{-2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1,-3,-2,-1,-4},
+		{ 0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4,-3,-2,-1,-4},
+		{-2,-1, 3, 4,-3, 0, 1,-1, 0,-3,-4, 0,-3,-3,-2, 0,-1,-4,-3,-3, 4, 1,-1,-4},
+		{-1, 0, 0, 1,-3, 3, 4,-2, 0,-3,-3, 1,-1,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,-4},
+		{ 0,-1,-1,-1,-2,-1,-1,-1,-1,-1,-1,-1,-1,-1,-2, 0, 0,-2,-1,-1,-1,-1,-1,-4},
+		{-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4,-4, 1}};
+	memset(g_blosum, 0, sizeof g_blosum);
+	for (int i = 0; i < 24; ++i)
+		for (int j = 0; j < 24; ++j)
+			{
+			uint8_t ui = (uint8_t) bl_alpha[i], uj = (uint8_t) bl_alpha[j];
+			uint8_t li = (uint8_t) tolower(ui), lj = (uint8_t) tolower(uj);
+			float v = (float) bl[i][j];
+			g_blosum[ui][uj] = v; g_blosum[ui][lj] = v; g_blosum[li][uj] = v; g_blosum[li][lj] = v;
+			}
+	g_cur_c2l = g_c2l;
+	g_cur_match = g_match;
 	g_tables_done = 1;
+	}
+
+/* selects the alphabet the UDB words and identity counts use (udbparams.cpp:235-261) */
+static void use_alpha(const uso_params *p)
+	{
+	init_tables();
+	if (p->is_nucleo)
+		{
+		g_cur_c2l = g_c2l; g_cur_A = 4; g_cur_match = g_match;
+		}
+	else
+		{
+		g_cur_c2l = g_c2l_aa; g_cur_A = 20; g_cur_match = g_match_aa;
+		}
+	}
+
+static unsigned slot_count_of(const uso_params *p)
+	{
+	unsigned A = p->is_nucleo ? 4 : 20, n = 1;
+	for (unsigned i = 0; i < p->word_length; ++i)
+		n *= A;
+	return n;
 	}
 
 void uso_default_params(uso_params *p, int cluster_fast)
@@ -113,6 +205,21 @@ void uso_default_params(uso_params *p, int cluster_fast)
 	p->mismatch = -2.0f;
 	p->dbmask_fast = 1;
 	p->cluster_mode = cluster_fast;
+	p->evalue = 10.0f;
+	p->xdrop_u = 16.0f;
+	p->xdrop_g = 32.0f;
+	p->lopen = -10.0f;
+	p->lext = -1.0f;
+	p->ka_dbsize = 1e9f;
+	}
+
+/* amino acid defaults: UDB words of 5 letters over the 20-letter alphabet (udbparams.cpp:236-261),
+ * LocalAligner2 words of 3 letters (makedbsearcher.cpp:116-120) */
+void uso_set_amino(uso_params *p)
+	{
+	p->is_nucleo = 0;
+	p->word_length = 5;
+	p->hspw = 3;
 	}
 
 /* ------------------------------------------------------------------ small helpers */
@@ -230,10 +337,10 @@ static uint32_t seq_to_word(const uint8_t *s, unsigned w)
 		uint8_t c = s[i];
 		if (islower(c))
 			return BADWORD;
-		unsigned letter = g_c2l[c];
-		if (letter == 0xff)
+		unsigned letter = g_cur_c2l[c];
+		if (letter >= g_cur_A)
 			return BADWORD;
-		word = word * 4 + letter;
+		word = word * g_cur_A + letter;
 		}
 	return word;
 	}
@@ -266,8 +373,8 @@ static unsigned unique_words(const uint8_t *seq, uint32_t L, unsigned w, uint8_t
 
 unsigned uso_query_unique_words(const uso_params *p, const uint8_t *q, uint32_t L, uint32_t *words)
 	{
-	init_tables();
-	unsigned slots = 1u << (2 * p->word_length);
+	use_alpha(p);
+	unsigned slots = slot_count_of(p);
 	uint8_t *found = (uint8_t *) calloc(slots, 1);
 	uint32_t *all = (uint32_t *) xrealloc(0, (L + 1) * sizeof(uint32_t));
 	unsigned n = unique_words(q, L, p->word_length, found, all, words);
@@ -297,7 +404,7 @@ uso_db *uso_db_create(const uso_params *p)
 	init_tables();
 	uso_db *db = (uso_db *) calloc(1, sizeof *db);
 	db->P = *p;
-	db->slot_count = 1u << (2 * p->word_length); /* udbparams.cpp:72-78: AlphaSize^w, non-hashed */
+	db->slot_count = slot_count_of(p); /* udbparams.cpp:72-78: AlphaSize^w, non-hashed */
 	db->sizes = (uint32_t *) calloc(db->slot_count, sizeof(uint32_t));
 	db->caps = (uint32_t *) calloc(db->slot_count, sizeof(uint32_t));
 	db->rows = (uint32_t **) calloc(db->slot_count, sizeof(uint32_t *));
@@ -316,6 +423,7 @@ uint32_t uso_db_add(uso_db *db, const uint8_t *seq, uint32_t L, const char *labe
 		db->lens = (uint32_t *) xrealloc(db->lens, db->cap * sizeof(uint32_t));
 		db->labels = (char **) xrealloc(db->labels, db->cap * sizeof(char *));
 		}
+	use_alpha(&db->P);
 	uint32_t idx = db->n++;
 	uint8_t *s = (uint8_t *) xrealloc(0, L + 1);
 	memcpy(s, seq, L);
@@ -403,6 +511,19 @@ struct uso_searcher
 	char *subpath; uint32_t subcap;
 	/* terminator */
 	unsigned acc, rej;
+	/* EStats (estats.cpp) */
+	double es_gl, es_ul, es_gk, es_uk, es_loggk, es_loguk, es_dbsize, es_maxevalue;
+	uint64_t es_letters;
+	/* LocalAligner2 (localaligner2.cpp) */
+	unsigned la_w, la_A, la_dict, la_hi, la_nq;
+	uint32_t *la_qcounts, *la_qcounts2, *la_base, *la_qwords, *la_qposvec, *la_twords;
+	uint32_t la_qcap, la_tcap;
+	float la_min_ungapped;
+	/* X-drop DP (xdpmem.h) */
+	float *xd_M, *xd_D; uint32_t xd_rowcap;
+	uint8_t *xd_TB; size_t xd_tbcap;
+	uint8_t *xd_revA, *xd_revB; uint32_t xd_seqcap;
+	int xd_poison;
 	};
 
 static void set_nuc_subst(float (*mx)[256], float match, float mismatch)
@@ -420,6 +541,8 @@ static void set_nuc_subst(float (*mx)[256], float match, float mismatch)
 			}
 	}
 
+static void la_init(uso_searcher *s);
+
 uso_searcher *uso_searcher_create(uso_db *db, const uso_params *p)
 	{
 	init_tables();
@@ -427,7 +550,17 @@ uso_searcher *uso_searcher_create(uso_db *db, const uso_params *p)
 	s->db = db;
 	s->P = *p;
 	s->subst = (float (*)[256]) xrealloc(0, 256 * 256 * sizeof(float));
-	set_nuc_subst(s->subst, p->match, p->mismatch);
+	if (p->is_nucleo)
+		set_nuc_subst(s->subst, p->match, p->mismatch);
+	else
+		memcpy(s->subst, g_blosum, 256 * 256 * sizeof(float)); /* alnparams.cpp:330-349: BLOSUM62 */
+	if (!p->is_nucleo && !p->local)
+		{
+		fprintf(stderr, "oracle: amino acid usearch_global is not restated\n");
+		abort();
+		}
+	s->xd_poison = getenv("USO_XD_POISON") != 0;
+	la_init(s);
 	/* alnheuristics.cpp:26-44 (nucleo branch) */
 	s->XDropGlobalHSP = p->xdrop_nw;
 	s->BandRadius = p->band;
@@ -437,7 +570,7 @@ uso_searcher *uso_searcher_create(uso_db *db, const uso_params *p)
 	s->Open = -10.0f; s->Ext = -1.0f; s->TermOpen = -0.5f; s->TermExt = -0.5f;
 	s->found = (uint8_t *) calloc(db->slot_count, 1);
 	/* hspfinder.cpp:193-217 */
-	s->hsp_w = p->hspw;
+	s->hsp_w = p->is_nucleo ? p->hspw : 0;
 	s->hsp_wordcount = 1;
 	for (unsigned i = 0; i < s->hsp_w; ++i)
 		s->hsp_wordcount *= 4;
@@ -456,6 +589,8 @@ void uso_searcher_free(uso_searcher *s)
 	free(s->cs_sizes); free(s->cs_offsets);
 	free(s->wordsA); free(s->wordsB); free(s->word2posA); free(s->wordcountsA);
 	free(s->ung); free(s->chain); free(s->Mrow); free(s->Drow); free(s->TB); free(s->subpath);
+	free(s->la_qcounts); free(s->la_qcounts2); free(s->la_base); free(s->la_qwords); free(s->la_qposvec);
+	free(s->la_twords); free(s->xd_M); free(s->xd_D); free(s->xd_TB); free(s->xd_revA); free(s->xd_revB);
 	free(s);
 	}
 
@@ -1296,6 +1431,672 @@ int uso_global_align(uso_searcher *s, const uint8_t *q, uint32_t LQ, const uint8
 
 /* ------------------------------------------------------------------ AlignResult stats */
 /* arscorer.cpp:201-296 FillLo + :554-570 GetGapOpenCount (global: m_HSP spans both sequences) */
+/* ------------------------------------------------------------------ local alignment (config 5)
+ * EStats (estats.cpp:25-101): Karlin-Altschul statistics in double; the DB size and the maximum
+ * E-value reach the constructor as floats (makedbsearcher.cpp:90-98). */
+static void estats_init(uso_searcher *s)
+	{
+	uso_db *db = s->db;
+	uint64_t letters = 0;
+	for (uint32_t i = 0; i < db->n; ++i)
+		letters += db->lens[i];
+	/* makedbsearcher.cpp:92-96: -ka_dbsize has a default (o_defaults.inc:2, 1e9) and defaults count
+	 * as "filled", so the letter count of the DB is never used */
+	float DBSize = s->P.ka_dbsize > 0.0f ? s->P.ka_dbsize : (float) letters;
+	s->es_dbsize = (double) DBSize;
+	s->es_maxevalue = (double) (float) s->P.evalue;
+	if (s->P.is_nucleo)
+		{
+		s->es_gl = 1.280; s->es_ul = 1.330; s->es_gk = 0.460; s->es_uk = 0.621;
+		}
+	else
+		{
+		s->es_gl = 0.267; s->es_ul = 0.311; s->es_gk = 0.0410; s->es_uk = 0.128;
+		}
+	s->es_loggk = log(s->es_gk);
+	s->es_loguk = log(s->es_uk);
+	s->es_letters = letters;
+	}
+
+/* estats.cpp:65-71 */
+static double es_min_ungapped_raw(const uso_searcher *s, unsigned QL)
+	{
+	double Log2 = log(2.0);
+	double BitScore = (log(s->es_dbsize * QL) - log(s->es_maxevalue)) / Log2;
+	return (BitScore * Log2 + s->es_loguk) / s->es_ul;
+	}
+
+/* estats.cpp:79-85 (gapped) */
+static double es_raw_to_bits(const uso_searcher *s, double raw)
+	{
+	double Log2 = log(2.0);
+	return (raw * s->es_gl - s->es_loggk) / Log2;
+	}
+
+/* estats.cpp:73-96 */
+static double es_raw_to_evalue(const uso_searcher *s, double raw, unsigned QL)
+	{
+	double BitScore = es_raw_to_bits(s, raw);
+	double NM = (double) QL * s->es_dbsize;
+	double p = pow(2.0, BitScore);
+	return NM / p;
+	}
+
+static void la_refresh_estats(uso_searcher *s)
+	{
+	/* the reference builds g_ES once, after the DB is loaded; the oracle's DB may still be
+	 * growing when the searcher is created, so recompute when the letter count changed */
+	uint64_t letters = 0;
+	for (uint32_t i = 0; i < s->db->n; ++i)
+		letters += s->db->lens[i];
+	if (letters != s->es_letters || s->es_gl == 0.0)
+		estats_init(s);
+	}
+
+/* LocalAligner2::InitImpl (localaligner2.cpp:47-62) */
+static void la_init(uso_searcher *s)
+	{
+	s->la_A = s->P.is_nucleo ? 4 : 20;
+	s->la_w = s->P.hspw; /* makedbsearcher.cpp:104-123: 5 nt / 3 aa unless -hspw */
+	s->la_dict = 1;
+	for (unsigned i = 0; i < s->la_w; ++i)
+		s->la_dict *= s->la_A;
+	s->la_hi = s->la_dict / s->la_A;
+	s->la_qcounts = (uint32_t *) calloc(s->la_dict, sizeof(uint32_t));
+	s->la_qcounts2 = (uint32_t *) calloc(s->la_dict, sizeof(uint32_t));
+	s->la_base = (uint32_t *) calloc(s->la_dict, sizeof(uint32_t));
+	}
+
+/* rolling words, wildcards -> letter 0, nothing skipped (localaligner2.cpp:85-117, localmulti.cpp:30-62) */
+static unsigned la_words(const uso_searcher *s, const uint8_t *seq, unsigned L, uint32_t *words)
+	{
+	const uint8_t *c2l = s->P.is_nucleo ? g_c2l : g_c2l_aa;
+	const unsigned A = s->la_A, w = s->la_w;
+	uint32_t Word = 0;
+	const uint8_t *Front = seq, *Back = seq;
+	for (unsigned i = 0; i + 1 < w; ++i)
+		{
+		unsigned Letter = c2l[*Front++];
+		if (Letter >= A)
+			Letter = 0;
+		Word = Word * A + Letter;
+		}
+	unsigned n = 0;
+	for (unsigned pos = w - 1; pos < L; ++pos)
+		{
+		unsigned Letter = c2l[*Front++];
+		if (Letter >= A)
+			Letter = 0;
+		Word = Word * A + Letter;
+		words[n++] = Word;
+		Letter = c2l[*Back++];
+		if (Letter >= A)
+			Letter = 0;
+		Word -= Letter * s->la_hi;
+		}
+	return n;
+	}
+
+/* LocalAligner2::SetQueryImpl (localaligner2.cpp:64-155) + LocalAligner::SetQueryImpl (:213-217) */
+static void la_set_query(uso_searcher *s, const uint8_t *Q, unsigned QL)
+	{
+	la_refresh_estats(s);
+	s->la_min_ungapped = (float) es_min_ungapped_raw(s, QL);
+	s->la_nq = 0;
+	if (QL <= s->la_w)
+		return;
+	if (s->la_qcap < QL + 1)
+		{
+		s->la_qcap = QL + 1;
+		s->la_qwords = (uint32_t *) xrealloc(s->la_qwords, s->la_qcap * sizeof(uint32_t));
+		s->la_qposvec = (uint32_t *) xrealloc(s->la_qposvec, s->la_qcap * sizeof(uint32_t));
+		}
+	unsigned n = la_words(s, Q, QL, s->la_qwords);
+	s->la_nq = n;
+	for (unsigned i = 0; i < n; ++i)
+		++s->la_qcounts2[s->la_qwords[i]];
+	unsigned Base = 0;
+	for (unsigned i = 0; i < n; ++i)
+		{
+		uint32_t Word = s->la_qwords[i];
+		unsigned c = s->la_qcounts2[Word];
+		if (c == 0)
+			continue;
+		s->la_base[Word] = Base;
+		s->la_qcounts2[Word] = 0;
+		Base += c;
+		}
+	for (unsigned i = 0; i < n; ++i)
+		{
+		uint32_t Word = s->la_qwords[i];
+		unsigned c = s->la_qcounts[Word];
+		s->la_qcounts[Word] = c + 1;
+		s->la_qposvec[s->la_base[Word] + c] = i;
+		}
+	}
+
+/* LocalAligner2::OnQueryDoneImpl (localaligner2.cpp:157-168) */
+static void la_query_done(uso_searcher *s)
+	{
+	for (unsigned i = 0; i < s->la_nq; ++i)
+		{
+		s->la_qcounts[s->la_qwords[i]] = 0;
+		s->la_qcounts2[s->la_qwords[i]] = 0;
+		}
+	s->la_nq = 0;
+	}
+
+static void xd_alloc(uso_searcher *s, unsigned LA, unsigned LB)
+	{
+	if (s->xd_rowcap < LB + 136)
+		{
+		s->xd_rowcap = LB + 136;
+		s->xd_M = (float *) xrealloc(s->xd_M, s->xd_rowcap * sizeof(float));
+		s->xd_D = (float *) xrealloc(s->xd_D, s->xd_rowcap * sizeof(float));
+		for (unsigned i = 0; i < s->xd_rowcap; ++i)
+			s->xd_M[i] = s->xd_D[i] = 0.0f;
+		}
+	size_t need = (size_t) (LA + 2) * (LB + 2);
+	if (s->xd_tbcap < need)
+		{
+		s->xd_tbcap = need;
+		s->xd_TB = (uint8_t *) xrealloc(s->xd_TB, need);
+		}
+	if (s->xd_seqcap < LA + LB + 2)
+		{
+		s->xd_seqcap = LA + LB + 2;
+		s->xd_revA = (uint8_t *) xrealloc(s->xd_revA, s->xd_seqcap);
+		s->xd_revB = (uint8_t *) xrealloc(s->xd_revB, s->xd_seqcap);
+		}
+	}
+
+#define XD_UNWRITTEN 0x80 /* oracle-only poison: a traceback that touches a cell this call did not write aborts */
+
+/* XDropFwdFastMem (xdropfwdmem.cpp:344-749) + XDropFwdTraceBackBitMem (:271-342).
+ * path receives the forward path (NUL-terminated, capacity >= LA+LB+1). */
+static float xdrop_fwd(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB, float X,
+  unsigned *Leni, unsigned *Lenj, char *path)
+	{
+	float (*Mx)[256] = s->subst;
+	if (LA == 1 || LB == 1)
+		{
+		*Leni = 1; *Lenj = 1;
+		path[0] = 'M'; path[1] = 0;
+		return Mx[A[0]][B[0]];
+		}
+	xd_alloc(s, LA, LB);
+	const float Open = s->P.lopen, Ext = s->P.lext;
+	const float AbsOpen = -Open, AbsExt = -Ext;
+	const size_t stride = (size_t) LB + 2;
+	uint8_t *TB = s->xd_TB;
+	memset(TB, XD_UNWRITTEN, (size_t) (LA + 2) * stride);
+	float *Mrow = s->xd_M + 1, *Drow = s->xd_D + 1;
+	if (s->xd_poison)
+		for (unsigned i = 0; i < s->xd_rowcap; ++i)
+			s->xd_M[i] = s->xd_D[i] = 1e30f;
+	Mrow[-1] = MINUS_INF;
+	Drow[0] = MINUS_INF;
+	Drow[1] = MINUS_INF;
+
+	float BestScore = Mx[A[0]][B[0]];
+	unsigned Besti = 0, Bestj = 0;
+	unsigned prev_jlo = 0, prev_jhi = 0, jlo = 1, jhi = 1;
+	float M0 = BestScore;
+	for (unsigned i = 1; i < LA; ++i)
+		{
+		if (jlo == prev_jlo)
+			{
+			Mrow[jlo - 1] = MINUS_INF;
+			Drow[jlo] = MINUS_INF;
+			}
+		unsigned endj = prev_jhi + 1 < LB ? prev_jhi + 1 : LB;
+		for (unsigned j = endj + 1; j <= (jhi + 1 < LB ? jhi + 1 : LB); ++j)
+			{
+			Mrow[j - 1] = MINUS_INF;
+			Drow[j] = MINUS_INF;
+			}
+		unsigned next_jlo = UINT_MAX, next_jhi = UINT_MAX;
+		const float *MxRow = Mx[A[i]];
+		float I0 = MINUS_INF;
+		uint8_t *TBrow = TB + (size_t) i * stride;
+		float SavedM0;
+		for (unsigned j = jlo; j <= jhi; ++j)
+			{
+			uint8_t b = B[j];
+			uint8_t TraceBits = 0;
+			SavedM0 = M0;
+			/* MATCH */
+			{
+			float xM = M0;
+			if (Drow[j] > xM)
+				{
+				xM = Drow[j];
+				TraceBits = TB_DM;
+				}
+			if (I0 > xM)
+				{
+				xM = I0;
+				TraceBits = TB_IM;
+				}
+			M0 = Mrow[j];
+			float sc = xM + MxRow[b];
+			Mrow[j] = sc;
+			float h = sc - BestScore + X;
+			if (h > 0)
+				{
+				if (j + 1 < next_jlo) next_jlo = j + 1;
+				next_jhi = j + 1;
+				}
+			if (h > AbsOpen)
+				if (j < next_jlo) next_jlo = j;
+			if (h > AbsExt && j == jhi && jhi + 1 < LB)
+				{
+				++jhi;
+				unsigned new_endj = jhi + 1 < LB ? jhi + 1 : LB;
+				if (new_endj < endj) new_endj = endj;
+				for (unsigned j2 = endj + 1; j2 <= new_endj; ++j2)
+					{
+					if (j2 - 1 > j)
+						Mrow[j2 - 1] = MINUS_INF;
+					Drow[j2] = MINUS_INF;
+					}
+				endj = new_endj;
+				}
+			if (sc >= BestScore)
+				{
+				BestScore = sc;
+				Besti = i;
+				Bestj = j;
+				}
+			}
+			/* DELETE */
+			if (j != jlo)
+				{
+				float md = SavedM0 + Open;
+				Drow[j] += Ext;
+				if (md >= Drow[j])
+					{
+					Drow[j] = md;
+					TraceBits |= TB_MD;
+					}
+				float h = Drow[j] - BestScore + X;
+				if (h > 0)
+					{
+					if (j - 1 < next_jlo) next_jlo = j - 1;
+					if (j - 1 > next_jhi) next_jhi = j - 1; /* max() with the UINT_MAX start value */
+					}
+				}
+			/* INSERT */
+			{
+			float mi = SavedM0 + Open;
+			I0 += Ext;
+			if (mi >= I0)
+				{
+				I0 = mi;
+				TraceBits |= TB_MI;
+				}
+			float h = I0 - BestScore + X;
+			if (h > 0)
+				{
+				if (j + 1 < next_jlo) next_jlo = j + 1;
+				next_jhi = j + 1;
+				}
+			if (h > AbsExt && j == jhi && jhi + 1 < LB)
+				{
+				++jhi;
+				unsigned new_endj = jhi + 1 < LB ? jhi + 1 : LB;
+				if (new_endj < endj) new_endj = endj;
+				for (unsigned j2 = endj + 1; j2 <= new_endj; ++j2)
+					{
+					Mrow[j2 - 1] = MINUS_INF;
+					Drow[j2] = MINUS_INF;
+					}
+				endj = new_endj;
+				}
+			}
+			TBrow[j] = TraceBits;
+			}
+		/* special case for the end of Drow */
+		if (jhi < LB)
+			{
+			const unsigned jhi1 = jhi + 1;
+			TBrow[jhi1] = 0;
+			float md = M0 + Open;
+			Drow[jhi1] += Ext;
+			if (md >= Drow[jhi1])
+				{
+				Drow[jhi1] = md;
+				TBrow[jhi1] = TB_MD;
+				}
+			}
+		if (next_jlo == UINT_MAX)
+			break;
+		prev_jlo = jlo;
+		prev_jhi = jhi;
+		jlo = next_jlo;
+		jhi = next_jhi;
+		if (jlo >= LB) jlo = LB - 1;
+		if (jhi >= LB) jhi = LB - 1;
+		if (jlo == prev_jlo)
+			{
+			M0 = MINUS_INF;
+			Drow[jlo] = MINUS_INF;
+			}
+		else
+			M0 = Mrow[jlo - 1];
+		}
+	if (BestScore <= 0.0f)
+		{
+		*Leni = 0; *Lenj = 0;
+		path[0] = 0;
+		return 0.0f;
+		}
+	/* traceback from (Besti,Bestj) in state M (xdropfwdmem.cpp:13-49,271-342) */
+	unsigned i = Besti, j = Bestj, n = 0;
+	char State = 'M';
+	for (;;)
+		{
+		path[n++] = State;
+		if (i == 0 && j == 0)
+			break;
+		char Next;
+		uint8_t c;
+		if (State == 'M')
+			{
+			c = TB[(size_t) i * stride + j];
+			Next = (c & TB_DM) ? 'D' : (c & TB_IM) ? 'I' : 'M';
+			--i; --j;
+			}
+		else if (State == 'D')
+			{
+			c = TB[(size_t) i * stride + j + 1];
+			Next = (c & TB_MD) ? 'M' : 'D';
+			--i;
+			}
+		else
+			{
+			c = TB[(size_t) (i + 1) * stride + j];
+			Next = (c & TB_MI) ? 'M' : 'I';
+			--j;
+			}
+		if (c == XD_UNWRITTEN)
+			{
+			fprintf(stderr, "oracle: X-drop traceback read an unwritten trace cell\n");
+			abort();
+			}
+		State = Next;
+		}
+	for (unsigned k = 0; k < n / 2; ++k)
+		{
+		char t = path[k]; path[k] = path[n - 1 - k]; path[n - 1 - k] = t;
+		}
+	path[n] = 0;
+	*Leni = Besti + 1;
+	*Lenj = Bestj + 1;
+	return BestScore;
+	}
+
+/* XDropBwdFastMem (xdropbwdmem.cpp:23-70) */
+static float xdrop_bwd(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB, float X,
+  unsigned *Leni, unsigned *Lenj, char *path)
+	{
+	xd_alloc(s, LA, LB);
+	uint8_t *RevA = (uint8_t *) xrealloc(0, LA + 1), *RevB = (uint8_t *) xrealloc(0, LB + 1);
+	for (unsigned i = 0; i < LA; ++i) RevA[i] = A[LA - i - 1];
+	for (unsigned i = 0; i < LB; ++i) RevB[i] = B[LB - i - 1];
+	float Score = xdrop_fwd(s, RevA, LA, RevB, LB, X, Leni, Lenj, path);
+	free(RevA); free(RevB);
+	if (Score <= 0.0)
+		return Score;
+	size_t n = strlen(path);
+	for (size_t k = 0; k < n / 2; ++k)
+		{
+		char t = path[k]; path[k] = path[n - 1 - k]; path[n - 1 - k] = t;
+		}
+	return Score;
+	}
+
+#define XD_MAXL 4096 /* xdpmem.h:6 g_MaxL: longer extensions take the Split path, not restated */
+
+/* XDropAlignMemMaxL2 (xdropalignmem.cpp:26-216).  h4 = {Loi, Loj, Leni, Lenj}. */
+static float xdrop_align(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB,
+  unsigned AncLoi, unsigned AncLoj, unsigned AncLen, float X, uint32_t *h4, char *path)
+	{
+	path[0] = 0;
+	if (AncLen <= 1)
+		return 0.0f;
+	unsigned AncHii = AncLoi + AncLen - 1, AncHij = AncLoj + AncLen - 1;
+	const uint8_t *FwdA = A + AncHii, *FwdB = B + AncHij;
+	unsigned FwdLA = LA - AncHii, FwdLB = LB - AncHij;
+	if (AncLoi > XD_MAXL || AncLoj > XD_MAXL || FwdLA > XD_MAXL || FwdLB > XD_MAXL)
+		{
+		fprintf(stderr, "oracle: X-drop extension longer than %u letters (XDropFwdSplit/BwdSplit) is not restated\n", XD_MAXL);
+		abort();
+		}
+	char *bwd = (char *) xrealloc(0, (size_t) AncLoi + AncLoj + 4);
+	char *fwd = (char *) xrealloc(0, (size_t) FwdLA + FwdLB + 4);
+	unsigned BwdLeni, BwdLenj, FwdLeni, FwdLenj;
+	float BwdScore = xdrop_bwd(s, A, AncLoi + 1, B, AncLoj + 1, X, &BwdLeni, &BwdLenj, bwd);
+	float FwdScore = xdrop_fwd(s, FwdA, FwdLA, FwdB, FwdLB, X, &FwdLeni, &FwdLenj, fwd);
+	size_t n = 0;
+	for (const char *p = bwd; *p; ++p) path[n++] = *p;
+	for (unsigned k = 0; k + 2 < AncLen; ++k) path[n++] = 'M';
+	for (const char *p = fwd; *p; ++p) path[n++] = *p;
+	path[n] = 0;
+	free(bwd); free(fwd);
+	float (*Mx)[256] = s->subst;
+	float AncScore = 0.0f;
+	for (unsigned k = 0; k < AncLen; ++k)
+		AncScore += Mx[A[AncLoi + k]][B[AncLoj + k]];
+	float DupeScore = Mx[A[AncLoi]][B[AncLoj]];
+	DupeScore += Mx[A[AncHii]][B[AncHij]];
+	float Score = BwdScore + FwdScore + AncScore - DupeScore;
+	h4[0] = AncLoi + 1 - BwdLeni;
+	h4[1] = AncLoj + 1 - BwdLenj;
+	h4[2] = BwdLeni + FwdLeni + AncLen - 2;
+	h4[3] = BwdLenj + FwdLenj + AncLen - 2;
+	return Score;
+	}
+
+/* GetAnchor (localaligner.cpp:11-64): best run of strictly positive pair scores */
+static float get_anchor(float (*Mx)[256], const uint8_t *Q, const uint8_t *T, unsigned Loi, unsigned Loj, unsigned L,
+  unsigned *AncLoi, unsigned *AncLoj, unsigned *AncLen)
+	{
+	unsigned Startk = UINT_MAX, BestStartk = UINT_MAX, Length = 0;
+	float AnchorScore = 0.0f, BestScore = 0.0f;
+	for (unsigned k = 0; k < L; ++k)
+		{
+		float Score = Mx[Q[Loi + k]][T[Loj + k]];
+		if (Score > 0)
+			{
+			if (Startk == UINT_MAX)
+				{
+				Startk = k;
+				AnchorScore = Score;
+				}
+			else
+				AnchorScore += Score;
+			}
+		else
+			{
+			if (AnchorScore > BestScore)
+				{
+				BestScore = AnchorScore;
+				BestStartk = Startk;
+				Length = k - Startk;
+				}
+			Startk = UINT_MAX;
+			}
+		}
+	if (AnchorScore > BestScore)
+		{
+		BestScore = AnchorScore;
+		BestStartk = Startk;
+		Length = L - Startk;
+		}
+	*AncLoi = Loi + BestStartk;
+	*AncLoj = Loj + BestStartk;
+	*AncLen = Length;
+	return BestScore;
+	}
+
+/* LocalAligner::AlignPos (localaligner.cpp:101-211).  Returns 1 and fills h4/score/path when an
+ * AlignResult would be created. */
+static int la_align_pos(uso_searcher *s, const uint8_t *Q, unsigned QL, const uint8_t *T, unsigned TL,
+  unsigned QueryPos, unsigned TargetPos, uint32_t *h4, float *score, char *path)
+	{
+	float (*Mx)[256] = s->subst;
+	const float XDropU = s->P.xdrop_u;
+	float LeftScore = 0.0f, LeftTotal = 0.0f;
+	unsigned LeftLength = 0, k = 0;
+	int i = (int) QueryPos, j = (int) TargetPos;
+	while (i >= 0 && j >= 0)
+		{
+		++k;
+		LeftTotal += Mx[Q[i]][T[j]];
+		if (LeftTotal > LeftScore)
+			{
+			LeftScore = LeftTotal;
+			LeftLength = k;
+			}
+		else if (LeftScore - LeftTotal > XDropU)
+			break;
+		--i; --j;
+		}
+	float RightScore = 0.0f, RightTotal = 0.0f;
+	unsigned RightLength = 0;
+	i = (int) QueryPos + 1;
+	j = (int) TargetPos + 1;
+	k = 0;
+	while (i < (int) QL && j < (int) TL)
+		{
+		++k;
+		RightTotal += Mx[Q[i]][T[j]];
+		if (RightTotal > RightScore)
+			{
+			RightScore = RightTotal;
+			RightLength = k;
+			}
+		else if (RightScore - RightTotal > XDropU)
+			break;
+		++i; ++j;
+		}
+	const float Score = LeftScore + RightScore;
+	if (Score < s->la_min_ungapped)
+		return 0;
+	unsigned Loi = (QueryPos + 1) - LeftLength, Loj = (TargetPos + 1) - LeftLength;
+	unsigned SegLength = LeftLength + RightLength;
+	unsigned AncLoi, AncLoj, AncLen;
+	float AncRaw = get_anchor(Mx, Q, T, Loi, Loj, SegLength, &AncLoi, &AncLoj, &AncLen);
+	if (AncRaw <= 0.0f)
+		return 0;
+	float Gapped = xdrop_align(s, Q, QL, T, TL, AncLoi, AncLoj, AncLen, s->P.xdrop_g, h4, path);
+	if (Gapped <= 0.0f)
+		return 0;
+	double Evalue = es_raw_to_evalue(s, Gapped, QL);
+	if (Evalue > s->P.evalue)
+		return 0;
+	*score = Gapped;
+	return 1;
+	}
+
+/* HSPData::OverlapFract (hsp.h:74-89) and LocalAligner2::LargeOverlap (localaligner2.cpp:252-258) */
+static int la_large_overlap(const uint32_t *a, const uint32_t *b)
+	{
+	if (a[2] == 0 || a[3] == 0)
+		return 0;
+	unsigned aHii = a[0] + a[2] - 1, aHij = a[1] + a[3] - 1, bHii = b[0] + b[2] - 1, bHij = b[1] + b[3] - 1;
+	unsigned MaxLoi = a[0] > b[0] ? a[0] : b[0], MaxLoj = a[1] > b[1] ? a[1] : b[1];
+	unsigned MinHii = aHii < bHii ? aHii : bHii, MinHij = aHij < bHij ? aHij : bHij;
+	unsigned Ovi = MinHii < MaxLoi ? 0 : MinHii - MaxLoi;
+	unsigned Ovj = MinHij < MaxLoj ? 0 : MinHij - MaxLoj;
+	double f = (double) (Ovi * Ovj) / (double) (a[2] * a[3]);
+	return f > 0.5;
+	}
+
+typedef struct la_ar { uint32_t h4[4]; float score; char *path; } la_ar;
+
+/* LocalAligner2::AlignMulti (localmulti.cpp:9-118).  Returns the number of ARs in *out (malloc'd). */
+static unsigned la_align_multi(uso_searcher *s, const uint8_t *Q, unsigned QL, const uint8_t *T, unsigned TL, la_ar **out)
+	{
+	*out = 0;
+	if (TL < 2 * s->la_w)
+		return 0;
+	if (s->la_tcap < TL + 1)
+		{
+		s->la_tcap = TL + 1;
+		s->la_twords = (uint32_t *) xrealloc(s->la_twords, s->la_tcap * sizeof(uint32_t));
+		}
+	const unsigned TargetWordCount = la_words(s, T, TL, s->la_twords);
+	la_ar *ars = 0;
+	unsigned nar = 0, cap = 0;
+	char *path = (char *) xrealloc(0, (size_t) QL + TL + 8);
+	for (unsigned TargetPos = 0; TargetPos < TargetWordCount; )
+		{
+		uint32_t TargetWord = s->la_twords[TargetPos];
+		unsigned N = s->la_qcounts[TargetWord];
+		int skipped = 0;
+		for (unsigned i = 0; i < N; ++i)
+			{
+			unsigned QueryPos = s->la_qposvec[s->la_base[TargetWord] + i];
+			la_ar ar;
+			if (!la_align_pos(s, Q, QL, T, TL, QueryPos, TargetPos, ar.h4, &ar.score, path))
+				continue;
+			int keep = 1;
+			for (unsigned k = 0; k < nar; ++k)
+				if (la_large_overlap(ar.h4, ars[k].h4))
+					{
+					keep = 0;
+					break;
+					}
+			if (!keep)
+				continue;
+			if (nar == cap)
+				{
+				cap = cap ? 2 * cap : 4;
+				ars = (la_ar *) xrealloc(ars, cap * sizeof(la_ar));
+				}
+			ar.path = strdup(path);
+			ars[nar++] = ar;
+			unsigned NewTargetPos = ar.h4[1] + ar.h4[3]; /* Hij + 1 */
+			if (NewTargetPos > TargetPos)
+				TargetPos = NewTargetPos;
+			else
+				++TargetPos;
+			skipped = 1;
+			break;
+			}
+		if (!skipped)
+			++TargetPos;
+		}
+	free(path);
+	*out = ars;
+	return nar;
+	}
+
+float uso_xdrop_fwd(const uso_params *p, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, float X,
+  uint32_t *leni, uint32_t *lenj, char *path)
+	{
+	uso_db *db = uso_db_create(p);
+	uso_searcher *s = uso_searcher_create(db, p);
+	unsigned li, lj;
+	float sc = xdrop_fwd(s, A, LA, B, LB, X, &li, &lj, path);
+	*leni = li; *lenj = lj;
+	uso_searcher_free(s);
+	uso_db_free(db);
+	return sc;
+	}
+
+int uso_local_align_pos(uso_searcher *s, const uint8_t *q, uint32_t LQ, const uint8_t *t, uint32_t LT,
+  uint32_t qpos, uint32_t tpos, uint32_t *hsp4, float *score, char *path)
+	{
+	use_alpha(&s->P);
+	la_refresh_estats(s);
+	s->la_min_ungapped = (float) es_min_ungapped_raw(s, LQ);
+	return la_align_pos(s, q, LQ, t, LT, qpos, tpos, hsp4, score, path);
+	}
+
+/* ------------------------------------------------------------------ hit statistics */
 static void fill_hit(uso_hit *h, const uint8_t *Q, const uint8_t *T, const char *path)
 	{
 	unsigned first = UINT_MAX, last = UINT_MAX, col = 0;
@@ -1322,7 +2123,7 @@ static void fill_hit(uso_hit *h, const uint8_t *Q, const uint8_t *T, const char 
 		char ch = path[c];
 		if (ch == 'M')
 			{
-			if (g_match[Q[qpos]][T[tpos]]) ++h->ids; else ++h->mism;
+			if (g_cur_match[Q[qpos]][T[tpos]]) ++h->ids; else ++h->mism;
 			++qpos; ++tpos;
 			}
 		else if (ch == 'D')
@@ -1373,6 +2174,65 @@ static int try_target(uso_searcher *s, uint32_t qindex, const uint8_t *q, uint32
 	uso_db *db = s->db;
 	const uint8_t *T = db->seqs[t];
 	unsigned TL = db->lens[t];
+	if (s->P.local)
+		{
+		/* Searcher::Align, AlignMulti branch (searcher.cpp:31-49): every AR of this target goes
+		 * through the Accepter; the target counts once for the Terminator */
+		la_ar *ars;
+		unsigned nar = la_align_multi(s, q, L, T, TL, &ars);
+		int any = 0;
+		for (unsigned k = 0; k < nar; ++k)
+			{
+			uso_hit h;
+			memset(&h, 0, sizeof h);
+			h.query = qindex; h.target = t; h.strand = (uint8_t) strand; h.ql = L; h.tl = TL;
+			h.loi = ars[k].h4[0]; h.loj = ars[k].h4[1]; h.leni = ars[k].h4[2]; h.lenj = ars[k].h4[3];
+			fill_hit(&h, q + h.loi, T + h.loj, ars[k].path);
+			h.first_mq += h.loi; h.last_mq += h.loi; h.first_mt += h.loj; h.last_mt += h.loj;
+			/* arscorer.cpp:87-103 raw score = the path re-scored (alnparams.cpp:447-505) */
+			float raw = 0.0f;
+			{
+			const uint8_t *a = q + h.loi, *b = T + h.loj;
+			char last = 'M';
+			for (const char *pp = ars[k].path; *pp; ++pp)
+				{
+				if (*pp == 'M')
+					raw += s->subst[toupper(*a++)][toupper(*b++)];
+				else if (*pp == 'D')
+					{
+					raw += last == 'M' ? s->P.lopen : s->P.lext;
+					++a;
+					}
+				else
+					{
+					raw += last == 'M' ? s->P.lopen : s->P.lext;
+					++b;
+					}
+				last = *pp;
+				}
+			}
+			if (raw != ars[k].score)
+				{
+				fprintf(stderr, "oracle: re-scored path %.1f != X-drop score %.1f\n", raw, ars[k].score);
+				abort();
+				}
+			h.raw = (double) raw;
+			h.evalue = es_raw_to_evalue(s, h.raw, L);
+			h.bits = es_raw_to_bits(s, h.raw);
+			double FractId = h.alnlen == 0 ? 0.0 : (double) h.ids / (double) h.alnlen;
+			int accept = !(FractId < (double) s->P.id) && !(h.evalue > (double) s->P.evalue);
+			if (accept)
+				{
+				any = 1;
+				h.path = ars[k].path;
+				hits_push(hits, nhits, caphits, &h);
+				}
+			else
+				free(ars[k].path);
+			}
+		free(ars);
+		return terminate(s, any);
+		}
 	int aligned = global_align(s, q, L, T, TL, path);
 	if (!aligned)
 		return terminate(s, 0);
@@ -1433,7 +2293,11 @@ static void search_strand(uso_searcher *s, uint32_t qindex, const uint8_t *q, ui
 			memset(s->U, 0, s->Ucap * sizeof(uint32_t));
 		s->ntop_prev = 0;
 		}
-	hsp_set_a(s, q, L); /* Aligner::SetQuery -> HSPFinder::SetA */
+	use_alpha(&s->P);
+	if (s->P.local)
+		la_set_query(s, q, L); /* Aligner::SetQuery -> LocalAligner2::SetQueryImpl */
+	else
+		hsp_set_a(s, q, L); /* Aligner::SetQuery -> HSPFinder::SetA */
 	s->acc = s->rej = 0; /* Terminator::OnNewQuery */
 	char *path = (char *) xrealloc(0, (size_t) L + 60000 + 2);
 	size_t pathcap = (size_t) L + 60000 + 2;
@@ -1503,6 +2367,8 @@ static void search_strand(uso_searcher *s, uint32_t qindex, const uint8_t *q, ui
 			U[s->TopT[i]] = 0;
 		s->ntop_prev = 0;
 		}
+	if (s->P.local)
+		la_query_done(s);
 	free(path);
 	}
 
@@ -1563,7 +2429,10 @@ unsigned uso_search(uso_searcher *s, uint32_t qindex, const uint8_t *q, uint32_t
 		for (unsigned i = 0; i < n; ++i)
 			{
 			const uso_hit *h = &(*hits)[n0 + i];
-			sc[i] = (float) (h->alnlen == 0 ? 0.0 : (double) h->ids / (double) h->alnlen);
+			if (s->P.local)
+				sc[i] = (float) h->raw; /* arscorer.cpp:818-824 */
+			else
+				sc[i] = (float) (h->alnlen == 0 ? 0.0 : (double) h->ids / (double) h->alnlen);
 			tmp[i] = *h;
 			}
 		quicksort_order_desc(sc, n, ord);
@@ -1621,4 +2490,31 @@ void uso_write_uc_hit(FILE *f, const uso_hit *h, const char *qlabel, const char 
 void uso_write_uc_nohit(FILE *f, uint32_t ql, const char *qlabel)
 	{
 	fprintf(f, "N\t*\t%u\t*\t.\t*\t*\t*\t%s\t*\n", ql, qlabel);
+	}
+
+/* local hits: qlo..thi are the 1-based segment ends (arscorer.cpp:683-745 without ORF/rev-comp) */
+/* -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand */
+void uso_write_userout_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
+	{
+	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
+	uso_compress_path(h->path, cp);
+	fprintf(f, "%s\t%s\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t%.3g\t%.0f\t%.0f\t%s\t%c\n", qlabel, tlabel, pct_id(h),
+	  h->alnlen, h->mism, h->opens, h->loi + 1, h->loi + h->leni, h->loj + 1, h->loj + h->lenj, h->evalue, h->bits,
+	  h->raw, cp, nucleo ? (h->strand ? '-' : '+') : '.');
+	free(cp);
+	}
+
+void uso_write_blast6_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
+	{
+	fprintf(f, "%s\t%s\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t%.2g\t%.1f\n", qlabel, tlabel, pct_id(h), h->alnlen,
+	  h->mism, h->opens, h->loi + 1, h->loi + h->leni, h->loj + 1, h->loj + h->lenj, h->evalue, h->bits);
+	}
+
+void uso_write_uc_hit_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
+	{
+	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
+	uso_compress_path(h->path, cp);
+	fprintf(f, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t%s\t%s\t%s\n", h->target, h->ql, pct_id(h), nucleo ? (h->strand ? '-' : '+') : '.', h->loi, h->loj, cp,
+	  qlabel, tlabel);
+	free(cp);
 	}

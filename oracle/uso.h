@@ -42,9 +42,17 @@ typedef struct uso_params {
 	int dbmask_fast;     /* 1 = fastnucleo soft masking of the DB (makeudb.cpp:11-25) */
 	int cluster_mode;    /* 1 = cluster_fast semantics (no DB masking, growing DB) */
 	int fulldp;          /* -fulldp: no HSPs, full Viterbi on every candidate (globalalignmem.cpp:153-157) */
+	int local;           /* 1 = -usearch_local: LocalAligner2 (localmulti.cpp), X-drop gapped extension */
+	float evalue;        /* -evalue (mandatory for usearch_local) */
+	float xdrop_u;       /* -xdrop_u 16 */
+	float xdrop_g;       /* -xdrop_g 32 */
+	float lopen;         /* local gap open, -10 (alnparams.cpp:362-369) */
+	float lext;          /* local gap extend, -1 */
+	float ka_dbsize;     /* -ka_dbsize, default 1e9 (o_defaults.inc:2); 0 = total DB letters */
 } uso_params;
 
 void uso_default_params(uso_params *p, int cluster_fast);
+void uso_set_amino(uso_params *p); /* word_length 5 over 20 letters, hspw 3 */
 
 /* One accepted hit (global alignment). */
 typedef struct uso_hit {
@@ -55,6 +63,10 @@ typedef struct uso_hit {
 	uint32_t first_mq, first_mt, last_mq, last_mt; /* 0-based first/last M positions */
 	uint32_t first_mcol, alnlen; /* cols between first and last M inclusive */
 	uint32_t ql, tl;
+	/* local alignments only (alignresult.cpp:173): segment start/length in query and target,
+	 * raw score (arscorer.cpp:87-103), E-value and bit score (estats.cpp:73-96) */
+	uint32_t loi, loj, leni, lenj;
+	double raw, evalue, bits;
 	char *path;          /* full path over {M,D,I}, NUL-terminated, owned by the hit */
 } uso_hit;
 
@@ -103,6 +115,17 @@ void uso_fastmask(const uint8_t *seq, uint32_t L, uint8_t *out);
 void uso_revcomp(const uint8_t *seq, uint32_t L, uint8_t *out);
 /* comppath.cpp:7-48 */
 void uso_compress_path(const char *path, char *out);
+
+/* a18-a20: local alignment of (q,t) around the seed (qpos,tpos) (localaligner.cpp:101-211);
+ * returns 0 if rejected, else fills loi/loj/leni/lenj/score and path. */
+int uso_local_align_pos(uso_searcher *s, const uint8_t *q, uint32_t LQ, const uint8_t *t, uint32_t LT,
+  uint32_t qpos, uint32_t tpos, uint32_t *hsp4, float *score, char *path);
+/* X-drop forward extension alone (xdropfwdmem.cpp:344-749): the cmd_test known answer. */
+float uso_xdrop_fwd(const uso_params *p, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, float X,
+  uint32_t *leni, uint32_t *lenj, char *path);
+void uso_write_userout_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo);
+void uso_write_blast6_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel); /* blast6out.cpp:27-80 */
+void uso_write_uc_hit_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo);
 
 /* ---- output formats (byte-identical to the reference's sinks) ---- */
 /* userout with -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand (userout.cpp:150-215) */

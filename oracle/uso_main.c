@@ -220,10 +220,63 @@ static int cluster_fast_main(int argc, char **argv)
 	return 0;
 	}
 
+/* uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt USEROUT UC B6 [maxaccepts maxrejects]
+ * = -usearch_local Q -db DB -id ID -evalue E [-strand plus] -userout .. -uc .. -blast6out ..
+ *   -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand */
+static int usearch_local_main(int argc, char **argv)
+	{
+	if (argc < 10)
+		{
+		fprintf(stderr, "usage: uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt USEROUT UC B6 [maxaccepts maxrejects]\n");
+		return 2;
+		}
+	uso_params P;
+	uso_default_params(&P, 0);
+	P.local = 1;
+	P.id = (float) atof(argv[4]);
+	P.evalue = (float) atof(argv[5]);
+	int nucleo = strcmp(argv[6], "nt") == 0;
+	if (!nucleo)
+		uso_set_amino(&P);
+	if (argc > 11)
+		{
+		P.maxaccepts = (unsigned) atoi(argv[10]);
+		P.maxrejects = (unsigned) atoi(argv[11]);
+		}
+	fasta Q, D;
+	read_fasta(argv[2], &Q);
+	read_fasta(argv[3], &D);
+	uso_db *db = uso_db_create(&P);
+	for (unsigned i = 0; i < D.n; ++i)
+		uso_db_add(db, D.seqs[i], D.lens[i], D.labels[i]);
+	uso_searcher *s = uso_searcher_create(db, &P);
+	FILE *fu = fopen(argv[7], "w"), *fc = fopen(argv[8], "w"), *fb = fopen(argv[9], "w");
+	uso_hit *hits = 0; unsigned nh = 0, cap = 0;
+	for (unsigned i = 0; i < Q.n; ++i)
+		{
+		nh = 0;
+		unsigned n = uso_search(s, i, Q.seqs[i], Q.lens[i], &hits, &nh, &cap);
+		for (unsigned k = 0; k < n; ++k)
+			{
+			const char *tl = uso_db_label(db, hits[k].target);
+			uso_write_userout_local(fu, &hits[k], Q.labels[i], tl, nucleo);
+			uso_write_uc_hit_local(fc, &hits[k], Q.labels[i], tl, nucleo);
+			uso_write_blast6_local(fb, &hits[k], Q.labels[i], tl);
+			free(hits[k].path);
+			}
+		if (n == 0)
+			uso_write_uc_nohit(fc, Q.lens[i], Q.labels[i]);
+		}
+	fclose(fu); fclose(fc); fclose(fb);
+	return 0;
+	}
+
 int main(int argc, char **argv)
 	{
 	if (argc >= 2 && strcmp(argv[1], "cluster_fast") == 0)
 		return cluster_fast_main(argc, argv);
+	if (argc >= 2 && strcmp(argv[1], "usearch_local") == 0)
+		return usearch_local_main(argc, argv);
 	if (argc < 9 || strcmp(argv[1], "usearch_global") != 0)
 		{
 		fprintf(stderr, "usage: uso_cli usearch_global Q.fa DB.fa ID plus|both USEROUT UC B6 [maxaccepts maxrejects]\n");

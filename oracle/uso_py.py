@@ -19,7 +19,9 @@ class Params(C.Structure):
         ("strand_both", C.c_int), ("word_length", C.c_uint), ("big", C.c_uint), ("bump", C.c_uint),
         ("stepwords", C.c_uint), ("band", C.c_uint), ("minhsp", C.c_uint), ("hspw", C.c_uint),
         ("xdrop_nw", C.c_float), ("match", C.c_float), ("mismatch", C.c_float), ("dbmask_fast", C.c_int),
-        ("cluster_mode", C.c_int), ("fulldp", C.c_int),
+        ("cluster_mode", C.c_int), ("fulldp", C.c_int), ("local", C.c_int), ("evalue", C.c_float),
+        ("xdrop_u", C.c_float), ("xdrop_g", C.c_float), ("lopen", C.c_float), ("lext", C.c_float),
+        ("ka_dbsize", C.c_float),
     ]
 
 
@@ -29,6 +31,8 @@ class Hit(C.Structure):
         ("ids", C.c_uint32), ("mism", C.c_uint32), ("intgaps", C.c_uint32), ("opens", C.c_uint32),
         ("first_mq", C.c_uint32), ("first_mt", C.c_uint32), ("last_mq", C.c_uint32), ("last_mt", C.c_uint32),
         ("first_mcol", C.c_uint32), ("alnlen", C.c_uint32), ("ql", C.c_uint32), ("tl", C.c_uint32),
+        ("loi", C.c_uint32), ("loj", C.c_uint32), ("leni", C.c_uint32), ("lenj", C.c_uint32),
+        ("raw", C.c_double), ("evalue", C.c_double), ("bits", C.c_double),
         ("path", C.c_char_p),
     ]
 
@@ -49,6 +53,13 @@ def lib():
         L = C.CDLL(LIB)
         vp = C.c_void_p
         L.uso_default_params.argtypes = [C.POINTER(Params), C.c_int]
+        L.uso_set_amino.argtypes = [C.POINTER(Params)]
+        L.uso_xdrop_fwd.argtypes = [C.POINTER(Params), C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_float,
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_char_p]
+        L.uso_xdrop_fwd.restype = C.c_float
+        L.uso_local_align_pos.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          vp, C.POINTER(C.c_float), C.c_char_p]
+        L.uso_local_align_pos.restype = C.c_int
         L.uso_db_create.argtypes = [C.POINTER(Params)]
         L.uso_db_create.restype = vp
         L.uso_db_add.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p]
@@ -84,9 +95,11 @@ def lib():
     return _lib
 
 
-def default_params(cluster_fast=False, **kw):
+def default_params(cluster_fast=False, amino=False, **kw):
     p = Params()
     lib().uso_default_params(C.byref(p), int(cluster_fast))
+    if amino:
+        lib().uso_set_amino(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -122,6 +135,15 @@ def viterbi_band(params, a, b, left_a, left_b, right_a, right_b):
     sc = lib().uso_viterbi_band(C.byref(params), a, len(a), b, len(b), int(left_a), int(left_b), int(right_a),
                                 int(right_b), out)
     return out.value.decode(), sc
+
+
+def xdrop_fwd(params, a, b, x):
+    """XDropFwdFastMem alone -> (score, leni, lenj, path)."""
+    a, b = _b(a), _b(b)
+    out = C.create_string_buffer(len(a) + len(b) + 2)
+    li, lj = C.c_uint32(), C.c_uint32()
+    sc = lib().uso_xdrop_fwd(C.byref(params), a, len(a), b, len(b), float(x), C.byref(li), C.byref(lj), out)
+    return sc, li.value, lj.value, out.value.decode()
 
 
 class DB:
@@ -191,6 +213,15 @@ class Searcher:
         nc = lib().uso_global_hsps(self.h, q, len(q), t, len(t), ung.ctypes.data, C.byref(nu), ch.ctypes.data, max_hsp,
                                    C.byref(fid))
         return ung[:4 * min(nu.value, max_hsp)].reshape(-1, 4), ch[:4 * min(nc, max_hsp)].reshape(-1, 4), fid.value
+
+    def local_align_pos(self, q, t, qpos, tpos):
+        """LocalAligner::AlignPos -> None or (loi, loj, leni, lenj, score, path)."""
+        q, t = _b(q), _b(t)
+        out = C.create_string_buffer(len(q) + len(t) + 8)
+        h4 = np.zeros(4, np.uint32)
+        sc = C.c_float()
+        ok = lib().uso_local_align_pos(self.h, q, len(q), t, len(t), qpos, tpos, h4.ctypes.data, C.byref(sc), out)
+        return (int(h4[0]), int(h4[1]), int(h4[2]), int(h4[3]), sc.value, out.value.decode()) if ok else None
 
     def global_align(self, q, t):
         q, t = _b(q), _b(t)
