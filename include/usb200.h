@@ -31,7 +31,7 @@ extern "C" {
  * accept test compares double(ids)/double(cols) with (double)(float)id (accepter.cpp:36-38). */
 typedef struct usb_params {
 	uint32_t struct_size;   /* = sizeof(usb_params), ABI check */
-	int32_t is_nucleo;      /* 1 = nucleotide DB (amino: usearch_local row, not built yet) */
+	int32_t is_nucleo;      /* 1 = nucleotide DB; 0 = amino acid DB (only with local = 1) */
 	float id;               /* -id */
 	uint32_t maxaccepts;    /* -maxaccepts (terminator.cpp:23-31), default 1 */
 	uint32_t maxrejects;    /* -maxrejects, default 32 (8 for cluster_fast) */
@@ -54,10 +54,23 @@ typedef struct usb_params {
 	int32_t cluster_mode;   /* 1 = cluster_fast semantics: raw un-masked centroids, growing DB */
 	int32_t fulldp;         /* -fulldp: no HSPs, full Viterbi per candidate (globalalignmem.cpp:153-157);
 	                           band = 0 (-band 0) alone selects the full DP for holes only (:103-106) */
+	/* -usearch_local (searchcmd.cpp:42, makedbsearcher.cpp:90-123) */
+	int32_t local;          /* 1 = LocalAligner2 + X-drop gapped extension instead of GlobalAligner */
+	float evalue;           /* -evalue (mandatory for usearch_local) */
+	float xdrop_u;          /* -xdrop_u, 16: ungapped X-drop (alnheuristics.cpp:29) */
+	float xdrop_g;          /* -xdrop_g, 32: gapped X-drop (alnheuristics.cpp:30) */
+	float lopen;            /* local gap open, -10 (alnparams.cpp:362-369; -lopen/-lext defaults count as set) */
+	float lext;             /* local gap extend, -1 */
+	float ka_dbsize;        /* -ka_dbsize, 1e9 (o_defaults.inc:2; the default counts as set, so the
+	                           letter count of the DB is never used, makedbsearcher.cpp:92-96) */
 } usb_params;
 
 /* Defaults of -usearch_global (cluster_fast=0) or -cluster_fast (=1). */
 void usb_default_params(usb_params *p, int cluster_fast);
+/* Switches a parameter block to -usearch_local on a nucleotide (nucleo=1: UDB words of 8, seed
+ * words of 5) or amino acid DB (nucleo=0: UDB words of 5 over 20 letters, udbparams.cpp:236-261;
+ * seed words of 3, makedbsearcher.cpp:104-123; BLOSUM62). */
+void usb_set_local(usb_params *p, int nucleo, float evalue);
 
 /* One accepted hit == the statistics the reference derives lazily from an AlignResult
  * (alignresult.h:17-245, arscorer.cpp:201-296 FillLo).  Coordinates are 0-based. */
@@ -71,6 +84,10 @@ typedef struct usb_hit {
 	uint32_t first_mcol, alnlen;                   /* alnlen = cols between first and last M */
 	uint32_t ql, tl;
 	uint32_t run_off, run_cnt; /* path as runs in the run arena: (length << 2) | op, op 0=M 1=D 2=I */
+	/* local hits (AlignResult::CreateLocalGapped, alignresult.cpp:173): the segment is
+	 * [first_mq, last_mq] x [first_mt, last_mt] (m_HSP), alnlen = all columns */
+	int32_t raw;           /* raw score (arscorer.cpp:87-103); 0 for global hits */
+	uint32_t sub;          /* index of this AR among the ARs of its target (localmulti.cpp:93-97) */
 } usb_hit;
 
 /* Per (query,strand) search counters (diagnostics; the reference has no equivalent object). */
@@ -146,6 +163,16 @@ int usb_batch_export_hits_device(usb_searcher *s, void *dev_dst, uint64_t cap_hi
  * committed queries.  Call again with the remaining queries.  Needs -maxaccepts 1, -strand plus. */
 int usb_cluster_round(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
   uint32_t *n_committed, uint32_t *cluster_idx, usb_result **out);
+
+/* Karlin-Altschul statistics of a local hit (estats.cpp:73-96, gapped): E-value and bit score of
+ * raw score `raw` for a query of ql letters, with the searcher's -ka_dbsize. */
+int usb_local_evalue(const usb_searcher *s, int32_t raw, uint32_t ql, double *evalue, double *bits);
+
+/* a18/a19: LocalAligner2::AlignMulti for explicit (query, target) pairs (localmulti.cpp:9-118).
+ * Every AR of pair i becomes a hit with rank = i and sub = its index among the pair's ARs
+ * (no -id filter; the E-value gate of AlignPos applies). */
+int usb_local_pairs(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_pairs, usb_result **out);
 
 /* Result accessors.  Hits are grouped by query (ascending) and, within a query, in the
  * reference's output order (HitMgr::Sort, hitmgr.cpp:477; sort.h:63-102). */

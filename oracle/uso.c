@@ -1458,28 +1458,32 @@ static void estats_init(uso_searcher *s)
 	s->es_letters = letters;
 	}
 
+/* The three EStats expressions below are written the way the reference BINARY evaluates them:
+ * its own build flags are -O3 -ffast-math (src/Makefile:11-14), under which gcc simplifies the
+ * source algebraically (x/Log2 -> x*(1/Log2), NM/pow(2,B) -> NM*exp2(-B), BitScore*Log2 cancels,
+ * one fused multiply-add).  Checked against the disassembly of oracle/_ref/usearch12; the forms
+ * matter for the last printed digit and for E-values below 1e-300 (source form: 0, binary:
+ * denormal arithmetic). */
+#define INV_LOG2 (1.0 / log(2.0))
+
 /* estats.cpp:65-71 */
 static double es_min_ungapped_raw(const uso_searcher *s, unsigned QL)
 	{
-	double Log2 = log(2.0);
-	double BitScore = (log(s->es_dbsize * QL) - log(s->es_maxevalue)) / Log2;
-	return (BitScore * Log2 + s->es_loguk) / s->es_ul;
+	return ((log((double) QL * s->es_dbsize) + s->es_loguk) - log(s->es_maxevalue)) / s->es_ul;
 	}
 
 /* estats.cpp:79-85 (gapped) */
 static double es_raw_to_bits(const uso_searcher *s, double raw)
 	{
-	double Log2 = log(2.0);
-	return (raw * s->es_gl - s->es_loggk) / Log2;
+	return fma(raw, s->es_gl, -s->es_loggk) * INV_LOG2;
 	}
 
 /* estats.cpp:73-96 */
 static double es_raw_to_evalue(const uso_searcher *s, double raw, unsigned QL)
 	{
-	double BitScore = es_raw_to_bits(s, raw);
-	double NM = (double) QL * s->es_dbsize;
-	double p = pow(2.0, BitScore);
-	return NM / p;
+	double x = (s->es_loggk - raw * s->es_gl) * INV_LOG2;
+	double e = exp2(x);
+	return (double) QL * (e * s->es_dbsize);
 	}
 
 static void la_refresh_estats(uso_searcher *s)

@@ -28,6 +28,26 @@ def test_oracle_matches_reference_golden(golden, variant):
         assert util.first_diff(got, ref) is None, kind
 
 
+@pytest.mark.parametrize("variant", list(util.LOCAL_VARIANTS))
+def test_oracle_local_matches_reference_golden(variant):
+    """usearch_local restatement vs the reference binary's outputs (tools/make_golden_local.py)."""
+    kw = dict(util.LOCAL_VARIANTS[variant])
+    nucleo = kw.pop("nucleo")
+    g = util.GoldenLocal("nt" if nucleo else "aa")
+    p = util.oracle_local_params(nucleo, **kw)
+    s = O.Searcher(O.DB(g.db, p, g.db_labels), p)
+    got = util.oracle_lines_local(s, g.q_labels, g.q, g.db_labels, nucleo)
+    for lines, kind in zip(got, ("user", "uc", "b6")):
+        assert util.first_diff(lines, g.lines(variant, kind)) is None, kind
+
+
+def test_known_answer_xdrop_fwd():
+    """The reference's own known answer (xdropalignmem.cpp:336-364 cmd_test): XDropFwdFastMem of
+    SEQVENCE / SEQVECE with BLOSUM62 scores 27.0, Leni 8, Lenj 7, alignment SEQVENCE / SEQVE-CE."""
+    p = O.default_params(amino=True, local=1)
+    assert O.xdrop_fwd(p, "SEQVENCE", "SEQVECE", 32.0) == (27.0, 8, 7, "MMMMMDMM")
+
+
 def test_known_answer_compress_path():
     assert O.compress_path("I" * 610 + "M" * 250 + "I" * 638) == "610I250M638I"
     assert O.compress_path("I" * 847 + "M" * 12 + "D" + "M" * 238 + "I" * 408) == "847I12MD238M408I"
@@ -41,7 +61,7 @@ def test_capi_library_exports_every_symbol():
     # header and binding agree on the struct sizes
     p = capi.default_params()
     assert p.struct_size == C.sizeof(capi.Params)
-    assert capi.HIT_DTYPE.itemsize == 72 and capi.QSTAT_DTYPE.itemsize == 28
+    assert capi.HIT_DTYPE.itemsize == 80 and capi.QSTAT_DTYPE.itemsize == 28
 
 
 def test_header_declares_bound_symbols():

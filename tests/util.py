@@ -129,3 +129,91 @@ def mutate(s, rate, rng, alphabet="ACGT"):
         else:
             out.append(c)
     return "".join(out)
+
+
+# ---------------------------------------------------------------- usearch_local
+LOCAL_VARIANTS = {
+    "loc_aa_e5": dict(nucleo=False, id=0.5, evalue=1e-5),
+    "loc_aa_ma4": dict(nucleo=False, id=0.3, evalue=10.0, maxaccepts=4, maxrejects=64),
+    "loc_nt_plus": dict(nucleo=True, id=0.9, evalue=1e-5, maxaccepts=2, maxrejects=16),
+}
+
+
+class GoldenLocal:
+    def __init__(self, kind):
+        self.db_labels, self.db = read_fasta(os.path.join(GOLDEN, "loc_%s_db.fa.gz" % kind))
+        self.q_labels, self.q = read_fasta(os.path.join(GOLDEN, "loc_%s_q.fa.gz" % kind))
+
+    def lines(self, variant, kind):
+        with gzip.open(os.path.join(GOLDEN, "%s.%s.gz" % (variant, kind)), "rt") as f:
+            return f.read().splitlines()
+
+
+def _strand_char(h, nucleo):
+    return ("-" if h["strand"] else "+") if nucleo else "."
+
+
+def fmt_local(h, cigar, evalue, bits, ql, tl, nucleo):
+    """(user, uc, b6) lines of one local hit; -userfields
+    query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand (userout.cpp:150-215),
+    blast6out.cpp:27-80, outputuc.cpp:45-69.  h holds loi/hii/loj/hij (0-based segment ends) and raw."""
+    p = pct(h["ids"], h["alnlen"])
+    st = _strand_char(h, nucleo)
+    user = "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.3g\t%.0f\t%.0f\t%s\t%s" % (
+        ql, tl, p, h["alnlen"], h["mism"], h["opens"], h["loi"] + 1, h["hii"] + 1, h["loj"] + 1, h["hij"] + 1, evalue, bits,
+        h["raw"], cigar, st)
+    uc = "H\t%d\t%d\t%.1f\t%s\t%d\t%d\t%s\t%s\t%s" % (h["target"], h["ql"], p, st, h["loi"], h["loj"], cigar, ql, tl)
+    b6 = "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.2g\t%.1f" % (
+        ql, tl, p, h["alnlen"], h["mism"], h["opens"], h["loi"] + 1, h["hii"] + 1, h["loj"] + 1, h["hij"] + 1, evalue, bits)
+    return user, uc, b6
+
+
+def product_lines_local(res, searcher, q_labels, q_seqs, db_labels, nucleo):
+    user, uc, b6 = [], [], []
+    for qi in range(len(q_seqs)):
+        b, e = int(res.qoff[qi]), int(res.qoff[qi + 1])
+        for k in range(b, e):
+            h = res.hits[k]
+            d = dict(ids=int(h["ids"]), alnlen=int(h["alnlen"]), mism=int(h["mism"]), opens=int(h["opens"]),
+                     loi=int(h["first_mq"]), hii=int(h["last_mq"]), loj=int(h["first_mt"]), hij=int(h["last_mt"]),
+                     raw=int(h["raw"]), target=int(h["target"]), ql=int(h["ql"]), strand=int(h["strand"]))
+            ev, bits = searcher.local_evalue(d["raw"], d["ql"])
+            u, c, x = fmt_local(d, res.cigar(h), ev, bits, q_labels[qi], db_labels[d["target"]], nucleo)
+            user.append(u)
+            uc.append(c)
+            b6.append(x)
+        if b == e:
+            uc.append(fmt_uc_nohit(len(q_seqs[qi]), q_labels[qi]))
+    return user, uc, b6
+
+
+def oracle_lines_local(searcher, q_labels, q_seqs, db_labels, nucleo):
+    from oracle import uso_py as O
+    user, uc, b6 = [], [], []
+    for qi, s in enumerate(q_seqs):
+        hits = searcher.search(s, qi)
+        for h in hits:
+            d = dict(h)
+            d["hii"] = h["loi"] + h["leni"] - 1
+            d["hij"] = h["loj"] + h["lenj"] - 1
+            u, c, x = fmt_local(d, O.compress_path(h["path"]), h["evalue"], h["bits"], q_labels[qi], db_labels[h["target"]],
+                                nucleo)
+            user.append(u)
+            uc.append(c)
+            b6.append(x)
+        if not hits:
+            uc.append(fmt_uc_nohit(len(s), q_labels[qi]))
+    return user, uc, b6
+
+
+def oracle_local_params(nucleo, **kw):
+    from oracle import uso_py as O
+    return O.default_params(amino=not nucleo, local=1, **kw)
+
+
+def product_local_params(nucleo, evalue, **kw):
+    import ctypes as C
+    from usearch12_b200 import capi
+    p = capi.default_params(**kw)
+    capi.lib().usb_set_local(C.byref(p), int(nucleo), float(evalue))
+    return p

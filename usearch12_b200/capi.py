@@ -26,7 +26,9 @@ class Params(C.Structure):
         ("band", C.c_uint32), ("minhsp", C.c_uint32), ("hspw", C.c_uint32), ("xdrop_nw", C.c_float),
         ("match", C.c_float), ("mismatch", C.c_float), ("gap_open", C.c_float), ("gap_ext", C.c_float),
         ("term_gap_open", C.c_float), ("term_gap_ext", C.c_float), ("dbmask", C.c_int32),
-        ("cluster_mode", C.c_int32), ("fulldp", C.c_int32),
+        ("cluster_mode", C.c_int32), ("fulldp", C.c_int32), ("local", C.c_int32), ("evalue", C.c_float),
+        ("xdrop_u", C.c_float), ("xdrop_g", C.c_float), ("lopen", C.c_float), ("lext", C.c_float),
+        ("ka_dbsize", C.c_float),
     ]
 
 
@@ -35,7 +37,7 @@ HIT_DTYPE = np.dtype([
     ("ids", "<u4"), ("mism", "<u4"), ("intgaps", "<u4"), ("opens", "<u4"),
     ("first_mq", "<u4"), ("first_mt", "<u4"), ("last_mq", "<u4"), ("last_mt", "<u4"),
     ("first_mcol", "<u4"), ("alnlen", "<u4"), ("ql", "<u4"), ("tl", "<u4"),
-    ("run_off", "<u4"), ("run_cnt", "<u4"),
+    ("run_off", "<u4"), ("run_cnt", "<u4"), ("raw", "<i4"), ("sub", "<u4"),
 ])
 QSTAT_DTYPE = np.dtype([
     ("n_cand", "<u4"), ("n_tried", "<u4"), ("n_hspfail", "<u4"), ("n_dp", "<u4"), ("dp_cells", "<u4"),
@@ -50,7 +52,7 @@ SYMBOLS = [
     "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
-    "usb_viterbi_batch",
+    "usb_viterbi_batch", "usb_set_local", "usb_local_evalue", "usb_local_pairs",
 ]
 
 _lib = None
@@ -106,6 +108,10 @@ def lib():
     L.usb_rank_batch.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.usb_align_pairs.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.POINTER(vp), vp, C.c_uint32]
     L.usb_viterbi_batch.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
+    L.usb_set_local.argtypes = [C.POINTER(Params), C.c_int, C.c_float]
+    L.usb_set_local.restype = None
+    L.usb_local_evalue.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.usb_local_pairs.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(vp)]
     _lib = L
     return L
 
@@ -285,6 +291,21 @@ class Searcher:
         check(lib().usb_rank_batch(self.handle, _ptr(data), _ptr(off), len(seqs), k_max, _ptr(ct), _ptr(cu), _ptr(nc),
                                    _ptr(u)))
         return ct, cu, nc, u
+
+    def local_evalue(self, raw, ql):
+        """(E-value, bit score) of a local hit's raw score (estats.cpp:73-96)."""
+        ev, bits = C.c_double(), C.c_double()
+        check(lib().usb_local_evalue(self.handle, int(raw), int(ql), C.byref(ev), C.byref(bits)))
+        return ev.value, bits.value
+
+    def local_pairs(self, seqs, pair_q, pair_t):
+        """LocalAligner2::AlignMulti on explicit (query, target) pairs -> Result grouped by pair."""
+        data, off = pack_seqs(seqs)
+        pq = np.ascontiguousarray(pair_q, dtype=np.uint32)
+        pt = np.ascontiguousarray(pair_t, dtype=np.uint32)
+        h = C.c_void_p()
+        check(lib().usb_local_pairs(self.handle, _ptr(data), _ptr(off), len(seqs), _ptr(pq), _ptr(pt), len(pq), C.byref(h)))
+        return Result(h, len(pq), 0)
 
     def align_pairs(self, seqs, pair_q, pair_t, max_hsp=0):
         data, off = pack_seqs(seqs)

@@ -1220,7 +1220,7 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 			else {
 				usb_hit h;
 				h.query = qi; h.target = t; h.strand = strand; h.rank = pairs ? job : k;
-				h.ql = w.LA; h.tl = w.LB; h.run_off = 0; h.run_cnt = 0;
+				h.ql = w.LA; h.tl = w.LB; h.run_off = 0; h.run_cnt = 0; h.raw = 0; h.sub = 0;
 				if (!path_stats(a, w, n, h)) {
 					if (lane == 0)
 						atomicOr(&a.ctr->err, ERR_NO_M);

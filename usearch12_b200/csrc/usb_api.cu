@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "usb_align.cuh"
+#include "usb_local.cuh"
 #include "usb_hostindex.h"
 #include "usb_rank.cuh"
 #include "usb_rankbig.cuh"
@@ -75,6 +76,27 @@ extern "C" void usb_default_params(usb_params *p, int cluster_fast)
 	p->term_gap_ext = -0.5f;
 	p->dbmask = cluster_fast ? 0 : 1;
 	p->cluster_mode = cluster_fast;
+	p->local = 0;
+	p->evalue = 10.0f;
+	p->xdrop_u = 16.0f;
+	p->xdrop_g = 32.0f;
+	p->lopen = -10.0f;
+	p->lext = -1.0f;
+	p->ka_dbsize = 1e9f;
+}
+
+extern "C" void usb_set_local(usb_params *p, int nucleo, float evalue)
+{
+	p->local = 1;
+	p->evalue = evalue;
+	p->is_nucleo = nucleo ? 1 : 0;
+	if (nucleo) {
+		p->word_length = 8;
+		p->hspw = 5;
+	} else {
+		p->word_length = 5;
+		p->hspw = 3;
+	}
 }
 
 // ------------------------------------------------------------------ objects
@@ -221,6 +243,13 @@ struct usb_searcher {
 	size_t rank_smem_set = 0;
 	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
 	bool bigsmem_set = false;
+	// -usearch_local
+	DevBuf<LocalDevTables> d_ltab;
+	DevBuf<float> d_min_ungapped;
+	DevBuf<int> d_min_gapped;
+	size_t local_smem_set = 0;
+	std::vector<float> es_min_ungapped; // per query length, NAN = not computed yet
+	std::vector<int> es_min_gapped;     // per query length, INT_MIN = not computed yet
 };
 
 static bool is_int2(float x) { return std::floor(2.0 * (double)x) == 2.0 * (double)x; }
@@ -230,11 +259,27 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 {
 	if (!p || p->struct_size != sizeof(usb_params))
 		return fail(USB_EINVAL, "usb_params.struct_size mismatch (header/library version skew)");
-	if (!p->is_nucleo)
-		return fail(USB_EINVAL, "amino-acid databases (usearch_local row) are not built yet");
-	if (p->word_length < 2 || p->word_length > 8)
-		return fail(USB_EINVAL, "word_length %u unsupported (2..8)", p->word_length);
-	if (p->hspw < 3 || p->hspw > 6)
+	if (!p->is_nucleo && !p->local)
+		return fail(USB_EINVAL, "amino-acid databases are supported for usearch_local only (local = 1)");
+	if (p->is_nucleo) {
+		if (p->word_length < 2 || p->word_length > 8)
+			return fail(USB_EINVAL, "word_length %u unsupported (2..8)", p->word_length);
+	} else if (p->word_length < 2 || p->word_length > 5)
+		return fail(USB_EINVAL, "amino word_length %u unsupported (2..5)", p->word_length);
+	if (p->local) {
+		if (p->hspw < 2 || (p->is_nucleo ? p->hspw > 8 : p->hspw > 3))
+			return fail(USB_EINVAL, "local seed word length (hspw) %u unsupported (nt 2..8, aa 2..3)", p->hspw);
+		if (p->cluster_mode || p->fulldp)
+			return fail(USB_EINVAL, "local = 1 cannot be combined with cluster_mode / fulldp");
+		const float iv[] = {p->lopen, p->lext, p->match, p->mismatch};
+		for (float v : iv)
+			if (std::floor((double)v) != (double)v || std::fabs(v) > 100)
+				return fail(USB_EINVAL, "local alignment needs integer scores (got %g)", (double)v);
+		if (!(p->lopen < 0.0f) || !(p->lext < 0.0f))
+			return fail(USB_EINVAL, "local gap penalties must be negative (lopen %g, lext %g)", (double)p->lopen, (double)p->lext);
+		if (!(p->evalue > 0.0f) || !(p->ka_dbsize > 0.0f) || !(p->xdrop_u >= 0.0f) || !(p->xdrop_g >= 0.0f))
+			return fail(USB_EINVAL, "local: evalue, ka_dbsize must be > 0 and xdrop_u, xdrop_g >= 0");
+	} else if (p->hspw < 3 || p->hspw > 6)
 		return fail(USB_EINVAL, "hspw %u unsupported (3..6)", p->hspw);
 	const float sc[] = {p->match, p->mismatch, p->gap_open, p->gap_ext, p->term_gap_open, p->term_gap_ext};
 	for (float v : sc)
@@ -256,10 +301,12 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 	D.minscore2 = 2.0f * minscore;
 	D.band = p->band;
 	D.hspw = p->hspw;
-	D.hsp_words = 1u << (2 * p->hspw);
+	D.hsp_words = p->local ? 0u : 1u << (2 * p->hspw);
 	D.hsp_hi = D.hsp_words / 4;
 	D.word_length = p->word_length;
-	D.slots = 1u << (2 * p->word_length);
+	D.alpha = p->is_nucleo ? 4 : 20;
+	D.slots = udb_slots(D.alpha, p->word_length);
+	D.hash_cap = 0;
 	D.maxaccepts = p->maxaccepts;
 	D.maxrejects = p->maxrejects;
 	D.bump = p->bump;
@@ -281,6 +328,7 @@ static int upload_tables(int device)
 	CK(cudaMemcpyToSymbol(c_cls, T.cls, sizeof T.cls));
 	CK(cudaMemcpyToSymbol(c_upper, T.upper, sizeof T.upper));
 	CK(cudaMemcpyToSymbol(c_comp, T.comp, sizeof T.comp));
+	CK(cudaMemcpyToSymbol(c_udb_aa, udb_letters(20), 256));
 	g_tables_uploaded[device] = true;
 	return 0;
 }
@@ -345,7 +393,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	if (ix->dyn || n < 8192) {
 		if (!ix->dyn) {
 			ix->dyn = new DynSegment;
-			if ((rc = ix->dyn->init(n0, ix->P.word_length)))
+			if ((rc = ix->dyn->init(n0, ix->P.word_length, ix->P.is_nucleo ? 4 : 20)))
 				return rc;
 		}
 		const uint64_t before = ix->dyn->n_postings;
@@ -356,7 +404,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	}
 	// new segment, then merge while the last two are of similar size (or the list is full)
 	IndexSegment *g = new IndexSegment;
-	build_csr(S, n0, n, ix->P.word_length, 0, g->H);
+	build_csr(S, n0, n, ix->P.word_length, ix->P.is_nucleo ? 4 : 20, 0, g->H);
 	ix->n_postings += g->H.n_postings;
 	ix->segs.push_back(g);
 	bool dirty = true;
@@ -402,7 +450,7 @@ extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? i
 
 extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size)
 {
-	if (!ix || word >= (1u << (2 * ix->P.word_length)))
+	if (!ix || word >= udb_slots(ix->P.is_nucleo ? 4 : 20, ix->P.word_length))
 		return fail(USB_EINVAL, "usb_index_row: bad word %u", word);
 	std::vector<uint32_t> &tmp = const_cast<usb_index *>(ix)->row_tmp;
 	tmp.clear();
@@ -428,6 +476,53 @@ extern "C" int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t
 	*len = ix->S.seq_len[target];
 	return 0;
 }
+
+// ------------------------------------------------------------------ EStats (estats.cpp:25-101)
+// Karlin-Altschul statistics in double, exactly the reference's expressions (same libm): the DB
+// size is -ka_dbsize (its default counts as set, makedbsearcher.cpp:92-96) and reaches the
+// constructor as a float, like the maximum E-value.
+struct EStats {
+	double gl, ul, gk, uk, loggk, loguk, dbsize, maxe, log2;
+	void init(const usb_params &P)
+	{
+		if (P.is_nucleo) {
+			gl = 1.280; ul = 1.330; gk = 0.460; uk = 0.621;
+		} else {
+			gl = 0.267; ul = 0.311; gk = 0.0410; uk = 0.128;
+		}
+		loggk = log(gk);
+		loguk = log(uk);
+		dbsize = (double)(float)P.ka_dbsize;
+		maxe = (double)(float)P.evalue;
+		log2 = log(2.0);
+	}
+	// The expressions are written the way the reference binary evaluates them under its own build
+	// flags (-O3 -ffast-math, src/Makefile:11-14: x/Log2 -> x*(1/Log2), NM/pow(2,B) -> NM*exp2(-B),
+	// one fused multiply-add), so that printed E-values and bit scores agree to the last digit.
+	double min_ungapped_raw(unsigned QL) const // estats.cpp:65-71
+	{
+		return ((log((double)QL * dbsize) + loguk) - log(maxe)) / ul;
+	}
+	double raw_to_bits(double raw) const { return std::fma(raw, gl, -loggk) * (1.0 / log2); } // estats.cpp:79-85, gapped
+	double raw_to_evalue(double raw, unsigned QL) const                                       // estats.cpp:73-96
+	{
+		const double x = (loggk - raw * gl) * (1.0 / log2);
+		return (double)QL * (exp2(x) * dbsize);
+	}
+	// smallest integer raw score >= 1 that passes `Evalue > -evalue -> reject` (localaligner.cpp:198-203)
+	int min_gapped_raw(unsigned QL, float evalue_opt) const
+	{
+		const double E = (double)evalue_opt;
+		auto pass = [&](int sc) { return !(raw_to_evalue((double)sc, QL) > E); };
+		double guess = ((log((double)QL * dbsize) - log(E)) + loggk) / gl;
+		int sc = guess > 1e9 ? 1000000000 : guess < 1 ? 1 : (int)guess;
+		while (sc > 1 && pass(sc - 1))
+			--sc;
+		while (sc < 2000000000 && !pass(sc))
+			++sc;
+		return sc;
+	}
+};
 
 // ------------------------------------------------------------------ searcher
 extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searcher **out)
@@ -457,6 +552,25 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 		usb_searcher_free(s);
 		return rc;
 	}
+	if (p->local) {
+		LocalTables T;
+		build_local_tables(p->is_nucleo != 0, (int)p->match, (int)p->mismatch, T);
+		LocalDevTables *H = new LocalDevTables;
+		for (int a = 0; a < USB_NCODE; ++a) {
+			for (int b = 0; b < USB_NCODE; ++b)
+				H->score[a * USB_NCODE + b] = T.score[a][b];
+			H->match[a] = T.match[a];
+			H->word_letter[a] = T.word_letter[a];
+		}
+		memcpy(H->code, T.code, 256);
+		rc = s->d_ltab.reserve(1);
+		cudaError_t e = rc ? cudaSuccess : cudaMemcpy(s->d_ltab.p, H, sizeof *H, cudaMemcpyHostToDevice);
+		delete H;
+		if (rc || e != cudaSuccess) {
+			usb_searcher_free(s);
+			return rc ? rc : fail(USB_ECUDA, "upload of the local tables failed: %s", cudaGetErrorString(e));
+		}
+	}
 	*out = s;
 	return 0;
 }
@@ -471,6 +585,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
+	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release();
 	for (auto &e : s->ev)
 		if (e)
 			cudaEventDestroy(e);
@@ -521,6 +636,31 @@ static int upload_queries(usb_searcher *s, const uint8_t *qseqs, const uint64_t 
 		for (uint32_t i = 0; i <= n_q; ++i)
 			rel[i] = q_off[i] - base;
 		CK(cudaMemcpyAsync(s->d_qoff.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+	}
+	if (s->P.local) {
+		// per-query gates of LocalAligner::AlignPos (localaligner.cpp:167-171,198-203), cached by length
+		EStats es;
+		es.init(s->P);
+		if (s->es_min_gapped.size() <= max_ql) {
+			s->es_min_gapped.resize((size_t)max_ql + 1, INT32_MIN);
+			s->es_min_ungapped.resize((size_t)max_ql + 1, 0.0f);
+		}
+		std::vector<float> mu(std::max(1u, n_q));
+		std::vector<int> mg(std::max(1u, n_q));
+		for (uint32_t i = 0; i < n_q; ++i) {
+			const uint32_t L = (uint32_t)(q_off[i + 1] - q_off[i]);
+			if (s->es_min_gapped[L] == INT32_MIN) {
+				s->es_min_ungapped[L] = (float)es.min_ungapped_raw(L);
+				s->es_min_gapped[L] = L ? es.min_gapped_raw(L, s->P.evalue) : 1;
+			}
+			mu[i] = s->es_min_ungapped[L];
+			mg[i] = s->es_min_gapped[L];
+		}
+		if ((rc = s->d_min_ungapped.reserve(mu.size())) || (rc = s->d_min_gapped.reserve(mg.size())))
+			return rc;
+		CK(cudaMemcpyAsync(s->d_min_ungapped.p, mu.data(), mu.size() * 4, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaMemcpyAsync(s->d_min_gapped.p, mg.data(), mg.size() * 4, cudaMemcpyHostToDevice, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	s->n_q = n_q;
@@ -586,11 +726,22 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		return 0;
 	if (!s->big && N > s->P.big)
 		s->big = true; // sticky, like UDBUsortedSearcher::SetQueryImpl (udbusortedsearcher.cpp:39-58)
+	if (s->big && !s->P.is_nucleo)
+		return fail(USB_ELIMIT, "amino acid databases larger than -big (%u targets) are not supported", s->P.big);
 	if (s->big)
 		return launch_rank_big(s, n_jobs, strands, k_max, want_u);
 	RankArgs a;
 	memset(&a, 0, sizeof a);
 	a.P = s->D;
+	size_t dedupe_bytes = s->D.slots / 8;
+	if (!s->P.is_nucleo) {
+		// hash set of the query's words: at least twice the number of word positions
+		uint32_t cap = 1024;
+		while (cap < 2 * (s->max_ql + 1))
+			cap <<= 1;
+		a.P.hash_cap = cap;
+		dedupe_bytes = (size_t)cap * 4;
+	}
 	a.q = s->d_q.p;
 	a.q_off = s->d_qoff.p;
 	a.n_jobs = n_jobs;
@@ -610,7 +761,7 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	a.rec_cap = wide ? RANK_REC_WIDE : RANK_REC_NARROW;
 	a.bump_d = s->P.bump / 100.0;
 	a.ctr = s->d_ctr.p;
-	const size_t smem = rank_smem_bytes(N, wide, s->D.slots, a.rec_cap, &a.u_bytes);
+	const size_t smem = rank_smem_bytes(N, wide, dedupe_bytes, a.rec_cap, &a.u_bytes);
 	if (smem > s->smem_optin)
 		return fail(USB_ELIMIT,
 		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
@@ -721,13 +872,109 @@ static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_ca
 	a.ctr = s->d_ctr.p;
 }
 
+struct LocalGeom {
+	int wpb;
+	uint32_t ql_cap, tl_cap, qk_cap, fast_bytes, tb_cap;
+	size_t smem;
+	uint64_t slab_stride;
+	uint32_t n_warps, grid;
+};
+
+static int local_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, LocalGeom &g)
+{
+	if (max_ql > LOCAL_MAXL || max_tl > LOCAL_MAXL)
+		return fail(USB_ELIMIT,
+		  "usearch_local supports sequences up to %u letters (query %u, target %u): longer X-drop extensions take the "
+		  "reference's split path, which is not built", LOCAL_MAXL, max_ql, max_tl);
+	g.ql_cap = lpad16(max_ql + 16);
+	g.tl_cap = lpad16(max_tl + 16);
+	g.qk_cap = 32;
+	while (g.qk_cap < max_ql + 1)
+		g.qk_cap <<= 1;
+	g.fast_bytes = lpad16(local_fast_bytes(g.ql_cap, g.tl_cap, g.qk_cap));
+	const size_t fixed = (sizeof(LocalShared) + 15) & ~(size_t)15;
+	const size_t budget = s->smem_optin > fixed + 1024 ? s->smem_optin - fixed - 1024 : 0;
+	g.wpb = (int)std::min<size_t>(LOCAL_MAX_WARPS, budget / g.fast_bytes);
+	if (g.wpb < 1)
+		return fail(USB_ELIMIT, "local alignment workspace of %u bytes per warp does not fit in shared memory", g.fast_bytes);
+	g.smem = fixed + (size_t)g.wpb * g.fast_bytes;
+	const uint64_t full = ((uint64_t)max_ql + 1) * ((uint64_t)max_tl + 2) + 64;
+	g.tb_cap = (uint32_t)std::min<uint64_t>(full, (uint64_t)32 << 20);
+	g.slab_stride = (local_slab_bytes(g.ql_cap, g.tl_cap, g.tb_cap) + 255) & ~(uint64_t)255;
+	g.grid = (uint32_t)s->num_sms;
+	g.n_warps = g.grid * g.wpb;
+	size_t free_b = 0, total_b = 0;
+	CK(cudaMemGetInfo(&free_b, &total_b));
+	const uint64_t limit = std::max<uint64_t>(total_b / 3, (uint64_t)256 << 20);
+	while ((uint64_t)g.n_warps * g.slab_stride > limit && g.wpb > 1) {
+		--g.wpb;
+		g.n_warps = g.grid * g.wpb;
+		g.smem = fixed + (size_t)g.wpb * g.fast_bytes;
+	}
+	while ((uint64_t)g.n_warps * g.slab_stride > limit && g.grid > 1) {
+		g.grid = std::max(1u, g.grid / 2);
+		g.n_warps = g.grid * g.wpb;
+	}
+	if ((uint64_t)g.n_warps * g.slab_stride > limit)
+		return fail(USB_ELIMIT, "local alignment workspace of %llu bytes per warp does not fit",
+		  (unsigned long long)g.slab_stride);
+	return 0;
+}
+
+static void fill_local_args(usb_searcher *s, const LocalGeom &g, LocalArgs &a)
+{
+	memset(&a, 0, sizeof a);
+	const usb_index *ix = s->ix;
+	a.P = s->D;
+	a.q = s->d_q.p;
+	a.q_off = s->d_qoff.p;
+	a.db_seq = ix->d_seqs.p;
+	a.db_off = ix->d_seq_off.p;
+	a.db_len = ix->d_seq_len.p;
+	a.min_ungapped = s->d_min_ungapped.p;
+	a.min_gapped = s->d_min_gapped.p;
+	a.tab = s->d_ltab.p;
+	a.slab = s->d_slab.p;
+	a.slab_stride = g.slab_stride;
+	a.ql_cap = g.ql_cap;
+	a.tl_cap = g.tl_cap;
+	a.qk_cap = g.qk_cap;
+	a.fast_bytes = g.fast_bytes;
+	a.tb_cap = g.tb_cap;
+	a.xdrop_u = s->P.xdrop_u;
+	a.xdrop_g = s->P.xdrop_g;
+	a.open = (int)s->P.lopen;
+	a.ext = (int)s->P.lext;
+	a.abs_open_f = -s->P.lopen;
+	a.abs_ext_f = -s->P.lext;
+	a.w = s->P.hspw;
+	a.alpha = s->P.is_nucleo ? 4 : 20;
+	a.alpha_hi = 1;
+	for (uint32_t i = 1; i < a.w; ++i)
+		a.alpha_hi *= a.alpha;
+	a.ctr = s->d_ctr.p;
+}
+
+static int launch_local(usb_searcher *s, const LocalArgs &a, const LocalGeom &g)
+{
+	if (g.smem > s->local_smem_set) {
+		CK(cudaFuncSetAttribute(k_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+		s->local_smem_set = g.smem;
+	}
+	k_local<<<g.grid, g.wpb * 32, g.smem, s->stream>>>(a);
+	CK(cudaGetLastError());
+	++s->launches;
+	return 0;
+}
+
 static const char *err_text(uint32_t e)
 {
 	static thread_local char buf[256];
-	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s", e, e & ERR_HITS_FULL ? " hit buffer full" : "",
+	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s%s%s", e, e & ERR_HITS_FULL ? " hit buffer full" : "",
 	  e & ERR_RUNS_FULL ? " run arena full" : "", e & ERR_HSP_FULL ? " HSP list full" : "",
 	  e & ERR_TRACE ? " traceback left the band" : "", e & ERR_RECORDS_FULL ? " U-sort record list full" : "",
-	  e & ERR_NO_M ? " alignment path without M" : "");
+	  e & ERR_NO_M ? " alignment path without M" : "", e & ERR_TB_FULL ? " X-drop trace arena full" : "",
+	  e & ERR_AR_FULL ? " more than 32 local alignments for one target" : "");
 	return buf;
 }
 
@@ -760,27 +1007,46 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		  k_max, RANK_KCAP);
 	s->k_max = k_max;
 	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->S.max_len / 8 + 16);
+	const bool local = s->P.local != 0;
 	AlignGeom g;
-	int rc = align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g);
+	LocalGeom lg;
+	int rc = local ? local_geometry(s, s->max_ql, ix->S.max_len, lg) : align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g);
 	if (rc)
 		return rc;
 	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : k_max;
-	const uint64_t hits_cap = std::max<uint64_t>(1, (uint64_t)s->n_jobs * per_job_hits);
+	// a local target can contribute several ARs (localmulti.cpp): start with room for two per
+	// accepted target and grow on demand
+	uint64_t hits_cap = std::max<uint64_t>(1, (uint64_t)s->n_jobs * per_job_hits * (local ? 2 : 1) + (local ? 1024 : 0));
 	if (hits_cap > 0xfffffff0ull)
 		return fail(USB_ELIMIT, "hit buffer of %llu records too large; use smaller batches", (unsigned long long)hits_cap);
 	uint64_t runs_cap = std::max<uint64_t>(s->d_runs.cap, std::max<uint64_t>((uint64_t)1 << 20, hits_cap * 24));
-	if ((rc = s->d_hits.reserve(hits_cap)) || (rc = s->d_qstat.reserve(std::max(1u, s->n_jobs))) ||
-	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride)))
+	if ((rc = s->d_qstat.reserve(std::max(1u, s->n_jobs))) ||
+	    (rc = s->d_slab.reserve(local ? (size_t)lg.n_warps * lg.slab_stride : (size_t)g.n_warps * g.slab_stride)))
 		return rc;
 	for (int attempt = 0;; ++attempt) {
-		if ((rc = s->d_runs.reserve(runs_cap)))
+		if ((rc = s->d_runs.reserve(runs_cap)) || (rc = s->d_hits.reserve(hits_cap)))
 			return rc;
 		CK(cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream));
 		CK(cudaEventRecord(s->ev[0], s->stream));
 		if ((rc = launch_rank(s, s->n_jobs, s->strands, k_max, false)))
 			return rc;
 		CK(cudaEventRecord(s->ev[1], s->stream));
-		if (s->n_jobs) {
+		if (s->n_jobs && local) {
+			LocalArgs a;
+			fill_local_args(s, lg, a);
+			a.n_jobs = s->n_jobs;
+			a.strands = s->strands;
+			a.cand_t = s->d_cand_t.p;
+			a.n_emit = s->d_nemit.p;
+			a.k_max = k_max;
+			a.hits = s->d_hits.p;
+			a.hits_cap = (uint32_t)hits_cap;
+			a.runs = s->d_runs.p;
+			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
+			a.qstat = s->d_qstat.p;
+			if ((rc = launch_local(s, a, lg)))
+				return rc;
+		} else if (s->n_jobs) {
 			AlignArgs a;
 			fill_align_args(s, g, hsp_cap, a);
 			a.n_jobs = s->n_jobs;
@@ -800,8 +1066,11 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		DevCounters c;
 		CK(cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
-		if (c.err == ERR_RUNS_FULL && attempt < 4) {
-			runs_cap = std::max<uint64_t>(runs_cap * 4, (uint64_t)c.n_runs + 1024);
+		if (c.err && !(c.err & ~(ERR_RUNS_FULL | ERR_HITS_FULL)) && attempt < 4) {
+			if (c.err & ERR_RUNS_FULL)
+				runs_cap = std::max<uint64_t>(runs_cap * 4, (uint64_t)c.n_runs + 1024);
+			if (c.err & ERR_HITS_FULL)
+				hits_cap = std::min<uint64_t>(0xfffffff0ull, std::max<uint64_t>(hits_cap * 2, (uint64_t)c.n_hits + 1024));
 			continue;
 		}
 		if (c.err)
@@ -843,7 +1112,7 @@ static void quicksort_desc(const float *v, uint32_t *ord, int lo, int hi)
 		quicksort_desc(v, ord, i, hi);
 }
 
-static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector<uint64_t> &qoff)
+static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector<uint64_t> &qoff, bool local)
 {
 	std::vector<float> sc;
 	std::vector<uint32_t> ord;
@@ -854,15 +1123,17 @@ static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector
 		if (n < 2)
 			continue;
 		// Searcher::Search appends plus-strand hits, then minus-strand hits (searcher.cpp:144-158)
+		// and, for local searches, the ARs of one target in AlignMulti order (searcher.cpp:36-47)
 		std::sort(hits.begin() + b, hits.begin() + e, [](const usb_hit &x, const usb_hit &y) {
-			return x.strand != y.strand ? x.strand < y.strand : x.rank < y.rank;
+			return x.strand != y.strand ? x.strand < y.strand : x.rank != y.rank ? x.rank < y.rank : x.sub < y.sub;
 		});
 		sc.resize(n);
 		ord.resize(n);
 		tmp.assign(hits.begin() + b, hits.begin() + e);
 		for (uint32_t i = 0; i < n; ++i) {
 			const usb_hit &h = tmp[i];
-			sc[i] = (float)(h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen); // arscorer.cpp:818
+			// arscorer.cpp:818-824: local = raw score, global = fractional identity
+			sc[i] = local ? (float)h.raw : (float)(h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen);
 			ord[i] = i;
 		}
 		quicksort_desc(sc.data(), ord.data(), 0, (int)n - 1);
@@ -910,7 +1181,7 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 	for (const usb_hit &h : raw)
 		r->hits[cur[group ? h.query : h.rank]++] = h;
 	if (group)
-		order_hits_like_hitmgr(r->hits, r->qoff);
+		order_hits_like_hitmgr(r->hits, r->qoff, s->P.local != 0);
 	*out = r;
 	return 0;
 }
@@ -1089,6 +1360,100 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 	rc = download_result(s, n_pairs, false, out); // grouped by pair index (hit.rank)
 	cleanup();
 	return rc;
+}
+
+extern "C" int usb_local_evalue(const usb_searcher *s, int32_t raw, uint32_t ql, double *evalue, double *bits)
+{
+	if (!s || !s->P.local)
+		return fail(USB_EINVAL, "usb_local_evalue: not a local searcher");
+	EStats es;
+	es.init(s->P);
+	if (evalue)
+		*evalue = es.raw_to_evalue((double)raw, ql);
+	if (bits)
+		*bits = es.raw_to_bits((double)raw);
+	return 0;
+}
+
+extern "C" int usb_local_pairs(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
+  const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_pairs, usb_result **out)
+{
+	if (!s || !pair_q || !pair_t || !out)
+		return fail(USB_EINVAL, "usb_local_pairs: null argument");
+	if (!s->P.local)
+		return fail(USB_EINVAL, "usb_local_pairs: not a local searcher");
+	const usb_index *ix = s->ix;
+	for (uint32_t i = 0; i < n_pairs; ++i)
+		if (pair_q[i] >= n_q || pair_t[i] >= ix->S.n())
+			return fail(USB_EINVAL, "pair %u out of range", i);
+	int rc = upload_queries(s, qseqs, q_off, n_q);
+	if (rc)
+		return rc;
+	LocalGeom g;
+	if ((rc = local_geometry(s, s->max_ql, ix->S.max_len, g)))
+		return rc;
+	DevBuf<uint32_t> d_pq, d_pt;
+	uint64_t hits_cap = (uint64_t)n_pairs * 4 + 64;
+	uint64_t runs_cap = std::max<uint64_t>((uint64_t)1 << 20, hits_cap * 64);
+	auto cleanup = [&]() { d_pq.release(); d_pt.release(); };
+	if ((rc = d_pq.reserve(n_pairs + 1)) || (rc = d_pt.reserve(n_pairs + 1)) ||
+	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride))) {
+		cleanup();
+		return rc;
+	}
+	cudaMemcpyAsync(d_pq.p, pair_q, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s->stream);
+	cudaMemcpyAsync(d_pt.p, pair_t, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s->stream);
+	DevCounters c;
+	memset(&c, 0, sizeof c);
+	for (int attempt = 0; n_pairs; ++attempt) {
+		if ((rc = s->d_runs.reserve(runs_cap)) || (rc = s->d_hits.reserve(hits_cap))) {
+			cleanup();
+			return rc;
+		}
+		cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream);
+		LocalArgs a;
+		fill_local_args(s, g, a);
+		a.n_jobs = n_pairs;
+		a.strands = 1;
+		a.pair_q = d_pq.p;
+		a.pair_t = d_pt.p;
+		a.hits = s->d_hits.p;
+		a.hits_cap = (uint32_t)hits_cap;
+		a.runs = s->d_runs.p;
+		a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
+		if ((rc = launch_local(s, a, g))) {
+			cleanup();
+			return rc;
+		}
+		cudaError_t e = cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s->stream);
+		if (e != cudaSuccess) {
+			cleanup();
+			return fail(USB_ECUDA, "local kernel failed: %s", cudaGetErrorString(e));
+		}
+		if (c.err && !(c.err & ~(ERR_RUNS_FULL | ERR_HITS_FULL)) && attempt < 4) {
+			if (c.err & ERR_RUNS_FULL)
+				runs_cap *= 4;
+			if (c.err & ERR_HITS_FULL)
+				hits_cap = std::max<uint64_t>(hits_cap * 2, (uint64_t)c.n_hits + 64);
+			continue;
+		}
+		break;
+	}
+	cleanup();
+	if (c.err)
+		return fail(USB_ELIMIT, "%s", err_text(c.err));
+	s->last_hits = c.n_hits;
+	s->last_runs = c.n_runs;
+	s->n_jobs = 0;
+	if ((rc = download_result(s, n_pairs, false, out))) // grouped by pair index (hit.rank)
+		return rc;
+	usb_result *r = *out;
+	for (uint32_t i = 0; i < n_pairs; ++i)
+		std::sort(r->hits.begin() + r->qoff[i], r->hits.begin() + r->qoff[i + 1],
+		  [](const usb_hit &x, const usb_hit &y) { return x.sub < y.sub; });
+	return 0;
 }
 
 extern "C" int usb_viterbi_batch(usb_searcher *s, const uint8_t *a_seq, const uint64_t *a_off, const uint8_t *b_seq,

@@ -39,6 +39,8 @@ struct DevParams {
 	uint32_t maxaccepts, maxrejects;
 	uint32_t bump;
 	uint32_t fulldp;                     // -fulldp (FullDPAlways)
+	uint32_t alpha;                      // UDB alphabet size: 4 (nt) or 20 (aa), udbparams.cpp:235-261
+	uint32_t hash_cap;                   // aa: entries of the per-CTA word hash set (power of two), else 0
 	double id_d;                         // (double)(float)id (accepter.cpp:36-38)
 };
 
@@ -76,6 +78,7 @@ struct HspRec {
 __constant__ uint16_t c_cls[256];
 __constant__ uint8_t c_upper[256];
 __constant__ uint8_t c_comp[256];
+__constant__ uint8_t c_udb_aa[256];   // amino UDB letter of a raw character, 0xff = bad (udbparams.cpp:546-552)
 
 // 0..3 for ACGTU in either case, 4 for everything else (alpha.cpp g_CharToLetterNucleo).
 __device__ __forceinline__ uint32_t nt_code(uint32_t c)

@@ -54,22 +54,28 @@ void fastmask_nt(const uint8_t *in, uint32_t L, uint8_t *out)
 		memcpy(out, m.data(), L);
 }
 
-// UDB word of w letters starting at s (udbparams.cpp:540-555): upper-case ACGTU only.
-static inline uint32_t udb_word(const uint8_t *s, uint32_t w)
+const uint8_t *udb_letters(uint32_t alpha)
 {
-	uint32_t word = 0;
-	for (uint32_t i = 0; i < w; ++i) {
-		uint32_t l;
-		switch (s[i]) {
-		case 'A': l = 0; break;
-		case 'C': l = 1; break;
-		case 'G': l = 2; break;
-		case 'T': case 'U': l = 3; break;
-		default: return UINT32_MAX;
-		}
-		word = (word << 2) | l;
+	static uint8_t nt[256], aa[256];
+	static bool done = false;
+	if (!done) {
+		memset(nt, 0xff, sizeof nt);
+		memset(aa, 0xff, sizeof aa);
+		nt['A'] = 0; nt['C'] = 1; nt['G'] = 2; nt['T'] = 3; nt['U'] = 3;
+		const char *a = "ACDEFGHIKLMNPQRSTVWY"; // alpha.cpp g_CharToLetterAmino
+		for (int i = 0; i < 20; ++i)
+			aa[(int)a[i]] = (uint8_t)i;
+		done = true;
 	}
-	return word;
+	return alpha == 4 ? nt : aa;
+}
+
+uint32_t udb_slots(uint32_t alpha, uint32_t word_length)
+{
+	uint64_t n = 1;
+	for (uint32_t i = 0; i < word_length; ++i)
+		n *= alpha;
+	return n > 0xffffffffull ? 0u : (uint32_t)n;
 }
 
 static unsigned pick_threads(int n_threads, uint32_t items)
@@ -125,15 +131,16 @@ struct Worker {
 }
 
 template <class F>
-static void for_each_unique_word(const HostSeqs &S, uint32_t word_length, uint32_t t, uint32_t stamp_id,
+static void for_each_unique_word(const HostSeqs &S, uint32_t word_length, uint32_t alpha, uint32_t t, uint32_t stamp_id,
   std::vector<uint32_t> &stamp, F f)
 {
+	const uint8_t *letters = udb_letters(alpha);
 	const uint8_t *s = S.seqs.data() + S.seq_off[t];
 	const uint32_t L = S.seq_len[t], w = word_length;
 	if (L < w)
 		return;
 	for (uint32_t p = 0; p + w <= L; ++p) {
-		const uint32_t word = udb_word(s + p, w);
+		const uint32_t word = udb_word(s + p, w, alpha, letters);
 		if (word == UINT32_MAX || stamp[word] == stamp_id)
 			continue;
 		stamp[word] = stamp_id;
@@ -141,11 +148,12 @@ static void for_each_unique_word(const HostSeqs &S, uint32_t word_length, uint32
 	}
 }
 
-void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, int n_threads, HostCSR &ix)
+void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, uint32_t alpha, int n_threads,
+  HostCSR &ix)
 {
 	ix.base = first;
 	ix.count = count;
-	ix.slots = 1u << (2 * word_length);
+	ix.slots = udb_slots(alpha, word_length);
 	const unsigned T = pick_threads(n_threads, count);
 	std::vector<Worker> W(T);
 	for (unsigned k = 0; k < T; ++k) {
@@ -158,7 +166,7 @@ void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_
 		w.counts.assign(ix.slots, 0);
 		w.stamp.assign(ix.slots, 0);
 		for (uint32_t t = w.t0; t < w.t1; ++t)
-			for_each_unique_word(S, word_length, t, t - first + 1, w.stamp, [&](uint32_t word) { ++w.counts[word]; });
+			for_each_unique_word(S, word_length, alpha, t, t - first + 1, w.stamp, [&](uint32_t word) { ++w.counts[word]; });
 	});
 	// row offsets; each worker's counts become its write cursor inside the row
 	ix.row_off.assign((size_t)ix.slots + 1, 0);
@@ -183,7 +191,7 @@ void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_
 		Worker &w = W[k];
 		std::fill(w.stamp.begin(), w.stamp.end(), 0u);
 		for (uint32_t t = w.t0; t < w.t1; ++t)
-			for_each_unique_word(S, word_length, t, t - first + 1, w.stamp,
+			for_each_unique_word(S, word_length, alpha, t, t - first + 1, w.stamp,
 			  [&](uint32_t word) { ix.postings[ix.row_off[word] + w.counts[word]++] = t; });
 	});
 }

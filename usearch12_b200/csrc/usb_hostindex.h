@@ -41,8 +41,27 @@ struct HostCSR {
 // FastMaskSeq soft-masking (fastmask.cpp:88-158); in == out allowed.
 void fastmask_nt(const uint8_t *in, uint32_t L, uint8_t *out);
 
+// UDB alphabet (udbparams.cpp:235-261): alpha = 4 (ACGT, U = T) or 20 (ACDEFGHIKLMNPQRSTVWY);
+// a word is `word_length` letters read as a base-alpha number, slots = alpha^word_length.
+// Returns the 256-entry character -> letter table (0xff = lower case / not in the alphabet).
+const uint8_t *udb_letters(uint32_t alpha);
+uint32_t udb_slots(uint32_t alpha, uint32_t word_length);
+// word starting at s, or UINT32_MAX when a letter is bad (udbparams.cpp:540-555)
+inline uint32_t udb_word(const uint8_t *s, uint32_t w, uint32_t alpha, const uint8_t *letters)
+{
+	uint32_t word = 0;
+	for (uint32_t i = 0; i < w; ++i) {
+		const uint32_t l = letters[s[i]];
+		if (l == 0xff)
+			return UINT32_MAX;
+		word = word * alpha + l;
+	}
+	return word;
+}
+
 // n_threads <= 0: hardware concurrency.
-void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, int n_threads, HostCSR &out);
+void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_length, uint32_t alpha, int n_threads,
+  HostCSR &out);
 // a covers [x, y), b covers [y, z): out covers [x, z) with rows = a's row followed by b's row.
 void merge_csr(const HostCSR &a, const HostCSR &b, HostCSR &out);
 

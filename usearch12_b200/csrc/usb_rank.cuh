@@ -292,8 +292,11 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		const uint32_t n128 = ((WIDE ? 2 * N : N) + 15) / 16;
 		for (uint32_t i = tid; i < n128; i += RANK_THREADS)
 			U128[i] = make_uint4(0, 0, 0, 0);
-		for (uint32_t i = tid; i < a.P.slots / 32; i += RANK_THREADS)
-			bitmap[i] = 0;
+		// nt: bitmap over the 4^w slots; aa: open-addressing hash set of the query's words
+		const uint32_t nbm = a.P.alpha == 4 ? a.P.slots / 32 : a.P.hash_cap;
+		const uint32_t bm0 = a.P.alpha == 4 ? 0u : 0xffffffffu;
+		for (uint32_t i = tid; i < nbm; i += RANK_THREADS)
+			bitmap[i] = bm0;
 		if (tid == 0) {
 			S.n_rows = 0; S.row_cur = 0; S.n_rec = 0; S.n_chg = 0; S.n_sel = 0; S.n_post = 0; S.n_surv = 0;
 		}
@@ -306,17 +309,39 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		const uint32_t p = base + tid;
 		if (p < npos) {
 			uint32_t word = 0, bad = 0;
-			for (uint32_t i = 0; i < WLEN; ++i) {
-				uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - (p + i)]] : (uint32_t)Q[p + i];
-				uint32_t l = udb_letter(c);
-				bad |= l >> 2;
-				word = (word << 2) | (l & 3);
-			}
-			if (!bad) {
-				uint32_t bit = 1u << (word & 31);
-				uint32_t old = atomicOr(&bitmap[word >> 5], bit);
-				if (!(old & bit))
-					S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+			if (a.P.alpha == 4) {
+				for (uint32_t i = 0; i < WLEN; ++i) {
+					uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - (p + i)]] : (uint32_t)Q[p + i];
+					uint32_t l = udb_letter(c);
+					bad |= l >> 2;
+					word = (word << 2) | (l & 3);
+				}
+				if (!bad) {
+					uint32_t bit = 1u << (word & 31);
+					uint32_t old = atomicOr(&bitmap[word >> 5], bit);
+					if (!(old & bit))
+						S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+				}
+			} else {
+				for (uint32_t i = 0; i < WLEN; ++i) {
+					const uint32_t l = c_udb_aa[Q[p + i]];
+					bad |= l >> 7;
+					word = word * 20u + (l & 31);
+				}
+				if (!bad) {
+					const uint32_t mask = a.P.hash_cap - 1;
+					uint32_t h = (word * 2654435761u) >> 12 & mask;
+					for (;;) {
+						const uint32_t old = atomicCAS(&bitmap[h], 0xffffffffu, word);
+						if (old == 0xffffffffu) {
+							S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+							break;
+						}
+						if (old == word)
+							break;
+						h = (h + 1) & mask;
+					}
+				}
 			}
 		}
 		__syncthreads();
@@ -512,7 +537,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 	RankShared &S = *(RankShared *)rank_smem;
 	uint8_t *U = rank_smem + ((sizeof(RankShared) + 15) & ~(size_t)15);
 	uint32_t *bitmap = (uint32_t *)(U + a.u_bytes);
-	uint32_t *rec_pos = bitmap + a.P.slots / 32;
+	uint32_t *rec_pos = bitmap + (a.P.alpha == 4 ? a.P.slots / 32 : a.P.hash_cap);
 	uint32_t *rec_val = rec_pos + a.rec_cap;
 	uint32_t *chg_pos = rec_val + a.rec_cap;
 	uint32_t *chg_minu = chg_pos + a.rec_cap;
@@ -528,11 +553,12 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 		rank_job<false>(a, job, S, U, bitmap, rec_pos, rec_val, chg_pos, chg_minu);
 }
 
-inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, uint32_t slots, uint32_t rec_cap, uint32_t *u_bytes)
+// dedupe_bytes: nt = slots / 8 (bitmap), aa = 4 * hash_cap
+inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, size_t dedupe_bytes, uint32_t rec_cap, uint32_t *u_bytes)
 {
 	size_t ub = (((size_t)n_seq * (wide ? 2 : 1)) + 15) & ~(size_t)15;
 	*u_bytes = (uint32_t)ub;
-	return ((sizeof(RankShared) + 15) & ~(size_t)15) + ub + slots / 8 + (size_t)4 * rec_cap * 4;
+	return ((sizeof(RankShared) + 15) & ~(size_t)15) + ub + dedupe_bytes + (size_t)4 * rec_cap * 4;
 }
 
 // Per-thread segment length (in targets) such that consecutive threads start in different
