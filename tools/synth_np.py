@@ -106,3 +106,63 @@ def write_fasta(path, letters, off, prefix, lo=0, hi=None):
             f.write(b">%s%d\n" % (prefix.encode(), i))
             f.write(buf[int(off[i]):int(off[i + 1])])
             f.write(b"\n")
+
+
+# ---------------------------------------------------------------- proteins (config 5)
+AA_LETTERS = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+
+
+def _mutate_concat_aa(codes, lens, rates, rng):
+    """aa mutation mix: 5 % deletion, 5 % insertion of a random residue after, 90 % substitution by
+    a uniformly random residue."""
+    n = codes.size
+    rate_e = np.repeat(rates.astype(np.float32), lens)
+    mut = rng.random(n, dtype=np.float32) < rate_e
+    k = rng.random(n, dtype=np.float32)
+    dele = mut & (k < 0.05)
+    ins = mut & (k >= 0.05) & (k < 0.10)
+    sub = mut & (k >= 0.10)
+    out = codes.copy()
+    out[sub] = rng.integers(0, 20, size=int(sub.sum()), dtype=np.uint8)
+    cnt = np.ones(n, dtype=np.uint8)
+    cnt[dele] = 0
+    cnt[ins] = 2
+    new = np.repeat(out, cnt)
+    cs = np.cumsum(cnt, dtype=np.int64)
+    ins_pos = cs[ins] - 1
+    new[ins_pos] = rng.integers(0, 20, size=ins_pos.size, dtype=np.uint8)
+    ends = np.cumsum(lens, dtype=np.int64)
+    cs0 = np.concatenate([[0], cs])
+    new_lens = cs0[ends] - cs0[ends - lens]
+    return new, new_lens
+
+
+def gen_aa(n_db, length, n_q, seed):
+    """-> (db letters, db offsets, query letters, query offsets, true target per query).
+    DB: n_db/20 random roots, target = root mutated at U(0.05, 0.5); query = random target mutated
+    at U(0.05, 0.4)."""
+    rng = np.random.default_rng(seed)
+    n_root = max(1, n_db // 20)
+    roots = rng.integers(0, 20, size=(n_root, length), dtype=np.uint8)
+    idx = np.arange(n_db) % n_root
+    dcodes, dlens = _mutate_concat_aa(roots[idx].reshape(-1), np.full(n_db, length, dtype=np.int64),
+                                      rng.uniform(0.05, 0.5, size=n_db), rng)
+    doff = np.zeros(n_db + 1, dtype=np.uint64)
+    doff[1:] = np.cumsum(dlens)
+    qparts, qlens, truth = [], [], []
+    chunk = 50000
+    for c0 in range(0, n_q, chunk):
+        m = min(n_q, c0 + chunk) - c0
+        t = rng.integers(0, n_db, size=m)
+        ln = dlens[t]
+        start = doff[t].astype(np.int64)
+        rel = np.arange(int(ln.sum()), dtype=np.int64) - np.repeat(np.cumsum(ln) - ln, ln)
+        codes = dcodes[np.repeat(start, ln) + rel]
+        new, nl = _mutate_concat_aa(codes, ln, rng.uniform(0.05, 0.4, size=m), rng)
+        qparts.append(new)
+        qlens.append(nl)
+        truth.append(t)
+    qlens = np.concatenate(qlens)
+    qoff = np.zeros(n_q + 1, dtype=np.uint64)
+    qoff[1:] = np.cumsum(qlens)
+    return AA_LETTERS[dcodes], doff, AA_LETTERS[np.concatenate(qparts)], qoff, np.concatenate(truth)
