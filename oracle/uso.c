@@ -2496,29 +2496,46 @@ void uso_write_uc_nohit(FILE *f, uint32_t ql, const char *qlabel)
 	fprintf(f, "N\t*\t%u\t*\t.\t*\t*\t*\t%s\t*\n", ql, qlabel);
 	}
 
-/* local hits: qlo..thi are the 1-based segment ends (arscorer.cpp:683-745 without ORF/rev-comp) */
+/* local hits: coordinates of the segment, on the plus strand of the query when it was
+ * reverse-complemented (arscorer.cpp:683-745 without ORFs); blast6 swaps the target ends then
+ * (arscorer.cpp:748-808) */
+static void local_coords(const uso_hit *h, unsigned *qlo, unsigned *qhi, unsigned *tlo, unsigned *thi)
+	{
+	unsigned hii = h->loi + h->leni - 1, hij = h->loj + h->lenj - 1;
+	*qlo = h->strand ? h->ql - hii - 1 : h->loi;
+	*qhi = h->strand ? h->ql - h->loi - 1 : hii;
+	*tlo = h->loj;
+	*thi = hij;
+	}
+
 /* -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand */
 void uso_write_userout_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
 	{
 	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
 	uso_compress_path(h->path, cp);
+	unsigned qlo, qhi, tlo, thi;
+	local_coords(h, &qlo, &qhi, &tlo, &thi);
 	fprintf(f, "%s\t%s\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t%.3g\t%.0f\t%.0f\t%s\t%c\n", qlabel, tlabel, pct_id(h),
-	  h->alnlen, h->mism, h->opens, h->loi + 1, h->loi + h->leni, h->loj + 1, h->loj + h->lenj, h->evalue, h->bits,
+	  h->alnlen, h->mism, h->opens, qlo + 1, qhi + 1, tlo + 1, thi + 1, h->evalue, h->bits,
 	  h->raw, cp, nucleo ? (h->strand ? '-' : '+') : '.');
 	free(cp);
 	}
 
 void uso_write_blast6_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
 	{
+	unsigned qlo, qhi, tlo, thi;
+	local_coords(h, &qlo, &qhi, &tlo, &thi);
 	fprintf(f, "%s\t%s\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t%.2g\t%.1f\n", qlabel, tlabel, pct_id(h), h->alnlen,
-	  h->mism, h->opens, h->loi + 1, h->loi + h->leni, h->loj + 1, h->loj + h->lenj, h->evalue, h->bits);
+	  h->mism, h->opens, qlo + 1, qhi + 1, h->strand ? thi + 1 : tlo + 1, h->strand ? tlo + 1 : thi + 1, h->evalue, h->bits);
 	}
 
 void uso_write_uc_hit_local(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
 	{
 	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
 	uso_compress_path(h->path, cp);
-	fprintf(f, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t%s\t%s\t%s\n", h->target, h->ql, pct_id(h), nucleo ? (h->strand ? '-' : '+') : '.', h->loi, h->loj, cp,
-	  qlabel, tlabel);
+	unsigned qlo, qhi, tlo, thi;
+	local_coords(h, &qlo, &qhi, &tlo, &thi);
+	fprintf(f, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t%s\t%s\t%s\n", h->target, h->ql, pct_id(h),
+	  nucleo ? (h->strand ? '-' : '+') : '.', qlo, tlo, cp, qlabel, tlabel);
 	free(cp);
 	}

@@ -220,14 +220,14 @@ static int cluster_fast_main(int argc, char **argv)
 	return 0;
 	}
 
-/* uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt USEROUT UC B6 [maxaccepts maxrejects]
+/* uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt|ntboth USEROUT UC B6 [maxaccepts maxrejects]
  * = -usearch_local Q -db DB -id ID -evalue E [-strand plus] -userout .. -uc .. -blast6out ..
  *   -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand */
 static int usearch_local_main(int argc, char **argv)
 	{
 	if (argc < 10)
 		{
-		fprintf(stderr, "usage: uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt USEROUT UC B6 [maxaccepts maxrejects]\n");
+		fprintf(stderr, "usage: uso_cli usearch_local Q.fa DB.fa ID EVALUE aa|nt|ntboth USEROUT UC B6 [maxaccepts maxrejects]\n");
 		return 2;
 		}
 	uso_params P;
@@ -235,7 +235,8 @@ static int usearch_local_main(int argc, char **argv)
 	P.local = 1;
 	P.id = (float) atof(argv[4]);
 	P.evalue = (float) atof(argv[5]);
-	int nucleo = strcmp(argv[6], "nt") == 0;
+	int nucleo = strcmp(argv[6], "nt") == 0 || strcmp(argv[6], "ntboth") == 0;
+	P.strand_both = strcmp(argv[6], "ntboth") == 0;
 	if (!nucleo)
 		uso_set_amino(&P);
 	if (argc > 11)

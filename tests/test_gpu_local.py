@@ -138,3 +138,36 @@ def test_local_pairs_stage():
     assert res.cigar(h) == "300M" and int(h["ids"]) == 300
     a, b = res.hits[0], res.hits[1]
     assert {(int(a["first_mq"]), int(a["first_mt"])), (int(b["first_mq"]), int(b["first_mt"]))} == {(0, 150), (150, 0)}
+
+
+@pytest.mark.parametrize("variant", ["loc_aa_e5", "loc_nt_both"])
+def test_local_cli_output_files_byte_identical_to_reference(variant, tmp_path):
+    """The C++ host driver (usearch12_b200_cli -usearch_local) writes the reference's files."""
+    import gzip
+    import subprocess
+    from usearch12_b200 import build
+    kw = dict(util.LOCAL_VARIANTS[variant])
+    nucleo = kw.pop("nucleo")
+    kind = "nt" if nucleo else "aa"
+    g = util.GoldenLocal(kind)
+    cli = build.build_cli()
+    paths = {}
+    for name in ("q", "db"):
+        dst = os.path.join(str(tmp_path), name + ".fa")
+        with gzip.open(os.path.join(util.GOLDEN, "loc_%s_%s.fa.gz" % (kind, name)), "rb") as fi, open(dst, "wb") as fo:
+            fo.write(fi.read())
+        paths[name] = dst
+    cmd = [cli, "-usearch_local", paths["q"], "-db", paths["db"], "-quiet", "-id", str(kw["id"]), "-evalue", str(kw["evalue"]),
+           "-userfields", "query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand", "-batch", "300"]
+    if nucleo:
+        cmd += ["-strand", "both" if kw.get("strand_both") else "plus"]
+    if "maxaccepts" in kw:
+        cmd += ["-maxaccepts", str(kw["maxaccepts"]), "-maxrejects", str(kw["maxrejects"])]
+    for k, o in (("user", "-userout"), ("uc", "-uc"), ("b6", "-blast6out")):
+        paths[k] = os.path.join(str(tmp_path), "o." + k)
+        cmd += [o, paths[k]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for k in ("user", "uc", "b6"):
+        d = util.first_diff(open(paths[k]).read().splitlines(), g.lines(variant, k))
+        assert d is None, "%s %s\n%s" % (variant, k, d)

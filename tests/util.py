@@ -136,6 +136,7 @@ LOCAL_VARIANTS = {
     "loc_aa_e5": dict(nucleo=False, id=0.5, evalue=1e-5),
     "loc_aa_ma4": dict(nucleo=False, id=0.3, evalue=10.0, maxaccepts=4, maxrejects=64),
     "loc_nt_plus": dict(nucleo=True, id=0.9, evalue=1e-5, maxaccepts=2, maxrejects=16),
+    "loc_nt_both": dict(nucleo=True, id=0.8, evalue=1e-3, maxaccepts=3, maxrejects=8, strand_both=1),
 }
 
 
@@ -159,12 +160,19 @@ def fmt_local(h, cigar, evalue, bits, ql, tl, nucleo):
     blast6out.cpp:27-80, outputuc.cpp:45-69.  h holds loi/hii/loj/hij (0-based segment ends) and raw."""
     p = pct(h["ids"], h["alnlen"])
     st = _strand_char(h, nucleo)
+    # query coordinates are reported on the plus strand (arscorer.cpp:683-745); blast6 swaps the
+    # target ends for a reverse-complemented query (arscorer.cpp:748-808)
+    rc = bool(h["strand"])
+    qlo = h["ql"] - h["hii"] - 1 if rc else h["loi"]
+    qhi = h["ql"] - h["loi"] - 1 if rc else h["hii"]
+    tlo, thi = h["loj"], h["hij"]
     user = "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.3g\t%.0f\t%.0f\t%s\t%s" % (
-        ql, tl, p, h["alnlen"], h["mism"], h["opens"], h["loi"] + 1, h["hii"] + 1, h["loj"] + 1, h["hij"] + 1, evalue, bits,
+        ql, tl, p, h["alnlen"], h["mism"], h["opens"], qlo + 1, qhi + 1, tlo + 1, thi + 1, evalue, bits,
         h["raw"], cigar, st)
-    uc = "H\t%d\t%d\t%.1f\t%s\t%d\t%d\t%s\t%s\t%s" % (h["target"], h["ql"], p, st, h["loi"], h["loj"], cigar, ql, tl)
+    uc = "H\t%d\t%d\t%.1f\t%s\t%d\t%d\t%s\t%s\t%s" % (h["target"], h["ql"], p, st, qlo, tlo, cigar, ql, tl)
     b6 = "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.2g\t%.1f" % (
-        ql, tl, p, h["alnlen"], h["mism"], h["opens"], h["loi"] + 1, h["hii"] + 1, h["loj"] + 1, h["hij"] + 1, evalue, bits)
+        ql, tl, p, h["alnlen"], h["mism"], h["opens"], qlo + 1, qhi + 1, thi + 1 if rc else tlo + 1,
+        tlo + 1 if rc else thi + 1, evalue, bits)
     return user, uc, b6
 
 

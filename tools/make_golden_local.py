@@ -114,6 +114,12 @@ def build_nt():
         t = rng.randrange(200)
         s = "".join(rng.choice("ACGT") for _ in range(rng.randrange(20, 200))) + gen_synth.mutate(db[t][200:900], 0.05, rng)
         add("long;t=db%d" % t, s)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    for k in range(60):                                           # minus-strand reads (hits only with -strand both)
+        t = rng.randrange(200)
+        p = rng.randrange(0, 900)
+        s = gen_synth.mutate(db[t][p:p + 250], rng.uniform(0, 0.05), rng)
+        add("rc;t=db%d" % t, "".join(comp.get(c, c) for c in reversed(s)))
     add("polyA", "A" * 200)
     return db, reads
 
@@ -161,6 +167,8 @@ def main():
     run("loc_aa_ma4", tmpf["aa_q"], tmpf["aa_db"], ["-id", "0.3", "-evalue", "10", "-maxaccepts", "4", "-maxrejects", "64"])
     run("loc_nt_plus", tmpf["nt_q"], tmpf["nt_db"], ["-id", "0.9", "-evalue", "1e-5", "-strand", "plus", "-maxaccepts", "2",
                                                    "-maxrejects", "16"])
+    run("loc_nt_both", tmpf["nt_q"], tmpf["nt_db"], ["-id", "0.8", "-evalue", "1e-3", "-strand", "both", "-maxaccepts", "3",
+                                                   "-maxrejects", "8"])
     for f in tmpf.values():
         os.remove(f)
 

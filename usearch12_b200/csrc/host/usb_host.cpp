@@ -149,12 +149,13 @@ void AlignResult::GetCompressedPath(std::string &CPath) const
 enum UserField {
 	UF_query, UF_target, UF_clusternr, UF_id, UF_fractid, UF_dist, UF_pairs, UF_gaps, UF_allgaps, UF_qlo, UF_qhi,
 	UF_tlo, UF_thi, UF_qlot, UF_qhit, UF_qunt, UF_tlot, UF_thit, UF_tunt, UF_ql, UF_tl, UF_alnlen, UF_opens,
-	UF_exts, UF_aln, UF_caln, UF_qstrand, UF_tstrand, UF_mism, UF_ids, UF_diffs, UF_COUNT
+	UF_exts, UF_aln, UF_caln, UF_qstrand, UF_tstrand, UF_mism, UF_ids, UF_diffs, UF_evalue, UF_bits, UF_raw, UF_qlor,
+	UF_qhir, UF_tlor, UF_thir, UF_COUNT
 };
 static const char *g_UserFieldNames[UF_COUNT] = {
 	"query", "target", "clusternr", "id", "fractid", "dist", "pairs", "gaps", "allgaps", "qlo", "qhi", "tlo",
 	"thi", "qlot", "qhit", "qunt", "tlot", "thit", "tunt", "ql", "tl", "alnlen", "opens", "exts", "aln", "caln",
-	"qstrand", "tstrand", "mism", "ids", "diffs"};
+	"qstrand", "tstrand", "mism", "ids", "diffs", "evalue", "bits", "raw", "qlor", "qhir", "tlor", "thir"};
 
 OutputSink::OutputSink(const OutputOpts &O)
 {
@@ -239,7 +240,7 @@ void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM)
 	for (const AlignResult &AR : HM.m_Hits) {
 		AR.GetCompressedPath(cp);
 		appendf(m_bUC, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t", AR.GetTargetIndex(), AR.GetIQL(), AR.GetPctId(),
-		  AR.GetQueryStrand(), 0u, 0u);
+		  AR.GetQueryStrand(), AR.GetIQLo(), AR.GetITLo());
 		m_bUC += cp;
 		m_bUC += '\t';
 		m_bUC += AR.GetQueryLabel();
@@ -259,8 +260,12 @@ void OutputSink::OutputBlast6(const HitMgr &HM)
 		m_bB6 += AR.GetQueryLabel();
 		m_bB6 += '\t';
 		m_bB6 += AR.GetTargetLabel();
-		appendf(m_bB6, "\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t*\t*\n", AR.GetPctId(), AR.GetAlnLength(),
+		appendf(m_bB6, "\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u", AR.GetPctId(), AR.GetAlnLength(),
 		  AR.GetMismatchCount(), AR.GetGapOpenCount(), AR.GetIQLo1(), AR.GetIQHi1(), AR.GetTLo6(), AR.GetTHi6());
+		if (AR.IsLocal())
+			appendf(m_bB6, "\t%.2g\t%.1f\n", AR.GetEvalue(), AR.GetBitScore());
+		else
+			m_bB6 += "\t*\t*\n";
 	}
 	Flush(m_fB6, m_bB6, false);
 }
@@ -307,6 +312,13 @@ void OutputSink::OutputUser(const HitMgr &HM)
 			case UF_mism: appendf(m_bUser, "%u", AR.GetMismatchCount()); break;
 			case UF_ids: appendf(m_bUser, "%u", AR.GetIdCount()); break;
 			case UF_diffs: appendf(m_bUser, "%u", AR.GetDiffCount()); break;
+			case UF_evalue: appendf(m_bUser, "%.3g", AR.GetEvalue()); break;
+			case UF_bits: appendf(m_bUser, "%.0f", AR.GetBitScore()); break;
+			case UF_raw: appendf(m_bUser, "%.0f", AR.GetRawScore()); break;
+			case UF_qlor: appendf(m_bUser, "%u", AR.GetLoi()); break;
+			case UF_qhir: appendf(m_bUser, "%u", AR.GetHii()); break;
+			case UF_tlor: appendf(m_bUser, "%u", AR.GetLoj()); break;
+			case UF_thir: appendf(m_bUser, "%u", AR.GetHij()); break;
 			}
 		}
 		m_bUser += '\n';
@@ -322,7 +334,7 @@ void OutputSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
 }
 
 // ------------------------------------------------------------------ GpuSearcher
-GpuSearcher::GpuSearcher(int Device, const SeqDB &DB, const usb_params &P) : m_DB(DB)
+GpuSearcher::GpuSearcher(int Device, const SeqDB &DB, const usb_params &P) : m_DB(DB), m_P(P)
 {
 	CheckUsb(usb_index_create(Device, &P, DB.Letters(), DB.Offsets(), DB.GetSeqCount(), &m_Index), "usb_index_create");
 	CheckUsb(usb_searcher_create(m_Index, &P, &m_Searcher), "usb_searcher_create");
@@ -361,6 +373,11 @@ void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Cou
 			AR.m_Query.m_RevComp = hits[k].strand != 0;
 			m_DB.GetSI(hits[k].target, AR.m_Target);
 			AR.m_Runs = arena->data() + hits[k].run_off;
+			AR.m_Nucleo = m_P.is_nucleo != 0;
+			AR.m_Local = m_P.local != 0;
+			if (AR.m_Local)
+				CheckUsb(usb_local_evalue(m_Searcher, hits[k].raw, hits[k].ql, &AR.m_Evalue, &AR.m_BitScore),
+				  "usb_local_evalue");
 			HM.m_Hits.push_back(AR);
 		}
 	}
@@ -368,6 +385,35 @@ void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Cou
 }
 
 void GpuSearcher::ReleaseArenas() { m_Arenas.clear(); }
+
+bool GuessIsNucleo(const std::string &FastaFileName)
+{
+	FILE *f = fopen(FastaFileName.c_str(), "rb");
+	if (!f)
+		Die("Cannot open %s", FastaFileName.c_str());
+	std::vector<char> buf(1u << 20);
+	const size_t n = fread(buf.data(), 1, buf.size(), f);
+	fclose(f);
+	std::vector<char> letters;
+	bool header = false;
+	for (size_t i = 0; i < n; ++i) {
+		const char c = buf[i];
+		if (c == '>' && (i == 0 || buf[i - 1] == '\n'))
+			header = true;
+		else if (c == '\n')
+			header = false;
+		else if (!header && isalpha((unsigned char)c))
+			letters.push_back(c);
+	}
+	if (letters.empty())
+		return false;
+	unsigned N = 0;
+	for (unsigned k = 0; k < 100; ++k) {
+		const char c = letters[(size_t)k * letters.size() / 100];
+		N += strchr("ACGTUNacgtun", c) != nullptr;
+	}
+	return N > 80;
+}
 
 // ------------------------------------------------------------------ Search driver
 uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts)

@@ -73,21 +73,37 @@ public:
 	unsigned GetDiffCount() const { return m_Hit.mism + m_Hit.intgaps; }
 	unsigned GetPathLength() const;
 	unsigned GetAllGapCount() const { return m_Hit.intgaps + (GetPathLength() - m_Hit.alnlen); }
-	// global alignments: the HSP spans both sequences (alignresult.cpp:137-145)
-	unsigned GetIQLo1() const { return 1; }
-	unsigned GetIQHi1() const { return m_Hit.ql; }
-	unsigned GetITLo1() const { return 1; }
-	unsigned GetITHi1() const { return m_Hit.tl; }
+	// m_HSP: global alignments span both sequences (alignresult.cpp:137-145); local ones carry
+	// the aligned segment (alignresult.cpp:173), which starts and ends with an M column
+	bool m_Local = false, m_Nucleo = true;
+	double m_Evalue = -1.0, m_BitScore = 0.0; // estats.cpp:73-96, filled by the searcher for local hits
+	unsigned GetLoi() const { return m_Local ? m_Hit.first_mq : 0; }
+	unsigned GetHii() const { return m_Local ? m_Hit.last_mq : m_Hit.ql - 1; }
+	unsigned GetLoj() const { return m_Local ? m_Hit.first_mt : 0; }
+	unsigned GetHij() const { return m_Local ? m_Hit.last_mt : m_Hit.tl - 1; }
+	// arscorer.cpp:683-745 (no ORFs on this path): query coordinates are on the plus strand
+	unsigned GetIQLo() const { return m_Hit.strand ? m_Hit.ql - GetHii() - 1 : GetLoi(); }
+	unsigned GetIQHi() const { return m_Hit.strand ? m_Hit.ql - GetLoi() - 1 : GetHii(); }
+	unsigned GetITLo() const { return GetLoj(); }
+	unsigned GetITHi() const { return GetHij(); }
+	unsigned GetIQLo1() const { return GetIQLo() + 1; }
+	unsigned GetIQHi1() const { return GetIQHi() + 1; }
+	unsigned GetITLo1() const { return GetITLo() + 1; }
+	unsigned GetITHi1() const { return GetITHi() + 1; }
 	unsigned GetTLo6() const { return m_Hit.strand ? GetITHi1() : GetITLo1(); } // arscorer.cpp:748-808
 	unsigned GetTHi6() const { return m_Hit.strand ? GetITLo1() : GetITHi1(); }
+	double GetRawScore() const { return m_Local ? (double)m_Hit.raw : 0.0; }   // arscorer.cpp:87-103
+	double GetEvalue() const { return m_Local ? m_Evalue : -1.0; }             // arscorer.cpp:69-85
+	double GetBitScore() const { return m_Local ? m_BitScore : 0.0; }          // arscorer.cpp:105-120
+	bool IsLocal() const { return m_Local; }
 	unsigned GetQLoT() const { return m_Hit.first_mq; }
 	unsigned GetQHiT() const { return m_Hit.last_mq; }
 	unsigned GetTLoT() const { return m_Hit.first_mt; }
 	unsigned GetTHiT() const { return m_Hit.last_mt; }
 	unsigned GetQUnT() const { return m_Hit.ql - m_Hit.last_mq - 1; }
 	unsigned GetTUnT() const { return m_Hit.tl - m_Hit.last_mt - 1; }
-	char GetQueryStrand() const { return m_Hit.strand ? '-' : '+'; }
-	char GetTargetStrand() const { return '+'; }
+	char GetQueryStrand() const { return !m_Nucleo ? '.' : m_Hit.strand ? '-' : '+'; } // arscorer.cpp:156-176
+	char GetTargetStrand() const { return m_Nucleo ? '+' : '.'; }
 	void GetPath(std::string &Path) const;           // pathinfo.cpp:37-214
 	void GetCompressedPath(std::string &CPath) const; // comppath.cpp:7-48
 };
@@ -152,6 +168,7 @@ public:
 private:
 	std::vector<std::shared_ptr<std::vector<uint32_t>>> m_Arenas;
 	const SeqDB &m_DB;
+	usb_params m_P;
 	usb_index *m_Index = nullptr;
 	usb_searcher *m_Searcher = nullptr;
 };
@@ -173,6 +190,11 @@ struct ClusterOpts {
 
 // clusterfast.cpp:81 ClusterFast() with -threads 1 semantics; returns the number of clusters.
 uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
+
+// SeqDB::GetIsNucleo (seqdb.cpp:268-310): a database is nucleotide when more than 80 of 100 sampled
+// letters are ACGTUN (either case).  The reference samples with rand(); here the sample is an even
+// stride over the first sequences of the file (deterministic).
+bool GuessIsNucleo(const std::string &FastaFileName);
 
 // search.cpp:89 Search(): returns the number of queries with at least one hit.
 uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts);

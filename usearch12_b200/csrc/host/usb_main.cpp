@@ -4,6 +4,8 @@
 //   usearch12_b200 -usearch_global Q.fa -db DB.fa -id 0.97 -strand plus|both
 //        [-maxaccepts n] [-maxrejects n] [-uc f] [-blast6out f] [-userout f] [-userfields a+b+..]
 //        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]
+//   usearch12_b200 -usearch_local Q.fa -db DB.fa -id 0.5 -evalue 1e-5 [-strand plus|both for nt DBs]
+//        [-maxaccepts n] [-maxrejects n] [-xdrop_u x] [-xdrop_g x] [-lopen x] [-lext x] [-ka_dbsize x] ...
 // Options of the reference that this build does not implement are refused (Die), never ignored.
 #include <cstdlib>
 #include <cstring>
@@ -69,26 +71,53 @@ int main(int argc, char **argv)
 	}
 	SearchOpts O;
 	usb_default_params(&O.P, 0);
-	const std::string query = take("usearch_global", nullptr);
-	if (query.empty())
-		Die("No command: this build implements -usearch_global and -cluster_fast");
+	std::string query = take("usearch_global", nullptr);
+	const std::string lquery = take("usearch_local", nullptr);
+	if (query.empty() && lquery.empty())
+		Die("No command: this build implements -usearch_global, -usearch_local and -cluster_fast");
 	const std::string db = take("db", nullptr);
 	const std::string id = take("id", nullptr);
 	if (id.empty())
-		Die("-id option required"); // accepter.cpp: identity threshold is mandatory for usearch_global
+		Die("--id not set"); // udbusortedsearcher.cpp:99-100: mandatory for both commands
 	O.P.id = (float)atof(id.c_str());
+	bool nucleo = true;
+	if (!lquery.empty()) {
+		// searchcmd.cpp:42 cmd_usearch_local; the DB alphabet is guessed from its letters like
+		// SeqDB::GetIsNucleo (seqdb.cpp:181-199): more than 90 % of the first letters are ACGTUN
+		query = lquery;
+		const std::string ev = take("evalue", nullptr);
+		if (ev.empty())
+			Die("Must set -evalue"); // accepter.cpp / search.cpp: mandatory for local searches
+		nucleo = GuessIsNucleo(db);
+		usb_set_local(&O.P, nucleo ? 1 : 0, (float)atof(ev.c_str()));
+		O.P.xdrop_u = (float)atof(take("xdrop_u", "16").c_str());
+		O.P.xdrop_g = (float)atof(take("xdrop_g", "32").c_str());
+		const std::string lo = take("lopen", nullptr), le = take("lext", nullptr);
+		if (lo.empty() != le.empty())
+			Die("Must set both --lopen and --lext"); // alnparams.cpp:362-366
+		if (!lo.empty()) {
+			if (atof(lo.c_str()) < 0.0 || atof(le.c_str()) < 0.0)
+				Die("Invalid --lopen/--lext, gap penalties must be >= 0");
+			O.P.lopen = -(float)atof(lo.c_str());
+			O.P.lext = -(float)atof(le.c_str());
+		}
+		O.P.ka_dbsize = (float)atof(take("ka_dbsize", "1e9").c_str());
+		const std::string hw = take("hspw", nullptr);
+		if (!hw.empty())
+			O.P.hspw = (uint32_t)atoi(hw.c_str());
+	}
 	const std::string strand = take("strand", nullptr);
-	if (strand != "plus" && strand != "both")
+	if (nucleo && strand != "plus" && strand != "both")
 		Die("Must specify -strand plus or both with nt db"); // search.cpp:23-34
-	O.P.strand_both = strand == "both";
+	O.P.strand_both = nucleo && strand == "both";
 	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", "1").c_str());
 	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", "32").c_str());
 	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
 	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
-	const std::string dbmask = take("dbmask", "fastnucleo");
-	if (dbmask != "fastnucleo" && dbmask != "none")
-		Die("-dbmask %s not supported (fastnucleo|none)", dbmask.c_str());
-	O.P.dbmask = dbmask == "fastnucleo";
+	const std::string dbmask = take("dbmask", nucleo ? "fastnucleo" : "fastamino");
+	if (dbmask != (nucleo ? "fastnucleo" : "fastamino") && dbmask != "none")
+		Die("-dbmask %s not supported (%s|none)", dbmask.c_str(), nucleo ? "fastnucleo" : "fastamino");
+	O.P.dbmask = dbmask != "none";
 	O.Out.uc = take("uc", nullptr);
 	O.Out.blast6out = take("blast6out", nullptr);
 	O.Out.userout = take("userout", nullptr);
