@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.txt
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 600 python bench.py --no-cpu-baseline --steps 2 > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; rc=$?
+  python - "$name" $rc <<'PY'
+import json,sys
+f="gpurun_out/bench_%s.json"%sys.argv[1]
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(sys.argv[1], "k_rank %.1f ms"%d["kernels_ms_per_step"]["k_rank"], "GB/s %.0f"%d["roofline"]["other"]["k_rank_GBps"], "hits", d["config"]["hit_rate"])
+except Exception as e:
+    print(sys.argv[1], "FAILED rc", sys.argv[2], e)
+PY
+  grep "phase cycles" gpurun_out/bench_$name.err | tail -1
+}
+run dflt
+run dflt_p USB_RANK_PROF=1
+run one_p USB_RANK_ONE_CTA=1 USB_RANK_PROF=1

@@ -224,7 +224,7 @@ struct usb_searcher {
 	usb_params P;
 	DevParams D;
 	int num_sms = 0;
-	size_t smem_optin = 0;
+	size_t smem_optin = 0, smem_per_sm = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint64_t launches = 0;
@@ -241,6 +241,7 @@ struct usb_searcher {
 	DevBuf<DevCounters> d_ctr;
 	DevBuf<uint8_t> d_slab, d_uarena;
 	size_t rank_smem_set = 0;
+	bool rank_two = false;
 	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
 	bool bigsmem_set = false;
 	// -usearch_local
@@ -545,6 +546,7 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 	CK(cudaGetDeviceProperties(&prop, ix->device));
 	s->num_sms = prop.multiProcessorCount;
 	s->smem_optin = prop.sharedMemPerBlockOptin;
+	s->smem_per_sm = prop.sharedMemPerMultiprocessor;
 	CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	for (auto &e : s->ev)
 		CK(cudaEventCreate(&e));
@@ -756,21 +758,36 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 	a.u_out = want_u ? s->d_uout.p : nullptr;
 	a.aux = s->d_aux.p;
 	const bool wide = s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > 255;
-	a.seg_narrow = rank_segment(N, false);
-	a.seg_wide = rank_segment(N, true);
 	a.rec_cap = wide ? RANK_REC_WIDE : RANK_REC_NARROW;
+	a.dedupe_words = (uint32_t)(dedupe_bytes / 4);
 	a.bump_d = s->P.bump / 100.0;
 	a.ctr = s->d_ctr.p;
-	const size_t smem = rank_smem_bytes(N, wide, dedupe_bytes, a.rec_cap, &a.u_bytes);
+	// Two CTAs of 512 threads per SM when their shared memory fits twice (each CTA also costs
+	// 1 KB of system shared memory): the serial scan/sort tail of one query then overlaps the
+	// posting walk of another.  Else one CTA of 1024 threads.
+	uint32_t threads = RANK_THREADS_2;
+	size_t smem = rank_smem_bytes(N, wide, dedupe_bytes, a.rec_cap, threads, &a.u_bytes);
+	const bool two = 2 * (smem + 1024) <= s->smem_per_sm && !getenv("USB_RANK_ONE_CTA");
+	if (!two) {
+		threads = RANK_THREADS;
+		smem = rank_smem_bytes(N, wide, dedupe_bytes, a.rec_cap, threads, &a.u_bytes);
+	}
+	a.seg_narrow = rank_segment(N, false, threads);
+	a.seg_wide = rank_segment(N, true, threads);
 	if (smem > s->smem_optin)
 		return fail(USB_ELIMIT,
 		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
 		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
-	if (smem > s->rank_smem_set) {
-		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		s->rank_smem_set = smem;
+	a.prof = getenv("USB_RANK_PROF") ? 1 : 0; // measurement knob: phase cycles to stderr
+	if (smem > s->rank_smem_set || two != s->rank_two) {
+		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, s->rank_smem_set)));
+		// two CTAs only fit with the whole L1/shared array carved out as shared memory
+		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributePreferredSharedMemoryCarveout,
+		  two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault));
+		s->rank_smem_set = std::max(smem, s->rank_smem_set);
+		s->rank_two = two;
 	}
-	k_rank<<<n_jobs, RANK_THREADS, smem, s->stream>>>(a);
+	k_rank<<<n_jobs, threads, smem, s->stream>>>(a);
 	CK(cudaGetLastError());
 	++s->launches;
 	return 0;
@@ -1078,6 +1095,14 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		s->last_hits = c.n_hits;
 		s->last_runs = c.n_runs;
 		s->last_postings = c.postings;
+		if (getenv("USB_RANK_PROF") && s->n_jobs) {
+			const char *nm[13] = {"zero", "words", "walk", "replay", "filter_tail", "emit", "f_count", "f_scan", "f_write",
+			  "r_max", "r_scan", "r_collect", "sort"};
+			fprintf(stderr, "k_rank phase cycles per job:");
+			for (int i = 0; i < 13; ++i)
+				fprintf(stderr, " %s %.0f", nm[i], (double)c.prof[i] / s->n_jobs);
+			fprintf(stderr, "\n");
+		}
 		break;
 	}
 	if (ms) {

@@ -52,6 +52,7 @@ struct DevCounters {
 	unsigned long long postings; // UDB postings walked by k_rank
 	uint32_t job_rank;           // job cursor of k_rank_big
 	uint32_t pad;
+	unsigned long long prof[16];  // k_rank phase cycles, summed over CTAs (only with RankArgs.prof)
 };
 
 // The UDB index as the kernels see it: a few CSR segments over consecutive target ranges

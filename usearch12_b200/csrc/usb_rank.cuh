@@ -9,24 +9,37 @@
 //   a6  CountSortOrderDesc + NextValue/2    countsort.cpp:6-108
 //
 // Design: the per-target counters live in shared memory (1 byte per target when the query has
-// <= 255 word positions, 2 bytes otherwise), so U never touches HBM.  Posting rows start on
-// 16-byte boundaries and are streamed with 128-bit loads, four in flight per lane (64 KB in
-// flight per SM), and counted with shared-memory atomics on packed 32-bit words.
-// The two order-dependent filters are evaluated exactly from the strict prefix maxima of U
-// ("records"): records are few, so one thread replays the
-// threshold evolution over them; every thread then filters its own contiguous target segment
-// against the threshold in force there, four (two) counters per instruction with the byte
-// (halfword) SIMD compares.  Survivors (TopOrder) are usually a few hundred: they are collected
-// unordered and bitonic-sorted by (U descending, target ascending), which is the reference's
-// stable counting-sort order.  Only when more than RANK_KCAP targets survive does the kernel fall
-// back to a radix-select of the first k_max of that order (the Terminator can never look
-// further than maxaccepts+maxrejects-1 candidates).
+// <= 255 word positions, 2 bytes otherwise), so U never touches HBM.
+//   * Word phase: one thread per query position; the threads that discover a unique word fetch
+//     its row descriptor (offset, size) at once, so those loads overlap.
+//   * Posting walk: warps draw whole rows from a shared cursor; rows start on 16-byte boundaries
+//     and are streamed with 128-bit loads that bypass L1 allocation, four in flight per lane,
+//     and counted with shared-memory atomics on packed 32-bit words.  Measured on B200 the walk
+//     itself runs at the HBM roofline (6.7 TB/s with the L2 hits); what is left is the tail.
+//   * Tail: the two order-dependent filters are evaluated exactly from the strict prefix maxima
+//     of U ("records").  Segment maxima -> block prefix-max scan ->
+//     the few threads whose segment holds records count and place them by a block scan (target
+//     order, no sort); one thread replays the SetTopBump threshold evolution over them; every
+//     thread then filters its own segment, 16 counters per 128-bit shared load, skipping
+//     segments and words whose largest counter is below the counting-sort cut-off (16-bit SIMD
+//     max is native on sm_100a, the 8-bit forms are emulated); survivors are placed by a
+//     block scan.  The Terminator never looks further than maxaccepts+maxrejects-1 = 32
+//     candidates, so the survivors are not sorted: every warp sorts 32 keys in registers and a
+//     tree of bitonic merges keeps the 32 smallest (U descending, target ascending = the
+//     reference's stable counting-sort order).  More than RANK_KCAP survivors: radix-select.
+//   * The tail is a chain of short serial sections (about a third of a query's time with one
+//     CTA per SM).  The scratch of the word phase (bitmap, row descriptors) and of the tail
+//     (records, survivor keys) share one region, which lets two CTAs of 512 threads live on one
+//     SM at 100 000 targets: one CTA's tail overlaps the other's posting walk.
 #pragma once
 #include "usb_dev.cuh"
 
 namespace usb {
 
-#define RANK_THREADS 1024
+#define RANK_THREADS 1024      // k_rank_big, and k_rank when only one CTA fits per SM
+#define RANK_THREADS_2 512     // k_rank when two CTAs fit per SM
+#define RANK_VEC 4u            // 128-bit posting loads in flight per lane
+#define RANK_CHUNK (128u * RANK_VEC) // postings per warp iteration of the walk
 #define RANK_KCAP 1024         // max candidates materialised per query
 #define RANK_REC_NARROW 256
 #define RANK_REC_WIDE 2048
@@ -48,20 +61,47 @@ struct RankArgs {
 	uint32_t *u_out;           // optional: n_jobs * n_seq
 	uint32_t seg_narrow, seg_wide; // targets per thread segment (bank-conflict-free strides)
 	uint32_t u_bytes;          // shared bytes reserved for the counters
+	uint32_t dedupe_words;     // 32-bit words of the word bitmap (nt) / hash set (aa)
 	uint32_t rec_cap;
 	double bump_d;             // BumpPct / 100.0 ; 0 = no bump
+	uint32_t prof;             // 1 = accumulate phase cycles in ctr->prof (measurement)
 	DevCounters *ctr;
 };
 
 struct RankShared {
 	uint32_t n_rows, row_cur, n_rec, n_chg;
 	uint32_t maxv, minv, total, vstar, m_eq, n_sel, bstar, above;
-	uint32_t take_all, n_post, n_surv, pad2;
+	uint32_t pad3, n_post, n_surv, pad2;
 	uint32_t warp_tmp[32];
-	uint32_t hist[256];
-	uint32_t rows[RANK_THREADS];
-	unsigned long long sel[RANK_KCAP];
+	long long pt;              // phase timer (measurement)
 };
+
+// The scratch region behind the counters, used by two phases in turn.
+struct RankScratch {
+	// word phase + posting walk
+	uint32_t *bitmap;          // dedupe_words
+	uint32_t *r_off;           // blockDim.x: row start / 4 (one segment) or the word itself (several segments)
+	uint32_t *r_size;          // blockDim.x
+	// ranking phase
+	unsigned long long *sel;   // RANK_KCAP
+	uint32_t *rec_pos, *rec_val, *chg_pos, *chg_minu; // rec_cap each
+	uint32_t *hist;            // 256
+};
+
+__device__ __forceinline__ RankScratch rank_scratch(uint8_t *X, uint32_t dedupe_words, uint32_t rec_cap)
+{
+	RankScratch r;
+	r.bitmap = (uint32_t *)X;
+	r.r_off = r.bitmap + dedupe_words;
+	r.r_size = r.r_off + blockDim.x;
+	r.sel = (unsigned long long *)X;
+	r.rec_pos = (uint32_t *)(r.sel + RANK_KCAP);
+	r.rec_val = r.rec_pos + rec_cap;
+	r.chg_pos = r.rec_val + rec_cap;
+	r.chg_minu = r.chg_pos + rec_cap;
+	r.hist = r.chg_minu + rec_cap;
+	return r;
+}
 
 // exclusive prefix maximum over the CTA in thread order
 __device__ __forceinline__ uint32_t block_excl_scan_max(uint32_t v, uint32_t *warp_tmp)
@@ -142,18 +182,91 @@ __device__ __forceinline__ void u_inc(uint32_t *U32, uint32_t t)
 		atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
 }
 
+// largest counter of a packed word; 16-bit SIMD max is native on sm_100a, the 8-bit forms are not
+template <bool WIDE>
+__device__ __forceinline__ uint32_t word_max(uint32_t word)
+{
+	if (!WIDE)
+		word = __vmaxu2(word & 0x00ff00ffu, (word >> 8) & 0x00ff00ffu);
+	return max(word & 0xffffu, word >> 16);
+}
+
+// f(k, word) for the 32-bit counter words of the 16-byte chunks [c0, c1): one 128-bit shared load
+// per four words
+template <class F>
+__device__ __forceinline__ void for_words(const uint4 *U128, uint32_t c0, uint32_t c1, F f)
+{
+	for (uint32_t c = c0; c < c1; ++c) {
+		const uint4 v = U128[c];
+		f(4 * c, v.x);
+		f(4 * c + 1, v.y);
+		f(4 * c + 2, v.z);
+		f(4 * c + 3, v.w);
+	}
+}
+
 // Survivor test for target t with count u (u > 0): SetTopBump threshold in force at t (changes
 // take effect after the record position that caused them) and the counting-sort cut-off.
 struct KeepCursor {
 	const uint32_t *chg_pos, *chg_minu;
 	uint32_t n_chg, minv, cur;
+	uint32_t mu, next;   // threshold in force and position of the next change, kept in registers
+	__device__ __forceinline__ void reset()
+	{
+		cur = 0;
+		mu = 1;
+		next = n_chg ? chg_pos[0] : 0xffffffffu;
+	}
+	// targets must be visited in ascending order between two reset()s
 	__device__ __forceinline__ uint32_t minu(uint32_t t)
 	{
-		while (cur < n_chg && chg_pos[cur] < t)
+		while (next < t) {
+			mu = chg_minu[cur];
 			++cur;
-		return cur == 0 ? 1u : chg_minu[cur - 1];
+			next = cur < n_chg ? chg_pos[cur] : 0xffffffffu;
+		}
+		return mu;
 	}
 	__device__ __forceinline__ bool keep(uint32_t t, uint32_t u) { return u >= minu(t) && u >= minv; }
+};
+
+// Both filters on one packed counter word: SetTopBump threshold in force at each target (KeepCursor)
+// and the counting-sort cut-off.  Words must be visited in ascending order after a reset().
+template <bool WIDE>
+struct SegFilter {
+	KeepCursor kc;
+	uint32_t floor_thr; // max(NextValue / 2, 1)
+	static constexpr uint32_t PER = WIDE ? 2 : 4, LANE_BITS = WIDE ? 16 : 8, LANE_MAX = WIDE ? 0xffffu : 0xffu;
+	__device__ __forceinline__ void reset() { kc.reset(); }
+	__device__ __forceinline__ static uint32_t lane_of(uint32_t word, uint32_t b) { return (word >> (b * LANE_BITS)) & LANE_MAX; }
+	// bit b set = counter b of word k survives
+	__device__ __forceinline__ uint32_t mask(uint32_t k, uint32_t word)
+	{
+		if (word_max<WIDE>(word) < floor_thr)
+			return 0u;
+		const uint32_t t = k * PER;
+		uint32_t thr = max(kc.minu(t), floor_thr);
+		uint32_t m = 0;
+		if (kc.next >= t + PER - 1) { // no change takes effect inside the word: one threshold
+			// x >= thr  <=>  max(x, thr) == x, two 16-bit lanes at a time (native SIMD max)
+			const uint32_t thr2 = thr * 0x00010001u;
+			if (WIDE) {
+				const uint32_t d = __vmaxu2(word, thr2) ^ word;
+				m = ((d & 0xffffu) ? 0u : 1u) | ((d >> 16) ? 0u : 2u);
+			} else {
+				const uint32_t lo = word & 0x00ff00ffu, hi = (word >> 8) & 0x00ff00ffu;
+				const uint32_t dl = __vmaxu2(lo, thr2) ^ lo, dh = __vmaxu2(hi, thr2) ^ hi;
+				m = ((dl & 0xffffu) ? 0u : 1u) | ((dh & 0xffffu) ? 0u : 2u) | ((dl >> 16) ? 0u : 4u) | ((dh >> 16) ? 0u : 8u);
+			}
+			return m;
+		}
+		for (uint32_t b = 0; b < PER; ++b) {
+			thr = max(kc.minu(t + b), floor_thr);
+			if (lane_of(word, b) >= thr)
+				m |= 1u << b;
+		}
+		return m;
+	}
 };
 
 __device__ __forceinline__ unsigned long long rank_key(uint32_t u, uint32_t t)
@@ -168,12 +281,12 @@ __device__ void block_sort_keys(unsigned long long *sel, uint32_t n)
 	uint32_t P2 = 1;
 	while (P2 < n)
 		P2 <<= 1;
-	for (uint32_t i = n + tid; i < P2; i += RANK_THREADS)
+	for (uint32_t i = n + tid; i < P2; i += blockDim.x)
 		sel[i] = ~0ull;
 	__syncthreads();
 	for (uint32_t k = 2; k <= P2; k <<= 1)
 		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = tid; i < P2; i += RANK_THREADS) {
+			for (uint32_t i = tid; i < P2; i += blockDim.x) {
 				const uint32_t x = i ^ j;
 				if (x > i) {
 					const unsigned long long A = sel[i], B = sel[x];
@@ -187,32 +300,102 @@ __device__ void block_sort_keys(unsigned long long *sel, uint32_t n)
 		}
 }
 
-// Rare path: more than RANK_KCAP survivors.  Radix-select the k_max-th largest surviving count,
-// take ties at the cut in ascending target order (block scan), leave the selection in S.sel.
+// ascending bitonic sort of 32 keys, one per lane
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long key, uint32_t lane)
+{
+#pragma unroll
+	for (uint32_t k = 2; k <= 32; k <<= 1)
+#pragma unroll
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			const unsigned long long o = __shfl_xor_sync(USB_FULL, key, j);
+			const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+			key = (lower == up) ? min(key, o) : max(key, o);
+		}
+	return key;
+}
+
+// the 32 smallest keys of two ascending runs, ascending: a[i] vs b[31 - i] leaves a bitonic run
+__device__ __forceinline__ unsigned long long warp_merge32(unsigned long long a, unsigned long long b_rev, uint32_t lane)
+{
+	unsigned long long key = min(a, b_rev);
+#pragma unroll
+	for (uint32_t j = 16; j > 0; j >>= 1) {
+		const unsigned long long o = __shfl_xor_sync(USB_FULL, key, j);
+		key = (lane & j) == 0 ? min(key, o) : max(key, o);
+	}
+	return key;
+}
+
+// The 32 smallest keys of sel[0..n) (n <= RANK_KCAP) in ascending order, left in sel[0..32);
+// the number of warps must be a power of two.  Every warp sorts its runs of 32 keys in registers
+// (shuffles only) and keeps the smallest 32; a tree of bitonic merges over the warps, exchanged
+// through shared memory, does the rest.
+__device__ void block_top32(unsigned long long *sel, uint32_t n)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+	// warp w owns runs w * per .. w * per + per - 1 (consecutive, so that padding runs are last)
+	const uint32_t per = (RANK_KCAP / 32) / nw;
+	unsigned long long key = ~0ull;
+	for (uint32_t r = 0; r < per; ++r) {
+		const uint32_t i0 = (w * per + r) * 32;
+		if (i0 >= n)
+			break;
+		unsigned long long k2 = i0 + lane < n ? sel[i0 + lane] : ~0ull;
+		k2 = warp_sort32(k2, lane);
+		key = r == 0 ? k2 : warp_merge32(key, __shfl_sync(USB_FULL, k2, 31 - lane), lane);
+	}
+	__syncthreads(); // every key is in a register now: sel becomes the exchange buffer
+	for (uint32_t d = 1; d * per * 32 < n; d <<= 1) { // runs starting at or after n are all padding
+		const uint32_t role = w & (2 * d - 1);
+		if (role == d)
+			sel[(w - d) * 32 + lane] = key;
+		__syncthreads();
+		if (role == 0 && (w + d) * per * 32 < n) // the partner is not all padding
+			key = warp_merge32(key, sel[w * 32 + 31 - lane], lane);
+		__syncthreads();
+	}
+	if (w == 0)
+		sel[lane] = key;
+	__syncthreads();
+}
+
+// More than RANK_KCAP survivors (a few percent of the queries: reads without a close target keep
+// every target above a low cut-off).  Radix-select the k_max-th largest surviving count, take
+// ties at the cut in ascending target order (block scan), leave the selection in X.sel.
 template <bool WIDE>
-__device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const uint8_t *U, KeepCursor kc, uint32_t t0,
-  uint32_t t1)
+__device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const RankScratch &X, const uint4 *U128,
+  SegFilter<WIDE> F, uint32_t c0, uint32_t c1, bool any)
 {
 	const uint32_t tid = threadIdx.x;
-	for (uint32_t i = tid; i < 256; i += RANK_THREADS)
-		S.hist[i] = 0;
+	constexpr uint32_t PER = WIDE ? 2 : 4;
+	// f(u, t) for every survivor of this thread's segment, ascending targets
+	auto for_survivors = [&](auto f) {
+		if (!any)
+			return;
+		F.reset();
+		for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) {
+			uint32_t m = F.mask(k, word);
+			while (m) {
+				const uint32_t b = (uint32_t)__ffs(m) - 1;
+				m &= m - 1;
+				f(SegFilter<WIDE>::lane_of(word, b), k * PER + b);
+			}
+		});
+	};
+	for (uint32_t i = tid; i < 256; i += blockDim.x)
+		X.hist[i] = 0;
 	if (tid == 0)
 		S.n_sel = 0;
 	__syncthreads();
-	kc.cur = 0;
-	for (uint32_t t = t0; t < t1; ++t) {
-		const uint32_t u = u_get<WIDE>(U, t);
-		if (u && kc.keep(t, u))
-			atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
-	}
+	for_survivors([&](uint32_t u, uint32_t) { atomicAdd(&X.hist[WIDE ? (u >> 8) : u], 1u); });
 	__syncthreads();
 	if (tid == 0) {
 		uint32_t cum = 0;
 		for (int b = 255; b >= 0; --b) {
-			cum += S.hist[b];
+			cum += X.hist[b];
 			if (cum >= a.k_max) {
 				S.bstar = (uint32_t)b;
-				S.above = cum - S.hist[b];
+				S.above = cum - X.hist[b];
 				break;
 			}
 		}
@@ -223,24 +406,22 @@ __device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const uin
 	}
 	__syncthreads();
 	if (WIDE) {
-		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
-			S.hist[i] = 0;
+		for (uint32_t i = tid; i < 256; i += blockDim.x)
+			X.hist[i] = 0;
 		__syncthreads();
-		kc.cur = 0;
 		const uint32_t bstar = S.bstar;
-		for (uint32_t t = t0; t < t1; ++t) {
-			const uint32_t u = u_get<WIDE>(U, t);
-			if (u && (u >> 8) == bstar && kc.keep(t, u))
-				atomicAdd(&S.hist[u & 255], 1u);
-		}
+		for_survivors([&](uint32_t u, uint32_t) {
+			if ((u >> 8) == bstar)
+				atomicAdd(&X.hist[u & 255], 1u);
+		});
 		__syncthreads();
 		if (tid == 0) {
 			uint32_t cum = S.above;
 			for (int b = 255; b >= 0; --b) {
-				cum += S.hist[b];
+				cum += X.hist[b];
 				if (cum >= a.k_max) {
 					S.vstar = (S.bstar << 8) | (uint32_t)b;
-					S.m_eq = a.k_max - (cum - S.hist[b]);
+					S.m_eq = a.k_max - (cum - X.hist[b]);
 					break;
 				}
 			}
@@ -249,35 +430,55 @@ __device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const uin
 	}
 	const uint32_t vstar = S.vstar, m_eq = S.m_eq;
 	uint32_t c_eq = 0;
-	kc.cur = 0;
-	for (uint32_t t = t0; t < t1; ++t) {
-		const uint32_t u = u_get<WIDE>(U, t);
-		if (u == vstar && u && kc.keep(t, u))
-			++c_eq;
-	}
+	for_survivors([&](uint32_t u, uint32_t) { c_eq += u == vstar ? 1u : 0u; });
 	uint32_t eq_rank = block_excl_scan_sum(c_eq, S.warp_tmp);
-	kc.cur = 0;
-	for (uint32_t t = t0; t < t1; ++t) {
-		const uint32_t u = u_get<WIDE>(U, t);
-		if (!u || !kc.keep(t, u))
-			continue;
+	for_survivors([&](uint32_t u, uint32_t t) {
 		bool take = u > vstar;
 		if (!take && u == vstar)
 			take = (eq_rank++ < m_eq);
 		if (take) {
 			const uint32_t slot = atomicAdd(&S.n_sel, 1u);
 			if (slot < RANK_KCAP)
-				S.sel[slot] = rank_key(u, t);
+				X.sel[slot] = rank_key(u, t);
 		}
-	}
+	});
 	__syncthreads();
 }
 
+// Counts vector j of a chunk with `rem` postings left in its row (rows are padded to whole
+// vectors, the pad entries of the ragged last vector are skipped).
 template <bool WIDE>
-__device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t *U, uint32_t *bitmap,
-  uint32_t *rec_pos, uint32_t *rec_val, uint32_t *chg_pos, uint32_t *chg_minu)
+__device__ __forceinline__ void vec_count(uint32_t *U32, const uint4 &x, uint32_t j, uint32_t rem, uint32_t lane)
 {
-	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t b = 4 * (lane + 32 * j);
+	if (b + 3 < rem) {
+		u_inc<WIDE>(U32, x.x); u_inc<WIDE>(U32, x.y); u_inc<WIDE>(U32, x.z); u_inc<WIDE>(U32, x.w);
+	} else if (b < rem) {
+		u_inc<WIDE>(U32, x.x);
+		if (b + 1 < rem) u_inc<WIDE>(U32, x.y);
+		if (b + 2 < rem) u_inc<WIDE>(U32, x.z);
+	}
+}
+
+// Posting rows are streamed once per query: they are not allocated in L1 (most of the unified
+// L1/shared memory array is carved out for the counters).
+__device__ __forceinline__ void vec_load(uint4 &x, const uint4 *v4, uint32_t j, uint32_t rem, uint32_t lane)
+{
+	if (4 * (lane + 32 * j) < rem) {
+#ifdef USB_RANK_LDG
+		x = __ldg(v4 + lane + 32 * j);
+#else
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		             : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+		             : "l"(v4 + lane + 32 * j));
+#endif
+	}
+}
+
+template <bool WIDE>
+__device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t *U, const RankScratch &X)
+{
+	const uint32_t tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
 	const uint32_t N = a.n_seq;
 	const uint32_t WLEN = a.P.word_length;
 	const uint32_t qi = job / a.strands, strand = job % a.strands;
@@ -285,30 +486,41 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
 	const uint8_t *Q = a.q + q0;
 	uint32_t *U32 = (uint32_t *)U;
+	uint32_t *bitmap = X.bitmap;
+	const bool one_seg = a.ix.n_seg == 1;
+#define USB_PHASE(i)                                               \
+	if (a.prof && tid == 0) {                                      \
+		const long long now = clock64();                           \
+		atomicAdd(&a.ctr->prof[i], (unsigned long long)(now - S.pt)); \
+		S.pt = now;                                                \
+	}
+	if (a.prof && tid == 0)
+		S.pt = clock64();
 
 	// ---- zero shared state (u_bytes is a multiple of 16)
 	{
 		uint4 *U128 = (uint4 *)U;
 		const uint32_t n128 = ((WIDE ? 2 * N : N) + 15) / 16;
-		for (uint32_t i = tid; i < n128; i += RANK_THREADS)
+		for (uint32_t i = tid; i < n128; i += NT)
 			U128[i] = make_uint4(0, 0, 0, 0);
 		// nt: bitmap over the 4^w slots; aa: open-addressing hash set of the query's words
-		const uint32_t nbm = a.P.alpha == 4 ? a.P.slots / 32 : a.P.hash_cap;
 		const uint32_t bm0 = a.P.alpha == 4 ? 0u : 0xffffffffu;
-		for (uint32_t i = tid; i < nbm; i += RANK_THREADS)
+		for (uint32_t i = tid; i < a.dedupe_words; i += NT)
 			bitmap[i] = bm0;
 		if (tid == 0) {
 			S.n_rows = 0; S.row_cur = 0; S.n_rec = 0; S.n_chg = 0; S.n_sel = 0; S.n_post = 0; S.n_surv = 0;
 		}
 	}
 	__syncthreads();
+	USB_PHASE(0)
 
 	// ---- a1/a2/a4: words -> unique rows -> posting walk
 	const uint32_t npos = L >= WLEN ? L - WLEN + 1 : 0;
-	for (uint32_t base = 0; base < npos; base += RANK_THREADS) {
+	for (uint32_t base = 0; base < npos; base += NT) {
 		const uint32_t p = base + tid;
 		if (p < npos) {
 			uint32_t word = 0, bad = 0;
+			bool fresh = false;
 			if (a.P.alpha == 4) {
 				for (uint32_t i = 0; i < WLEN; ++i) {
 					uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - (p + i)]] : (uint32_t)Q[p + i];
@@ -319,8 +531,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				if (!bad) {
 					uint32_t bit = 1u << (word & 31);
 					uint32_t old = atomicOr(&bitmap[word >> 5], bit);
-					if (!(old & bit))
-						S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+					fresh = !(old & bit);
 				}
 			} else {
 				for (uint32_t i = 0; i < WLEN; ++i) {
@@ -334,7 +545,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 					for (;;) {
 						const uint32_t old = atomicCAS(&bitmap[h], 0xffffffffu, word);
 						if (old == 0xffffffffu) {
-							S.rows[atomicAdd(&S.n_rows, 1u)] = word;
+							fresh = true;
 							break;
 						}
 						if (old == word)
@@ -343,46 +554,86 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 					}
 				}
 			}
+			if (fresh) {
+				if (one_seg) {
+					// row descriptor now: the loads of all unique words of the pass overlap
+					const SegDesc &seg = a.ix.seg[0];
+					const uint32_t size = __ldg(seg.row_size + word);
+					const uint64_t off = __ldg(seg.row_off + word);
+					if (size) {
+						const uint32_t idx = atomicAdd(&S.n_rows, 1u);
+						X.r_off[idx] = (uint32_t)(off >> 2);
+						X.r_size[idx] = size;
+					}
+				} else
+					X.r_off[atomicAdd(&S.n_rows, 1u)] = word;
+			}
 		}
 		__syncthreads();
 		const uint32_t n_rows = S.n_rows;
-		uint32_t my_post = 0;
-		for (;;) {
-			uint32_t r = 0;
-			if (lane == 0)
-				r = atomicAdd(&S.row_cur, 1u);
-			r = __shfl_sync(USB_FULL, r, 0);
-			if (r >= n_rows)
-				break;
-			const uint32_t word = S.rows[r];
-			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
-				const SegDesc &seg = a.ix.seg[sg];
-				const uint32_t size = seg.row_size[word];
-				if (size == 0)
-					continue;
-				const uint32_t *row = seg.postings + seg.row_off[word];
-				const uint4 *v4 = (const uint4 *)row;
-				const uint32_t nvec = size >> 2;
-				my_post += size;
-				uint32_t i = lane;
-				for (; i + 96 < nvec; i += 128) {
-					const uint4 x0 = __ldg(v4 + i), x1 = __ldg(v4 + i + 32), x2 = __ldg(v4 + i + 64), x3 = __ldg(v4 + i + 96);
-					u_inc<WIDE>(U32, x0.x); u_inc<WIDE>(U32, x0.y); u_inc<WIDE>(U32, x0.z); u_inc<WIDE>(U32, x0.w);
-					u_inc<WIDE>(U32, x1.x); u_inc<WIDE>(U32, x1.y); u_inc<WIDE>(U32, x1.z); u_inc<WIDE>(U32, x1.w);
-					u_inc<WIDE>(U32, x2.x); u_inc<WIDE>(U32, x2.y); u_inc<WIDE>(U32, x2.z); u_inc<WIDE>(U32, x2.w);
-					u_inc<WIDE>(U32, x3.x); u_inc<WIDE>(U32, x3.y); u_inc<WIDE>(U32, x3.z); u_inc<WIDE>(U32, x3.w);
+		if (one_seg) {
+			const uint32_t size = tid < n_rows ? X.r_size[tid] : 0;
+			const uint32_t sz = __reduce_add_sync(USB_FULL, size);
+			if (lane == 0 && sz)
+				atomicAdd(&S.n_post, sz);
+			USB_PHASE(1)
+			const uint4 *P4 = (const uint4 *)a.ix.seg[0].postings;
+			// whole rows per warp, drawn from a shared cursor
+			for (;;) {
+				uint32_t r = 0;
+				if (lane == 0)
+					r = atomicAdd(&S.row_cur, 1u);
+				r = __shfl_sync(USB_FULL, r, 0);
+				if (r >= n_rows)
+					break;
+				const uint32_t size = X.r_size[r];
+				const uint4 *v4 = P4 + X.r_off[r];
+				for (uint32_t done = 0; done < size; done += RANK_CHUNK) {
+					const uint32_t rem = min(size - done, RANK_CHUNK);
+					uint4 x[RANK_VEC];
+#pragma unroll
+					for (uint32_t j = 0; j < RANK_VEC; ++j)
+						vec_load(x[j], v4 + done / 4, j, rem, lane);
+#pragma unroll
+					for (uint32_t j = 0; j < RANK_VEC; ++j)
+						vec_count<WIDE>(U32, x[j], j, rem, lane);
 				}
-				for (; i < nvec; i += 32) {
-					const uint4 x = __ldg(v4 + i);
-					u_inc<WIDE>(U32, x.x); u_inc<WIDE>(U32, x.y); u_inc<WIDE>(U32, x.z); u_inc<WIDE>(U32, x.w);
-				}
-				if (lane < (size & 3))
-					u_inc<WIDE>(U32, __ldg(row + 4 * nvec + lane));
 			}
+		} else {
+			// several index segments (a growing cluster_fast database): whole rows per warp
+			uint32_t my_post = 0;
+			for (;;) {
+				uint32_t r = 0;
+				if (lane == 0)
+					r = atomicAdd(&S.row_cur, 1u);
+				r = __shfl_sync(USB_FULL, r, 0);
+				if (r >= n_rows)
+					break;
+				const uint32_t word = X.r_off[r];
+				for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
+					const SegDesc &seg = a.ix.seg[sg];
+					const uint32_t size = seg.row_size[word];
+					if (size == 0)
+						continue;
+					const uint4 *v4 = (const uint4 *)(seg.postings + seg.row_off[word]);
+					my_post += size;
+					for (uint32_t done = 0; done < size; done += (RANK_CHUNK)) {
+						const uint32_t rem = min(size - done, (RANK_CHUNK));
+						uint4 x[RANK_VEC];
+#pragma unroll
+						for (uint32_t j = 0; j < RANK_VEC; ++j)
+							vec_load(x[j], v4 + done / 4, j, rem, lane);
+#pragma unroll
+						for (uint32_t j = 0; j < RANK_VEC; ++j)
+							vec_count<WIDE>(U32, x[j], j, rem, lane);
+					}
+				}
+			}
+			if (lane == 0 && my_post)
+				atomicAdd(&S.n_post, my_post);
 		}
-		if (lane == 0 && my_post)
-			atomicAdd(&S.n_post, my_post);
 		__syncthreads();
+		USB_PHASE(2)
 		if (tid == 0) {
 			S.n_rows = 0;
 			S.row_cur = 0;
@@ -391,55 +642,75 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	}
 
 	if (a.u_out)
-		for (uint32_t t = tid; t < N; t += RANK_THREADS)
+		for (uint32_t t = tid; t < N; t += NT)
 			a.u_out[(uint64_t)job * N + t] = u_get<WIDE>(U, t);
 
 	// ---- strict prefix maxima ("records") of U in target order; SIMD max over the segment
+	uint32_t *rec_pos = X.rec_pos, *rec_val = X.rec_val, *chg_pos = X.chg_pos, *chg_minu = X.chg_minu;
 	const uint32_t seg = WIDE ? a.seg_wide : a.seg_narrow;
 	const uint32_t t0 = min(N, tid * seg), t1 = min(N, t0 + seg);
 	const uint32_t PER = WIDE ? 2 : 4;   // counters per 32-bit word
 	// segment start is word aligned; threads past the end own nothing
 	const uint32_t w0 = t0 / PER, w1 = t0 < t1 ? (t1 + PER - 1) / PER : w0;
+	// the same range in 16-byte chunks (segments are whole chunks; counters past N are zero)
+	const uint4 *U128 = (const uint4 *)U;
+	const uint32_t c0 = w0 / 4, c1 = t0 < t1 ? (w1 + 3) / 4 : c0;
 	uint32_t m = 0;
 	{
 		uint32_t acc = 0;
-		for (uint32_t k = w0; k < w1; ++k)
-			acc = WIDE ? __vmaxu2(acc, U32[k]) : __vmaxu4(acc, U32[k]);
-		if (WIDE)
-			m = max(acc & 0xffff, acc >> 16);
-		else
-			m = max(max(acc & 0xff, (acc >> 8) & 0xff), max((acc >> 16) & 0xff, acc >> 24));
+		for_words(U128, c0, c1, [&](uint32_t, uint32_t word) {
+			if (WIDE)
+				acc = __vmaxu2(acc, word);
+			else
+				acc = __vmaxu2(__vmaxu2(acc, word & 0x00ff00ffu), (word >> 8) & 0x00ff00ffu);
+		});
+		m = max(acc & 0xffffu, acc >> 16);
 	}
-	uint32_t run = block_excl_scan_max(m, S.warp_tmp);
-	if (m > run)
-		for (uint32_t t = t0; t < t1; ++t) {
-			uint32_t u = u_get<WIDE>(U, t);
-			if (u > run) {
-				uint32_t idx = atomicAdd(&S.n_rec, 1u);
-				if (idx < a.rec_cap) {
-					rec_pos[idx] = t;
-					rec_val[idx] = u;
+	// records are counted per thread and placed by a block scan, which leaves them in target order
+	USB_PHASE(9)
+	const uint32_t run0 = block_excl_scan_max(m, S.warp_tmp);
+	USB_PHASE(10)
+	uint32_t nrec = 0;
+	if (m > run0) {
+		uint32_t run = run0;
+		for_words(U128, c0, c1, [&](uint32_t, uint32_t word) {
+			if (word_max<WIDE>(word) > run)
+				for (uint32_t b = 0; b < PER; ++b) {
+					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+					if (u > run) {
+						++nrec;
+						run = u;
+					}
 				}
-				run = u;
-			}
-		}
+		});
+	}
+	uint32_t rslot = block_excl_scan_sum(nrec, S.warp_tmp);
+	if (tid == NT - 1)
+		S.n_rec = rslot + nrec;
+	if (nrec) {
+		uint32_t run = run0;
+		for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) {
+			if (word_max<WIDE>(word) > run)
+				for (uint32_t b = 0; b < PER; ++b) {
+					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
+					if (u > run) {
+						if (rslot < a.rec_cap) {
+							rec_pos[rslot] = k * PER + b;
+							rec_val[rslot] = u;
+						}
+						++rslot;
+						run = u;
+					}
+				}
+		});
+	}
 	__syncthreads();
+	USB_PHASE(11)
 	if (tid == 0) {
 		uint32_t n = S.n_rec;
 		if (n > a.rec_cap) {
 			atomicOr(&a.ctr->err, ERR_RECORDS_FULL);
 			n = a.rec_cap;
-		}
-		for (uint32_t i = 1; i < n; ++i) { // few records: insertion sort by position
-			uint32_t p = rec_pos[i], v = rec_val[i];
-			uint32_t j = i;
-			while (j > 0 && rec_pos[j - 1] > p) {
-				rec_pos[j] = rec_pos[j - 1];
-				rec_val[j] = rec_val[j - 1];
-				--j;
-			}
-			rec_pos[j] = p;
-			rec_val[j] = v;
 		}
 		// SetTopBump replayed over the records (udbusortedsearcher.cpp:247-263)
 		uint32_t MinU = 1, MaxCount = 0, nchg = 0;
@@ -463,57 +734,63 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		S.minv = (n >= 2 ? rec_val[n - 2] : 0) / 2;
 	}
 	__syncthreads();
+	USB_PHASE(3)
 
-	// ---- survivors of both filters, collected unordered
-	KeepCursor kc{chg_pos, chg_minu, S.n_chg, S.minv, 0};
+	// ---- survivors of both filters: counted per thread, placed by a block scan (ascending targets).
+	// A segment whose largest counter is below the counting-sort cut-off has none; a word is
+	// looked at counter by counter only when its largest counter reaches the threshold.
+	SegFilter<WIDE> F{KeepCursor{chg_pos, chg_minu, S.n_chg, S.minv, 0, 1, 0}, max(S.minv, 1u)};
+	const uint32_t floor_thr = F.floor_thr;
+	constexpr uint32_t LANE_BITS = WIDE ? 16 : 8, LANE_MAX = WIDE ? 0xffffu : 0xffu;
 	{
-		const uint32_t mu0 = kc.minu(t0);          // threshold at the segment start
-		const uint32_t cur0 = kc.cur;
-		// constant over the segment unless a change position lies in [t0, t1 - 1)
-		const bool constant = !(cur0 < kc.n_chg && chg_pos[cur0] + 1 < t1);
-		if (constant) {
-			const uint32_t thr = max(max(mu0, kc.minv), 1u);
-			if (thr <= (WIDE ? 0xffffu : 0xffu)) {
-				const uint32_t thr_v = WIDE ? thr * 0x00010001u : thr * 0x01010101u;
-				for (uint32_t k = w0; k < w1; ++k) {
-					const uint32_t word = U32[k];
-					uint32_t mask = WIDE ? __vcmpgeu2(word, thr_v) : __vcmpgeu4(word, thr_v);
-					while (mask) {
-						const uint32_t b = (uint32_t)(__ffs(mask) - 1) / (WIDE ? 16 : 8);
-						mask &= ~((WIDE ? 0xffffu : 0xffu) << (b * (WIDE ? 16 : 8)));
-						const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
-						const uint32_t t = k * PER + b;
-						const uint32_t slot = atomicAdd(&S.n_surv, 1u);
-						if (slot < RANK_KCAP)
-							S.sel[slot] = rank_key(u, t);
-					}
-				}
-			}
-		} else {
-			kc.cur = 0;
-			for (uint32_t t = t0; t < t1; ++t) {
-				const uint32_t u = u_get<WIDE>(U, t);
-				if (u && kc.keep(t, u)) {
-					const uint32_t slot = atomicAdd(&S.n_surv, 1u);
-					if (slot < RANK_KCAP)
-						S.sel[slot] = rank_key(u, t);
-				}
-			}
+		uint32_t cnt = 0;
+		if (m >= floor_thr) {
+			F.reset();
+			for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) { cnt += __popc(F.mask(k, word)); });
 		}
+		USB_PHASE(6)
+		uint32_t slot = block_excl_scan_sum(cnt, S.warp_tmp);
+		USB_PHASE(7)
+		if (tid == NT - 1)
+			S.n_surv = slot + cnt;
+		if (cnt && slot < RANK_KCAP) {
+			F.reset();
+			for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) {
+				uint32_t mask = F.mask(k, word);
+				while (mask) {
+					const uint32_t b = (uint32_t)__ffs(mask) - 1;
+					mask &= mask - 1;
+					if (slot < RANK_KCAP)
+						X.sel[slot] = rank_key((word >> (b * LANE_BITS)) & LANE_MAX, k * PER + b);
+					++slot;
+				}
+			});
+		}
+		USB_PHASE(8)
 	}
 	__syncthreads();
+	USB_PHASE(4)
 	const uint32_t total = S.n_surv;
 	uint32_t nsel;
+	const bool top32 = a.k_max <= 32 && (NT & (NT - 1)) == 0 && NT >= 32;
 	if (total <= RANK_KCAP) {
 		nsel = min(total, a.k_max);
-		block_sort_keys(S.sel, total);
+		if (top32)
+			block_top32(X.sel, total);
+		else
+			block_sort_keys(X.sel, total);
 	} else {
-		rank_select_fallback<WIDE>(a, S, U, kc, t0, t1);
+		rank_select_fallback<WIDE>(a, S, X, U128, F, c0, c1, m >= floor_thr);
 		nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
-		block_sort_keys(S.sel, nsel);
+		if (top32)
+			block_top32(X.sel, nsel);
+		else
+			block_sort_keys(X.sel, nsel);
+		nsel = min(nsel, a.k_max);
 	}
-	for (uint32_t i = tid; i < nsel; i += RANK_THREADS) {
-		const unsigned long long key = S.sel[i];
+	USB_PHASE(12)
+	for (uint32_t i = tid; i < nsel; i += NT) {
+		const unsigned long long key = X.sel[i];
 		a.cand_t[(uint64_t)job * a.k_max + i] = (uint32_t)key;
 		if (a.cand_u)
 			a.cand_u[(uint64_t)job * a.k_max + i] = 0xFFFFu - (uint32_t)(key >> 32);
@@ -529,6 +806,8 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		}
 		atomicAdd(&a.ctr->postings, (unsigned long long)S.n_post);
 	}
+	USB_PHASE(5)
+#undef USB_PHASE
 }
 
 __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
@@ -536,11 +815,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 	extern __shared__ __align__(16) uint8_t rank_smem[];
 	RankShared &S = *(RankShared *)rank_smem;
 	uint8_t *U = rank_smem + ((sizeof(RankShared) + 15) & ~(size_t)15);
-	uint32_t *bitmap = (uint32_t *)(U + a.u_bytes);
-	uint32_t *rec_pos = bitmap + (a.P.alpha == 4 ? a.P.slots / 32 : a.P.hash_cap);
-	uint32_t *rec_val = rec_pos + a.rec_cap;
-	uint32_t *chg_pos = rec_val + a.rec_cap;
-	uint32_t *chg_minu = chg_pos + a.rec_cap;
+	const RankScratch X = rank_scratch(U + a.u_bytes, a.dedupe_words, a.rec_cap);
 	const uint32_t job = blockIdx.x;
 	if (job >= a.n_jobs)
 		return;
@@ -548,25 +823,28 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 	const uint32_t L = (uint32_t)(a.q_off[qi + 1] - a.q_off[qi]);
 	const uint32_t npos = L >= a.P.word_length ? L - a.P.word_length + 1 : 0;
 	if (npos > 255)
-		rank_job<true>(a, job, S, U, bitmap, rec_pos, rec_val, chg_pos, chg_minu);
+		rank_job<true>(a, job, S, U, X);
 	else
-		rank_job<false>(a, job, S, U, bitmap, rec_pos, rec_val, chg_pos, chg_minu);
+		rank_job<false>(a, job, S, U, X);
 }
 
 // dedupe_bytes: nt = slots / 8 (bitmap), aa = 4 * hash_cap
-inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, size_t dedupe_bytes, uint32_t rec_cap, uint32_t *u_bytes)
+inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, size_t dedupe_bytes, uint32_t rec_cap, uint32_t threads,
+  uint32_t *u_bytes)
 {
 	size_t ub = (((size_t)n_seq * (wide ? 2 : 1)) + 15) & ~(size_t)15;
 	*u_bytes = (uint32_t)ub;
-	return ((sizeof(RankShared) + 15) & ~(size_t)15) + ub + dedupe_bytes + (size_t)4 * rec_cap * 4;
+	const size_t walk = dedupe_bytes + (size_t)4 * (2 * threads);
+	const size_t rank = (size_t)8 * RANK_KCAP + (size_t)16 * rec_cap + 4 * 256;
+	return ((sizeof(RankShared) + 15) & ~(size_t)15) + ub + ((std::max(walk, rank) + 15) & ~(size_t)15);
 }
 
-// Per-thread segment length (in targets) such that consecutive threads start in different
-// shared-memory banks: seg * width / 4 must be odd.
-inline uint32_t rank_segment(uint32_t n_seq, bool wide)
+// Per-thread segment length (in targets): whole 16-byte chunks of counters, an odd number of them,
+// so that the 128-bit loads of the eight lanes of a quarter warp fall into different bank groups.
+inline uint32_t rank_segment(uint32_t n_seq, bool wide, uint32_t threads)
 {
-	uint32_t per = (n_seq + RANK_THREADS - 1) / RANK_THREADS;
-	uint32_t unit = wide ? 2 : 4;
+	uint32_t per = (n_seq + threads - 1) / threads;
+	uint32_t unit = wide ? 8 : 16;
 	uint32_t m = (per + unit - 1) / unit;
 	if (m == 0)
 		m = 1;
