@@ -303,7 +303,8 @@ def main():
         qs = res.qstat
         hits = res.hits
         # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
-        b_k1 = 4.0 * ctr["postings"] + 8.0 * float(np.minimum(qs["n_cand"], s_kmax(p, a.db)).sum()) + float(reads.size)
+        pw = float(ix.posting_width)  # 2 = bank-aware 2-byte rows (DBs up to 131 070 targets), else 4
+        b_k1 = pw * ctr["postings"] + 8.0 * float(np.minimum(qs["n_cand"], s_kmax(p, a.db)).sum()) + float(reads.size)
         b_k2 = float(qs["seq_bytes"].sum()) + float(np.ceil(qs["dp_cells"] / 2.0).sum()) + \
             float((hits["ql"] + hits["tl"]).sum()) + 72.0 * len(hits) + 4.0 * len(res.runs)
         peaks = {}
@@ -328,8 +329,9 @@ def main():
             "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(a), "reads_per_gpu": a.reads, "db_seqs": a.db,
-                       "postings": int(ix.posting_count), "l2": "inputs larger than L2 (reads %d MB + postings %d MB)" % (
-                           reads.size >> 20, (4 * ix.posting_count) >> 20),
+                       "postings": int(ix.posting_count), "posting_bytes": int(pw),
+                       "l2": "inputs larger than L2 (reads %d MB + postings %d MB)" % (
+                           reads.size >> 20, (int(pw) * ix.posting_count) >> 20),
                        "hit_rate": float(len(hits)) / a.reads, "gen_s": round(t_gen, 1), "index_build_s": round(t_ix, 1)},
             "kernels_ms_per_step": {"k_rank": k1 / a.steps, "k_align": k2 / a.steps, "nccl_gather": gat / a.steps,
                                     "wall": wall_ms / a.steps},

@@ -121,6 +121,10 @@ int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off
 void usb_index_free(usb_index *ix);
 uint32_t usb_index_seq_count(const usb_index *ix);
 uint64_t usb_index_posting_count(const usb_index *ix);
+/* Bytes per posting of the rows as they lie in HBM now: 2 = bank-aware 2-byte layout (one static
+ * segment of at most 131 070 targets, walked by the U-sort kernel only), 4 = ascending 4-byte rows
+ * (UDBData::m_UDBRows, udbdata.h:15-31).  The layout is an internal choice; results are identical. */
+uint32_t usb_index_posting_width(const usb_index *ix);
 /* Host-side introspection for parity tests: one UDB row (m_UDBRows[word], m_Sizes[word]). */
 int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size);
 /* Masked target sequence as indexed (SeqDB::GetSeq after SeqDB::Mask, seqdb.cpp:415). */

@@ -47,7 +47,7 @@ QSTAT_DTYPE = np.dtype([
 # every symbol include/usb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
-    "usb_index_seq_count", "usb_index_posting_count", "usb_index_row", "usb_index_seq",
+    "usb_index_seq_count", "usb_index_posting_count", "usb_index_posting_width", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
     "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
@@ -77,6 +77,8 @@ def lib():
     L.usb_index_seq_count.restype = C.c_uint32
     L.usb_index_posting_count.argtypes = [vp]
     L.usb_index_posting_count.restype = C.c_uint64
+    L.usb_index_posting_width.argtypes = [vp]
+    L.usb_index_posting_width.restype = C.c_uint32
     L.usb_index_row.argtypes = [vp, C.c_uint32, C.POINTER(u32p), u32p]
     L.usb_index_seq.argtypes = [vp, C.c_uint32, C.POINTER(u8p), u32p]
     L.usb_searcher_create.argtypes = [vp, C.POINTER(Params), C.POINTER(vp)]
@@ -211,6 +213,11 @@ class Index:
     @property
     def posting_count(self):
         return lib().usb_index_posting_count(self.handle)
+
+    @property
+    def posting_width(self):
+        """Bytes per posting as laid out in HBM now (2 = bank-aware 2-byte rows, 4 = ascending rows)."""
+        return lib().usb_index_posting_width(self.handle)
 
     def close(self):
         if self.handle:

@@ -149,20 +149,43 @@ template <class T> struct DevBuf {
 	}
 };
 
-// One immutable CSR segment of the index on the host and on the device.
+// One immutable CSR segment of the index on the host and on the device.  On the device the
+// postings are either 4-byte ascending rows (any kernel) or the 2-byte bank-aware layout of
+// HostHalf (k_rank only), never both.
 struct IndexSegment {
 	HostCSR H;
 	DevBuf<uint64_t> d_row_off;
 	DevBuf<uint32_t> d_row_size, d_postings;
-	int upload()
+	DevBuf<uint16_t> d_post16;
+	bool on_dev = false, half = false;
+	uint32_t half_blocks = 0;
+	int upload(bool want_half, uint32_t n_targets)
 	{
+		if (on_dev && half == want_half)
+			return 0;
 		int rc;
-		if ((rc = d_row_off.reserve(H.row_off.size())) || (rc = d_row_size.reserve(H.row_size.size())) ||
-		    (rc = d_postings.reserve(H.postings.size())))
-			return rc;
-		CK(cudaMemcpy(d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
-		CK(cudaMemcpy(d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
-		CK(cudaMemcpy(d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
+		if (want_half) {
+			HostHalf hh;
+			make_half(H, n_targets, 0, hh);
+			d_postings.release();
+			if ((rc = d_row_off.reserve(hh.row_off.size())) || (rc = d_row_size.reserve(hh.row_size.size())) ||
+			    (rc = d_post16.reserve(hh.postings.size())))
+				return rc;
+			CK(cudaMemcpy(d_row_off.p, hh.row_off.data(), hh.row_off.size() * 8, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_row_size.p, hh.row_size.data(), hh.row_size.size() * 4, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_post16.p, hh.postings.data(), hh.postings.size() * 2, cudaMemcpyHostToDevice));
+			half_blocks = hh.n_blocks;
+		} else {
+			d_post16.release();
+			if ((rc = d_row_off.reserve(H.row_off.size())) || (rc = d_row_size.reserve(H.row_size.size())) ||
+			    (rc = d_postings.reserve(H.postings.size())))
+				return rc;
+			CK(cudaMemcpy(d_row_off.p, H.row_off.data(), H.row_off.size() * 8, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_postings.p, H.postings.data(), H.postings.size() * 4, cudaMemcpyHostToDevice));
+		}
+		on_dev = true;
+		half = want_half;
 		return 0;
 	}
 	void release()
@@ -170,6 +193,8 @@ struct IndexSegment {
 		d_row_off.release();
 		d_row_size.release();
 		d_postings.release();
+		d_post16.release();
+		on_dev = false;
 	}
 };
 
@@ -183,11 +208,32 @@ struct usb_index {
 	DynSegment *dyn = nullptr;           // growable tail segment for small appends (cluster_fast)
 	uint32_t n_dev = 0;                  // targets whose letters are on the device
 	uint64_t n_postings = 0;
+	bool no_half = false;                // a kernel other than k_rank needed the 4-byte postings
 	DevBuf<uint8_t> d_seqs;
 	DevBuf<uint64_t> d_seq_off;
 	DevBuf<uint32_t> d_seq_len;
 	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
+
+// 2-byte postings: one static segment from target 0, at most 131 070 targets, and no use of the
+// big-database or cluster kernels (they walk 4-byte rows).
+static bool index_wants_half(const usb_index *ix)
+{
+	return !ix->no_half && !ix->P.cluster_mode && !ix->dyn && ix->segs.size() == 1 && ix->segs[0]->H.base == 0 &&
+	       ix->S.n() <= USB_HALF_MAX_TARGETS && ix->S.n() <= ix->P.big && !getenv("USB_NO_HALF");
+}
+
+// Brings every segment to the layout the index wants now (no-op when nothing changed).
+static int index_sync_layout(usb_index *ix)
+{
+	const bool half = index_wants_half(ix);
+	for (IndexSegment *g : ix->segs) {
+		int rc = g->upload(half, ix->S.n());
+		if (rc)
+			return rc;
+	}
+	return 0;
+}
 
 static void fill_index_view(const usb_index *ix, IndexView &v)
 {
@@ -196,9 +242,15 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 	v.n_seq = ix->S.n();
 	for (uint32_t i = 0; i < v.n_seg; ++i) {
 		const IndexSegment *g = ix->segs[i];
-		v.seg[i].row_off = g->d_row_off.p;
-		v.seg[i].row_size = g->d_row_size.p;
+		v.seg[i].row_off = g->half ? nullptr : g->d_row_off.p;
+		v.seg[i].row_size = g->half ? nullptr : g->d_row_size.p;
 		v.seg[i].postings = g->d_postings.p;
+		if (g->half) {
+			v.post16 = g->d_post16.p;
+			v.row_off16 = g->d_row_off.p;
+			v.row_size16 = g->d_row_size.p;
+			v.half_blocks = g->half_blocks;
+		}
 		v.seg[i].base = g->H.base;
 		v.seg[i].count = g->H.count;
 	}
@@ -401,7 +453,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 		if ((rc = ix->dyn->append(S, n0, n, ix->P.word_length)))
 			return rc;
 		ix->n_postings += ix->dyn->n_postings - before;
-		return 0;
+		return index_sync_layout(ix); // a tail segment ends the 2-byte layout of a static one
 	}
 	// new segment, then merge while the last two are of similar size (or the list is full)
 	IndexSegment *g = new IndexSegment;
@@ -422,9 +474,8 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 		ix->segs.pop_back();
 		ix->segs.back() = m;
 	}
-	if (dirty && (rc = ix->segs.back()->upload()))
-		return rc;
-	return 0;
+	(void)dirty;
+	return index_sync_layout(ix);
 }
 
 extern "C" void usb_index_free(usb_index *ix)
@@ -448,6 +499,10 @@ extern "C" void usb_index_free(usb_index *ix)
 
 extern "C" uint32_t usb_index_seq_count(const usb_index *ix) { return ix ? ix->S.n() : 0; }
 extern "C" uint64_t usb_index_posting_count(const usb_index *ix) { return ix ? ix->n_postings : 0; }
+extern "C" uint32_t usb_index_posting_width(const usb_index *ix)
+{
+	return ix && ix->segs.size() == 1 && !ix->dyn && ix->segs[0]->half ? 2u : 4u;
+}
 
 extern "C" int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint32_t *size)
 {
@@ -674,6 +729,12 @@ static int upload_queries(usb_searcher *s, const uint8_t *qseqs, const uint64_t 
 // K1b launch: persistent CTAs, each with its own counter array in global memory.
 static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint32_t k_max, bool want_u)
 {
+	if (!s->ix->no_half) { // this kernel walks 4-byte rows
+		s->ix->no_half = true;
+		int rc = index_sync_layout(s->ix);
+		if (rc)
+			return rc;
+	}
 	const usb_index *ix = s->ix;
 	const uint32_t N = ix->S.n();
 	if (s->max_ql >= s->D.word_length && s->max_ql - s->D.word_length + 1 > BIG_MAX_POS)
@@ -780,14 +841,20 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
 	a.prof = getenv("USB_RANK_PROF") ? 1 : 0; // measurement knob: phase cycles to stderr
 	if (smem > s->rank_smem_set || two != s->rank_two) {
-		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, s->rank_smem_set)));
+		const int carve = two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+		const int bytes = (int)std::max(smem, s->rank_smem_set);
+		CK(cudaFuncSetAttribute(k_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		CK(cudaFuncSetAttribute(k_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 		// two CTAs only fit with the whole L1/shared array carved out as shared memory
-		CK(cudaFuncSetAttribute(k_rank, cudaFuncAttributePreferredSharedMemoryCarveout,
-		  two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault));
-		s->rank_smem_set = std::max(smem, s->rank_smem_set);
+		CK(cudaFuncSetAttribute(k_rank<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+		CK(cudaFuncSetAttribute(k_rank<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+		s->rank_smem_set = (size_t)bytes;
 		s->rank_two = two;
 	}
-	k_rank<<<n_jobs, threads, smem, s->stream>>>(a);
+	if (a.ix.post16)
+		k_rank<true><<<n_jobs, threads, smem, s->stream>>>(a);
+	else
+		k_rank<false><<<n_jobs, threads, smem, s->stream>>>(a);
 	CK(cudaGetLastError());
 	++s->launches;
 	return 0;

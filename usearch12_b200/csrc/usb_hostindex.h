@@ -38,6 +38,30 @@ struct HostCSR {
 	uint64_t n_postings = 0;
 };
 
+// The same index with 2-byte postings in a bank-aware order, for k_rank on indexes of at most
+// USB_HALF_MAX_TARGETS targets starting at target 0.  Halves the HBM bytes of the U-sort walk and
+// removes most shared-memory bank conflicts of its counter increments, which is what bounds the
+// walk on B200 (profiles/README.md).
+//   * Targets are cut into blocks of 65 535; a word has one row fragment per block, holding
+//     target - 65535 * block (<= 65 534; 0xffff marks padding).  Fragment f = word * n_blocks +
+//     block: row_off[f] (in entries, multiples of 8 = 16 bytes), row_size[f].
+//   * The order inside a fragment does not matter for U.  It is chosen for the way a warp walks
+//     it: lane l loads the 8-entry vector 32 * s + l of slot s and the warp then issues one
+//     increment instruction per entry index i = 0..7, i.e. for entries {256 s + 8 l + i}.  The
+//     fragment's postings are dealt round-robin over the 32 banks of their 1-byte counters
+//     (bank = (target / 4) % 32) and sequence index q = 256 s + 32 i + l goes to entry
+//     256 s + 8 l + i, so the 32 increments of one instruction fall into (mostly) different banks.
+//     The last m = size % 256 entries use nv = ceil(m / 8) vectors: q -> entry 8 (q % nv) + q / nv.
+#define USB_HALF_BLOCK 65535u
+#define USB_HALF_MAX_TARGETS (2u * USB_HALF_BLOCK)
+struct HostHalf {
+	uint32_t n_blocks = 1;
+	std::vector<uint64_t> row_off;   // slots * n_blocks + 1
+	std::vector<uint32_t> row_size;  // slots * n_blocks
+	std::vector<uint16_t> postings;
+};
+void make_half(const HostCSR &H, uint32_t n_targets, int n_threads, HostHalf &out);
+
 // FastMaskSeq soft-masking (fastmask.cpp:88-158); in == out allowed.
 void fastmask_nt(const uint8_t *in, uint32_t L, uint8_t *out);
 

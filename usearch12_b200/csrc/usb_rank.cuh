@@ -460,6 +460,32 @@ __device__ __forceinline__ void vec_count(uint32_t *U32, const uint4 &x, uint32_
 	}
 }
 
+// One vector of eight 2-byte postings of the bank-aware layout (usb_hostindex.h HostHalf); hi =
+// first target of the fragment's block.  CHECKED: the vector belongs to the ragged last group of
+// its fragment, whose padding entries (0xffff) are skipped.
+template <bool WIDE, bool CHECKED>
+__device__ __forceinline__ void vec_count16(uint32_t *U32, const uint4 &x, uint32_t hi)
+{
+#define USB_INC16(W)                                                     \
+	{                                                                    \
+		const uint32_t lo_ = (W) & 0xffffu, hi_ = (W) >> 16;             \
+		if (!CHECKED || lo_ != 0xffffu) u_inc<WIDE>(U32, lo_ + hi);      \
+		if (!CHECKED || hi_ != 0xffffu) u_inc<WIDE>(U32, hi_ + hi);      \
+	}
+	USB_INC16(x.x)
+	USB_INC16(x.y)
+	USB_INC16(x.z)
+	USB_INC16(x.w)
+#undef USB_INC16
+}
+
+__device__ __forceinline__ uint4 ld_stream128(const uint4 *p)
+{
+	uint4 x;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(p));
+	return x;
+}
+
 // Posting rows are streamed once per query: they are not allocated in L1 (most of the unified
 // L1/shared memory array is carved out for the counters).
 __device__ __forceinline__ void vec_load(uint4 &x, const uint4 *v4, uint32_t j, uint32_t rem, uint32_t lane)
@@ -475,7 +501,7 @@ __device__ __forceinline__ void vec_load(uint4 &x, const uint4 *v4, uint32_t j, 
 	}
 }
 
-template <bool WIDE>
+template <bool WIDE, bool HALF>
 __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t *U, const RankScratch &X)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -488,6 +514,9 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	uint32_t *U32 = (uint32_t *)U;
 	uint32_t *bitmap = X.bitmap;
 	const bool one_seg = a.ix.n_seg == 1;
+	// HALF: 2-byte postings, one or two row fragments per word; a pass then takes NT / blocks
+	// positions so that its fragment descriptors fit the NT entries of r_off / r_size
+	const uint32_t PW = HALF ? NT / a.ix.half_blocks : NT;
 #define USB_PHASE(i)                                               \
 	if (a.prof && tid == 0) {                                      \
 		const long long now = clock64();                           \
@@ -516,9 +545,9 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 
 	// ---- a1/a2/a4: words -> unique rows -> posting walk
 	const uint32_t npos = L >= WLEN ? L - WLEN + 1 : 0;
-	for (uint32_t base = 0; base < npos; base += NT) {
+	for (uint32_t base = 0; base < npos; base += PW) {
 		const uint32_t p = base + tid;
-		if (p < npos) {
+		if (tid < PW && p < npos) {
 			uint32_t word = 0, bad = 0;
 			bool fresh = false;
 			if (a.P.alpha == 4) {
@@ -554,7 +583,22 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 					}
 				}
 			}
-			if (fresh) {
+			if (fresh && HALF) {
+				// descriptors of the word's row fragments (block in the top bit of the size)
+				const uint32_t nb = a.ix.half_blocks;
+				const uint32_t s0 = __ldg(a.ix.row_size16 + word * nb), s1 = nb > 1 ? __ldg(a.ix.row_size16 + word * nb + 1) : 0u;
+				const uint64_t o0 = __ldg(a.ix.row_off16 + word * nb), o1 = nb > 1 ? __ldg(a.ix.row_off16 + word * nb + 1) : 0ull;
+				if (s0) {
+					const uint32_t idx = atomicAdd(&S.n_rows, 1u);
+					X.r_off[idx] = (uint32_t)(o0 >> 3);
+					X.r_size[idx] = s0;
+				}
+				if (s1) {
+					const uint32_t idx = atomicAdd(&S.n_rows, 1u);
+					X.r_off[idx] = (uint32_t)(o1 >> 3);
+					X.r_size[idx] = s1 | 0x80000000u;
+				}
+			} else if (fresh) {
 				if (one_seg) {
 					// row descriptor now: the loads of all unique words of the pass overlap
 					const SegDesc &seg = a.ix.seg[0];
@@ -571,14 +615,14 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		}
 		__syncthreads();
 		const uint32_t n_rows = S.n_rows;
-		if (one_seg) {
-			const uint32_t size = tid < n_rows ? X.r_size[tid] : 0;
+		if (HALF || one_seg) {
+			const uint32_t size = tid < n_rows ? X.r_size[tid] & 0x7fffffffu : 0;
 			const uint32_t sz = __reduce_add_sync(USB_FULL, size);
 			if (lane == 0 && sz)
 				atomicAdd(&S.n_post, sz);
 			USB_PHASE(1)
-			const uint4 *P4 = (const uint4 *)a.ix.seg[0].postings;
-			// whole rows per warp, drawn from a shared cursor
+			const uint4 *P4 = HALF ? (const uint4 *)a.ix.post16 : (const uint4 *)a.ix.seg[0].postings;
+			// whole rows (row fragments) per warp, drawn from a shared cursor
 			for (;;) {
 				uint32_t r = 0;
 				if (lane == 0)
@@ -586,8 +630,29 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				r = __shfl_sync(USB_FULL, r, 0);
 				if (r >= n_rows)
 					break;
-				const uint32_t size = X.r_size[r];
+				const uint32_t size = X.r_size[r] & 0x7fffffffu;
 				const uint4 *v4 = P4 + X.r_off[r];
+				if (HALF) {
+					const uint32_t hi = (X.r_size[r] >> 31) * 65535u;
+					const uint32_t vfull = (size >> 8) * 32;            // vectors of whole 256-entry groups
+					const uint32_t vall = vfull + (((size & 255u) + 7) >> 3);
+					for (uint32_t s0 = 0; s0 < vall; s0 += 32 * RANK_VEC) {
+						uint4 x[RANK_VEC];
+#pragma unroll
+						for (uint32_t j = 0; j < RANK_VEC; ++j)
+							if (s0 + 32 * j + lane < vall)
+								x[j] = ld_stream128(v4 + s0 + 32 * j + lane);
+#pragma unroll
+						for (uint32_t j = 0; j < RANK_VEC; ++j) {
+							const uint32_t slot = s0 + 32 * j + lane;
+							if (slot < vfull)
+								vec_count16<WIDE, false>(U32, x[j], hi);
+							else if (slot < vall)
+								vec_count16<WIDE, true>(U32, x[j], hi);
+						}
+					}
+					continue;
+				}
 				for (uint32_t done = 0; done < size; done += RANK_CHUNK) {
 					const uint32_t rem = min(size - done, RANK_CHUNK);
 					uint4 x[RANK_VEC];
@@ -810,6 +875,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 #undef USB_PHASE
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 {
 	extern __shared__ __align__(16) uint8_t rank_smem[];
@@ -823,9 +889,9 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 	const uint32_t L = (uint32_t)(a.q_off[qi + 1] - a.q_off[qi]);
 	const uint32_t npos = L >= a.P.word_length ? L - a.P.word_length + 1 : 0;
 	if (npos > 255)
-		rank_job<true>(a, job, S, U, X);
+		rank_job<true, HALF>(a, job, S, U, X);
 	else
-		rank_job<false>(a, job, S, U, X);
+		rank_job<false, HALF>(a, job, S, U, X);
 }
 
 // dedupe_bytes: nt = slots / 8 (bitmap), aa = 4 * hash_cap
