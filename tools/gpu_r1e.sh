@@ -8,13 +8,12 @@ run() { # name, env...
 import json,sys
 f="gpurun_out/bench_%s.json"%sys.argv[1]
 try:
-    d=json.loads(open(f).read().strip().splitlines()[-1]); print(sys.argv[1], "k_rank %.1f ms"%d["kernels_ms_per_step"]["k_rank"], "GB/s %.0f"%d["roofline"]["other"]["k_rank_GBps"], "hits", d["config"]["hit_rate"], "e2e", round(d["e2e"]["value"]), "value", round(d["value"]))
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(sys.argv[1], "k_rank %.1f ms"%d["kernels_ms_per_step"]["k_rank"], "GB/s %.0f"%d["roofline"]["other"]["k_rank_GBps"], "hits", d["config"]["hit_rate"], "e2e", round(d["e2e"]["value"]), "value", round(d["value"]), "ix_s", d["config"]["index_build_s"])
 except Exception as e:
     print(sys.argv[1], "FAILED rc", sys.argv[2], e)
 PY
   grep "phase cycles" gpurun_out/bench_$name.err | tail -1
 }
-run half
-run half_p USB_RANK_PROF=1
-run half_one_p USB_RANK_ONE_CTA=1 USB_RANK_PROF=1
-run nohalf USB_NO_HALF=1
+run v3
+run v3_p USB_RANK_PROF=1
+run v3_one_p USB_RANK_ONE_CTA=1 USB_RANK_PROF=1

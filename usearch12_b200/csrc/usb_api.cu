@@ -155,10 +155,9 @@ template <class T> struct DevBuf {
 struct IndexSegment {
 	HostCSR H;
 	DevBuf<uint64_t> d_row_off;
-	DevBuf<uint32_t> d_row_size, d_postings;
+	DevBuf<uint32_t> d_row_size, d_postings, d_row_groups;
 	DevBuf<uint16_t> d_post16;
 	bool on_dev = false, half = false;
-	uint32_t half_blocks = 0;
 	int upload(bool want_half, uint32_t n_targets)
 	{
 		if (on_dev && half == want_half)
@@ -168,15 +167,16 @@ struct IndexSegment {
 			HostHalf hh;
 			make_half(H, n_targets, 0, hh);
 			d_postings.release();
-			if ((rc = d_row_off.reserve(hh.row_off.size())) || (rc = d_row_size.reserve(hh.row_size.size())) ||
-			    (rc = d_post16.reserve(hh.postings.size())))
+			if ((rc = d_row_off.reserve(hh.row_off.size())) || (rc = d_row_size.reserve(H.row_size.size())) ||
+			    (rc = d_row_groups.reserve(hh.row_groups.size())) || (rc = d_post16.reserve(hh.postings.size())))
 				return rc;
 			CK(cudaMemcpy(d_row_off.p, hh.row_off.data(), hh.row_off.size() * 8, cudaMemcpyHostToDevice));
-			CK(cudaMemcpy(d_row_size.p, hh.row_size.data(), hh.row_size.size() * 4, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_row_size.p, H.row_size.data(), H.row_size.size() * 4, cudaMemcpyHostToDevice));
+			CK(cudaMemcpy(d_row_groups.p, hh.row_groups.data(), hh.row_groups.size() * 4, cudaMemcpyHostToDevice));
 			CK(cudaMemcpy(d_post16.p, hh.postings.data(), hh.postings.size() * 2, cudaMemcpyHostToDevice));
-			half_blocks = hh.n_blocks;
 		} else {
 			d_post16.release();
+			d_row_groups.release();
 			if ((rc = d_row_off.reserve(H.row_off.size())) || (rc = d_row_size.reserve(H.row_size.size())) ||
 			    (rc = d_postings.reserve(H.postings.size())))
 				return rc;
@@ -194,6 +194,7 @@ struct IndexSegment {
 		d_row_size.release();
 		d_postings.release();
 		d_post16.release();
+		d_row_groups.release();
 		on_dev = false;
 	}
 };
@@ -215,7 +216,7 @@ struct usb_index {
 	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
 
-// 2-byte postings: one static segment from target 0, at most 131 070 targets, and no use of the
+// 2-byte postings: one static segment from target 0, at most USB_HALF_MAX_TARGETS, and no use of the
 // big-database or cluster kernels (they walk 4-byte rows).
 static bool index_wants_half(const usb_index *ix)
 {
@@ -243,13 +244,12 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 	for (uint32_t i = 0; i < v.n_seg; ++i) {
 		const IndexSegment *g = ix->segs[i];
 		v.seg[i].row_off = g->half ? nullptr : g->d_row_off.p;
-		v.seg[i].row_size = g->half ? nullptr : g->d_row_size.p;
+		v.seg[i].row_size = g->d_row_size.p;
 		v.seg[i].postings = g->d_postings.p;
 		if (g->half) {
 			v.post16 = g->d_post16.p;
 			v.row_off16 = g->d_row_off.p;
-			v.row_size16 = g->d_row_size.p;
-			v.half_blocks = g->half_blocks;
+			v.row_groups = g->d_row_groups.p;
 		}
 		v.seg[i].base = g->H.base;
 		v.seg[i].count = g->H.count;

@@ -69,12 +69,11 @@ struct IndexView {
 	SegDesc seg[USB_MAX_SEG];
 	uint32_t n_seg;
 	uint32_t n_seq;
-	// 2-byte postings in bank-aware order (usb_hostindex.h HostHalf): one static segment; then
-	// seg[0].postings / row_off / row_size are null and only k_rank may walk the index
+	// 2-byte increment descriptors (usb_hostindex.h HostHalf): one static segment; then
+	// seg[0].postings / row_off are null and only k_rank may walk the index
 	const uint16_t *post16;
-	const uint64_t *row_off16;  // slots * half_blocks + 1
-	const uint32_t *row_size16; // slots * half_blocks
-	uint32_t half_blocks;       // 1 or 2 blocks of 65 535 targets
+	const uint64_t *row_off16;   // slots + 1, entries (multiples of 256)
+	const uint32_t *row_groups;  // slots: groups of 256 entries
 };
 
 struct HspRec {

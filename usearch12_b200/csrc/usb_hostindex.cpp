@@ -198,74 +198,69 @@ void build_csr(const HostSeqs &S, uint32_t first, uint32_t count, uint32_t word_
 
 void make_half(const HostCSR &H, uint32_t n_targets, int n_threads, HostHalf &out)
 {
-	const uint32_t nb = n_targets > USB_HALF_BLOCK ? 2u : 1u;
-	out.n_blocks = nb;
-	const size_t nf = (size_t)H.slots * nb;
-	out.row_off.assign(nf + 1, 0);
-	out.row_size.assign(nf, 0);
-	// fragment sizes: rows are ascending, so block 0 is a prefix of the row
+	out.dummy0 = ((n_targets + 15) & ~15u) / 4;
+	out.row_off.assign((size_t)H.slots + 1, 0);
+	out.row_groups.assign(H.slots, 0);
 	const unsigned T = pick_threads(n_threads, H.slots);
+	// groups per row: the fullest byte class decides
 	run_threads(T, [&](unsigned k) {
 		const uint32_t a = (uint32_t)((uint64_t)H.slots * k / T), b = (uint32_t)((uint64_t)H.slots * (k + 1) / T);
 		for (uint32_t w = a; w < b; ++w) {
 			const uint32_t *src = H.postings.data() + H.row_off[w];
-			const uint32_t n = H.row_size[w];
-			const uint32_t c0 = (uint32_t)(std::lower_bound(src, src + n, USB_HALF_BLOCK) - src);
-			out.row_size[(size_t)w * nb] = nb == 1 ? n : c0;
-			if (nb == 2)
-				out.row_size[(size_t)w * nb + 1] = n - c0;
+			uint32_t c[4] = {0, 0, 0, 0};
+			for (uint32_t i = 0; i < H.row_size[w]; ++i)
+				++c[src[i] & 3];
+			const uint32_t m = std::max(std::max(c[0], c[1]), std::max(c[2], c[3]));
+			out.row_groups[w] = (m + 63) / 64;
 		}
 	});
 	uint64_t total = 0;
-	for (size_t f = 0; f < nf; ++f) {
-		out.row_off[f] = total;
-		total = (total + out.row_size[f] + 7) & ~(uint64_t)7;
+	for (uint32_t w = 0; w < H.slots; ++w) {
+		out.row_off[w] = total;
+		total += (uint64_t)out.row_groups[w] * 256;
 	}
-	out.row_off[nf] = total;
-	out.postings.assign(total + 8, (uint16_t)0xffff);
+	out.row_off[H.slots] = total;
+	out.postings.assign(total + 8, 0);
 	run_threads(T, [&](unsigned k) {
 		const uint32_t a = (uint32_t)((uint64_t)H.slots * k / T), b = (uint32_t)((uint64_t)H.slots * (k + 1) / T);
-		std::vector<uint32_t> seq, bucket;
+		std::vector<uint32_t> seq[4], bucket;
 		for (uint32_t w = a; w < b; ++w) {
-			const uint32_t *row = H.postings.data() + H.row_off[w];
-			uint32_t done = 0;
-			for (uint32_t blk = 0; blk < nb; ++blk) {
-				const size_t f = (size_t)w * nb + blk;
-				const uint32_t n = out.row_size[f];
-				const uint32_t *src = row + done;
-				done += n;
-				if (n == 0)
-					continue;
-				// deal the postings round-robin over the banks of their counters
-				uint32_t cnt[32] = {0}, start[33];
+			const uint32_t G = out.row_groups[w];
+			if (G == 0)
+				continue;
+			const uint32_t *src = H.postings.data() + H.row_off[w];
+			const uint32_t n = H.row_size[w];
+			// per byte class: word indexes dealt round-robin over the banks
+			for (uint32_t cls = 0; cls < 4; ++cls) {
+				uint32_t cnt[32] = {0}, start[33], cur[32], maxc = 0;
 				for (uint32_t i = 0; i < n; ++i)
-					++cnt[(src[i] >> 2) & 31];
+					if ((src[i] & 3) == cls)
+						++cnt[(src[i] >> 2) & 31];
 				start[0] = 0;
-				uint32_t maxc = 0;
 				for (int j = 0; j < 32; ++j) {
 					start[j + 1] = start[j] + cnt[j];
+					cur[j] = start[j];
 					maxc = std::max(maxc, cnt[j]);
 				}
-				bucket.resize(n);
-				{
-					uint32_t cur[32];
-					for (int j = 0; j < 32; ++j)
-						cur[j] = start[j];
-					for (uint32_t i = 0; i < n; ++i)
-						bucket[cur[(src[i] >> 2) & 31]++] = src[i];
-				}
-				seq.clear();
+				bucket.resize(start[32]);
+				for (uint32_t i = 0; i < n; ++i)
+					if ((src[i] & 3) == cls)
+						bucket[cur[(src[i] >> 2) & 31]++] = src[i] >> 2;
+				seq[cls].clear();
 				for (uint32_t r = 0; r < maxc; ++r)
 					for (int j = 0; j < 32; ++j)
 						if (r < cnt[j])
-							seq.push_back(bucket[start[j] + r]);
-				uint16_t *dst = out.postings.data() + out.row_off[f];
-				const uint32_t full = n & ~255u, m = n & 255u, nv = (m + 7) >> 3;
-				for (uint32_t q = 0; q < full; ++q)
-					dst[(q & ~255u) + 8 * (q & 31) + ((q >> 5) & 7)] = (uint16_t)(seq[q] - blk * USB_HALF_BLOCK);
-				for (uint32_t q = 0; q < m; ++q)
-					dst[full + 8 * (q % nv) + q / nv] = (uint16_t)(seq[full + q] - blk * USB_HALF_BLOCK);
+							seq[cls].push_back(bucket[start[j] + r]);
 			}
+			uint16_t *dst = out.postings.data() + out.row_off[w];
+			for (uint32_t g = 0; g < G; ++g)
+				for (uint32_t i = 0; i < 8; ++i) {
+					const std::vector<uint32_t> &sq = seq[i >> 1];
+					for (uint32_t l = 0; l < 32; ++l) {
+						const uint32_t q = g * 64 + (i & 1) * 32 + l;
+						dst[g * 256 + 8 * l + i] = (uint16_t)(q < sq.size() ? sq[q] : out.dummy0 + l);
+					}
+				}
 		}
 	});
 }

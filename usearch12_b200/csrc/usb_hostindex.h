@@ -38,26 +38,28 @@ struct HostCSR {
 	uint64_t n_postings = 0;
 };
 
-// The same index with 2-byte postings in a bank-aware order, for k_rank on indexes of at most
-// USB_HALF_MAX_TARGETS targets starting at target 0.  Halves the HBM bytes of the U-sort walk and
-// removes most shared-memory bank conflicts of its counter increments, which is what bounds the
-// walk on B200 (profiles/README.md).
-//   * Targets are cut into blocks of 65 535; a word has one row fragment per block, holding
-//     target - 65535 * block (<= 65 534; 0xffff marks padding).  Fragment f = word * n_blocks +
-//     block: row_off[f] (in entries, multiples of 8 = 16 bytes), row_size[f].
-//   * The order inside a fragment does not matter for U.  It is chosen for the way a warp walks
-//     it: lane l loads the 8-entry vector 32 * s + l of slot s and the warp then issues one
-//     increment instruction per entry index i = 0..7, i.e. for entries {256 s + 8 l + i}.  The
-//     fragment's postings are dealt round-robin over the 32 banks of their 1-byte counters
-//     (bank = (target / 4) % 32) and sequence index q = 256 s + 32 i + l goes to entry
-//     256 s + 8 l + i, so the 32 increments of one instruction fall into (mostly) different banks.
-//     The last m = size % 256 entries use nv = ceil(m / 8) vectors: q -> entry 8 (q % nv) + q / nv.
-#define USB_HALF_BLOCK 65535u
-#define USB_HALF_MAX_TARGETS (2u * USB_HALF_BLOCK)
+// The same index as 2-byte "increment descriptors" laid out for the way a warp of k_rank walks a
+// row, for static indexes of at most USB_HALF_MAX_TARGETS targets starting at target 0.  It halves
+// the HBM bytes of the U-sort walk, removes most shared-memory bank conflicts of the counter
+// increments and cuts the walk to three instructions per posting (extract, address, ATOMS),
+// which is what bounds it on B200 (profiles/README.md).
+//   * The counter of target t is byte t % 4 of the 32-bit shared-memory word t / 4.  An entry is
+//     the word index t / 4 (16 bits); the byte is implied by the entry's position.
+//   * A row is a whole number of groups of 256 entries = 32 lanes x one 128-bit vector.  Lane l
+//     loads vector 32 g + l of group g; the warp then issues one increment instruction per entry
+//     index i = 0..7, i.e. for the entries {256 g + 8 l + i : l}.  Entries i = 2b and 2b + 1 hold
+//     targets with t % 4 == b, so the increment value 1 << 8b is a constant of the instruction.
+//   * The order of the postings inside a row does not matter for U: the targets of each byte
+//     class are dealt round-robin over the 32 banks (bank = (t / 4) % 32), so the 32 increments
+//     of one instruction fall into (mostly) different banks.
+//   * Unused entries of lane l point at dummy word dummy0 + l behind the counters (one per bank),
+//     so the walk has no validity tests at all.  row_groups[w] = max over the byte classes of
+//     ceil(n_class / 64): about 7 % padding at 2 146 postings per row.
+#define USB_HALF_MAX_TARGETS 200000u
 struct HostHalf {
-	uint32_t n_blocks = 1;
-	std::vector<uint64_t> row_off;   // slots * n_blocks + 1
-	std::vector<uint32_t> row_size;  // slots * n_blocks
+	uint32_t dummy0 = 0;             // first dummy word = round16(n_targets) / 4
+	std::vector<uint64_t> row_off;   // slots + 1, in entries (multiples of 256)
+	std::vector<uint32_t> row_groups; // slots
 	std::vector<uint16_t> postings;
 };
 void make_half(const HostCSR &H, uint32_t n_targets, int n_threads, HostHalf &out);

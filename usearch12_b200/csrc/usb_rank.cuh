@@ -40,6 +40,9 @@ namespace usb {
 #define RANK_THREADS_2 512     // k_rank when two CTAs fit per SM
 #define RANK_VEC 4u            // 128-bit posting loads in flight per lane
 #define RANK_CHUNK (128u * RANK_VEC) // postings per warp iteration of the walk
+#ifndef RANK_VEC16
+#define RANK_VEC16 4u          // same for the 2-byte layout (8 measured no faster)
+#endif
 #define RANK_KCAP 1024         // max candidates materialised per query
 #define RANK_REC_NARROW 256
 #define RANK_REC_WIDE 2048
@@ -460,22 +463,28 @@ __device__ __forceinline__ void vec_count(uint32_t *U32, const uint4 &x, uint32_
 	}
 }
 
-// One vector of eight 2-byte postings of the bank-aware layout (usb_hostindex.h HostHalf); hi =
-// first target of the fragment's block.  CHECKED: the vector belongs to the ragged last group of
-// its fragment, whose padding entries (0xffff) are skipped.
-template <bool WIDE, bool CHECKED>
-__device__ __forceinline__ void vec_count16(uint32_t *U32, const uint4 &x, uint32_t hi)
+// One vector of eight 2-byte increment descriptors (usb_hostindex.h HostHalf): entry i is the
+// index of a 32-bit counter word, its byte class is i / 2.  Narrow counters: one ATOMS per entry
+// with a constant increment.  Wide (16-bit) counters: target 4 w + b lives in halfword b % 2 of
+// word 2 w + b / 2.
+template <bool WIDE>
+__device__ __forceinline__ void vec_count16(uint32_t *U32, const uint4 &x)
 {
-#define USB_INC16(W)                                                     \
-	{                                                                    \
-		const uint32_t lo_ = (W) & 0xffffu, hi_ = (W) >> 16;             \
-		if (!CHECKED || lo_ != 0xffffu) u_inc<WIDE>(U32, lo_ + hi);      \
-		if (!CHECKED || hi_ != 0xffffu) u_inc<WIDE>(U32, hi_ + hi);      \
+#define USB_INC16(W, B)                                                                  \
+	{                                                                                    \
+		const uint32_t lo_ = (W) & 0xffffu, hi_ = (W) >> 16;                             \
+		if (WIDE) {                                                                      \
+			atomicAdd(&U32[2 * lo_ + ((B) >> 1)], 1u << (16 * ((B) & 1)));               \
+			atomicAdd(&U32[2 * hi_ + ((B) >> 1)], 1u << (16 * ((B) & 1)));               \
+		} else {                                                                         \
+			atomicAdd(&U32[lo_], 1u << (8 * (B)));                                       \
+			atomicAdd(&U32[hi_], 1u << (8 * (B)));                                       \
+		}                                                                                \
 	}
-	USB_INC16(x.x)
-	USB_INC16(x.y)
-	USB_INC16(x.z)
-	USB_INC16(x.w)
+	USB_INC16(x.x, 0)
+	USB_INC16(x.y, 1)
+	USB_INC16(x.z, 2)
+	USB_INC16(x.w, 3)
 #undef USB_INC16
 }
 
@@ -514,9 +523,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 	uint32_t *U32 = (uint32_t *)U;
 	uint32_t *bitmap = X.bitmap;
 	const bool one_seg = a.ix.n_seg == 1;
-	// HALF: 2-byte postings, one or two row fragments per word; a pass then takes NT / blocks
-	// positions so that its fragment descriptors fit the NT entries of r_off / r_size
-	const uint32_t PW = HALF ? NT / a.ix.half_blocks : NT;
+	const uint32_t PW = NT; // query positions per pass
 #define USB_PHASE(i)                                               \
 	if (a.prof && tid == 0) {                                      \
 		const long long now = clock64();                           \
@@ -584,19 +591,15 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				}
 			}
 			if (fresh && HALF) {
-				// descriptors of the word's row fragments (block in the top bit of the size)
-				const uint32_t nb = a.ix.half_blocks;
-				const uint32_t s0 = __ldg(a.ix.row_size16 + word * nb), s1 = nb > 1 ? __ldg(a.ix.row_size16 + word * nb + 1) : 0u;
-				const uint64_t o0 = __ldg(a.ix.row_off16 + word * nb), o1 = nb > 1 ? __ldg(a.ix.row_off16 + word * nb + 1) : 0ull;
-				if (s0) {
+				// row descriptor now: the loads of all unique words of the pass overlap
+				const uint32_t size = __ldg(a.ix.seg[0].row_size + word);
+				const uint32_t groups = __ldg(a.ix.row_groups + word);
+				const uint64_t off = __ldg(a.ix.row_off16 + word);
+				if (size) {
 					const uint32_t idx = atomicAdd(&S.n_rows, 1u);
-					X.r_off[idx] = (uint32_t)(o0 >> 3);
-					X.r_size[idx] = s0;
-				}
-				if (s1) {
-					const uint32_t idx = atomicAdd(&S.n_rows, 1u);
-					X.r_off[idx] = (uint32_t)(o1 >> 3);
-					X.r_size[idx] = s1 | 0x80000000u;
+					X.r_off[idx] = (uint32_t)(off >> 3);
+					X.r_size[idx] = groups;
+					atomicAdd(&S.n_post, size);
 				}
 			} else if (fresh) {
 				if (one_seg) {
@@ -616,13 +619,15 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		__syncthreads();
 		const uint32_t n_rows = S.n_rows;
 		if (HALF || one_seg) {
-			const uint32_t size = tid < n_rows ? X.r_size[tid] & 0x7fffffffu : 0;
-			const uint32_t sz = __reduce_add_sync(USB_FULL, size);
-			if (lane == 0 && sz)
-				atomicAdd(&S.n_post, sz);
+			if (!HALF) {
+				const uint32_t size = tid < n_rows ? X.r_size[tid] : 0;
+				const uint32_t sz = __reduce_add_sync(USB_FULL, size);
+				if (lane == 0 && sz)
+					atomicAdd(&S.n_post, sz);
+			}
 			USB_PHASE(1)
 			const uint4 *P4 = HALF ? (const uint4 *)a.ix.post16 : (const uint4 *)a.ix.seg[0].postings;
-			// whole rows (row fragments) per warp, drawn from a shared cursor
+			// whole rows per warp, drawn from a shared cursor
 			for (;;) {
 				uint32_t r = 0;
 				if (lane == 0)
@@ -630,26 +635,21 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				r = __shfl_sync(USB_FULL, r, 0);
 				if (r >= n_rows)
 					break;
-				const uint32_t size = X.r_size[r] & 0x7fffffffu;
+				const uint32_t size = X.r_size[r];
 				const uint4 *v4 = P4 + X.r_off[r];
 				if (HALF) {
-					const uint32_t hi = (X.r_size[r] >> 31) * 65535u;
-					const uint32_t vfull = (size >> 8) * 32;            // vectors of whole 256-entry groups
-					const uint32_t vall = vfull + (((size & 255u) + 7) >> 3);
-					for (uint32_t s0 = 0; s0 < vall; s0 += 32 * RANK_VEC) {
-						uint4 x[RANK_VEC];
+					// size = groups of 32 vectors; every entry is a valid increment (padding
+					// points at dummy words), so there is nothing to test
+					for (uint32_t g0 = 0; g0 < size; g0 += RANK_VEC16) {
+						uint4 x[RANK_VEC16];
 #pragma unroll
-						for (uint32_t j = 0; j < RANK_VEC; ++j)
-							if (s0 + 32 * j + lane < vall)
-								x[j] = ld_stream128(v4 + s0 + 32 * j + lane);
+						for (uint32_t j = 0; j < RANK_VEC16; ++j)
+							if (g0 + j < size)
+								x[j] = ld_stream128(v4 + (g0 + j) * 32 + lane);
 #pragma unroll
-						for (uint32_t j = 0; j < RANK_VEC; ++j) {
-							const uint32_t slot = s0 + 32 * j + lane;
-							if (slot < vfull)
-								vec_count16<WIDE, false>(U32, x[j], hi);
-							else if (slot < vall)
-								vec_count16<WIDE, true>(U32, x[j], hi);
-						}
+						for (uint32_t j = 0; j < RANK_VEC16; ++j)
+							if (g0 + j < size)
+								vec_count16<WIDE>(U32, x[j]);
 					}
 					continue;
 				}
@@ -898,7 +898,9 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank(const RankArgs a)
 inline size_t rank_smem_bytes(uint32_t n_seq, bool wide, size_t dedupe_bytes, uint32_t rec_cap, uint32_t threads,
   uint32_t *u_bytes)
 {
-	size_t ub = (((size_t)n_seq * (wide ? 2 : 1)) + 15) & ~(size_t)15;
+	// + the dummy words behind the counters that padding entries of the 2-byte layout increment
+	// (usb_hostindex.h HostHalf: words dummy0 .. dummy0 + 31, twice as far for 16-bit counters)
+	size_t ub = ((((size_t)n_seq + 15) & ~(size_t)15) + 128) * (wide ? 2 : 1);
 	*u_bytes = (uint32_t)ub;
 	const size_t walk = dedupe_bytes + (size_t)4 * (2 * threads);
 	const size_t rank = (size_t)8 * RANK_KCAP + (size_t)16 * rec_cap + 4 * 256;
