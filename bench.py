@@ -317,13 +317,20 @@ def main():
         dom_ms = (k2 if k2 >= k1 else k1) / a.steps
         dom_bytes = b_k2 if k2 >= k1 else b_k1
         achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
-        traffic = None
+        traffic, prof = None, {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            if prof.get("workload") == workload_name(a):
-                traffic = prof.get(dom)
+            if prof.get("workload") != workload_name(a):
+                prof = {}
+            traffic = prof.get(dom)
         except (OSError, ValueError):
             pass
+
+        def kernel_line(name, ms, nbytes, bound):
+            gbps = nbytes / (ms / a.steps / 1000.0) / 1e9 if ms else None
+            return {"ms": ms / a.steps, "share_of_step": ms / max(k1 + k2, 1e-9), "algorithmic_bytes_per_launch": nbytes,
+                    "achieved_GBps": gbps, "frac_of_hbm_peak": gbps / peak if gbps else None, "traffic": prof.get(name),
+                    "bound": bound}
         line = {
             "metric": METRIC, "value": value, "unit": "query-seqs/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -338,8 +345,11 @@ def main():
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": dom_bytes,
-                         "other": {"k_rank_GBps": b_k1 / (k1 / a.steps / 1000.0) / 1e9 if k1 else None,
-                                   "k_align_GBps": b_k2 / (k2 / a.steps / 1000.0) / 1e9 if k2 else None}},
+                         "kernels": {
+                             "k_rank": kernel_line("k_rank", k1, b_k1, "hbm during the posting walk; a third of the launch is a "
+                                                   "serial scan/select tail (DESIGN.md section 3)"),
+                             "k_align": kernel_line("k_align", k2, b_k2, "instruction issue / latency (ncu: issue slots ~48 % "
+                                                    "busy, DRAM < 1 % of peak): its HBM fraction is small by construction")}},
             "e2e": {"value": e2e, "unit": "query-seqs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -14,6 +14,6 @@ except Exception as e:
 PY
   grep "phase cycles" gpurun_out/bench_$name.err | tail -1
 }
-run v3
-run v3_p USB_RANK_PROF=1
-run v3_one_p USB_RANK_ONE_CTA=1 USB_RANK_PROF=1
+run e64_p USB_RANK_PROF=1
+run e0_p USB_RANK_EARLY=0 USB_RANK_PROF=1
+run e128_p USB_RANK_EARLY=128 USB_RANK_PROF=1

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <thread>
 
 namespace usbhost {
@@ -87,15 +88,22 @@ void SeqDB::FromFasta(const std::string &FileName)
 		} else if (q > p) {
 			if (!have_label)
 				Die("Bad FASTA file %s, expected '>' in line %u", FileName.c_str(), line_nr);
-			for (const char *c = p; c < q; ++c) {
-				unsigned char ch = (unsigned char)*c;
-				if (isalpha(ch))
-					m_Letters.push_back(ch);
-				else if (isspace(ch) || ch == '-' || ch == '.')
-					continue;
-				else
-					++bad_bytes;
-			}
+			// lines of letters only (the normal case) are appended in one piece
+			const char *c = p;
+			while (c < q && (((unsigned char)*c | 0x20u) - 'a') < 26u)
+				++c;
+			if (c == q)
+				m_Letters.insert(m_Letters.end(), (const uint8_t *)p, (const uint8_t *)q);
+			else
+				for (c = p; c < q; ++c) {
+					unsigned char ch = (unsigned char)*c;
+					if (isalpha(ch))
+						m_Letters.push_back(ch);
+					else if (isspace(ch) || ch == '-' || ch == '.')
+						continue;
+					else
+						++bad_bytes;
+				}
 		}
 		p = eol + 1;
 	}
@@ -227,7 +235,7 @@ static void appendf(std::string &s, const char *fmt, ...)
 }
 
 // outputuc.cpp:19-22,45-69
-void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM)
+void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &m_bUC) const
 {
 	if (!m_fUC)
 		return;
@@ -248,11 +256,10 @@ void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM)
 		m_bUC += AR.GetTargetLabel();
 		m_bUC += '\n';
 	}
-	Flush(m_fUC, m_bUC, false);
 }
 
 // blast6out.cpp:27-80 (global alignments: evalue and bit score print as '*')
-void OutputSink::OutputBlast6(const HitMgr &HM)
+void OutputSink::OutputBlast6(const HitMgr &HM, std::string &m_bB6) const
 {
 	if (!m_fB6)
 		return;
@@ -267,11 +274,10 @@ void OutputSink::OutputBlast6(const HitMgr &HM)
 		else
 			m_bB6 += "\t*\t*\n";
 	}
-	Flush(m_fB6, m_bB6, false);
 }
 
 // userout.cpp:126-215
-void OutputSink::OutputUser(const HitMgr &HM)
+void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 {
 	if (!m_fUser)
 		return;
@@ -323,14 +329,51 @@ void OutputSink::OutputUser(const HitMgr &HM)
 		}
 		m_bUser += '\n';
 	}
-	Flush(m_fUser, m_bUser, false);
 }
 
 void OutputSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
 {
-	OutputUC(Query, HM);
-	OutputBlast6(HM);
-	OutputUser(HM);
+	OutputUC(Query, HM, m_bUC);
+	OutputBlast6(HM, m_bB6);
+	OutputUser(HM, m_bUser);
+	Flush(m_fUC, m_bUC, false);
+	Flush(m_fB6, m_bB6, false);
+	Flush(m_fUser, m_bUser, false);
+}
+
+void OutputSink::OnBatchDone(const std::vector<HitMgr> &Batch)
+{
+	const size_t n = Batch.size();
+	const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, n / 4096}));
+	if (T <= 1) {
+		for (const HitMgr &HM : Batch)
+			OnQueryDone(HM.m_Query, HM);
+		return;
+	}
+	struct Chunk {
+		std::string uc, b6, user;
+	};
+	std::vector<Chunk> chunks(T);
+	std::vector<std::thread> th;
+	for (unsigned k = 0; k < T; ++k)
+		th.emplace_back([&, k]() {
+			Chunk &c = chunks[k];
+			for (size_t i = n * k / T; i < n * (k + 1) / T; ++i) {
+				OutputUC(Batch[i].m_Query, Batch[i], c.uc);
+				OutputBlast6(Batch[i], c.b6);
+				OutputUser(Batch[i], c.user);
+			}
+		});
+	for (auto &t : th)
+		t.join();
+	Flush(m_fUC, m_bUC, true);
+	Flush(m_fB6, m_bB6, true);
+	Flush(m_fUser, m_bUser, true);
+	for (Chunk &c : chunks) {
+		Flush(m_fUC, c.uc, true);
+		Flush(m_fB6, c.b6, true);
+		Flush(m_fUser, c.user, true);
+	}
 }
 
 // ------------------------------------------------------------------ GpuSearcher
@@ -358,12 +401,13 @@ void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Cou
 	const uint64_t *qoff = usb_result_query_offsets(R);
 	uint64_t n_runs = 0;
 	const uint32_t *runs = usb_result_runs(R, &n_runs);
-	// the run arena must outlive the result handle: keep a copy owned by the first HitMgr's vector
+	// the run arena must outlive the result handle: a copy shared by the batch's HitMgrs
 	auto arena = std::make_shared<std::vector<uint32_t>>(runs, runs + n_runs);
-	m_Arenas.push_back(arena);
 	Out.resize(Count);
 	for (uint32_t q = 0; q < Count; ++q) {
 		HitMgr &HM = Out[q];
+		if (q == 0 || qoff[q] != qoff[q + 1])
+			HM.m_Arena = arena;
 		Queries.GetSI(First + q, HM.m_Query);
 		HM.m_Hits.clear();
 		for (uint64_t k = qoff[q]; k < qoff[q + 1]; ++k) {
@@ -383,8 +427,6 @@ void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Cou
 	}
 	usb_result_free(R);
 }
-
-void GpuSearcher::ReleaseArenas() { m_Arenas.clear(); }
 
 bool GuessIsNucleo(const std::string &FastaFileName)
 {
@@ -426,11 +468,14 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	if (ndev <= 0)
 		Die("No CUDA device available: this build has no CPU search path");
 	const int gpus = std::min(std::max(1, Opts.gpus), ndev);
+	const bool timing = getenv("USB_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_start = now();
+	// the query file is parsed while the database is parsed, indexed and uploaded
 	SeqDB DB, Q;
+	std::thread parse_q([&]() { Q.FromFasta(QueryFileName); });
 	DB.FromFasta(DBFileName);
-	Q.FromFasta(QueryFileName);
-	if (!Opts.quiet)
-		fprintf(stderr, "%u db seqs, %u query seqs, %d GPU(s)\n", DB.GetSeqCount(), Q.GetSeqCount(), gpus);
+	const double t_db = now();
 	std::vector<GpuSearcher *> searchers(gpus, nullptr);
 	{
 		std::vector<std::thread> th;
@@ -439,15 +484,20 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		for (auto &t : th)
 			t.join();
 	}
+	parse_q.join();
+	const double t_ready = now();
+	if (!Opts.quiet)
+		fprintf(stderr, "%u db seqs, %u query seqs, %d GPU(s)\n", DB.GetSeqCount(), Q.GetSeqCount(), gpus);
 	OutputSink Sink(Opts.Out);
 	const uint32_t NQ = Q.GetSeqCount();
 	const uint32_t nbatch = (NQ + Opts.batch - 1) / Opts.batch;
 	uint64_t queries_with_hits = 0;
-	// batches are dealt round-robin to the devices and drained in input order, so the output
-	// files are in query order for any GPU count (the reference guarantees that only for 1 thread)
-	for (uint32_t b0 = 0; b0 < nbatch; b0 += gpus) {
+	// Batches are dealt round-robin to the devices and drained in input order, so the output
+	// files are in query order for any GPU count (the reference guarantees that only for 1
+	// thread).  While one group of batches is formatted and written, the next one is searched.
+	auto run_group = [&](uint32_t b0, std::vector<std::vector<HitMgr>> &results) {
 		const uint32_t nb = std::min<uint32_t>(gpus, nbatch - b0);
-		std::vector<std::vector<HitMgr>> results(nb);
+		results.assign(nb, std::vector<HitMgr>());
 		std::vector<std::thread> th;
 		for (uint32_t k = 0; k < nb; ++k)
 			th.emplace_back([&, k]() {
@@ -456,17 +506,37 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 			});
 		for (auto &t : th)
 			t.join();
-		for (uint32_t k = 0; k < nb; ++k) {
-			for (const HitMgr &HM : results[k]) {
-				Sink.OnQueryDone(HM.m_Query, HM);
+	};
+	std::vector<std::vector<HitMgr>> cur, nxt;
+	double t_wait = 0, t_sink = 0;
+	if (nbatch)
+		run_group(0, cur);
+	for (uint32_t b0 = 0; b0 < nbatch; b0 += gpus) {
+		const bool more = b0 + gpus < nbatch;
+		std::thread ahead;
+		if (more)
+			ahead = std::thread([&]() { run_group(b0 + gpus, nxt); });
+		const double t0 = now();
+		for (const std::vector<HitMgr> &batch : cur) {
+			Sink.OnBatchDone(batch);
+			for (const HitMgr &HM : batch)
 				queries_with_hits += HM.GetHitCount() > 0;
-			}
-			searchers[k]->ReleaseArenas();
 		}
+		const double t1 = now();
+		cur.clear();
+		if (more) {
+			ahead.join();
+			cur.swap(nxt);
+		}
+		t_sink += t1 - t0;
+		t_wait += now() - t1;
 	}
 	Sink.OnAllDone();
 	for (GpuSearcher *s : searchers)
 		delete s;
+	if (timing)
+		fprintf(stderr, "timing: db parse %.2fs, index+upload (query parse alongside) %.2fs, search+output %.2fs (sinks %.2fs, waiting for the GPU %.2fs)\n",
+		  t_db - t_start, t_ready - t_db, now() - t_ready, t_sink, t_wait);
 	return queries_with_hits;
 }
 

@@ -113,6 +113,7 @@ class HitMgr {
 public:
 	SeqInfo m_Query;
 	std::vector<AlignResult> m_Hits;
+	std::shared_ptr<std::vector<uint32_t>> m_Arena; // run arena the hits' paths point into
 	unsigned GetHitCount() const { return (unsigned)m_Hits.size(); }
 	const AlignResult *GetTopHit() const { return m_Hits.empty() ? nullptr : &m_Hits[0]; }
 };
@@ -121,6 +122,12 @@ class HitSink {
 public:
 	virtual ~HitSink() {}
 	virtual void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) = 0;
+	// all queries of a batch, in input order (default: one OnQueryDone per query)
+	virtual void OnBatchDone(const std::vector<HitMgr> &Batch)
+	{
+		for (const HitMgr &HM : Batch)
+			OnQueryDone(HM.m_Query, HM);
+	}
 	virtual void OnAllDone() {}
 };
 
@@ -135,13 +142,16 @@ public:
 	explicit OutputSink(const OutputOpts &O);
 	~OutputSink() override;
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
+	// the reference formats under one lock (outputsink.cpp:360,380); here the queries of a batch
+	// are formatted by several threads into per-chunk buffers that are written in input order
+	void OnBatchDone(const std::vector<HitMgr> &Batch) override;
 	void OnAllDone() override;
 
 private:
 	void Flush(FILE *f, std::string &buf, bool force);
-	void OutputUC(const SeqInfo &Query, const HitMgr &HM);
-	void OutputBlast6(const HitMgr &HM);
-	void OutputUser(const HitMgr &HM);
+	void OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &out) const;
+	void OutputBlast6(const HitMgr &HM, std::string &out) const;
+	void OutputUser(const HitMgr &HM, std::string &out) const;
 	FILE *m_fUC = nullptr, *m_fB6 = nullptr, *m_fUser = nullptr;
 	std::string m_bUC, m_bB6, m_bUser;
 	std::vector<int> m_UserFields;
@@ -162,11 +172,8 @@ public:
 	~GpuSearcher() override;
 	void SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out) override;
 	uint64_t GetLaunchCount() const;
-	// AlignResults of a batch point into a run arena owned here; release it once the sinks ran
-	void ReleaseArenas();
 
 private:
-	std::vector<std::shared_ptr<std::vector<uint32_t>>> m_Arenas;
 	const SeqDB &m_DB;
 	usb_params m_P;
 	usb_index *m_Index = nullptr;
