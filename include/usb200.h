@@ -130,6 +130,30 @@ int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint
 /* Masked target sequence as indexed (SeqDB::GetSeq after SeqDB::Mask, seqdb.cpp:415). */
 int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t **seq, uint32_t *len);
 
+/* ---- .udb database files (udbfile.h:17-62, udbio.cpp:242-364, seqdbio.cpp:17-258).  Host only: these
+ * entry points need no device.
+ * usb_udb_write = -makeudb_usearch (makeudb.cpp:27-60): MaskDB + UDBData::FromSeqDB + ToUDBFile for
+ * the default index (not hashed / coded / spaced, -dbstep 1, -dbaccelpct 100); the file is byte for
+ * byte the one the reference writes, so either program can load the other's databases.
+ * labels[i] = NUL-terminated label of target i. */
+int usb_udb_write(const char *path, const usb_params *p, const uint8_t *seqs, const uint64_t *seq_off,
+  const char *const *labels, uint32_t n_seq);
+/* 1 when the file starts with the .udb magic (loaddb.cpp:100-107 picks the loader the same way). */
+int usb_udb_probe(const char *path);
+/* UDBData::FromUDBFile (udbio.cpp:242-279): header, row sizes, rows, SeqDB.  The sequences come
+ * back masked as stored (lower case = masked): pass them to usb_index_create with dbmask = 0,
+ * like the reference, which does not mask a loaded .udb again (loaddb.cpp:107-118). */
+typedef struct usb_udb usb_udb;
+int usb_udb_read(const char *path, usb_udb **out);
+void usb_udb_free(usb_udb *u);
+uint32_t usb_udb_seq_count(const usb_udb *u);
+int usb_udb_is_nucleo(const usb_udb *u);
+uint32_t usb_udb_word_length(const usb_udb *u);
+const uint8_t *usb_udb_seqs(const usb_udb *u, const uint64_t **seq_off);
+const char *usb_udb_label(const usb_udb *u, uint32_t i);
+/* m_UDBRows[word], m_Sizes[word] as stored in the file (parity checks against usb_index_row). */
+int usb_udb_row(const usb_udb *u, uint32_t word, const uint32_t **row, uint32_t *size);
+
 /* ---- searcher: replaces MakeDBSearcher (makedbsearcher.cpp:75) wiring for one device. */
 int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searcher **out);
 void usb_searcher_free(usb_searcher *s);

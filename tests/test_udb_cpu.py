@@ -1,0 +1,94 @@
+""".udb files: usb_udb_write must produce, byte for byte, the file the
+reference's -makeudb_usearch writes (udbio.cpp:281-364, seqdbio.cpp:17-135), and usb_udb_read must
+take such a file apart again.  Host-only entry points: no GPU needed."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import util
+from usearch12_b200 import capi
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "usearch12")
+DIGESTS = json.load(open(os.path.join(GOLDEN, "udb_sha256.json")))
+
+
+def params_for(name):
+    p = capi.default_params()
+    if "aa" in name:
+        capi.lib().usb_set_local(C.byref(p), 0, 1e-5)
+    return p
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS))
+def test_udb_write_is_byte_identical_to_the_reference(name, tmp_path):
+    labels, seqs = util.read_fasta(os.path.join(GOLDEN, name))
+    path = str(tmp_path / "ours.udb")
+    capi.udb_write(path, labels, seqs, params_for(name))
+    ours = open(path, "rb").read()
+    assert len(ours) == DIGESTS[name]["bytes"]
+    assert hashlib.sha256(ours).hexdigest() == DIGESTS[name]["sha256"]
+    assert capi.lib().usb_udb_probe(path.encode()) == 1
+    if os.path.exists(REF):  # this container: the reference binary itself, byte by byte
+        fa = str(tmp_path / "in.fa")
+        with gzip.open(os.path.join(GOLDEN, name), "rb") as f, open(fa, "wb") as g:
+            g.write(f.read())
+        ref = str(tmp_path / "ref.udb")
+        subprocess.run([REF, "-makeudb_usearch", fa, "-output", ref, "-quiet"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        assert open(ref, "rb").read() == ours
+
+
+def test_udb_read_round_trip(tmp_path):
+    labels, seqs = util.read_fasta(os.path.join(GOLDEN, "db.fa.gz"))
+    path = str(tmp_path / "db.udb")
+    capi.udb_write(path, labels, seqs)
+    u = capi.Udb(path)
+    assert u.n_seq == len(seqs) and u.is_nucleo and u.word_length == 8
+    assert u.labels == labels
+    # stored letters = the masked database: same letters, lower case where FastMaskSeq masked
+    assert [s.upper() for s in u.seqs] == [s.upper().encode() for s in seqs]
+    assert any(s != s.upper() for s in u.seqs)
+    # rows: ascending, every target at most once, and exactly the targets that contain the word unmasked
+    code = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("T"): 3}
+    want = {}
+    for t, s in enumerate(u.seqs):
+        for i in range(len(s) - 7):
+            w = 0
+            for c in s[i:i + 8]:
+                if c not in code:
+                    w = -1
+                    break
+                w = w * 4 + code[c]
+            if w >= 0:
+                want.setdefault(w, set()).add(t)
+    rng = np.random.default_rng(5)
+    words = list(rng.integers(0, 65536, 300)) + list(want)[:300]
+    for w in words:
+        row = u.row(int(w))
+        assert list(row) == sorted(want.get(int(w), ()))
+    u.close()
+
+
+def test_udb_read_rejects_other_files(tmp_path):
+    bad = tmp_path / "x.udb"
+    bad.write_bytes(b">seq\nACGT\n")
+    assert capi.lib().usb_udb_probe(str(bad).encode()) == 0
+    h = C.c_void_p()
+    assert capi.lib().usb_udb_read(str(bad).encode(), C.byref(h)) == -1
+    assert b"not a .udb file" in capi.lib().usb_last_error()
+    labels, seqs = util.read_fasta(os.path.join(GOLDEN, "db.fa.gz"))
+    path = str(tmp_path / "db.udb")
+    capi.udb_write(path, labels[:50], seqs[:50])
+    whole = open(path, "rb").read()
+    trunc = tmp_path / "t.udb"
+    trunc.write_bytes(whole[:len(whole) - 1000])
+    assert capi.lib().usb_udb_read(str(trunc).encode(), C.byref(h)) == -1
+    assert b"truncated" in capi.lib().usb_last_error()
+    assert capi.lib().usb_udb_write(path.encode(), C.byref(capi.default_params()), None, None, None, 0) == -1

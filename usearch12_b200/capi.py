@@ -53,6 +53,8 @@ SYMBOLS = [
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
     "usb_viterbi_batch", "usb_set_local", "usb_local_evalue", "usb_local_pairs",
+    "usb_udb_write", "usb_udb_probe", "usb_udb_read", "usb_udb_free", "usb_udb_seq_count", "usb_udb_is_nucleo",
+    "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row",
 ]
 
 _lib = None
@@ -79,6 +81,21 @@ def lib():
     L.usb_index_posting_count.restype = C.c_uint64
     L.usb_index_posting_width.argtypes = [vp]
     L.usb_index_posting_width.restype = C.c_uint32
+    L.usb_udb_write.argtypes = [C.c_char_p, C.POINTER(Params), vp, vp, C.POINTER(C.c_char_p), C.c_uint32]
+    L.usb_udb_probe.argtypes = [C.c_char_p]
+    L.usb_udb_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.usb_udb_free.argtypes = [vp]
+    L.usb_udb_free.restype = None
+    L.usb_udb_seq_count.argtypes = [vp]
+    L.usb_udb_seq_count.restype = C.c_uint32
+    L.usb_udb_is_nucleo.argtypes = [vp]
+    L.usb_udb_word_length.argtypes = [vp]
+    L.usb_udb_word_length.restype = C.c_uint32
+    L.usb_udb_seqs.argtypes = [vp, C.POINTER(u64p)]
+    L.usb_udb_seqs.restype = u8p
+    L.usb_udb_label.argtypes = [vp, C.c_uint32]
+    L.usb_udb_label.restype = C.c_char_p
+    L.usb_udb_row.argtypes = [vp, C.c_uint32, C.POINTER(u32p), u32p]
     L.usb_index_row.argtypes = [vp, C.c_uint32, C.POINTER(u32p), u32p]
     L.usb_index_seq.argtypes = [vp, C.c_uint32, C.POINTER(u8p), u32p]
     L.usb_searcher_create.argtypes = [vp, C.POINTER(Params), C.POINTER(vp)]
@@ -180,6 +197,46 @@ class Result:
         ops = "MDI?"
         r = self.runs[int(hit["run_off"]):int(hit["run_off"]) + int(hit["run_cnt"])]
         return "".join(("%d" % (int(v) >> 2) if (int(v) >> 2) != 1 else "") + ops[int(v) & 3] for v in r)
+
+
+def udb_write(path, labels, seqs, params=None):
+    """-makeudb_usearch (makeudb.cpp:27-60): masks, indexes and writes a .udb file; host only."""
+    p = params or default_params()
+    data, off = pack_seqs(seqs)
+    arr = (C.c_char_p * len(labels))(*[l.encode() if isinstance(l, str) else l for l in labels])
+    check(lib().usb_udb_write(os.fsencode(path), C.byref(p), _ptr(data), _ptr(off), arr, len(seqs)))
+
+
+class Udb:
+    """A .udb file in memory (UDBData::FromUDBFile, udbio.cpp:242-279); host only."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        check(lib().usb_udb_read(os.fsencode(path), C.byref(h)))
+        self.handle = h
+        self.n_seq = lib().usb_udb_seq_count(h)
+        self.is_nucleo = bool(lib().usb_udb_is_nucleo(h))
+        self.word_length = lib().usb_udb_word_length(h)
+        offp = C.POINTER(C.c_uint64)()
+        sp = lib().usb_udb_seqs(h, C.byref(offp))
+        off = np.ctypeslib.as_array(offp, shape=(self.n_seq + 1,)).copy()
+        buf = bytes(np.ctypeslib.as_array(sp, shape=(int(off[-1]),))) if off[-1] else b""
+        self.seqs = [buf[int(off[i]):int(off[i + 1])] for i in range(self.n_seq)]
+        self.labels = [lib().usb_udb_label(h, i).decode() for i in range(self.n_seq)]
+
+    def row(self, word):
+        p = C.POINTER(C.c_uint32)()
+        n = C.c_uint32()
+        check(lib().usb_udb_row(self.handle, word, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def close(self):
+        if self.handle:
+            lib().usb_udb_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
 
 
 class Index:

@@ -112,6 +112,46 @@ void SeqDB::FromFasta(const std::string &FileName)
 		Warning("%u invalid bytes in FASTA file %s ignored", bad_bytes, FileName.c_str());
 }
 
+void SeqDB::FromUDB(const std::string &FileName, bool &IsNucleo, uint32_t &WordLength)
+{
+	usb_udb *u = nullptr;
+	CheckUsb(usb_udb_read(FileName.c_str(), &u), "usb_udb_read");
+	const uint32_t n = usb_udb_seq_count(u);
+	const uint64_t *off = nullptr;
+	const uint8_t *letters = usb_udb_seqs(u, &off);
+	m_Letters.assign(letters, letters + off[n]);
+	m_Offsets.assign(off, off + n + 1);
+	m_Labels.clear();
+	for (uint32_t i = 0; i < n; ++i)
+		m_Labels.push_back(usb_udb_label(u, i));
+	IsNucleo = usb_udb_is_nucleo(u) != 0;
+	WordLength = usb_udb_word_length(u);
+	usb_udb_free(u);
+}
+
+bool IsUDBFile(const std::string &FileName) { return usb_udb_probe(FileName.c_str()) != 0; }
+
+bool UDBIsNucleo(const std::string &FileName)
+{
+	usb_udb *u = nullptr;
+	CheckUsb(usb_udb_read(FileName.c_str(), &u), "usb_udb_read");
+	const bool nucleo = usb_udb_is_nucleo(u) != 0;
+	usb_udb_free(u);
+	return nucleo;
+}
+
+void MakeUDB(const std::string &FastaFileName, const std::string &OutputFileName, const usb_params &P)
+{
+	if (FastaFileName.empty() || OutputFileName.empty())
+		Die("Missing input or output filename"); // makeudb.cpp:30-31
+	SeqDB DB;
+	DB.FromFasta(FastaFileName);
+	std::vector<const char *> labels(DB.GetSeqCount());
+	for (uint32_t i = 0; i < DB.GetSeqCount(); ++i)
+		labels[i] = DB.GetLabel(i);
+	CheckUsb(usb_udb_write(OutputFileName.c_str(), &P, DB.Letters(), DB.Offsets(), labels.data(), DB.GetSeqCount()), "usb_udb_write");
+}
+
 void SeqDB::GetSI(uint32_t Index, SeqInfo &SI) const
 {
 	SI.m_Label = m_Labels[Index].c_str();
@@ -474,13 +514,24 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	// the query file is parsed while the database is parsed, indexed and uploaded
 	SeqDB DB, Q;
 	std::thread parse_q([&]() { Q.FromFasta(QueryFileName); });
-	DB.FromFasta(DBFileName);
+	usb_params P = Opts.P;
+	if (IsUDBFile(DBFileName)) {
+		// LoadUDB (loaddb.cpp:100-127): the stored sequences are masked already
+		bool nucleo = true;
+		uint32_t wl = 0;
+		DB.FromUDB(DBFileName, nucleo, wl);
+		if (nucleo != (P.is_nucleo != 0))
+			Die("%s is a%s database, the command was set up for the other alphabet", DBFileName.c_str(), nucleo ? " nucleotide" : "n amino acid");
+		P.word_length = wl;
+		P.dbmask = 0;
+	} else
+		DB.FromFasta(DBFileName);
 	const double t_db = now();
 	std::vector<GpuSearcher *> searchers(gpus, nullptr);
 	{
 		std::vector<std::thread> th;
 		for (int d = 0; d < gpus; ++d)
-			th.emplace_back([&, d]() { searchers[d] = new GpuSearcher(d, DB, Opts.P); });
+			th.emplace_back([&, d]() { searchers[d] = new GpuSearcher(d, DB, P); });
 		for (auto &t : th)
 			t.join();
 	}

@@ -35,6 +35,9 @@ struct SeqInfo {
 class SeqDB {
 public:
 	void FromFasta(const std::string &FileName);
+	// SeqDB part of a .udb file (UDBData::FromUDBFile, udbio.cpp:242-279): letters come back masked
+	// as stored; returns the alphabet and word width of the file's header
+	void FromUDB(const std::string &FileName, bool &IsNucleo, uint32_t &WordLength);
 	uint32_t GetSeqCount() const { return (uint32_t)m_Offsets.size() - 1; }
 	void GetSI(uint32_t Index, SeqInfo &SI) const;
 	const uint8_t *GetSeq(uint32_t i) const { return m_Letters.data() + m_Offsets[i]; }
@@ -203,7 +206,16 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
 // stride over the first sequences of the file (deterministic).
 bool GuessIsNucleo(const std::string &FastaFileName);
 
-// search.cpp:89 Search(): returns the number of queries with at least one hit.
+// makeudb.cpp:27-60 cmd_makeudb_usearch: mask, index, write a .udb the reference can load too.
+void MakeUDB(const std::string &FastaFileName, const std::string &OutputFileName, const usb_params &P);
+
+// True when the file starts with the .udb magic (loaddb.cpp:100-107 chooses the loader the same way).
+bool IsUDBFile(const std::string &FileName);
+// Alphabet recorded in a .udb header.
+bool UDBIsNucleo(const std::string &FileName);
+
+// search.cpp:89 Search(): returns the number of queries with at least one hit.  DBFileName may be
+// a FASTA file (masked and indexed here, LoadDB loaddb.cpp:129) or a .udb file.
 uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName, const SearchOpts &Opts);
 
 } // namespace usbhost

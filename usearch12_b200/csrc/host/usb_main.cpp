@@ -4,6 +4,8 @@
 //   usearch12_b200 -usearch_global Q.fa -db DB.fa -id 0.97 -strand plus|both
 //        [-maxaccepts n] [-maxrejects n] [-uc f] [-blast6out f] [-userout f] [-userfields a+b+..]
 //        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]
+//   usearch12_b200 -makeudb_usearch DB.fa -output DB.udb [-dbmask fastnucleo|fastamino|none]
+//        (the file is byte for byte the reference's; -db accepts FASTA or .udb, from either program)
 //   usearch12_b200 -usearch_local Q.fa -db DB.fa -id 0.5 -evalue 1e-5 [-strand plus|both for nt DBs]
 //        [-maxaccepts n] [-maxrejects n] [-xdrop_u x] [-xdrop_g x] [-lopen x] [-lext x] [-ka_dbsize x] ...
 // Options of the reference that this build does not implement are refused (Die), never ignored.
@@ -69,6 +71,26 @@ int main(int argc, char **argv)
 		ClusterFast(reads, C);
 		return 0;
 	}
+	const std::string mk = take("makeudb_usearch", nullptr);
+	if (!mk.empty()) {
+		// makeudb.cpp:62 cmd_makeudb_usearch
+		usb_params P;
+		usb_default_params(&P, 0);
+		const bool nt = GuessIsNucleo(mk);
+		if (!nt)
+			usb_set_local(&P, 0, 1.0f); // amino acid alphabet: words of 5 over 20 letters
+		const std::string mask = take("dbmask", nt ? "fastnucleo" : "fastamino");
+		if (mask != (nt ? "fastnucleo" : "fastamino") && mask != "none")
+			Die("-dbmask %s not supported (%s|none)", mask.c_str(), nt ? "fastnucleo" : "fastamino");
+		P.dbmask = mask != "none";
+		const std::string out = take("output", nullptr);
+		take("quiet", nullptr);
+		take("threads", nullptr);
+		if (!opt.empty())
+			Die("Option -%s is not supported by this build", opt.begin()->first.c_str());
+		MakeUDB(mk, out, P);
+		return 0;
+	}
 	SearchOpts O;
 	usb_default_params(&O.P, 0);
 	std::string query = take("usearch_global", nullptr);
@@ -88,7 +110,7 @@ int main(int argc, char **argv)
 		const std::string ev = take("evalue", nullptr);
 		if (ev.empty())
 			Die("Must set -evalue"); // accepter.cpp / search.cpp: mandatory for local searches
-		nucleo = GuessIsNucleo(db);
+		nucleo = IsUDBFile(db) ? UDBIsNucleo(db) : GuessIsNucleo(db);
 		usb_set_local(&O.P, nucleo ? 1 : 0, (float)atof(ev.c_str()));
 		O.P.xdrop_u = (float)atof(take("xdrop_u", "16").c_str());
 		O.P.xdrop_g = (float)atof(take("xdrop_g", "32").c_str());

@@ -32,6 +32,15 @@ static int fail(int code, const char *fmt, ...)
 	return code;
 }
 
+// same for the host-only translation units of the library (usb_udbfile.cpp)
+namespace usb {
+int fail_msg(int code, const char *msg)
+{
+	g_err = msg;
+	return code;
+}
+}
+
 #define CK(call)                                                                                     \
 	do {                                                                                             \
 		cudaError_t e_ = (call);                                                                     \
@@ -442,8 +451,9 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	CK(cudaMemcpy(ix->d_seq_off.p + n0, S.seq_off.data() + n0, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
 	ix->n_dev = n0 + n;
-	// small appends (and everything after the first one) go to the growable tail segment
-	if (ix->dyn || n < 8192) {
+	// small appends (and everything after the first one) go to the growable tail segment; the
+	// initial targets of a search database always form a static segment (2-byte layout)
+	if (ix->dyn || (n < 8192 && (ix->P.cluster_mode || n0 > 0))) {
 		if (!ix->dyn) {
 			ix->dyn = new DynSegment;
 			if ((rc = ix->dyn->init(n0, ix->P.word_length, ix->P.is_nucleo ? 4 : 20)))
