@@ -72,3 +72,34 @@ def test_index_from_udb_sequences_has_the_rows_of_the_file(golden, tmp_path):
         assert ix.seq(t) == u.seqs[t]
     ix.close()
     u.close()
+
+
+def test_device_index_build_equals_host_build():
+    """k_ix_pass / k_ix_scan (usb_ixbuild.inc) against the host builder (usb_hostindex.cpp): every row
+    of a 5 000-target database with masked runs, wildcards, lower case and short targets."""
+    import random
+    rng = random.Random(17)
+    roots = ["".join(rng.choice("ACGT") for _ in range(400)) for _ in range(40)]
+    db = []
+    for i in range(5000):
+        s = util.mutate(roots[i % 40], rng.uniform(0.02, 0.2), rng)
+        k = rng.random()
+        if k < 0.05:
+            s = s[:150] + "A" * 12 + "ACACACACACAC" + s[150:]      # masking triggers
+        elif k < 0.10:
+            s = s[:60] + "N" + s[61:200].lower() + "RY" + s[202:]  # wildcards, lower case
+        elif k < 0.12:
+            s = s[:rng.randrange(0, 12)]                            # shorter than a word / empty-ish
+        db.append(s if s else "A")
+    os.environ["USB_HOST_INDEX"] = "1"
+    try:
+        host = capi.Index(db, capi.default_params(), device=0)
+    finally:
+        del os.environ["USB_HOST_INDEX"]
+    dev = capi.Index(db, capi.default_params(), device=0)
+    assert host.posting_count == dev.posting_count and dev.posting_count > 100000
+    for w in range(65536):
+        a, b = host.row(w), dev.row(w)
+        assert np.array_equal(a, b), w
+    host.close()
+    dev.close()

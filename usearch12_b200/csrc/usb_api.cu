@@ -225,6 +225,8 @@ struct usb_index {
 	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
 
+#include "usb_ixbuild.inc"
+
 // 2-byte postings: one static segment from target 0, at most USB_HALF_MAX_TARGETS, and no use of the
 // big-database or cluster kernels (they walk 4-byte rows).
 static bool index_wants_half(const usb_index *ix)
@@ -467,7 +469,15 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	}
 	// new segment, then merge while the last two are of similar size (or the list is full)
 	IndexSegment *g = new IndexSegment;
-	build_csr(S, n0, n, ix->P.word_length, ix->P.is_nucleo ? 4 : 20, 0, g->H);
+	// nucleotide indexes are built on the device from the letters uploaded above (USB_HOST_INDEX=1:
+	// host builder, the one the tests compare with)
+	if (ix->P.is_nucleo && n >= 2048 && !getenv("USB_HOST_INDEX")) {
+		if ((rc = build_csr_device(ix, n0, n, g->H))) {
+			delete g;
+			return rc;
+		}
+	} else
+		build_csr(S, n0, n, ix->P.word_length, ix->P.is_nucleo ? 4 : 20, 0, g->H);
 	ix->n_postings += g->H.n_postings;
 	ix->segs.push_back(g);
 	bool dirty = true;
