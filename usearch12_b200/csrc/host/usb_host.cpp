@@ -416,6 +416,171 @@ void OutputSink::OnBatchDone(const std::vector<HitMgr> &Batch)
 	}
 }
 
+// ------------------------------------------------------------------ OtuTabSink
+static void SplitFields(const std::string &Str, std::vector<std::string> &Fields, char Sep)
+{
+	// myutils.cpp:1588-1607 Split with a non-zero separator: empty fields are kept, except a last one
+	Fields.clear();
+	std::string s;
+	for (char c : Str) {
+		if (c == Sep) {
+			Fields.push_back(s);
+			s.clear();
+		} else
+			s.push_back(c);
+	}
+	if (!s.empty())
+		Fields.push_back(s);
+}
+
+static void GetStrField(const std::string &Label, const std::string &NameEq, std::string &Value)
+{
+	// label.cpp:27-45
+	Value.clear();
+	std::vector<std::string> Fields;
+	SplitFields(Label, Fields, ';');
+	for (const std::string &F : Fields)
+		if (F.compare(0, NameEq.size(), NameEq) == 0) {
+			Value = F.substr(NameEq.size());
+			break;
+		}
+}
+
+unsigned OtuTabSink::GetSizeFromLabel(const std::string &Label, unsigned Default)
+{
+	const char *p = strstr(Label.c_str(), ";size="); // label.cpp:152-161
+	return p ? (unsigned)atoi(p + 6) : Default;
+}
+
+void OtuTabSink::GetOTUNameFromLabel(const std::string &Label, std::string &OTUName)
+{
+	GetStrField(Label, "otu=", OTUName); // label.cpp:193-202
+	if (!OTUName.empty())
+		return;
+	// GetAccFromLabel, label.cpp:168-182
+	for (char c : Label) {
+		if (c == ' ' || c == '|' || c == ';')
+			if (OTUName != "gi")
+				break;
+		OTUName += c;
+	}
+	if (OTUName.empty())
+		Die("Empty OTU name in label >%s", Label.c_str());
+}
+
+void OtuTabSink::GetSampleNameFromLabel(const std::string &Label, std::string &SampleName) const
+{
+	// label.cpp:204-234
+	GetStrField(Label, "sample=", SampleName);
+	if (!SampleName.empty())
+		return;
+	GetStrField(Label, "barcodelabel=", SampleName);
+	if (!SampleName.empty())
+		return;
+	if (!m_SampleDelim.empty()) {
+		const size_t n = Label.find(m_SampleDelim);
+		if (n == std::string::npos)
+			Die("delim '%s' not found in >%s", m_SampleDelim.c_str(), Label.c_str());
+		SampleName = Label.substr(0, n);
+		return;
+	}
+	for (char c : Label) {
+		if (!isalpha((unsigned char)c) && !isdigit((unsigned char)c) && c != '_')
+			return;
+		SampleName.push_back(c);
+	}
+}
+
+OtuTabSink::OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet)
+  : m_OtuTabOut(OtuTabOut), m_SampleDelim(SampleDelim), m_Quiet(Quiet)
+{
+	if (!MapOut.empty()) {
+		m_fMap = fopen(MapOut.c_str(), "wb");
+		if (!m_fMap)
+			Die("Cannot create %s", MapOut.c_str());
+	}
+}
+
+OtuTabSink::~OtuTabSink() { OnAllDone(); }
+
+unsigned OtuTabSink::IndexAdd(std::vector<std::pair<std::string, unsigned>> &Map, std::vector<std::string> &Names,
+  const std::string &Name, bool &Added)
+{
+	auto it = std::lower_bound(Map.begin(), Map.end(), Name,
+	  [](const std::pair<std::string, unsigned> &a, const std::string &b) { return a.first < b; });
+	Added = it == Map.end() || it->first != Name;
+	if (!Added)
+		return it->second;
+	const unsigned Index = (unsigned)Names.size();
+	Names.push_back(Name);
+	Map.insert(it, std::make_pair(Name, Index));
+	return Index;
+}
+
+void OtuTabSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
+{
+	const std::string QueryLabel = Query.m_Label;
+	const unsigned Size = GetSizeFromLabel(QueryLabel, 1);
+	m_QueryCount += Size;
+	if (HM.GetHitCount() == 0)
+		return;
+	// HitMgr::GetTopHit (hitmgr.cpp:400-420): best float score, ties to the lowest target index
+	const AlignResult *Top = &HM.m_Hits[0];
+	for (const AlignResult &AR : HM.m_Hits)
+		if ((float)AR.GetFractId() > (float)Top->GetFractId() ||
+		    ((float)AR.GetFractId() == (float)Top->GetFractId() && AR.GetTargetIndex() < Top->GetTargetIndex()))
+			Top = &AR;
+	std::string OTUName, SampleName;
+	GetOTUNameFromLabel(Top->GetTargetLabel(), OTUName);
+	GetSampleNameFromLabel(QueryLabel, SampleName);
+	m_AssignedCount += Size;
+	// OTUTable::IncCount (otutab.cpp:548-556): the OTU first, then the sample
+	bool added = false;
+	const unsigned o = IndexAdd(m_OTUIndex, m_OTUNames, OTUName, added);
+	if (added)
+		m_Counts.emplace_back(m_SampleNames.size(), 0u);
+	const unsigned sidx = IndexAdd(m_SampleIndex, m_SampleNames, SampleName, added);
+	if (added)
+		for (auto &row : m_Counts)
+			row.push_back(0);
+	m_Counts[o][sidx] += Size;
+	if (m_fMap)
+		fprintf(m_fMap, "%s\t%s\n", QueryLabel.c_str(), OTUName.c_str());
+}
+
+void OtuTabSink::OnAllDone()
+{
+	if (m_Done)
+		return;
+	m_Done = true;
+	if (!m_Quiet)
+		fprintf(stderr, "%u / %u mapped to OTUs (%.1f%%)\n", m_AssignedCount, m_QueryCount,
+		  m_QueryCount ? 100.0 * m_AssignedCount / m_QueryCount : 0.0);
+	if (m_fMap) {
+		fclose(m_fMap);
+		m_fMap = nullptr;
+	}
+	if (m_OtuTabOut.empty())
+		return;
+	// OTUTable::ToTabbedFile (otutab.cpp:247-310)
+	FILE *f = fopen(m_OtuTabOut.c_str(), "wb");
+	if (!f)
+		Die("Cannot create %s", m_OtuTabOut.c_str());
+	fprintf(f, "#OTU ID");
+	for (const std::string &sn : m_SampleNames) {
+		fputc('\t', f);
+		fputs(sn.c_str(), f);
+	}
+	fputc('\n', f);
+	for (size_t o = 0; o < m_OTUNames.size(); ++o) {
+		fputs(m_OTUNames[o].c_str(), f);
+		for (size_t k = 0; k < m_SampleNames.size(); ++k)
+			fprintf(f, "\t%u", m_Counts[o][k]);
+		fputc('\n', f);
+	}
+	fclose(f);
+}
+
 // ------------------------------------------------------------------ GpuSearcher
 GpuSearcher::GpuSearcher(int Device, const SeqDB &DB, const usb_params &P) : m_DB(DB), m_P(P)
 {
@@ -570,6 +735,8 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		const double t0 = now();
 		for (const std::vector<HitMgr> &batch : cur) {
 			Sink.OnBatchDone(batch);
+			for (HitSink *x : Opts.ExtraSinks)
+				x->OnBatchDone(batch);
 			for (const HitMgr &HM : batch)
 				queries_with_hits += HM.GetHitCount() > 0;
 		}
@@ -583,6 +750,8 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		t_wait += now() - t1;
 	}
 	Sink.OnAllDone();
+	for (HitSink *x : Opts.ExtraSinks)
+		x->OnAllDone();
 	for (GpuSearcher *s : searchers)
 		delete s;
 	if (timing)

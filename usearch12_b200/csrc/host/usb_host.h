@@ -160,6 +160,32 @@ private:
 	std::vector<int> m_UserFields;
 };
 
+// OTU table of -otutab (otutabsink.cpp:25-76, otutab.cpp:247-310,444-556, label.cpp:152-234): every
+// query adds its size= annotation (default 1) to the cell (OTU of its top hit, its sample).  OTUs
+// and samples are numbered in order of first appearance, which with input-order draining is the
+// reference's order for -threads 1.
+class OtuTabSink : public HitSink {
+public:
+	OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet);
+	~OtuTabSink() override;
+	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
+	void OnAllDone() override;
+	static unsigned GetSizeFromLabel(const std::string &Label, unsigned Default);
+	static void GetOTUNameFromLabel(const std::string &Label, std::string &OTUName);
+	void GetSampleNameFromLabel(const std::string &Label, std::string &SampleName) const;
+
+private:
+	std::string m_OtuTabOut, m_SampleDelim;
+	FILE *m_fMap = nullptr;
+	bool m_Quiet = false, m_Done = false;
+	std::vector<std::string> m_OTUNames, m_SampleNames;
+	std::vector<std::vector<unsigned>> m_Counts; // [otu][sample]
+	std::vector<std::pair<std::string, unsigned>> m_OTUIndex, m_SampleIndex; // sorted lookup tables
+	unsigned m_AssignedCount = 0, m_QueryCount = 0;
+	unsigned IndexAdd(std::vector<std::pair<std::string, unsigned>> &Map, std::vector<std::string> &Names, const std::string &Name,
+	  bool &Added);
+};
+
 // Abstract searcher (searcher.h:21-96), batched.
 class Searcher {
 public:
@@ -186,6 +212,7 @@ private:
 struct SearchOpts {
 	usb_params P;
 	OutputOpts Out;
+	std::vector<HitSink *> ExtraSinks; // run after the OutputSink for every batch (not owned)
 	int gpus = 1;
 	uint32_t batch = 1u << 18;
 	bool quiet = false;

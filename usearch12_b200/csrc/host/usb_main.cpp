@@ -4,6 +4,8 @@
 //   usearch12_b200 -usearch_global Q.fa -db DB.fa -id 0.97 -strand plus|both
 //        [-maxaccepts n] [-maxrejects n] [-uc f] [-blast6out f] [-userout f] [-userfields a+b+..]
 //        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]
+//   usearch12_b200 -otutab READS.fa -otus|-zotus|-db OTUS.fa -otutabout TABLE.txt [-mapout MAP.txt]
+//        [-sample_delim s] (searchcmd.cpp:21-40: -id 0.97 -strand both -maxaccepts 3 -maxrejects 32)
 //   usearch12_b200 -makeudb_usearch DB.fa -output DB.udb [-dbmask fastnucleo|fastamino|none]
 //        (the file is byte for byte the reference's; -db accepts FASTA or .udb, from either program)
 //   usearch12_b200 -usearch_local Q.fa -db DB.fa -id 0.5 -evalue 1e-5 [-strand plus|both for nt DBs]
@@ -12,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 
 #include "usb_host.h"
@@ -95,10 +98,29 @@ int main(int argc, char **argv)
 	usb_default_params(&O.P, 0);
 	std::string query = take("usearch_global", nullptr);
 	const std::string lquery = take("usearch_local", nullptr);
-	if (query.empty() && lquery.empty())
-		Die("No command: this build implements -usearch_global, -usearch_local and -cluster_fast");
-	const std::string db = take("db", nullptr);
-	const std::string id = take("id", nullptr);
+	const std::string oquery = take("otutab", nullptr);
+	if (query.empty() && lquery.empty() && oquery.empty())
+		Die("No command: this build implements -usearch_global, -usearch_local, -otutab, -cluster_fast and -makeudb_usearch");
+	std::string db = take("db", nullptr);
+	std::string id = take("id", nullptr);
+	std::unique_ptr<OtuTabSink> otusink;
+	const char *dflt_strand = nullptr, *dflt_ma = "1", *dflt_mr = "32";
+	if (!oquery.empty()) {
+		// searchcmd.cpp:21-40 cmd_otutab: defaults, then the OTU FASTA from -db, -otus or -zotus
+		query = oquery;
+		if (id.empty())
+			id = "0.97";
+		dflt_strand = "both";
+		dflt_ma = "3";
+		const std::string otus = take("otus", nullptr), zotus = take("zotus", nullptr);
+		if (db.empty())
+			db = !otus.empty() ? otus : zotus;
+		if (db.empty())
+			Die("Must specify OTU FASTA -db, -otus or -zotus");
+		const std::string tab = take("otutabout", nullptr), mapout = take("mapout", nullptr);
+		otusink.reset(new OtuTabSink(tab, mapout, take("sample_delim", nullptr), opt.count("quiet") != 0));
+		O.ExtraSinks.push_back(otusink.get());
+	}
 	if (id.empty())
 		Die("--id not set"); // udbusortedsearcher.cpp:99-100: mandatory for both commands
 	O.P.id = (float)atof(id.c_str());
@@ -128,12 +150,12 @@ int main(int argc, char **argv)
 		if (!hw.empty())
 			O.P.hspw = (uint32_t)atoi(hw.c_str());
 	}
-	const std::string strand = take("strand", nullptr);
+	const std::string strand = take("strand", dflt_strand);
 	if (nucleo && strand != "plus" && strand != "both")
 		Die("Must specify -strand plus or both with nt db"); // search.cpp:23-34
 	O.P.strand_both = nucleo && strand == "both";
-	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", "1").c_str());
-	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", "32").c_str());
+	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", dflt_ma).c_str());
+	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", dflt_mr).c_str());
 	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
 	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
 	const std::string dbmask = take("dbmask", nucleo ? "fastnucleo" : "fastamino");
