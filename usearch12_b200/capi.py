@@ -167,25 +167,41 @@ def _ptr(a):
 
 
 class Result:
-    """Host copy of a usb_result (hits grouped by query in the reference's output order)."""
+    """A usb_result (hits grouped by query in the reference's output order).  copy=True (default):
+    numpy copies, the handle is released at once.  copy=False: the arrays are views of the library's
+    buffers, valid while this object is alive (what a C caller of usb_search_batch sees)."""
 
-    def __init__(self, handle, n_groups, n_jobs):
+    def __init__(self, handle, n_groups, n_jobs, copy=True):
         L = lib()
+        self._handle = handle
         n = L.usb_result_hit_count(handle)
-        self.hits = np.zeros(n, dtype=HIT_DTYPE)
-        if n:
-            C.memmove(self.hits.ctypes.data, L.usb_result_hits(handle), n * HIT_DTYPE.itemsize)
+
+        def view(ptr, count, dtype):
+            if not count or not ptr:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(int(ptr))
+            a = np.frombuffer(buf, dtype=dtype, count=count)
+            return a.copy() if copy else a
+
+        self.hits = view(L.usb_result_hits(handle), n, HIT_DTYPE)
         nr = C.c_uint64()
         rp = L.usb_result_runs(handle, C.byref(nr))
-        self.runs = np.zeros(nr.value, dtype=np.uint32)
-        if nr.value:
-            C.memmove(self.runs.ctypes.data, rp, nr.value * 4)
-        self.qoff = np.zeros(n_groups + 1, dtype=np.uint64)
-        C.memmove(self.qoff.ctypes.data, L.usb_result_query_offsets(handle), (n_groups + 1) * 8)
-        self.qstat = np.zeros(n_jobs, dtype=QSTAT_DTYPE)
-        if n_jobs:
-            C.memmove(self.qstat.ctypes.data, L.usb_result_qstats(handle), n_jobs * QSTAT_DTYPE.itemsize)
-        L.usb_result_free(handle)
+        self.runs = view(rp, nr.value, np.uint32)
+        self.qoff = view(L.usb_result_query_offsets(handle), n_groups + 1, np.uint64)
+        self.qstat = view(L.usb_result_qstats(handle), n_jobs, QSTAT_DTYPE)
+        if copy:
+            self.close()
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            lib().usb_result_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def path(self, hit):
         ops = "MDI?"
@@ -301,11 +317,11 @@ class Searcher:
         data, off = pack_seqs(seqs)
         return self.search_packed(data, off)
 
-    def search_packed(self, data, off):
+    def search_packed(self, data, off, copy=True):
         n = len(off) - 1
         h = C.c_void_p()
         check(lib().usb_search_batch(self.handle, _ptr(data), _ptr(off), n, C.byref(h)))
-        return Result(h, n, n * self.strands)
+        return Result(h, n, n * self.strands, copy)
 
     def upload(self, data, off):
         self._nq = len(off) - 1

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -305,6 +306,9 @@ struct usb_searcher {
 	DevBuf<uint8_t> d_slab, d_uarena;
 	size_t rank_smem_set = 0;
 	bool rank_two = false;
+	// pinned host staging for the raw (unordered) hit records of a batch
+	void *h_stage = nullptr;
+	size_t h_stage_cap = 0;
 	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
 	bool bigsmem_set = false;
 	// -usearch_local
@@ -663,6 +667,8 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
 	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release();
+	if (s->h_stage)
+		cudaFreeHost(s->h_stage);
 	for (auto &e : s->ev)
 		if (e)
 			cudaEventDestroy(e);
@@ -1254,29 +1260,77 @@ static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector
 	}
 }
 
+// Result objects are recycled (two at most): their vectors keep their capacity, so a steady stream
+// of batches does not page-fault through ~200 MB of fresh allocations per call.
+static std::mutex g_pool_mu;
+static std::vector<usb_result *> g_pool;
+
+static usb_result *result_new()
+{
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	if (g_pool.empty())
+		return new usb_result;
+	usb_result *r = g_pool.back();
+	g_pool.pop_back();
+	return r;
+}
+
+static void result_recycle(usb_result *r)
+{
+	if (!r)
+		return;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		if (g_pool.size() < 2) {
+			r->hits.clear();
+			r->runs.clear();
+			r->qoff.clear();
+			r->qstat.clear();
+			g_pool.push_back(r);
+			return;
+		}
+	}
+	delete r;
+}
+
 static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result **out)
 {
-	usb_result *r = new usb_result;
+	usb_result *r = result_new();
 	const uint32_t nh = s->last_hits, nr = s->last_runs;
-	std::vector<usb_hit> raw(nh);
+	// raw hits + TopOrder sizes go to pinned staging, the rest straight into the result
+	const size_t raw_bytes = (size_t)nh * sizeof(usb_hit), nc_bytes = (size_t)s->n_jobs * 4;
+	if (raw_bytes + nc_bytes + 64 > s->h_stage_cap) {
+		if (s->h_stage)
+			cudaFreeHost(s->h_stage);
+		s->h_stage = nullptr;
+		s->h_stage_cap = 0;
+		const size_t want = (raw_bytes + nc_bytes + 64) * 5 / 4;
+		if (cudaHostAlloc(&s->h_stage, want, cudaHostAllocDefault) != cudaSuccess) {
+			cudaGetLastError();
+			result_recycle(r);
+			return fail(USB_ENOMEM, "cudaHostAlloc of %zu bytes failed", want);
+		}
+		s->h_stage_cap = want;
+	}
+	const usb_hit *raw = (const usb_hit *)s->h_stage;
+	const uint32_t *ncand = (const uint32_t *)((uint8_t *)s->h_stage + ((raw_bytes + 15) & ~(size_t)15));
 	r->runs.resize(nr);
 	r->qstat.resize(s->n_jobs);
-	std::vector<uint32_t> ncand(s->n_jobs);
 	cudaError_t e = cudaSuccess;
 	if (nh)
-		e = cudaMemcpyAsync(raw.data(), s->d_hits.p, (size_t)nh * sizeof(usb_hit), cudaMemcpyDeviceToHost, s->stream);
+		e = cudaMemcpyAsync((void *)raw, s->d_hits.p, raw_bytes, cudaMemcpyDeviceToHost, s->stream);
 	if (e == cudaSuccess && nr)
 		e = cudaMemcpyAsync(r->runs.data(), s->d_runs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s->stream);
 	if (e == cudaSuccess && s->n_jobs && group) {
 		e = cudaMemcpyAsync(r->qstat.data(), s->d_qstat.p, (size_t)s->n_jobs * sizeof(usb_qstat), cudaMemcpyDeviceToHost,
 		  s->stream);
 		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(ncand.data(), s->d_ncand.p, (size_t)s->n_jobs * 4, cudaMemcpyDeviceToHost, s->stream);
+			e = cudaMemcpyAsync((void *)ncand, s->d_ncand.p, nc_bytes, cudaMemcpyDeviceToHost, s->stream);
 	}
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s->stream);
 	if (e != cudaSuccess) {
-		delete r;
+		result_recycle(r);
 		return fail(USB_ECUDA, "result download failed: %s", cudaGetErrorString(e));
 	}
 	if (group)
@@ -1284,14 +1338,14 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 			r->qstat[j].n_cand = ncand[j];
 	// group by query (counting sort), then the reference's per-query order
 	r->qoff.assign((size_t)n_q + 1, 0);
-	for (const usb_hit &h : raw)
-		++r->qoff[(size_t)(group ? h.query : h.rank) + 1];
+	for (uint32_t k = 0; k < nh; ++k)
+		++r->qoff[(size_t)(group ? raw[k].query : raw[k].rank) + 1];
 	for (uint32_t q = 0; q < n_q; ++q)
 		r->qoff[q + 1] += r->qoff[q];
 	r->hits.resize(nh);
 	std::vector<uint64_t> cur(r->qoff.begin(), r->qoff.end() - 1);
-	for (const usb_hit &h : raw)
-		r->hits[cur[group ? h.query : h.rank]++] = h;
+	for (uint32_t k = 0; k < nh; ++k)
+		r->hits[cur[group ? raw[k].query : raw[k].rank]++] = raw[k];
 	if (group)
 		order_hits_like_hitmgr(r->hits, r->qoff, s->P.local != 0);
 	*out = r;
@@ -1344,7 +1398,7 @@ extern "C" const uint32_t *usb_result_runs(const usb_result *r, uint64_t *n_runs
 }
 extern "C" const uint64_t *usb_result_query_offsets(const usb_result *r) { return r ? r->qoff.data() : nullptr; }
 extern "C" const usb_qstat *usb_result_qstats(const usb_result *r) { return r ? r->qstat.data() : nullptr; }
-extern "C" void usb_result_free(usb_result *r) { delete r; }
+extern "C" void usb_result_free(usb_result *r) { result_recycle(r); }
 
 extern "C" uint32_t usb_result_path(const usb_result *r, const usb_hit *h, char *buf)
 {
