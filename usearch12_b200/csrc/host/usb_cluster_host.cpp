@@ -67,6 +67,125 @@ static void appendf2(std::string &s, const char *fmt, ...)
 		s.append(tmp, (size_t)std::min<int>(n, (int)sizeof tmp - 1));
 }
 
+// DerepFull (derepfull.cpp:130-212) with -threads 1 semantics: case-insensitive equality, uniques in
+// first-occurrence order.  UniqOf[i] = unique of sequence i, First[u] = its first member, USize[u].
+static void DerepFullHost(const SeqDB &Input, std::vector<unsigned> &UniqOf, std::vector<unsigned> &First,
+  std::vector<unsigned> &USize)
+{
+	const unsigned SeqCount = Input.GetSeqCount();
+	UniqOf.assign(SeqCount, 0);
+	First.clear();
+	USize.clear();
+	size_t nb = 16;
+	while (nb < 2 * (size_t)SeqCount + 16)
+		nb <<= 1;
+	std::vector<int> bucket(nb, -1);
+	for (unsigned i = 0; i < SeqCount; ++i) {
+		const uint8_t *s = Input.GetSeq(i);
+		const unsigned L = Input.GetSeqLength(i);
+		uint32_t h = 2166136261u;
+		for (unsigned k = 0; k < L; ++k)
+			h = (h ^ (uint32_t)toupper(s[k])) * 16777619u;
+		size_t b = h & (nb - 1);
+		for (;;) {
+			if (bucket[b] < 0) {
+				bucket[b] = (int)First.size();
+				UniqOf[i] = (unsigned)First.size();
+				First.push_back(i);
+				USize.push_back(0);
+				break;
+			}
+			const unsigned f = First[bucket[b]];
+			bool eq = Input.GetSeqLength(f) == L;
+			const uint8_t *t = Input.GetSeq(f);
+			for (unsigned k = 0; eq && k < L; ++k)
+				eq = toupper(s[k]) == toupper(t[k]);
+			if (eq) {
+				UniqOf[i] = (unsigned)bucket[b];
+				break;
+			}
+			b = (b + 1) & (nb - 1);
+		}
+		++USize[UniqOf[i]];
+	}
+}
+
+// label.cpp:47-75 StripAnnot
+static void StripAnnot(std::string &Label, const std::string &NameEq)
+{
+	if (Label.find(NameEq) == std::string::npos)
+		return;
+	std::string NewLabel, f;
+	std::vector<std::string> Fields;
+	for (char c : Label) { // myutils.cpp:1588-1607 Split(';')
+		if (c == ';') {
+			Fields.push_back(f);
+			f.clear();
+		} else
+			f.push_back(c);
+	}
+	if (!f.empty())
+		Fields.push_back(f);
+	for (const std::string &F : Fields) {
+		if (F.find(NameEq) == 0)
+			continue;
+		NewLabel += F + ";";
+	}
+	if (NewLabel.find('=') == std::string::npos)
+		Label = NewLabel.empty() ? NewLabel : NewLabel.substr(0, NewLabel.size() - 1);
+	else
+		Label = NewLabel;
+}
+
+// -fastx_uniques (derepfull.cpp:214-236, derepresult.cpp:255-284,689-775,811-820): uniques in order
+// of decreasing size (the reference's own quicksort, not stable), labelled with the first member's
+// label, optionally relabelled and annotated with ;size=N;
+uint64_t FastxUniques(const std::string &InputFileName, const UniquesOpts &Opts)
+{
+	SeqDB Input;
+	Input.FromFasta(InputFileName);
+	std::vector<unsigned> UniqOf, First, USize, Order;
+	DerepFullHost(Input, UniqOf, First, USize);
+	QuickSortOrderDesc(USize, Order);
+	if (Opts.fastaout.empty())
+		return First.size();
+	FILE *f = fopen(Opts.fastaout.c_str(), "wb");
+	if (!f)
+		Die("Cannot create %s", Opts.fastaout.c_str());
+	std::string out;
+	unsigned counter = 0;
+	for (unsigned k = 0; k < Order.size(); ++k) {
+		const unsigned u = Order[k], Size = USize[u];
+		if (Size < Opts.minuniquesize)
+			break;
+		std::string Label = Input.GetLabel(First[u]);
+		if (!Opts.relabel.empty())
+			Label = Opts.relabel + std::to_string(++counter);
+		if (Opts.sizeout) {
+			StripAnnot(Label, "size=");
+			if (!Label.empty() && Label.back() != ';') // myutils.cpp:824-839 Psasc
+				Label += ';';
+			Label += "size=" + std::to_string(Size) + ";";
+		}
+		const uint8_t *s = Input.GetSeq(First[u]);
+		const unsigned L = Input.GetSeqLength(First[u]);
+		out += '>';
+		out += Label;
+		out += '\n';
+		for (unsigned i = 0; i < L; i += 80) {
+			out.append((const char *)s + i, std::min(80u, L - i));
+			out += '\n';
+		}
+		if (out.size() > (1u << 20)) {
+			fwrite(out.data(), 1, out.size(), f);
+			out.clear();
+		}
+	}
+	fwrite(out.data(), 1, out.size(), f);
+	fclose(f);
+	return First.size();
+}
+
 uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 {
 	if (usb_device_count() <= 0)
@@ -77,42 +196,8 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	if (SeqCount == 0)
 		Die("No sequences in input file");
 
-	// ---- DerepFull: open-addressing hash over upper-cased letters
-	std::vector<unsigned> UniqOf(SeqCount), First, USize;
-	{
-		size_t nb = 16;
-		while (nb < 2 * (size_t)SeqCount + 16)
-			nb <<= 1;
-		std::vector<int> bucket(nb, -1);
-		for (unsigned i = 0; i < SeqCount; ++i) {
-			const uint8_t *s = Input.GetSeq(i);
-			const unsigned L = Input.GetSeqLength(i);
-			uint32_t h = 2166136261u;
-			for (unsigned k = 0; k < L; ++k)
-				h = (h ^ (uint32_t)toupper(s[k])) * 16777619u;
-			size_t b = h & (nb - 1);
-			for (;;) {
-				if (bucket[b] < 0) {
-					bucket[b] = (int)First.size();
-					UniqOf[i] = (unsigned)First.size();
-					First.push_back(i);
-					USize.push_back(0);
-					break;
-				}
-				const unsigned f = First[bucket[b]];
-				bool eq = Input.GetSeqLength(f) == L;
-				const uint8_t *t = Input.GetSeq(f);
-				for (unsigned k = 0; eq && k < L; ++k)
-					eq = toupper(s[k]) == toupper(t[k]);
-				if (eq) {
-					UniqOf[i] = (unsigned)bucket[b];
-					break;
-				}
-				b = (b + 1) & (nb - 1);
-			}
-			++USize[UniqOf[i]];
-		}
-	}
+	std::vector<unsigned> UniqOf, First, USize;
+	DerepFullHost(Input, UniqOf, First, USize);
 	const unsigned UniqueCount = (unsigned)First.size();
 	// members of each unique in input order (CSR)
 	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(SeqCount);

@@ -228,6 +228,14 @@ struct ClusterOpts {
 // clusterfast.cpp:81 ClusterFast() with -threads 1 semantics; returns the number of clusters.
 uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
 
+struct UniquesOpts {
+	std::string fastaout, relabel;
+	bool sizeout = false;
+	unsigned minuniquesize = 0;
+};
+// -fastx_uniques (derepfull.cpp:214-236): full-length dereplication, host only; returns the number of uniques.
+uint64_t FastxUniques(const std::string &InputFileName, const UniquesOpts &Opts);
+
 // SeqDB::GetIsNucleo (seqdb.cpp:268-310): a database is nucleotide when more than 80 of 100 sampled
 // letters are ACGTUN (either case).  The reference samples with rand(); here the sample is an even
 // stride over the first sequences of the file (deterministic).

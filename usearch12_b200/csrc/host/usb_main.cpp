@@ -6,6 +6,7 @@
 //        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]
 //   usearch12_b200 -otutab READS.fa -otus|-zotus|-db OTUS.fa -otutabout TABLE.txt [-mapout MAP.txt]
 //        [-sample_delim s] (searchcmd.cpp:21-40: -id 0.97 -strand both -maxaccepts 3 -maxrejects 32)
+//   usearch12_b200 -fastx_uniques IN.fa -fastaout OUT.fa [-sizeout] [-relabel prefix] [-minuniquesize n]
 //   usearch12_b200 -makeudb_usearch DB.fa -output DB.udb [-dbmask fastnucleo|fastamino|none]
 //        (the file is byte for byte the reference's; -db accepts FASTA or .udb, from either program)
 //   usearch12_b200 -usearch_local Q.fa -db DB.fa -id 0.5 -evalue 1e-5 [-strand plus|both for nt DBs]
@@ -24,7 +25,7 @@ using namespace usbhost;
 int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
-	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", nullptr};
+	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", nullptr};
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
 		if (a[0] != '-')
@@ -72,6 +73,25 @@ int main(int argc, char **argv)
 		if (!opt.empty())
 			Die("Option -%s is not supported by this build", opt.begin()->first.c_str());
 		ClusterFast(reads, C);
+		return 0;
+	}
+	const std::string un = take("fastx_uniques", nullptr);
+	if (!un.empty()) {
+		// derepfull.cpp:233 cmd_fastx_uniques (host only)
+		UniquesOpts U;
+		U.fastaout = take("fastaout", nullptr);
+		U.relabel = take("relabel", nullptr);
+		U.sizeout = !take("sizeout", nullptr).empty();
+		U.minuniquesize = (unsigned)atoi(take("minuniquesize", "0").c_str());
+		const bool quiet = !take("quiet", nullptr).empty();
+		take("threads", nullptr); // the unique order follows the reference's -threads 1 behaviour
+		if (opt.count("output"))
+			Die("Use -fastaout, not -output"); // derepfull.cpp:216-217
+		if (!opt.empty())
+			Die("Option -%s is not supported by this build", opt.begin()->first.c_str());
+		const uint64_t n = FastxUniques(un, U);
+		if (!quiet)
+			fprintf(stderr, "%llu uniques\n", (unsigned long long)n);
 		return 0;
 	}
 	const std::string mk = take("makeudb_usearch", nullptr);
