@@ -362,89 +362,114 @@ __device__ void block_top32(unsigned long long *sel, uint32_t n)
 	__syncthreads();
 }
 
-// More than RANK_KCAP survivors (a few percent of the queries: reads without a close target keep
-// every target above a low cut-off).  Radix-select the k_max-th largest surviving count, take
-// ties at the cut in ascending target order (block scan), leave the selection in X.sel.
+// More than RANK_KCAP survivors (at config 4 every read without a close target: its cut-off is
+// low and thousands of targets pass).  Only the first k_max of (U desc, target asc) are wanted, so
+// the cut-off is raised by bisection until between k_max and RANK_KCAP survivors remain; a
+// counting pass is cheap because segments and words below the trial cut-off are skipped.  When a
+// single count value straddles both bounds (many ties), everything above it is taken plus its
+// first ties in ascending target order.  Leaves the selection in X.sel[0 .. S.n_sel).
 template <bool WIDE>
-__device__ void rank_select_fallback(const RankArgs &a, RankShared &S, const RankScratch &X, const uint4 *U128,
-  SegFilter<WIDE> F, uint32_t c0, uint32_t c1, bool any)
+__device__ void rank_select_bisect(const RankArgs &a, RankShared &S, const RankScratch &X, const uint4 *U128,
+  const SegFilter<WIDE> &F0, uint32_t c0, uint32_t c1, uint32_t seg_max)
 {
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, NT = blockDim.x;
 	constexpr uint32_t PER = WIDE ? 2 : 4;
-	// f(u, t) for every survivor of this thread's segment, ascending targets
-	auto for_survivors = [&](auto f) {
-		if (!any)
+	// survivors of this thread's segment with U >= thr (thr >= the original cut-off)
+	auto count_at = [&](uint32_t thr) -> uint32_t {
+		uint32_t cnt = 0;
+		if (seg_max >= thr) {
+			SegFilter<WIDE> F = F0;
+			F.floor_thr = thr;
+			F.reset();
+			for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) { cnt += __popc(F.mask(k, word)); });
+		}
+		return cnt;
+	};
+	// block total of v, and this thread's exclusive prefix
+	auto block_total = [&](uint32_t v, uint32_t &excl) -> uint32_t {
+		excl = block_excl_scan_sum(v, S.warp_tmp);
+		if (tid == NT - 1)
+			S.total = excl + v;
+		__syncthreads();
+		const uint32_t t = S.total;
+		__syncthreads();
+		return t;
+	};
+	uint32_t lo = F0.floor_thr, hi = S.maxv + 1; // count(lo) > RANK_KCAP, count(hi) = 0
+	uint32_t thr = 0, my = 0, excl = 0, c_hi = 0, my_hi = 0, excl_hi = 0;
+	bool found = false;
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		my = count_at(mid);
+		const uint32_t c = block_total(my, excl);
+		if (c > RANK_KCAP)
+			lo = mid;
+		else if (c >= a.k_max) {
+			found = true;
+			thr = mid;
+			break;
+		} else {
+			hi = mid;
+			c_hi = c;
+			my_hi = my;
+			excl_hi = excl;
+		}
+	}
+	if (!found) { // count(hi) < k_max <= RANK_KCAP < count(hi - 1): take all >= hi, then ties at hi - 1
+		thr = hi;
+		my = my_hi;
+		excl = excl_hi;
+	}
+	// everything at or above thr, ascending targets
+	if (my) {
+		SegFilter<WIDE> F = F0;
+		F.floor_thr = thr;
+		F.reset();
+		uint32_t slot = excl;
+		for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) {
+			uint32_t m = F.mask(k, word);
+			while (m) {
+				const uint32_t b = (uint32_t)__ffs(m) - 1;
+				m &= m - 1;
+				X.sel[slot++] = rank_key(SegFilter<WIDE>::lane_of(word, b), k * PER + b);
+			}
+		});
+	}
+	if (found) {
+		if (tid == 0)
+			S.n_sel = S.total; // block_total left count(thr) there
+		__syncthreads();
+		return;
+	}
+	// ties: survivors with U == hi - 1, the first k_max - c_hi of them in target order
+	const uint32_t tie = hi - 1, need = a.k_max - c_hi;
+	uint32_t ties = 0;
+	auto for_ties = [&](auto f) {
+		if (seg_max < tie)
 			return;
+		SegFilter<WIDE> F = F0;
+		F.floor_thr = max(F0.floor_thr, tie);
 		F.reset();
 		for_words(U128, c0, c1, [&](uint32_t k, uint32_t word) {
 			uint32_t m = F.mask(k, word);
 			while (m) {
 				const uint32_t b = (uint32_t)__ffs(m) - 1;
 				m &= m - 1;
-				f(SegFilter<WIDE>::lane_of(word, b), k * PER + b);
+				if (SegFilter<WIDE>::lane_of(word, b) == tie)
+					f(k * PER + b);
 			}
 		});
 	};
-	for (uint32_t i = tid; i < 256; i += blockDim.x)
-		X.hist[i] = 0;
-	if (tid == 0)
-		S.n_sel = 0;
-	__syncthreads();
-	for_survivors([&](uint32_t u, uint32_t) { atomicAdd(&X.hist[WIDE ? (u >> 8) : u], 1u); });
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t cum = 0;
-		for (int b = 255; b >= 0; --b) {
-			cum += X.hist[b];
-			if (cum >= a.k_max) {
-				S.bstar = (uint32_t)b;
-				S.above = cum - X.hist[b];
-				break;
-			}
-		}
-		if (!WIDE) {
-			S.vstar = S.bstar;
-			S.m_eq = a.k_max - S.above;
-		}
-	}
-	__syncthreads();
-	if (WIDE) {
-		for (uint32_t i = tid; i < 256; i += blockDim.x)
-			X.hist[i] = 0;
-		__syncthreads();
-		const uint32_t bstar = S.bstar;
-		for_survivors([&](uint32_t u, uint32_t) {
-			if ((u >> 8) == bstar)
-				atomicAdd(&X.hist[u & 255], 1u);
-		});
-		__syncthreads();
-		if (tid == 0) {
-			uint32_t cum = S.above;
-			for (int b = 255; b >= 0; --b) {
-				cum += X.hist[b];
-				if (cum >= a.k_max) {
-					S.vstar = (S.bstar << 8) | (uint32_t)b;
-					S.m_eq = a.k_max - (cum - X.hist[b]);
-					break;
-				}
-			}
-		}
-		__syncthreads();
-	}
-	const uint32_t vstar = S.vstar, m_eq = S.m_eq;
-	uint32_t c_eq = 0;
-	for_survivors([&](uint32_t u, uint32_t) { c_eq += u == vstar ? 1u : 0u; });
-	uint32_t eq_rank = block_excl_scan_sum(c_eq, S.warp_tmp);
-	for_survivors([&](uint32_t u, uint32_t t) {
-		bool take = u > vstar;
-		if (!take && u == vstar)
-			take = (eq_rank++ < m_eq);
-		if (take) {
-			const uint32_t slot = atomicAdd(&S.n_sel, 1u);
-			if (slot < RANK_KCAP)
-				X.sel[slot] = rank_key(u, t);
-		}
+	for_ties([&](uint32_t) { ++ties; });
+	uint32_t rank;
+	block_total(ties, rank);
+	for_ties([&](uint32_t t) {
+		if (rank < need)
+			X.sel[c_hi + rank] = rank_key(tie, t);
+		++rank;
 	});
+	if (tid == 0)
+		S.n_sel = a.k_max;
 	__syncthreads();
 }
 
@@ -845,7 +870,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 		else
 			block_sort_keys(X.sel, total);
 	} else {
-		rank_select_fallback<WIDE>(a, S, X, U128, F, c0, c1, m >= floor_thr);
+		rank_select_bisect<WIDE>(a, S, X, U128, F, c0, c1, m);
 		nsel = min(S.n_sel, (uint32_t)RANK_KCAP);
 		if (top32)
 			block_top32(X.sel, nsel);
