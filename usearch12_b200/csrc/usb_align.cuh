@@ -76,6 +76,7 @@ struct WarpWs {
 	uint32_t *order, *prev, *chain;
 	int *cscore;
 	uint32_t LA, LB, nwordsA;
+	bool seed_dirty;          // a wide DP borrowed the seed table's memory: rebuild before the next seed search
 };
 
 inline __host__ __device__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -783,7 +784,13 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 	const uint64_t W = (uint64_t)LB + 1;
 	// rows in shared memory when the rectangle is narrow enough, else in the global slab
 	const bool rows_fit = 8u * (LB + 8) <= a.scratch_bytes;
-	int *Mrow = (rows_fit ? (int *)w.scratch : w.rows_slab) + 4;
+	// next choice: the query's seed table (cnt, start, pos) lies right in front of the scratch and
+	// is not needed any more for this candidate; it is rebuilt if another candidate follows
+	const uint32_t big_bytes = (uint32_t)((w.scratch + a.scratch_bytes) - w.cnt);
+	const bool rows_big = !rows_fit && a.fast_in_smem && 8u * (LB + 8) <= big_bytes;
+	if (rows_big)
+		w.seed_dirty = true;
+	int *Mrow = (rows_fit ? (int *)w.scratch : rows_big ? (int *)w.cnt : w.rows_slab) + 4;
 	int *Drow = Mrow + LB + 4;
 	uint8_t *TB = w.TB;
 	for (uint32_t j = lane; j <= LB + 1; j += 32) {
@@ -1193,9 +1200,14 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 		const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
 		load_query(a, w, a.q + q0, L, strand);
 		build_seed_table(a, w);
+		w.seed_dirty = false;
 		uint32_t acc = 0, rej = 0;
 		for (uint32_t k = 0; k < ncand; ++k) {
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			if (w.seed_dirty) {
+				build_seed_table(a, w);
+				w.seed_dirty = false;
+			}
 			load_target(a, w, t);
 			++st.n_tried;
 			st.seq_bytes += w.LA + w.LB;
