@@ -918,45 +918,65 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 	if (cells)
 		*cells += ncell;
 
-	// traceback (tracebackbitmem.cpp:8-73), lane 0, reversed into w.rev
+	// traceback (tracebackbitmem.cpp:8-73), reversed into w.rev.  The walk is serial, one dependent
+	// trace-byte load per step; here the warp looks 32 steps ahead along the current state's run
+	// (diagonal for M, column for D, row for I): lane l loads the byte step l would read if the
+	// state did not change, the first lane whose byte ends the run (or runs off the matrix) is
+	// found with a ballot, and the whole run is emitted at once.
 	uint32_t n = 0;
-	if (lane == 0) {
+	{
 		uint32_t i = LA, j = LB;
 		char *rev = w.rev;
 		const uint32_t limit = LA + LB;
+		bool bad = false;
 		while ((i != 0 || j != 0) && n < limit) {
-			rev[n++] = State;
+			bool valid;
+			uint32_t ci, cj;
 			if (State == 'M') {
-				if (i == 0 || j == 0) {
-					atomicOr(&a.ctr->err, ERR_TRACE);
-					break;
-				}
-				const uint32_t t = TB[(uint64_t)(i - 1) * W + (j - 1)];
-				State = (t & TB_DM) ? 'D' : (t & TB_IM) ? 'I' : 'M';
-				--i;
-				--j;
+				valid = i > lane && j > lane;
+				ci = i - 1 - lane;
+				cj = j - 1 - lane;
 			} else if (State == 'D') {
-				if (i == 0) {
-					atomicOr(&a.ctr->err, ERR_TRACE);
-					break;
-				}
-				const uint32_t t = TB[(uint64_t)(i - 1) * W + j];
-				State = (t & TB_MD) ? 'M' : 'D';
-				--i;
+				valid = i > lane;
+				ci = i - 1 - lane;
+				cj = j;
 			} else {
-				if (j == 0) {
-					atomicOr(&a.ctr->err, ERR_TRACE);
-					break;
-				}
-				const uint32_t t = TB[(uint64_t)i * W + (j - 1)];
-				State = (t & TB_MI) ? 'M' : 'I';
-				--j;
+				valid = j > lane;
+				ci = i;
+				cj = j - 1 - lane;
 			}
+			const uint32_t t = valid ? (uint32_t)TB[(uint64_t)ci * W + cj] : 0u;
+			const bool leave = State == 'M' ? (t & (TB_DM | TB_IM)) != 0 : State == 'D' ? (t & TB_MD) != 0 : (t & TB_MI) != 0;
+			const uint32_t vmask = __ballot_sync(USB_FULL, valid);
+			const uint32_t stop = __ballot_sync(USB_FULL, !valid || leave);
+			const uint32_t first = stop ? (uint32_t)__ffs(stop) - 1 : 32u;
+			const bool first_valid = first < 32 && ((vmask >> first) & 1u);
+			uint32_t cnt = first < 32 ? first + (first_valid ? 1u : 0u) : 32u;
+			const bool cut = cnt > limit - n;
+			cnt = min(cnt, limit - n);
+			if (cnt == 0) { // the serial walk would step off the matrix here
+				bad = true;
+				break;
+			}
+			if (lane < cnt)
+				rev[n + lane] = State;
+			n += cnt;
+			const char prev = State;
+			if (first_valid && !cut) {
+				const uint32_t tf = __shfl_sync(USB_FULL, t, first);
+				State = prev == 'M' ? ((tf & TB_DM) ? 'D' : 'I') : 'M';
+			}
+			if (prev == 'M') {
+				i -= cnt;
+				j -= cnt;
+			} else if (prev == 'D')
+				i -= cnt;
+			else
+				j -= cnt;
 		}
-		if (i != 0 || j != 0)
+		if ((bad || i != 0 || j != 0) && lane == 0)
 			atomicOr(&a.ctr->err, ERR_TRACE);
 	}
-	n = __shfl_sync(USB_FULL, n, 0);
 	__syncwarp();
 	for (uint32_t k = lane; k < n; k += 32)
 		out[k] = w.rev[n - 1 - k];
