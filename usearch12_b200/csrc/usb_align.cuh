@@ -672,7 +672,67 @@ __device__ __forceinline__ bool is_staggered(const HspRec &h, uint32_t LA, uint3
 __device__ uint32_t chain_hsps(const AlignArgs &a, WarpWs &w, uint32_t n)
 {
 	uint32_t len = 0;
-	if (lane_id() == 0 && n > 0) {
+	const uint32_t lane = lane_id();
+	if (n > 0 && n <= 32) {
+		// Up to 32 HSPs (always, in practice): lane k holds HSP k in registers and the recurrence
+		// runs on shuffles and ballots -- the arrays of the serial version live in global memory
+		// and every step of it was a dependent load.
+		const bool have = lane < n;
+		HspRec h = have ? w.ung[lane] : HspRec{0, 0, 0, 0};
+		// stable order by query start: rank = HSPs that come before this one
+		uint32_t rank = 0;
+		for (uint32_t j = 0; j < n; ++j) {
+			const uint32_t lj = __shfl_sync(USB_FULL, h.Loi, j);
+			rank += (lj < h.Loi || (lj == h.Loi && j < lane)) ? 1u : 0u;
+		}
+		int cs = 0;
+		uint32_t prev = 0xffffffffu;
+		for (uint32_t oi = 0; oi < n; ++oi) {
+			const uint32_t k = (uint32_t)__ffs(__ballot_sync(USB_FULL, have && rank == oi)) - 1;
+			const uint32_t kLoi = __shfl_sync(USB_FULL, h.Loi, k), kLoj = __shfl_sync(USB_FULL, h.Loj, k);
+			const int kscore = __shfl_sync(USB_FULL, h.score2, k);
+			// best predecessor: largest chain score among the compatible HSPs earlier in the order,
+			// the earliest of them on ties (the serial scan only replaces on a strictly larger score)
+			const bool ok = have && rank < oi && h.Loi + h.Len - 1 < kLoi && h.Loj + h.Len - 1 < kLoj;
+			const uint32_t key = ok ? (((uint32_t)cs << 6) | (63u - rank)) : 0u;
+			const uint32_t bestkey = __reduce_max_sync(USB_FULL, key);
+			uint32_t bestc = 0xffffffffu;
+			int best = 0;
+			if (bestkey) {
+				const uint32_t brank = 63u - (bestkey & 63u);
+				bestc = (uint32_t)__ffs(__ballot_sync(USB_FULL, have && rank == brank)) - 1;
+				best = (int)(bestkey >> 6);
+			}
+			if (lane == k) {
+				prev = bestc;
+				cs = best + kscore;
+			}
+		}
+		// best chain end: largest score, lowest index on ties
+		const uint32_t okey = have ? (((uint32_t)cs << 6) | (63u - lane)) : 0u;
+		const uint32_t opt = 63u - (__reduce_max_sync(USB_FULL, okey) & 63u);
+		uint32_t members = 0; // lanes on the chain
+		for (uint32_t k = opt; k != 0xffffffffu; k = __shfl_sync(USB_FULL, prev, k)) {
+			members |= 1u << k;
+			++len;
+		}
+		// chain in order of query start == ascending rank; position = chain members ranked lower
+		{
+			uint32_t pos = 0;
+			for (uint32_t j = 0; j < n; ++j) {
+				const uint32_t rj = __shfl_sync(USB_FULL, rank, j);
+				pos += (((members >> j) & 1u) && rj < rank) ? 1u : 0u;
+			}
+			if ((members >> lane) & 1u)
+				w.chain[pos] = lane;
+		}
+		const bool stag = ((members >> lane) & 1u) && is_staggered(h, w.LA, w.LB); // hspfinder.cpp:537-553
+		if (__any_sync(USB_FULL, stag))
+			len = 0;
+		__syncwarp();
+		return len;
+	}
+	if (lane == 0 && n > 0) {
 		const HspRec *H = w.ung;
 		uint32_t *order = w.order, *prev = w.prev;
 		int *cs = w.cscore;
