@@ -154,6 +154,11 @@ const char *usb_udb_label(const usb_udb *u, uint32_t i);
 /* m_UDBRows[word], m_Sizes[word] as stored in the file (parity checks against usb_index_row). */
 int usb_udb_row(const usb_udb *u, uint32_t word, const uint32_t **row, uint32_t *size);
 
+/* Host-only test hook: the 2-byte device layout (groups of 256 increment descriptors, see
+ * usb_index_posting_width) of ONE row with the given ascending targets in an index of n_targets. */
+int usb_debug_half_row(const uint32_t *targets, uint32_t n, uint32_t n_targets, uint16_t *out, uint32_t out_cap,
+  uint32_t *groups, uint32_t *dummy0);
+
 /* ---- searcher: replaces MakeDBSearcher (makedbsearcher.cpp:75) wiring for one device. */
 int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searcher **out);
 void usb_searcher_free(usb_searcher *s);

@@ -54,7 +54,7 @@ SYMBOLS = [
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
     "usb_viterbi_batch", "usb_set_local", "usb_local_evalue", "usb_local_pairs",
     "usb_udb_write", "usb_udb_probe", "usb_udb_read", "usb_udb_free", "usb_udb_seq_count", "usb_udb_is_nucleo",
-    "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row",
+    "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row", "usb_debug_half_row",
 ]
 
 _lib = None
@@ -96,6 +96,7 @@ def lib():
     L.usb_udb_label.argtypes = [vp, C.c_uint32]
     L.usb_udb_label.restype = C.c_char_p
     L.usb_udb_row.argtypes = [vp, C.c_uint32, C.POINTER(u32p), u32p]
+    L.usb_debug_half_row.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, u32p, u32p]
     L.usb_index_row.argtypes = [vp, C.c_uint32, C.POINTER(u32p), u32p]
     L.usb_index_seq.argtypes = [vp, C.c_uint32, C.POINTER(u8p), u32p]
     L.usb_searcher_create.argtypes = [vp, C.POINTER(Params), C.POINTER(vp)]

@@ -260,3 +260,34 @@ extern "C" int usb_udb_row(const usb_udb *u, uint32_t word, const uint32_t **row
 	*size = u->sizes[word];
 	return 0;
 }
+
+// ---- host-only view of the 2-byte device layout of one row (tests): see usb_hostindex.h HostHalf
+extern "C" int usb_debug_half_row(const uint32_t *targets, uint32_t n, uint32_t n_targets, uint16_t *out, uint32_t out_cap,
+  uint32_t *groups, uint32_t *dummy0)
+{
+	if ((!targets && n) || !out || !groups || !dummy0)
+		return fail(USB_EINVAL, "usb_debug_half_row: null argument");
+	if (n_targets == 0 || n_targets > USB_HALF_MAX_TARGETS)
+		return fail(USB_EINVAL, "usb_debug_half_row: %u targets (1..%u)", n_targets, USB_HALF_MAX_TARGETS);
+	HostCSR H;
+	H.base = 0;
+	H.count = n_targets;
+	H.slots = 1;
+	H.row_off = {0, (uint64_t)((n + 3) & ~3u)};
+	H.row_size = {n};
+	H.postings.assign(((size_t)n + 3 & ~(size_t)3) + 4, 0xffffffffu);
+	for (uint32_t i = 0; i < n; ++i) {
+		if (targets[i] >= n_targets || (i && targets[i] <= targets[i - 1]))
+			return fail(USB_EINVAL, "usb_debug_half_row: targets must be ascending and < n_targets");
+		H.postings[i] = targets[i];
+	}
+	H.n_postings = n;
+	HostHalf hh;
+	make_half(H, n_targets, 1, hh);
+	*groups = hh.row_groups[0];
+	*dummy0 = hh.dummy0;
+	if ((uint64_t)hh.row_groups[0] * 256 > out_cap)
+		return fail(USB_ELIMIT, "usb_debug_half_row: %u entries needed", hh.row_groups[0] * 256);
+	memcpy(out, hh.postings.data(), (size_t)hh.row_groups[0] * 256 * 2);
+	return 0;
+}
