@@ -499,7 +499,7 @@ struct uso_searcher
 	uint32_t *TopU, *TopT, *TopOrder, *TopT2; uint32_t topcap; uint32_t ntop_prev;
 	uint32_t *cs_sizes, *cs_offsets; uint32_t cscap;
 	/* HSP finder */
-	unsigned hsp_w, hsp_wordcount, hsp_hi;
+	unsigned hsp_w, hsp_A, hsp_wordcount, hsp_hi;
 	uint32_t *wordsA, *wordsB; uint32_t wAcap, wBcap;
 	unsigned nwordsA, nwordsB;
 	uint32_t *word2posA, *wordcountsA;
@@ -554,27 +554,41 @@ uso_searcher *uso_searcher_create(uso_db *db, const uso_params *p)
 		set_nuc_subst(s->subst, p->match, p->mismatch);
 	else
 		memcpy(s->subst, g_blosum, 256 * 256 * sizeof(float)); /* alnparams.cpp:330-349: BLOSUM62 */
-	if (!p->is_nucleo && !p->local)
-		{
-		fprintf(stderr, "oracle: amino acid usearch_global is not restated\n");
-		abort();
-		}
 	s->xd_poison = getenv("USO_XD_POISON") != 0;
 	la_init(s);
-	/* alnheuristics.cpp:26-44 (nucleo branch) */
+	/* alnheuristics.cpp:26-61 */
 	s->XDropGlobalHSP = p->xdrop_nw;
 	s->BandRadius = p->band;
 	s->MinGlobalHSPLength = p->minhsp;
-	s->MinGlobalHSPFractId = p->id > 0.75f ? p->id : 0.75f;
-	s->MinGlobalHSPScore = s->MinGlobalHSPFractId * s->MinGlobalHSPLength * p->match;
-	s->Open = -10.0f; s->Ext = -1.0f; s->TermOpen = -0.5f; s->TermExt = -0.5f;
+	if (p->is_nucleo)
+		{
+		s->MinGlobalHSPFractId = p->id > 0.75f ? p->id : 0.75f;
+		s->MinGlobalHSPScore = s->MinGlobalHSPFractId * s->MinGlobalHSPLength * p->match;
+		s->Open = -10.0f;
+		}
+	else
+		{
+		/* alnheuristics.cpp:40-58: smallest diagonal score of the matrix over the 20 letters */
+		float MinDiagScore = 9e9f;
+		for (unsigned i = 0; i < 20; ++i)
+			{
+			uint8_t c = (uint8_t) "ACDEFGHIKLMNPQRSTVWY"[i];
+			if (s->subst[c][c] < MinDiagScore)
+				MinDiagScore = s->subst[c][c];
+			}
+		s->MinGlobalHSPFractId = p->id > 0.5f ? p->id : 0.5f;
+		s->MinGlobalHSPScore = s->MinGlobalHSPFractId * MinDiagScore * s->MinGlobalHSPLength;
+		s->Open = -17.0f; /* alnparams.cpp:381-384 */
+		}
+	s->Ext = -1.0f; s->TermOpen = -0.5f; s->TermExt = -0.5f;
 	s->found = (uint8_t *) calloc(db->slot_count, 1);
 	/* hspfinder.cpp:193-217 */
-	s->hsp_w = p->is_nucleo ? p->hspw : 0;
+	s->hsp_w = (p->is_nucleo || !p->local) ? p->hspw : 0;
+	s->hsp_A = p->is_nucleo ? 4 : 20;
 	s->hsp_wordcount = 1;
 	for (unsigned i = 0; i < s->hsp_w; ++i)
-		s->hsp_wordcount *= 4;
-	s->hsp_hi = s->hsp_wordcount / 4;
+		s->hsp_wordcount *= s->hsp_A;
+	s->hsp_hi = s->hsp_wordcount / s->hsp_A;
 	s->word2posA = (uint32_t *) xrealloc(0, s->hsp_wordcount * MAXREPS * sizeof(uint32_t));
 	s->wordcountsA = (uint32_t *) xrealloc(0, s->hsp_wordcount * sizeof(uint32_t));
 	return s;
@@ -783,25 +797,26 @@ unsigned uso_rank_candidates(uso_searcher *s, const uint8_t *q, uint32_t L, uint
 /* hspfinder.cpp:226-270 SeqToWords: rolling words, wildcard -> letter 0, never skipped */
 static unsigned hsp_seq_to_words(const uso_searcher *s, const uint8_t *seq, unsigned L, uint32_t *words)
 	{
-	const unsigned w = s->hsp_w;
+	const unsigned w = s->hsp_w, A = s->hsp_A;
+	const uint8_t *c2l = s->P.is_nucleo ? g_c2l : g_c2l_aa; /* hspfinder.cpp:201 m_CharToLetter */
 	if (L < w)
 		return 0;
 	uint32_t word = 0;
 	const uint8_t *front = seq, *back = seq;
 	for (unsigned i = 0; i < w - 1; ++i)
 		{
-		unsigned l = g_c2l[*front++];
-		if (l >= 4) l = 0;
-		word = word * 4 + l;
+		unsigned l = c2l[*front++];
+		if (l >= A) l = 0;
+		word = word * A + l;
 		}
 	for (unsigned i = w - 1; i < L; ++i)
 		{
-		unsigned l = g_c2l[*front++];
-		if (l >= 4) l = 0;
-		word = word * 4 + l;
+		unsigned l = c2l[*front++];
+		if (l >= A) l = 0;
+		word = word * A + l;
 		*words++ = word;
-		l = g_c2l[*back++];
-		if (l >= 4) l = 0;
+		l = c2l[*back++];
+		if (l >= A) l = 0;
 		word -= l * s->hsp_hi;
 		}
 	return L - w + 1;
@@ -1064,7 +1079,7 @@ static unsigned get_global_hsps(uso_searcher *s, const uint8_t *A, unsigned LA, 
 		const hsp *h = &s->ung[s->chain[c]];
 		TotalLength += h->Len;
 		for (unsigned k = 0; k < h->Len; ++k) /* GetHSPIdCount hspfinder.cpp:561-579 */
-			if (g_match[A[h->Loi + k]][B[h->Loj + k]])
+			if ((s->P.is_nucleo ? g_match : g_match_aa)[A[h->Loi + k]][B[h->Loj + k]])
 				++TotalSame;
 		}
 	*HSPFractId = TotalLength == 0 ? 0.0f : (float) TotalSame / (float) TotalLength;
@@ -2463,13 +2478,19 @@ static double pct_id(const uso_hit *h)
 
 /* userout.cpp:150-215 with fields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand.
  * Global: m_HSP spans both sequences (alignresult.cpp:137-145) so qlo..thi = 1,QL,1,TL. */
-void uso_write_userout(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
+void uso_write_userout2(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
 	{
 	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
 	uso_compress_path(h->path, cp);
+	/* amino acid searches have no strand: '.' (arscorer.cpp GetQueryStrand) */
 	fprintf(f, "%s\t%s\t%.1f\t%u\t%u\t%u\t%u\t%u\t%u\t%u\t%s\t%c\n", qlabel, tlabel, pct_id(h), h->alnlen,
-	  h->mism, h->opens, 1u, h->ql, 1u, h->tl, cp, h->strand ? '-' : '+');
+	  h->mism, h->opens, 1u, h->ql, 1u, h->tl, cp, nucleo ? (h->strand ? '-' : '+') : '.');
 	free(cp);
+	}
+
+void uso_write_userout(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
+	{
+	uso_write_userout2(f, h, qlabel, tlabel, 1);
 	}
 
 /* blast6out.cpp:27-80; arscorer.cpp:748-808: target coords flip when query is rev-comped */
@@ -2481,13 +2502,18 @@ void uso_write_blast6(FILE *f, const uso_hit *h, const char *qlabel, const char 
 	}
 
 /* outputuc.cpp:45-69 */
-void uso_write_uc_hit(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
+void uso_write_uc_hit2(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo)
 	{
 	char *cp = (char *) xrealloc(0, strlen(h->path) * 2 + 16);
 	uso_compress_path(h->path, cp);
 	fprintf(f, "H\t%u\t%u\t%.1f\t%c\t%u\t%u\t%s\t%s\t%s\n", h->target, h->ql, pct_id(h),
-	  h->strand ? '-' : '+', 0u, 0u, cp, qlabel, tlabel);
+	  nucleo ? (h->strand ? '-' : '+') : '.', 0u, 0u, cp, qlabel, tlabel);
 	free(cp);
+	}
+
+void uso_write_uc_hit(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel)
+	{
+	uso_write_uc_hit2(f, h, qlabel, tlabel, 1);
 	}
 
 /* outputuc.cpp:19-20 */

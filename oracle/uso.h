@@ -24,7 +24,7 @@ extern "C" {
 /* Snapshot of the options the path reads.  Floats stay `float`: the
  * reference stores every float option as float and widens on read (opts.cpp:8-15,80-88). */
 typedef struct uso_params {
-	int is_nucleo;       /* 1 = nt DB (only nt is restated so far) */
+	int is_nucleo;       /* 1 = nt DB, 0 = amino acid DB (BLOSUM62, gap open -17, HSP words of 3 letters) */
 	float id;            /* -id */
 	unsigned maxaccepts; /* terminator.cpp:23-31 */
 	unsigned maxrejects;
@@ -131,6 +131,9 @@ void uso_write_uc_hit_local(FILE *f, const uso_hit *h, const char *qlabel, const
 /* userout with -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand (userout.cpp:150-215) */
 void uso_write_userout(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel);
 void uso_write_blast6(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel); /* blast6out.cpp:27-80 */
+/* same with the strand column of an amino acid search ('.') when nucleo == 0 */
+void uso_write_userout2(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo);
+void uso_write_uc_hit2(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel, int nucleo);
 void uso_write_uc_hit(FILE *f, const uso_hit *h, const char *qlabel, const char *tlabel); /* outputuc.cpp:45-69 */
 void uso_write_uc_nohit(FILE *f, uint32_t ql, const char *qlabel);                        /* outputuc.cpp:19-20 */
 

@@ -1,6 +1,6 @@
 /*
  * uso_main.c -- CLI around the CPU ORACLE (test infrastructure, NOT product code).
- *   uso_cli usearch_global QUERY.fa DB.fa ID [plus|both] USEROUT UC B6 [maxaccepts maxrejects]
+ *   uso_cli usearch_global QUERY.fa DB.fa ID plus|both|aa USEROUT UC B6 [maxaccepts maxrejects]
  * Writes the same three output files the reference writes for
  *   -usearch_global Q -db DB -id ID -strand S -userout .. -uc .. -blast6out ..
  *   -userfields query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand
@@ -280,13 +280,15 @@ int main(int argc, char **argv)
 		return usearch_local_main(argc, argv);
 	if (argc < 9 || strcmp(argv[1], "usearch_global") != 0)
 		{
-		fprintf(stderr, "usage: uso_cli usearch_global Q.fa DB.fa ID plus|both USEROUT UC B6 [maxaccepts maxrejects]\n");
+		fprintf(stderr, "usage: uso_cli usearch_global Q.fa DB.fa ID plus|both|aa USEROUT UC B6 [maxaccepts maxrejects]\n");
 		return 2;
 		}
 	uso_params P;
 	uso_default_params(&P, 0);
 	P.id = (float) atof(argv[4]);
 	P.strand_both = strcmp(argv[5], "both") == 0;
+	if (strcmp(argv[5], "aa") == 0) /* amino acid DB: no -strand option (search.cpp:23-34) */
+		uso_set_amino(&P);
 	if (argc > 10)
 		{
 		P.maxaccepts = (unsigned) atoi(argv[9]);
@@ -312,8 +314,8 @@ int main(int argc, char **argv)
 		for (unsigned k = 0; k < n; ++k)
 			{
 			const char *tl = uso_db_label(db, hits[k].target);
-			uso_write_userout(fu, &hits[k], Q.labels[i], tl);
-			uso_write_uc_hit(fc, &hits[k], Q.labels[i], tl);
+			uso_write_userout2(fu, &hits[k], Q.labels[i], tl, P.is_nucleo);
+			uso_write_uc_hit2(fc, &hits[k], Q.labels[i], tl, P.is_nucleo);
 			uso_write_blast6(fb, &hits[k], Q.labels[i], tl);
 			free(hits[k].path);
 			}

@@ -41,6 +41,19 @@ def test_oracle_local_matches_reference_golden(variant):
         assert util.first_diff(lines, g.lines(variant, kind)) is None, kind
 
 
+@pytest.mark.parametrize("variant", list(util.AA_GLOBAL_VARIANTS))
+def test_oracle_aa_global_matches_reference_golden(variant):
+    """Amino acid usearch_global (BASELINE config 1 = cfg1_id90) vs the reference binary's outputs
+    (tools/make_golden_aa_global.py): BLOSUM62, gap open -17, HSP words of 3 letters."""
+    kw = dict(util.AA_GLOBAL_VARIANTS[variant])
+    dl, d, ql, q = util.aa_global_inputs(kw.pop("inputs"))
+    p = O.default_params(amino=True, **kw)
+    s = O.Searcher(O.DB(d, p, dl), p)
+    got = util.oracle_lines(s, ql, q, dl, nucleo=False)
+    for lines, kind in zip(got, ("user", "uc", "b6")):
+        assert util.first_diff(lines, util.golden_lines(variant, kind)) is None, kind
+
+
 def test_known_answer_xdrop_fwd():
     """The reference's own known answer (xdropalignmem.cpp:336-364 cmd_test): XDropFwdFastMem of
     SEQVENCE / SEQVECE with BLOSUM62 scores 27.0, Leni 8, Lenj 7, alignment SEQVENCE / SEQVE-CE."""

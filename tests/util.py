@@ -51,10 +51,10 @@ def pct(ids, alnlen):
     return 100.0 * (float(ids) / float(alnlen) if alnlen else 0.0)
 
 
-def fmt_user(h, cigar, ql, tl):
+def fmt_user(h, cigar, ql, tl, nucleo=True):
     return "%s\t%s\t%.1f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
         ql, tl, pct(h["ids"], h["alnlen"]), h["alnlen"], h["mism"], h["opens"], 1, h["ql"], 1, h["tl"], cigar,
-        "-" if h["strand"] else "+")
+        ("-" if h["strand"] else "+") if nucleo else ".")
 
 
 def fmt_b6(h, ql, tl):
@@ -63,16 +63,16 @@ def fmt_b6(h, ql, tl):
         ql, tl, pct(h["ids"], h["alnlen"]), h["alnlen"], h["mism"], h["opens"], 1, h["ql"], tlo, thi)
 
 
-def fmt_uc_hit(h, cigar, ql, tl):
+def fmt_uc_hit(h, cigar, ql, tl, nucleo=True):
     return "H\t%d\t%d\t%.1f\t%s\t0\t0\t%s\t%s\t%s" % (
-        h["target"], h["ql"], pct(h["ids"], h["alnlen"]), "-" if h["strand"] else "+", cigar, ql, tl)
+        h["target"], h["ql"], pct(h["ids"], h["alnlen"]), ("-" if h["strand"] else "+") if nucleo else ".", cigar, ql, tl)
 
 
 def fmt_uc_nohit(qlen, ql):
     return "N\t*\t%d\t*\t.\t*\t*\t*\t%s\t*" % (qlen, ql)
 
 
-def product_lines(res, q_labels, q_seqs, db_labels):
+def product_lines(res, q_labels, q_seqs, db_labels, nucleo=True):
     """usb200 Result -> (user, uc, b6) line lists in query input order."""
     user, uc, b6 = [], [], []
     for qi in range(len(q_seqs)):
@@ -81,15 +81,15 @@ def product_lines(res, q_labels, q_seqs, db_labels):
             h = res.hits[k]
             cig = res.cigar(h)
             tl = db_labels[int(h["target"])]
-            user.append(fmt_user(h, cig, q_labels[qi], tl))
-            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl))
+            user.append(fmt_user(h, cig, q_labels[qi], tl, nucleo))
+            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl, nucleo))
             b6.append(fmt_b6(h, q_labels[qi], tl))
         if b == e:
             uc.append(fmt_uc_nohit(len(q_seqs[qi]), q_labels[qi]))
     return user, uc, b6
 
 
-def oracle_lines(searcher, q_labels, q_seqs, db_labels):
+def oracle_lines(searcher, q_labels, q_seqs, db_labels, nucleo=True):
     from oracle import uso_py as O
     user, uc, b6 = [], [], []
     for qi, s in enumerate(q_seqs):
@@ -97,8 +97,8 @@ def oracle_lines(searcher, q_labels, q_seqs, db_labels):
         for h in hits:
             cig = O.compress_path(h["path"])
             tl = db_labels[h["target"]]
-            user.append(fmt_user(h, cig, q_labels[qi], tl))
-            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl))
+            user.append(fmt_user(h, cig, q_labels[qi], tl, nucleo))
+            uc.append(fmt_uc_hit(h, cig, q_labels[qi], tl, nucleo))
             b6.append(fmt_b6(h, q_labels[qi], tl))
         if not hits:
             uc.append(fmt_uc_nohit(len(s), q_labels[qi]))
@@ -129,6 +129,34 @@ def mutate(s, rate, rng, alphabet="ACGT"):
         else:
             out.append(c)
     return "".join(out)
+
+
+# ---------------------------------------------------------------- amino acid usearch_global
+# tools/make_golden_aa_global.py: config 1 (the reference's tmp/test.fa vs itself) and the protein
+# families of the usearch_local fixtures searched globally
+AA_GLOBAL_VARIANTS = {
+    "cfg1_id90": dict(inputs="cfg1", id=0.9),
+    "cfg1_id30_ma8": dict(inputs="cfg1", id=0.3, maxaccepts=8, maxrejects=64),
+    "gaa_id50": dict(inputs="gaa", id=0.5),
+    "gaa_id30_ma8": dict(inputs="gaa", id=0.3, maxaccepts=8, maxrejects=64),
+    "gaa_id90": dict(inputs="gaa", id=0.9),
+    "gaa_id70_ma3": dict(inputs="gaa", id=0.7, maxaccepts=3, maxrejects=16),
+}
+
+
+def aa_global_inputs(kind):
+    """-> (db_labels, db, q_labels, q)"""
+    if kind == "cfg1":
+        labels, seqs = read_fasta(os.path.join(GOLDEN, "cfg1_test.fa.gz"))
+        return labels, seqs, labels, seqs
+    dl, d = read_fasta(os.path.join(GOLDEN, "loc_aa_db.fa.gz"))
+    ql, q = read_fasta(os.path.join(GOLDEN, "loc_aa_q.fa.gz"))
+    return dl, d, ql, q
+
+
+def golden_lines(variant, kind):
+    with gzip.open(os.path.join(GOLDEN, "%s.%s.gz" % (variant, kind)), "rt") as f:
+        return f.read().splitlines()
 
 
 # ---------------------------------------------------------------- usearch_local
