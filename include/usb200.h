@@ -71,6 +71,12 @@ void usb_default_params(usb_params *p, int cluster_fast);
  * words of 5) or amino acid DB (nucleo=0: UDB words of 5 over 20 letters, udbparams.cpp:236-261;
  * seed words of 3, makedbsearcher.cpp:104-123; BLOSUM62). */
 void usb_set_local(usb_params *p, int nucleo, float evalue);
+/* Switches a -usearch_global parameter block to an amino acid database (BASELINE config 1; the
+ * reference builds a GlobalAligner for either alphabet, makedbsearcher.cpp:132-140): UDB words of 5
+ * over 20 letters (udbparams.cpp:251-257), HSP words of 3 (alnheuristics.cpp:37), BLOSUM62
+ * (blosum62.cpp:17-96), gap open -17 / extend -1 (alnparams.cpp:381-384), HSP identity gate
+ * max(id, 0.5) (alnheuristics.cpp:56), no strands. */
+void usb_set_amino(usb_params *p);
 
 /* One accepted hit == the statistics the reference derives lazily from an AlignResult
  * (alignresult.h:17-245, arscorer.cpp:201-296 FillLo).  Coordinates are 0-based. */
@@ -179,6 +185,14 @@ int usb_batch_download(usb_searcher *s, usb_result **out);
 /* Counters of the last usb_batch_run: out[0] = UDB postings read by the U-sort kernel,
  * out[1] = hits, out[2] = path runs, out[3] = (query,strand) jobs. */
 int usb_batch_counters(const usb_searcher *s, uint64_t out[4]);
+/* Device time of the last usb_batch_run by kernel family, in milliseconds (CUDA events on the
+ * library stream): out[0] U-sort (UDBUsortedSearcher::SetTargetOrder, udbusortedsearcher.cpp:284-410),
+ * out[1] HSP gate kernels (GlobalAlign_AllOpts up to the identity gate, globalalignmem.cpp:129-176),
+ * out[2] DP kernels (AlignHSPMem / ViterbiFastBandMem + FillLo, globalalignmem.cpp:70-112),
+ * out[3] work-list and commit kernels (Terminator, terminator.cpp:64-100), out[4] the number of
+ * records the gate passed on to the DP, out[5] DP cells.  Entries 1..3 are 0 when the candidate
+ * loop ran as one kernel (amino acids, unusual scores). */
+int usb_batch_kernel_ms(const usb_searcher *s, double out[6]);
 /* Number of kernel launches issued by this searcher so far. */
 uint64_t usb_searcher_launch_count(const usb_searcher *s);
 /* Device-resident packed hit records of the last usb_batch_run (for the NCCL gather of

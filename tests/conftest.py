@@ -16,3 +16,17 @@ def pytest_configure(config):
 def golden():
     from tests import util
     return util.Golden()
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests need a CUDA device: skipped (not failed) where there is none."""
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items:
+        return
+    # a library that does not load must fail the tests loudly, so only the device count decides
+    from usearch12_b200 import capi
+    have = capi.lib().usb_device_count() > 0
+    if not have:
+        skip = pytest.mark.skip(reason="no CUDA device (usb_device_count() == 0)")
+        for it in gpu_items:
+            it.add_marker(skip)

@@ -92,3 +92,32 @@ def test_udb_read_rejects_other_files(tmp_path):
     assert capi.lib().usb_udb_read(str(trunc).encode(), C.byref(h)) == -1
     assert b"truncated" in capi.lib().usb_last_error()
     assert capi.lib().usb_udb_write(path.encode(), C.byref(capi.default_params()), None, None, None, 0) == -1
+
+
+def test_udb_read_rejects_hostile_sizes(tmp_path):
+    """A .udb whose size fields exceed the file must come back as an error code, not as an
+    exception or abort through the C ABI (sizes are checked against the bytes left in the file)."""
+    import random
+    labels = ["t%d" % i for i in range(20)]
+    rng = random.Random(3)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(300)) for _ in labels]
+    path = str(tmp_path / "ok.udb")
+    capi.udb_write(path, labels, seqs)
+    raw = bytearray(open(path, "rb").read())
+    u = capi.Udb(path)
+    assert u.n_seq == 20
+    u.close()
+    # header is 200 bytes, then sizes[65536] (u32): blow every row size up
+    bad = bytearray(raw)
+    bad[200:200 + 4 * 65536] = b"\xff" * (4 * 65536)
+    p2 = str(tmp_path / "bad.udb")
+    open(p2, "wb").write(bad)
+    h = C.c_void_p()
+    rc = capi.lib().usb_udb_read(p2.encode(), C.byref(h))
+    assert rc != 0 and not h.value
+    assert b"inconsistent" in capi.lib().usb_last_error() or b"truncated" in capi.lib().usb_last_error()
+    # truncated file
+    p3 = str(tmp_path / "short.udb")
+    open(p3, "wb").write(raw[: len(raw) // 2])
+    rc = capi.lib().usb_udb_read(p3.encode(), C.byref(h))
+    assert rc != 0

@@ -49,10 +49,10 @@ SYMBOLS = [
     "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
     "usb_index_seq_count", "usb_index_posting_count", "usb_index_posting_width", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
-    "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_searcher_launch_count", "usb_batch_export_hits_device",
+    "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_batch_kernel_ms", "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
-    "usb_viterbi_batch", "usb_set_local", "usb_local_evalue", "usb_local_pairs",
+    "usb_viterbi_batch", "usb_set_local", "usb_set_amino", "usb_local_evalue", "usb_local_pairs",
     "usb_udb_write", "usb_udb_probe", "usb_udb_read", "usb_udb_free", "usb_udb_seq_count", "usb_udb_is_nucleo",
     "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row", "usb_debug_half_row",
 ]
@@ -107,6 +107,7 @@ def lib():
     L.usb_batch_run.argtypes = [vp, C.POINTER(C.c_float)]
     L.usb_batch_download.argtypes = [vp, C.POINTER(vp)]
     L.usb_batch_counters.argtypes = [vp, u64p]
+    L.usb_batch_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.usb_cluster_round.argtypes = [vp, vp, vp, C.c_uint32, u32p, vp, C.POINTER(vp)]
     L.usb_searcher_launch_count.argtypes = [vp]
     L.usb_searcher_launch_count.restype = C.c_uint64
@@ -130,6 +131,8 @@ def lib():
     L.usb_viterbi_batch.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
     L.usb_set_local.argtypes = [C.POINTER(Params), C.c_int, C.c_float]
     L.usb_set_local.restype = None
+    L.usb_set_amino.argtypes = [C.POINTER(Params)]
+    L.usb_set_amino.restype = None
     L.usb_local_evalue.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.usb_local_pairs.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(vp)]
     _lib = L
@@ -357,6 +360,11 @@ class Searcher:
         out = (C.c_uint64 * 4)()
         check(lib().usb_batch_counters(self.handle, out))
         return dict(postings=out[0], hits=out[1], runs=out[2], jobs=out[3])
+
+    def kernel_ms(self):
+        out = (C.c_double * 6)()
+        check(lib().usb_batch_kernel_ms(self.handle, out))
+        return dict(rank=out[0], gate=out[1], dp=out[2], misc=out[3], dp_records=int(out[4]), dp_cells=int(out[5]))
 
     @property
     def launch_count(self):

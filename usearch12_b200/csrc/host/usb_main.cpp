@@ -169,6 +169,17 @@ int main(int argc, char **argv)
 		const std::string hw = take("hspw", nullptr);
 		if (!hw.empty())
 			O.P.hspw = (uint32_t)atoi(hw.c_str());
+	} else if (oquery.empty()) {
+		// -usearch_global takes either alphabet (makedbsearcher.cpp:132-140); amino acid databases
+		// switch to BLOSUM62, gap open -17 and HSP words of 3 letters
+		// (a missing database is reported by Search() after the option checks below)
+		FILE *probe = fopen(db.c_str(), "rb");
+		if (probe) {
+			fclose(probe);
+			nucleo = IsUDBFile(db) ? UDBIsNucleo(db) : GuessIsNucleo(db);
+		}
+		if (!nucleo)
+			usb_set_amino(&O.P);
 	}
 	const std::string strand = take("strand", dflt_strand);
 	if (nucleo && strand != "plus" && strand != "both")

@@ -23,8 +23,20 @@
 // alignment column per lane with ballot/popc prefix counts.
 #pragma once
 #include "usb_dev.cuh"
+#include "usb_tables.h"
 
 namespace usb {
+
+// Letter tables of the amino acid path (config 1: amino acid -usearch_global, makedbsearcher.cpp:132-140).
+// Sequences are staged as the 6-bit character classes of usb_tables.h; substitution scores come
+// from BLOSUM62 (blosum62.cpp:17-96), identities from g_MatchMxAmino (alpha2.cpp:250-279), HSP
+// words are numbers of hspw letters in base 20 with wildcards as letter 0 (hspfinder.cpp:226-270).
+struct AlignTables {
+	int8_t score[USB_NCODE * USB_NCODE];
+	unsigned long long match[USB_NCODE];
+	uint8_t word_letter[USB_NCODE];
+	uint8_t code[256];
+};
 
 struct AlignArgs {
 	DevParams P;
@@ -54,6 +66,7 @@ struct AlignArgs {
 	uint32_t fast_bytes;      // per-warp bytes of the "fast" arrays
 	uint32_t scratch_bytes;   // per-warp bytes of the scratch union inside the fast arrays
 	uint32_t fast_in_smem;    // 1: fast arrays in shared memory, 0: in the slab
+	const AlignTables *tab;   // amino acid path only
 	DevCounters *ctr;
 };
 
@@ -76,6 +89,7 @@ struct WarpWs {
 	uint32_t *order, *prev, *chain;
 	int *cscore;
 	uint32_t LA, LB, nwordsA;
+	const AlignTables *T;     // amino acid path: tables in shared memory
 	bool seed_dirty;          // a wide DP borrowed the seed table's memory: rebuild before the next seed search
 };
 
@@ -122,18 +136,40 @@ __device__ __forceinline__ void ws_setup(const AlignArgs &a, WarpWs &w, uint8_t 
 
 // %id identity of query position qp vs target position tp; raw letters are only needed (and the
 // target's only fetched from global memory) when a wildcard is involved.
-__device__ __forceinline__ bool pos_match(const WarpWs &w, uint32_t qp, uint32_t tp)
+template <bool AA> __device__ __forceinline__ bool pos_match(const WarpWs &w, uint32_t qp, uint32_t tp)
 {
 	const uint32_t ca = w.Ac[qp], cb = w.Bc[tp];
+	if constexpr (AA)
+		return (w.T->match[ca] >> cb) & 1ull;
 	if ((ca | cb) < 4)
 		return ca == cb;
 	return chars_match_dev(w.A[qp], w.B[tp], ca, cb);
 }
 
+// doubled substitution score of two staged letters
+template <bool AA> __device__ __forceinline__ int subst2g(const AlignArgs &a, const WarpWs &w, uint32_t ca, uint32_t cb)
+{
+	if constexpr (AA)
+		return 2 * (int)w.T->score[ca * USB_NCODE + cb];
+	else
+		return subst2(a.P, ca, cb);
+}
+
 // ------------------------------------------------------------------ sequence staging
+template <bool AA>
 __device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const uint8_t *Q, uint32_t L, uint32_t strand)
 {
 	const uint32_t lane = lane_id();
+	if constexpr (AA) {
+		for (uint32_t i = lane; i < L; i += 32) {
+			const uint32_t c = Q[i];
+			w.A[i] = (uint8_t)c;
+			w.Ac[i] = w.T->code[c];
+		}
+		w.LA = L;
+		__syncwarp();
+		return;
+	}
 	for (uint32_t i = lane; i < L; i += 32) {
 		uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
 		w.A[i] = (uint8_t)c;
@@ -156,11 +192,18 @@ __device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const 
 	__syncwarp();
 }
 
-__device__ __forceinline__ void load_target(const AlignArgs &a, WarpWs &w, uint32_t t)
+template <bool AA> __device__ __forceinline__ void load_target(const AlignArgs &a, WarpWs &w, uint32_t t)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t L = a.db_len[t];
 	w.B = a.db_seq + a.db_off[t];
+	if constexpr (AA) {
+		for (uint32_t i = lane; i < L; i += 32)
+			w.Bc[i] = w.T->code[w.B[i]];
+		w.LB = L;
+		__syncwarp();
+		return;
+	}
 	const uint4 *src = (const uint4 *)w.B;
 	uint4 *dC = (uint4 *)w.Bc;
 	const uint32_t n16 = (L + 15) / 16;
@@ -205,10 +248,23 @@ __device__ __forceinline__ uint32_t hsp_word_at(const uint32_t *X2, uint32_t p, 
 	return ext16(X2, p) & (hsp_words - 1);
 }
 
+// HSP word at position p of the query (which = 0) or the target (1)
+template <bool AA> __device__ __forceinline__ uint32_t word_at(const AlignArgs &a, const WarpWs &w, int which, uint32_t p)
+{
+	if constexpr (AA) {
+		const uint8_t *c = (which ? w.Bc : w.Ac) + p;
+		uint32_t word = 0;
+		for (uint32_t i = 0; i < a.P.hspw; ++i)
+			word = word * 20u + w.T->word_letter[c[i]];
+		return word;
+	} else
+		return hsp_word_at(which ? w.B2 : w.A2, p, a.P.hsp_words);
+}
+
 // Builds cnt[word] = min(8, occurrences) and, per word, the first 8 query positions in query
 // order (hspfinder.cpp:304-323), as a CSR (start, pos).  Query order inside a word is kept by
 // processing positions in chunks of 32 and ranking equal words inside a chunk with match_any.
-__device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
+template <bool AA> __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t hw = a.P.hspw, HW = a.P.hsp_words;
@@ -224,7 +280,7 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 	for (uint32_t base = 0; base < nw; base += 32) {
 		const uint32_t p = base + lane;
 		const bool valid = p < nw;
-		const uint32_t word = valid ? hsp_word_at(w.A2, p, HW) : (0x80000000u | lane);
+		const uint32_t word = valid ? word_at<AA>(a, w, 0, p) : (0x80000000u | lane);
 		const uint32_t peers = __match_any_sync(USB_FULL, word);
 		if (valid && (peers & lanemask_lt()) == 0) {
 			uint32_t c = w.cnt[word] + __popc(peers);
@@ -255,7 +311,7 @@ __device__ void build_seed_table(const AlignArgs &a, WarpWs &w)
 	for (uint32_t base = 0; base < nw; base += 32) {
 		const uint32_t p = base + lane;
 		const bool valid = p < nw;
-		const uint32_t word = valid ? hsp_word_at(w.A2, p, HW) : (0x80000000u | lane);
+		const uint32_t word = valid ? word_at<AA>(a, w, 0, p) : (0x80000000u | lane);
 		const uint32_t peers = __match_any_sync(USB_FULL, word);
 		uint32_t before = 0;
 		if (valid)
@@ -296,6 +352,7 @@ __device__ __forceinline__ bool is_global_hsp(uint32_t ALo, uint32_t BLo, uint32
 // One lane extends one seed letter by letter (ungappedblast.cpp:76-193): right from the seed's
 // last letter, then left from its first letter starting at the best right-extended score.
 // Scores are doubled.  Generic form, used when the score signs do not allow the packed walk.
+template <bool AA>
 __device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
   int &best_out, uint32_t &best_lo_out, uint32_t &best_hi_out)
 {
@@ -304,7 +361,7 @@ __device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const Warp
 	const uint8_t *Ac = w.Ac, *Bc = w.Bc;
 	int score = 0;
 	for (uint32_t j = 0; j < hw; ++j)
-		score += subst2(P, Ac[APos + j], Bc[BPos + j]);
+		score += subst2g<AA>(a, w, Ac[APos + j], Bc[BPos + j]);
 	int best = score;
 	uint32_t bp = BPos + hw - 1, ap = APos + hw - 1, best_hi = bp;
 	for (;;) {
@@ -314,7 +371,7 @@ __device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const Warp
 		++ap;
 		if (ap >= LA)
 			break;
-		score += subst2(P, Ac[ap], Bc[bp]);
+		score += subst2g<AA>(a, w, Ac[ap], Bc[bp]);
 		if (score > best) {
 			best = score;
 			best_hi = bp;
@@ -330,7 +387,7 @@ __device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const Warp
 			break;
 		--bp;
 		--ap;
-		score += subst2(P, Ac[ap], Bc[bp]);
+		score += subst2g<AA>(a, w, Ac[ap], Bc[bp]);
 		if (score > best) {
 			best = score;
 			best_lo = bp;
@@ -349,6 +406,7 @@ __device__ __forceinline__ void extend_seed_bytes(const AlignArgs &a, const Warp
 // applied at once: it cannot trigger the X-drop test and, if it ends above the best score, its
 // last letter is the new best end.  A wildcard pair changes nothing.  A mismatch is the only
 // step that can terminate.  The result is identical to extend_seed_bytes.
+template <bool WILD>
 __device__ __forceinline__ void extend_seed_packed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
   int seed2, int &best_out, uint32_t &best_lo_out, uint32_t &best_hi_out)
 {
@@ -363,7 +421,7 @@ __device__ __forceinline__ void extend_seed_packed(const AlignArgs &a, const War
 			if (k == 0)
 				break;
 			const uint32_t x = ext16(w.A2, pa) ^ ext16(w.B2, pb);
-			const uint32_t wl = (ext16(w.An2, pa) | ext16(w.Bn2, pb)) & M55;
+			const uint32_t wl = WILD ? (ext16(w.An2, pa) | ext16(w.Bn2, pb)) & M55 : 0u;
 			uint32_t stop = ((x | (x >> 1)) & M55) | wl; // pairs that are not a definite match
 			uint32_t done = 0;
 			bool term = false;
@@ -404,7 +462,7 @@ __device__ __forceinline__ void extend_seed_packed(const AlignArgs &a, const War
 				break;
 			const uint32_t sh = 32 - 2 * k;
 			const uint32_t x = ext16(w.A2, pa - k) ^ ext16(w.B2, pb - k);
-			const uint32_t wl = ((ext16(w.An2, pa - k) | ext16(w.Bn2, pb - k)) & M55) << sh;
+			const uint32_t wl = WILD ? ((ext16(w.An2, pa - k) | ext16(w.Bn2, pb - k)) & M55) << sh : 0u;
 			uint32_t stop = (((x | (x >> 1)) & M55) << sh) | wl; // nearest letter at bit 30
 			uint32_t done = 0;
 			bool term = false;
@@ -447,21 +505,22 @@ __device__ __forceinline__ void extend_seed_packed(const AlignArgs &a, const War
 // window (or the sequence ends there), the gain on that side is at most its match count; when
 // both sides are bounded like that and seed + bounds < MinGlobalHSPScore the seed can never be
 // accepted.  About 85 % of random seeds end here.
-__device__ __forceinline__ bool seed_may_pass(const AlignArgs &a, const WarpWs &w, uint32_t ap, uint32_t bp, int &seed2)
+template <bool WILD>
+__device__ __forceinline__ bool seed_may_pass_p(const AlignArgs &a, const WarpWs &w, uint32_t ap, uint32_t bp, int &seed2)
 {
 	const DevParams &P = a.P;
 	const uint32_t LA = w.LA, LB = w.LB, hw = P.hspw;
 	if (!is_global_hsp(ap, bp, LA, LB))
 		return false;
 	const uint32_t seedmask = M55 & (P.hsp_words - 1);
-	const uint32_t wseed = (ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask;
+	const uint32_t wseed = WILD ? (ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask : 0u;
 	seed2 = P.match2 * (int)(hw - __popc(wseed));
 	const uint32_t ra = ap + hw, rb = bp + hw;
 	const uint32_t kR = min(16u, min(LA - ra, LB - rb));
 	uint32_t mR = 0;
 	if (kR) {
 		const uint32_t x = ext16(w.A2, ra) ^ ext16(w.B2, rb);
-		const uint32_t wl = ext16(w.An2, ra) | ext16(w.Bn2, rb);
+		const uint32_t wl = WILD ? ext16(w.An2, ra) | ext16(w.Bn2, rb) : 0u;
 		const uint32_t mis = ((x | (x >> 1)) & ~wl & M55) & (kR == 16 ? M55 : ((1u << (2 * kR)) - 1));
 		mR = kR - __popc(mis);
 	}
@@ -469,7 +528,7 @@ __device__ __forceinline__ bool seed_may_pass(const AlignArgs &a, const WarpWs &
 	uint32_t mL = 0;
 	if (kL) {
 		const uint32_t x = ext16(w.A2, ap - kL) ^ ext16(w.B2, bp - kL);
-		const uint32_t wl = ext16(w.An2, ap - kL) | ext16(w.Bn2, bp - kL);
+		const uint32_t wl = WILD ? ext16(w.An2, ap - kL) | ext16(w.Bn2, bp - kL) : 0u;
 		const uint32_t mis = ((x | (x >> 1)) & ~wl & M55) & (kL == 16 ? M55 : ((1u << (2 * kL)) - 1));
 		mL = kL - __popc(mis);
 	}
@@ -480,16 +539,44 @@ __device__ __forceinline__ bool seed_may_pass(const AlignArgs &a, const WarpWs &
 	return true;
 }
 
+__device__ __forceinline__ bool seed_may_pass(const AlignArgs &a, const WarpWs &w, uint32_t ap, uint32_t bp, int &seed2)
+{
+	return seed_may_pass_p<true>(a, w, ap, bp, seed2);
+}
+
+// Acceptance test of a seed extended on the packed sequences (ungappedblast.cpp:172-193).
+template <bool WILD>
+__device__ __forceinline__ bool extend_seed_p(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos, int seed2,
+  uint32_t MinLength, HspRec &out, uint32_t &Bhi_out)
+{
+	int best;
+	uint32_t best_lo, best_hi;
+	extend_seed_packed<WILD>(a, w, APos, BPos, seed2, best, best_lo, best_hi);
+	const uint32_t Length = best_hi - best_lo + 1;
+	const uint32_t Alo = best_lo - (BPos - APos); // same diagonal; wrap-around arithmetic is exact
+	if (Length < MinLength || (float)best < a.P.minscore2)
+		return false;
+	if (!is_global_hsp(Alo, best_lo, w.LA, w.LB))
+		return false;
+	out.Loi = Alo;
+	out.Loj = best_lo;
+	out.Len = Length;
+	out.score2 = best;
+	Bhi_out = best_hi;
+	return true;
+}
+
 // Acceptance test of an extended seed (ungappedblast.cpp:172-193).
+template <bool AA>
 __device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w, uint32_t APos, uint32_t BPos,
   int seed2, bool packed, uint32_t MinLength, HspRec &out, uint32_t &Bhi_out)
 {
 	int best;
 	uint32_t best_lo, best_hi;
-	if (packed)
-		extend_seed_packed(a, w, APos, BPos, seed2, best, best_lo, best_hi);
+	if (!AA && packed)
+		extend_seed_packed<true>(a, w, APos, BPos, seed2, best, best_lo, best_hi);
 	else
-		extend_seed_bytes(a, w, APos, BPos, best, best_lo, best_hi);
+		extend_seed_bytes<AA>(a, w, APos, BPos, best, best_lo, best_hi);
 	const uint32_t Length = best_hi - best_lo + 1;
 	const uint32_t Alo = best_lo - (BPos - APos); // same diagonal; wrap-around arithmetic is exact
 	if (Length < MinLength || (float)best < a.P.minscore2)
@@ -511,6 +598,11 @@ __device__ __forceinline__ bool extend_seed(const AlignArgs &a, const WarpWs &w,
 #define SEED_SCRATCH_BYTES (8 * SEEDQ1 + 6 * SEEDQ2)
 
 // Extends the queued survivors 32 at a time and accepts in order (see ungapped_blast).
+// (Measured and dropped: letting only the first seed of every diagonal walk and the others wait
+// -- the walks of a batch run in lockstep, so a batch costs its longest walk whether one or twenty
+// lanes walk that diagonal, and every waiting seed that is needed after all costs a second round:
+// k_align 347 -> 473 ms.)
+template <bool AA>
 __device__ __forceinline__ void extend_queued(const AlignArgs &a, WarpWs &w, const uint32_t *q2b, const uint16_t *q2a,
   uint32_t n2, bool packed, uint32_t MinLength, uint32_t &cur, uint32_t &nung)
 {
@@ -528,11 +620,11 @@ __device__ __forceinline__ void extend_queued(const AlignArgs &a, WarpWs &w, con
 			const uint32_t ap = q2a[s];
 			if (bp >= cur) {
 				int seed2 = 0;
-				if (packed) {
+				if (!AA && packed) {
 					const uint32_t seedmask = M55 & (P.hsp_words - 1);
 					seed2 = P.match2 * (int)(P.hspw - __popc((ext16(w.An2, ap) | ext16(w.Bn2, bp)) & seedmask));
 				}
-				ok = extend_seed(a, w, ap, bp, seed2, packed, MinLength, h, bhi);
+				ok = extend_seed<AA>(a, w, ap, bp, seed2, packed, MinLength, h, bhi);
 			}
 		}
 		uint32_t okmask = __ballot_sync(USB_FULL, ok);
@@ -569,7 +661,7 @@ __device__ __forceinline__ void extend_queued(const AlignArgs &a, WarpWs &w, con
 // at a time.  An extension does not depend on scan history, so the sequential result is: walk
 // the survivors in order, accept the first acceptable one at or after the current scan
 // position, move the scan position past it, continue.
-__device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLength)
+template <bool AA> __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLength)
 {
 	const uint32_t lane = lane_id();
 	const DevParams &P = a.P;
@@ -577,7 +669,7 @@ __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLe
 	const uint32_t LB = w.LB;
 	if (LB < 2 * hw)
 		return 0;
-	const bool packed = P.match2 > 0 && P.mismatch2 < 0;
+	const bool packed = !AA && P.match2 > 0 && P.mismatch2 < 0;
 	const uint32_t nwordsB = LB - hw + 1;
 	uint32_t *q1b = (uint32_t *)w.scratch;
 	uint32_t *q1s = q1b + SEEDQ1;
@@ -592,7 +684,7 @@ __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLe
 			const uint32_t bpos = scan + lane;
 			uint32_t na = 0, word = 0;
 			if (bpos < nwordsB) {
-				word = hsp_word_at(w.B2, bpos, HW);
+				word = word_at<AA>(a, w, 1, bpos);
 				na = w.cnt[word];
 			}
 			const uint32_t m = __ballot_sync(USB_FULL, na != 0);
@@ -608,7 +700,7 @@ __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLe
 		uint32_t n2 = 0;
 		for (uint32_t e0 = 0; e0 < n1; e0 += 32) {
 			if (n2 + 256 > SEEDQ2) {
-				extend_queued(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
+				extend_queued<AA>(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
 				n2 = 0;
 			}
 			const uint32_t e = e0 + lane;
@@ -640,7 +732,7 @@ __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs &w, uint32_t MinLe
 			n2 += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
 		}
 		__syncwarp();
-		extend_queued(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
+		extend_queued<AA>(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
 		scan = max(scan, cur);
 	}
 	__syncwarp();
@@ -828,6 +920,7 @@ __device__ __forceinline__ int scan_gap(int v, int ext)
 // (viterbifastbandmem.cpp:232-253), LA, LB >= 1.  Appends the path at out[0..) and returns its
 // length; *score2 receives the doubled score.  Rows are swept in order; within a row each lane
 // owns one column: M and D depend only on the previous row, the I state is a prefix max-plus scan.
+template <bool AA>
 __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *Ac, uint32_t LA, const uint8_t *Bc,
   uint32_t LB, const GapCosts &G, char *out, int *score2, uint32_t *cells)
 {
@@ -899,7 +992,7 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 				xM = Iexcl;
 				bits = TB_IM;
 			}
-			const int mnew = xM + (act ? subst2(P, ca, Bc[j]) : 0);
+			const int mnew = xM + (act ? subst2g<AA>(a, w, ca, Bc[j]) : 0);
 			const int ob = (j == 0) ? G.LOpenB : G.OpenB, eb = (j == 0) ? G.LExtB : G.ExtB;
 			const int md = saved + ob;
 			int dnew = dold + eb;
@@ -1053,6 +1146,7 @@ __device__ __forceinline__ uint32_t fill_run(char *out, char c, uint32_t n)
 }
 
 // globalalignmem.cpp:70-112 AlignHSPMem
+template <bool AA>
 __device__ uint32_t align_hole(const AlignArgs &a, WarpWs &w, uint32_t Loi, uint32_t Loj, uint32_t Leni, uint32_t Lenj,
   char *out, usb_qstat &st)
 {
@@ -1062,11 +1156,12 @@ __device__ uint32_t align_hole(const AlignArgs &a, WarpWs &w, uint32_t Loi, uint
 		return fill_run(out, 'D', Leni);
 	const GapCosts G = hole_costs(a.P, Loi == 0, Loj == 0, Loi + Leni == w.LA, Loj + Lenj == w.LB);
 	++st.n_dp;
-	return viterbi_band(a, w, w.Ac + Loi, Leni, w.Bc + Loj, Lenj, G, out, nullptr, &st.dp_cells);
+	return viterbi_band<AA>(a, w, w.Ac + Loi, Leni, w.Bc + Loj, Lenj, G, out, nullptr, &st.dp_cells);
 }
 
 // GlobalAlign_AllOpts (globalalignmem.cpp:129-236).  Returns path length, 0 = rejected (no AR).
 // The seed table of the query must be current.
+template <bool AA>
 __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, uint32_t *n_chain_out)
 {
 	const DevParams &P = a.P;
@@ -1079,12 +1174,12 @@ __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, u
 			return 0;
 		const GapCosts G = hole_costs(P, true, true, true, true);
 		++st.n_dp;
-		return viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, w.path, nullptr, &st.dp_cells);
+		return viterbi_band<AA>(a, w, w.Ac, LA, w.Bc, LB, G, w.path, nullptr, &st.dp_cells);
 	}
 	uint32_t MinHSPLength = P.min_hsp_len == 0 ? 32 : P.min_hsp_len;
 	MinHSPLength = min(MinHSPLength, LA / 4);
 	MinHSPLength = max(MinHSPLength, 16u);
-	const uint32_t nung = ungapped_blast(a, w, MinHSPLength);
+	const uint32_t nung = ungapped_blast<AA>(a, w, MinHSPLength);
 	const uint32_t nchain = chain_hsps(a, w, nung);
 	if (n_chain_out)
 		*n_chain_out = nchain;
@@ -1097,7 +1192,7 @@ __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, u
 			const uint32_t k = base + lane;
 			bool same = false;
 			if (k < h.Len)
-				same = pos_match(w, h.Loi + k, h.Loj + k);
+				same = pos_match<AA>(w, h.Loi + k, h.Loj + k);
 			TotalSame += __popc(__ballot_sync(USB_FULL, same));
 		}
 	}
@@ -1113,24 +1208,24 @@ __device__ uint32_t global_align(const AlignArgs &a, WarpWs &w, usb_qstat &st, u
 			return 0;
 		const GapCosts G = hole_costs(P, true, true, true, true);
 		++st.n_dp;
-		return viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, path, nullptr, &st.dp_cells);
+		return viterbi_band<AA>(a, w, w.Ac, LA, w.Bc, LB, G, path, nullptr, &st.dp_cells);
 	}
 	uint32_t Loi = 0, Loj = 0;
 	for (uint32_t c = 0; c < nchain; ++c) {
 		const HspRec h = w.ung[w.chain[c]];
-		n += align_hole(a, w, Loi, Loj, h.Loi - Loi, h.Loj - Loj, path + n, st);
+		n += align_hole<AA>(a, w, Loi, Loj, h.Loi - Loi, h.Loj - Loj, path + n, st);
 		n += fill_run(path + n, 'M', h.Len);
 		Loi = h.Loi + h.Len;
 		Loj = h.Loj + h.Len;
 	}
-	n += align_hole(a, w, Loi, Loj, LA - Loi, LB - Loj, path + n, st);
+	n += align_hole<AA>(a, w, Loi, Loj, LA - Loi, LB - Loj, path + n, st);
 	__syncwarp();
 	return n;
 }
 
 // ------------------------------------------------------------------ a17: statistics + hit record
 // arscorer.cpp:201-296 FillLo over the path between the first and last M column.
-__device__ bool path_stats(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_hit &h)
+template <bool AA> __device__ bool path_stats(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_hit &h)
 {
 	const uint32_t lane = lane_id();
 	const char *path = w.path;
@@ -1182,7 +1277,7 @@ __device__ bool path_stats(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_
 		const uint32_t tp = tpos + __popc(tm & lanemask_lt());
 		bool same = false;
 		if (isM)
-			same = pos_match(w, qp, tp);
+			same = pos_match<AA>(w, qp, tp);
 		uint32_t prev = __shfl_up_sync(USB_FULL, ch, 1);
 		if (lane == 0)
 			prev = prev_carry;
@@ -1266,7 +1361,7 @@ __device__ bool emit_runs(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_h
 }
 
 // ------------------------------------------------------------------ the job loop
-__device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
+template <bool AA> __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 {
 	const uint32_t lane = lane_id();
 	const bool pairs = a.pair_q != nullptr;
@@ -1278,21 +1373,21 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 	if (ncand != 0) {
 		const uint64_t q0 = a.q_off[qi];
 		const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
-		load_query(a, w, a.q + q0, L, strand);
-		build_seed_table(a, w);
+		load_query<AA>(a, w, a.q + q0, L, strand);
+		build_seed_table<AA>(a, w);
 		w.seed_dirty = false;
 		uint32_t acc = 0, rej = 0;
 		for (uint32_t k = 0; k < ncand; ++k) {
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
 			if (w.seed_dirty) {
-				build_seed_table(a, w);
+				build_seed_table<AA>(a, w);
 				w.seed_dirty = false;
 			}
-			load_target(a, w, t);
+			load_target<AA>(a, w, t);
 			++st.n_tried;
 			st.seq_bytes += w.LA + w.LB;
 			uint32_t nchain = 0;
-			const uint32_t n = global_align(a, w, st, &nchain);
+			const uint32_t n = global_align<AA>(a, w, st, &nchain);
 			if (pairs && a.hsp_out) {
 				uint32_t *ho = a.hsp_out + (uint64_t)job * (1 + 4 * a.max_hsp);
 				if (lane == 0) {
@@ -1313,7 +1408,7 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 				usb_hit h;
 				h.query = qi; h.target = t; h.strand = strand; h.rank = pairs ? job : k;
 				h.ql = w.LA; h.tl = w.LB; h.run_off = 0; h.run_cnt = 0; h.raw = 0; h.sub = 0;
-				if (!path_stats(a, w, n, h)) {
+				if (!path_stats<AA>(a, w, n, h)) {
 					if (lane == 0)
 						atomicOr(&a.ctr->err, ERR_NO_M);
 				} else {
@@ -1359,16 +1454,27 @@ __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 }
 
 #define ALIGN_MAX_WARPS 16
-__global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_align(const AlignArgs a)
+// AA = true: amino acid alphabet; the letter tables sit in front of the per-warp arrays in shared memory.
+#define ALIGN_TAB_BYTES ((uint32_t)((sizeof(AlignTables) + 15) & ~(size_t)15))
+template <bool AA> __global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_align(const AlignArgs a)
 {
 	extern __shared__ __align__(16) uint8_t align_smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
 	uint8_t *slab = a.slab + (uint64_t)gw * a.slab_stride;
-	uint8_t *fast = a.fast_in_smem ? align_smem + (size_t)warp * a.fast_bytes : slab;
+	uint8_t *smem = align_smem;
+	WarpWs w;
+	w.T = nullptr;
+	if constexpr (AA) {
+		for (uint32_t i = threadIdx.x; i < sizeof(AlignTables) / 4; i += blockDim.x)
+			((uint32_t *)smem)[i] = ((const uint32_t *)a.tab)[i];
+		__syncthreads();
+		w.T = (const AlignTables *)smem;
+		smem += ALIGN_TAB_BYTES;
+	}
+	uint8_t *fast = a.fast_in_smem ? smem + (size_t)warp * a.fast_bytes : slab;
 	if (!a.fast_in_smem)
 		slab += a.fast_bytes;
-	WarpWs w;
 	ws_setup(a, w, fast, slab);
 	for (;;) {
 		uint32_t job = 0;
@@ -1377,7 +1483,7 @@ __global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_align(const AlignAr
 		job = __shfl_sync(USB_FULL, job, 0);
 		if (job >= a.n_jobs)
 			break;
-		align_job(a, w, job);
+		align_job<AA>(a, w, job);
 	}
 }
 
@@ -1403,6 +1509,7 @@ __global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_viterbi(const Viter
 	if (!a.fast_in_smem)
 		slab += a.fast_bytes;
 	WarpWs w;
+	w.T = nullptr;
 	ws_setup(a, w, fast, slab);
 	for (;;) {
 		uint32_t job = 0;
@@ -1426,7 +1533,7 @@ __global__ void __launch_bounds__(ALIGN_MAX_WARPS * 32, 1) k_viterbi(const Viter
 		char *out = v.paths + v.path_off[job];
 		int sc = 0;
 		uint32_t cells = 0;
-		const uint32_t n = viterbi_band(a, w, w.Ac, LA, w.Bc, LB, G, out, &sc, &cells);
+		const uint32_t n = viterbi_band<false>(a, w, w.Ac, LA, w.Bc, LB, G, out, &sc, &cells);
 		if (lane == 0) {
 			out[n] = 0;
 			v.score2[job] = sc;

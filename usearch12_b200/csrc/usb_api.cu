@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "usb_align.cuh"
+#include "usb_stage.cuh"
 #include "usb_local.cuh"
 #include "usb_hostindex.h"
 #include "usb_rank.cuh"
@@ -50,6 +51,37 @@ int fail_msg(int code, const char *msg)
 	} while (0)
 
 extern "C" const char *usb_last_error(void) { return g_err.c_str(); }
+
+// cudaFuncSetAttribute state is per function and per device, shared by every searcher and host
+// thread of the process: it is tracked here under one mutex and the dynamic shared-memory limit is
+// only ever raised.  The mutex is held across "set attribute + launch" so that a launch never sees
+// a limit or carve-out another thread chose.
+enum { FN_RANK_F, FN_RANK_T, FN_RANK_BIG, FN_ALIGN_NT, FN_ALIGN_AA, FN_VITERBI, FN_LOCAL, FN_GATE, FN_DP, FN_COUNT };
+static std::mutex g_attr_mu;
+static size_t g_attr_smem[64][FN_COUNT];
+static int g_attr_carve[64][FN_COUNT];
+
+// call with g_attr_mu held
+static cudaError_t func_smem_locked(const void *fn, int id, size_t bytes, int carve = -2)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev < 0 || dev >= 64)
+		return cudaErrorInvalidDevice;
+	if (bytes > g_attr_smem[dev][id]) {
+		if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess)
+			return e;
+		g_attr_smem[dev][id] = bytes;
+	}
+	if (carve != -2 && carve != g_attr_carve[dev][id] - 1000) {
+		if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess)
+			return e;
+		g_attr_carve[dev][id] = carve + 1000; // 0 = never set
+	}
+	return cudaSuccess;
+}
 
 extern "C" int usb_device_count(void)
 {
@@ -107,6 +139,19 @@ extern "C" void usb_set_local(usb_params *p, int nucleo, float evalue)
 		p->word_length = 5;
 		p->hspw = 3;
 	}
+}
+
+// Amino acid database searched globally (makedbsearcher.cpp:132-140 builds a GlobalAligner for either
+// alphabet): UDB words of 5 letters over 20 (udbparams.cpp:251-257), HSP words of 3
+// (alnheuristics.cpp:37), BLOSUM62, gap open -17 / extend -1 (alnparams.cpp:381-384), no strands.
+extern "C" void usb_set_amino(usb_params *p)
+{
+	p->is_nucleo = 0;
+	p->strand_both = 0;
+	p->word_length = 5;
+	p->hspw = 3;
+	p->gap_open = -17.0f;
+	p->gap_ext = -1.0f;
 }
 
 // ------------------------------------------------------------------ objects
@@ -223,6 +268,9 @@ struct usb_index {
 	DevBuf<uint8_t> d_seqs;
 	DevBuf<uint64_t> d_seq_off;
 	DevBuf<uint32_t> d_seq_len;
+	// nucleotide targets packed two bits per letter + wildcard flags (k_pack_targets, usb_stage.cuh)
+	DevBuf<uint32_t> d_db2, d_dbn;
+	DevBuf<uint8_t> d_wild;
 	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
 
@@ -304,18 +352,25 @@ struct usb_searcher {
 	DevBuf<usb_qstat> d_qstat;
 	DevBuf<DevCounters> d_ctr;
 	DevBuf<uint8_t> d_slab, d_uarena;
-	size_t rank_smem_set = 0;
-	bool rank_two = false;
 	// pinned host staging for the raw (unordered) hit records of a batch
 	void *h_stage = nullptr;
 	size_t h_stage_cap = 0;
 	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
-	bool bigsmem_set = false;
 	// -usearch_local
 	DevBuf<LocalDevTables> d_ltab;
 	DevBuf<float> d_min_ungapped;
 	DevBuf<int> d_min_gapped;
-	size_t local_smem_set = 0;
+	DevBuf<AlignTables> d_atab;          // amino acid usearch_global: letter tables of k_align
+	// staged candidate loop (usb_stage.cuh)
+	DevBuf<uint32_t> d_job_state, d_verdict, d_items, d_hsp_arena;
+	DevBuf<PassRec> d_recs;
+	DevBuf<usb_hit> d_hits_stage;
+	DevBuf<StageCounters> d_sc;
+	DevBuf<uint8_t> d_gslab;
+	cudaEvent_t ev_st[4 * STAGE_MAX + 1];
+	int n_ev_st = 0;
+	float ms_gate = 0, ms_dp = 0, ms_misc = 0, ms_rank = 0;
+	uint32_t last_recs = 0;
 	std::vector<float> es_min_ungapped; // per query length, NAN = not computed yet
 	std::vector<int> es_min_gapped;     // per query length, INT_MIN = not computed yet
 };
@@ -327,8 +382,8 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 {
 	if (!p || p->struct_size != sizeof(usb_params))
 		return fail(USB_EINVAL, "usb_params.struct_size mismatch (header/library version skew)");
-	if (!p->is_nucleo && !p->local)
-		return fail(USB_EINVAL, "amino-acid databases are supported for usearch_local only (local = 1)");
+	if (!p->is_nucleo && !p->local && (p->cluster_mode || p->hspw != 3))
+		return fail(USB_EINVAL, "amino acid usearch_global: cluster_mode is not supported and hspw must be 3 (got %u)", p->hspw);
 	if (p->is_nucleo) {
 		if (p->word_length < 2 || p->word_length > 8)
 			return fail(USB_EINVAL, "word_length %u unsupported (2..8)", p->word_length);
@@ -347,7 +402,7 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 			return fail(USB_EINVAL, "local gap penalties must be negative (lopen %g, lext %g)", (double)p->lopen, (double)p->lext);
 		if (!(p->evalue > 0.0f) || !(p->ka_dbsize > 0.0f) || !(p->xdrop_u >= 0.0f) || !(p->xdrop_g >= 0.0f))
 			return fail(USB_EINVAL, "local: evalue, ka_dbsize must be > 0 and xdrop_u, xdrop_g >= 0");
-	} else if (p->hspw < 3 || p->hspw > 6)
+	} else if (p->is_nucleo && (p->hspw < 3 || p->hspw > 6))
 		return fail(USB_EINVAL, "hspw %u unsupported (3..6)", p->hspw);
 	const float sc[] = {p->match, p->mismatch, p->gap_open, p->gap_ext, p->term_gap_open, p->term_gap_ext};
 	for (float v : sc)
@@ -362,15 +417,27 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 	D.topen2 = (int)std::lround(2.0 * p->term_gap_open);
 	D.text2 = (int)std::lround(2.0 * p->term_gap_ext);
 	D.xdrop2 = 2.0f * p->xdrop_nw;
-	D.min_hsp_fract_id = p->id > 0.75f ? p->id : 0.75f;
 	D.min_hsp_len = p->minhsp;
-	// MinGlobalHSPScore = FractId * Length * match, evaluated in float like the reference
-	float minscore = D.min_hsp_fract_id * (float)p->minhsp * p->match;
+	float minscore;
+	if (p->is_nucleo) {
+		// MinGlobalHSPScore = FractId * Length * match, evaluated in float like the reference
+		D.min_hsp_fract_id = p->id > 0.75f ? p->id : 0.75f;
+		minscore = D.min_hsp_fract_id * (float)p->minhsp * p->match;
+	} else {
+		// alnheuristics.cpp:40-58: amino acids gate at max(id, 0.5) and scale the score threshold by
+		// the smallest diagonal entry of the matrix over the 20 letters (BLOSUM62: 4)
+		float min_diag = 9e9f;
+		for (int i = 0; i < 24; ++i)
+			if (kBlosumOrder[i] != 'B' && kBlosumOrder[i] != 'Z' && kBlosumOrder[i] != 'X' && kBlosumOrder[i] != '*')
+				min_diag = std::min(min_diag, (float)kBlosum62[i][i]);
+		D.min_hsp_fract_id = p->id > 0.5f ? p->id : 0.5f;
+		minscore = D.min_hsp_fract_id * min_diag * (float)p->minhsp;
+	}
 	D.minscore2 = 2.0f * minscore;
 	D.band = p->band;
 	D.hspw = p->hspw;
-	D.hsp_words = p->local ? 0u : 1u << (2 * p->hspw);
-	D.hsp_hi = D.hsp_words / 4;
+	D.hsp_words = p->local ? 0u : p->is_nucleo ? 1u << (2 * p->hspw) : 8000u;
+	D.hsp_hi = D.hsp_words / (p->is_nucleo ? 4 : 20);
 	D.word_length = p->word_length;
 	D.alpha = p->is_nucleo ? 4 : 20;
 	D.slots = udb_slots(D.alpha, p->word_length);
@@ -457,6 +524,16 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	CK(cudaMemcpy(ix->d_seq_off.p + n0, S.seq_off.data() + n0, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
 	ix->n_dev = n0 + n;
+	if (ix->P.is_nucleo) {
+		const size_t w0 = (size_t)(b0 / 16) + 2 * (size_t)n0, w1 = (size_t)(b1 / 16) + 2 * ((size_t)n0 + n);
+		if ((rc = ix->d_db2.grow_keep(w1 + 4, w0)) || (rc = ix->d_dbn.grow_keep(w1 + 4, w0)) ||
+		    (rc = ix->d_wild.grow_keep((size_t)n0 + n + 1, n0)))
+			return rc;
+		k_pack_targets<<<std::min<uint32_t>((n + 7) / 8, 4096), 256>>>(ix->d_seqs.p, ix->d_seq_off.p, ix->d_seq_len.p, n0, n,
+		  ix->d_db2.p, ix->d_dbn.p, ix->d_wild.p);
+		CK(cudaGetLastError());
+		CK(cudaDeviceSynchronize());
+	}
 	// small appends (and everything after the first one) go to the growable tail segment; the
 	// initial targets of a search database always form a static segment (2-byte layout)
 	if (ix->dyn || (n < 8192 && (ix->P.cluster_mode || n0 > 0))) {
@@ -510,6 +587,9 @@ extern "C" void usb_index_free(usb_index *ix)
 	ix->d_seqs.release();
 	ix->d_seq_off.release();
 	ix->d_seq_len.release();
+	ix->d_db2.release();
+	ix->d_dbn.release();
+	ix->d_wild.release();
 	for (IndexSegment *g : ix->segs) {
 		g->release();
 		delete g;
@@ -629,6 +709,10 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 	CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	for (auto &e : s->ev)
 		CK(cudaEventCreate(&e));
+	for (auto &e : s->ev_st) {
+		e = nullptr;
+		CK(cudaEventCreate(&e));
+	}
 	if ((rc = s->d_ctr.reserve(1))) {
 		usb_searcher_free(s);
 		return rc;
@@ -652,6 +736,25 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 			return rc ? rc : fail(USB_ECUDA, "upload of the local tables failed: %s", cudaGetErrorString(e));
 		}
 	}
+	if (!p->is_nucleo && !p->local) {
+		LocalTables T;
+		build_local_tables(false, 0, 0, T);
+		AlignTables *H = new AlignTables;
+		for (int a = 0; a < USB_NCODE; ++a) {
+			for (int b = 0; b < USB_NCODE; ++b)
+				H->score[a * USB_NCODE + b] = T.score[a][b];
+			H->match[a] = T.match[a];
+			H->word_letter[a] = T.word_letter[a];
+		}
+		memcpy(H->code, T.code, 256);
+		rc = s->d_atab.reserve(1);
+		cudaError_t e = rc ? cudaSuccess : cudaMemcpy(s->d_atab.p, H, sizeof *H, cudaMemcpyHostToDevice);
+		delete H;
+		if (rc || e != cudaSuccess) {
+			usb_searcher_free(s);
+			return rc ? rc : fail(USB_ECUDA, "upload of the amino acid tables failed: %s", cudaGetErrorString(e));
+		}
+	}
 	*out = s;
 	return 0;
 }
@@ -666,12 +769,17 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
-	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release();
+	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release(); s->d_atab.release();
 	if (s->h_stage)
 		cudaFreeHost(s->h_stage);
 	for (auto &e : s->ev)
 		if (e)
 			cudaEventDestroy(e);
+	for (auto &e : s->ev_st)
+		if (e)
+			cudaEventDestroy(e);
+	s->d_job_state.release(); s->d_verdict.release(); s->d_items.release(); s->d_hsp_arena.release();
+	s->d_recs.release(); s->d_hits_stage.release(); s->d_sc.release(); s->d_gslab.release();
 	if (s->stream)
 		cudaStreamDestroy(s->stream);
 	delete s;
@@ -687,6 +795,19 @@ extern "C" int usb_batch_counters(const usb_searcher *s, uint64_t out[4])
 	out[1] = s->last_hits;
 	out[2] = s->last_runs;
 	out[3] = s->n_jobs;
+	return 0;
+}
+
+extern "C" int usb_batch_kernel_ms(const usb_searcher *s, double out[6])
+{
+	if (!s || !out || !s->ran)
+		return fail(USB_EINVAL, "usb_batch_kernel_ms: no completed batch");
+	out[0] = s->ms_rank;
+	out[1] = s->ms_gate;
+	out[2] = s->ms_dp;
+	out[3] = s->ms_misc;
+	out[4] = (double)s->last_recs;
+	out[5] = 0.0;
 	return 0;
 }
 
@@ -791,12 +912,12 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 		return rc;
 	a.u_arena = s->d_uarena.p;
 	const size_t smem = sizeof(RankBigShared);
-	if (!s->bigsmem_set) {
-		CK(cudaFuncSetAttribute(k_rank_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		s->bigsmem_set = true;
+	{
+		std::lock_guard<std::mutex> lk(g_attr_mu);
+		CK(func_smem_locked((const void *)k_rank_big, FN_RANK_BIG, smem));
+		k_rank_big<<<grid, RANK_THREADS, smem, s->stream>>>(a);
+		CK(cudaGetLastError());
 	}
-	k_rank_big<<<grid, RANK_THREADS, smem, s->stream>>>(a);
-	CK(cudaGetLastError());
 	++s->launches;
 	return 0;
 }
@@ -866,22 +987,19 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
 		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
 	a.prof = getenv("USB_RANK_PROF") ? 1 : 0; // measurement knob: phase cycles to stderr
-	if (smem > s->rank_smem_set || two != s->rank_two) {
-		const int carve = two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
-		const int bytes = (int)std::max(smem, s->rank_smem_set);
-		CK(cudaFuncSetAttribute(k_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		CK(cudaFuncSetAttribute(k_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	{
 		// two CTAs only fit with the whole L1/shared array carved out as shared memory
-		CK(cudaFuncSetAttribute(k_rank<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-		CK(cudaFuncSetAttribute(k_rank<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-		s->rank_smem_set = (size_t)bytes;
-		s->rank_two = two;
+		const int carve = two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+		std::lock_guard<std::mutex> lk(g_attr_mu);
+		if (a.ix.post16) {
+			CK(func_smem_locked((const void *)k_rank<true>, FN_RANK_T, smem, carve));
+			k_rank<true><<<n_jobs, threads, smem, s->stream>>>(a);
+		} else {
+			CK(func_smem_locked((const void *)k_rank<false>, FN_RANK_F, smem, carve));
+			k_rank<false><<<n_jobs, threads, smem, s->stream>>>(a);
+		}
+		CK(cudaGetLastError());
 	}
-	if (a.ix.post16)
-		k_rank<true><<<n_jobs, threads, smem, s->stream>>>(a);
-	else
-		k_rank<false><<<n_jobs, threads, smem, s->stream>>>(a);
-	CK(cudaGetLastError());
 	++s->launches;
 	return 0;
 }
@@ -902,7 +1020,8 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 	// The scratch gets whatever is left of a 1/16 share of shared memory, never less than the
 	// seed queues need; rectangles whose DP rows do not fit use the global slab.
 	const uint32_t fixed = align_fast_bytes(g.ql_cap, g.tl_cap, s->D.hsp_words);
-	const size_t budget = s->smem_optin > 1024 ? s->smem_optin - 1024 : 0;
+	const size_t tab_bytes = (!s->P.is_nucleo && !s->P.local) ? ALIGN_TAB_BYTES : 0;
+	const size_t budget = s->smem_optin > 1024 + tab_bytes ? s->smem_optin - 1024 - tab_bytes : 0;
 	const uint32_t min_scratch = std::max<uint32_t>(SEED_SCRATCH_BYTES, pad16(s->D.hsp_words));
 	uint32_t share = (uint32_t)((budget / ALIGN_MAX_WARPS) & ~(size_t)15);
 	g.scratch_bytes = share > fixed + min_scratch ? share - fixed : min_scratch;
@@ -913,7 +1032,7 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 	g.fast_in_smem = g.wpb != 0;
 	if (!g.fast_in_smem)
 		g.wpb = 8;
-	g.smem = g.fast_in_smem ? (size_t)g.wpb * g.fast_bytes : 0;
+	g.smem = (g.fast_in_smem ? (size_t)g.wpb * g.fast_bytes : 0) + tab_bytes;
 	g.slab_stride = align_slab_bytes(g.ql_cap, g.tl_cap, hsp_cap) + (g.fast_in_smem ? 0 : g.fast_bytes);
 	g.slab_stride = (g.slab_stride + 255) & ~(uint64_t)255;
 	g.grid = (uint32_t)s->num_sms;
@@ -937,24 +1056,24 @@ static int align_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uin
 
 static cudaError_t launch_align(const AlignArgs &a, const AlignGeom &g, cudaStream_t st)
 {
-	static thread_local size_t smem_set = 0;
-	static thread_local int dev_set = -1;
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (g.smem > smem_set || dev != dev_set) {
-		cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-		if (e != cudaSuccess)
+	std::lock_guard<std::mutex> lk(g_attr_mu);
+	cudaError_t e;
+	if (a.tab) {
+		if ((e = func_smem_locked((const void *)k_align<true>, FN_ALIGN_AA, g.smem)) != cudaSuccess)
 			return e;
-		smem_set = g.smem;
-		dev_set = dev;
+		k_align<true><<<g.grid, g.wpb * 32, g.smem, st>>>(a);
+	} else {
+		if ((e = func_smem_locked((const void *)k_align<false>, FN_ALIGN_NT, g.smem)) != cudaSuccess)
+			return e;
+		k_align<false><<<g.grid, g.wpb * 32, g.smem, st>>>(a);
 	}
-	k_align<<<g.grid, g.wpb * 32, g.smem, st>>>(a);
 	return cudaGetLastError();
 }
 
 static cudaError_t launch_viterbi(const ViterbiArgs &v, const AlignGeom &g, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+	std::lock_guard<std::mutex> lk(g_attr_mu);
+	cudaError_t e = func_smem_locked((const void *)k_viterbi, FN_VITERBI, g.smem);
 	if (e != cudaSuccess)
 		return e;
 	k_viterbi<<<g.grid, g.wpb * 32, g.smem, st>>>(v);
@@ -979,6 +1098,7 @@ static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_ca
 	a.fast_bytes = g.fast_bytes;
 	a.scratch_bytes = g.scratch_bytes;
 	a.fast_in_smem = g.fast_in_smem;
+	a.tab = (!s->P.is_nucleo && !s->P.local) ? s->d_atab.p : nullptr;
 	a.ctr = s->d_ctr.p;
 }
 
@@ -1067,20 +1187,197 @@ static void fill_local_args(usb_searcher *s, const LocalGeom &g, LocalArgs &a)
 
 static int launch_local(usb_searcher *s, const LocalArgs &a, const LocalGeom &g)
 {
-	if (g.smem > s->local_smem_set) {
-		CK(cudaFuncSetAttribute(k_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-		s->local_smem_set = g.smem;
+	{
+		std::lock_guard<std::mutex> lk(g_attr_mu);
+		CK(func_smem_locked((const void *)k_local, FN_LOCAL, g.smem));
+		k_local<<<g.grid, g.wpb * 32, g.smem, s->stream>>>(a);
+		CK(cudaGetLastError());
 	}
-	k_local<<<g.grid, g.wpb * 32, g.smem, s->stream>>>(a);
-	CK(cudaGetLastError());
 	++s->launches;
 	return 0;
+}
+
+// ------------------------------------------------------------------ staged candidate loop
+struct StageGeom {
+	bool ok;
+	// gate
+	uint32_t g_qw, g_tw, g_start_bytes, g_q1_bytes, g_bytes, g_wpb;
+	size_t g_smem;
+	uint64_t gslab_stride;
+	// dp
+	uint32_t ql_cap, tl_cap, d_fast_bytes, d_scratch_bytes, d_wpb;
+	size_t d_smem;
+	uint64_t dslab_stride;
+	uint32_t grid;
+};
+
+static uint32_t up4(uint32_t x) { return (x + 3u) & ~3u; }
+
+// The staged pipeline serves nucleotide global searches whose scores allow the packed X-drop walk
+// (match > 0 > mismatch) and whose per-warp arrays fit in shared memory; everything else (amino
+// acids, unusual scores, very long sequences) takes the one-kernel candidate loop k_align.
+static bool stage_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, uint32_t hsp_cap, StageGeom &g)
+{
+	memset(&g, 0, sizeof g);
+	if (!s->P.is_nucleo || s->P.local || !(s->D.match2 > 0 && s->D.mismatch2 < 0) || getenv("USB_ONE_KERNEL_ALIGN"))
+		return false;
+	if (max_ql > 65000 || s->smem_optin < 65536)
+		return false;
+	g.ql_cap = pad16(max_ql + 16);
+	g.tl_cap = pad16(max_tl + 16);
+	const size_t budget = s->smem_optin - 1024;
+	g.g_qw = up4(g.ql_cap / 16 + 2);
+	g.g_tw = up4(g.tl_cap / 16 + 2);
+	g.g_start_bytes = pad16(2 * (s->D.hsp_words + 2));
+	g.g_q1_bytes = std::max<uint32_t>(pad16(4 * GATE_Q1), pad16(s->D.hsp_words));
+	g.g_bytes = 8 * g.g_qw + 8 * g.g_tw + g.g_start_bytes + pad16(2 * g.ql_cap) + g.g_q1_bytes + pad16(2 * GATE_Q1) +
+	            4 * GATE_Q2 + pad16(2 * GATE_Q2);
+	g.g_wpb = (uint32_t)std::min<size_t>(GATE_MAX_WARPS, budget / g.g_bytes);
+	if (g.g_wpb < 4)
+		return false;
+	g.g_smem = (size_t)g.g_wpb * g.g_bytes;
+	g.gslab_stride = ((uint64_t)hsp_cap * (sizeof(HspRec) + 16) + 255) & ~(uint64_t)255;
+	// dp: letters + DP rows (as wide as fits; wider rectangles use rows in the global slab)
+	const uint32_t fixed = 2 * g.ql_cap + g.tl_cap;
+	const uint32_t want_rows = pad16(8u * (g.tl_cap + 8));
+	g.d_wpb = 0;
+	for (uint32_t wpb = DP_MAX_WARPS; wpb >= 1; --wpb) {
+		const size_t share = (budget / wpb) & ~(size_t)15;
+		if (share >= (size_t)fixed + 2048) {
+			g.d_wpb = wpb;
+			g.d_scratch_bytes = (uint32_t)std::min<size_t>(want_rows, share - fixed);
+			break;
+		}
+	}
+	if (!g.d_wpb)
+		return false;
+	g.d_fast_bytes = fixed + g.d_scratch_bytes;
+	g.d_smem = (size_t)g.d_wpb * g.d_fast_bytes;
+	g.dslab_stride = (align_slab_bytes(g.ql_cap, g.tl_cap, 0) + 255) & ~(uint64_t)255;
+	g.grid = (uint32_t)s->num_sms;
+	size_t free_b = 0, total_b = 0;
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+		return false;
+	const uint64_t limit = std::max<uint64_t>(total_b / 3, (uint64_t)256 << 20);
+	while ((uint64_t)g.grid * g.d_wpb * g.dslab_stride > limit && g.grid > 1)
+		g.grid = std::max(1u, g.grid / 2);
+	if ((uint64_t)g.grid * g.d_wpb * g.dslab_stride > limit)
+		return false;
+	g.ok = true;
+	return true;
+}
+
+struct StageCaps {
+	uint64_t recs, hsp_words, staged;
+};
+
+// Launches the stages of one batch on the searcher's stream (no host synchronisation inside).
+// a: AlignArgs with the batch fields (n_jobs, cand_t / pairs, hits, runs, qstat ...) filled in.
+static int run_staged(usb_searcher *s, const StageGeom &g, AlignArgs a, uint32_t hsp_cap, const StageCaps &caps)
+{
+	const usb_index *ix = s->ix;
+	const bool pairs = a.pair_q != nullptr;
+	const uint32_t n_jobs = a.n_jobs, k_max = pairs ? 1u : a.k_max;
+	int rc;
+	if ((rc = s->d_job_state.reserve(std::max(1u, n_jobs))) || (rc = s->d_verdict.reserve((size_t)std::max(1u, n_jobs) * k_max)) ||
+	    (rc = s->d_items.reserve(std::max(1u, n_jobs))) || (rc = s->d_recs.reserve(caps.recs)) ||
+	    (rc = s->d_hsp_arena.reserve(caps.hsp_words)) || (rc = s->d_hits_stage.reserve(caps.staged)) ||
+	    (rc = s->d_sc.reserve(1)) || (rc = s->d_gslab.reserve((size_t)g.grid * g.g_wpb * g.gslab_stride)) ||
+	    (rc = s->d_slab.reserve((size_t)g.grid * g.d_wpb * g.dslab_stride)))
+		return rc;
+	CK(cudaMemsetAsync(s->d_sc.p, 0, sizeof(StageCounters), s->stream));
+	StageArgs S;
+	memset(&S, 0, sizeof S);
+	S.A = a;
+	S.A.k_max = k_max;
+	S.A.ql_cap = g.ql_cap;
+	S.A.tl_cap = g.tl_cap;
+	S.A.hsp_cap = hsp_cap;
+	S.A.fast_in_smem = 1;
+	S.A.tab = nullptr;
+	S.db2 = ix->d_db2.p;
+	S.dbn = ix->d_dbn.p;
+	S.db_wild = ix->d_wild.p;
+	S.job_state = s->d_job_state.p;
+	S.verdict = s->d_verdict.p;
+	S.recs = s->d_recs.p;
+	S.recs_cap = (uint32_t)std::min<uint64_t>(caps.recs, 0x3ffffff0ull);
+	S.hsp_arena = s->d_hsp_arena.p;
+	S.hsp_arena_cap = (uint32_t)std::min<uint64_t>(caps.hsp_words, 0xfffffff0ull);
+	S.hits_stage = s->d_hits_stage.p;
+	S.stage_cap = (uint32_t)std::min<uint64_t>(caps.staged, 0xfffffff0ull);
+	S.sc = s->d_sc.p;
+	S.g_qw = g.g_qw;
+	S.g_tw = g.g_tw;
+	S.g_start_bytes = g.g_start_bytes;
+	S.g_q1_bytes = g.g_q1_bytes;
+	S.g_bytes = g.g_bytes;
+	s->n_ev_st = 0;
+	auto mark = [&]() { return cudaEventRecord(s->ev_st[s->n_ev_st++], s->stream); };
+	CK(mark());
+	uint32_t ka = 0, stage = 0;
+	while (ka < k_max && stage < STAGE_MAX) {
+		const uint32_t kb = stage == 0 ? 1u : (stage == STAGE_MAX - 1 ? k_max : std::min(k_max, ka + STAGE_WIDTH));
+		S.ka = ka;
+		S.kb = kb;
+		S.stage = stage;
+		S.items = stage == 0 ? nullptr : s->d_items.p;
+		const uint32_t tgrid = std::min<uint32_t>((n_jobs + 255) / 256, (uint32_t)s->num_sms * 8);
+		k_stage_prep<<<std::max(1u, tgrid), 256, 0, s->stream>>>(S);
+		CK(cudaGetLastError());
+		{
+			// gate: the HSP scratch lives in its own slab
+			StageArgs G = S;
+			G.A.slab = s->d_gslab.p;
+			G.A.slab_stride = g.gslab_stride;
+			std::lock_guard<std::mutex> lk(g_attr_mu);
+			CK(func_smem_locked((const void *)k_gate, FN_GATE, g.g_smem));
+			k_gate<<<g.grid, g.g_wpb * 32, g.g_smem, s->stream>>>(G);
+			CK(cudaGetLastError());
+		}
+		CK(mark());
+		{
+			StageArgs D = S;
+			D.A.slab = s->d_slab.p;
+			D.A.slab_stride = g.dslab_stride;
+			D.A.fast_bytes = g.d_fast_bytes;
+			D.A.scratch_bytes = g.d_scratch_bytes;
+			std::lock_guard<std::mutex> lk(g_attr_mu);
+			CK(func_smem_locked((const void *)k_dp, FN_DP, g.d_smem));
+			k_dp<<<g.grid, g.d_wpb * 32, g.d_smem, s->stream>>>(D);
+			CK(cudaGetLastError());
+		}
+		CK(mark());
+		k_commit<<<std::max(1u, tgrid), 256, 0, s->stream>>>(S);
+		CK(cudaGetLastError());
+		CK(mark());
+		s->launches += 4;
+		ka = kb;
+		++stage;
+	}
+	return 0;
+}
+
+// per-kernel times of the last staged batch (after the stream was synchronised)
+static void stage_times(usb_searcher *s)
+{
+	s->ms_gate = s->ms_dp = s->ms_misc = 0;
+	for (int i = 0; i + 3 < s->n_ev_st; i += 3) {
+		float a = 0, b = 0, c = 0;
+		cudaEventElapsedTime(&a, s->ev_st[i], s->ev_st[i + 1]);
+		cudaEventElapsedTime(&b, s->ev_st[i + 1], s->ev_st[i + 2]);
+		cudaEventElapsedTime(&c, s->ev_st[i + 2], s->ev_st[i + 3]);
+		s->ms_gate += a;
+		s->ms_dp += b;
+		s->ms_misc += c;
+	}
 }
 
 static const char *err_text(uint32_t e)
 {
 	static thread_local char buf[256];
-	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s%s%s", e, e & ERR_HITS_FULL ? " hit buffer full" : "",
+	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s%s%s%s%s", e, e & ERR_REC_FULL ? " gate record list full" : "",
+	  e & ERR_HSPARENA_FULL ? " HSP arena full" : "", e & ERR_HITS_FULL ? " hit buffer full" : "",
 	  e & ERR_RUNS_FULL ? " run arena full" : "", e & ERR_HSP_FULL ? " HSP list full" : "",
 	  e & ERR_TRACE ? " traceback left the band" : "", e & ERR_RECORDS_FULL ? " U-sort record list full" : "",
 	  e & ERR_NO_M ? " alignment path without M" : "", e & ERR_TB_FULL ? " X-drop trace arena full" : "",
@@ -1120,9 +1417,16 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 	const bool local = s->P.local != 0;
 	AlignGeom g;
 	LocalGeom lg;
-	int rc = local ? local_geometry(s, s->max_ql, ix->S.max_len, lg) : align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g);
+	StageGeom sg;
+	const bool staged = stage_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, sg);
+	int rc = local ? local_geometry(s, s->max_ql, ix->S.max_len, lg)
+	               : staged ? 0 : align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g);
 	if (rc)
 		return rc;
+	StageCaps caps;
+	caps.recs = s->D.fulldp ? (uint64_t)s->n_jobs * k_max + 1024 : (uint64_t)s->n_jobs * 2 + 4096;
+	caps.recs = std::max<uint64_t>(caps.recs, s->d_recs.cap);
+	caps.hsp_words = std::max<uint64_t>(caps.recs * 12, s->d_hsp_arena.cap);
 	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : k_max;
 	// a local target can contribute several ARs (localmulti.cpp): start with room for two per
 	// accepted target and grow on demand
@@ -1131,7 +1435,7 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		return fail(USB_ELIMIT, "hit buffer of %llu records too large; use smaller batches", (unsigned long long)hits_cap);
 	uint64_t runs_cap = std::max<uint64_t>(s->d_runs.cap, std::max<uint64_t>((uint64_t)1 << 20, hits_cap * 24));
 	if ((rc = s->d_qstat.reserve(std::max(1u, s->n_jobs))) ||
-	    (rc = s->d_slab.reserve(local ? (size_t)lg.n_warps * lg.slab_stride : (size_t)g.n_warps * g.slab_stride)))
+	    (!staged && (rc = s->d_slab.reserve(local ? (size_t)lg.n_warps * lg.slab_stride : (size_t)g.n_warps * g.slab_stride))))
 		return rc;
 	for (int attempt = 0;; ++attempt) {
 		if ((rc = s->d_runs.reserve(runs_cap)) || (rc = s->d_hits.reserve(hits_cap)))
@@ -1158,7 +1462,17 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 				return rc;
 		} else if (s->n_jobs) {
 			AlignArgs a;
-			fill_align_args(s, g, hsp_cap, a);
+			if (staged) {
+				memset(&a, 0, sizeof a);
+				a.P = s->D;
+				a.q = s->d_q.p;
+				a.q_off = s->d_qoff.p;
+				a.db_seq = ix->d_seqs.p;
+				a.db_off = ix->d_seq_off.p;
+				a.db_len = ix->d_seq_len.p;
+				a.ctr = s->d_ctr.p;
+			} else
+				fill_align_args(s, g, hsp_cap, a);
 			a.n_jobs = s->n_jobs;
 			a.strands = s->strands;
 			a.cand_t = s->d_cand_t.p;
@@ -1169,18 +1483,28 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			a.runs = s->d_runs.p;
 			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
 			a.qstat = s->d_qstat.p;
-			CK(launch_align(a, g, s->stream));
-			++s->launches;
+			if (staged) {
+				caps.staged = hits_cap + 1024;
+				if ((rc = run_staged(s, sg, a, hsp_cap, caps)))
+					return rc;
+			} else {
+				CK(launch_align(a, g, s->stream));
+				++s->launches;
+			}
 		}
 		CK(cudaEventRecord(s->ev[2], s->stream));
 		DevCounters c;
 		CK(cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
-		if (c.err && !(c.err & ~(ERR_RUNS_FULL | ERR_HITS_FULL)) && attempt < 4) {
+		if (c.err && !(c.err & ~(ERR_RUNS_FULL | ERR_HITS_FULL | ERR_REC_FULL | ERR_HSPARENA_FULL)) && attempt < 6) {
 			if (c.err & ERR_RUNS_FULL)
 				runs_cap = std::max<uint64_t>(runs_cap * 4, (uint64_t)c.n_runs + 1024);
 			if (c.err & ERR_HITS_FULL)
 				hits_cap = std::min<uint64_t>(0xfffffff0ull, std::max<uint64_t>(hits_cap * 2, (uint64_t)c.n_hits + 1024));
+			if (c.err & ERR_REC_FULL)
+				caps.recs *= 4;
+			if (c.err & (ERR_REC_FULL | ERR_HSPARENA_FULL))
+				caps.hsp_words = std::max<uint64_t>(caps.hsp_words * 4, caps.recs * 12);
 			continue;
 		}
 		if (c.err)
@@ -1198,6 +1522,15 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		}
 		break;
 	}
+	s->last_recs = 0;
+	if (staged && s->n_jobs && !local) {
+		stage_times(s);
+		StageCounters sc;
+		CK(cudaMemcpy(&sc, s->d_sc.p, sizeof sc, cudaMemcpyDeviceToHost));
+		s->last_recs = sc.n_recs;
+	} else
+		s->ms_gate = s->ms_dp = s->ms_misc = 0;
+	CK(cudaEventElapsedTime(&s->ms_rank, s->ev[0], s->ev[1]));
 	if (ms) {
 		CK(cudaEventElapsedTime(&ms[0], s->ev[0], s->ev[1]));
 		CK(cudaEventElapsedTime(&ms[1], s->ev[1], s->ev[2]));
@@ -1460,16 +1793,22 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 		return rc;
 	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->S.max_len / 8 + 16);
 	AlignGeom g;
-	if ((rc = align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g)))
+	StageGeom sg;
+	const bool staged = stage_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, sg);
+	if (!staged && (rc = align_geometry(s, s->max_ql, ix->S.max_len, hsp_cap, g)))
 		return rc;
 	DevBuf<uint32_t> d_pq, d_pt, d_hsp;
 	DevBuf<uint8_t> d_al;
 	const size_t hsp_words = hsp_out ? (size_t)n_pairs * (1 + 4 * max_hsp) : 0;
 	uint64_t runs_cap = std::max<uint64_t>((uint64_t)1 << 20, (uint64_t)n_pairs * 64);
+	StageCaps caps;
+	caps.recs = (uint64_t)n_pairs + 64;
+	caps.hsp_words = caps.recs * 12;
+	caps.staged = caps.recs;
 	auto cleanup = [&]() { d_pq.release(); d_pt.release(); d_hsp.release(); d_al.release(); };
 	if ((rc = d_pq.reserve(n_pairs + 1)) || (rc = d_pt.reserve(n_pairs + 1)) || (rc = d_al.reserve(n_pairs + 1)) ||
 	    (rc = d_hsp.reserve(hsp_words + 1)) || (rc = s->d_hits.reserve(n_pairs + 1)) ||
-	    (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride))) {
+	    (!staged && (rc = s->d_slab.reserve((size_t)g.n_warps * g.slab_stride)))) {
 		cleanup();
 		return rc;
 	}
@@ -1485,9 +1824,20 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 		cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream);
 		cudaMemsetAsync(d_al.p, 0, n_pairs, s->stream);
 		AlignArgs a;
-		fill_align_args(s, g, hsp_cap, a);
+		if (staged) {
+			memset(&a, 0, sizeof a);
+			a.P = s->D;
+			a.q = s->d_q.p;
+			a.q_off = s->d_qoff.p;
+			a.db_seq = ix->d_seqs.p;
+			a.db_off = ix->d_seq_off.p;
+			a.db_len = ix->d_seq_len.p;
+			a.ctr = s->d_ctr.p;
+		} else
+			fill_align_args(s, g, hsp_cap, a);
 		a.n_jobs = n_pairs;
 		a.strands = 1;
+		a.k_max = 1;
 		a.pair_q = d_pq.p;
 		a.pair_t = d_pt.p;
 		a.hits = s->d_hits.p;
@@ -1497,8 +1847,16 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 		a.aligned = d_al.p;
 		a.hsp_out = hsp_out ? d_hsp.p : nullptr;
 		a.max_hsp = max_hsp;
-		cudaError_t e = launch_align(a, g, s->stream);
-		++s->launches;
+		cudaError_t e = cudaSuccess;
+		if (staged) {
+			if ((rc = run_staged(s, sg, a, hsp_cap, caps))) {
+				cleanup();
+				return rc;
+			}
+		} else {
+			e = launch_align(a, g, s->stream);
+			++s->launches;
+		}
 		if (e == cudaSuccess)
 			e = cudaMemcpyAsync(&c, s->d_ctr.p, sizeof c, cudaMemcpyDeviceToHost, s->stream);
 		if (e == cudaSuccess)
@@ -1507,8 +1865,11 @@ extern "C" int usb_align_pairs(usb_searcher *s, const uint8_t *qseqs, const uint
 			cleanup();
 			return fail(USB_ECUDA, "align kernel failed: %s", cudaGetErrorString(e));
 		}
-		if (c.err == ERR_RUNS_FULL && attempt < 4) {
-			runs_cap *= 4;
+		if (c.err && !(c.err & ~(ERR_RUNS_FULL | ERR_HSPARENA_FULL)) && attempt < 5) {
+			if (c.err & ERR_RUNS_FULL)
+				runs_cap *= 4;
+			if (c.err & ERR_HSPARENA_FULL)
+				caps.hsp_words *= 4;
 			continue;
 		}
 		break;

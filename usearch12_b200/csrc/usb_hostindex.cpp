@@ -54,20 +54,25 @@ void fastmask_nt(const uint8_t *in, uint32_t L, uint8_t *out)
 		memcpy(out, m.data(), L);
 }
 
-const uint8_t *udb_letters(uint32_t alpha)
-{
-	static uint8_t nt[256], aa[256];
-	static bool done = false;
-	if (!done) {
+namespace {
+struct UdbLetterTables {
+	uint8_t nt[256], aa[256];
+	UdbLetterTables()
+	{
 		memset(nt, 0xff, sizeof nt);
 		memset(aa, 0xff, sizeof aa);
 		nt['A'] = 0; nt['C'] = 1; nt['G'] = 2; nt['T'] = 3; nt['U'] = 3;
 		const char *a = "ACDEFGHIKLMNPQRSTVWY"; // alpha.cpp g_CharToLetterAmino
 		for (int i = 0; i < 20; ++i)
 			aa[(int)a[i]] = (uint8_t)i;
-		done = true;
 	}
-	return alpha == 4 ? nt : aa;
+};
+}
+
+const uint8_t *udb_letters(uint32_t alpha)
+{
+	static const UdbLetterTables T; // function-local static: initialised once, thread-safe
+	return alpha == 4 ? T.nt : T.aa;
 }
 
 uint32_t udb_slots(uint32_t alpha, uint32_t word_length)

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <memory>
+#include <new>
 #include <vector>
 
 #include "../../include/usb200.h"
@@ -158,16 +160,27 @@ extern "C" int usb_udb_probe(const char *path)
 	return fread(&m, 4, 1, in.f) == 1 && m == UDB_MAGIC1;
 }
 
-extern "C" int usb_udb_read(const char *path, usb_udb **out)
+// The sizes in a .udb header are untrusted: every allocation is checked against the bytes left in
+// the file first, and allocation failures are reported as USB_ENOMEM (no exception crosses the ABI).
+static int udb_read_checked(const char *path, usb_udb **out)
 {
-	if (!path || !out)
-		return fail(USB_EINVAL, "usb_udb_read: null argument");
 	File in;
 	in.f = fopen(path, "rb");
 	if (!in.f)
 		return fail(USB_EINVAL, "Cannot open %s", path);
+	uint64_t file_bytes = 0;
+	if (fseek(in.f, 0, SEEK_END) == 0) {
+		const long e = ftell(in.f);
+		file_bytes = e > 0 ? (uint64_t)e : 0;
+	}
+	rewind(in.f);
 	bool ok = true;
-	auto get = [&](void *d, size_t n) { ok = ok && (n == 0 || fread(d, 1, n, in.f) == n); };
+	uint64_t consumed = 0;
+	auto get = [&](void *d, size_t n) {
+		ok = ok && (n == 0 || fread(d, 1, n, in.f) == n);
+		consumed += n;
+	};
+	auto left = [&]() { return file_bytes > consumed ? file_bytes - consumed : 0; };
 	UdbHdr h;
 	get(&h, sizeof h);
 	if (!ok || h.magic1 != UDB_MAGIC1 || h.magic2 != UDB_MAGIC2)
@@ -182,7 +195,9 @@ extern "C" int usb_udb_read(const char *path, usb_udb **out)
 	const uint32_t slots = udb_slots(nucleo ? 4 : 20, h.word_width);
 	if (slots == 0 || (nucleo ? h.word_width > 8 : h.word_width > 5) || h.seq_count > 0xfffffff0ull)
 		return fail(USB_EINVAL, "%s: word width %u / %llu sequences unsupported", path, h.word_width, (unsigned long long)h.seq_count);
-	usb_udb *u = new usb_udb;
+	if ((uint64_t)slots * 4 > left())
+		return fail(USB_EINVAL, "%s: truncated or inconsistent .udb file", path);
+	std::unique_ptr<usb_udb> u(new usb_udb);
 	u->nucleo = nucleo;
 	u->word_length = h.word_width;
 	u->slots = slots;
@@ -190,27 +205,27 @@ extern "C" int usb_udb_read(const char *path, usb_udb **out)
 	get(u->sizes.data(), (size_t)slots * 4);
 	uint32_t m = 0;
 	get(&m, 4);
-	if (!ok || m != UDB_MAGIC3) {
-		delete u;
+	if (!ok || m != UDB_MAGIC3)
 		return fail(USB_EINVAL, "%s: .udb magic3 %08x should be %08x", path, m, UDB_MAGIC3);
-	}
 	u->row_off.assign((size_t)slots + 1, 0);
 	for (uint32_t w = 0; w < slots; ++w)
 		u->row_off[w + 1] = u->row_off[w] + u->sizes[w];
+	if (u->row_off[slots] > left() / 4)
+		return fail(USB_EINVAL, "%s: truncated or inconsistent .udb file (rows of %llu entries)", path,
+		  (unsigned long long)u->row_off[slots]);
 	u->rows.resize(u->row_off[slots]);
 	get(u->rows.data(), u->rows.size() * 4);
 	get(&m, 4);
-	if (!ok || m != UDB_MAGIC4) {
-		delete u;
+	if (!ok || m != UDB_MAGIC4)
 		return fail(USB_EINVAL, "%s: .udb magic4 0x%08x should be 0x%08x", path, m, UDB_MAGIC4);
-	}
 	SeqDbHdr sh;
 	get(&sh, sizeof sh);
-	if (!ok || sh.magic1 != SEQDB_MAGIC1 || sh.magic2 != SEQDB_MAGIC2 || sh.seq_count != h.seq_count) {
-		delete u;
+	if (!ok || sh.magic1 != SEQDB_MAGIC1 || sh.magic2 != SEQDB_MAGIC2 || sh.seq_count != h.seq_count)
 		return fail(USB_EINVAL, "%s: SeqDB::FromFile, invalid header magics %08x %08x", path, sh.magic1, sh.magic2);
-	}
 	const uint32_t n = sh.seq_count;
+	if ((uint64_t)n * 8 > left() || (uint64_t)sh.label_bytes > left() - (uint64_t)n * 8 ||
+	    (uint64_t)sh.seq_bytes > left() - (uint64_t)n * 8 - sh.label_bytes)
+		return fail(USB_EINVAL, "%s: truncated or inconsistent .udb file", path);
 	u->label_off.resize(n);
 	get(u->label_off.data(), (size_t)n * 4);
 	u->labels.resize((size_t)sh.label_bytes + 1, 0);
@@ -228,12 +243,21 @@ extern "C" int usb_udb_read(const char *path, usb_udb **out)
 	}
 	for (uint32_t i = 0; ok && i < n; ++i)
 		ok = u->label_off[i] < sh.label_bytes;
-	if (!ok) {
-		delete u;
+	if (!ok)
 		return fail(USB_EINVAL, "%s: truncated or inconsistent .udb file", path);
-	}
-	*out = u;
+	*out = u.release();
 	return 0;
+}
+
+extern "C" int usb_udb_read(const char *path, usb_udb **out)
+{
+	if (!path || !out)
+		return fail(USB_EINVAL, "usb_udb_read: null argument");
+	try {
+		return udb_read_checked(path, out);
+	} catch (const std::bad_alloc &) {
+		return fail(USB_ENOMEM, "%s: out of memory while reading the .udb file", path);
+	}
 }
 
 extern "C" void usb_udb_free(usb_udb *u) { delete u; }
