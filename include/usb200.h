@@ -63,7 +63,49 @@ typedef struct usb_params {
 	float lext;             /* local gap extend, -1 */
 	float ka_dbsize;        /* -ka_dbsize, 1e9 (o_defaults.inc:2; the default counts as set, so the
 	                           letter count of the DB is never used, makedbsearcher.cpp:92-96) */
+	/* Accepter / Terminator options beyond -id (accepter.cpp:41-94,145-197, terminator.cpp:66-86).
+	 * accept_flags = the options that are set (the reference tests ofilled()/oget_flag()); the
+	 * values are compared the way the reference compares them (double vs widened float). */
+	uint32_t accept_flags;  /* USB_ACC_* */
+	float maxid;            /* -maxid (default 1.0 counts as set, o_defaults.inc:7) */
+	uint32_t mincols;       /* -mincols: alignment columns between the first and last M */
+	uint32_t maxgaps;       /* -maxgaps: internal gap columns */
+	uint32_t maxdiffs;      /* -maxdiffs: mismatches + internal gap columns */
+	uint32_t mindiffs;      /* -mindiffs */
+	float query_cov, max_query_cov;   /* (lastMq - firstMq + 1) / QL   (arscorer.cpp:122-137) */
+	float target_cov, max_target_cov; /* (ids + mismatches) / TL        (arscorer.cpp:139-154) */
+	float abskew;           /* -abskew: target size= / query size= (arscorer.cpp:809-816) */
+	float min_sizeratio;    /* -min_sizeratio: same ratio, tested before the alignment */
+	float minqt, maxqt;     /* QL / TL bounds */
+	float minsl, maxsl;     /* shorter / longer bounds */
+	float termid;           /* -termid: stop when the lowest accepted identity <= termid */
+	float termidd;          /* -termidd: stop when highest - lowest accepted identity > termidd */
 } usb_params;
+
+#define USB_ACC_SELF 0x1u           /* -self: reject pairs with identical labels */
+#define USB_ACC_NOTSELF 0x2u        /* -notself: reject pairs with different labels */
+#define USB_ACC_SELFID 0x4u         /* -selfid: reject pairs with identical letters (global only) */
+#define USB_ACC_MAXID 0x8u
+#define USB_ACC_MINCOLS 0x10u
+#define USB_ACC_MAXGAPS 0x20u
+#define USB_ACC_QUERY_COV 0x40u
+#define USB_ACC_MAX_QUERY_COV 0x80u
+#define USB_ACC_TARGET_COV 0x100u
+#define USB_ACC_MAX_TARGET_COV 0x200u
+#define USB_ACC_MAXDIFFS 0x400u
+#define USB_ACC_MINDIFFS 0x800u
+#define USB_ACC_ABSKEW 0x1000u
+#define USB_ACC_MIN_SIZERATIO 0x2000u
+#define USB_ACC_MINQT 0x4000u
+#define USB_ACC_MAXQT 0x8000u
+#define USB_ACC_MINSL 0x10000u
+#define USB_ACC_MAXSL 0x20000u
+#define USB_ACC_TERMID 0x40000u
+#define USB_ACC_TERMIDD 0x80000u
+/* options that need the label identities / size= annotations of usb_index_set_attrs and
+ * usb_batch_set_query_attrs */
+#define USB_ACC_NEEDS_LABELS (USB_ACC_SELF | USB_ACC_NOTSELF)
+#define USB_ACC_NEEDS_SIZES (USB_ACC_ABSKEW | USB_ACC_MIN_SIZERATIO)
 
 /* Defaults of -usearch_global (cluster_fast=0) or -cluster_fast (=1). */
 void usb_default_params(usb_params *p, int cluster_fast);
@@ -190,9 +232,19 @@ int usb_batch_counters(const usb_searcher *s, uint64_t out[4]);
  * out[1] HSP gate kernels (GlobalAlign_AllOpts up to the identity gate, globalalignmem.cpp:129-176),
  * out[2] DP kernels (AlignHSPMem / ViterbiFastBandMem + FillLo, globalalignmem.cpp:70-112),
  * out[3] work-list and commit kernels (Terminator, terminator.cpp:64-100), out[4] the number of
- * records the gate passed on to the DP, out[5] DP cells.  Entries 1..3 are 0 when the candidate
- * loop ran as one kernel (amino acids, unusual scores). */
-int usb_batch_kernel_ms(const usb_searcher *s, double out[6]);
+ * (query, target) records the gate passed on to the DP, out[5] DP cells, out[6] letters (query +
+ * target) of those records, out[7] words of chained-HSP coordinates written by the gate.
+ * Entries 1..7 are 0 when the candidate loop ran as one kernel (amino acids, unusual scores). */
+int usb_batch_kernel_ms(const usb_searcher *s, double out[8]);
+/* Label identities and size= annotations for the Accepter rules that read labels (-self, -notself:
+ * accepter.cpp:150-154; -min_sizeratio, -abskew: GetSizeFromLabel, label.cpp:152-161).  label_id:
+ * two sequences have the same label iff their ids are equal (the caller numbers the distinct
+ * labels); size: the size= value.  Either array may be NULL when no set option needs it.
+ * Targets [first, first + n) of the index; queries of the uploaded batch (call between
+ * usb_batch_upload and usb_batch_run, or before usb_search_batch with queries_ahead = 1: the
+ * attributes then apply to the next batch). */
+int usb_index_set_attrs(usb_index *ix, uint32_t first, uint32_t n, const uint32_t *label_id, const uint32_t *size);
+int usb_batch_set_query_attrs(usb_searcher *s, uint32_t n_q, const uint32_t *label_id, const uint32_t *size);
 /* Number of kernel launches issued by this searcher so far. */
 uint64_t usb_searcher_launch_count(const usb_searcher *s);
 /* Device-resident packed hit records of the last usb_batch_run (for the NCCL gather of

@@ -128,7 +128,7 @@ def test_cli_refuses_unsupported_options(tmp_path):
     import subprocess
     from usearch12_b200 import build
     cli = build.build_cli()
-    r = subprocess.run([cli, "-usearch_global", "x.fa", "-db", "y.fa", "-id", "0.9", "-strand", "plus", "-maxhits", "3"],
+    r = subprocess.run([cli, "-usearch_global", "x.fa", "-db", "y.fa", "-id", "0.9", "-strand", "plus", "-uparse_break", "3"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "not supported" in r.stdout
 

@@ -10,7 +10,7 @@ else
   timeout 1000 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$T.txt 2>&1; echo "pytest rc=$?"
 fi
 tail -5 gpurun_out/pytest_$T.txt
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; echo "bench rc=$?"
+timeout 600 python bench.py --no-cpu-baseline --no-legs > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; echo "bench rc=$?"
 python - <<PY
 import json
 d = json.loads(open("gpurun_out/bench_$T.json").read().strip().splitlines()[-1])

@@ -29,7 +29,18 @@ class Params(C.Structure):
         ("cluster_mode", C.c_int32), ("fulldp", C.c_int32), ("local", C.c_int32), ("evalue", C.c_float),
         ("xdrop_u", C.c_float), ("xdrop_g", C.c_float), ("lopen", C.c_float), ("lext", C.c_float),
         ("ka_dbsize", C.c_float),
+        ("accept_flags", C.c_uint32), ("maxid", C.c_float), ("mincols", C.c_uint32), ("maxgaps", C.c_uint32),
+        ("maxdiffs", C.c_uint32), ("mindiffs", C.c_uint32), ("query_cov", C.c_float), ("max_query_cov", C.c_float),
+        ("target_cov", C.c_float), ("max_target_cov", C.c_float), ("abskew", C.c_float), ("min_sizeratio", C.c_float),
+        ("minqt", C.c_float), ("maxqt", C.c_float), ("minsl", C.c_float), ("maxsl", C.c_float),
+        ("termid", C.c_float), ("termidd", C.c_float),
     ]
+
+
+# usb_params.accept_flags (include/usb200.h USB_ACC_*)
+ACC = dict(self=0x1, notself=0x2, selfid=0x4, maxid=0x8, mincols=0x10, maxgaps=0x20, query_cov=0x40, max_query_cov=0x80,
+           target_cov=0x100, max_target_cov=0x200, maxdiffs=0x400, mindiffs=0x800, abskew=0x1000, min_sizeratio=0x2000,
+           minqt=0x4000, maxqt=0x8000, minsl=0x10000, maxsl=0x20000, termid=0x40000, termidd=0x80000)
 
 
 HIT_DTYPE = np.dtype([
@@ -49,7 +60,8 @@ SYMBOLS = [
     "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
     "usb_index_seq_count", "usb_index_posting_count", "usb_index_posting_width", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
-    "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_batch_kernel_ms", "usb_searcher_launch_count", "usb_batch_export_hits_device",
+    "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_batch_kernel_ms", "usb_index_set_attrs", "usb_batch_set_query_attrs",
+    "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
     "usb_viterbi_batch", "usb_set_local", "usb_set_amino", "usb_local_evalue", "usb_local_pairs",
@@ -131,6 +143,8 @@ def lib():
     L.usb_viterbi_batch.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
     L.usb_set_local.argtypes = [C.POINTER(Params), C.c_int, C.c_float]
     L.usb_set_local.restype = None
+    L.usb_index_set_attrs.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
+    L.usb_batch_set_query_attrs.argtypes = [vp, C.c_uint32, vp, vp]
     L.usb_set_amino.argtypes = [C.POINTER(Params)]
     L.usb_set_amino.restype = None
     L.usb_local_evalue.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -145,12 +159,20 @@ def check(rc):
 
 
 def default_params(cluster_fast=False, **kw):
+    """usb_default_params + overrides.  Accepter / Terminator options (maxid, mincols, query_cov, termid ...)
+    also set their accept_flags bit; self / notself / selfid are flags only (pass True)."""
     p = Params()
     lib().usb_default_params(C.byref(p), int(cluster_fast))
     for k, v in kw.items():
+        if k in ("self", "notself", "selfid"):
+            if v:
+                p.accept_flags |= ACC[k]
+            continue
         if not hasattr(p, k):
             raise AttributeError("unknown usb_params field %r" % k)
         setattr(p, k, v)
+        if k in ACC:
+            p.accept_flags |= ACC[k]
     return p
 
 
@@ -362,9 +384,10 @@ class Searcher:
         return dict(postings=out[0], hits=out[1], runs=out[2], jobs=out[3])
 
     def kernel_ms(self):
-        out = (C.c_double * 6)()
+        out = (C.c_double * 8)()
         check(lib().usb_batch_kernel_ms(self.handle, out))
-        return dict(rank=out[0], gate=out[1], dp=out[2], misc=out[3], dp_records=int(out[4]), dp_cells=int(out[5]))
+        return dict(rank=out[0], gate=out[1], dp=out[2], misc=out[3], dp_records=int(out[4]), dp_cells=int(out[5]),
+                    dp_seq_bytes=int(out[6]), hsp_words=int(out[7]))
 
     @property
     def launch_count(self):

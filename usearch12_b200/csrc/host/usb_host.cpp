@@ -8,7 +8,10 @@
 #include <cstring>
 #include <mutex>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 namespace usbhost {
 
@@ -218,8 +221,7 @@ OutputSink::OutputSink(const OutputOpts &O)
 	m_fUC = open(O.uc);
 	m_fB6 = open(O.blast6out);
 	m_fUser = open(O.userout);
-	if (O.output_no_hits)
-		Die("-output_no_hits is not supported by this build");
+	m_OutputNoHits = O.output_no_hits;
 	if (m_fUser) {
 		// userout.cpp:20-60: fields separated by '+'; default query+target+id
 		std::string spec = O.userfields.empty() ? "query+target+id" : O.userfields;
@@ -303,6 +305,10 @@ void OutputSink::OutputBlast6(const HitMgr &HM, std::string &m_bB6) const
 {
 	if (!m_fB6)
 		return;
+	if (HM.m_Hits.empty() && m_OutputNoHits) { // blast6out.cpp:82-103
+		m_bB6 += HM.m_Query.m_Label;
+		m_bB6 += "\t*\t0\t0\t0\t0\t0\t0\t0\t0\t*\t0\n";
+	}
 	for (const AlignResult &AR : HM.m_Hits) {
 		m_bB6 += AR.GetQueryLabel();
 		m_bB6 += '\t';
@@ -322,6 +328,26 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 	if (!m_fUser)
 		return;
 	std::string tmp;
+	if (HM.m_Hits.empty() && m_OutputNoHits) { // userout.cpp:53-124
+		for (size_t i = 0; i < m_UserFields.size(); ++i) {
+			if (i)
+				m_bUser += '\t';
+			switch (m_UserFields[i]) {
+			case UF_query: m_bUser += HM.m_Query.m_Label; break;
+			case UF_ql: appendf(m_bUser, "%u", HM.m_Query.m_L); break;
+			case UF_clusternr: appendf(m_bUser, "%u", 0xffffffffu); break; // hitmgr.cpp:84 m_QueryClusterIndex = UINT_MAX
+			case UF_target: case UF_evalue: case UF_id: case UF_fractid: case UF_pairs: case UF_gaps: case UF_qlo: case UF_qhi:
+			case UF_qlor: case UF_qhir: case UF_tlo: case UF_thi: case UF_tlor: case UF_thir: case UF_tl: case UF_alnlen:
+			case UF_opens: case UF_exts: case UF_raw: case UF_bits: case UF_aln: case UF_caln: case UF_qstrand:
+			case UF_tstrand: case UF_mism: case UF_ids: case UF_diffs:
+				m_bUser += '*';
+				break;
+			default:
+				Die("Invalid user field index %u (-output_no_hits)", (unsigned)m_UserFields[i]);
+			}
+		}
+		m_bUser += '\n';
+	}
 	for (const AlignResult &AR : HM.m_Hits) {
 		for (size_t i = 0; i < m_UserFields.size(); ++i) {
 			if (i)
@@ -596,41 +622,100 @@ GpuSearcher::~GpuSearcher()
 
 uint64_t GpuSearcher::GetLaunchCount() const { return usb_searcher_launch_count(m_Searcher); }
 
+void GpuSearcher::SetTargetAttrs(const uint32_t *LabelIds, const uint32_t *Sizes)
+{
+	CheckUsb(usb_index_set_attrs(m_Index, 0, m_DB.GetSeqCount(), LabelIds, Sizes), "usb_index_set_attrs");
+}
+
 // Replaces the loop "SS->GetNext(Query); searcher->Search(Query)" of Thread() (search.cpp:63-86)
 // for a batch: one C-ABI call, then one HitMgr per query holding AlignResults in output order.
-void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out)
+std::shared_ptr<void> GpuSearcher::SearchRaw(const SeqDB &Queries, uint32_t First, uint32_t Count)
 {
 	usb_result *R = nullptr;
+	if (m_QLabelIds || m_QSizes)
+		CheckUsb(usb_batch_set_query_attrs(m_Searcher, Count, m_QLabelIds ? m_QLabelIds + First : nullptr,
+		           m_QSizes ? m_QSizes + First : nullptr), "usb_batch_set_query_attrs");
 	CheckUsb(usb_search_batch(m_Searcher, Queries.Letters(), Queries.Offsets() + First, Count, &R), "usb_search_batch");
+	return std::shared_ptr<void>(R, [](void *p) { usb_result_free((usb_result *)p); });
+}
+
+void GpuSearcher::BuildHitMgrs(const std::shared_ptr<void> &Result, const SeqDB &Queries, uint32_t First, uint32_t Count,
+  std::vector<HitMgr> &Out, unsigned Threads) const
+{
+	const usb_result *R = (const usb_result *)Result.get();
 	const usb_hit *hits = usb_result_hits(R);
 	const uint64_t *qoff = usb_result_query_offsets(R);
 	uint64_t n_runs = 0;
 	const uint32_t *runs = usb_result_runs(R, &n_runs);
-	// the run arena must outlive the result handle: a copy shared by the batch's HitMgrs
-	auto arena = std::make_shared<std::vector<uint32_t>>(runs, runs + n_runs);
 	Out.resize(Count);
-	for (uint32_t q = 0; q < Count; ++q) {
-		HitMgr &HM = Out[q];
-		if (q == 0 || qoff[q] != qoff[q + 1])
-			HM.m_Arena = arena;
-		Queries.GetSI(First + q, HM.m_Query);
-		HM.m_Hits.clear();
-		for (uint64_t k = qoff[q]; k < qoff[q + 1]; ++k) {
-			AlignResult AR;
-			AR.m_Hit = hits[k];
-			AR.m_Query = HM.m_Query;
-			AR.m_Query.m_RevComp = hits[k].strand != 0;
-			m_DB.GetSI(hits[k].target, AR.m_Target);
-			AR.m_Runs = arena->data() + hits[k].run_off;
-			AR.m_Nucleo = m_P.is_nucleo != 0;
-			AR.m_Local = m_P.local != 0;
-			if (AR.m_Local)
-				CheckUsb(usb_local_evalue(m_Searcher, hits[k].raw, hits[k].ql, &AR.m_Evalue, &AR.m_BitScore),
-				  "usb_local_evalue");
-			HM.m_Hits.push_back(AR);
+	auto build = [&](uint32_t q0, uint32_t q1) {
+		for (uint32_t q = q0; q < q1; ++q) {
+			HitMgr &HM = Out[q];
+			// the paths point into the result's run arena: the first HitMgr of the batch and every
+			// HitMgr with hits keep the result alive
+			if (q == 0 || qoff[q] != qoff[q + 1])
+				HM.m_Arena = Result;
+			Queries.GetSI(First + q, HM.m_Query);
+			HM.m_Hits.clear();
+			for (uint64_t k = qoff[q]; k < qoff[q + 1]; ++k) {
+				AlignResult AR;
+				AR.m_Hit = hits[k];
+				AR.m_Query = HM.m_Query;
+				AR.m_Query.m_RevComp = hits[k].strand != 0;
+				m_DB.GetSI(hits[k].target, AR.m_Target);
+				AR.m_Runs = runs + hits[k].run_off;
+				AR.m_Nucleo = m_P.is_nucleo != 0;
+				AR.m_Local = m_P.local != 0;
+				if (AR.m_Local)
+					CheckUsb(usb_local_evalue(m_Searcher, hits[k].raw, hits[k].ql, &AR.m_Evalue, &AR.m_BitScore),
+					  "usb_local_evalue");
+				HM.m_Hits.push_back(AR);
+			}
+			if (m_Sel.Any() && !HM.m_Hits.empty()) {
+				// HitMgr::GetHitCount / GetHit (hitmgr.cpp:367-398,466-475); m_Hits is in HitMgr::Sort order
+				std::vector<AlignResult> &H = HM.m_Hits;
+				auto score = [&](const AlignResult &AR) { return AR.IsLocal() ? (float)AR.GetRawScore() : (float)AR.GetFractId(); };
+				size_t n = H.size();
+				if (m_Sel.maxhits && n > m_Sel.maxhits)
+					n = m_Sel.maxhits;
+				if (m_Sel.top_hit_only) {
+					size_t top = 0; // GetTopHit over every hit (hitmgr.cpp:400-420)
+					for (size_t i = 1; i < H.size(); ++i)
+						if (score(H[i]) > score(H[top]) ||
+						    (score(H[i]) == score(H[top]) && H[i].GetTargetIndex() < H[top].GetTargetIndex()))
+							top = i;
+					const AlignResult keep = H[top];
+					H.assign(1, keep);
+				} else {
+					if (m_Sel.top_hits_only) {
+						float best = score(H[0]);
+						for (const AlignResult &AR : H)
+							best = std::max(best, score(AR));
+						size_t i = 1;
+						while (i < n && !(score(H[i]) < best))
+							++i;
+						n = i;
+					}
+					H.resize(n);
+				}
+			}
 		}
+	};
+	const unsigned T = std::max(1u, std::min(Threads, Count / 4096));
+	if (T <= 1) {
+		build(0, Count);
+		return;
 	}
-	usb_result_free(R);
+	std::vector<std::thread> th;
+	for (unsigned k = 0; k < T; ++k)
+		th.emplace_back(build, (uint32_t)((uint64_t)Count * k / T), (uint32_t)((uint64_t)Count * (k + 1) / T));
+	for (auto &t : th)
+		t.join();
+}
+
+void GpuSearcher::SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out)
+{
+	BuildHitMgrs(SearchRaw(Queries, First, Count), Queries, First, Count, Out, 1);
 }
 
 bool GuessIsNucleo(const std::string &FastaFileName)
@@ -701,6 +786,43 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 			t.join();
 	}
 	parse_q.join();
+	// Accepter rules that read labels: identities of equal labels, size= annotations
+	std::vector<uint32_t> q_label, t_label, q_size, t_size;
+	if (P.accept_flags & USB_ACC_NEEDS_LABELS) {
+		std::unordered_map<std::string, uint32_t> ids;
+		t_label.resize(DB.GetSeqCount());
+		for (uint32_t i = 0; i < DB.GetSeqCount(); ++i)
+			t_label[i] = ids.emplace(DB.GetLabel(i), i).first->second;
+		q_label.resize(Q.GetSeqCount());
+		for (uint32_t i = 0; i < Q.GetSeqCount(); ++i) {
+			auto it = ids.find(Q.GetLabel(i));
+			q_label[i] = it == ids.end() ? DB.GetSeqCount() + i : it->second;
+		}
+	}
+	if (P.accept_flags & USB_ACC_NEEDS_SIZES) {
+		auto size_of = [](const char *Label) { // label.cpp:152-161 with Default = UINT_MAX
+			const char *p = strstr(Label, ";size=");
+			if (!p)
+				Die("Missing size= in >%s", Label);
+			const unsigned v = (unsigned)atoi(p + 6);
+			if (v == 0)
+				Die("size=0 in >%s", Label);
+			return v;
+		};
+		t_size.resize(DB.GetSeqCount());
+		for (uint32_t i = 0; i < DB.GetSeqCount(); ++i)
+			t_size[i] = size_of(DB.GetLabel(i));
+		q_size.resize(Q.GetSeqCount());
+		for (uint32_t i = 0; i < Q.GetSeqCount(); ++i)
+			q_size[i] = size_of(Q.GetLabel(i));
+	}
+	for (GpuSearcher *gs : searchers) {
+		gs->SetHitSelection(Opts.Sel);
+		if (!t_label.empty() || !t_size.empty()) {
+			gs->SetTargetAttrs(t_label.empty() ? nullptr : t_label.data(), t_size.empty() ? nullptr : t_size.data());
+			gs->SetQueryAttrs(q_label.empty() ? nullptr : q_label.data(), q_size.empty() ? nullptr : q_size.data());
+		}
+	}
 	const double t_ready = now();
 	if (!Opts.quiet)
 		fprintf(stderr, "%u db seqs, %u query seqs, %d GPU(s)\n", DB.GetSeqCount(), Q.GetSeqCount(), gpus);
@@ -708,55 +830,76 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	const uint32_t NQ = Q.GetSeqCount();
 	const uint32_t nbatch = (NQ + Opts.batch - 1) / Opts.batch;
 	uint64_t queries_with_hits = 0;
-	// Batches are dealt round-robin to the devices and drained in input order, so the output
-	// files are in query order for any GPU count (the reference guarantees that only for 1
-	// thread).  While one group of batches is formatted and written, the next one is searched.
-	auto run_group = [&](uint32_t b0, std::vector<std::vector<HitMgr>> &results) {
-		const uint32_t nb = std::min<uint32_t>(gpus, nbatch - b0);
-		results.assign(nb, std::vector<HitMgr>());
-		std::vector<std::thread> th;
-		for (uint32_t k = 0; k < nb; ++k)
-			th.emplace_back([&, k]() {
-				const uint32_t first = (b0 + k) * Opts.batch;
-				searchers[k]->SearchBatch(Q, first, std::min<uint32_t>(Opts.batch, NQ - first), results[k]);
-			});
-		for (auto &t : th)
-			t.join();
-	};
-	std::vector<std::vector<HitMgr>> cur, nxt;
-	double t_wait = 0, t_sink = 0;
-	if (nbatch)
-		run_group(0, cur);
-	for (uint32_t b0 = 0; b0 < nbatch; b0 += gpus) {
-		const bool more = b0 + gpus < nbatch;
-		std::thread ahead;
-		if (more)
-			ahead = std::thread([&]() { run_group(b0 + gpus, nxt); });
+	// Three overlapped stages.  (1) One submitting thread per device runs usb_search_batch on the
+	// batches dealt to it round-robin, at most two ahead of the consumer.  (2) The consumer takes
+	// the results in input order and turns them into HitMgrs with several threads.  (3) The sinks
+	// format (several threads) and write.  The output files are in query order for any GPU count
+	// (the reference guarantees that only for 1 thread).
+	std::vector<std::shared_ptr<void>> raw(nbatch);
+	std::vector<char> ready(nbatch, 0);
+	std::mutex mu;
+	std::condition_variable cv;
+	uint32_t consumed = 0; // batches the consumer is done with
+	std::vector<std::thread> submit;
+	for (int d = 0; d < gpus; ++d)
+		submit.emplace_back([&, d]() {
+			for (uint32_t b = (uint32_t)d; b < nbatch; b += (uint32_t)gpus) {
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [&]() { return b < consumed + 2u * (uint32_t)gpus; });
+				}
+				const uint32_t first = b * Opts.batch;
+				std::shared_ptr<void> r = searchers[d]->SearchRaw(Q, first, std::min<uint32_t>(Opts.batch, NQ - first));
+				{
+					std::lock_guard<std::mutex> lk(mu);
+					raw[b] = std::move(r);
+					ready[b] = 1;
+				}
+				cv.notify_all();
+			}
+		});
+	const unsigned host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	double t_wait = 0, t_sink = 0, t_build = 0;
+	std::vector<HitMgr> batch;
+	for (uint32_t b = 0; b < nbatch; ++b) {
 		const double t0 = now();
-		for (const std::vector<HitMgr> &batch : cur) {
-			Sink.OnBatchDone(batch);
-			for (HitSink *x : Opts.ExtraSinks)
-				x->OnBatchDone(batch);
-			for (const HitMgr &HM : batch)
-				queries_with_hits += HM.GetHitCount() > 0;
+		std::shared_ptr<void> r;
+		{
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&]() { return ready[b] != 0; });
+			r = std::move(raw[b]);
 		}
 		const double t1 = now();
-		cur.clear();
-		if (more) {
-			ahead.join();
-			cur.swap(nxt);
+		const uint32_t first = b * Opts.batch, count = std::min<uint32_t>(Opts.batch, NQ - first);
+		searchers[b % gpus]->BuildHitMgrs(r, Q, first, count, batch, host_threads);
+		r.reset();
+		const double t2 = now();
+		Sink.OnBatchDone(batch);
+		for (HitSink *x : Opts.ExtraSinks)
+			x->OnBatchDone(batch);
+		for (const HitMgr &HM : batch)
+			queries_with_hits += HM.GetHitCount() > 0;
+		batch.clear();
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			consumed = b + 1;
 		}
-		t_sink += t1 - t0;
-		t_wait += now() - t1;
+		cv.notify_all();
+		const double t3 = now();
+		t_wait += t1 - t0;
+		t_build += t2 - t1;
+		t_sink += t3 - t2;
 	}
+	for (auto &t : submit)
+		t.join();
 	Sink.OnAllDone();
 	for (HitSink *x : Opts.ExtraSinks)
 		x->OnAllDone();
 	for (GpuSearcher *s : searchers)
 		delete s;
 	if (timing)
-		fprintf(stderr, "timing: db parse %.2fs, index+upload (query parse alongside) %.2fs, search+output %.2fs (sinks %.2fs, waiting for the GPU %.2fs)\n",
-		  t_db - t_start, t_ready - t_db, now() - t_ready, t_sink, t_wait);
+		fprintf(stderr, "timing: db parse %.2fs, index+upload (query parse alongside) %.2fs, search+output %.2fs (hit lists %.2fs, sinks %.2fs, waiting for the GPU %.2fs)\n",
+		  t_db - t_start, t_ready - t_db, now() - t_ready, t_build, t_sink, t_wait);
 	return queries_with_hits;
 }
 

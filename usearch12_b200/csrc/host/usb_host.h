@@ -116,7 +116,7 @@ class HitMgr {
 public:
 	SeqInfo m_Query;
 	std::vector<AlignResult> m_Hits;
-	std::shared_ptr<std::vector<uint32_t>> m_Arena; // run arena the hits' paths point into
+	std::shared_ptr<void> m_Arena; // keeps the batch result (run arena the hits' paths point into) alive
 	unsigned GetHitCount() const { return (unsigned)m_Hits.size(); }
 	const AlignResult *GetTopHit() const { return m_Hits.empty() ? nullptr : &m_Hits[0]; }
 };
@@ -139,6 +139,14 @@ struct OutputOpts {
 	bool output_no_hits = false;
 };
 
+// HitMgr::GetHitCount / GetHit (hitmgr.cpp:367-398,466-475): which of a query's hits the sinks see
+struct HitSelection {
+	unsigned maxhits = 0;      // -maxhits, 0 = not set
+	bool top_hit_only = false; // -top_hit_only: GetTopHit (best score, ties to the lowest target index)
+	bool top_hits_only = false; // -top_hits_only: the hits that share the best score
+	bool Any() const { return maxhits != 0 || top_hit_only || top_hits_only; }
+};
+
 // outputsink.cpp:358-381; formats of outputuc.cpp:19-69, blast6out.cpp:27-80, userout.cpp:126-215
 class OutputSink : public HitSink {
 public:
@@ -156,6 +164,7 @@ private:
 	void OutputBlast6(const HitMgr &HM, std::string &out) const;
 	void OutputUser(const HitMgr &HM, std::string &out) const;
 	FILE *m_fUC = nullptr, *m_fB6 = nullptr, *m_fUser = nullptr;
+	bool m_OutputNoHits = false;
 	std::string m_bUC, m_bB6, m_bUser;
 	std::vector<int> m_UserFields;
 };
@@ -200,9 +209,25 @@ public:
 	GpuSearcher(int Device, const SeqDB &DB, const usb_params &P);
 	~GpuSearcher() override;
 	void SearchBatch(const SeqDB &Queries, uint32_t First, uint32_t Count, std::vector<HitMgr> &Out) override;
+	// the two halves of SearchBatch, for callers that overlap them: the C-ABI call (one thread per
+	// device) and the construction of the HitMgrs from its result (any number of threads)
+	std::shared_ptr<void> SearchRaw(const SeqDB &Queries, uint32_t First, uint32_t Count);
+	void BuildHitMgrs(const std::shared_ptr<void> &Result, const SeqDB &Queries, uint32_t First, uint32_t Count,
+	  std::vector<HitMgr> &Out, unsigned Threads) const;
 	uint64_t GetLaunchCount() const;
+	void SetHitSelection(const HitSelection &Sel) { m_Sel = Sel; }
+	// label identities / size= annotations of the queries (indexed like the query SeqDB), for the
+	// Accepter rules that read labels; the pointers must stay valid while batches are searched
+	void SetQueryAttrs(const uint32_t *LabelIds, const uint32_t *Sizes)
+	{
+		m_QLabelIds = LabelIds;
+		m_QSizes = Sizes;
+	}
+	void SetTargetAttrs(const uint32_t *LabelIds, const uint32_t *Sizes);
 
 private:
+	HitSelection m_Sel;
+	const uint32_t *m_QLabelIds = nullptr, *m_QSizes = nullptr;
 	const SeqDB &m_DB;
 	usb_params m_P;
 	usb_index *m_Index = nullptr;
@@ -216,6 +241,7 @@ struct SearchOpts {
 	int gpus = 1;
 	uint32_t batch = 1u << 18;
 	bool quiet = false;
+	HitSelection Sel;
 };
 
 struct ClusterOpts {

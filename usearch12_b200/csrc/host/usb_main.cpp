@@ -25,7 +25,8 @@ using namespace usbhost;
 int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
-	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", nullptr};
+	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", "self", "notself", "selfid", "top_hit_only",
+	                              "top_hits_only", nullptr};
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
 		if (a[0] != '-')
@@ -198,6 +199,53 @@ int main(int argc, char **argv)
 	O.Out.userout = take("userout", nullptr);
 	O.Out.userfields = take("userfields", nullptr);
 	O.Out.output_no_hits = !take("output_no_hits", nullptr).empty();
+	// Accepter / Terminator / HitMgr options (accepter.cpp:41-94,145-197; terminator.cpp:66-86;
+	// hitmgr.cpp:367-398)
+	{
+		auto flag = [&](const char *name, uint32_t bit) {
+			if (!take(name, nullptr).empty())
+				O.P.accept_flags |= bit;
+		};
+		auto flt = [&](const char *name, uint32_t bit, float &dst) {
+			const std::string v = take(name, nullptr);
+			if (!v.empty()) {
+				dst = (float)atof(v.c_str());
+				O.P.accept_flags |= bit;
+			}
+		};
+		auto uns = [&](const char *name, uint32_t bit, uint32_t &dst) {
+			const std::string v = take(name, nullptr);
+			if (!v.empty()) {
+				dst = (uint32_t)atoi(v.c_str());
+				O.P.accept_flags |= bit;
+			}
+		};
+		flag("self", USB_ACC_SELF);
+		flag("notself", USB_ACC_NOTSELF);
+		flag("selfid", USB_ACC_SELFID);
+		flt("maxid", USB_ACC_MAXID, O.P.maxid);
+		uns("mincols", USB_ACC_MINCOLS, O.P.mincols);
+		uns("maxgaps", USB_ACC_MAXGAPS, O.P.maxgaps);
+		flt("query_cov", USB_ACC_QUERY_COV, O.P.query_cov);
+		flt("max_query_cov", USB_ACC_MAX_QUERY_COV, O.P.max_query_cov);
+		flt("target_cov", USB_ACC_TARGET_COV, O.P.target_cov);
+		flt("max_target_cov", USB_ACC_MAX_TARGET_COV, O.P.max_target_cov);
+		uns("maxdiffs", USB_ACC_MAXDIFFS, O.P.maxdiffs);
+		uns("mindiffs", USB_ACC_MINDIFFS, O.P.mindiffs);
+		flt("abskew", USB_ACC_ABSKEW, O.P.abskew);
+		flt("min_sizeratio", USB_ACC_MIN_SIZERATIO, O.P.min_sizeratio);
+		flt("minqt", USB_ACC_MINQT, O.P.minqt);
+		flt("maxqt", USB_ACC_MAXQT, O.P.maxqt);
+		flt("minsl", USB_ACC_MINSL, O.P.minsl);
+		flt("maxsl", USB_ACC_MAXSL, O.P.maxsl);
+		flt("termid", USB_ACC_TERMID, O.P.termid);
+		flt("termidd", USB_ACC_TERMIDD, O.P.termidd);
+		const std::string mh = take("maxhits", nullptr);
+		if (!mh.empty())
+			O.Sel.maxhits = (unsigned)atoi(mh.c_str());
+		O.Sel.top_hit_only = !take("top_hit_only", nullptr).empty();
+		O.Sel.top_hits_only = !take("top_hits_only", nullptr).empty();
+	}
 	O.gpus = atoi(take("gpus", "1").c_str());
 	O.batch = (uint32_t)atoi(take("batch", "262144").c_str());
 	O.quiet = !take("quiet", nullptr).empty();

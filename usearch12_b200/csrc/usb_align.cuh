@@ -67,6 +67,9 @@ struct AlignArgs {
 	uint32_t scratch_bytes;   // per-warp bytes of the scratch union inside the fast arrays
 	uint32_t fast_in_smem;    // 1: fast arrays in shared memory, 0: in the slab
 	const AlignTables *tab;   // amino acid path only
+	// label identities and size= annotations of queries and targets (Accepter rules that read labels)
+	const uint32_t *q_label, *q_size, *t_label, *t_size;
+	const uint32_t *n_cand_all; // TopOrder.Size per job when skipped pairs can exhaust the materialised candidates, else null
 	DevCounters *ctr;
 };
 

@@ -125,6 +125,8 @@ extern "C" void usb_default_params(usb_params *p, int cluster_fast)
 	p->lopen = -10.0f;
 	p->lext = -1.0f;
 	p->ka_dbsize = 1e9f;
+	p->accept_flags = USB_ACC_MAXID; // o_defaults.inc:7: -maxid has a default, which counts as set
+	p->maxid = 1.0f;
 }
 
 extern "C" void usb_set_local(usb_params *p, int nucleo, float evalue)
@@ -271,6 +273,9 @@ struct usb_index {
 	// nucleotide targets packed two bits per letter + wildcard flags (k_pack_targets, usb_stage.cuh)
 	DevBuf<uint32_t> d_db2, d_dbn;
 	DevBuf<uint8_t> d_wild;
+	// label identities / size= annotations of the targets (usb_index_set_attrs); n_attr = targets covered
+	DevBuf<uint32_t> d_t_label, d_t_size;
+	uint32_t n_label = 0, n_size = 0;
 	std::vector<uint32_t> row_tmp;       // usb_index_row scratch
 };
 
@@ -336,7 +341,7 @@ struct usb_searcher {
 	usb_params P;
 	DevParams D;
 	int num_sms = 0;
-	size_t smem_optin = 0, smem_per_sm = 0;
+	size_t smem_optin = 0, smem_per_sm = 0, l2_persist_bytes = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint64_t launches = 0;
@@ -367,10 +372,14 @@ struct usb_searcher {
 	DevBuf<usb_hit> d_hits_stage;
 	DevBuf<StageCounters> d_sc;
 	DevBuf<uint8_t> d_gslab;
+	DevBuf<float2> d_job_ids;
+	DevBuf<uint32_t> d_q_label, d_q_size; // usb_batch_set_query_attrs
+	uint32_t n_q_label = 0, n_q_size = 0;
 	cudaEvent_t ev_st[4 * STAGE_MAX + 1];
 	int n_ev_st = 0;
 	float ms_gate = 0, ms_dp = 0, ms_misc = 0, ms_rank = 0;
-	uint32_t last_recs = 0;
+	uint32_t last_recs = 0, last_hsp_words = 0;
+	uint64_t last_dp_cells = 0, last_dp_seq_bytes = 0;
 	std::vector<float> es_min_ungapped; // per query length, NAN = not computed yet
 	std::vector<int> es_min_gapped;     // per query length, INT_MIN = not computed yet
 };
@@ -447,6 +456,35 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 	D.bump = p->bump;
 	D.fulldp = p->fulldp != 0;
 	D.id_d = (double)p->id;
+	// Accepter / Terminator options (accepter.cpp:41-94,145-197; terminator.cpp:66-86)
+	D.accept_flags = p->accept_flags;
+	if ((p->accept_flags & USB_ACC_MAXID) && !(p->maxid < 1.0f))
+		D.accept_flags &= ~USB_ACC_MAXID; // identities never exceed 1: the default -maxid 1.0 rejects nothing
+	const uint32_t extra = D.accept_flags;
+	if (extra && (p->local || !p->is_nucleo || p->cluster_mode))
+		return fail(USB_EINVAL, "Accepter / Terminator options beyond -id (accept_flags 0x%x) are supported for nucleotide "
+		                        "usearch_global only", extra);
+	if ((extra & (USB_ACC_TERMID | USB_ACC_TERMIDD)) && p->strand_both)
+		return fail(USB_EINVAL, "-termid / -termidd with -strand both: the reference carries the accepted hits of the plus "
+		                        "strand into the minus-strand search; not supported");
+	D.mincols = p->mincols;
+	D.maxgaps = p->maxgaps;
+	D.maxdiffs = p->maxdiffs;
+	D.mindiffs = p->mindiffs;
+	D.reject_pair_counts = 0;
+	D.maxid_d = (double)p->maxid;
+	D.query_cov_d = (double)p->query_cov;
+	D.max_query_cov_d = (double)p->max_query_cov;
+	D.target_cov_d = (double)p->target_cov;
+	D.max_target_cov_d = (double)p->max_target_cov;
+	D.abskew_d = (double)p->abskew;
+	D.min_sizeratio_d = (double)p->min_sizeratio;
+	D.minqt_d = (double)p->minqt;
+	D.maxqt_d = (double)p->maxqt;
+	D.minsl_d = (double)p->minsl;
+	D.maxsl_d = (double)p->maxsl;
+	D.termid_d = (double)p->termid;
+	D.termidd_d = (double)p->termidd;
 	return 0;
 }
 
@@ -590,6 +628,8 @@ extern "C" void usb_index_free(usb_index *ix)
 	ix->d_db2.release();
 	ix->d_dbn.release();
 	ix->d_wild.release();
+	ix->d_t_label.release();
+	ix->d_t_size.release();
 	for (IndexSegment *g : ix->segs) {
 		g->release();
 		delete g;
@@ -706,6 +746,17 @@ extern "C" int usb_searcher_create(usb_index *ix, const usb_params *p, usb_searc
 	s->num_sms = prop.multiProcessorCount;
 	s->smem_optin = prop.sharedMemPerBlockOptin;
 	s->smem_per_sm = prop.sharedMemPerMultiprocessor;
+	{
+		// share of L2 that may hold persisting lines (USB_RANK_L2_MB overrides; 0 disables)
+		size_t want = (size_t)prop.persistingL2CacheMaxSize;
+		if (const char *e = getenv("USB_RANK_L2_MB"))
+			want = std::min<size_t>(want, (size_t)atol(e) << 20);
+		want = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+		if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+			s->l2_persist_bytes = want;
+		else
+			cudaGetLastError();
+	}
 	CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	for (auto &e : s->ev)
 		CK(cudaEventCreate(&e));
@@ -780,6 +831,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 			cudaEventDestroy(e);
 	s->d_job_state.release(); s->d_verdict.release(); s->d_items.release(); s->d_hsp_arena.release();
 	s->d_recs.release(); s->d_hits_stage.release(); s->d_sc.release(); s->d_gslab.release();
+	s->d_job_ids.release(); s->d_q_label.release(); s->d_q_size.release();
 	if (s->stream)
 		cudaStreamDestroy(s->stream);
 	delete s;
@@ -798,7 +850,56 @@ extern "C" int usb_batch_counters(const usb_searcher *s, uint64_t out[4])
 	return 0;
 }
 
-extern "C" int usb_batch_kernel_ms(const usb_searcher *s, double out[6])
+extern "C" int usb_index_set_attrs(usb_index *ix, uint32_t first, uint32_t n, const uint32_t *label_id, const uint32_t *size)
+{
+	if (!ix || (uint64_t)first + n > ix->S.n())
+		return fail(USB_EINVAL, "usb_index_set_attrs: targets [%u, %u) out of range", first, first + n);
+	CK(cudaSetDevice(ix->device));
+	int rc;
+	if (label_id) {
+		if ((rc = ix->d_t_label.grow_keep((size_t)first + n, ix->n_label)))
+			return rc;
+		CK(cudaMemcpy(ix->d_t_label.p + first, label_id, (size_t)n * 4, cudaMemcpyHostToDevice));
+		ix->n_label = std::max(ix->n_label, first + n);
+	}
+	if (size) {
+		for (uint32_t i = 0; i < n; ++i)
+			if (size[i] == 0)
+				return fail(USB_EINVAL, "usb_index_set_attrs: size of target %u is 0", first + i);
+		if ((rc = ix->d_t_size.grow_keep((size_t)first + n, ix->n_size)))
+			return rc;
+		CK(cudaMemcpy(ix->d_t_size.p + first, size, (size_t)n * 4, cudaMemcpyHostToDevice));
+		ix->n_size = std::max(ix->n_size, first + n);
+	}
+	return 0;
+}
+
+extern "C" int usb_batch_set_query_attrs(usb_searcher *s, uint32_t n_q, const uint32_t *label_id, const uint32_t *size)
+{
+	if (!s)
+		return fail(USB_EINVAL, "usb_batch_set_query_attrs: null searcher");
+	CK(cudaSetDevice(s->ix->device));
+	int rc;
+	s->n_q_label = s->n_q_size = 0;
+	if (label_id && n_q) {
+		if ((rc = s->d_q_label.reserve(n_q)))
+			return rc;
+		CK(cudaMemcpy(s->d_q_label.p, label_id, (size_t)n_q * 4, cudaMemcpyHostToDevice));
+		s->n_q_label = n_q;
+	}
+	if (size && n_q) {
+		for (uint32_t i = 0; i < n_q; ++i)
+			if (size[i] == 0)
+				return fail(USB_EINVAL, "usb_batch_set_query_attrs: size of query %u is 0", i);
+		if ((rc = s->d_q_size.reserve(n_q)))
+			return rc;
+		CK(cudaMemcpy(s->d_q_size.p, size, (size_t)n_q * 4, cudaMemcpyHostToDevice));
+		s->n_q_size = n_q;
+	}
+	return 0;
+}
+
+extern "C" int usb_batch_kernel_ms(const usb_searcher *s, double out[8])
 {
 	if (!s || !out || !s->ran)
 		return fail(USB_EINVAL, "usb_batch_kernel_ms: no completed batch");
@@ -807,7 +908,9 @@ extern "C" int usb_batch_kernel_ms(const usb_searcher *s, double out[6])
 	out[2] = s->ms_dp;
 	out[3] = s->ms_misc;
 	out[4] = (double)s->last_recs;
-	out[5] = 0.0;
+	out[5] = (double)s->last_dp_cells;
+	out[6] = (double)s->last_dp_seq_bytes;
+	out[7] = (double)s->last_hsp_words;
 	return 0;
 }
 
@@ -987,6 +1090,22 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
 		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
 	a.prof = getenv("USB_RANK_PROF") ? 1 : 0; // measurement knob: phase cycles to stderr
+	a.period_ns = getenv("USB_RANK_PERIOD_NS") ? (uint32_t)atol(getenv("USB_RANK_PERIOD_NS")) : 0u;
+	// Every query streams ~243 random rows of an index that is larger than L2, so a row's reuse
+	// distance is the whole index and an LRU L2 keeps nothing (ncu: 6 % hits).  A persisting access
+	// window over the first part of the postings turns that part into L2 hits; the rest streams.
+	const bool l2win = a.ix.post16 && s->l2_persist_bytes > 0;
+	if (l2win) {
+		cudaStreamAttrValue av;
+		memset(&av, 0, sizeof av);
+		const size_t bytes = std::min<size_t>(s->l2_persist_bytes, (size_t)ix->segs[0]->d_post16.cap * 2);
+		av.accessPolicyWindow.base_ptr = (void *)a.ix.post16;
+		av.accessPolicyWindow.num_bytes = bytes;
+		av.accessPolicyWindow.hitRatio = 1.0f;
+		av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		CK(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+	}
 	{
 		// two CTAs only fit with the whole L1/shared array carved out as shared memory
 		const int carve = two ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
@@ -999,6 +1118,11 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 			k_rank<false><<<n_jobs, threads, smem, s->stream>>>(a);
 		}
 		CK(cudaGetLastError());
+	}
+	if (l2win) { // the window only serves the U-sort kernel
+		cudaStreamAttrValue av;
+		memset(&av, 0, sizeof av);
+		CK(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av));
 	}
 	++s->launches;
 	return 0;
@@ -1299,6 +1423,12 @@ static int run_staged(usb_searcher *s, const StageGeom &g, AlignArgs a, uint32_t
 	S.dbn = ix->d_dbn.p;
 	S.db_wild = ix->d_wild.p;
 	S.job_state = s->d_job_state.p;
+	S.job_ids = nullptr;
+	if (a.P.accept_flags & (USB_ACC_TERMID | USB_ACC_TERMIDD)) {
+		if ((rc = s->d_job_ids.reserve(std::max(1u, n_jobs))))
+			return rc;
+		S.job_ids = s->d_job_ids.p;
+	}
 	S.verdict = s->d_verdict.p;
 	S.recs = s->d_recs.p;
 	S.recs_cap = (uint32_t)std::min<uint64_t>(caps.recs, 0x3ffffff0ull);
@@ -1375,7 +1505,13 @@ static void stage_times(usb_searcher *s)
 
 static const char *err_text(uint32_t e)
 {
-	static thread_local char buf[256];
+	static thread_local char buf[400];
+	if (e & ERR_KCAP) {
+		snprintf(buf, sizeof buf, "a query ran through all %u materialised candidates without terminating because pairs were "
+		                          "skipped (-self / -notself / -selfid / size and length ratio rules): the candidate list is longer "
+		                          "than this build materialises", (unsigned)RANK_KCAP);
+		return buf;
+	}
 	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s%s%s%s%s", e, e & ERR_REC_FULL ? " gate record list full" : "",
 	  e & ERR_HSPARENA_FULL ? " HSP arena full" : "", e & ERR_HITS_FULL ? " hit buffer full" : "",
 	  e & ERR_RUNS_FULL ? " run arena full" : "", e & ERR_HSP_FULL ? " HSP list full" : "",
@@ -1406,6 +1542,12 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 	uint32_t k_max = N;
 	if (s->P.maxaccepts > 0 && s->P.maxrejects > 0)
 		k_max = std::min<uint64_t>(N, (uint64_t)s->P.maxaccepts + s->P.maxrejects - 1);
+	// RejectPair-ed candidates are skipped without a Terminator call on the small-database path
+	// (searcher.cpp:63-67), so the loop can reach any candidate of the list: materialise as many as
+	// the build allows; a query that runs out of them unterminated is reported (ERR_KCAP)
+	const bool pair_skips = (s->D.accept_flags & ACC_PAIR_FLAGS) != 0 && !(s->big || N > s->P.big);
+	if (pair_skips)
+		k_max = std::min<uint32_t>(N, RANK_KCAP);
 	if (k_max == 0)
 		k_max = 1;
 	if (k_max > RANK_KCAP)
@@ -1483,6 +1625,23 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			a.runs = s->d_runs.p;
 			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
 			a.qstat = s->d_qstat.p;
+			if (s->D.accept_flags) {
+				if (!staged)
+					return fail(USB_EINVAL, "Accepter / Terminator options beyond -id need the staged candidate loop "
+					                        "(nucleotide scores with match > 0 > mismatch, sequences that fit in shared memory)");
+				if ((s->D.accept_flags & USB_ACC_NEEDS_LABELS) && (ix->n_label < N || s->n_q_label < s->n_q))
+					return fail(USB_EINVAL, "-self / -notself need label identities: call usb_index_set_attrs for every target "
+					                        "and usb_batch_set_query_attrs for this batch");
+				if ((s->D.accept_flags & USB_ACC_NEEDS_SIZES) && (ix->n_size < N || s->n_q_size < s->n_q))
+					return fail(USB_EINVAL, "-abskew / -min_sizeratio need size= annotations: call usb_index_set_attrs for every "
+					                        "target and usb_batch_set_query_attrs for this batch");
+				a.q_label = s->d_q_label.p;
+				a.q_size = s->d_q_size.p;
+				a.t_label = ix->d_t_label.p;
+				a.t_size = ix->d_t_size.p;
+				a.P.reject_pair_counts = s->big ? 1u : 0u;
+				a.n_cand_all = pair_skips ? s->d_ncand.p : nullptr;
+			}
 			if (staged) {
 				caps.staged = hits_cap + 1024;
 				if ((rc = run_staged(s, sg, a, hsp_cap, caps)))
@@ -1522,12 +1681,16 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		}
 		break;
 	}
-	s->last_recs = 0;
+	s->last_recs = s->last_hsp_words = 0;
+	s->last_dp_cells = s->last_dp_seq_bytes = 0;
 	if (staged && s->n_jobs && !local) {
 		stage_times(s);
 		StageCounters sc;
 		CK(cudaMemcpy(&sc, s->d_sc.p, sizeof sc, cudaMemcpyDeviceToHost));
 		s->last_recs = sc.n_recs;
+		s->last_hsp_words = sc.n_hsp_words;
+		s->last_dp_cells = sc.dp_cells;
+		s->last_dp_seq_bytes = sc.dp_seq_bytes;
 	} else
 		s->ms_gate = s->ms_dp = s->ms_misc = 0;
 	CK(cudaEventElapsedTime(&s->ms_rank, s->ev[0], s->ev[1]));

@@ -42,6 +42,13 @@ struct DevParams {
 	uint32_t alpha;                      // UDB alphabet size: 4 (nt) or 20 (aa), udbparams.cpp:235-261
 	uint32_t hash_cap;                   // aa: entries of the per-CTA word hash set (power of two), else 0
 	double id_d;                         // (double)(float)id (accepter.cpp:36-38)
+	// Accepter / Terminator options beyond -id (usb200.h USB_ACC_*), widened like oget_flt does
+	uint32_t accept_flags;
+	uint32_t mincols, maxgaps, maxdiffs, mindiffs;
+	uint32_t reject_pair_counts;         // 1: a RejectPair-ed target counts as a reject (big-database path,
+	                                     // udbusortedsearcherbig.cpp:119-128), 0: it is skipped (searcher.cpp:63-67)
+	double maxid_d, query_cov_d, max_query_cov_d, target_cov_d, max_target_cov_d, abskew_d, min_sizeratio_d;
+	double minqt_d, maxqt_d, minsl_d, maxsl_d, termid_d, termidd_d;
 };
 
 struct DevCounters {

@@ -29,11 +29,12 @@ namespace usb {
 
 #define ERR_REC_FULL 256u
 #define ERR_HSPARENA_FULL 512u
+#define ERR_KCAP 1024u
 
 #define STAGE_MAX 20          // stages per batch: [0,1), then ranges of STAGE_WIDTH candidates
 #define STAGE_WIDTH 64
 #define GATE_MAX_WARPS 32
-#define GATE_Q1 288           // flat seed queue: < 32 carried over + at most 8 x 32 per scan step
+#define GATE_Q1 512           // flat seed queue (ring, power of two): < 32 waiting + at most 8 x 32 per slow scan step
 #define GATE_Q2 64            // survivors of the pre-filter waiting for a full batch of walks
 #define DP_MAX_WARPS 16
 
@@ -44,6 +45,7 @@ struct PassRec {
 
 struct StageCounters {
 	uint32_t n_recs, n_hsp_words, n_staged, pad;
+	unsigned long long dp_cells, dp_seq_bytes; // totals over the records (measurement)
 	struct {
 		uint32_t n_items, gate_cursor, rec_begin, dp_cursor;
 	} st[STAGE_MAX];
@@ -55,6 +57,7 @@ struct StageArgs {
 	const uint8_t *db_wild;        // per target: any letter outside ACGTU
 	uint32_t ka, kb, stage;
 	uint32_t *job_state;           // done << 31 | accepts << 16 | rejects
+	float2 *job_ids;               // lowest / highest accepted identity per job (-termid, -termidd), else null
 	uint32_t *verdict;             // n_jobs x k_max: 1 = failed the gate, rec << 2 | 2 = record
 	uint32_t *items;               // jobs of this stage; null: every job (stage 0 and pairs mode)
 	PassRec *recs;
@@ -132,6 +135,89 @@ __global__ void k_stage_prep(const StageArgs S)
 		if (act)
 			S.items[base + __popc(m & ((1u << lane) - 1))] = job;
 	}
+}
+
+// ------------------------------------------------------------------ Accepter rules
+#define ACC_PAIR_FLAGS (USB_ACC_SELF | USB_ACC_NOTSELF | USB_ACC_SELFID | USB_ACC_MIN_SIZERATIO | USB_ACC_MINQT | \
+                        USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)
+
+// Accepter::RejectPair (accepter.cpp:145-197): rules on the pair itself, before any alignment.
+// Q = raw query letters, L its length; the target's raw (masked) letters come from the database.
+__device__ bool reject_pair(const AlignArgs &a, uint32_t qi, uint32_t strand, uint32_t t, const uint8_t *Q, uint32_t L)
+{
+	const DevParams &P = a.P;
+	const uint32_t f = P.accept_flags;
+	if ((f & USB_ACC_SELF) && a.q_label[qi] == a.t_label[t])
+		return true;
+	if ((f & USB_ACC_NOTSELF) && a.q_label[qi] != a.t_label[t])
+		return true;
+	const uint32_t TL = a.db_len[t];
+	if ((f & USB_ACC_SELFID) && TL == L) { // same length and the same letters, byte for byte
+		const uint8_t *T = a.db_seq + a.db_off[t];
+		bool diff = false;
+		for (uint32_t i = lane_id(); i < L; i += 32) {
+			const uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
+			diff |= c != (uint32_t)T[i];
+		}
+		if (!__any_sync(USB_FULL, diff))
+			return true;
+	}
+	if (f & USB_ACC_MIN_SIZERATIO) {
+		const double Ratio = (double)a.t_size[t] / (double)a.q_size[qi];
+		if (Ratio < P.min_sizeratio_d)
+			return true;
+	}
+	if (f & (USB_ACC_MINQT | USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)) {
+		const double q = (double)L, tt = (double)TL;
+		const double s = (double)min(L, TL), l = (double)max(L, TL);
+		const double qt = q / tt, sl = s / l;
+		if ((f & USB_ACC_MINQT) && qt < P.minqt_d)
+			return true;
+		if ((f & USB_ACC_MAXQT) && qt > P.maxqt_d)
+			return true;
+		if ((f & USB_ACC_MINSL) && sl < P.minsl_d)
+			return true;
+		if ((f & USB_ACC_MAXSL) && sl > P.maxsl_d)
+			return true;
+	}
+	return false;
+}
+
+// Accepter::IsAcceptLo (accepter.cpp:41-94) on the statistics of an alignment.
+__device__ __forceinline__ bool accept_hit(const AlignArgs &a, const usb_hit &h, uint32_t qi)
+{
+	const DevParams &P = a.P;
+	const uint32_t f = P.accept_flags;
+	const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
+	if (fid < P.id_d)
+		return false;
+	if ((f & USB_ACC_MAXID) && fid > P.maxid_d)
+		return false;
+	if ((f & USB_ACC_MINCOLS) && h.alnlen < P.mincols)
+		return false;
+	if ((f & USB_ACC_MAXGAPS) && h.intgaps > P.maxgaps)
+		return false;
+	if (f & (USB_ACC_QUERY_COV | USB_ACC_MAX_QUERY_COV)) {
+		const double cov = (double)(h.last_mq - h.first_mq + 1) / (double)h.ql; // arscorer.cpp:122-137
+		if ((f & USB_ACC_QUERY_COV) && cov < P.query_cov_d)
+			return false;
+		if ((f & USB_ACC_MAX_QUERY_COV) && cov > P.max_query_cov_d)
+			return false;
+	}
+	if (f & (USB_ACC_TARGET_COV | USB_ACC_MAX_TARGET_COV)) {
+		const double cov = (double)(h.ids + h.mism) / (double)h.tl; // arscorer.cpp:139-154
+		if ((f & USB_ACC_TARGET_COV) && cov < P.target_cov_d)
+			return false;
+		if ((f & USB_ACC_MAX_TARGET_COV) && cov > P.max_target_cov_d)
+			return false;
+	}
+	if ((f & USB_ACC_MAXDIFFS) && h.mism + h.intgaps > P.maxdiffs)
+		return false;
+	if ((f & USB_ACC_MINDIFFS) && h.mism + h.intgaps < P.mindiffs)
+		return false;
+	if ((f & USB_ACC_ABSKEW) && (double)a.t_size[h.target] / (double)a.q_size[qi] < P.abskew_d)
+		return false;
+	return true;
 }
 
 // ------------------------------------------------------------------ gate kernel
@@ -302,7 +388,8 @@ __device__ __forceinline__ void gate_extend(const StageArgs &S, GateWs &g, uint3
 	}
 }
 
-// ungappedblast.cpp:45-210 as a stream: scan 32 target word positions -> flat seed queue (scan
+// ungappedblast.cpp:45-210 as a stream: scan 128 target word positions per step (four consecutive
+// positions per lane, their words cut from one 16-letter window) -> flat seed queue (a ring, scan
 // order: position, then query order) -> pre-filter one seed per lane -> survivor queue -> walks in
 // full batches of 32.  Seeds behind the sequential scan position `cur` are dropped wherever they are.
 template <bool WILD> __device__ uint32_t gate_ungapped(const StageArgs &S, GateWs &g, uint32_t MinLength)
@@ -315,42 +402,22 @@ template <bool WILD> __device__ uint32_t gate_ungapped(const StageArgs &S, GateW
 	if (LB < 2 * hw)
 		return 0;
 	const uint32_t nwordsB = LB - hw + 1;
-	uint32_t nung = 0, scan = 0, cur = 0, n1 = 0, n2 = 0;
-	for (;;) {
-		const bool more = scan < nwordsB;
-		if (more) {
-			// 32 target positions -> their seeds
-			const uint32_t bpos = scan + lane;
-			uint32_t na = 0, st = 0;
-			if (bpos < nwordsB) {
-				const uint32_t word = hsp_word_at(w.B2, bpos, HW);
-				st = g.start[word];
-				na = (uint32_t)g.start[word + 1] - st;
-			}
-			const uint32_t lt = lanemask_lt();
-			const uint32_t b0 = __ballot_sync(USB_FULL, na & 1), b1 = __ballot_sync(USB_FULL, na & 2),
-			               b2 = __ballot_sync(USB_FULL, na & 4), b3 = __ballot_sync(USB_FULL, na & 8);
-			uint32_t d = n1 + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
-			for (uint32_t i = 0; i < na; ++i, ++d) {
-				g.q1b[d] = bpos;
-				g.q1a[d] = g.pos[st + i];
-			}
-			n1 += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
-			scan += 32;
-			__syncwarp();
-		}
-		// pre-filter: full batches while the scan goes on, the rest at its end
-		uint32_t done1 = 0;
-		while (done1 < n1 && (n1 - done1 >= 32 || !more)) {
-			const uint32_t e = done1 + lane;
+	constexpr uint32_t QM = GATE_Q1 - 1;
+	uint32_t nung = 0, scan = 0, cur = 0, n2 = 0;
+	uint32_t head = 0, tail = 0; // ring of queued seeds [head, tail)
+	// pre-filter: full batches of 32 queued seeds (all = true: the rest too)
+	auto drain = [&](bool all) {
+		while (tail - head >= 32 || (all && tail != head)) {
+			const uint32_t cnt = min(32u, tail - head);
 			bool keep = false;
 			uint32_t bp = 0, ap = 0;
-			if (e < n1) {
-				bp = g.q1b[e];
-				ap = g.q1a[e];
+			if (lane < cnt) {
+				bp = g.q1b[(head + lane) & QM];
+				ap = g.q1a[(head + lane) & QM];
 				int seed2;
 				keep = bp >= cur && seed_may_pass_p<WILD>(S.A, w, ap, bp, seed2);
 			}
+			head += cnt;
 			const uint32_t km = __ballot_sync(USB_FULL, keep);
 			if (keep) {
 				const uint32_t d = n2 + __popc(km & lanemask_lt());
@@ -358,12 +425,10 @@ template <bool WILD> __device__ uint32_t gate_ungapped(const StageArgs &S, GateW
 				g.q2a[d] = (uint16_t)ap;
 			}
 			n2 += __popc(km);
-			done1 += 32;
 			__syncwarp();
 			if (n2 >= 32) {
 				gate_extend<WILD>(S, g, 32, MinLength, cur, nung);
-				// move the rest of the queue to its front
-				const uint32_t rest = n2 - 32;
+				const uint32_t rest = n2 - 32; // move the rest of the survivor queue to its front
 				uint32_t mb = 0, ma = 0;
 				if (lane < rest) {
 					mb = g.q2b[32 + lane];
@@ -378,32 +443,78 @@ template <bool WILD> __device__ uint32_t gate_ungapped(const StageArgs &S, GateW
 				__syncwarp();
 			}
 		}
-		done1 = min(done1, n1);
-		if (done1) { // carry the unfiltered tail (< 32 seeds) to the front of the queue
-			const uint32_t rest = n1 - done1;
-			uint32_t mb = 0, ma = 0;
-			if (lane < rest) {
-				mb = g.q1b[done1 + lane];
-				ma = g.q1a[done1 + lane];
+	};
+	while (scan < nwordsB) {
+		const uint32_t bpos0 = scan + 4 * lane;
+		uint32_t st[4], na[4];
+		uint32_t c = 0;
+		{
+			const uint32_t x = bpos0 < nwordsB ? ext16(w.B2, bpos0) : 0u;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				st[i] = 0;
+				na[i] = 0;
+				if (bpos0 + i < nwordsB) {
+					const uint32_t word = (x >> (2 * i)) & (HW - 1);
+					st[i] = g.start[word];
+					na[i] = (uint32_t)g.start[word + 1] - st[i];
+				}
+				c += na[i];
 			}
-			__syncwarp();
-			if (lane < rest) {
-				g.q1b[lane] = mb;
-				g.q1a[lane] = (uint16_t)ma;
-			}
-			n1 = rest;
-			__syncwarp();
 		}
-		if (!more) {
-			if (n2) {
-				gate_extend<WILD>(S, g, n2, MinLength, cur, nung);
-				n2 = 0;
-			}
-			break;
+		uint32_t incl = c;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(USB_FULL, incl, d);
+			if (lane >= (uint32_t)d)
+				incl += t;
 		}
+		const uint32_t T = __shfl_sync(USB_FULL, incl, 31);
+		if (tail - head + T <= GATE_Q1) {
+			uint32_t d = tail + incl - c;
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				for (uint32_t j = 0; j < na[i]; ++j, ++d) {
+					g.q1b[d & QM] = bpos0 + i;
+					g.q1a[d & QM] = g.pos[st[i] + j];
+				}
+			tail += T;
+			__syncwarp();
+			drain(false);
+		} else {
+			// a low-complexity stretch (up to 8 seeds per position): 32 positions at a time
+			for (uint32_t r = 0; r < 4; ++r) {
+				const uint32_t bpos = scan + 32 * r + lane;
+				uint32_t n1 = 0, s1 = 0;
+				if (bpos < nwordsB) {
+					const uint32_t word = hsp_word_at(w.B2, bpos, HW);
+					s1 = g.start[word];
+					n1 = (uint32_t)g.start[word + 1] - s1;
+				}
+				uint32_t in2 = n1;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t t = __shfl_up_sync(USB_FULL, in2, d);
+					if (lane >= (uint32_t)d)
+						in2 += t;
+				}
+				uint32_t d = tail + in2 - n1;
+				for (uint32_t j = 0; j < n1; ++j, ++d) {
+					g.q1b[d & QM] = bpos;
+					g.q1a[d & QM] = g.pos[s1 + j];
+				}
+				tail += __shfl_sync(USB_FULL, in2, 31);
+				__syncwarp();
+				drain(false);
+			}
+		}
+		scan += 128;
 		if (cur > scan)
 			scan = cur;
 	}
+	drain(true);
+	if (n2)
+		gate_extend<WILD>(S, g, n2, MinLength, cur, nung);
 	__syncwarp();
 	return nung;
 }
@@ -531,6 +642,15 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 		}
 		for (uint32_t k = k0; k < k1; ++k) {
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			if (a.P.accept_flags & ACC_PAIR_FLAGS) {
+				const uint64_t q0 = a.q_off[qi];
+				if (reject_pair(a, qi, strand, t, a.q + q0, (uint32_t)(a.q_off[qi + 1] - q0))) {
+					// skipped without a Terminator call, or counted as a reject on the big-database path
+					if (lane == 0)
+						S.verdict[(uint64_t)job * a.k_max + (pairs ? 0u : k)] = a.P.reject_pair_counts ? 1u : 3u;
+					continue;
+				}
+			}
 			const bool twild = S.db_wild[t] != 0;
 			uint32_t nchain = 0, pass;
 			if (a.P.fulldp) {
@@ -716,9 +836,8 @@ __global__ void __launch_bounds__(DP_MAX_WARPS * 32, 1) k_dp(const StageArgs S)
 			if (lane == 0)
 				atomicOr(&a.ctr->err, ERR_NO_M);
 		} else {
-			// accepter.cpp:27-38: reject iff double(ids)/double(cols) < (double)(float)id
-			const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
-			if ((pairs || !(fid < a.P.id_d)) && emit_runs(a, w, n, h)) {
+			// accepter.cpp:27-94: reject iff double(ids)/double(cols) < (double)(float)id, then the other rules
+			if ((pairs || accept_hit(a, h, qi)) && emit_runs(a, w, n, h)) {
 				if (lane == 0)
 					hit = atomicAdd(&S.sc->n_staged, 1u);
 				hit = __shfl_sync(USB_FULL, hit, 0);
@@ -734,6 +853,8 @@ __global__ void __launch_bounds__(DP_MAX_WARPS * 32, 1) k_dp(const StageArgs S)
 			}
 		}
 		if (lane == 0) {
+			atomicAdd(&S.sc->dp_cells, (unsigned long long)st.dp_cells);
+			atomicAdd(&S.sc->dp_seq_bytes, (unsigned long long)(LA + LB));
 			S.recs[ri].hit = hit;
 			S.recs[ri].n_dp = st.n_dp;
 			S.recs[ri].dp_cells = st.dp_cells;
@@ -757,6 +878,12 @@ __global__ void k_commit(const StageArgs S)
 		} else
 			st = a.qstat[job];
 		uint32_t acc = (state >> 16) & 0x7fff, rej = state & 0xffff;
+		// HitMgr::GetMinFractId / GetMaxFractId (hitmgr.cpp:508-532) of the hits accepted so far
+		float minid = 1.0f, maxid = 0.0f;
+		if (S.job_ids && S.stage != 0) {
+			minid = S.job_ids[job].x;
+			maxid = S.job_ids[job].y;
+		}
 		const uint32_t ncand = pairs ? 1u : a.n_emit[job];
 		const uint32_t n = min(ncand, S.kb);
 		bool done = false;
@@ -768,6 +895,8 @@ __global__ void k_commit(const StageArgs S)
 		for (uint32_t k = S.ka; k < n; ++k) {
 			const uint32_t v = S.verdict[(uint64_t)job * a.k_max + k];
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			if (v == 3u) // RejectPair: no alignment, no Terminator call (searcher.cpp:63-67)
+				continue;
 			++st.n_tried;
 			st.seq_bytes += LA + a.db_len[t];
 			bool accept = false;
@@ -784,17 +913,30 @@ __global__ void k_commit(const StageArgs S)
 				if (pairs)
 					a.aligned[job] = 1;
 				if (accept) {
+					const usb_hit hh = S.hits_stage[r.hit - 1];
 					const uint32_t slot = atomicAdd(&a.ctr->n_hits, 1u);
 					if (slot < a.hits_cap)
-						a.hits[slot] = S.hits_stage[r.hit - 1];
+						a.hits[slot] = hh;
 					else
 						atomicOr(&a.ctr->err, ERR_HITS_FULL);
 					++st.n_accept;
+					const float fid = (float)(hh.alnlen == 0 ? 0.0 : (double)hh.ids / (double)hh.alnlen);
+					minid = fminf(minid, fid);
+					maxid = fmaxf(maxid, fid);
 				}
 			}
 			if (pairs)
 				break;
-			// terminator.cpp:64-100
+			// terminator.cpp:64-100: -termid / -termidd look at the hits accepted so far (this one included)
+			if ((a.P.accept_flags & USB_ACC_TERMID) && acc + (accept ? 1u : 0u) > 0 && (double)minid <= a.P.termid_d) {
+				done = true;
+				break;
+			}
+			if ((a.P.accept_flags & USB_ACC_TERMIDD) && acc + (accept ? 1u : 0u) > 0 &&
+			    (double)(maxid - minid) > a.P.termidd_d) {
+				done = true;
+				break;
+			}
 			if (accept)
 				++acc;
 			else
@@ -804,9 +946,15 @@ __global__ void k_commit(const StageArgs S)
 				break;
 			}
 		}
-		if (S.kb >= ncand)
+		if (S.kb >= ncand) {
+			// every materialised candidate was looked at; with skipped pairs the reference may go on
+			if (!done && a.n_cand_all && a.n_cand_all[job] > ncand)
+				atomicOr(&a.ctr->err, ERR_KCAP);
 			done = true;
+		}
 		S.job_state[job] = (done ? 0x80000000u : 0u) | (acc << 16) | rej;
+		if (S.job_ids)
+			S.job_ids[job] = make_float2(minid, maxid);
 		if (a.qstat)
 			a.qstat[job] = st;
 	}
