@@ -84,9 +84,11 @@ def test_viterbi_matches_oracle(env):
     s = capi.Searcher(env["ix"], env["ix"].params)
     rng = random.Random(3)
     A, B, F = [], [], []
-    for k in range(400):
+    for k in range(640):
         la = rng.choice([1, 2, 3, 5, 17, 24, 31, 32, 33, 40, 64, 65, 100, 184, 250])
-        b = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 2, 7, 33, 64, 100, 364, 700, 1291])))
+        # (rows of 96 and more columns take the four-columns-per-lane sweep)
+        b = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 2, 7, 33, 64, 95, 96, 97, 100, 127, 128, 129, 131, 255, 257,
+                                                                  364, 511, 700, 1291, 1409])))
         mode = k % 4
         if mode == 0:      # related: A is a mutated window of B
             st = rng.randrange(0, max(1, len(b) - la + 1))

@@ -937,17 +937,19 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 		dlo = 1;
 		dhi = LA + LB - 1;
 	}
-	const uint64_t W = (uint64_t)LB + 1;
+	// trace rows start on 4-byte boundaries and the two DP rows on 16-byte boundaries: wide rows are
+	// swept four columns per lane with vector loads and stores
+	const uint64_t W = ((uint64_t)LB + 4) & ~(uint64_t)3;
 	// rows in shared memory when the rectangle is narrow enough, else in the global slab
-	const bool rows_fit = 8u * (LB + 8) <= a.scratch_bytes;
+	const bool rows_fit = 8u * (LB + 12) <= a.scratch_bytes;
 	// next choice: the query's seed table (cnt, start, pos) lies right in front of the scratch and
 	// is not needed any more for this candidate; it is rebuilt if another candidate follows
 	const uint32_t big_bytes = (uint32_t)((w.scratch + a.scratch_bytes) - w.cnt);
-	const bool rows_big = !rows_fit && a.fast_in_smem && 8u * (LB + 8) <= big_bytes;
+	const bool rows_big = !rows_fit && a.fast_in_smem && 8u * (LB + 12) <= big_bytes;
 	if (rows_big)
 		w.seed_dirty = true;
 	int *Mrow = (rows_fit ? (int *)w.scratch : rows_big ? (int *)w.cnt : w.rows_slab) + 4;
-	int *Drow = Mrow + LB + 4;
+	int *Drow = Mrow + ((LB + 4 + 3) & ~3u);
 	uint8_t *TB = w.TB;
 	for (uint32_t j = lane; j <= LB + 1; j += 32) {
 		Mrow[(int)j - 1] = USB_NEG;
@@ -970,6 +972,106 @@ __device__ uint32_t viterbi_band(const AlignArgs &a, WarpWs &w, const uint8_t *A
 			TBrow[sj - 1] = TB_IM;
 		int Icarry = USB_NEG;
 		int lastMold = Mcarry;
+		if (ej - sj >= 96) {
+			// Wide row: four consecutive columns per lane, 128 per step.  Inside a lane the insert
+			// state runs serially over its four columns; across lanes it is the same max-plus scan
+			// as below on the lanes' aggregates (what leaves the lane if nothing enters it), with a
+			// step cost of four extensions.  One scan, three shuffles and vector accesses serve 128
+			// cells.  Columns left of sj (the chunk starts on a multiple of four) are dead cells;
+			// column sj - 1 carries the row's start value so that column sj sees it as `saved`.
+			const uint32_t b0 = sj & ~3u;
+			int McW = (b0 == sj) ? Mcarry : USB_NEG;
+			for (uint32_t base = b0; base < ej; base += 128) {
+				const uint32_t j0 = base + 4 * lane;
+				int mo[4], dol[4];
+				if (j0 >= sj && j0 + 3 < ej) {
+					const int4 m4 = *(const int4 *)(Mrow + j0), d4 = *(const int4 *)(Drow + j0);
+					mo[0] = m4.x; mo[1] = m4.y; mo[2] = m4.z; mo[3] = m4.w;
+					dol[0] = d4.x; dol[1] = d4.y; dol[2] = d4.z; dol[3] = d4.w;
+				} else {
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const uint32_t j = j0 + c;
+						const bool act = j >= sj && j < ej;
+						mo[c] = act ? Mrow[j] : (j + 1 == sj ? Mcarry : USB_NEG);
+						dol[c] = act ? Drow[j] : USB_NEG;
+					}
+				}
+				int sv[4];
+				sv[0] = __shfl_up_sync(USB_FULL, mo[3], 1);
+				if (lane == 0)
+					sv[0] = McW;
+				sv[1] = mo[0]; sv[2] = mo[1]; sv[3] = mo[2];
+				const int g0 = sv[0] + OpenA, g1 = sv[1] + OpenA, g2 = sv[2] + OpenA, g3 = sv[3] + OpenA;
+				const int L = max(max(g0 + 3 * ExtA, g1 + 2 * ExtA), max(g2 + ExtA, g3));
+				const int R = scan_gap(L, 4 * ExtA);
+				const int Iout = max(R, Icarry + (int)(lane + 1) * 4 * ExtA);
+				int Ie = __shfl_up_sync(USB_FULL, Iout, 1);
+				if (lane == 0)
+					Ie = Icarry;
+				const int gg[4] = {g0, g1, g2, g3};
+				int mn[4], dn[4];
+				uint32_t tb = 0;
+				uint32_t b4 = 0;
+				if (j0 < ej) {
+					// four target letters; Bc + j0 is not word aligned in general (a hole starts anywhere
+					// in the target): two aligned words and a funnel shift (the buffer is padded)
+					const uintptr_t pb = (uintptr_t)(Bc + j0);
+					const uint32_t *pw = (const uint32_t *)(pb & ~(uintptr_t)3);
+					b4 = __funnelshift_r(pw[0], pw[1], 8 * (uint32_t)(pb & 3));
+				}
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					const uint32_t j = j0 + c;
+					const bool act = j >= sj && j < ej;
+					uint32_t bits = 0;
+					int xM = sv[c];
+					if (dol[c] > xM) {
+						xM = dol[c];
+						bits = TB_DM;
+					}
+					if (Ie > xM) {
+						xM = Ie;
+						bits = TB_IM;
+					}
+					mn[c] = xM + (act ? subst2g<AA>(a, w, ca, (b4 >> (8 * c)) & 0xffu) : 0);
+					const int ob = (j == 0) ? G.LOpenB : G.OpenB, eb = (j == 0) ? G.LExtB : G.ExtB;
+					const int md = sv[c] + ob;
+					int dnew = dol[c] + eb;
+					if (md >= dnew) {
+						dnew = md;
+						bits |= TB_MD;
+					}
+					if (gg[c] >= Ie + ExtA)
+						bits |= TB_MI;
+					dn[c] = dnew;
+					tb |= bits << (8 * c);
+					Ie = max(gg[c], Ie + ExtA);
+				}
+				// carries: old M of the row's last column (right edge), of this step's last column, I
+				const uint32_t last = min(127u, ej - 1 - base);
+				const uint32_t lc = last & 3;
+				const int msel = lc == 0 ? mo[0] : lc == 1 ? mo[1] : lc == 2 ? mo[2] : mo[3];
+				lastMold = __shfl_sync(USB_FULL, msel, last >> 2);
+				McW = __shfl_sync(USB_FULL, mo[3], 31);
+				Icarry = __shfl_sync(USB_FULL, Iout, 31);
+				if (j0 >= sj && j0 + 3 < ej) {
+					*(int4 *)(Mrow + j0) = make_int4(mn[0], mn[1], mn[2], mn[3]);
+					*(int4 *)(Drow + j0) = make_int4(dn[0], dn[1], dn[2], dn[3]);
+					*(uint32_t *)(TBrow + j0) = tb;
+				} else {
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const uint32_t j = j0 + c;
+						if (j >= sj && j < ej) {
+							Mrow[j] = mn[c];
+							Drow[j] = dn[c];
+							TBrow[j] = (uint8_t)(tb >> (8 * c));
+						}
+					}
+				}
+			}
+		} else
 		for (uint32_t base = sj; base < ej; base += 32) {
 			const uint32_t j = base + lane;
 			const bool act = j < ej;

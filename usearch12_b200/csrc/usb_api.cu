@@ -9,6 +9,7 @@
 #include <ctime>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "usb_align.cuh"
@@ -155,6 +156,8 @@ extern "C" void usb_set_amino(usb_params *p)
 	p->gap_open = -17.0f;
 	p->gap_ext = -1.0f;
 }
+
+#define CLUSTER_ROWS_CAP 32 // sampled words per query the cluster round's conflict kernel handles
 
 // ------------------------------------------------------------------ objects
 template <class T> struct DevBuf {
@@ -373,6 +376,13 @@ struct usb_searcher {
 	DevBuf<StageCounters> d_sc;
 	DevBuf<uint8_t> d_gslab;
 	DevBuf<float2> d_job_ids;
+	// cluster rounds: the block's own sequences laid out as targets (usb_cluster.inc)
+	DevBuf<uint8_t> d_tseq, d_twild, d_pal;
+	DevBuf<uint64_t> d_toff;
+	DevBuf<uint32_t> d_tlen, d_tdb2, d_tdbn, d_ppq, d_ppt;
+	DevBuf<uint32_t> d_rows_out, d_nrows_out;          // sampled words per job (k_rank_big)
+	DevBuf<uint32_t> d_tcnt, d_trow_size, d_tpost, d_lim, d_theta, d_conf; // conflict kernel
+	DevBuf<uint64_t> d_trow_off;
 	DevBuf<uint32_t> d_q_label, d_q_size; // usb_batch_set_query_attrs
 	uint32_t n_q_label = 0, n_q_size = 0;
 	cudaEvent_t ev_st[4 * STAGE_MAX + 1];
@@ -574,14 +584,21 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	}
 	// small appends (and everything after the first one) go to the growable tail segment; the
 	// initial targets of a search database always form a static segment (2-byte layout)
-	if (ix->dyn || (n < 8192 && (ix->P.cluster_mode || n0 > 0))) {
+	// (cluster_fast: every append goes to the tail segment, large ones through the device builder)
+	if (ix->dyn || ix->P.cluster_mode || (n < 8192 && n0 > 0)) {
 		if (!ix->dyn) {
 			ix->dyn = new DynSegment;
 			if ((rc = ix->dyn->init(n0, ix->P.word_length, ix->P.is_nucleo ? 4 : 20)))
 				return rc;
 		}
 		const uint64_t before = ix->dyn->n_postings;
-		if ((rc = ix->dyn->append(S, n0, n, ix->P.word_length)))
+		if (ix->P.is_nucleo && n >= 256 && !getenv("USB_HOST_INDEX")) {
+			int num_sms = 0;
+			CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ix->device));
+			rc = ix->dyn->append_device(ix->d_seqs.p, ix->d_seq_off.p, ix->d_seq_len.p, n0, n, ix->P.word_length, num_sms);
+		} else
+			rc = ix->dyn->append(S, n0, n, ix->P.word_length);
+		if (rc)
 			return rc;
 		ix->n_postings += ix->dyn->n_postings - before;
 		return index_sync_layout(ix); // a tail segment ends the 2-byte layout of a static one
@@ -832,6 +849,10 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 	s->d_job_state.release(); s->d_verdict.release(); s->d_items.release(); s->d_hsp_arena.release();
 	s->d_recs.release(); s->d_hits_stage.release(); s->d_sc.release(); s->d_gslab.release();
 	s->d_job_ids.release(); s->d_q_label.release(); s->d_q_size.release();
+	s->d_tseq.release(); s->d_twild.release(); s->d_pal.release(); s->d_toff.release(); s->d_tlen.release();
+	s->d_tdb2.release(); s->d_tdbn.release(); s->d_ppq.release(); s->d_ppt.release();
+	s->d_rows_out.release(); s->d_nrows_out.release(); s->d_tcnt.release(); s->d_trow_size.release(); s->d_tpost.release();
+	s->d_lim.release(); s->d_theta.release(); s->d_conf.release(); s->d_trow_off.release();
 	if (s->stream)
 		cudaStreamDestroy(s->stream);
 	delete s;
@@ -991,6 +1012,7 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 		return fail(USB_ELIMIT, "big-database path supports queries up to %u letters (got %u)",
 		  BIG_MAX_POS + s->D.word_length - 1, s->max_ql);
 	RankBigArgs a;
+	int rc0;
 	memset(&a, 0, sizeof a);
 	a.P = s->D;
 	a.q = s->d_q.p;
@@ -1007,6 +1029,14 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 	a.u_out = want_u ? s->d_uout.p : nullptr;
 	a.aux = s->d_aux.p;
 	a.stepwords = s->P.stepwords;
+	a.rows_out = nullptr;
+	if (s->P.cluster_mode) { // usb_cluster_round reads the sampled words back on the device
+		if ((rc0 = s->d_rows_out.reserve((size_t)n_jobs * CLUSTER_ROWS_CAP)) || (rc0 = s->d_nrows_out.reserve(n_jobs)))
+			return rc0;
+		a.rows_out = s->d_rows_out.p;
+		a.n_rows_out = s->d_nrows_out.p;
+		a.rows_cap = CLUSTER_ROWS_CAP;
+	}
 	a.ctr = s->d_ctr.p;
 	a.u_stride = (((uint64_t)N * 2 + 64) + 255) & ~(uint64_t)255;
 	const uint32_t grid = std::min<uint32_t>(n_jobs, (uint32_t)s->num_sms * 2);
@@ -1090,7 +1120,6 @@ static int launch_rank(usb_searcher *s, uint32_t n_jobs, uint32_t strands, uint3
 		  "U-sort needs %zu bytes of shared memory for %u targets (%s counters) > %zu available; tiled U-sort is not built yet",
 		  smem, N, wide ? "2-byte" : "1-byte", s->smem_optin);
 	a.prof = getenv("USB_RANK_PROF") ? 1 : 0; // measurement knob: phase cycles to stderr
-	a.period_ns = getenv("USB_RANK_PERIOD_NS") ? (uint32_t)atol(getenv("USB_RANK_PERIOD_NS")) : 0u;
 	// Every query streams ~243 random rows of an index that is larger than L2, so a row's reuse
 	// distance is the whole index and an LRU L2 keeps nothing (ncu: 6 % hits).  A persisting access
 	// window over the first part of the postings turns that part into L2 hits; the rest streams.
@@ -1397,7 +1426,14 @@ struct StageCaps {
 
 // Launches the stages of one batch on the searcher's stream (no host synchronisation inside).
 // a: AlignArgs with the batch fields (n_jobs, cand_t / pairs, hits, runs, qstat ...) filled in.
-static int run_staged(usb_searcher *s, const StageGeom &g, AlignArgs a, uint32_t hsp_cap, const StageCaps &caps)
+// packed 2-bit letters of the targets the staged kernels read (default: the index's)
+struct PackedTargets {
+	const uint32_t *db2, *dbn;
+	const uint8_t *wild;
+};
+
+static int run_staged(usb_searcher *s, const StageGeom &g, AlignArgs a, uint32_t hsp_cap, const StageCaps &caps,
+  const PackedTargets *PT = nullptr)
 {
 	const usb_index *ix = s->ix;
 	const bool pairs = a.pair_q != nullptr;
@@ -1419,9 +1455,9 @@ static int run_staged(usb_searcher *s, const StageGeom &g, AlignArgs a, uint32_t
 	S.A.hsp_cap = hsp_cap;
 	S.A.fast_in_smem = 1;
 	S.A.tab = nullptr;
-	S.db2 = ix->d_db2.p;
-	S.dbn = ix->d_dbn.p;
-	S.db_wild = ix->d_wild.p;
+	S.db2 = PT ? PT->db2 : ix->d_db2.p;
+	S.dbn = PT ? PT->dbn : ix->d_dbn.p;
+	S.db_wild = PT ? PT->wild : ix->d_wild.p;
 	S.job_state = s->d_job_state.p;
 	S.job_ids = nullptr;
 	if (a.P.accept_flags & (USB_ACC_TERMID | USB_ACC_TERMIDD)) {

@@ -68,7 +68,6 @@ struct RankArgs {
 	uint32_t rec_cap;
 	double bump_d;             // BumpPct / 100.0 ; 0 = no bump
 	uint32_t prof;             // 1 = accumulate phase cycles in ctr->prof (measurement)
-	uint32_t period_ns;        // > 0: phase-locked row order (see rank_job), period of one sweep over the words
 	DevCounters *ctr;
 };
 
@@ -624,7 +623,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				if (size) {
 					const uint32_t idx = atomicAdd(&S.n_rows, 1u);
 					X.r_off[idx] = (uint32_t)(off >> 3);
-					X.r_size[idx] = groups | (word << 16); // nt words fit 16 bits; groups < 65536
+					X.r_size[idx] = groups;
 					atomicAdd(&S.n_post, size);
 				}
 			} else if (fresh) {
@@ -652,32 +651,6 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 					atomicAdd(&S.n_post, sz);
 			}
 			USB_PHASE(1)
-			// Phase-locked row order.  Co-resident CTAs read ~40 % of their row bytes in common
-			// (frequent words), but in query order those reads are spread over the whole launch and
-			// the rows (2.4x the L2) are gone by the time the next CTA wants them.  Here every CTA
-			// walks its rows in ascending word order, starting at the word the global clock points
-			// at and wrapping around: all CTAs sweep the index in step, so a row wanted by several
-			// of them is wanted at about the same time and comes from L2.  U does not depend on the
-			// order of the rows.  (One pass only: the bitmap's memory holds the permutation.)
-			const bool sweep = HALF && a.period_ns != 0 && a.P.alpha == 4 && npos <= PW && n_rows > 1;
-			uint16_t *perm = (uint16_t *)bitmap;
-			uint32_t sweep0 = 0;
-			if (sweep) {
-				uint32_t mine = 0xffffffffu, rank = 0;
-				if (tid < n_rows)
-					mine = X.r_size[tid] >> 16;
-				for (uint32_t j = 0; j < n_rows; ++j)
-					rank += (X.r_size[j] >> 16) < mine ? 1u : 0u;
-				unsigned long long now;
-				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-				// the clock of thread 0 decides for the CTA
-				if (tid == 0)
-					S.vstar = (uint32_t)((now % a.period_ns) * (unsigned long long)a.P.slots / a.period_ns);
-				__syncthreads(); // everybody is done with the bitmap and has read its word
-				if (tid < n_rows)
-					perm[rank] = (uint16_t)tid;
-				sweep0 = __syncthreads_count(tid < n_rows && mine < S.vstar);
-			}
 			const uint4 *P4 = HALF ? (const uint4 *)a.ix.post16 : (const uint4 *)a.ix.seg[0].postings;
 			// whole rows per warp, drawn from a shared cursor
 			for (;;) {
@@ -687,12 +660,7 @@ __device__ void rank_job(const RankArgs &a, uint32_t job, RankShared &S, uint8_t
 				r = __shfl_sync(USB_FULL, r, 0);
 				if (r >= n_rows)
 					break;
-				if (sweep) {
-					uint32_t k = sweep0 + r;
-					k = k >= n_rows ? k - n_rows : k;
-					r = perm[k];
-				}
-				const uint32_t size = HALF ? (X.r_size[r] & 0xffffu) : X.r_size[r];
+				const uint32_t size = X.r_size[r];
 				const uint4 *v4 = P4 + X.r_off[r];
 				if (HALF) {
 					// size = groups of 32 vectors; every entry is a valid increment (padding

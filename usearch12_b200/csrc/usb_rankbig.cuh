@@ -43,6 +43,9 @@ struct RankBigArgs {
 	uint8_t *u_arena;          // gridDim.x counter arrays of u_stride bytes
 	uint64_t u_stride;         // >= 2 * n_seq, multiple of 16
 	uint32_t stepwords;
+	uint32_t *rows_out;        // optional: the sampled words of every job, rows_cap per job
+	uint32_t *n_rows_out;      // their number (0xffffffff when more than rows_cap)
+	uint32_t rows_cap;
 	DevCounters *ctr;
 };
 
@@ -464,6 +467,12 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank_big(const RankBigArgs 
 		const uint32_t n_rows = min((nu + Step - 1) / Step, (uint32_t)BIG_MAX_ROWS);
 		for (uint32_t r = tid; r < n_rows; r += RANK_THREADS)
 			S.rows[r] = S.uniq[r * Step];
+		if (a.rows_out) { // the words this query counts with, for the cluster round's conflict kernel
+			for (uint32_t r = tid; r < n_rows && r < a.rows_cap; r += RANK_THREADS)
+				a.rows_out[(uint64_t)job * a.rows_cap + r] = S.uniq[r * Step];
+			if (tid == 0)
+				a.n_rows_out[job] = n_rows <= a.rows_cap ? n_rows : 0xffffffffu;
+		}
 		__syncthreads();
 		if (n_rows > 255)
 			rank_big_job<true>(a, job, S, U, n_rows, Step);
