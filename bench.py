@@ -244,7 +244,7 @@ def leg_cluster(a, amplicon, db, db_off):
         ours = time.perf_counter() - t
         out = {"workload": "cluster_fast %dx250bp %s reads -id 0.97 (host CLI, FASTA in -> .uc + centroids out)" % (
             n, "amplicon" if amplicon else "window-random"), "value": n / ours, "unit": "seqs/s", "seconds": ours,
-            "rc": r.returncode, "log": r.stdout.strip().splitlines()[-2:]}
+            "rc": r.returncode, "log": r.stdout.strip().splitlines()[-3:]}
         if not a.no_cpu_baseline and os.path.exists(REF_BIN):
             ns = min(a.cluster_ref_sample, n)
             fs = os.path.join(tmp, "s.fa")

@@ -17,6 +17,8 @@
 
 #include "usb_host.h"
 
+#include <chrono>
+
 namespace usbhost {
 
 static void CheckUsb2(int rc, const char *what)
@@ -190,14 +192,19 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 {
 	if (usb_device_count() <= 0)
 		Die("No CUDA device available: this build has no CPU search path");
+	const bool timing = getenv("USB_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_start = now();
 	SeqDB Input;
 	Input.FromFasta(ReadsFileName);
 	const unsigned SeqCount = Input.GetSeqCount();
 	if (SeqCount == 0)
 		Die("No sequences in input file");
+	const double t_parsed = now();
 
 	std::vector<unsigned> UniqOf, First, USize;
 	DerepFullHost(Input, UniqOf, First, USize);
+	const double t_derep = now();
 	const unsigned UniqueCount = (unsigned)First.size();
 	// members of each unique in input order (CSR)
 	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(SeqCount);
@@ -239,6 +246,8 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	CheckUsb2(usb_index_create(0, &Opts.P, Letters.data(), zero_off, 0, &Index), "usb_index_create");
 	CheckUsb2(usb_searcher_create(Index, &Opts.P, &Srch), "usb_searcher_create");
 
+	const double t_ready = now();
+	double t_rounds = 0;
 	FILE *fUC = nullptr;
 	if (!Opts.uc.empty() && !(fUC = fopen(Opts.uc.c_str(), "wb")))
 		Die("Cannot create %s", Opts.uc.c_str());
@@ -253,7 +262,9 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		cidx.resize(n);
 		uint32_t ncom = 0;
 		usb_result *R = nullptr;
+		const double tr0 = now();
 		CheckUsb2(usb_cluster_round(Srch, Letters.data(), Off.data() + pos, n, &ncom, cidx.data(), &R), "usb_cluster_round");
+		t_rounds += now() - tr0;
 		++rounds;
 		const usb_hit *hits = usb_result_hits(R);
 		const uint64_t *qoff = usb_result_query_offsets(R);
@@ -314,6 +325,7 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		else
 			B = std::max<uint32_t>(64, std::min<uint32_t>(B, 2 * ncom));
 	}
+	const double t_loop = now();
 	const unsigned ClusterCount = (unsigned)ClusterSizes.size();
 	if (fUC) {
 		for (unsigned c = 0; c < ClusterCount; ++c) {
@@ -353,6 +365,9 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	if (!Opts.quiet)
 		fprintf(stderr, "%u seqs, %u uniques, %u clusters, %llu rounds\n", SeqCount, UniqueCount, ClusterCount,
 		  (unsigned long long)rounds);
+	if (timing)
+		fprintf(stderr, "timing: parse %.2fs, derep %.2fs, order+flatten+index %.2fs, rounds %.2fs (+ .uc lines %.2fs), C records + centroids %.2fs\n",
+		  t_parsed - t_start, t_derep - t_parsed, t_ready - t_derep, t_rounds, t_loop - t_ready - t_rounds, now() - t_loop);
 	usb_searcher_free(Srch);
 	usb_index_free(Index);
 	return ClusterCount;

@@ -607,6 +607,150 @@ void OtuTabSink::OnAllDone()
 	fclose(f);
 }
 
+// ------------------------------------------------------------------ ClosedRefSink
+ClosedRefSink::ClosedRefSink(const std::string &TabbedOut, const std::string &DbOtus, const std::string &DataOtus)
+  : m_DbOtus(DbOtus), m_DataOtus(DataOtus)
+{
+	if (!TabbedOut.empty() && !(m_fTab = fopen(TabbedOut.c_str(), "wb")))
+		Die("Cannot create %s", TabbedOut.c_str());
+}
+
+ClosedRefSink::~ClosedRefSink() { OnAllDone(); }
+
+void ClosedRefSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
+{
+	const char *QueryLabel = Query.m_Label;
+	const unsigned Size = OtuTabSink::GetSizeFromLabel(QueryLabel, 1);
+	if (HM.m_Hits.empty()) {
+		if (m_fTab)
+			fprintf(m_fTab, "%s\t*\t*\t*\t*\t*\n", QueryLabel);
+		return;
+	}
+	// HitMgr::GetTopHit (hitmgr.cpp:400-420): best float score, ties to the lowest target index
+	const AlignResult *Top = &HM.m_Hits[0];
+	for (const AlignResult &AR : HM.m_Hits)
+		if ((float)AR.GetFractId() > (float)Top->GetFractId() ||
+		    ((float)AR.GetFractId() == (float)Top->GetFractId() && AR.GetTargetIndex() < Top->GetTargetIndex()))
+			Top = &AR;
+	const unsigned TopTargetIndex = Top->GetTargetIndex();
+	const double TopFractId = (float)HM.m_Hits[0].GetFractId(); // HitMgr::GetFractId(0): first in sorted order
+	if (TopTargetIndex >= m_RefSeqIndexToOTUIndex.size())
+		m_RefSeqIndexToOTUIndex.resize((size_t)TopTargetIndex + 1, UINT32_MAX);
+	unsigned OTUIndex = m_RefSeqIndexToOTUIndex[TopTargetIndex];
+	if (OTUIndex == UINT32_MAX) {
+		OTUIndex = (unsigned)m_OTUTotalSize.size();
+		m_RefSeqIndexToOTUIndex[TopTargetIndex] = OTUIndex;
+		m_OTUTotalSize.push_back(0);
+		m_OTUMemberCount.push_back(0);
+		m_RefLabels.push_back(Top->GetTargetLabel());
+		std::string stored;
+		if (m_Searcher)
+			m_Searcher->GetStoredTarget(TopTargetIndex, stored);
+		m_RefSeqs.push_back(stored);
+		m_DataLabels.push_back(QueryLabel);
+		m_DataSeqs.push_back(std::string((const char *)Query.m_Seq, Query.m_L));
+	}
+	m_OTUTotalSize[OTUIndex] += Size;
+	const unsigned MemberIndex = m_OTUMemberCount[OTUIndex]++;
+	unsigned Ties = 0;
+	std::string TiesStr;
+	if (HM.m_Hits.size() > 1)
+		for (const AlignResult &AR : HM.m_Hits) {
+			if ((double)(float)AR.GetFractId() < TopFractId)
+				break;
+			if (AR.GetTargetIndex() == TopTargetIndex)
+				continue;
+			if (Ties > 0)
+				TiesStr += ",";
+			TiesStr += AR.GetTargetLabel();
+			++Ties;
+		}
+	if (m_fTab) {
+		fprintf(m_fTab, "%s\t%u\t%u\t%s\t%.1f\tties=%u", QueryLabel, OTUIndex, MemberIndex, Top->GetTargetLabel(),
+		  TopFractId * 100.0, Ties);
+		if (Ties > 0)
+			fprintf(m_fTab, ":%s", TiesStr.c_str());
+		fputc('\n', m_fTab);
+	}
+}
+
+static void PsascStr(std::string &Str, const std::string &Tail) // myutils.cpp:824-839 Psasc
+{
+	if (!Str.empty() && Str.back() != ';')
+		Str += ';';
+	Str += Tail;
+	if (!Str.empty() && Str.back() != ';')
+		Str += ';';
+}
+
+static void WriteFasta80(FILE *f, const std::string &Label, const std::string &Seq) // seqdb.cpp:62-95 SeqToFasta
+{
+	if (!f || Seq.empty())
+		return;
+	fprintf(f, ">%s\n", Label.c_str());
+	for (size_t i = 0; i < Seq.size(); i += 80) {
+		fwrite(Seq.data() + i, 1, std::min<size_t>(80, Seq.size() - i), f);
+		fputc('\n', f);
+	}
+}
+
+// the reference's own (unstable) descending quicksort on unsigned keys (sort.h:63-102)
+static void QuickSortOrderDescU(const std::vector<unsigned> &v, std::vector<unsigned> &ord, int lo, int hi)
+{
+	int i = lo, j = hi;
+	const unsigned pivot = v[ord[(lo + hi) / 2]];
+	while (i <= j) {
+		while (v[ord[i]] > pivot)
+			++i;
+		while (v[ord[j]] < pivot)
+			--j;
+		if (i <= j) {
+			std::swap(ord[i], ord[j]);
+			++i;
+			--j;
+		}
+	}
+	if (lo < j)
+		QuickSortOrderDescU(v, ord, lo, j);
+	if (i < hi)
+		QuickSortOrderDescU(v, ord, i, hi);
+}
+
+void ClosedRefSink::OnAllDone()
+{
+	if (m_Done)
+		return;
+	m_Done = true;
+	if (m_fTab) {
+		fclose(m_fTab);
+		m_fTab = nullptr;
+	}
+	if (m_DbOtus.empty() && m_DataOtus.empty())
+		return;
+	const unsigned N = (unsigned)m_OTUTotalSize.size();
+	std::vector<unsigned> Order(N);
+	for (unsigned i = 0; i < N; ++i)
+		Order[i] = i;
+	if (N > 1)
+		QuickSortOrderDescU(m_OTUTotalSize, Order, 0, (int)N - 1);
+	FILE *fDb = m_DbOtus.empty() ? nullptr : fopen(m_DbOtus.c_str(), "wb");
+	FILE *fData = m_DataOtus.empty() ? nullptr : fopen(m_DataOtus.c_str(), "wb");
+	if ((!m_DbOtus.empty() && !fDb) || (!m_DataOtus.empty() && !fData))
+		Die("Cannot create %s", !fDb ? m_DbOtus.c_str() : m_DataOtus.c_str());
+	for (unsigned k = 0; k < N; ++k) {
+		const unsigned o = Order[k];
+		std::string OutRef = m_RefLabels[o], OutData = m_DataLabels[o];
+		PsascStr(OutRef, "otu=" + std::to_string(k + 1) + ";size=" + std::to_string(m_OTUTotalSize[o]) + ";");
+		PsascStr(OutData, "otu=" + std::to_string(k + 1) + ";ref=" + m_RefLabels[o]);
+		WriteFasta80(fDb, OutRef, m_RefSeqs[o]);
+		WriteFasta80(fData, OutData, m_DataSeqs[o]);
+	}
+	if (fDb)
+		fclose(fDb);
+	if (fData)
+		fclose(fData);
+}
+
 // ------------------------------------------------------------------ GpuSearcher
 GpuSearcher::GpuSearcher(int Device, const SeqDB &DB, const usb_params &P) : m_DB(DB), m_P(P)
 {
@@ -621,6 +765,14 @@ GpuSearcher::~GpuSearcher()
 }
 
 uint64_t GpuSearcher::GetLaunchCount() const { return usb_searcher_launch_count(m_Searcher); }
+
+void GpuSearcher::GetStoredTarget(uint32_t Target, std::string &Seq) const
+{
+	const uint8_t *p = nullptr;
+	uint32_t L = 0;
+	CheckUsb(usb_index_seq(m_Index, Target, &p, &L), "usb_index_seq");
+	Seq.assign((const char *)p, L);
+}
 
 void GpuSearcher::SetTargetAttrs(const uint32_t *LabelIds, const uint32_t *Sizes)
 {
@@ -816,6 +968,8 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		for (uint32_t i = 0; i < Q.GetSeqCount(); ++i)
 			q_size[i] = size_of(Q.GetLabel(i));
 	}
+	if (Opts.ClosedRef)
+		Opts.ClosedRef->SetSearcher(searchers[0]);
 	for (GpuSearcher *gs : searchers) {
 		gs->SetHitSelection(Opts.Sel);
 		if (!t_label.empty() || !t_size.empty()) {

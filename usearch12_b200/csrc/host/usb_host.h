@@ -195,6 +195,29 @@ private:
 	  bool &Added);
 };
 
+class GpuSearcher;
+
+// -closed_ref (closedrefsink.cpp:34-165): every query goes to the reference sequence of its top hit;
+// the reference sequences that were hit become OTUs numbered in order of first use.  -tabbedout gets
+// one line per query, -dbotus / -dataotus the OTUs' reference sequences (as stored in the database,
+// i.e. masked) and first member reads in decreasing size order.
+class ClosedRefSink : public HitSink {
+public:
+	ClosedRefSink(const std::string &TabbedOut, const std::string &DbOtus, const std::string &DataOtus);
+	~ClosedRefSink() override;
+	void SetSearcher(const GpuSearcher *S) { m_Searcher = S; }
+	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
+	void OnAllDone() override;
+
+private:
+	const GpuSearcher *m_Searcher = nullptr;
+	FILE *m_fTab = nullptr;
+	std::string m_DbOtus, m_DataOtus;
+	bool m_Done = false;
+	std::vector<unsigned> m_RefSeqIndexToOTUIndex, m_OTUTotalSize, m_OTUMemberCount;
+	std::vector<std::string> m_RefLabels, m_RefSeqs, m_DataLabels, m_DataSeqs;
+};
+
 // Abstract searcher (searcher.h:21-96), batched.
 class Searcher {
 public:
@@ -224,6 +247,8 @@ public:
 		m_QSizes = Sizes;
 	}
 	void SetTargetAttrs(const uint32_t *LabelIds, const uint32_t *Sizes);
+	// letters of a target as the index stores them (masked), usb_index_seq
+	void GetStoredTarget(uint32_t Target, std::string &Seq) const;
 
 private:
 	HitSelection m_Sel;
@@ -238,6 +263,7 @@ struct SearchOpts {
 	usb_params P;
 	OutputOpts Out;
 	std::vector<HitSink *> ExtraSinks; // run after the OutputSink for every batch (not owned)
+	ClosedRefSink *ClosedRef = nullptr; // one of ExtraSinks: gets the searcher for the stored target letters
 	int gpus = 1;
 	uint32_t batch = 1u << 18;
 	bool quiet = false;

@@ -120,12 +120,31 @@ int main(int argc, char **argv)
 	std::string query = take("usearch_global", nullptr);
 	const std::string lquery = take("usearch_local", nullptr);
 	const std::string oquery = take("otutab", nullptr);
+	const std::string cquery = take("closed_ref", nullptr);
+	std::unique_ptr<ClosedRefSink> crsink;
+	if (query.empty() && lquery.empty() && oquery.empty() && !cquery.empty()) {
+		// searchcmd.cpp:11-19 cmd_closed_ref: -id 0.97 and -stepwords 0 unless given, Terminator 4 / 16
+		// (terminator.cpp:16-20), GlobalAligner, ClosedRefSink behind the OutputSink
+		query = cquery;
+	}
 	if (query.empty() && lquery.empty() && oquery.empty())
 		Die("No command: this build implements -usearch_global, -usearch_local, -otutab, -cluster_fast and -makeudb_usearch");
 	std::string db = take("db", nullptr);
 	std::string id = take("id", nullptr);
+	if (!cquery.empty()) {
+		if (id.empty())
+			id = "0.97";
+		O.P.stepwords = 0;
+		crsink.reset(new ClosedRefSink(take("tabbedout", nullptr), take("dbotus", nullptr), take("dataotus", nullptr)));
+		O.ExtraSinks.push_back(crsink.get());
+		O.ClosedRef = crsink.get();
+	}
 	std::unique_ptr<OtuTabSink> otusink;
 	const char *dflt_strand = nullptr, *dflt_ma = "1", *dflt_mr = "32";
+	if (!cquery.empty()) { // terminator.cpp:16-20
+		dflt_ma = "4";
+		dflt_mr = "16";
+	}
 	if (!oquery.empty()) {
 		// searchcmd.cpp:21-40 cmd_otutab: defaults, then the OTU FASTA from -db, -otus or -zotus
 		query = oquery;

@@ -57,7 +57,7 @@ extern "C" const char *usb_last_error(void) { return g_err.c_str(); }
 // thread of the process: it is tracked here under one mutex and the dynamic shared-memory limit is
 // only ever raised.  The mutex is held across "set attribute + launch" so that a launch never sees
 // a limit or carve-out another thread chose.
-enum { FN_RANK_F, FN_RANK_T, FN_RANK_BIG, FN_ALIGN_NT, FN_ALIGN_AA, FN_VITERBI, FN_LOCAL, FN_GATE, FN_DP, FN_COUNT };
+enum { FN_RANK_F, FN_RANK_T, FN_RANK_BIG, FN_ALIGN_NT, FN_ALIGN_AA, FN_VITERBI, FN_LOCAL, FN_GATE, FN_DP, FN_CONFLICT, FN_COUNT };
 static std::mutex g_attr_mu;
 static size_t g_attr_smem[64][FN_COUNT];
 static int g_attr_carve[64][FN_COUNT];
@@ -573,7 +573,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
 	ix->n_dev = n0 + n;
 	if (ix->P.is_nucleo) {
-		const size_t w0 = (size_t)(b0 / 16) + 2 * (size_t)n0, w1 = (size_t)(b1 / 16) + 2 * ((size_t)n0 + n);
+		const size_t w0 = n0 ? (size_t)pack_words(b0, n0) : 0, w1 = (size_t)pack_words(b1, (uint64_t)n0 + n);
 		if ((rc = ix->d_db2.grow_keep(w1 + 4, w0)) || (rc = ix->d_dbn.grow_keep(w1 + 4, w0)) ||
 		    (rc = ix->d_wild.grow_keep((size_t)n0 + n + 1, n0)))
 			return rc;
@@ -1383,7 +1383,7 @@ static bool stage_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, ui
 	g.g_tw = up4(g.tl_cap / 16 + 2);
 	g.g_start_bytes = pad16(2 * (s->D.hsp_words + 2));
 	g.g_q1_bytes = std::max<uint32_t>(pad16(4 * GATE_Q1), pad16(s->D.hsp_words));
-	g.g_bytes = 8 * g.g_qw + 8 * g.g_tw + g.g_start_bytes + pad16(2 * g.ql_cap) + g.g_q1_bytes + pad16(2 * GATE_Q1) +
+	g.g_bytes = 8 * g.g_qw + 12 * g.g_tw + 16 + g.g_start_bytes + pad16(2 * g.ql_cap) + g.g_q1_bytes + pad16(2 * GATE_Q1) +
 	            4 * GATE_Q2 + pad16(2 * GATE_Q2);
 	g.g_wpb = (uint32_t)std::min<size_t>(GATE_MAX_WARPS, budget / g.g_bytes);
 	if (g.g_wpb < 4)

@@ -34,7 +34,7 @@ namespace usb {
 #define STAGE_MAX 20          // stages per batch: [0,1), then ranges of STAGE_WIDTH candidates
 #define STAGE_WIDTH 64
 #define GATE_MAX_WARPS 32
-#define GATE_Q1 512           // flat seed queue (ring, power of two): < 32 waiting + at most 8 x 32 per slow scan step
+#define GATE_Q1 256           // flat seed queue (ring, power of two): < 32 waiting + at most 8 x 16 per slow scan step
 #define GATE_Q2 64            // survivors of the pre-filter waiting for a full batch of walks
 #define DP_MAX_WARPS 16
 
@@ -74,8 +74,15 @@ struct StageArgs {
 
 // ------------------------------------------------------------------ packed database
 // word offset of target t in db2 / dbn: one word per 16 letters (targets are padded to 16 letters)
-// plus two zero words behind every target for ext16's look-ahead
-__host__ __device__ inline uint64_t pack_off(const uint64_t *db_off, uint32_t t) { return db_off[t] / 16 + 2ull * t; }
+// plus two zero words behind every target for ext16's look-ahead, rounded up to 16 bytes so that a
+// packed target can be fetched with one bulk copy (cp.async.bulk needs 16-byte aligned addresses).
+// Target t occupies [off, off + n16 + 2); off(t + 1) >= off(t) + n16 + 3.
+__host__ __device__ inline uint64_t pack_off(const uint64_t *db_off, uint32_t t)
+{
+	return (db_off[t] / 16 + 6ull * t + 3) & ~3ull;
+}
+// words of db2 / dbn that hold n targets ending at letter offset end_off
+__host__ __device__ inline uint64_t pack_words(uint64_t end_off, uint64_t n) { return end_off / 16 + 6 * n + 16; }
 
 // One warp per target: 2-bit letters (wildcards as 0) and wildcard flags (bit 0 of each pair).
 __global__ void k_pack_targets(const uint8_t *db_seq, const uint64_t *db_off, const uint32_t *db_len, uint32_t t0, uint32_t n,
@@ -228,6 +235,10 @@ struct GateWs {
 	uint16_t *q1a;
 	uint32_t *q2b;
 	uint16_t *q2a;
+	uint32_t *B2base;      // two packed-target buffers filled by bulk copies: B2base + b * B2words
+	uint32_t B2words;
+	uint64_t *bar;         // their mbarriers
+	uint32_t phase;        // bit b: parity barrier b completes next
 	const uint8_t *Qraw;   // raw letters of the query (global), for wildcard identities
 	uint32_t strand;
 	bool wild;             // query or target holds a letter outside ACGTU
@@ -260,18 +271,63 @@ __device__ __forceinline__ bool gate_load_query(GateWs &g, const uint8_t *Q, uin
 	return __any_sync(USB_FULL, wild);
 }
 
-__device__ __forceinline__ void gate_load_target(const StageArgs &S, GateWs &g, uint32_t t, bool twild)
+// ---- TMA staging of the packed targets: one lane arms the warp's mbarrier with the byte count
+// and issues a bulk copy global -> shared (cp.async.bulk, SASS UBLKCP); the warp waits on the
+// barrier's phase before it reads the buffer.  Two buffers per warp: the next candidate's letters
+// are in flight while the current one is searched.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "WAIT_%=:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra DONE_%=;\n"
+	             "bra WAIT_%=;\n"
+	             "DONE_%=:\n"
+	             "}" ::"r"(smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+
+// starts the copy of target t's packed letters into buffer b (lane 0 issues it)
+__device__ __forceinline__ void gate_prefetch_target(const StageArgs &S, GateWs &g, uint32_t t, uint32_t b)
+{
+	if (lane_id() == 0) {
+		const uint32_t nw = ((S.A.db_len[t] + 15) / 16 + 2 + 3) & ~3u; // whole 16-byte units (the arrays are padded)
+		tma_load_1d(g.B2base + b * g.B2words, S.db2 + pack_off(S.A.db_off, t), 4 * nw, g.bar + b);
+	}
+}
+
+// waits for buffer b (filled by gate_prefetch_target for target t) and makes it the current target
+__device__ __forceinline__ void gate_take_target(const StageArgs &S, GateWs &g, uint32_t t, uint32_t b, bool twild)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t L = S.A.db_len[t];
-	const uint64_t o = pack_off(S.A.db_off, t);
-	const uint32_t nw = (L + 15) / 16 + 2;
+	mbar_wait(g.bar + b, (g.phase >> b) & 1u);
+	g.phase ^= 1u << b;
+	g.w.B2 = g.B2base + b * g.B2words;
 	g.w.B = S.A.db_seq + S.A.db_off[t];
-	for (uint32_t k = lane; k < nw; k += 32)
-		g.w.B2[k] = __ldg(S.db2 + o + k);
-	if (twild)
+	if (twild) {
+		const uint64_t o = pack_off(S.A.db_off, t);
+		const uint32_t nw = (L + 15) / 16 + 2;
 		for (uint32_t k = lane; k < nw; k += 32)
 			g.w.Bn2[k] = __ldg(S.dbn + o + k);
+	}
 	g.w.LB = L;
 	__syncwarp();
 }
@@ -482,11 +538,11 @@ template <bool WILD> __device__ uint32_t gate_ungapped(const StageArgs &S, GateW
 			__syncwarp();
 			drain(false);
 		} else {
-			// a low-complexity stretch (up to 8 seeds per position): 32 positions at a time
-			for (uint32_t r = 0; r < 4; ++r) {
-				const uint32_t bpos = scan + 32 * r + lane;
+			// a low-complexity stretch (up to 8 seeds per position): 16 positions at a time
+			for (uint32_t r = 0; r < 8; ++r) {
+				const uint32_t bpos = scan + 16 * r + lane;
 				uint32_t n1 = 0, s1 = 0;
-				if (bpos < nwordsB) {
+				if (lane < 16 && bpos < nwordsB) {
 					const uint32_t word = hsp_word_at(w.B2, bpos, HW);
 					s1 = g.start[word];
 					n1 = (uint32_t)g.start[word + 1] - s1;
@@ -596,8 +652,12 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 		uint8_t *p = stage_smem + (size_t)warp * S.g_bytes;
 		g.w.A2 = (uint32_t *)p; p += 4 * S.g_qw;
 		g.w.An2 = (uint32_t *)p; p += 4 * S.g_qw;
-		g.w.B2 = (uint32_t *)p; p += 4 * S.g_tw;
+		g.B2base = (uint32_t *)p; p += 8 * S.g_tw;
+		g.B2words = S.g_tw;
+		g.w.B2 = g.B2base;
 		g.w.Bn2 = (uint32_t *)p; p += 4 * S.g_tw;
+		g.bar = (uint64_t *)p; p += 16;
+		g.phase = 0;
 		g.start = (uint16_t *)p; p += S.g_start_bytes;
 		g.pos = (uint16_t *)p; p += pad16(2 * a.ql_cap);
 		g.q1b = (uint32_t *)p; p += S.g_q1_bytes;
@@ -614,6 +674,12 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 		// the wildcard arrays are only read when a wildcard is present; keep them defined anyway
 		for (uint32_t k = lane; k < S.g_tw; k += 32)
 			g.w.Bn2[k] = 0;
+		if (lane == 0) {
+			mbar_init(g.bar, 1);
+			mbar_init(g.bar + 1, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		__syncwarp();
 	}
 	const bool pairs = a.pair_q != nullptr;
 	const uint32_t n_items = S.items ? S.sc->st[S.stage].n_items : a.n_jobs;
@@ -640,14 +706,32 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 				gate_seed_table(S, g);
 			cur_job = job;
 		}
+		// the packed letters of candidate k + 1 are fetched while candidate k is searched; a
+		// candidate whose pair is rejected beforehand (Accepter::RejectPair) is fetched all the same
+		auto target_of = [&](uint32_t k) { return pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k]; };
+		const bool stage_targets = !a.P.fulldp;
+		uint32_t buf = 0;
+		if (stage_targets)
+			gate_prefetch_target(S, g, target_of(k0), buf);
 		for (uint32_t k = k0; k < k1; ++k) {
-			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			const uint32_t t = target_of(k);
+			const uint32_t cur = buf;
+			if (stage_targets) {
+				buf ^= 1u;
+				__syncwarp(); // every lane is done with the other buffer (the candidate before this one)
+				if (k + 1 < k1)
+					gate_prefetch_target(S, g, target_of(k + 1), buf);
+			}
 			if (a.P.accept_flags & ACC_PAIR_FLAGS) {
 				const uint64_t q0 = a.q_off[qi];
 				if (reject_pair(a, qi, strand, t, a.q + q0, (uint32_t)(a.q_off[qi + 1] - q0))) {
 					// skipped without a Terminator call, or counted as a reject on the big-database path
 					if (lane == 0)
 						S.verdict[(uint64_t)job * a.k_max + (pairs ? 0u : k)] = a.P.reject_pair_counts ? 1u : 3u;
+					if (stage_targets) { // consume the buffer's phase
+						mbar_wait(g.bar + cur, (g.phase >> cur) & 1u);
+						g.phase ^= 1u << cur;
+					}
 					continue;
 				}
 			}
@@ -657,7 +741,7 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 				g.w.LB = a.db_len[t];
 				pass = (g.w.LA == 0 || g.w.LB == 0) ? 0u : 1u;
 			} else {
-				gate_load_target(S, g, t, twild);
+				gate_take_target(S, g, t, cur, twild);
 				g.wild = qwild || twild;
 				pass = g.wild ? gate_pair<true>(S, g, nchain) : gate_pair<false>(S, g, nchain);
 				if (twild) { // leave the wildcard array clean for the next target
