@@ -45,3 +45,62 @@ def test_otutab_needs_an_otu_database(tmp_path):
     cli = build.build_cli()
     r = subprocess.run([cli, "-otutab", "x.fa", "-otutabout", "t.txt"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "Must specify OTU FASTA -db, -otus or -zotus" in r.stdout
+
+
+def test_closed_ref_sink_follows_the_reference_source(tmp_path):
+    """-closed_ref (searchcmd.cpp:11-19, closedrefsink.cpp:34-165).  PARITY UNPINNED: both reference
+    binaries (the one built here and the prebuilt tmp/usearch_linux_x86_12.0-beta) crash with SIGSEGV on
+    -closed_ref, so there are no golden files; the sink is checked against a restatement of
+    ClosedRefSink::OnQueryDone / OnAllDone applied to the hit lists of the same run (-userout)."""
+    import numpy as np
+    cli = build.build_cli()
+    db = _gunzip("acc_db.fa.gz", str(tmp_path / "db.fa"))
+    q = _gunzip("acc_q.fa.gz", str(tmp_path / "q.fa"))
+    out = {k: str(tmp_path / k) for k in ("tab", "dbotus", "dataotus", "user")}
+    r = subprocess.run([cli, "-closed_ref", q, "-db", db, "-strand", "both", "-id", "0.9", "-quiet", "-tabbedout", out["tab"],
+                        "-dbotus", out["dbotus"], "-dataotus", out["dataotus"], "-userout", out["user"], "-userfields",
+                        "query+target+ids+alnlen+clusternr"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    ql, qs = util.read_fasta(q)
+    hits = {}
+    for line in open(out["user"]).read().splitlines():      # HitMgr order per query
+        qq, t, ids, aln, ti = line.split("\t")
+        hits.setdefault(qq, []).append((t, np.float32(int(ids) / int(aln)), int(ti)))
+    want, otu_of, totals, members = [], {}, [], []
+    for qq in ql:
+        h = hits.get(qq)
+        if not h:
+            want.append("%s\t*\t*\t*\t*\t*" % qq)
+            continue
+        top = h[0]
+        for x in h:                                            # GetTopHit: best score, ties to the lowest target index
+            if x[1] > top[1] or (x[1] == top[1] and x[2] < top[2]):
+                top = x
+        if top[2] not in otu_of:
+            otu_of[top[2]] = len(totals)
+            totals.append(0)
+            members.append(0)
+        o = otu_of[top[2]]
+        totals[o] += int(qq.split(";size=")[1].split(";")[0]) if ";size=" in qq else 1
+        m = members[o]
+        members[o] += 1
+        ties = []
+        if len(h) > 1:
+            for x in h:
+                if x[1] < h[0][1]:
+                    break
+                if x[2] != top[2]:
+                    ties.append(x[0])
+        line = "%s\t%d\t%d\t%s\t%.1f\tties=%d" % (qq, o, m, top[0], float(h[0][1]) * 100.0, len(ties))
+        want.append(line + (":" + ",".join(ties) if ties else ""))
+    got = open(out["tab"]).read().splitlines()
+    assert util.first_diff(got, want) is None
+    assert len(totals) > 50
+    # OTU files: every OTU once, labels ...otu=<rank>;size=<total>; in decreasing size order
+    dl, _ = util.read_fasta(out["dbotus"])
+    al, _ = util.read_fasta(out["dataotus"])
+    assert len(dl) == len(totals) == len(al)
+    sizes = [int(x.rstrip(";").split(";size=")[-1]) for x in dl]
+    assert sizes == sorted(sizes, reverse=True) and sorted(sizes) == sorted(totals)
+    for k, (d, a_) in enumerate(zip(dl, al)):
+        assert ";otu=%d;" % (k + 1) in d and ";otu=%d;ref=" % (k + 1) in a_
