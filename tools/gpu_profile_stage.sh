@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-legs > gpurun_out/ncu_launch_$T.log 2>&1; echo "list rc=$?"
 for k in $K; do
   case $k in
-    gate) ncu --set full --clock-control none --import-source on -k regex:k_gate -s 7 -c 1 -f -o gpurun_out/prof_gate_$T \
+    gate) ncu --set full --clock-control none --import-source on -k regex:k_gate -s 6 -c 2 -f -o gpurun_out/prof_gate_$T \
             python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-legs > gpurun_out/ncu_gate_$T.log 2>&1; echo "gate rc=$?";;
     dp)   ncu --set full --clock-control none --import-source on -k regex:k_dp -s 6 -c 2 -f -o gpurun_out/prof_dp_$T \
             python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-legs > gpurun_out/ncu_dp_$T.log 2>&1; echo "dp rc=$?";;

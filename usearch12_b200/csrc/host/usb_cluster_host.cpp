@@ -258,7 +258,11 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	uint32_t B = 256;
 	uint64_t rounds = 0;
 	while (pos < UniqueCount) {
-		const uint32_t n = std::min<uint32_t>(B, UniqueCount - pos);
+		// While the database is below -big the round's conflict scan runs on the host over every word
+		// of the block (the big-database path samples ~10 words per query and scans on the device):
+		// keep those blocks small.
+		const uint32_t cap = ClusterSizes.size() <= Opts.P.big ? std::min<uint32_t>(Opts.max_block, 4096) : Opts.max_block;
+		const uint32_t n = std::min<uint32_t>(std::min(B, cap), UniqueCount - pos);
 		cidx.resize(n);
 		uint32_t ncom = 0;
 		usb_result *R = nullptr;
