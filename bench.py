@@ -421,7 +421,7 @@ def main():
     HB = capi.HIT_DTYPE.itemsize
     cap_hits = a.reads * max(1, p.maxaccepts)
     gather_src = torch.zeros(cap_hits * HB, dtype=torch.uint8, device="cuda") if world > 1 else None
-    gather_dst = torch.zeros((cap_hits + 1024 * world) * HB, dtype=torch.uint8, device="cuda") \
+    gather_dst = torch.zeros(cap_hits * world * HB, dtype=torch.uint8, device="cuda") \
         if world > 1 and rank == 0 else None
     counts_dev = torch.zeros(world, dtype=torch.int64, device="cuda") if world > 1 else None
 
