@@ -2391,6 +2391,57 @@ static void search_strand(uso_searcher *s, uint32_t qindex, const uint8_t *q, ui
 	free(path);
 	}
 
+/* Candidate order of UDBSearchBig (udbusortedsearcherbig.cpp:82-135) without the alignments:
+ * sampled words, first-touch list, CountSortSubsetDesc.  For tests of the ranking kernel. */
+unsigned uso_rank_candidates_big(uso_searcher *s, const uint8_t *q, uint32_t L, uint32_t *cand_t, uint32_t *cand_u)
+	{
+	uso_db *db = s->db;
+	const unsigned N = db->n;
+	if (N == 0)
+		return 0;
+	use_alpha(&s->P);
+	alloc_query(s, L);
+	unsigned nu = unique_words(q, L, s->P.word_length, s->found, s->qw, s->quw);
+	unsigned MinU, Step;
+	word_counting_params(s, nu, &MinU, &Step);
+	if (s->Ucap < N)
+		{
+		uint32_t nc = ((N + 65536 + 65535) / 65536) * 65536;
+		s->U = (uint32_t *) xrealloc(s->U, nc * sizeof(uint32_t));
+		memset(s->U, 0, nc * sizeof(uint32_t));
+		s->Ucap = nc;
+		}
+	else
+		memset(s->U, 0, s->Ucap * sizeof(uint32_t));
+	alloc_top(s, N);
+	uint32_t *U = s->U;
+	unsigned top = 0, top2 = 0;
+	for (unsigned i = 0; i < nu; i += Step)
+		{
+		uint32_t w = s->quw[i];
+		const uint32_t *row = db->rows[w];
+		unsigned size = db->sizes[w];
+		for (unsigned j = 0; j < size; ++j)
+			{
+			uint32_t t = row[j];
+			if (U[t] == 0)
+				s->TopT[top++] = t;
+			++U[t];
+			}
+		}
+	if (top > 0)
+		top2 = count_sort_subset_desc(s, U, top, s->TopT, s->TopT2);
+	for (unsigned k = 0; k < top2; ++k)
+		{
+		if (cand_t) cand_t[k] = s->TopT2[k];
+		if (cand_u) cand_u[k] = U[s->TopT2[k]];
+		}
+	for (unsigned i = 0; i < top; ++i)
+		U[s->TopT[i]] = 0;
+	s->ntop_prev = 0;
+	return top2;
+	}
+
 /* sort.h:63-102,132 QuickSortOrderDesc<float> -- the reference's own (unstable) quicksort,
  * restated with an explicit stack; partition scheme and recursion order (left part first)
  * are what determine the tie order. */

@@ -100,6 +100,8 @@ unsigned uso_query_unique_words(const uso_params *p, const uint8_t *q, uint32_t 
  * cand_t/cand_u hold up to seq_count entries.  Returns candidate count (TopOrder.Size). */
 unsigned uso_rank_candidates(uso_searcher *s, const uint8_t *q, uint32_t L, uint32_t *U,
   uint32_t *cand_t, uint32_t *cand_u);
+/* the same for the big-database path (udbusortedsearcherbig.cpp:82-135); cand_* sized db n */
+unsigned uso_rank_candidates_big(uso_searcher *s, const uint8_t *q, uint32_t L, uint32_t *cand_t, uint32_t *cand_u);
 /* a10..a12: ungapped + chained HSPs for (q, target).  Arrays hold up to max_hsp entries of
  * {Loi, Loj, Len, score*2 (int)}; returns chained count, *n_ungapped set, *hsp_fract_id set. */
 unsigned uso_global_hsps(uso_searcher *s, const uint8_t *q, uint32_t LQ, const uint8_t *t, uint32_t LT,

@@ -80,6 +80,8 @@ def lib():
         L.uso_hits_free.argtypes = [C.POINTER(Hit), C.c_uint]
         L.uso_rank_candidates.argtypes = [vp, C.c_char_p, C.c_uint32, vp, vp, vp]
         L.uso_rank_candidates.restype = C.c_uint
+        L.uso_rank_candidates_big.argtypes = [vp, C.c_char_p, C.c_uint32, vp, vp]
+        L.uso_rank_candidates_big.restype = C.c_uint
         L.uso_global_hsps.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, vp, C.POINTER(C.c_uint), vp,
                                       C.c_uint, C.POINTER(C.c_float)]
         L.uso_global_hsps.restype = C.c_uint
@@ -203,6 +205,15 @@ class Searcher:
         cu = np.zeros(max(N, 1), np.uint32)
         k = lib().uso_rank_candidates(self.h, s, len(s), U.ctypes.data, ct.ctypes.data, cu.ctypes.data)
         return U[:N], ct[:k], cu[:k]
+
+    def rank_big(self, seq):
+        """Candidate order of the big-database path -> (targets, U)."""
+        s = _b(seq)
+        N = self.db.n
+        ct = np.zeros(max(N, 1), np.uint32)
+        cu = np.zeros(max(N, 1), np.uint32)
+        k = lib().uso_rank_candidates_big(self.h, s, len(s), ct.ctypes.data, cu.ctypes.data)
+        return ct[:k], cu[:k]
 
     def global_hsps(self, q, t, max_hsp=256):
         q, t = _b(q), _b(t)

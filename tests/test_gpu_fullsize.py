@@ -115,3 +115,32 @@ def test_oracle_spot_check_on_the_full_database(full):
         for k, w in enumerate(want):
             h = res.hits[b + k]
             assert int(h["target"]) == w["target"] and int(h["ids"]) == w["ids"] and res.path(h) == w["path"], qi
+
+
+def test_first_20000_reads_identical_to_the_reference_binary(full, tmp_path):
+    """The unmodified reference binary (oracle/_ref/usearch12, built by oracle/Makefile.ref; it travels
+    with the repository) searches the first 20 000 reads against the same 100 k-target database; the
+    command line of this repository must write the same .uc and .b6 bytes (search.cpp:63-86 ->
+    outputuc.cpp:45-93, blast6out.cpp:27-80)."""
+    import subprocess
+    import synth_np
+    from usearch12_b200 import build
+    ref = os.path.join(util.ROOT, "oracle", "_ref", "usearch12")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/usearch12 not built (python __graft_entry__.py builds it where /root/reference exists)")
+    n = min(20000, N_READS)
+    dbfa, qfa = str(tmp_path / "db.fa"), str(tmp_path / "q.fa")
+    synth_np.write_fasta(dbfa, full["db"], full["db_off"], "db")
+    synth_np.write_fasta(qfa, full["reads"], full["r_off"], "q", 0, n)
+    out = {}
+    for name, exe in (("ref", ref), ("usb", build.build_cli())):
+        uc, b6 = str(tmp_path / (name + ".uc")), str(tmp_path / (name + ".b6"))
+        cmd = [exe, "-usearch_global", qfa, "-db", dbfa, "-id", "0.97", "-strand", "plus", "-uc", uc, "-blast6out", b6, "-quiet"]
+        if name == "ref":
+            cmd += ["-threads", "1"]  # one thread: the binary writes hits in the order its threads finish
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        out[name] = (open(uc, "rb").read(), open(b6, "rb").read())
+    assert len(out["ref"][0].splitlines()) == n
+    assert out["usb"][0] == out["ref"][0], "uc"
+    assert out["usb"][1] == out["ref"][1], "b6"
+    assert len(out["ref"][1]) > 0

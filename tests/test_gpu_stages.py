@@ -169,3 +169,33 @@ def test_big_database_path_matches_oracle(env, big, id_, stepwords):
     for a, b, kind in zip(got, want, ("user", "uc", "b6")):
         assert util.first_diff(a, b) is None, kind
     assert len(got[0]) > 50
+
+
+@pytest.mark.parametrize("stepwords", [0, 8])
+def test_big_path_with_more_survivors_than_slots(env, stepwords):
+    """UDBSearchBig on a database where thousands of targets pass U >= NextValue/2 (queries without a
+    close target: NextValue is 1 or 2): the first k_max of (U descending, first-touch order) are
+    selected by the histogram of the survivor pass, ties at the cut row by row
+    (udbusortedsearcherbig.cpp:82-135, countsort.cpp:110-191)."""
+    capi, O = env["capi"], env["O"]
+    rng = random.Random(77 + stepwords)
+    db = ["".join(rng.choice("ACGT") for _ in range(300)) for _ in range(60000)]
+    p = capi.default_params(big=1000, stepwords=stepwords)
+    ix = capi.Index(db, p)
+    s = capi.Searcher(ix, p)
+    op = O.default_params(big=1000, stepwords=stepwords)
+    osr = O.Searcher(O.DB(db, op), op)
+    qs = ["".join(rng.choice("ACGT") for _ in range(250)) for _ in range(12)]
+    qs += [util.mutate(db[rng.randrange(len(db))][20:270], r, rng) for r in (0.0, 0.02, 0.05, 0.1, 0.2, 0.3) for _ in range(3)]
+    qs += ["ACGT" * 60, "A" * 100 + "".join(rng.choice("ACGT") for _ in range(150))]
+    n_many = 0
+    for K in (33, 200):
+        ct, cu, nc, _ = s.rank(qs, K)
+        for j, q in enumerate(qs):
+            oct, ocu = osr.rank_big(q)
+            assert nc[j] == len(oct), (K, j, nc[j], len(oct))
+            k = min(K, len(oct))
+            assert np.array_equal(ct[j, :k], oct[:k]), (K, j, ct[j, :k][:12], oct[:12])
+            assert np.array_equal(cu[j, :k], ocu[:k]), (K, j)
+            n_many += len(oct) > 1024
+    assert n_many >= 20

@@ -18,6 +18,8 @@
 #include "usb_host.h"
 
 #include <chrono>
+#include <thread>
+#include <cstring>
 
 namespace usbhost {
 
@@ -82,13 +84,30 @@ static void DerepFullHost(const SeqDB &Input, std::vector<unsigned> &UniqOf, std
 	while (nb < 2 * (size_t)SeqCount + 16)
 		nb <<= 1;
 	std::vector<int> bucket(nb, -1);
+	// hashes of all sequences first (threads), then the order-dependent insertion
+	std::vector<uint32_t> Hash(SeqCount);
+	{
+		const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		std::vector<std::thread> th;
+		for (unsigned k = 0; k < T; ++k)
+			th.emplace_back([&, k]() {
+				const unsigned a = (unsigned)((uint64_t)SeqCount * k / T), b = (unsigned)((uint64_t)SeqCount * (k + 1) / T);
+				for (unsigned i = a; i < b; ++i) {
+					const uint8_t *s = Input.GetSeq(i);
+					const unsigned L = Input.GetSeqLength(i);
+					uint32_t h = 2166136261u;
+					for (unsigned j = 0; j < L; ++j)
+						h = (h ^ (uint32_t)toupper(s[j])) * 16777619u;
+					Hash[i] = h;
+				}
+			});
+		for (auto &t : th)
+			t.join();
+	}
 	for (unsigned i = 0; i < SeqCount; ++i) {
 		const uint8_t *s = Input.GetSeq(i);
 		const unsigned L = Input.GetSeqLength(i);
-		uint32_t h = 2166136261u;
-		for (unsigned k = 0; k < L; ++k)
-			h = (h ^ (uint32_t)toupper(s[k])) * 16777619u;
-		size_t b = h & (nb - 1);
+		size_t b = Hash[i] & (nb - 1);
 		for (;;) {
 			if (bucket[b] < 0) {
 				bucket[b] = (int)First.size();
@@ -98,7 +117,7 @@ static void DerepFullHost(const SeqDB &Input, std::vector<unsigned> &UniqOf, std
 				break;
 			}
 			const unsigned f = First[bucket[b]];
-			bool eq = Input.GetSeqLength(f) == L;
+			bool eq = Input.GetSeqLength(f) == L && Hash[f] == Hash[i];
 			const uint8_t *t = Input.GetSeq(f);
 			for (unsigned k = 0; eq && k < L; ++k)
 				eq = toupper(s[k]) == toupper(t[k]);
@@ -195,6 +214,15 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	const bool timing = getenv("USB_TIMING") != nullptr;
 	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t_start = now();
+	// the device context, the (empty) index and the searcher come up while the host reads the input
+	usb_index *Index = nullptr;
+	usb_searcher *Srch = nullptr;
+	std::thread device_up([&]() {
+		uint64_t zero_off[1] = {0};
+		uint8_t none = 0;
+		CheckUsb2(usb_index_create(0, &Opts.P, &none, zero_off, 0, &Index), "usb_index_create");
+		CheckUsb2(usb_searcher_create(Index, &Opts.P, &Srch), "usb_searcher_create");
+	});
 	SeqDB Input;
 	Input.FromFasta(ReadsFileName);
 	const unsigned SeqCount = Input.GetSeqCount();
@@ -232,19 +260,25 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		Die("-cluster_fast does not support -sort other, use -cluster_smallmem");
 
 	// uniques in cluster order, flattened
-	std::vector<uint8_t> Letters;
-	std::vector<uint64_t> Off(1, 0);
-	for (unsigned k = 0; k < UniqueCount; ++k) {
-		const unsigned r = First[Order[k]];
-		Letters.insert(Letters.end(), Input.GetSeq(r), Input.GetSeq(r) + Input.GetSeqLength(r));
-		Off.push_back(Letters.size());
+	std::vector<uint64_t> Off(UniqueCount + 1, 0);
+	for (unsigned k = 0; k < UniqueCount; ++k)
+		Off[k + 1] = Off[k] + Input.GetSeqLength(First[Order[k]]);
+	std::vector<uint8_t> Letters(Off[UniqueCount] + 16);
+	{
+		const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		std::vector<std::thread> th;
+		for (unsigned j = 0; j < T; ++j)
+			th.emplace_back([&, j]() {
+				const unsigned a = (unsigned)((uint64_t)UniqueCount * j / T), b = (unsigned)((uint64_t)UniqueCount * (j + 1) / T);
+				for (unsigned k = a; k < b; ++k) {
+					const unsigned r = First[Order[k]];
+					memcpy(Letters.data() + Off[k], Input.GetSeq(r), Input.GetSeqLength(r));
+				}
+			});
+		for (auto &t : th)
+			t.join();
 	}
-
-	usb_index *Index = nullptr;
-	usb_searcher *Srch = nullptr;
-	uint64_t zero_off[1] = {0};
-	CheckUsb2(usb_index_create(0, &Opts.P, Letters.data(), zero_off, 0, &Index), "usb_index_create");
-	CheckUsb2(usb_searcher_create(Index, &Opts.P, &Srch), "usb_searcher_create");
+	device_up.join();
 
 	const double t_ready = now();
 	double t_rounds = 0;
@@ -258,10 +292,7 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	uint32_t B = 256;
 	uint64_t rounds = 0;
 	while (pos < UniqueCount) {
-		// While the database is below -big the round's conflict scan runs on the host over every word
-		// of the block (the big-database path samples ~10 words per query and scans on the device):
-		// keep those blocks small.
-		const uint32_t cap = ClusterSizes.size() <= Opts.P.big ? std::min<uint32_t>(Opts.max_block, 4096) : Opts.max_block;
+		const uint32_t cap = Opts.max_block;
 		const uint32_t n = std::min<uint32_t>(std::min(B, cap), UniqueCount - pos);
 		cidx.resize(n);
 		uint32_t ncom = 0;

@@ -259,6 +259,42 @@ struct IndexSegment {
 	}
 };
 
+// USB_TIMING=1: wall-clock phases of the append path, printed at exit (measurement aid)
+struct AppendTimers {
+	double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	uint64_t calls = 0;
+	bool on = getenv("USB_TIMING") != nullptr;
+	double tk = 0;
+	static double now()
+	{
+		struct timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return ts.tv_sec + 1e-9 * ts.tv_nsec;
+	}
+	void start()
+	{
+		if (on)
+			tk = now();
+	}
+	void lap(int i)
+	{
+		if (on) {
+			cudaDeviceSynchronize();
+			const double x = now();
+			t[i] += x - tk;
+			tk = x;
+		}
+	}
+	~AppendTimers()
+	{
+		if (on && calls)
+			fprintf(stderr, "usb_index_append: %llu calls; host copy %.3fs letters up %.3fs pack %.3fs | count+scan %.3fs sizes down %.3fs "
+			                "plan %.3fs pool grow %.3fs move %.3fs fill %.3fs tables up %.3fs | layout %.3fs\n",
+			  (unsigned long long)calls, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10]);
+	}
+};
+static AppendTimers g_at;
+
 #include "usb_dynseg.inc"
 
 struct usb_index {
@@ -561,7 +597,10 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 		if (seq_off[i + 1] < seq_off[i] || seq_off[i + 1] - seq_off[i] > (1u << 24))
 			return fail(USB_EINVAL, "usb_index_append: bad offsets at target %u", i);
 	HostSeqs &S = ix->S;
+	g_at.start();
+	++g_at.calls;
 	S.append(seqs, seq_off, n, ix->P.dbmask && !ix->P.cluster_mode, 0);
+	g_at.lap(0);
 	int rc;
 	// letters and lengths of the new targets
 	const uint64_t b0 = S.seq_off[n0], b1 = S.seq_off[n0 + n];
@@ -572,6 +611,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 	CK(cudaMemcpy(ix->d_seq_off.p + n0, S.seq_off.data() + n0, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(ix->d_seq_len.p + n0, S.seq_len.data() + n0, (size_t)n * 4, cudaMemcpyHostToDevice));
 	ix->n_dev = n0 + n;
+	g_at.lap(1);
 	if (ix->P.is_nucleo) {
 		const size_t w0 = n0 ? (size_t)pack_words(b0, n0) : 0, w1 = (size_t)pack_words(b1, (uint64_t)n0 + n);
 		if ((rc = ix->d_db2.grow_keep(w1 + 4, w0)) || (rc = ix->d_dbn.grow_keep(w1 + 4, w0)) ||
@@ -582,6 +622,7 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 		CK(cudaGetLastError());
 		CK(cudaDeviceSynchronize());
 	}
+	g_at.lap(2);
 	// small appends (and everything after the first one) go to the growable tail segment; the
 	// initial targets of a search database always form a static segment (2-byte layout)
 	// (cluster_fast: every append goes to the tail segment, large ones through the device builder)
@@ -601,7 +642,10 @@ extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64
 		if (rc)
 			return rc;
 		ix->n_postings += ix->dyn->n_postings - before;
-		return index_sync_layout(ix); // a tail segment ends the 2-byte layout of a static one
+		g_at.start();
+		rc = index_sync_layout(ix); // a tail segment ends the 2-byte layout of a static one
+		g_at.lap(10);
+		return rc;
 	}
 	// new segment, then merge while the last two are of similar size (or the list is full)
 	IndexSegment *g = new IndexSegment;

@@ -129,43 +129,58 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
   uint32_t step)
 {
 	uint32_t minv_out = 1;
-	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr uint32_t NW = RANK_THREADS / 32;
 	const uint32_t N = a.n_seq;
 	uint32_t *U32 = (uint32_t *)U;
-	const uint32_t PER = WIDE ? 2 : 4;
+	constexpr uint32_t PER = WIDE ? 2 : 4, BITS = WIDE ? 16 : 8, CMASK = WIDE ? 0xffffu : 0xffu;
 	const uint32_t n_words32 = (N + PER - 1) / PER;
+	const uint32_t n128 = (n_words32 + 3) / 4; // (u_stride leaves room for the rounding)
 
-	// ---- zero the counters (global, L2 resident)
+	// ---- zero the counters (global, L2 resident) and the survivor histogram
 	{
 		uint4 *U128 = (uint4 *)U;
-		const uint32_t n128 = (n_words32 + 3) / 4;
 		for (uint32_t i = tid; i < n128; i += RANK_THREADS)
-			U128[i] = make_uint4(0, 0, 0, 0);
+			__stcg(U128 + i, make_uint4(0, 0, 0, 0));
+		for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+			S.hist[i] = 0;
 	}
 	__syncthreads();
 
-	// ---- count: warps take sampled rows from a shared cursor; packed fire-and-forget adds
+	// ---- count: every warp takes a part of a sampled row; four postings in flight per lane.  The
+	// adds return the old word: the largest value any add produces is the maximum of U, so no pass
+	// over the counters is needed for it.
+	uint32_t my_max = 0;
 	{
+		const uint32_t parts = n_rows >= NW ? 1u : min(8u, NW / n_rows);
 		uint32_t my_post = 0;
-		for (;;) {
-			uint32_t r = 0;
-			if (lane == 0)
-				r = atomicAdd(&S.row_cur, 1u);
-			r = __shfl_sync(USB_FULL, r, 0);
-			if (r >= n_rows)
-				break;
+		for (uint32_t item = warp; item < n_rows * parts; item += NW) {
+			const uint32_t r = item / parts, part = item - r * parts;
 			const uint32_t word = S.rows[r];
 			for (uint32_t sg = 0; sg < a.ix.n_seg; ++sg) {
 				const SegDesc &seg = a.ix.seg[sg];
 				const uint32_t size = seg.row_size[word];
+				if (size == 0)
+					continue;
 				const uint32_t *row = seg.postings + seg.row_off[word];
-				my_post += size;
-				for (uint32_t i = lane; i < size; i += 32) {
-					const uint32_t t = __ldg(row + i);
-					if (WIDE)
-						atomicAdd(&U32[t >> 1], 1u << ((t & 1) * 16));
-					else
-						atomicAdd(&U32[t >> 2], 1u << ((t & 3) * 8));
+				const uint32_t b0 = (uint32_t)((uint64_t)size * part / parts);
+				const uint32_t b1 = (uint32_t)((uint64_t)size * (part + 1) / parts);
+				if (part == 0)
+					my_post += size;
+				for (uint32_t i0 = b0; i0 < b1; i0 += 128) {
+					uint32_t t[4];
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						const uint32_t i = i0 + 32 * j + lane;
+						t[j] = i < b1 ? __ldg(row + i) : 0xffffffffu;
+					}
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j)
+						if (t[j] != 0xffffffffu) {
+							const uint32_t sh = (t[j] & (PER - 1)) * BITS;
+							const uint32_t old = atomicAdd(&U32[t[j] / PER], 1u << sh);
+							my_max = max(my_max, ((old >> sh) & CMASK) + 1);
+						}
 				}
 			}
 		}
@@ -173,22 +188,12 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 			atomicAdd(&S.n_post, my_post);
 	}
 	__threadfence();
-	__syncthreads();
+	const uint32_t gmax = block_reduce_max(my_max, S.warp_tmp);
 
 	if (a.u_out)
 		for (uint32_t t = tid; t < N; t += RANK_THREADS)
 			a.u_out[(uint64_t)job * N + t] = ug_get<WIDE>(U, t);
 
-	// ---- global max of U
-	uint32_t m = 0;
-	{
-		uint32_t acc = 0;
-		const volatile uint32_t *V = (const volatile uint32_t *)U32;
-		for (uint32_t i = tid; i < n_words32; i += RANK_THREADS)
-			acc = WIDE ? __vmaxu2(acc, V[i]) : __vmaxu4(acc, V[i]);
-		m = WIDE ? max(acc & 0xffff, acc >> 16) : max(max(acc & 0xff, (acc >> 8) & 0xff), max((acc >> 16) & 0xff, acc >> 24));
-	}
-	const uint32_t gmax = block_reduce_max(m, S.warp_tmp);
 	uint32_t total = 0, nsel = 0;
 	if (gmax > 0) {
 		// ---- p* = first-touched target holding gmax: first sampled row with such a target, lowest t
@@ -233,22 +238,68 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 		const uint32_t minv = max(nextv / 2, 1u);
 		minv_out = minv;
 
-		// ---- survivors
+		// ---- survivors: one pass of 128-bit loads; slots are handed out per warp; the numbers of
+		// survivors with U = minv .. minv + 3 are kept in registers, larger values go to the histogram
 		{
-			const volatile uint32_t *V = (const volatile uint32_t *)U32;
+			const uint4 *U128 = (const uint4 *)U;
 			const uint32_t thr_v = WIDE ? minv * 0x00010001u : minv * 0x01010101u;
-			const bool possible = minv <= (WIDE ? 0xffffu : 0xffu);
-			for (uint32_t i = tid; possible && i < n_words32; i += RANK_THREADS) {
-				const uint32_t word = V[i];
-				uint32_t mask = WIDE ? __vcmpgeu2(word, thr_v) : __vcmpgeu4(word, thr_v);
-				while (mask) {
-					const uint32_t b = (uint32_t)(__ffs(mask) - 1) / (WIDE ? 16 : 8);
-					mask &= ~((WIDE ? 0xffffu : 0xffu) << (b * (WIDE ? 16 : 8)));
-					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
-					const uint32_t t = i * PER + b;
-					const uint32_t slot = atomicAdd(&S.n_surv, 1u);
-					if (slot < RANK_KCAP)
-						S.sel[slot] = ((unsigned long long)u << 32) | t;
+			const bool possible = minv <= CMASK;
+			uint32_t h[4] = {0, 0, 0, 0};
+			for (uint32_t i0 = 0; possible && i0 < n128; i0 += RANK_THREADS) {
+				const uint32_t i = i0 + tid;
+				uint4 x = make_uint4(0, 0, 0, 0);
+				if (i < n128)
+					x = __ldcg(U128 + i);
+				const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+				uint32_t m[4], c = 0;
+#pragma unroll
+				for (uint32_t j = 0; j < 4; ++j) {
+					m[j] = w4[j] == 0 ? 0u : (WIDE ? __vcmpgeu2(w4[j], thr_v) : __vcmpgeu4(w4[j], thr_v));
+					c += __popc(m[j]) / BITS;
+				}
+				if (__ballot_sync(USB_FULL, c != 0) == 0)
+					continue;
+				uint32_t incl = c;
+#pragma unroll
+				for (uint32_t d = 1; d < 32; d <<= 1) {
+					const uint32_t v = __shfl_up_sync(USB_FULL, incl, d);
+					if (lane >= d)
+						incl += v;
+				}
+				uint32_t base = 0;
+				if (lane == 31)
+					base = atomicAdd(&S.n_surv, incl);
+				base = __shfl_sync(USB_FULL, base, 31);
+				uint32_t slot = base + incl - c;
+#pragma unroll
+				for (uint32_t j = 0; j < 4; ++j) {
+					uint32_t mask = m[j];
+					while (mask) {
+						const uint32_t b = (uint32_t)(__ffs(mask) - 1) / BITS;
+						mask &= ~(CMASK << (b * BITS));
+						const uint32_t u = (w4[j] >> (b * BITS)) & CMASK;
+						const uint32_t t = (i * 4 + j) * PER + b;
+						if (slot < RANK_KCAP)
+							S.sel[slot] = ((unsigned long long)u << 32) | t;
+						++slot;
+						if (!WIDE) {
+							const uint32_t d = u - minv;
+							h[0] += d == 0;
+							h[1] += d == 1;
+							h[2] += d == 2;
+							h[3] += d == 3;
+							if (d >= 4)
+								atomicAdd(&S.hist[u], 1u);
+						}
+					}
+				}
+			}
+			if (!WIDE) {
+#pragma unroll
+				for (uint32_t d = 0; d < 4; ++d) {
+					const uint32_t sum = __reduce_add_sync(USB_FULL, h[d]);
+					if (lane == 0 && sum && minv + d < 256)
+						atomicAdd(&S.hist[minv + d], sum);
 				}
 			}
 		}
@@ -264,22 +315,25 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 			block_sort_keys(S.sel, total);
 			nsel = min(total, a.k_max);
 		} else {
-			// ---- rare: select the first k_max of (U desc, first-touch order)
-			for (uint32_t i = tid; i < 256; i += RANK_THREADS)
-				S.hist[i] = 0;
+			// ---- more survivors than slots (the usual case for a query without a close target:
+			// NextValue is 1 or 2 then): select the first k_max of (U desc, first-touch order)
 			if (tid == 0) {
 				S.n_sel = 0;
 				S.taken = 0;
 			}
-			__syncthreads();
 			const volatile uint32_t *V = (const volatile uint32_t *)U32;
-			// radix select on U (two levels when WIDE)
-			for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
-				const uint32_t word = V[i];
-				for (uint32_t b = 0; b < PER; ++b) {
-					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
-					if (u >= minv)
-						atomicAdd(&S.hist[WIDE ? (u >> 8) : u], 1u);
+			if (WIDE) {
+				// radix select on U, two levels (the histogram of the survivor pass is not kept here)
+				for (uint32_t i = tid; i < 256; i += RANK_THREADS)
+					S.hist[i] = 0;
+				__syncthreads();
+				for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
+					const uint32_t word = V[i];
+					for (uint32_t b = 0; word && b < PER; ++b) {
+						const uint32_t u = (word >> (b * BITS)) & CMASK;
+						if (u >= minv)
+							atomicAdd(&S.hist[u >> 8], 1u);
+					}
 				}
 			}
 			__syncthreads();
@@ -303,7 +357,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 				__syncthreads();
 				for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
 					const uint32_t word = V[i];
-					for (uint32_t b = 0; b < PER; ++b) {
+					for (uint32_t b = 0; word && b < PER; ++b) {
 						const uint32_t u = (word >> (b * 16)) & 0xffffu;
 						if (u >= minv && (u >> 8) == bstar)
 							atomicAdd(&S.hist[u & 255], 1u);
@@ -325,17 +379,23 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 				__syncthreads();
 			}
 			const uint32_t vstar = S.vstar, m_eq = S.m_eq;
-			// everything above the cut value
-			for (uint32_t i = tid; i < n_words32; i += RANK_THREADS) {
-				const uint32_t word = V[i];
-				for (uint32_t b = 0; b < PER; ++b) {
-					const uint32_t u = (word >> (b * (WIDE ? 16 : 8))) & (WIDE ? 0xffffu : 0xffu);
-					if (u > vstar) {
-						const uint32_t t = i * PER + b;
-						const uint32_t slot = atomicAdd(&S.n_sel, 1u);
-						if (slot < RANK_KCAP)
-							S.sel[slot] = big_key(u, first_row_of(a, S, t, n_rows), t);
-					}
+			// everything above the cut value (fewer than k_max targets)
+			if (S.above) {
+				const uint4 *U128 = (const uint4 *)U;
+				for (uint32_t i = tid; i < n128; i += RANK_THREADS) {
+					const uint4 x = __ldcg(U128 + i);
+					const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j)
+						for (uint32_t b = 0; w4[j] && b < PER; ++b) {
+							const uint32_t u = (w4[j] >> (b * BITS)) & CMASK;
+							if (u > vstar) {
+								const uint32_t t = (i * 4 + j) * PER + b;
+								const uint32_t slot = atomicAdd(&S.n_sel, 1u);
+								if (slot < RANK_KCAP)
+									S.sel[slot] = big_key(u, first_row_of(a, S, t, n_rows), t);
+							}
+						}
 				}
 			}
 			__syncthreads();
