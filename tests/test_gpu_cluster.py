@@ -120,3 +120,61 @@ def test_cluster_fast_cli_byte_identical_to_reference(sort, tmp_path):
             want = f.read().splitlines()
         d = util.first_diff(open(got).read().splitlines(), want)
         assert d is None, "%s\n%s" % (name, d)
+
+
+@pytest.mark.parametrize("variant", sorted(util.CLUSTER_SIZE_VARIANTS))
+def test_cluster_fast_size_annotations_byte_identical_to_reference(variant, tmp_path):
+    """-sizein / -sizeout / -relabel / -minsize (clustersink.cpp:118-143,217-272, derepresult.cpp:211-225,
+    clusterfast.cpp:38-79): .uc and centroids identical to the reference binary's
+    (tools/make_golden_cluster_sizes.py)."""
+    import gzip
+    import os
+    import subprocess
+    from usearch12_b200 import build
+    cli = build.build_cli()
+    reads = os.path.join(str(tmp_path), "r.fa")
+    util.sized_cluster_reads(reads)
+    uc, cen = os.path.join(str(tmp_path), "o.uc"), os.path.join(str(tmp_path), "o.fa")
+    cmd = [cli, "-cluster_fast", reads, "-id", "0.97", "-uc", uc, "-centroids", cen, "-quiet"] + util.CLUSTER_SIZE_VARIANTS[variant]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for got, name in ((uc, "cluster_%s.uc.gz" % variant), (cen, "cluster_%s.centroids.fa.gz" % variant)):
+        with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+            want = f.read().splitlines()
+        d = util.first_diff(open(got).read().splitlines(), want)
+        assert d is None, "%s\n%s" % (name, d)
+
+
+@pytest.mark.parametrize("variant", sorted(util.SMALLMEM_VARIANTS))
+def test_cluster_smallmem_byte_identical_to_reference(variant, tmp_path):
+    """-cluster_smallmem (clustersmallmem.cpp:50-143): no dereplication, input order checked against
+    -sortedby, Terminator 1/32 (terminator.cpp:22-31); .uc and centroids identical to the reference
+    binary's (tools/make_golden_cluster_sizes.py)."""
+    import gzip
+    import os
+    import subprocess
+    from usearch12_b200 import build
+    cli = build.build_cli()
+    order, extra = util.SMALLMEM_VARIANTS[variant]
+    reads = os.path.join(str(tmp_path), "r.fa")
+    util.smallmem_reads(reads, order)
+    uc, cen = os.path.join(str(tmp_path), "o.uc"), os.path.join(str(tmp_path), "o.fa")
+    r = subprocess.run([cli, "-cluster_smallmem", reads, "-id", "0.97", "-uc", uc, "-centroids", cen, "-quiet"] + extra,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for got, name in ((uc, "cluster_%s.uc.gz" % variant), (cen, "cluster_%s.centroids.fa.gz" % variant)):
+        with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+            want = f.read().splitlines()
+        d = util.first_diff(open(got).read().splitlines(), want)
+        assert d is None, "%s\n%s" % (name, d)
+
+
+def test_cluster_smallmem_refuses_unsorted_input(tmp_path):
+    import os
+    import subprocess
+    from usearch12_b200 import build
+    reads = os.path.join(str(tmp_path), "r.fa")
+    util.smallmem_reads(reads, "none")
+    r = subprocess.run([build.build_cli(), "-cluster_smallmem", reads, "-id", "0.97", "-uc", os.path.join(str(tmp_path), "o.uc")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode != 0 and "Not sorted by length" in r.stdout

@@ -253,3 +253,44 @@ def product_local_params(nucleo, evalue, **kw):
     p = capi.default_params(**kw)
     capi.lib().usb_set_local(C.byref(p), int(nucleo), float(evalue))
     return p
+
+
+# -cluster_fast with size annotations: option sets of the golden files cluster_<name>.* (made by
+# tools/make_golden_cluster_sizes.py with the reference binary)
+CLUSTER_SIZE_VARIANTS = {
+    "szin": ["-sizein", "-sizeout", "-sort", "size"],
+    "szout": ["-sizeout", "-relabel", "Otu", "-minsize", "3", "-sort", "size"],
+    "szin_len": ["-sizein", "-sort", "length"],
+}
+
+
+def sized_cluster_reads(path):
+    """tests/golden/cluster_reads.fa.gz with ';size=N;' appended to every label."""
+    import gzip
+    labels, seqs = read_fasta(os.path.join(GOLDEN, "cluster_reads.fa.gz"))
+    with open(path, "w") as f:
+        for i, (lab, s) in enumerate(zip(labels, seqs)):
+            f.write(">%s;size=%d;\n%s\n" % (lab, 1 + (i * 7) % 13, s if isinstance(s, str) else s.decode()))
+
+
+# -cluster_smallmem golden variants (tools/make_golden_cluster_sizes.py): name -> (input order, options)
+SMALLMEM_VARIANTS = {
+    "sm_len": ("length", []),
+    "sm_size": ("size", ["-sortedby", "size", "-sizein", "-sizeout", "-minsize", "4"]),
+    "sm_other": ("none", ["-sortedby", "other", "-maxrejects", "8"]),
+}
+
+
+def smallmem_reads(path, order):
+    """cluster_reads.fa.gz with size annotations, sorted for -cluster_smallmem (stable): by decreasing
+    length, by decreasing size annotation, or in file order."""
+    labels, seqs = read_fasta(os.path.join(GOLDEN, "cluster_reads.fa.gz"))
+    recs = [("%s;size=%d;" % (lab, 1 + (i * 7) % 13), s if isinstance(s, str) else s.decode(), 1 + (i * 7) % 13)
+            for i, (lab, s) in enumerate(zip(labels, seqs))]
+    if order == "length":
+        recs.sort(key=lambda r: -len(r[1]))
+    elif order == "size":
+        recs.sort(key=lambda r: -r[2])
+    with open(path, "w") as f:
+        for lab, s, _ in recs:
+            f.write(">%s\n%s\n" % (lab, s))

@@ -18,6 +18,7 @@
 #include "usb_host.h"
 
 #include <chrono>
+#include <climits>
 #include <thread>
 #include <cstring>
 
@@ -158,6 +159,25 @@ static void StripAnnot(std::string &Label, const std::string &NameEq)
 		Label = NewLabel;
 }
 
+// label.cpp:152-161 GetSizeFromLabel
+static unsigned GetSizeFromLabel(const char *Label, unsigned Default)
+{
+	const char *p = strstr(Label, ";size=");
+	if (p)
+		return (unsigned)atoi(p + 6);
+	if (Default == UINT_MAX)
+		Die("Missing size= in >%s", Label);
+	return Default;
+}
+
+// label.cpp:88-91 AppendSize -> AppendIntField (myutils.cpp:824-839 Psasc)
+static void AppendSize(std::string &Label, unsigned Size)
+{
+	if (!Label.empty() && Label.back() != ';')
+		Label += ';';
+	Label += "size=" + std::to_string(Size) + ";";
+}
+
 // -fastx_uniques (derepfull.cpp:214-236, derepresult.cpp:255-284,689-775,811-820): uniques in order
 // of decreasing size (the reference's own quicksort, not stable), labelled with the first member's
 // label, optionally relabelled and annotated with ;size=N;
@@ -231,28 +251,71 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	const double t_parsed = now();
 
 	std::vector<unsigned> UniqOf, First, USize;
-	DerepFullHost(Input, UniqOf, First, USize);
+	unsigned UsedCount = SeqCount; // cluster_smallmem -sortedby size -minsize: the input ends at the first smaller size
+	if (Opts.smallmem) {
+		// every sequence is searched, in input order; the order is only checked (clustersmallmem.cpp:88-127)
+		const std::string so = Opts.sortedby.empty() ? "length" : Opts.sortedby;
+		if (so != "length" && so != "size" && so != "other")
+			Die("Invalid -sortedby");
+		unsigned PrevL = UINT_MAX, PrevSize = UINT_MAX;
+		for (unsigned i = 0; i < SeqCount; ++i) {
+			if (so == "length") {
+				const unsigned L = Input.GetSeqLength(i);
+				if (L > PrevL)
+					Die("Not sorted by length, see -sortedby option in manual");
+				PrevL = L;
+			} else if (so == "size") {
+				const unsigned Size = GetSizeFromLabel(Input.GetLabel(i), UINT_MAX);
+				if (Opts.minsize_filled && Size < Opts.minsize) {
+					UsedCount = i;
+					break;
+				}
+				if (Size > PrevSize)
+					Die("Not sorted by size; prev %u >%s", PrevSize, Input.GetLabel(i));
+				PrevSize = Size;
+			}
+		}
+		UniqOf.resize(UsedCount);
+		First.resize(UsedCount);
+		USize.assign(UsedCount, 1);
+		for (unsigned i = 0; i < UsedCount; ++i)
+			UniqOf[i] = First[i] = i;
+	} else
+		DerepFullHost(Input, UniqOf, First, USize);
 	const double t_derep = now();
 	const unsigned UniqueCount = (unsigned)First.size();
 	// members of each unique in input order (CSR)
-	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(SeqCount);
-	for (unsigned i = 0; i < SeqCount; ++i)
+	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(UsedCount);
+	for (unsigned i = 0; i < UsedCount; ++i)
 		++MemberOff[UniqOf[i] + 1];
 	for (unsigned u = 0; u < UniqueCount; ++u)
 		MemberOff[u + 1] += MemberOff[u];
 	{
 		std::vector<unsigned> cur(MemberOff.begin(), MemberOff.end() - 1);
-		for (unsigned i = 0; i < SeqCount; ++i)
+		for (unsigned i = 0; i < UsedCount; ++i)
 			Members[cur[UniqOf[i]]++] = i;
 	}
+	// sizes: DerepResult::GetSumSizeIn (derepresult.cpp:211-225, size annotations count whether or not
+	// -sizein is given: -sort size) and ClusterSink::GetSize (clustersink.cpp:118-143: annotations
+	// only with -sizein, and then every label must have one)
+	std::vector<unsigned> SumSizeIn(UniqueCount, 0), QSize(UniqueCount, 0);
+	for (unsigned u = 0; u < UniqueCount; ++u)
+		for (unsigned m = MemberOff[u]; m < MemberOff[u + 1]; ++m) {
+			const char *Label = Input.GetLabel(Members[m]);
+			SumSizeIn[u] += GetSizeFromLabel(Label, 1);
+			QSize[u] += Opts.sizein ? GetSizeFromLabel(Label, UINT_MAX) : 1u;
+		}
 	// ---- GetSeqOrder
 	std::vector<unsigned> Order(UniqueCount);
 	for (unsigned u = 0; u < UniqueCount; ++u)
 		Order[u] = u;
-	if (Opts.sort == "length" || Opts.sort == "size") {
+	if (Opts.smallmem) {
+		if (!Opts.sort.empty())
+			Die("-sort is an option of -cluster_fast; -cluster_smallmem takes the input order (-sortedby)");
+	} else if (Opts.sort == "length" || Opts.sort == "size") {
 		std::vector<unsigned> v(UniqueCount);
 		for (unsigned u = 0; u < UniqueCount; ++u)
-			v[u] = Opts.sort == "length" ? Input.GetSeqLength(First[u]) : USize[u];
+			v[u] = Opts.sort == "length" ? Input.GetSeqLength(First[u]) : SumSizeIn[u];
 		QuickSortOrderDesc(v, Order);
 	} else if (!Opts.sort.empty() && Opts.sort != "other" && Opts.sort != "user")
 		Die("Invalid sort name %s", Opts.sort.c_str());
@@ -314,7 +377,7 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 				// ClusterSink::OnQueryDone, no hit: new centroid (clustersink.cpp:318-329)
 				if (c != ClusterSizes.size())
 					Die("internal: centroid index %u != cluster count %zu", c, ClusterSizes.size());
-				ClusterSizes.push_back(USize[u]);
+				ClusterSizes.push_back(QSize[u]);
 				CentroidRead.push_back(r0);
 				if (fUC) {
 					appendf2(buf, "S\t%u\t%u\t*\t.\t*\t*\t*\t", c, L);
@@ -329,7 +392,7 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 					}
 				}
 			} else {
-				ClusterSizes[c] += USize[u];
+				ClusterSizes[c] += QSize[u];
 				if (fUC) {
 					AlignResult AR;
 					AR.m_Hit = hits[qoff[q]];
@@ -378,10 +441,21 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		std::vector<unsigned> COrder;
 		QuickSortOrderDesc(ClusterSizes, COrder);
 		std::string out;
+		unsigned RelabelCounter = 0;
 		for (unsigned k = 0; k < ClusterCount; ++k) {
 			const unsigned r = CentroidRead[COrder[k]];
+			if (ClusterSizes[COrder[k]] < Opts.minsize)
+				break; // clustersink.cpp:245-246 (sizes descend)
+			// ClusterSink::MakeCentroidLabel (clustersink.cpp:217-241)
+			std::string Label = Input.GetLabel(r);
+			if (Opts.sizein || Opts.sizeout)
+				StripAnnot(Label, "size=");
+			if (!Opts.relabel.empty())
+				Label = Opts.relabel + std::to_string(++RelabelCounter);
+			if (Opts.sizeout)
+				AppendSize(Label, ClusterSizes[COrder[k]]);
 			out += '>';
-			out += Input.GetLabel(r);
+			out += Label;
 			out += '\n';
 			const uint8_t *s = Input.GetSeq(r);
 			const unsigned L = Input.GetSeqLength(r);

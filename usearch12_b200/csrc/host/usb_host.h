@@ -272,12 +272,20 @@ struct SearchOpts {
 
 struct ClusterOpts {
 	usb_params P;             // usb_default_params(&P, 1) + -id
-	std::string uc, centroids, sort;
+	std::string uc, centroids, sort, relabel;
 	uint32_t max_block = 1u << 16;
+	unsigned minsize = 0;     // -minsize: centroids of smaller clusters are not written
+	bool minsize_filled = false;
+	bool sizein = false, sizeout = false;
 	bool quiet = false;
+	// -cluster_smallmem (clustersmallmem.cpp:50-143): no dereplication, input order, the input must be
+	// sorted as -sortedby says (length by default; size; other = no check)
+	bool smallmem = false;
+	std::string sortedby;
 };
 
-// clusterfast.cpp:81 ClusterFast() with -threads 1 semantics; returns the number of clusters.
+// clusterfast.cpp:81 ClusterFast() with -threads 1 semantics (or ClusterSmallmem, clustersmallmem.cpp:50,
+// when Opts.smallmem); returns the number of clusters.
 uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
 
 struct UniquesOpts {

@@ -25,7 +25,7 @@ using namespace usbhost;
 int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
-	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", "self", "notself", "selfid", "top_hit_only",
+	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", "sizein", "self", "notself", "selfid", "top_hit_only",
 	                              "top_hits_only", nullptr};
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
@@ -52,11 +52,19 @@ int main(int argc, char **argv)
 		opt.erase(it);
 		return v;
 	};
-	const std::string reads = take("cluster_fast", nullptr);
-	if (!reads.empty()) {
-		// clusterfast.cpp:135 cmd_cluster_fast
+	std::string reads = take("cluster_fast", nullptr);
+	const std::string reads_sm = take("cluster_smallmem", nullptr);
+	if (!reads.empty() || !reads_sm.empty()) {
+		// clusterfast.cpp:135 cmd_cluster_fast, clustersmallmem.cpp:145 cmd_cluster_smallmem
 		ClusterOpts C;
 		usb_default_params(&C.P, 1);
+		if (reads.empty()) {
+			reads = reads_sm;
+			C.smallmem = true;
+			C.sortedby = take("sortedby", nullptr);
+			if (opt.count("fastaout"))
+				Die("-fastaout not supported, use -centroids"); // clustersmallmem.cpp:55-61
+		}
 		const std::string cid = take("id", nullptr);
 		if (cid.empty())
 			Die("Must specify -id"); // makeclustersearcher.cpp:30-31
@@ -64,10 +72,15 @@ int main(int argc, char **argv)
 		const std::string cstrand = take("strand", "plus");
 		if (cstrand != "plus")
 			Die("-cluster_fast -strand %s is not supported by this build", cstrand.c_str());
-		C.P.maxrejects = (uint32_t)atoi(take("maxrejects", "8").c_str());
+		C.P.maxrejects = (uint32_t)atoi(take("maxrejects", C.smallmem ? "32" : "8").c_str()); // terminator.cpp:10-31
 		C.uc = take("uc", nullptr);
 		C.centroids = take("centroids", nullptr);
 		C.sort = take("sort", nullptr);
+		C.sizein = !take("sizein", nullptr).empty();
+		C.sizeout = !take("sizeout", nullptr).empty();
+		C.relabel = take("relabel", nullptr);
+		C.minsize_filled = opt.count("minsize") != 0;
+		C.minsize = (unsigned)atoi(take("minsize", "0").c_str());
 		C.max_block = (uint32_t)atoi(take("batch", "65536").c_str());
 		C.quiet = !take("quiet", nullptr).empty();
 		take("threads", nullptr); // derep/cluster order follow the reference's -threads 1 behaviour

@@ -368,11 +368,48 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 	}
 }
 
+// Result arrays live in page-locked host memory (device-to-host copies at full PCIe speed, no staging
+// copy) and are not value-initialised on resize (they are overwritten by the copies).  Falls back to
+// pageable memory when page-locking fails.
+template <class T> struct PinnedNoInit {
+	using value_type = T;
+	PinnedNoInit() = default;
+	template <class U> PinnedNoInit(const PinnedNoInit<U> &) {}
+	T *allocate(size_t n)
+	{
+		const size_t bytes = n * sizeof(T) + 64;
+		void *p = nullptr;
+		uint64_t pinned = 1;
+		if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+			cudaGetLastError();
+			pinned = 0;
+			p = aligned_alloc(64, (bytes + 63) & ~(size_t)63);
+			if (!p)
+				throw std::bad_alloc();
+		}
+		*(uint64_t *)p = pinned;
+		return (T *)((uint8_t *)p + 64);
+	}
+	void deallocate(T *q, size_t)
+	{
+		void *p = (uint8_t *)q - 64;
+		if (*(uint64_t *)p)
+			cudaFreeHost(p);
+		else
+			free(p);
+	}
+	template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
+	template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+	template <class U> bool operator==(const PinnedNoInit<U> &) const { return true; }
+	template <class U> bool operator!=(const PinnedNoInit<U> &) const { return false; }
+};
+template <class T> using PinVec = std::vector<T, PinnedNoInit<T>>;
+
 struct usb_result {
-	std::vector<usb_hit> hits;
-	std::vector<uint32_t> runs;
-	std::vector<uint64_t> qoff;
-	std::vector<usb_qstat> qstat;
+	PinVec<usb_hit> hits;
+	PinVec<uint32_t> runs;
+	PinVec<uint64_t> qoff;
+	PinVec<usb_qstat> qstat;
 };
 
 struct usb_searcher {
@@ -389,6 +426,9 @@ struct usb_searcher {
 	bool ran = false;
 	uint32_t last_hits = 0, last_runs = 0;
 	uint64_t last_postings = 0;
+	DevBuf<uint32_t> d_grp_cnt;   // download_result: hits per group, then scatter cursors
+	DevBuf<uint64_t> d_grp_off;
+	DevBuf<usb_hit> d_hits_grp;
 	DevBuf<uint8_t> d_q;
 	DevBuf<uint64_t> d_qoff;
 	DevBuf<uint32_t> d_cand_t, d_cand_u, d_ncand, d_nemit, d_runs, d_uout, d_aux;
@@ -880,6 +920,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 		cudaStreamSynchronize(s->stream);
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
+	s->d_grp_cnt.release(); s->d_grp_off.release(); s->d_hits_grp.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
 	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release(); s->d_atab.release();
 	if (s->h_stage)
@@ -1073,6 +1114,10 @@ static int launch_rank_big(usb_searcher *s, uint32_t n_jobs, uint32_t strands, u
 	a.u_out = want_u ? s->d_uout.p : nullptr;
 	a.aux = s->d_aux.p;
 	a.stepwords = s->P.stepwords;
+	{
+		static const uint32_t variant = getenv("USB_BIG_VARIANT") ? (uint32_t)atoi(getenv("USB_BIG_VARIANT")) : 0u;
+		a.variant = variant;
+	}
 	a.rows_out = nullptr;
 	if (s->P.cluster_mode) { // usb_cluster_round reads the sampled words back on the device
 		if ((rc0 = s->d_rows_out.reserve((size_t)n_jobs * CLUSTER_ROWS_CAP)) || (rc0 = s->d_nrows_out.reserve(n_jobs)))
@@ -1806,7 +1851,7 @@ static void quicksort_desc(const float *v, uint32_t *ord, int lo, int hi)
 		quicksort_desc(v, ord, i, hi);
 }
 
-static void order_hits_like_hitmgr(std::vector<usb_hit> &hits, const std::vector<uint64_t> &qoff, bool local)
+static void order_hits_like_hitmgr(PinVec<usb_hit> &hits, const PinVec<uint64_t> &qoff, bool local)
 {
 	std::vector<float> sc;
 	std::vector<uint32_t> ord;
@@ -1857,7 +1902,7 @@ static void result_recycle(usb_result *r)
 		return;
 	{
 		std::lock_guard<std::mutex> lk(g_pool_mu);
-		if (g_pool.size() < 2) {
+		if (g_pool.size() < 8) {
 			r->hits.clear();
 			r->runs.clear();
 			r->qoff.clear();
@@ -1869,18 +1914,34 @@ static void result_recycle(usb_result *r)
 	delete r;
 }
 
+// USB_TIMING=1: wall-clock phases of usb_search_batch, printed at exit (measurement aid)
+struct BatchTimers {
+	double t[6] = {0, 0, 0, 0, 0, 0};
+	uint64_t calls = 0;
+	bool on = getenv("USB_TIMING") != nullptr;
+	~BatchTimers()
+	{
+		if (on && calls)
+			fprintf(stderr, "usb_search_batch: %llu calls; upload %.3fs run %.3fs copy back %.3fs group %.3fs order %.3fs\n",
+			  (unsigned long long)calls, t[0], t[1], t[2], t[3], t[4]);
+	}
+};
+static BatchTimers g_bt;
+
 static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result **out)
 {
+	double tk = g_bt.on ? AppendTimers::now() : 0;
 	usb_result *r = result_new();
 	const uint32_t nh = s->last_hits, nr = s->last_runs;
-	// raw hits + TopOrder sizes go to pinned staging, the rest straight into the result
-	const size_t raw_bytes = (size_t)nh * sizeof(usb_hit), nc_bytes = (size_t)s->n_jobs * 4;
-	if (raw_bytes + nc_bytes + 64 > s->h_stage_cap) {
+	// The hits are grouped on the device (count per group, offsets, scatter) and everything is
+	// copied straight into the result's page-locked arrays.
+	const size_t nc_bytes = (size_t)s->n_jobs * 4;
+	if (nc_bytes + 64 > s->h_stage_cap) {
 		if (s->h_stage)
 			cudaFreeHost(s->h_stage);
 		s->h_stage = nullptr;
 		s->h_stage_cap = 0;
-		const size_t want = (raw_bytes + nc_bytes + 64) * 5 / 4;
+		const size_t want = (nc_bytes + 64) * 5 / 4;
 		if (cudaHostAlloc(&s->h_stage, want, cudaHostAllocDefault) != cudaSuccess) {
 			cudaGetLastError();
 			result_recycle(r);
@@ -1888,13 +1949,38 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 		}
 		s->h_stage_cap = want;
 	}
-	const usb_hit *raw = (const usb_hit *)s->h_stage;
-	const uint32_t *ncand = (const uint32_t *)((uint8_t *)s->h_stage + ((raw_bytes + 15) & ~(size_t)15));
-	r->runs.resize(nr);
-	r->qstat.resize(s->n_jobs);
-	cudaError_t e = cudaSuccess;
-	if (nh)
-		e = cudaMemcpyAsync((void *)raw, s->d_hits.p, raw_bytes, cudaMemcpyDeviceToHost, s->stream);
+	const uint32_t *ncand = (const uint32_t *)s->h_stage;
+	try {
+		r->runs.resize(nr);
+		r->qstat.resize(s->n_jobs);
+		r->hits.resize(nh);
+		r->qoff.resize((size_t)n_q + 1);
+	} catch (const std::bad_alloc &) {
+		result_recycle(r);
+		return fail(USB_ENOMEM, "out of host memory for the result (%u hits)", nh);
+	}
+	int rc;
+	if ((rc = s->d_grp_cnt.reserve((size_t)n_q + 1)) || (rc = s->d_grp_off.reserve((size_t)n_q + 1)) ||
+	    (rc = s->d_hits_grp.reserve((size_t)nh + 1))) {
+		result_recycle(r);
+		return rc;
+	}
+	cudaError_t e = cudaMemsetAsync(s->d_grp_cnt.p, 0, ((size_t)n_q + 1) * 4, s->stream);
+	if (e == cudaSuccess && nh) {
+		const uint32_t grid = std::min<uint32_t>((nh + 255) / 256, (uint32_t)s->num_sms * 8);
+		k_hit_count<<<grid, 256, 0, s->stream>>>(s->d_hits.p, nh, group ? 1 : 0, s->d_grp_cnt.p);
+		k_row_offsets<<<1, 1024, 0, s->stream>>>(s->d_grp_cnt.p, n_q, s->d_grp_off.p);
+		e = cudaMemsetAsync(s->d_grp_cnt.p, 0, ((size_t)n_q + 1) * 4, s->stream);
+		k_hit_scatter<<<grid, 256, 0, s->stream>>>(s->d_hits.p, nh, group ? 1 : 0, s->d_grp_off.p, s->d_grp_cnt.p, s->d_hits_grp.p);
+		if (e == cudaSuccess)
+			e = cudaGetLastError();
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(r->hits.data(), s->d_hits_grp.p, (size_t)nh * sizeof(usb_hit), cudaMemcpyDeviceToHost, s->stream);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(r->qoff.data(), s->d_grp_off.p, ((size_t)n_q + 1) * 8, cudaMemcpyDeviceToHost, s->stream);
+		s->launches += 3;
+	} else
+		std::fill(r->qoff.begin(), r->qoff.end(), (uint64_t)0);
 	if (e == cudaSuccess && nr)
 		e = cudaMemcpyAsync(r->runs.data(), s->d_runs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s->stream);
 	if (e == cudaSuccess && s->n_jobs && group) {
@@ -1912,18 +1998,20 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 	if (group)
 		for (uint32_t j = 0; j < s->n_jobs; ++j)
 			r->qstat[j].n_cand = ncand[j];
-	// group by query (counting sort), then the reference's per-query order
-	r->qoff.assign((size_t)n_q + 1, 0);
-	for (uint32_t k = 0; k < nh; ++k)
-		++r->qoff[(size_t)(group ? raw[k].query : raw[k].rank) + 1];
-	for (uint32_t q = 0; q < n_q; ++q)
-		r->qoff[q + 1] += r->qoff[q];
-	r->hits.resize(nh);
-	std::vector<uint64_t> cur(r->qoff.begin(), r->qoff.end() - 1);
-	for (uint32_t k = 0; k < nh; ++k)
-		r->hits[cur[group ? raw[k].query : raw[k].rank]++] = raw[k];
+	if (g_bt.on) {
+		const double x = AppendTimers::now();
+		g_bt.t[2] += x - tk;
+		tk = x;
+	}
+	if (g_bt.on) {
+		const double x = AppendTimers::now();
+		g_bt.t[3] += x - tk;
+		tk = x;
+	}
 	if (group)
 		order_hits_like_hitmgr(r->hits, r->qoff, s->P.local != 0);
+	if (g_bt.on)
+		g_bt.t[4] += AppendTimers::now() - tk;
 	*out = r;
 	return 0;
 }
@@ -1941,11 +2029,22 @@ extern "C" int usb_batch_download(usb_searcher *s, usb_result **out)
 extern "C" int usb_search_batch(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
   usb_result **out)
 {
+	double tk = g_bt.on ? AppendTimers::now() : 0;
 	int rc = upload_queries(s, qseqs, q_off, n_q);
 	if (rc)
 		return rc;
+	if (g_bt.on) {
+		cudaStreamSynchronize(s->stream);
+		const double x = AppendTimers::now();
+		g_bt.t[0] += x - tk;
+		tk = x;
+	}
 	if ((rc = usb_batch_run(s, nullptr)))
 		return rc;
+	if (g_bt.on) {
+		g_bt.t[1] += AppendTimers::now() - tk;
+		++g_bt.calls;
+	}
 	return usb_batch_download(s, out);
 }
 

@@ -46,6 +46,7 @@ struct RankBigArgs {
 	uint32_t *rows_out;        // optional: the sampled words of every job, rows_cap per job
 	uint32_t *n_rows_out;      // their number (0xffffffff when more than rows_cap)
 	uint32_t rows_cap;
+	uint32_t variant;          // measurement knob (USB_BIG_VARIANT)
 	DevCounters *ctr;
 };
 
@@ -271,6 +272,27 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					base = atomicAdd(&S.n_surv, incl);
 				base = __shfl_sync(USB_FULL, base, 31);
 				uint32_t slot = base + incl - c;
+				if (!WIDE && a.variant == 0) {
+					// histogram without a loop over the bytes: U = minv .. minv + 3 by SIMD compares, the
+					// (few) larger ones one by one
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						if (m[j] == 0)
+							continue;
+#pragma unroll
+						for (uint32_t d = 0; d < 4; ++d)
+							if (minv + d < 256)
+								h[d] += __popc(__vcmpeq4(w4[j], (minv + d) * 0x01010101u)) / 8;
+						uint32_t big = minv + 4 < 256 ? __vcmpgeu4(w4[j], (minv + 4) * 0x01010101u) : 0u;
+						while (big) {
+							const uint32_t b = (uint32_t)(__ffs(big) - 1) / 8;
+							big &= ~(0xffu << (b * 8));
+							atomicAdd(&S.hist[(w4[j] >> (b * 8)) & 0xffu], 1u);
+						}
+					}
+				}
+				if (base >= RANK_KCAP && a.variant == 0)
+					continue; // (warp-uniform) the slots are used up: only the counts matter from here on
 #pragma unroll
 				for (uint32_t j = 0; j < 4; ++j) {
 					uint32_t mask = m[j];
@@ -282,7 +304,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 						if (slot < RANK_KCAP)
 							S.sel[slot] = ((unsigned long long)u << 32) | t;
 						++slot;
-						if (!WIDE) {
+						if (!WIDE && a.variant != 0) {
 							const uint32_t d = u - minv;
 							h[0] += d == 0;
 							h[1] += d == 1;
@@ -386,16 +408,20 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					const uint4 x = __ldcg(U128 + i);
 					const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-					for (uint32_t j = 0; j < 4; ++j)
-						for (uint32_t b = 0; w4[j] && b < PER; ++b) {
+					for (uint32_t j = 0; j < 4; ++j) {
+						if (w4[j] == 0 || vstar >= CMASK)
+							continue;
+						uint32_t mask = WIDE ? __vcmpgeu2(w4[j], (vstar + 1) * 0x00010001u) : __vcmpgeu4(w4[j], (vstar + 1) * 0x01010101u);
+						while (mask) {
+							const uint32_t b = (uint32_t)(__ffs(mask) - 1) / BITS;
+							mask &= ~(CMASK << (b * BITS));
 							const uint32_t u = (w4[j] >> (b * BITS)) & CMASK;
-							if (u > vstar) {
-								const uint32_t t = (i * 4 + j) * PER + b;
-								const uint32_t slot = atomicAdd(&S.n_sel, 1u);
-								if (slot < RANK_KCAP)
-									S.sel[slot] = big_key(u, first_row_of(a, S, t, n_rows), t);
-							}
+							const uint32_t t = (i * 4 + j) * PER + b;
+							const uint32_t slot = atomicAdd(&S.n_sel, 1u);
+							if (slot < RANK_KCAP)
+								S.sel[slot] = big_key(u, first_row_of(a, S, t, n_rows), t);
 						}
+					}
 				}
 			}
 			__syncthreads();
