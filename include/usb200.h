@@ -178,6 +178,15 @@ int usb_index_row(const usb_index *ix, uint32_t word, const uint32_t **row, uint
 /* Masked target sequence as indexed (SeqDB::GetSeq after SeqDB::Mask, seqdb.cpp:415). */
 int usb_index_seq(const usb_index *ix, uint32_t target, const uint8_t **seq, uint32_t *len);
 
+/* ---- full-length dereplication on the device: replaces DerepFull (derepfull.cpp:130-212; hashing
+ * seqhash.cpp:6-51) with its -threads 1 result: sequences are equal when they have the same length
+ * and the same letters ignoring case; uniq_of[i] = number of sequence i's unique, uniques numbered
+ * in order of first occurrence (what DerepResult::m_ClusterCount / GetClusterIndex give,
+ * derepresult.cpp:211-225,811-820); *n_uniq = their count.  Callers: -fastx_uniques and the first
+ * step of -cluster_fast (clusterfast.cpp:97-100). */
+int usb_derep_full(int device, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n, uint32_t *uniq_of,
+                   uint32_t *n_uniq);
+
 /* ---- .udb database files (udbfile.h:17-62, udbio.cpp:242-364, seqdbio.cpp:17-258).  Host only: these
  * entry points need no device.
  * usb_udb_write = -makeudb_usearch (makeudb.cpp:27-60): MaskDB + UDBData::FromSeqDB + ToUDBFile for

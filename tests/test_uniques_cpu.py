@@ -1,37 +1,24 @@
-"""-fastx_uniques (derepfull.cpp:130-236, derepresult.cpp:255-284,689-775):
-host-only dereplication, byte-identical to the reference binary's -fastaout (tools/make_golden_uniques.py)."""
-import gzip
-import os
+"""-fastx_uniques argument checks that need no device (derepfull.cpp:214-218); the dereplication itself runs
+on the device and is tested in tests/test_gpu_uniques.py."""
 import subprocess
 
-import pytest
-
-from tests import util
 from usearch12_b200 import build
-
-VARIANTS = {
-    "uniq_sizeout": ["-sizeout"],
-    "uniq_relabel": ["-sizeout", "-relabel", "Uniq", "-minuniquesize", "2"],
-    "uniq_plain": [],
-}
-
-
-@pytest.mark.parametrize("name", sorted(VARIANTS))
-def test_fastx_uniques_byte_identical_to_reference(name, tmp_path):
-    cli = build.build_cli()
-    src = str(tmp_path / "in.fa")
-    with gzip.open(os.path.join(util.GOLDEN, "uniq_in.fa.gz"), "rb") as f, open(src, "wb") as g:
-        g.write(f.read())
-    dst = str(tmp_path / "out.fa")
-    r = subprocess.run([cli, "-fastx_uniques", src, "-fastaout", dst, "-quiet"] + VARIANTS[name], stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0, r.stdout
-    with gzip.open(os.path.join(util.GOLDEN, name + ".fa.gz"), "rb") as f:
-        want = f.read()
-    assert open(dst, "rb").read() == want
 
 
 def test_fastx_uniques_refuses_output_option(tmp_path):
     cli = build.build_cli()
     r = subprocess.run([cli, "-fastx_uniques", "x.fa", "-output", "y.fa"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "Use -fastaout, not -output" in r.stdout
+
+
+def test_fastx_uniques_fails_loudly_without_a_device(tmp_path):
+    """No CPU path: without a CUDA device the command must stop with an error, not fall back."""
+    from usearch12_b200 import capi
+    if capi.lib().usb_device_count() > 0:
+        import pytest
+        pytest.skip("a CUDA device is present")
+    src = tmp_path / "in.fa"
+    src.write_text(">a\nACGT\n>b\nacgt\n")
+    r = subprocess.run([build.build_cli(), "-fastx_uniques", str(src), "-fastaout", str(tmp_path / "o.fa")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stdout

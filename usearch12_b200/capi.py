@@ -66,10 +66,19 @@ SYMBOLS = [
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
     "usb_viterbi_batch", "usb_set_local", "usb_set_amino", "usb_local_evalue", "usb_local_pairs",
     "usb_udb_write", "usb_udb_probe", "usb_udb_read", "usb_udb_free", "usb_udb_seq_count", "usb_udb_is_nucleo",
-    "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row", "usb_debug_half_row",
+    "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row", "usb_debug_half_row", "usb_derep_full",
 ]
 
 _lib = None
+
+
+def derep_full(seqs, device=0):
+    """DerepFull (derepfull.cpp:130-212) on the device -> (uniq_of[n], n_uniq)."""
+    data, off = pack_seqs(seqs)
+    out = np.zeros(max(1, len(seqs)), np.uint32)
+    nu = C.c_uint32(0)
+    check(lib().usb_derep_full(device, _ptr(data), _ptr(off), len(seqs), _ptr(out), C.byref(nu)))
+    return out[:len(seqs)], nu.value
 
 
 def lib():
@@ -93,6 +102,7 @@ def lib():
     L.usb_index_posting_count.restype = C.c_uint64
     L.usb_index_posting_width.argtypes = [vp]
     L.usb_index_posting_width.restype = C.c_uint32
+    L.usb_derep_full.argtypes = [C.c_int, vp, vp, C.c_uint32, vp, u32p]
     L.usb_udb_write.argtypes = [C.c_char_p, C.POINTER(Params), vp, vp, C.POINTER(C.c_char_p), C.c_uint32]
     L.usb_udb_probe.argtypes = [C.c_char_p]
     L.usb_udb_read.argtypes = [C.c_char_p, C.POINTER(vp)]

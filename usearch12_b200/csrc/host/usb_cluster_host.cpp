@@ -74,61 +74,37 @@ static void appendf2(std::string &s, const char *fmt, ...)
 
 // DerepFull (derepfull.cpp:130-212) with -threads 1 semantics: case-insensitive equality, uniques in
 // first-occurrence order.  UniqOf[i] = unique of sequence i, First[u] = its first member, USize[u].
-static void DerepFullHost(const SeqDB &Input, std::vector<unsigned> &UniqOf, std::vector<unsigned> &First,
+// The grouping runs on the device (usb_derep_full); the letters are flattened for it.
+static void DerepFullDevice(const SeqDB &Input, std::vector<unsigned> &UniqOf, std::vector<unsigned> &First,
   std::vector<unsigned> &USize)
 {
 	const unsigned SeqCount = Input.GetSeqCount();
-	UniqOf.assign(SeqCount, 0);
-	First.clear();
-	USize.clear();
-	size_t nb = 16;
-	while (nb < 2 * (size_t)SeqCount + 16)
-		nb <<= 1;
-	std::vector<int> bucket(nb, -1);
-	// hashes of all sequences first (threads), then the order-dependent insertion
-	std::vector<uint32_t> Hash(SeqCount);
+	std::vector<uint64_t> Off((size_t)SeqCount + 1, 0);
+	for (unsigned i = 0; i < SeqCount; ++i)
+		Off[i + 1] = Off[i] + Input.GetSeqLength(i);
+	std::vector<uint8_t> Letters(Off[SeqCount] + 16);
 	{
 		const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
 		std::vector<std::thread> th;
 		for (unsigned k = 0; k < T; ++k)
 			th.emplace_back([&, k]() {
 				const unsigned a = (unsigned)((uint64_t)SeqCount * k / T), b = (unsigned)((uint64_t)SeqCount * (k + 1) / T);
-				for (unsigned i = a; i < b; ++i) {
-					const uint8_t *s = Input.GetSeq(i);
-					const unsigned L = Input.GetSeqLength(i);
-					uint32_t h = 2166136261u;
-					for (unsigned j = 0; j < L; ++j)
-						h = (h ^ (uint32_t)toupper(s[j])) * 16777619u;
-					Hash[i] = h;
-				}
+				for (unsigned i = a; i < b; ++i)
+					memcpy(Letters.data() + Off[i], Input.GetSeq(i), Input.GetSeqLength(i));
 			});
 		for (auto &t : th)
 			t.join();
 	}
+	UniqOf.assign(SeqCount, 0);
+	uint32_t nu = 0;
+	CheckUsb2(usb_derep_full(0, Letters.data(), Off.data(), SeqCount, UniqOf.data(), &nu), "usb_derep_full");
+	First.assign(nu, UINT_MAX);
+	USize.assign(nu, 0);
 	for (unsigned i = 0; i < SeqCount; ++i) {
-		const uint8_t *s = Input.GetSeq(i);
-		const unsigned L = Input.GetSeqLength(i);
-		size_t b = Hash[i] & (nb - 1);
-		for (;;) {
-			if (bucket[b] < 0) {
-				bucket[b] = (int)First.size();
-				UniqOf[i] = (unsigned)First.size();
-				First.push_back(i);
-				USize.push_back(0);
-				break;
-			}
-			const unsigned f = First[bucket[b]];
-			bool eq = Input.GetSeqLength(f) == L && Hash[f] == Hash[i];
-			const uint8_t *t = Input.GetSeq(f);
-			for (unsigned k = 0; eq && k < L; ++k)
-				eq = toupper(s[k]) == toupper(t[k]);
-			if (eq) {
-				UniqOf[i] = (unsigned)bucket[b];
-				break;
-			}
-			b = (b + 1) & (nb - 1);
-		}
-		++USize[UniqOf[i]];
+		const unsigned u = UniqOf[i];
+		if (First[u] == UINT_MAX)
+			First[u] = i;
+		++USize[u];
 	}
 }
 
@@ -186,7 +162,9 @@ uint64_t FastxUniques(const std::string &InputFileName, const UniquesOpts &Opts)
 	SeqDB Input;
 	Input.FromFasta(InputFileName);
 	std::vector<unsigned> UniqOf, First, USize, Order;
-	DerepFullHost(Input, UniqOf, First, USize);
+	if (usb_device_count() <= 0)
+		Die("No CUDA device available: this build has no CPU path");
+	DerepFullDevice(Input, UniqOf, First, USize);
 	QuickSortOrderDesc(USize, Order);
 	if (Opts.fastaout.empty())
 		return First.size();
@@ -281,7 +259,7 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		for (unsigned i = 0; i < UsedCount; ++i)
 			UniqOf[i] = First[i] = i;
 	} else
-		DerepFullHost(Input, UniqOf, First, USize);
+		DerepFullDevice(Input, UniqOf, First, USize);
 	const double t_derep = now();
 	const unsigned UniqueCount = (unsigned)First.size();
 	// members of each unique in input order (CSR)

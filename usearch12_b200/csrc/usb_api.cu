@@ -9,6 +9,7 @@
 #include <ctime>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
@@ -319,6 +320,7 @@ struct usb_index {
 };
 
 #include "usb_ixbuild.inc"
+#include "usb_derep.inc"
 
 // 2-byte postings: one static segment from target 0, at most USB_HALF_MAX_TARGETS, and no use of the
 // big-database or cluster kernels (they walk 4-byte rows).
