@@ -560,9 +560,10 @@ def main():
 
         bounds = {
             "k_rank": "hbm during the posting walk; about a third of the launch is the serial scan/select tail",
-            "k_gate": "instruction issue (ncu: issue slots 87 % busy, DRAM < 1 % of peak): integer/bit work on packed "
-                      "letters in shared memory; its HBM fraction is small by construction",
-            "k_dp": "shared-memory latency / issue (ncu: issue slots ~50 % busy); writes one trace byte per cell to HBM",
+            "k_gate": "instruction issue (ncu: issue slots 71 % busy in the stage that holds 86 % of its time, DRAM < 1 % of "
+                      "peak): integer/bit work on packed letters in shared memory; its HBM fraction is small by construction",
+            "k_dp": "shared-memory latency / issue (ncu: issue slots 46-62 % busy at 16 warps/SM); writes one trace byte per "
+                    "cell to HBM",
             "k_align": "instruction issue / latency"}
 
         def kernel_line(name):
