@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--no-legs", action="store_true")
     ap.add_argument("--legs", default="config2,cluster,cluster_amplicon,local,cli")
     ap.add_argument("--cluster-reads", type=int, default=1000000)
-    ap.add_argument("--cluster-ref-sample", type=int, default=20000)
+    ap.add_argument("--cluster-ref-sample", type=int, default=120000)  # past the -big switch (100 000 clusters)
     ap.add_argument("--local-queries", type=int, default=200000)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 0)

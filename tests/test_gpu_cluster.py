@@ -178,3 +178,33 @@ def test_cluster_smallmem_refuses_unsorted_input(tmp_path):
     r = subprocess.run([build.build_cli(), "-cluster_smallmem", reads, "-id", "0.97", "-uc", os.path.join(str(tmp_path), "o.uc")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode != 0 and "Not sorted by length" in r.stdout
+
+
+def test_cluster_fast_120k_reads_identical_to_reference_across_the_big_switch(tmp_path):
+    """BASELINE config 3 on real volume: the first 120 000 window-random reads of the bench workload give
+    ~105 000 clusters, so the run crosses -big (100 000 targets: udbusortedsearcher.cpp:39-58) and the last
+    rounds take the big-database path (sampled words, first-touch order, k_rank_big's many-survivor
+    selection).  .uc byte-identical to the unmodified reference binary (-threads 1)."""
+    import os
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    import synth_np
+    from usearch12_b200 import build
+    ref = os.path.join(util.ROOT, "oracle", "_ref", "usearch12")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/usearch12 not built")
+    n = int(os.environ.get("USB_CLUSTER_TEST_READS", "120000"))
+    db, db_off = synth_np.gen_db(100000, 1500, seed=4)
+    reads, r_off, _ = synth_np.gen_reads(db, db_off, n, 250, seed=3000)
+    fa = str(tmp_path / "r.fa")
+    synth_np.write_fasta(fa, reads, r_off, "r")
+    out = {}
+    for name, exe, extra in (("ref", ref, ["-threads", "1"]), ("usb", build.build_cli(), [])):
+        uc = str(tmp_path / (name + ".uc"))
+        subprocess.run([exe, "-cluster_fast", fa, "-id", "0.97", "-uc", uc, "-quiet"] + extra, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=1200)
+        out[name] = open(uc, "rb").read()
+    n_clusters = sum(1 for l in out["ref"].splitlines() if l.startswith(b"C\t"))
+    assert n_clusters > 100000, n_clusters
+    assert out["usb"] == out["ref"]

@@ -193,8 +193,14 @@ template <class T> struct DevBuf {
 			cudaGetLastError();
 			return fail(USB_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
 		}
-		if (p && used)
-			cudaMemcpy(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice);
+		if (p && used) {
+			e = cudaMemcpy(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice);
+			if (e != cudaSuccess) {
+				cudaGetLastError();
+				cudaFree(q);
+				return fail(USB_ECUDA, "device copy of %zu bytes failed: %s", used * sizeof(T), cudaGetErrorString(e));
+			}
+		}
 		if (p)
 			cudaFree(p);
 		p = q;
@@ -625,7 +631,30 @@ extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *
 // Appends targets [N, N+n): UDBData::AddSIToDB_CopyData (udbbuild.cpp:286) for a whole block.
 // The new targets form a CSR segment; neighbouring segments of similar size are concatenated
 // (log-structured merge) so that the number of row fragments per word stays logarithmic.
+static int index_append_impl(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n);
+
+// A failed append (device memory, a CUDA error) must not leave targets on the host side that have
+// no postings: the host copy and the device count are rolled back to the state before the call.
 extern "C" int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n)
+{
+	if (!ix)
+		return fail(USB_EINVAL, "usb_index_append: null argument");
+	const uint32_t n0 = ix->S.n(), dev0 = ix->n_dev, max0 = ix->S.max_len;
+	const size_t nseg0 = ix->segs.size();
+	const uint64_t post0 = ix->n_postings;
+	const int rc = index_append_impl(ix, seqs, seq_off, n);
+	if (rc && ix->S.n() != n0 && ix->segs.size() == nseg0 && !(ix->dyn && ix->dyn->base + ix->dyn->count > n0)) {
+		ix->S.seq_len.resize(n0);
+		ix->S.seq_off.resize((size_t)n0 + 1);
+		ix->S.seqs.resize(ix->S.seq_off.back() + 16);
+		ix->S.max_len = max0;
+		ix->n_dev = dev0;
+		ix->n_postings = post0;
+	}
+	return rc;
+}
+
+static int index_append_impl(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n)
 {
 	if (!ix || !seq_off || (!seqs && n))
 		return fail(USB_EINVAL, "usb_index_append: null argument");
