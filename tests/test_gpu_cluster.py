@@ -180,11 +180,13 @@ def test_cluster_smallmem_refuses_unsorted_input(tmp_path):
     assert r.returncode != 0 and "Not sorted by length" in r.stdout
 
 
-def test_cluster_fast_120k_reads_identical_to_reference_across_the_big_switch(tmp_path):
-    """BASELINE config 3 on real volume: the first 120 000 window-random reads of the bench workload give
-    ~105 000 clusters, so the run crosses -big (100 000 targets: udbusortedsearcher.cpp:39-58) and the last
-    rounds take the big-database path (sampled words, first-touch order, k_rank_big's many-survivor
-    selection).  .uc byte-identical to the unmodified reference binary (-threads 1)."""
+@pytest.mark.parametrize("kind,n_default", [("window", 120000), ("amplicon", 200000)])
+def test_cluster_fast_120k_reads_identical_to_reference_across_the_big_switch(kind, n_default, tmp_path):
+    """BASELINE config 3 on real volume: the first 120 000 window-random (200 000 amplicon) reads of the
+    bench workload give more than 100 000 clusters, so the run crosses -big (100 000 targets:
+    udbusortedsearcher.cpp:39-58) and the last rounds take the big-database path (sampled words,
+    first-touch order, k_rank_big's many-survivor selection).  .uc byte-identical to the unmodified
+    reference binary (-threads 1)."""
     import os
     import subprocess
     import sys
@@ -194,9 +196,9 @@ def test_cluster_fast_120k_reads_identical_to_reference_across_the_big_switch(tm
     ref = os.path.join(util.ROOT, "oracle", "_ref", "usearch12")
     if not os.path.exists(ref):
         pytest.skip("oracle/_ref/usearch12 not built")
-    n = int(os.environ.get("USB_CLUSTER_TEST_READS", "120000"))
+    n = int(os.environ.get("USB_CLUSTER_TEST_READS", str(n_default)))
     db, db_off = synth_np.gen_db(100000, 1500, seed=4)
-    reads, r_off, _ = synth_np.gen_reads(db, db_off, n, 250, seed=3000)
+    reads, r_off, _ = synth_np.gen_reads(db, db_off, n, 250, seed=3000, window=(500, 750) if kind == "amplicon" else None)
     fa = str(tmp_path / "r.fa")
     synth_np.write_fasta(fa, reads, r_off, "r")
     out = {}

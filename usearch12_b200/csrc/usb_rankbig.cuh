@@ -153,7 +153,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 	// over the counters is needed for it.
 	uint32_t my_max = 0;
 	{
-		const uint32_t parts = n_rows >= NW ? 1u : min(8u, NW / n_rows);
+		const uint32_t parts = n_rows >= NW || n_rows == 0 ? 1u : min(8u, NW / n_rows);
 		uint32_t my_post = 0;
 		for (uint32_t item = warp; item < n_rows * parts; item += NW) {
 			const uint32_t r = item / parts, part = item - r * parts;
