@@ -163,6 +163,7 @@ template <bool AA>
 __device__ __forceinline__ void load_query(const AlignArgs &a, WarpWs &w, const uint8_t *Q, uint32_t L, uint32_t strand)
 {
 	const uint32_t lane = lane_id();
+	__syncwarp(); // lanes may still be reading the previous query's arrays
 	if constexpr (AA) {
 		for (uint32_t i = lane; i < L; i += 32) {
 			const uint32_t c = Q[i];
@@ -199,6 +200,7 @@ template <bool AA> __device__ __forceinline__ void load_target(const AlignArgs &
 {
 	const uint32_t lane = lane_id();
 	const uint32_t L = a.db_len[t];
+	__syncwarp(); // lanes may still be reading the previous target's arrays
 	w.B = a.db_seq + a.db_off[t];
 	if constexpr (AA) {
 		for (uint32_t i = lane; i < L; i += 32)
@@ -736,6 +738,7 @@ template <bool AA> __device__ uint32_t ungapped_blast(const AlignArgs &a, WarpWs
 		}
 		__syncwarp();
 		extend_queued<AA>(a, w, q2b, q2a, n2, packed, MinLength, cur, nung);
+		__syncwarp(); // the queue is refilled next: every lane is done reading it
 		scan = max(scan, cur);
 	}
 	__syncwarp();

@@ -745,6 +745,7 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 				g.wild = qwild || twild;
 				pass = g.wild ? gate_pair<true>(S, g, nchain) : gate_pair<false>(S, g, nchain);
 				if (twild) { // leave the wildcard array clean for the next target
+					__syncwarp(); // (every lane is done reading it)
 					const uint32_t nw = (g.w.LB + 15) / 16 + 2;
 					for (uint32_t j = lane; j < nw; j += 32)
 						g.w.Bn2[j] = 0;
@@ -802,6 +803,7 @@ __global__ void __launch_bounds__(GATE_MAX_WARPS * 32, 1) k_gate(const StageArgs
 // Byte codes of the query (strand-adjusted) for the DP and the statistics.
 __device__ __forceinline__ void dp_load_query(WarpWs &w, const uint8_t *Q, uint32_t L, uint32_t strand)
 {
+	__syncwarp(); // lanes may still be reading the previous record's arrays
 	for (uint32_t i = lane_id(); i < L; i += 32) {
 		const uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
 		w.A[i] = (uint8_t)c;
@@ -820,6 +822,7 @@ __device__ __forceinline__ void dp_load_target(const StageArgs &S, WarpWs &w, ui
 	const bool twild = S.db_wild[t] != 0;
 	uint4 *dC = (uint4 *)w.Bc;
 	const uint32_t n16 = (L + 15) / 16;
+	__syncwarp(); // lanes may still be reading the previous record's arrays
 	for (uint32_t k = lane_id(); k < n16; k += 32) {
 		const uint32_t p2 = __ldg(S.db2 + o + k);
 		const uint32_t pn = twild ? __ldg(S.dbn + o + k) : 0u;
