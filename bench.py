@@ -211,6 +211,8 @@ def leg_config2(capi, a):
     for _ in range(3):
         s.run()
     ms = [s.run() for _ in range(3)]
+    for _ in range(2):  # warm-up of the end-to-end path (staging buffers, recycled result objects)
+        res = s.search_packed(reads, r_off, copy=False)
     t = time.perf_counter()
     for _ in range(3):
         res = s.search_packed(reads, r_off, copy=False)
@@ -273,6 +275,8 @@ def leg_local(capi, a):
     for _ in range(2):
         s.run()
     ms = [s.run() for _ in range(3)]
+    for _ in range(2):  # warm-up of the end-to-end path (staging buffers, recycled result objects)
+        res = s.search_packed(q, qoff, copy=False)
     t = time.perf_counter()
     for _ in range(3):
         res = s.search_packed(q, qoff, copy=False)

@@ -166,6 +166,10 @@ int usb_index_create(int device, const usb_params *p, const uint8_t *seqs, const
  * (udbbuild.cpp:286 -> AddSeqNoncoded :256 -> AddWord/GrowRow :111,:74), as cluster_fast does for
  * every new centroid.  Searchers created on the index see the new targets on their next batch. */
 int usb_index_append(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n);
+/* Capacity hint for an index that grows by appends (UDBData::AddSeq grows its SeqDB and rows on demand,
+ * udbbuild.cpp:74-130, seqdb.cpp AddSeq_CopyData): room for n_seqs targets with n_letters letters in
+ * all, on the host and on the device.  Optional; appends beyond the hint still work. */
+int usb_index_reserve(usb_index *ix, uint32_t n_seqs, uint64_t n_letters);
 void usb_index_free(usb_index *ix);
 uint32_t usb_index_seq_count(const usb_index *ix);
 uint64_t usb_index_posting_count(const usb_index *ix);

@@ -57,7 +57,8 @@ QSTAT_DTYPE = np.dtype([
 
 # every symbol include/usb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_free",
+    "usb_default_params", "usb_last_error", "usb_device_count", "usb_index_create", "usb_index_append", "usb_index_reserve",
+    "usb_index_free",
     "usb_index_seq_count", "usb_index_posting_count", "usb_index_posting_width", "usb_index_row", "usb_index_seq",
     "usb_searcher_create", "usb_searcher_free", "usb_search_batch", "usb_batch_upload", "usb_batch_run",
     "usb_batch_download", "usb_cluster_round", "usb_batch_counters", "usb_batch_kernel_ms", "usb_index_set_attrs", "usb_batch_set_query_attrs",
@@ -94,6 +95,7 @@ def lib():
     L.usb_default_params.restype = None
     L.usb_index_create.argtypes = [C.c_int, C.POINTER(Params), vp, vp, C.c_uint32, C.POINTER(vp)]
     L.usb_index_append.argtypes = [vp, vp, vp, C.c_uint32]
+    L.usb_index_reserve.argtypes = [vp, C.c_uint32, C.c_uint64]
     L.usb_index_free.argtypes = [vp]
     L.usb_index_free.restype = None
     L.usb_index_seq_count.argtypes = [vp]

@@ -320,6 +320,8 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 			t.join();
 	}
 	device_up.join();
+	// every unique may become a centroid: reserve once instead of growing through the rounds
+	CheckUsb2(usb_index_reserve(Index, UniqueCount, Off[UniqueCount]), "usb_index_reserve");
 
 	const double t_ready = now();
 	double t_rounds = 0;

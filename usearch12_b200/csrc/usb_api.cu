@@ -376,36 +376,21 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 	}
 }
 
-// Result arrays live in page-locked host memory (device-to-host copies at full PCIe speed, no staging
-// copy) and are not value-initialised on resize (they are overwritten by the copies).  Falls back to
-// pageable memory when page-locking fails.
+// Result arrays are not value-initialised on resize (the download overwrites them); they are plain
+// pageable memory: page-locking a fresh 100 MB result costs more (about 1.3 ms per MB here) than
+// copying it out of the searcher's one page-locked staging buffer.
 template <class T> struct PinnedNoInit {
 	using value_type = T;
 	PinnedNoInit() = default;
 	template <class U> PinnedNoInit(const PinnedNoInit<U> &) {}
 	T *allocate(size_t n)
 	{
-		const size_t bytes = n * sizeof(T) + 64;
-		void *p = nullptr;
-		uint64_t pinned = 1;
-		if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
-			cudaGetLastError();
-			pinned = 0;
-			p = aligned_alloc(64, (bytes + 63) & ~(size_t)63);
-			if (!p)
-				throw std::bad_alloc();
-		}
-		*(uint64_t *)p = pinned;
-		return (T *)((uint8_t *)p + 64);
+		void *p = aligned_alloc(64, (n * sizeof(T) + 63) & ~(size_t)63);
+		if (!p)
+			throw std::bad_alloc();
+		return (T *)p;
 	}
-	void deallocate(T *q, size_t)
-	{
-		void *p = (uint8_t *)q - 64;
-		if (*(uint64_t *)p)
-			cudaFreeHost(p);
-		else
-			free(p);
-	}
+	void deallocate(T *q, size_t) { free(q); }
 	template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
 	template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
 	template <class U> bool operator==(const PinnedNoInit<U> &) const { return true; }
@@ -632,6 +617,36 @@ extern "C" int usb_index_create(int device, const usb_params *p, const uint8_t *
 // The new targets form a CSR segment; neighbouring segments of similar size are concatenated
 // (log-structured merge) so that the number of row fragments per word stays logarithmic.
 static int index_append_impl(usb_index *ix, const uint8_t *seqs, const uint64_t *seq_off, uint32_t n);
+
+// Capacity hint for an index that will grow by appends (cluster_fast knows its uniques up front):
+// host and device arrays for n_seqs targets with n_letters letters in all.  Appends beyond it still work.
+extern "C" int usb_index_reserve(usb_index *ix, uint32_t n_seqs, uint64_t n_letters)
+{
+	if (!ix)
+		return fail(USB_EINVAL, "usb_index_reserve: null argument");
+	CK(cudaSetDevice(ix->device));
+	const uint64_t bytes = n_letters + 16ull * n_seqs + 64; // every target is padded to 16 bytes
+	const uint32_t n0 = ix->S.n();
+	try {
+		ix->S.seqs.reserve(bytes);
+		ix->S.seq_off.reserve((size_t)n_seqs + 1);
+		ix->S.seq_len.reserve(n_seqs);
+	} catch (const std::bad_alloc &) {
+		return fail(USB_ENOMEM, "usb_index_reserve: out of host memory (%llu bytes)", (unsigned long long)bytes);
+	}
+	const uint64_t b0 = ix->S.seq_off[n0];
+	int rc;
+	if ((rc = ix->d_seqs.grow_keep(bytes + 16, b0)) || (rc = ix->d_seq_off.grow_keep((size_t)n_seqs + 2, (size_t)n0 + 1)) ||
+	    (rc = ix->d_seq_len.grow_keep((size_t)n_seqs + 2, n0)))
+		return rc;
+	if (ix->P.is_nucleo) {
+		const size_t w0 = n0 ? (size_t)pack_words(b0, n0) : 0, w1 = (size_t)pack_words(bytes, n_seqs);
+		if ((rc = ix->d_db2.grow_keep(w1 + 4, w0)) || (rc = ix->d_dbn.grow_keep(w1 + 4, w0)) ||
+		    (rc = ix->d_wild.grow_keep((size_t)n_seqs + 2, n0)))
+			return rc;
+	}
+	return 0;
+}
 
 // A failed append (device memory, a CUDA error) must not leave targets on the host side that have
 // no postings: the host copy and the device count are rolled back to the state before the call.
@@ -1964,15 +1979,20 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 	double tk = g_bt.on ? AppendTimers::now() : 0;
 	usb_result *r = result_new();
 	const uint32_t nh = s->last_hits, nr = s->last_runs;
-	// The hits are grouped on the device (count per group, offsets, scatter) and everything is
-	// copied straight into the result's page-locked arrays.
-	const size_t nc_bytes = (size_t)s->n_jobs * 4;
-	if (nc_bytes + 64 > s->h_stage_cap) {
+	// The hits are grouped on the device (count per group, offsets, scatter); everything comes back
+	// through the searcher's page-locked staging buffer and is copied into the result by a few threads.
+	const bool want_q = s->n_jobs && group;
+	const size_t b_hits = ((size_t)nh * sizeof(usb_hit) + 63) & ~(size_t)63, b_off = (((size_t)n_q + 1) * 8 + 63) & ~(size_t)63,
+	             b_runs = ((size_t)nr * 4 + 63) & ~(size_t)63,
+	             b_qstat = want_q ? ((size_t)s->n_jobs * sizeof(usb_qstat) + 63) & ~(size_t)63 : 0,
+	             b_nc = want_q ? ((size_t)s->n_jobs * 4 + 63) & ~(size_t)63 : 0;
+	const size_t stage_bytes = b_hits + b_off + b_runs + b_qstat + b_nc + 64;
+	if (stage_bytes > s->h_stage_cap) {
 		if (s->h_stage)
 			cudaFreeHost(s->h_stage);
 		s->h_stage = nullptr;
 		s->h_stage_cap = 0;
-		const size_t want = (nc_bytes + 64) * 5 / 4;
+		const size_t want = stage_bytes * 5 / 4;
 		if (cudaHostAlloc(&s->h_stage, want, cudaHostAllocDefault) != cudaSuccess) {
 			cudaGetLastError();
 			result_recycle(r);
@@ -1980,7 +2000,9 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 		}
 		s->h_stage_cap = want;
 	}
-	const uint32_t *ncand = (const uint32_t *)s->h_stage;
+	uint8_t *st_hits = (uint8_t *)s->h_stage, *st_off = st_hits + b_hits, *st_runs = st_off + b_off, *st_qstat = st_runs + b_runs,
+	        *st_nc = st_qstat + b_qstat;
+	const uint32_t *ncand = (const uint32_t *)st_nc;
 	try {
 		r->runs.resize(nr);
 		r->qstat.resize(s->n_jobs);
@@ -2006,25 +2028,55 @@ static int download_result(usb_searcher *s, uint32_t n_q, bool group, usb_result
 		if (e == cudaSuccess)
 			e = cudaGetLastError();
 		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(r->hits.data(), s->d_hits_grp.p, (size_t)nh * sizeof(usb_hit), cudaMemcpyDeviceToHost, s->stream);
+			e = cudaMemcpyAsync(st_hits, s->d_hits_grp.p, (size_t)nh * sizeof(usb_hit), cudaMemcpyDeviceToHost, s->stream);
 		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(r->qoff.data(), s->d_grp_off.p, ((size_t)n_q + 1) * 8, cudaMemcpyDeviceToHost, s->stream);
+			e = cudaMemcpyAsync(st_off, s->d_grp_off.p, ((size_t)n_q + 1) * 8, cudaMemcpyDeviceToHost, s->stream);
 		s->launches += 3;
 	} else
-		std::fill(r->qoff.begin(), r->qoff.end(), (uint64_t)0);
+		memset(st_off, 0, ((size_t)n_q + 1) * 8);
 	if (e == cudaSuccess && nr)
-		e = cudaMemcpyAsync(r->runs.data(), s->d_runs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s->stream);
-	if (e == cudaSuccess && s->n_jobs && group) {
-		e = cudaMemcpyAsync(r->qstat.data(), s->d_qstat.p, (size_t)s->n_jobs * sizeof(usb_qstat), cudaMemcpyDeviceToHost,
-		  s->stream);
+		e = cudaMemcpyAsync(st_runs, s->d_runs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess && want_q) {
+		e = cudaMemcpyAsync(st_qstat, s->d_qstat.p, (size_t)s->n_jobs * sizeof(usb_qstat), cudaMemcpyDeviceToHost, s->stream);
 		if (e == cudaSuccess)
-			e = cudaMemcpyAsync((void *)ncand, s->d_ncand.p, nc_bytes, cudaMemcpyDeviceToHost, s->stream);
+			e = cudaMemcpyAsync(st_nc, s->d_ncand.p, (size_t)s->n_jobs * 4, cudaMemcpyDeviceToHost, s->stream);
 	}
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s->stream);
 	if (e != cudaSuccess) {
 		result_recycle(r);
 		return fail(USB_ECUDA, "result download failed: %s", cudaGetErrorString(e));
+	}
+	{
+		// staging -> result: four copies, in parallel when they are large
+		struct Part {
+			void *dst;
+			const void *src;
+			size_t n;
+		} parts[4] = {{r->hits.data(), st_hits, (size_t)nh * sizeof(usb_hit)}, {r->qoff.data(), st_off, ((size_t)n_q + 1) * 8},
+		              {r->runs.data(), st_runs, (size_t)nr * 4}, {r->qstat.data(), st_qstat, want_q ? (size_t)s->n_jobs * sizeof(usb_qstat) : 0}};
+		size_t total = 0;
+		for (const Part &p : parts)
+			total += p.n;
+		if (total < ((size_t)8 << 20)) {
+			for (const Part &p : parts)
+				if (p.n)
+					memcpy(p.dst, p.src, p.n);
+		} else {
+			// every part in four pieces, one per thread
+			std::vector<std::thread> th;
+			for (int k = 0; k < 4; ++k)
+				th.emplace_back([&, k]() {
+					for (int q = 0; q < 4; ++q) {
+						const Part &p = parts[q];
+						const size_t a0 = p.n * k / 4, a1 = p.n * (k + 1) / 4;
+						if (a1 > a0)
+							memcpy((uint8_t *)p.dst + a0, (const uint8_t *)p.src + a0, a1 - a0);
+					}
+				});
+			for (auto &t : th)
+				t.join();
+		}
 	}
 	if (group)
 		for (uint32_t j = 0; j < s->n_jobs; ++j)
