@@ -87,10 +87,43 @@ __device__ __forceinline__ uint32_t block_reduce_min(uint32_t v, uint32_t *warp_
 	return r;
 }
 
-template <bool WIDE>
+// Counter widths of the big-database path: 4 bits when a query counts with at most 15 words (the usual
+// case: about 11 sampled words at -id 0.97 for 250 bp reads; halves the array that is zeroed and read
+// per query), 8 bits up to 255 words, 16 bits beyond.
+#define BIG_NIB 0
+#define BIG_BYTE 1
+#define BIG_WIDE 2
+
+template <int MODE>
 __device__ __forceinline__ uint32_t ug_get(const uint8_t *U, uint32_t t)
 {
-	return WIDE ? (uint32_t)((const volatile uint16_t *)U)[t] : (uint32_t)((const volatile uint8_t *)U)[t];
+	if (MODE == BIG_WIDE)
+		return (uint32_t)((const volatile uint16_t *)U)[t];
+	if (MODE == BIG_BYTE)
+		return (uint32_t)((const volatile uint8_t *)U)[t];
+	return ((uint32_t)((const volatile uint8_t *)U)[t >> 1] >> ((t & 1) * 4)) & 0xfu;
+}
+
+// all bits of every counter of the packed word that is >= thr (1 <= thr <= counter maximum)
+template <int MODE>
+__device__ __forceinline__ uint32_t ge_mask(uint32_t w, uint32_t thr)
+{
+	if (MODE == BIG_WIDE)
+		return __vcmpgeu2(w, thr * 0x00010001u);
+	if (MODE == BIG_BYTE)
+		return __vcmpgeu4(w, thr * 0x01010101u);
+	const uint32_t t4 = thr * 0x01010101u;
+	return (__vcmpgeu4(w & 0x0f0f0f0fu, t4) & 0x0f0f0f0fu) | (__vcmpgeu4((w >> 4) & 0x0f0f0f0fu, t4) & 0xf0f0f0f0u);
+}
+
+// number of counters of the packed word equal to v (v >= 1; BIG_NIB / BIG_BYTE)
+template <int MODE>
+__device__ __forceinline__ uint32_t eq_count(uint32_t w, uint32_t v)
+{
+	const uint32_t v4 = v * 0x01010101u;
+	if (MODE == BIG_BYTE)
+		return __popc(__vcmpeq4(w, v4)) / 8;
+	return (__popc(__vcmpeq4(w & 0x0f0f0f0fu, v4)) + __popc(__vcmpeq4((w >> 4) & 0x0f0f0f0fu, v4))) / 8;
 }
 
 // index of the first sampled row that contains target t (rows ascending), or n_rows
@@ -125,16 +158,17 @@ __device__ __forceinline__ unsigned long long big_key(uint32_t u, uint32_t k, ui
 	return ((unsigned long long)(0xFFFFu - u) << 48) | ((unsigned long long)(k & 0xFFFFu) << 32) | t;
 }
 
-template <bool WIDE>
+template <int MODE>
 __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &S, uint8_t *U, uint32_t n_rows,
   uint32_t step)
 {
+	constexpr bool WIDE = MODE == BIG_WIDE;
 	uint32_t minv_out = 1;
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr uint32_t NW = RANK_THREADS / 32;
 	const uint32_t N = a.n_seq;
 	uint32_t *U32 = (uint32_t *)U;
-	constexpr uint32_t PER = WIDE ? 2 : 4, BITS = WIDE ? 16 : 8, CMASK = WIDE ? 0xffffu : 0xffu;
+	constexpr uint32_t PER = MODE == BIG_WIDE ? 2 : MODE == BIG_BYTE ? 4 : 8, BITS = 32 / PER, CMASK = (1u << BITS) - 1;
 	const uint32_t n_words32 = (N + PER - 1) / PER;
 	const uint32_t n128 = (n_words32 + 3) / 4; // (u_stride leaves room for the rounding)
 
@@ -193,7 +227,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 
 	if (a.u_out)
 		for (uint32_t t = tid; t < N; t += RANK_THREADS)
-			a.u_out[(uint64_t)job * N + t] = ug_get<WIDE>(U, t);
+			a.u_out[(uint64_t)job * N + t] = ug_get<MODE>(U, t);
 
 	uint32_t total = 0, nsel = 0;
 	if (gmax > 0) {
@@ -208,7 +242,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 				const uint32_t *row = seg.postings + seg.row_off[word];
 				for (uint32_t i = tid; i < size; i += RANK_THREADS) {
 					const uint32_t t = __ldg(row + i);
-					if (ug_get<WIDE>(U, t) == gmax)
+					if (ug_get<MODE>(U, t) == gmax)
 						best = min(best, t);
 				}
 			}
@@ -231,7 +265,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					const uint32_t t = __ldg(row + i);
 					if (k == kstar && t >= tstar)
 						break; // ascending row: the rest of this thread's stride is beyond p* too
-					nv = max(nv, ug_get<WIDE>(U, t)); // (no target before p* holds gmax)
+					nv = max(nv, ug_get<MODE>(U, t)); // (no target before p* holds gmax)
 				}
 			}
 		}
@@ -243,7 +277,6 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 		// survivors with U = minv .. minv + 3 are kept in registers, larger values go to the histogram
 		{
 			const uint4 *U128 = (const uint4 *)U;
-			const uint32_t thr_v = WIDE ? minv * 0x00010001u : minv * 0x01010101u;
 			const bool possible = minv <= CMASK;
 			uint32_t h[4] = {0, 0, 0, 0};
 			for (uint32_t i0 = 0; possible && i0 < n128; i0 += RANK_THREADS) {
@@ -255,7 +288,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 				uint32_t m[4], c = 0;
 #pragma unroll
 				for (uint32_t j = 0; j < 4; ++j) {
-					m[j] = w4[j] == 0 ? 0u : (WIDE ? __vcmpgeu2(w4[j], thr_v) : __vcmpgeu4(w4[j], thr_v));
+					m[j] = w4[j] == 0 ? 0u : ge_mask<MODE>(w4[j], minv);
 					c += __popc(m[j]) / BITS;
 				}
 				if (__ballot_sync(USB_FULL, c != 0) == 0)
@@ -281,13 +314,13 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 							continue;
 #pragma unroll
 						for (uint32_t d = 0; d < 4; ++d)
-							if (minv + d < 256)
-								h[d] += __popc(__vcmpeq4(w4[j], (minv + d) * 0x01010101u)) / 8;
-						uint32_t big = minv + 4 < 256 ? __vcmpgeu4(w4[j], (minv + 4) * 0x01010101u) : 0u;
+							if (minv + d <= CMASK)
+								h[d] += eq_count<WIDE ? BIG_BYTE : MODE>(w4[j], minv + d);
+						uint32_t big = minv + 4 <= CMASK ? ge_mask<MODE>(w4[j], minv + 4) : 0u;
 						while (big) {
-							const uint32_t b = (uint32_t)(__ffs(big) - 1) / 8;
-							big &= ~(0xffu << (b * 8));
-							atomicAdd(&S.hist[(w4[j] >> (b * 8)) & 0xffu], 1u);
+							const uint32_t b = (uint32_t)(__ffs(big) - 1) / BITS;
+							big &= ~(CMASK << (b * BITS));
+							atomicAdd(&S.hist[(w4[j] >> (b * BITS)) & CMASK], 1u);
 						}
 					}
 				}
@@ -320,7 +353,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 #pragma unroll
 				for (uint32_t d = 0; d < 4; ++d) {
 					const uint32_t sum = __reduce_add_sync(USB_FULL, h[d]);
-					if (lane == 0 && sum && minv + d < 256)
+					if (lane == 0 && sum && minv + d <= CMASK)
 						atomicAdd(&S.hist[minv + d], sum);
 				}
 			}
@@ -411,7 +444,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					for (uint32_t j = 0; j < 4; ++j) {
 						if (w4[j] == 0 || vstar >= CMASK)
 							continue;
-						uint32_t mask = WIDE ? __vcmpgeu2(w4[j], (vstar + 1) * 0x00010001u) : __vcmpgeu4(w4[j], (vstar + 1) * 0x01010101u);
+						uint32_t mask = ge_mask<MODE>(w4[j], vstar + 1);
 						while (mask) {
 							const uint32_t b = (uint32_t)(__ffs(mask) - 1) / BITS;
 							mask &= ~(CMASK << (b * BITS));
@@ -438,7 +471,7 @@ __device__ void rank_big_job(const RankBigArgs &a, uint32_t job, RankBigShared &
 					bool hit = false;
 					if (i < size) {
 						t = __ldg(row + i);
-						hit = ug_get<WIDE>(U, t) == vstar && first_row_of(a, S, t, k) == k;
+						hit = ug_get<MODE>(U, t) == vstar && first_row_of(a, S, t, k) == k;
 					}
 					const uint32_t rank = block_excl_scan_sum(hit ? 1u : 0u, S.warp_tmp);
 					const uint32_t already = S.taken;
@@ -561,9 +594,11 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) k_rank_big(const RankBigArgs 
 		}
 		__syncthreads();
 		if (n_rows > 255)
-			rank_big_job<true>(a, job, S, U, n_rows, Step);
+			rank_big_job<BIG_WIDE>(a, job, S, U, n_rows, Step);
+		else if (n_rows > 15 || a.variant == 2)
+			rank_big_job<BIG_BYTE>(a, job, S, U, n_rows, Step);
 		else
-			rank_big_job<false>(a, job, S, U, n_rows, Step);
+			rank_big_job<BIG_NIB>(a, job, S, U, n_rows, Step);
 	}
 }
 
