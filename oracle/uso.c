@@ -1875,7 +1875,86 @@ static float xdrop_bwd(uso_searcher *s, const uint8_t *A, unsigned LA, const uin
 	return Score;
 	}
 
-#define XD_MAXL 4096 /* xdpmem.h:6 g_MaxL: longer extensions take the Split path, not restated */
+#define XD_MAXL 4096 /* xdpmem.h:6 g_MaxL */
+
+/* xdropfwdsplit.cpp:15-22 GetSubL */
+static unsigned xd_sub_l(unsigned L)
+	{
+	if (L <= XD_MAXL)
+		return L;
+	if (L < 2 * XD_MAXL)
+		return L / 2;
+	return XD_MAXL;
+	}
+
+/* XDropFwdSplit (xdropfwdsplit.cpp:24-91): extensions of at most g_MaxL letters, one after the other */
+static float xdrop_fwd_split(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB, float X,
+  unsigned *Leni, unsigned *Lenj, char *path)
+	{
+	*Leni = 0;
+	*Lenj = 0;
+	path[0] = 0;
+	size_t n = 0;
+	char *sub = (char *) xrealloc(0, (size_t) 2 * XD_MAXL + 8);
+	float SumScore = 0.0f;
+	for (;;)
+		{
+		if (*Leni == LA || *Lenj == LB)
+			break;
+		unsigned SubLA = xd_sub_l(LA - *Leni), SubLB = xd_sub_l(LB - *Lenj);
+		unsigned SubLeni, SubLenj;
+		float Score = xdrop_fwd(s, A + *Leni, SubLA, B + *Lenj, SubLB, X, &SubLeni, &SubLenj, sub);
+		if (Score == 0.0f)
+			break;
+		SumScore += Score;
+		*Leni += SubLeni;
+		*Lenj += SubLenj;
+		size_t m = strlen(sub);
+		memcpy(path + n, sub, m);
+		n += m;
+		path[n] = 0;
+		if (SubLeni < SubLA && SubLenj < SubLB)
+			break;
+		}
+	free(sub);
+	return SumScore;
+	}
+
+/* XDropBwdSplit (xdropbwdsplit.cpp:15-79) */
+static float xdrop_bwd_split(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB, float X,
+  unsigned *Leni, unsigned *Lenj, char *path)
+	{
+	*Leni = 0;
+	*Lenj = 0;
+	path[0] = 0;
+	size_t n = 0;
+	char *sub = (char *) xrealloc(0, (size_t) 2 * XD_MAXL + 8);
+	float SumScore = 0.0f;
+	unsigned DoneA = 0, DoneB = 0;
+	for (;;)
+		{
+		if (DoneA == LA || DoneB == LB)
+			break;
+		unsigned SubLA = xd_sub_l(LA - DoneA), SubLB = xd_sub_l(LB - DoneB);
+		unsigned SubLeni, SubLenj;
+		float Score = xdrop_bwd(s, A + LA - DoneA - SubLA, SubLA, B + LB - DoneB - SubLB, SubLB, X, &SubLeni, &SubLenj, sub);
+		if (Score == 0.0f)
+			break;
+		SumScore += Score;
+		*Leni += SubLeni;
+		*Lenj += SubLenj;
+		size_t m = strlen(sub);
+		memmove(path + m, path, n + 1); /* PrependPath */
+		memcpy(path, sub, m);
+		n += m;
+		if (SubLeni < SubLA && SubLenj < SubLB)
+			break;
+		DoneA += SubLeni;
+		DoneB += SubLenj;
+		}
+	free(sub);
+	return SumScore;
+	}
 
 /* XDropAlignMemMaxL2 (xdropalignmem.cpp:26-216).  h4 = {Loi, Loj, Leni, Lenj}. */
 static float xdrop_align(uso_searcher *s, const uint8_t *A, unsigned LA, const uint8_t *B, unsigned LB,
@@ -1887,16 +1966,16 @@ static float xdrop_align(uso_searcher *s, const uint8_t *A, unsigned LA, const u
 	unsigned AncHii = AncLoi + AncLen - 1, AncHij = AncLoj + AncLen - 1;
 	const uint8_t *FwdA = A + AncHii, *FwdB = B + AncHij;
 	unsigned FwdLA = LA - AncHii, FwdLB = LB - AncHij;
-	if (AncLoi > XD_MAXL || AncLoj > XD_MAXL || FwdLA > XD_MAXL || FwdLB > XD_MAXL)
-		{
-		fprintf(stderr, "oracle: X-drop extension longer than %u letters (XDropFwdSplit/BwdSplit) is not restated\n", XD_MAXL);
-		abort();
-		}
-	char *bwd = (char *) xrealloc(0, (size_t) AncLoi + AncLoj + 4);
+	char *bwd = (char *) xrealloc(0, (size_t) AncLoi + AncLoj + 8);
 	char *fwd = (char *) xrealloc(0, (size_t) FwdLA + FwdLB + 4);
 	unsigned BwdLeni, BwdLenj, FwdLeni, FwdLenj;
-	float BwdScore = xdrop_bwd(s, A, AncLoi + 1, B, AncLoj + 1, X, &BwdLeni, &BwdLenj, bwd);
-	float FwdScore = xdrop_fwd(s, FwdA, FwdLA, FwdB, FwdLB, X, &FwdLeni, &FwdLenj, fwd);
+	/* xdropalignmem.cpp:87-139 */
+	float BwdScore = (AncLoi > XD_MAXL || AncLoj > XD_MAXL)
+	  ? xdrop_bwd_split(s, A, AncLoi + 1, B, AncLoj + 1, X, &BwdLeni, &BwdLenj, bwd)
+	  : xdrop_bwd(s, A, AncLoi + 1, B, AncLoj + 1, X, &BwdLeni, &BwdLenj, bwd);
+	float FwdScore = (FwdLA > XD_MAXL || FwdLB > XD_MAXL)
+	  ? xdrop_fwd_split(s, FwdA, FwdLA, FwdB, FwdLB, X, &FwdLeni, &FwdLenj, fwd)
+	  : xdrop_fwd(s, FwdA, FwdLA, FwdB, FwdLB, X, &FwdLeni, &FwdLenj, fwd);
 	size_t n = 0;
 	for (const char *p = bwd; *p; ++p) path[n++] = *p;
 	for (unsigned k = 0; k + 2 < AncLen; ++k) path[n++] = 'M';
