@@ -140,6 +140,45 @@ def test_local_pairs_stage():
     assert {(int(a["first_mq"]), int(a["first_mt"])), (int(b["first_mq"]), int(b["first_mt"]))} == {(0, 150), (150, 0)}
 
 
+@pytest.mark.parametrize("variant", list(util.LOCAL_LONG_VARIANTS))
+def test_local_split_extensions_match_reference_golden(variant):
+    """Sequences above g_MaxL = 4096 letters (up to 20 000 here): extensions longer than g_MaxL are split
+    (xdropalignmem.cpp:87-139 -> XDropFwdSplit / XDropBwdSplit); letters and word keys of the long mode
+    live in the per-warp slab.  Output lines identical to the reference binary's."""
+    kw = dict(util.LOCAL_LONG_VARIANTS[variant])
+    nucleo = kw.pop("nucleo")
+    evalue = kw.pop("evalue")
+    g = util.GoldenLocal("nt" if nucleo else "aa", prefix="loclong")
+    ix, s = _searchers(g.db, nucleo, evalue, **kw)
+    res = s.search(g.q)
+    got = util.product_lines_local(res, s, g.q_labels, g.q, g.db_labels, nucleo)
+    for lines, kind in zip(got, ("user", "uc", "b6")):
+        d = util.first_diff(lines, g.lines(variant, kind))
+        assert d is None, "%s %s\n%s" % (variant, kind, d)
+    assert max(int(l.split("\t")[3]) for l in got[0]) > 4096
+
+
+def test_local_long_and_short_sequences_in_one_database():
+    """A batch whose longest sequence is above g_MaxL switches the whole batch to the long mode: the short
+    pairs in it must give what the normal mode gives (oracle, seeded inputs)."""
+    from oracle import uso_py as O
+    rng = random.Random(31)
+    g = util.GoldenLocal("nt")
+    db = list(g.db[:60]) + ["".join(rng.choice("ACGT") for _ in range(9000))]
+    qs = list(g.q[:80]) + [util.mutate(db[-1][1000:8000], 0.05, rng)]
+    labels = ["q%d" % i for i in range(len(qs))]
+    dbl = ["t%d" % i for i in range(len(db))]
+    ix, s = _searchers(db, True, 1e-5, id=0.8, strand_both=1)
+    res = s.search(qs)
+    got = util.product_lines_local(res, s, labels, qs, dbl, True)
+    op = util.oracle_local_params(True, id=0.8, evalue=1e-5, strand_both=1)
+    osr = O.Searcher(O.DB(db, op, dbl), op)
+    want = util.oracle_lines_local(osr, labels, qs, dbl, True)
+    for a, b, kind in zip(got, want, ("user", "uc", "b6")):
+        assert util.first_diff(a, b) is None, kind
+    assert len(got[0]) > 40
+
+
 @pytest.mark.parametrize("variant", ["loc_aa_e5", "loc_nt_both"])
 def test_local_cli_output_files_byte_identical_to_reference(variant, tmp_path):
     """The C++ host driver (usearch12_b200_cli -usearch_local) writes the reference's files."""

@@ -41,6 +41,21 @@ def test_oracle_local_matches_reference_golden(variant):
         assert util.first_diff(lines, g.lines(variant, kind)) is None, kind
 
 
+@pytest.mark.parametrize("variant", list(util.LOCAL_LONG_VARIANTS))
+def test_oracle_local_split_extensions_match_reference_golden(variant):
+    """Sequences above g_MaxL = 4096 letters: XDropFwdSplit / XDropBwdSplit (xdropfwdsplit.cpp:24-91,
+    xdropbwdsplit.cpp:15-79) vs the reference binary's outputs (tools/make_golden_local_long.py)."""
+    kw = dict(util.LOCAL_LONG_VARIANTS[variant])
+    nucleo = kw.pop("nucleo")
+    g = util.GoldenLocal("nt" if nucleo else "aa", prefix="loclong")
+    p = util.oracle_local_params(nucleo, **kw)
+    s = O.Searcher(O.DB(g.db, p, g.db_labels), p)
+    got = util.oracle_lines_local(s, g.q_labels, g.q, g.db_labels, nucleo)
+    for lines, kind in zip(got, ("user", "uc", "b6")):
+        assert util.first_diff(lines, g.lines(variant, kind)) is None, kind
+    assert max(int(l.split("\t")[3]) for l in got[0]) > 4096
+
+
 @pytest.mark.parametrize("variant", list(util.AA_GLOBAL_VARIANTS))
 def test_oracle_aa_global_matches_reference_golden(variant):
     """Amino acid usearch_global (BASELINE config 1 = cfg1_id90) vs the reference binary's outputs

@@ -168,10 +168,17 @@ LOCAL_VARIANTS = {
 }
 
 
+# sequences above g_MaxL = 4096 letters: split X-drop extensions (tools/make_golden_local_long.py)
+LOCAL_LONG_VARIANTS = {
+    "loclong_nt_both": dict(nucleo=True, id=0.7, evalue=1e-5, maxaccepts=2, maxrejects=16, strand_both=1),
+    "loclong_aa_e5": dict(nucleo=False, id=0.5, evalue=1e-5),
+}
+
+
 class GoldenLocal:
-    def __init__(self, kind):
-        self.db_labels, self.db = read_fasta(os.path.join(GOLDEN, "loc_%s_db.fa.gz" % kind))
-        self.q_labels, self.q = read_fasta(os.path.join(GOLDEN, "loc_%s_q.fa.gz" % kind))
+    def __init__(self, kind, prefix="loc"):
+        self.db_labels, self.db = read_fasta(os.path.join(GOLDEN, "%s_%s_db.fa.gz" % (prefix, kind)))
+        self.q_labels, self.q = read_fasta(os.path.join(GOLDEN, "%s_%s_q.fa.gz" % (prefix, kind)))
 
     def lines(self, variant, kind):
         with gzip.open(os.path.join(GOLDEN, "%s.%s.gz" % (variant, kind)), "rt") as f:

@@ -1392,7 +1392,8 @@ static void fill_align_args(usb_searcher *s, const AlignGeom &g, uint32_t hsp_ca
 
 struct LocalGeom {
 	int wpb;
-	uint32_t ql_cap, tl_cap, qk_cap, fast_bytes, tb_cap;
+	bool long_mode;
+	uint32_t ql_cap, tl_cap, qk_cap, row_cap, fast_bytes, tb_cap;
 	size_t smem;
 	uint64_t slab_stride;
 	uint32_t n_warps, grid;
@@ -1400,16 +1401,20 @@ struct LocalGeom {
 
 static int local_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, LocalGeom &g)
 {
-	if (max_ql > LOCAL_MAXL || max_tl > LOCAL_MAXL)
-		return fail(USB_ELIMIT,
-		  "usearch_local supports sequences up to %u letters (query %u, target %u): longer X-drop extensions take the "
-		  "reference's split path, which is not built", LOCAL_MAXL, max_ql, max_tl);
+	// Sequences above g_MaxL letters (xdpmem.h:6): extensions are split into pieces of at most g_MaxL
+	// columns (xdropfwdsplit.cpp, xdropbwdsplit.cpp), so the DP rows keep their size; letters and word
+	// keys of the whole sequences move from shared memory to the per-warp slab.
+	g.long_mode = max_ql > LOCAL_MAXL || max_tl > LOCAL_MAXL;
+	if (max_ql > LOCAL_LONG_MAX || max_tl > LOCAL_LONG_MAX)
+		return fail(USB_ELIMIT, "usearch_local supports sequences up to %u letters (query %u, target %u)", LOCAL_LONG_MAX, max_ql,
+		  max_tl);
 	g.ql_cap = lpad16(max_ql + 16);
 	g.tl_cap = lpad16(max_tl + 16);
+	g.row_cap = g.long_mode ? std::min<uint32_t>(g.tl_cap, lpad16(LOCAL_MAXL + 16)) : g.tl_cap;
 	g.qk_cap = 32;
 	while (g.qk_cap < max_ql + 1)
 		g.qk_cap <<= 1;
-	g.fast_bytes = lpad16(local_fast_bytes(g.ql_cap, g.tl_cap, g.qk_cap));
+	g.fast_bytes = lpad16(local_fast_bytes(g.ql_cap, g.tl_cap, g.qk_cap, g.row_cap, g.long_mode));
 	const size_t fixed = (sizeof(LocalShared) + 15) & ~(size_t)15;
 	const size_t budget = s->smem_optin > fixed + 1024 ? s->smem_optin - fixed - 1024 : 0;
 	g.wpb = (int)std::min<size_t>(LOCAL_MAX_WARPS, budget / g.fast_bytes);
@@ -1418,7 +1423,7 @@ static int local_geometry(usb_searcher *s, uint32_t max_ql, uint32_t max_tl, Loc
 	g.smem = fixed + (size_t)g.wpb * g.fast_bytes;
 	const uint64_t full = ((uint64_t)max_ql + 1) * ((uint64_t)max_tl + 2) + 64;
 	g.tb_cap = (uint32_t)std::min<uint64_t>(full, (uint64_t)32 << 20);
-	g.slab_stride = (local_slab_bytes(g.ql_cap, g.tl_cap, g.tb_cap) + 255) & ~(uint64_t)255;
+	g.slab_stride = (local_slab_bytes(g.ql_cap, g.tl_cap, g.tb_cap, g.qk_cap, g.long_mode) + 255) & ~(uint64_t)255;
 	g.grid = (uint32_t)s->num_sms;
 	g.n_warps = g.grid * g.wpb;
 	size_t free_b = 0, total_b = 0;
@@ -1458,6 +1463,8 @@ static void fill_local_args(usb_searcher *s, const LocalGeom &g, LocalArgs &a)
 	a.tl_cap = g.tl_cap;
 	a.qk_cap = g.qk_cap;
 	a.fast_bytes = g.fast_bytes;
+	a.long_mode = g.long_mode ? 1u : 0u;
+	a.row_cap = g.row_cap;
 	a.tb_cap = g.tb_cap;
 	a.xdrop_u = s->P.xdrop_u;
 	a.xdrop_g = s->P.xdrop_g;

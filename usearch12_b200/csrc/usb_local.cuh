@@ -35,7 +35,8 @@ namespace usb {
 #define LOCAL_MAX_AR 32
 #define LOCAL_SEEDQ 64
 #define LOCAL_MAX_WARPS 16
-#define LOCAL_MAXL 4096   // xdpmem.h:6 g_MaxL: longer extensions take the Split path (not built)
+#define LOCAL_MAXL 4096   // xdpmem.h:6 g_MaxL: longer extensions are split (XDropFwdSplit / XDropBwdSplit)
+#define LOCAL_LONG_MAX 65000 // longest sequence of the long mode (positions are packed in 16 bits)
 
 struct LocalDevTables {
 	int8_t score[USB_NCODE * USB_NCODE];
@@ -69,6 +70,8 @@ struct LocalArgs {
 	uint64_t slab_stride;
 	uint32_t ql_cap, tl_cap, qk_cap; // padded capacities (letters, letters, sorted word keys = power of two)
 	uint32_t fast_bytes;
+	uint32_t long_mode;              // sequences above LOCAL_MAXL: letters and word keys live in the slab
+	uint32_t row_cap;                // columns of the DP rows (tl_cap, or LOCAL_MAXL + 16 in long mode)
 	uint32_t tb_cap;                 // trace bytes per warp
 	float xdrop_u, xdrop_g;          // -xdrop_u, -xdrop_g
 	float abs_open_f, abs_ext_f;
@@ -97,24 +100,33 @@ struct LocalWs {
 
 inline __host__ __device__ uint32_t lpad16(uint32_t x) { return (x + 15u) & ~15u; }
 
-inline __host__ __device__ uint32_t local_fast_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t qk_cap)
+// Long mode (a sequence above LOCAL_MAXL letters): the DP rows stay in shared memory -- an extension never
+// spans more than LOCAL_MAXL columns, longer ones are split -- but the letters and the sorted word keys of
+// whole sequences move to the slab.
+inline __host__ __device__ uint32_t local_fast_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t qk_cap, uint32_t row_cap,
+  bool long_mode)
 {
-	return ql_cap + tl_cap + 4 * qk_cap + 2 * lpad16(4 * (tl_cap + 8)) + 4 * LOCAL_SEEDQ;
+	const uint32_t rows = 2 * lpad16(4 * (row_cap + 8)) + 4 * LOCAL_SEEDQ;
+	return long_mode ? rows : ql_cap + tl_cap + 4 * qk_cap + rows;
 }
 
-inline __host__ __device__ uint64_t local_slab_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t tb_cap)
+inline __host__ __device__ uint64_t local_slab_bytes(uint32_t ql_cap, uint32_t tl_cap, uint32_t tb_cap, uint32_t qk_cap,
+  bool long_mode)
 {
-	return (uint64_t)lpad16(tb_cap) + 3ull * lpad16(4 * (ql_cap + 8)) + 2ull * lpad16(ql_cap + tl_cap + 16);
+	return (uint64_t)lpad16(tb_cap) + 3ull * lpad16(4 * (ql_cap + 8)) + 2ull * lpad16(ql_cap + tl_cap + 16) +
+	       (long_mode ? (uint64_t)ql_cap + tl_cap + 4ull * qk_cap : 0ull);
 }
 
 __device__ __forceinline__ void local_ws_setup(const LocalArgs &a, LocalWs &w, uint8_t *fast, uint8_t *slab)
 {
 	uint8_t *p = fast;
-	w.A = p; p += a.ql_cap;
-	w.B = p; p += a.tl_cap;
-	w.qk = (uint32_t *)p; p += 4 * a.qk_cap;
-	w.Mrow = (int *)p; p += lpad16(4 * (a.tl_cap + 8));
-	w.Drow = (int *)p; p += lpad16(4 * (a.tl_cap + 8));
+	if (!a.long_mode) {
+		w.A = p; p += a.ql_cap;
+		w.B = p; p += a.tl_cap;
+		w.qk = (uint32_t *)p; p += 4 * a.qk_cap;
+	}
+	w.Mrow = (int *)p; p += lpad16(4 * (a.row_cap + 8));
+	w.Drow = (int *)p; p += lpad16(4 * (a.row_cap + 8));
 	w.seedq = (uint32_t *)p;
 	uint8_t *s = slab;
 	w.tb = s; s += lpad16(a.tb_cap);
@@ -122,7 +134,12 @@ __device__ __forceinline__ void local_ws_setup(const LocalArgs &a, LocalWs &w, u
 	w.rowhi = (uint32_t *)s; s += lpad16(4 * (a.ql_cap + 8));
 	w.rowoff = (uint32_t *)s; s += lpad16(4 * (a.ql_cap + 8));
 	w.path = (char *)s; s += lpad16(a.ql_cap + a.tl_cap + 16);
-	w.tmp = (char *)s;
+	w.tmp = (char *)s; s += lpad16(a.ql_cap + a.tl_cap + 16);
+	if (a.long_mode) {
+		w.A = s; s += a.ql_cap;
+		w.B = s; s += a.tl_cap;
+		w.qk = (uint32_t *)s;
+	}
 }
 
 __device__ __forceinline__ int clampneg(int x) { return x < USB_NEG / 2 ? USB_NEG : x; }
@@ -522,6 +539,54 @@ struct LocalHsp {
 
 // XDropAlignMemMaxL2 (xdropalignmem.cpp:26-216): w.path receives the whole path; returns its length
 // (0 = no alignment).
+// xdropfwdsplit.cpp:15-22 GetSubL
+__device__ __forceinline__ uint32_t local_sub_l(uint32_t L)
+{
+	if (L <= LOCAL_MAXL)
+		return L;
+	if (L < 2 * LOCAL_MAXL)
+		return L / 2;
+	return LOCAL_MAXL;
+}
+
+// One extension of XDropAlignMemMaxL2 in one direction (dir = -1 backward from (i0, j0) over la x lb
+// letters, +1 forward), the piece XDropFwdFastMem / XDropBwdFastMem compute: score, lengths and the path
+// in w.tmp -- in raw traceback order, which is the forward order of the sequences for the backward
+// extension and the reverse of it for the forward one.  *m = path length; false = trace arena full.
+__device__ bool xdrop_piece(const LocalArgs &a, const LocalShared &S, LocalWs &w, uint32_t i0, uint32_t j0, int dir, uint32_t la,
+  uint32_t lb, int &score, uint32_t &leni, uint32_t &lenj, uint32_t &m, usb_qstat &st)
+{
+	const uint32_t lane = lane_id();
+	if (la == 1 || lb == 1) {
+		score = S.score[w.A[i0] * USB_NCODE + w.B[j0]];
+		leni = 1;
+		lenj = 1;
+		if (lane == 0)
+			w.tmp[0] = 'M';
+		m = 1;
+		__syncwarp();
+		return true;
+	}
+	uint32_t bi, bj, rows = 0, cells = 0;
+	score = xdrop_dp(a, S, w, w.A + i0, dir, la, w.B + j0, dir, lb, bi, bj, rows, cells);
+	++st.n_dp;
+	st.dp_cells += cells;
+	if (score <= 0) {
+		score = 0;
+		leni = 0;
+		lenj = 0;
+		m = 0;
+		return true;
+	}
+	m = xdrop_traceback(a, w, bi, bj, rows, w.tmp, a.ql_cap + a.tl_cap);
+	if (m == 0)
+		return false;
+	leni = bi + 1;
+	lenj = bj + 1;
+	__syncwarp();
+	return true;
+}
+
 __device__ uint32_t xdrop_align(const LocalArgs &a, const LocalShared &S, LocalWs &w, uint32_t AncLoi, uint32_t AncLoj,
   uint32_t AncLen, LocalHsp &H, usb_qstat &st)
 {
@@ -532,73 +597,84 @@ __device__ uint32_t xdrop_align(const LocalArgs &a, const LocalShared &S, LocalW
 	const uint32_t LA = w.LA, LB = w.LB;
 	const uint32_t AncHii = AncLoi + AncLen - 1, AncHij = AncLoj + AncLen - 1;
 	uint32_t n = 0;
-	// backward: prefixes A[0..AncLoi], B[0..AncLoj] reversed
-	uint32_t BwdLeni, BwdLenj;
-	int BwdScore;
+	// backward: prefixes A[0..AncLoi], B[0..AncLoj] reversed; above g_MaxL letters in pieces, each piece
+	// in front of the ones before it (XDropBwdSplit, xdropbwdsplit.cpp:15-79: PrependPath)
+	uint32_t BwdLeni = 0, BwdLenj = 0;
+	int BwdScore = 0;
 	{
 		const uint32_t la = AncLoi + 1, lb = AncLoj + 1;
-		if (la == 1 || lb == 1) {
-			BwdScore = S.score[w.A[AncLoi] * USB_NCODE + w.B[AncLoj]];
-			BwdLeni = 1;
-			BwdLenj = 1;
-			if (lane == 0)
-				w.path[0] = 'M';
-			n = 1;
-		} else {
-			uint32_t bi, bj, rows = 0, cells = 0;
-			BwdScore = xdrop_dp(a, S, w, w.A + AncLoi, -1, la, w.B + AncLoj, -1, lb, bi, bj, rows, cells);
-			++st.n_dp;
-			st.dp_cells += cells;
-			if (BwdScore <= 0) {
-				BwdScore = 0;
-				BwdLeni = 0;
-				BwdLenj = 0;
-			} else {
-				// raw traceback order of the reversed problem == forward order of the original
-				n = xdrop_traceback(a, w, bi, bj, rows, w.path, a.ql_cap + a.tl_cap);
-				if (n == 0)
-					return 0;
-				BwdLeni = bi + 1;
-				BwdLenj = bj + 1;
+		const bool split = AncLoi > LOCAL_MAXL || AncLoj > LOCAL_MAXL; // xdropalignmem.cpp:87
+		uint32_t doneA = 0, doneB = 0;
+		for (;;) {
+			if (split && (doneA == la || doneB == lb))
+				break;
+			const uint32_t sla = split ? local_sub_l(la - doneA) : la, slb = split ? local_sub_l(lb - doneB) : lb;
+			int sc;
+			uint32_t li, lj, m;
+			if (!xdrop_piece(a, S, w, AncLoi - doneA, AncLoj - doneB, -1, sla, slb, sc, li, lj, m, st))
+				return 0;
+			if (split && sc == 0)
+				break;
+			BwdScore += sc;
+			BwdLeni += li;
+			BwdLenj += lj;
+			if (m) {
+				// shift what is there to the right by m (from the end, 32 letters at a time), piece in front
+				for (uint32_t k = n; k > 0;) {
+					const uint32_t c = min(32u, k);
+					char ch = 0;
+					if (lane < c)
+						ch = w.path[k - c + lane];
+					__syncwarp();
+					if (lane < c)
+						w.path[k - c + lane + m] = ch;
+					__syncwarp();
+					k -= c;
+				}
+				for (uint32_t k = lane; k < m; k += 32)
+					w.path[k] = w.tmp[k];
+				n += m;
+				__syncwarp();
 			}
+			if (!split || (li < sla && lj < slb))
+				break;
+			doneA += li;
+			doneB += lj;
 		}
 	}
 	// the anchor without its first and last column (they belong to the two extensions)
 	for (uint32_t k = lane; k + 2 < AncLen; k += 32)
 		w.path[n + k] = 'M';
 	n += AncLen - 2;
-	// forward: suffixes from the last anchor column
-	uint32_t FwdLeni, FwdLenj;
-	int FwdScore;
+	// forward: suffixes from the last anchor column (XDropFwdSplit, xdropfwdsplit.cpp:24-91: AppendPath)
+	uint32_t FwdLeni = 0, FwdLenj = 0;
+	int FwdScore = 0;
 	{
 		const uint32_t la = LA - AncHii, lb = LB - AncHij;
-		if (la == 1 || lb == 1) {
-			FwdScore = S.score[w.A[AncHii] * USB_NCODE + w.B[AncHij]];
-			FwdLeni = 1;
-			FwdLenj = 1;
-			if (lane == 0)
-				w.path[n] = 'M';
-			n += 1;
-		} else {
-			uint32_t bi, bj, rows = 0, cells = 0;
-			FwdScore = xdrop_dp(a, S, w, w.A + AncHii, 1, la, w.B + AncHij, 1, lb, bi, bj, rows, cells);
-			++st.n_dp;
-			st.dp_cells += cells;
-			if (FwdScore <= 0) {
-				FwdScore = 0;
-				FwdLeni = 0;
-				FwdLenj = 0;
-			} else {
-				const uint32_t m = xdrop_traceback(a, w, bi, bj, rows, w.tmp, a.ql_cap + a.tl_cap);
-				if (m == 0)
-					return 0;
-				__syncwarp();
+		const bool split = la > LOCAL_MAXL || lb > LOCAL_MAXL; // xdropalignmem.cpp:120
+		for (;;) {
+			if (split && (FwdLeni == la || FwdLenj == lb))
+				break;
+			const uint32_t sla = split ? local_sub_l(la - FwdLeni) : la, slb = split ? local_sub_l(lb - FwdLenj) : lb;
+			int sc;
+			uint32_t li, lj, m;
+			if (!xdrop_piece(a, S, w, AncHii + FwdLeni, AncHij + FwdLenj, 1, sla, slb, sc, li, lj, m, st))
+				return 0;
+			if (split && sc == 0)
+				break;
+			FwdScore += sc;
+			FwdLeni += li;
+			FwdLenj += lj;
+			if (m == 1 && (sla == 1 || slb == 1)) {
+				if (lane == 0)
+					w.path[n] = 'M';
+			} else
 				for (uint32_t k = lane; k < m; k += 32)
 					w.path[n + k] = w.tmp[m - 1 - k];
-				n += m;
-				FwdLeni = bi + 1;
-				FwdLenj = bj + 1;
-			}
+			n += m;
+			__syncwarp();
+			if (!split || (li < sla && lj < slb))
+				break;
 		}
 	}
 	__syncwarp();
