@@ -118,10 +118,12 @@ def test_local_degenerate_batches_and_split_invariance():
     assert key(whole) == key(parts[0]) + key(parts[1])
     again = s.search(qs)
     assert key(whole) == key(again)
-    # sequences longer than the X-drop split limit are refused loudly, not silently mis-aligned
+    # sequences above g_MaxL letters run in the long mode (split extensions); beyond the 16-bit position
+    # limit they are refused loudly, not silently mis-aligned
     from usearch12_b200 import capi
+    assert len(s.search(["ACDEFGHIKL" * 500]).qoff) == 2
     with pytest.raises(capi.UsbError):
-        s.search(["ACDEFGHIKL" * 500])
+        s.search(["ACDEFGHIKL" * 7000])
 
 
 def test_local_pairs_stage():
