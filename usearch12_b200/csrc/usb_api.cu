@@ -379,10 +379,10 @@ static void fill_index_view(const usb_index *ix, IndexView &v)
 // Result arrays are not value-initialised on resize (the download overwrites them); they are plain
 // pageable memory: page-locking a fresh 100 MB result costs more (about 1.3 ms per MB here) than
 // copying it out of the searcher's one page-locked staging buffer.
-template <class T> struct PinnedNoInit {
+template <class T> struct NoInitAlloc {
 	using value_type = T;
-	PinnedNoInit() = default;
-	template <class U> PinnedNoInit(const PinnedNoInit<U> &) {}
+	NoInitAlloc() = default;
+	template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
 	T *allocate(size_t n)
 	{
 		void *p = aligned_alloc(64, (n * sizeof(T) + 63) & ~(size_t)63);
@@ -393,16 +393,16 @@ template <class T> struct PinnedNoInit {
 	void deallocate(T *q, size_t) { free(q); }
 	template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
 	template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
-	template <class U> bool operator==(const PinnedNoInit<U> &) const { return true; }
-	template <class U> bool operator!=(const PinnedNoInit<U> &) const { return false; }
+	template <class U> bool operator==(const NoInitAlloc<U> &) const { return true; }
+	template <class U> bool operator!=(const NoInitAlloc<U> &) const { return false; }
 };
-template <class T> using PinVec = std::vector<T, PinnedNoInit<T>>;
+template <class T> using NoInitVec = std::vector<T, NoInitAlloc<T>>;
 
 struct usb_result {
-	PinVec<usb_hit> hits;
-	PinVec<uint32_t> runs;
-	PinVec<uint64_t> qoff;
-	PinVec<usb_qstat> qstat;
+	NoInitVec<usb_hit> hits;
+	NoInitVec<uint32_t> runs;
+	NoInitVec<uint64_t> qoff;
+	NoInitVec<usb_qstat> qstat;
 };
 
 struct usb_searcher {
@@ -1904,7 +1904,7 @@ static void quicksort_desc(const float *v, uint32_t *ord, int lo, int hi)
 		quicksort_desc(v, ord, i, hi);
 }
 
-static void order_hits_like_hitmgr(PinVec<usb_hit> &hits, const PinVec<uint64_t> &qoff, bool local)
+static void order_hits_like_hitmgr(NoInitVec<usb_hit> &hits, const NoInitVec<uint64_t> &qoff, bool local)
 {
 	std::vector<float> sc;
 	std::vector<uint32_t> ord;
