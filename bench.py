@@ -52,17 +52,59 @@ def workload_name(a):
 
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs: NVML in a thread of
+    this process (an nvidia-smi child per rank takes a second to start and holds driver locks that
+    stretch an 80 ms step at 8 GPUs by ~15 ms); nvidia-smi -lms only where pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    _nvml = None
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []      # nvidia-smi lines
+        self.samples = []   # (sm MHz, max MHz, reasons bitmask) from NVML
         self.proc = None
+        self.handle = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            if ClockSampler._nvml is None:
+                pynvml.nvmlInit()
+                ClockSampler._nvml = pynvml
+            nv = ClockSampler._nvml
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.handle = None
+
+    def _sample(self):
+        nv = ClockSampler._nvml
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            try:
+                why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((sm, self.max_mhz, why))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            self._sample()
+            self.stop_flag.wait(0.02)
 
     def start(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -77,6 +119,16 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.handle is not None:
+            self._sample()  # at least one sample inside the region, however short it was
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(n for n in names if any(x[2] & bits[n] for x in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz if sm else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +137,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
                 continue
@@ -98,7 +149,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------- reference arm
@@ -466,9 +517,9 @@ def main():
 
     def timed_pass(e2e_off):
         """W warm-up + K timed device steps on the uploaded batch, then K end-to-end steps."""
+        sampler = ClockSampler(local_rank)  # (NVML handle set up before the warm-up, outside the timed region)
         for _ in range(a.warmup):
             device_step()
-        sampler = ClockSampler(local_rank)
         sync_all()
         sampler.start()
         launches0 = s.launch_count
