@@ -46,6 +46,31 @@ VARIANTS = {
 }
 
 
+# The same rules on the other candidate loops: -usearch_local (nucleotide and protein) and amino acid
+# -usearch_global.  (With -usearch_local the reference binary dies with SIGSEGV -- or survives with
+# corrupted results -- as soon as a RejectPair rule rejects a pair: -self, -notself, -selfid,
+# -min_sizeratio, -minqt/-maxqt, -minsl/-maxsl.  No golden files for those; the library refuses them in
+# local mode.)  name -> (command, query file, database file, options); inputs are existing fixtures.
+VARIANTS2 = {
+    "accl_nt_cov": ("-usearch_local", "loc_nt_q.fa.gz", "loc_nt_db.fa.gz",
+                    ["-id", "0.8", "-evalue", "1e-3", "-strand", "both", "-maxaccepts", "3", "-maxrejects", "8", "-query_cov", "0.9",
+                     "-maxgaps", "2"]),
+    "accl_nt_skew": ("-usearch_local", "acc_q.fa.gz", "acc_db.fa.gz",
+                     ["-id", "0.8", "-evalue", "1e-3", "-strand", "plus", "-maxaccepts", "2", "-maxrejects", "8", "-abskew", "2.0",
+                      "-max_target_cov", "0.9"]),
+    "accl_aa_tcov": ("-usearch_local", "loc_aa_q.fa.gz", "loc_aa_db.fa.gz",
+                     ["-id", "0.3", "-evalue", "10", "-maxaccepts", "4", "-maxrejects", "64", "-target_cov", "0.5", "-mincols", "100",
+                      "-maxdiffs", "120"]),
+    "accl_aa_maxid": ("-usearch_local", "loc_aa_q.fa.gz", "loc_aa_db.fa.gz",
+                      ["-id", "0.5", "-evalue", "1e-5", "-maxaccepts", "2", "-maxrejects", "8", "-maxid", "0.97",
+                       "-mindiffs", "2", "-max_query_cov", "0.99"]),
+    "accg_aa_diffs": ("-usearch_global", "loc_aa_q.fa.gz", "loc_aa_db.fa.gz",
+                      ["-id", "0.5", "-maxaccepts", "4", "-maxrejects", "16", "-maxid", "0.95", "-mindiffs", "3", "-query_cov", "0.8"]),
+    "accg_aa_qt": ("-usearch_global", "loc_aa_q.fa.gz", "loc_aa_db.fa.gz",
+                   ["-id", "0.3", "-maxaccepts", "8", "-maxrejects", "32", "-minqt", "0.8", "-maxqt", "1.2", "-selfid"]),
+}
+
+
 def build_inputs():
     g = util.Golden()
     rng = random.Random(20261020)
@@ -84,6 +109,21 @@ def main():
                 fo.write(fi.read())
         for name, extra in VARIANTS.items():
             cmd = [REF, "-usearch_global", os.path.join(tmp, "q.fa"), "-db", os.path.join(tmp, "db.fa"), "-threads", "1", "-quiet",
+                   "-uc", os.path.join(tmp, "uc"), "-blast6out", os.path.join(tmp, "b6"), "-userout", os.path.join(tmp, "user"),
+                   "-userfields", USERFIELDS] + extra
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            sizes = []
+            for x in ("user", "uc", "b6"):
+                data = open(os.path.join(tmp, x), "rb").read()
+                sizes.append(data.count(b"\n"))
+                with gzip.GzipFile(os.path.join(OUT, "%s.%s.gz" % (name, x)), "wb", compresslevel=9, mtime=0) as fo:
+                    fo.write(data)
+            print("golden", name, sizes)
+        for name, (cmdname, qf, df, extra) in VARIANTS2.items():
+            for src, dst in ((qf, "q2.fa"), (df, "d2.fa")):
+                with gzip.open(os.path.join(OUT, src), "rb") as fi, open(os.path.join(tmp, dst), "wb") as fo:
+                    fo.write(fi.read())
+            cmd = [REF, cmdname, os.path.join(tmp, "q2.fa"), "-db", os.path.join(tmp, "d2.fa"), "-threads", "1", "-quiet",
                    "-uc", os.path.join(tmp, "uc"), "-blast6out", os.path.join(tmp, "b6"), "-userout", os.path.join(tmp, "user"),
                    "-userfields", USERFIELDS] + extra
             subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)

@@ -1468,6 +1468,94 @@ __device__ bool emit_runs(const AlignArgs &a, const WarpWs &w, uint32_t n, usb_h
 	return true;
 }
 
+// ------------------------------------------------------------------ Accepter rules (all candidate loops)
+#define ACC_PAIR_FLAGS (USB_ACC_SELF | USB_ACC_NOTSELF | USB_ACC_SELFID | USB_ACC_MIN_SIZERATIO | USB_ACC_MINQT | \
+                        USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)
+#define ERR_KCAP 1024u // skipped pairs used up the materialised candidates before the Terminator fired
+
+// Accepter::RejectPair (accepter.cpp:145-197): rules on the pair itself, before any alignment.
+// Q = raw query letters, L its length; the target's raw (masked) letters come from the database.
+template <class Args>
+__device__ bool reject_pair(const Args &a, uint32_t qi, uint32_t strand, uint32_t t, const uint8_t *Q, uint32_t L)
+{
+	const DevParams &P = a.P;
+	const uint32_t f = P.accept_flags;
+	if ((f & USB_ACC_SELF) && a.q_label[qi] == a.t_label[t])
+		return true;
+	if ((f & USB_ACC_NOTSELF) && a.q_label[qi] != a.t_label[t])
+		return true;
+	const uint32_t TL = a.db_len[t];
+	if ((f & USB_ACC_SELFID) && TL == L) { // same length and the same letters, byte for byte
+		const uint8_t *T = a.db_seq + a.db_off[t];
+		bool diff = false;
+		for (uint32_t i = lane_id(); i < L; i += 32) {
+			const uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
+			diff |= c != (uint32_t)T[i];
+		}
+		if (!__any_sync(USB_FULL, diff))
+			return true;
+	}
+	if (f & USB_ACC_MIN_SIZERATIO) {
+		const double Ratio = (double)a.t_size[t] / (double)a.q_size[qi];
+		if (Ratio < P.min_sizeratio_d)
+			return true;
+	}
+	if (f & (USB_ACC_MINQT | USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)) {
+		const double q = (double)L, tt = (double)TL;
+		const double s = (double)min(L, TL), l = (double)max(L, TL);
+		const double qt = q / tt, sl = s / l;
+		if ((f & USB_ACC_MINQT) && qt < P.minqt_d)
+			return true;
+		if ((f & USB_ACC_MAXQT) && qt > P.maxqt_d)
+			return true;
+		if ((f & USB_ACC_MINSL) && sl < P.minsl_d)
+			return true;
+		if ((f & USB_ACC_MAXSL) && sl > P.maxsl_d)
+			return true;
+	}
+	return false;
+}
+
+// Accepter::IsAcceptLo (accepter.cpp:41-94) on the statistics of an alignment.
+template <class Args>
+__device__ __forceinline__ bool accept_hit(const Args &a, const usb_hit &h, uint32_t qi, bool local = false)
+{
+	const DevParams &P = a.P;
+	const uint32_t f = P.accept_flags;
+	const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
+	if (fid < P.id_d)
+		return false;
+	if ((f & USB_ACC_MAXID) && fid > P.maxid_d)
+		return false;
+	if ((f & USB_ACC_MINCOLS) && h.alnlen < P.mincols)
+		return false;
+	if ((f & USB_ACC_MAXGAPS) && h.intgaps > P.maxgaps)
+		return false;
+	if (f & (USB_ACC_QUERY_COV | USB_ACC_MAX_QUERY_COV)) {
+		const double cov = (double)(h.last_mq - h.first_mq + 1) / (double)h.ql; // arscorer.cpp:122-137
+		if ((f & USB_ACC_QUERY_COV) && cov < P.query_cov_d)
+			return false;
+		if ((f & USB_ACC_MAX_QUERY_COV) && cov > P.max_query_cov_d)
+			return false;
+	}
+	if (f & (USB_ACC_TARGET_COV | USB_ACC_MAX_TARGET_COV)) {
+		// arscorer.cpp:139-154: letter pairs over TL for a global alignment, the segment length for a local one
+		const double cov = (double)(local ? h.last_mt - h.first_mt + 1 : h.ids + h.mism) / (double)h.tl;
+		if ((f & USB_ACC_TARGET_COV) && cov < P.target_cov_d)
+			return false;
+		if ((f & USB_ACC_MAX_TARGET_COV) && cov > P.max_target_cov_d)
+			return false;
+	}
+	if ((f & USB_ACC_MAXDIFFS) && h.mism + h.intgaps > P.maxdiffs)
+		return false;
+	if ((f & USB_ACC_MINDIFFS) && h.mism + h.intgaps < P.mindiffs)
+		return false;
+	if ((f & USB_ACC_ABSKEW) && (double)a.t_size[h.target] / (double)a.q_size[qi] < P.abskew_d)
+		return false;
+	return true;
+}
+
+
 // ------------------------------------------------------------------ the job loop
 template <bool AA> __device__ void align_job(const AlignArgs &a, WarpWs &w, uint32_t job)
 {
@@ -1485,11 +1573,22 @@ template <bool AA> __device__ void align_job(const AlignArgs &a, WarpWs &w, uint
 		build_seed_table<AA>(a, w);
 		w.seed_dirty = false;
 		uint32_t acc = 0, rej = 0;
+		bool stopped = pairs;
 		for (uint32_t k = 0; k < ncand; ++k) {
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
 			if (w.seed_dirty) {
 				build_seed_table<AA>(a, w);
 				w.seed_dirty = false;
+			}
+			// Accepter::RejectPair before any alignment (searcher.cpp:63-67): skipped without a Terminator
+			// call on the small-database path, a reject on the big one (udbusortedsearcherbig.cpp:119-128)
+			if (!pairs && (a.P.accept_flags & ACC_PAIR_FLAGS) &&
+			    reject_pair(a, qi, strand, t, a.q + q0, L)) {
+				if (a.P.reject_pair_counts && a.P.maxrejects > 0 && ++rej == a.P.maxrejects) {
+					stopped = true;
+					break;
+				}
+				continue;
 			}
 			load_target<AA>(a, w, t);
 			++st.n_tried;
@@ -1521,8 +1620,7 @@ template <bool AA> __device__ void align_job(const AlignArgs &a, WarpWs &w, uint
 						atomicOr(&a.ctr->err, ERR_NO_M);
 				} else {
 					// accepter.cpp:27-38: reject iff double(ids)/double(cols) < (double)(float)id
-					const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
-					accept = pairs || !(fid < a.P.id_d);
+					accept = pairs || accept_hit(a, h, qi);
 					if (accept) {
 						if (emit_runs(a, w, n, h)) {
 							uint32_t slot = 0;
@@ -1549,11 +1647,14 @@ template <bool AA> __device__ void align_job(const AlignArgs &a, WarpWs &w, uint
 				++acc;
 			else
 				++rej;
-			if (a.P.maxaccepts > 0 && acc == a.P.maxaccepts)
+			if ((a.P.maxaccepts > 0 && acc == a.P.maxaccepts) || (a.P.maxrejects > 0 && rej == a.P.maxrejects)) {
+				stopped = true;
 				break;
-			if (a.P.maxrejects > 0 && rej == a.P.maxrejects)
-				break;
+			}
 		}
+		// every materialised candidate was looked at; with skipped pairs the reference may go on
+		if (!stopped && a.n_cand_all && a.n_cand_all[job] > ncand && lane == 0)
+			atomicOr(&a.ctr->err, ERR_KCAP);
 	}
 	if (lane == 0 && a.qstat) {
 		usb_qstat *o = a.qstat + job;

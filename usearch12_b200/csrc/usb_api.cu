@@ -540,9 +540,9 @@ static int make_dev_params(const usb_params *p, DevParams &D)
 	if ((p->accept_flags & USB_ACC_MAXID) && !(p->maxid < 1.0f))
 		D.accept_flags &= ~USB_ACC_MAXID; // identities never exceed 1: the default -maxid 1.0 rejects nothing
 	const uint32_t extra = D.accept_flags;
-	if (extra && (p->local || !p->is_nucleo || p->cluster_mode))
-		return fail(USB_EINVAL, "Accepter / Terminator options beyond -id (accept_flags 0x%x) are supported for nucleotide "
-		                        "usearch_global only", extra);
+	if (extra && p->cluster_mode)
+		return fail(USB_EINVAL, "Accepter / Terminator options beyond -id (accept_flags 0x%x) are not supported in cluster mode",
+		  extra);
 	if ((extra & (USB_ACC_TERMID | USB_ACC_TERMIDD)) && p->strand_both)
 		return fail(USB_EINVAL, "-termid / -termidd with -strand both: the reference carries the accepted hits of the plus "
 		                        "strand into the minus-strand search; not supported");
@@ -1723,7 +1723,8 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 	// RejectPair-ed candidates are skipped without a Terminator call on the small-database path
 	// (searcher.cpp:63-67), so the loop can reach any candidate of the list: materialise as many as
 	// the build allows; a query that runs out of them unterminated is reported (ERR_KCAP)
-	const bool pair_skips = (s->D.accept_flags & ACC_PAIR_FLAGS) != 0 && !(s->big || N > s->P.big);
+	// (a local search never skips: its rejected pairs are rejects, searcher.cpp:26-49)
+	const bool pair_skips = (s->D.accept_flags & ACC_PAIR_FLAGS) != 0 && !(s->big || N > s->P.big) && !s->P.local;
 	if (pair_skips)
 		k_max = std::min<uint32_t>(N, RANK_KCAP);
 	if (k_max == 0)
@@ -1778,6 +1779,28 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			a.runs = s->d_runs.p;
 			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
 			a.qstat = s->d_qstat.p;
+			if (s->D.accept_flags) {
+				if (s->D.accept_flags & (USB_ACC_TERMID | USB_ACC_TERMIDD))
+					return fail(USB_EINVAL, "-termid / -termidd are not supported with -usearch_local");
+				// In a local search the reference applies RejectPair only inside IsAccept (searcher.cpp:26-49) and
+				// dies with SIGSEGV -- or goes on with corrupted results -- when one of these rules rejects a
+				// pair: there is nothing to be identical to
+				if (s->D.accept_flags & ACC_PAIR_FLAGS)
+					return fail(USB_EINVAL, "-self, -notself, -selfid, -min_sizeratio, -minqt/-maxqt and -minsl/-maxsl are not "
+					                        "supported with -usearch_local (the reference crashes on them)");
+				if ((s->D.accept_flags & USB_ACC_NEEDS_LABELS) && (ix->n_label < N || s->n_q_label < s->n_q))
+					return fail(USB_EINVAL, "-self / -notself need label identities: call usb_index_set_attrs for every target "
+					                        "and usb_batch_set_query_attrs for this batch");
+				if ((s->D.accept_flags & USB_ACC_NEEDS_SIZES) && (ix->n_size < N || s->n_q_size < s->n_q))
+					return fail(USB_EINVAL, "-abskew / -min_sizeratio need size= annotations: call usb_index_set_attrs for every "
+					                        "target and usb_batch_set_query_attrs for this batch");
+				a.q_label = s->d_q_label.p;
+				a.q_size = s->d_q_size.p;
+				a.t_label = ix->d_t_label.p;
+				a.t_size = ix->d_t_size.p;
+				a.P.reject_pair_counts = s->big ? 1u : 0u;
+				a.n_cand_all = pair_skips ? s->d_ncand.p : nullptr;
+			}
 			if ((rc = launch_local(s, a, lg)))
 				return rc;
 		} else if (s->n_jobs) {
@@ -1804,9 +1827,9 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			a.runs_cap = (uint32_t)std::min<uint64_t>(s->d_runs.cap, 0xfffffff0ull);
 			a.qstat = s->d_qstat.p;
 			if (s->D.accept_flags) {
-				if (!staged)
-					return fail(USB_EINVAL, "Accepter / Terminator options beyond -id need the staged candidate loop "
-					                        "(nucleotide scores with match > 0 > mismatch, sequences that fit in shared memory)");
+				if (!staged && (s->D.accept_flags & (USB_ACC_TERMID | USB_ACC_TERMIDD)))
+					return fail(USB_EINVAL, "-termid / -termidd need the staged candidate loop (nucleotide scores with "
+					                        "match > 0 > mismatch, sequences that fit in shared memory)");
 				if ((s->D.accept_flags & USB_ACC_NEEDS_LABELS) && (ix->n_label < N || s->n_q_label < s->n_q))
 					return fail(USB_EINVAL, "-self / -notself need label identities: call usb_index_set_attrs for every target "
 					                        "and usb_batch_set_query_attrs for this batch");

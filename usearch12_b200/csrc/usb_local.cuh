@@ -25,6 +25,7 @@
 // sentinel of the reference, which absorbs every addition, is the exact integer USB_NEG here
 // (every dead value is clamped back to it), so even dead cells carry the reference's trace bits.
 #pragma once
+#include "usb_align.cuh" // Accepter rules shared by all candidate loops
 #include "usb_dev.cuh"
 #include "usb_tables.h"
 
@@ -58,6 +59,8 @@ struct LocalArgs {
 	const uint8_t *db_seq;
 	const uint64_t *db_off;
 	const uint32_t *db_len;
+	const uint32_t *q_label, *q_size, *t_label, *t_size; // Accepter rules on labels / size= annotations (or null)
+	const uint32_t *n_cand_all; // TopOrder.Size per job when skipped pairs can exhaust the materialised candidates
 	const float *min_ungapped; // per query: (float) EStats::GetMinUngappedRawScore(QL)
 	const int *min_gapped;     // per query: smallest raw score with RawScoreToEvalue(score) <= -evalue
 	const LocalDevTables *tab;
@@ -955,8 +958,8 @@ __device__ void local_process_seeds(const LocalArgs &a, const LocalShared &S, Lo
 		h.raw = H.score;
 		h.sub = sub;
 		local_path_stats(S, w, np, H, h);
-		const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
-		const bool accept = pairs || !(fid < a.P.id_d);
+		// Accepter::IsAcceptLo (accepter.cpp:41-94); -evalue was applied above
+		const bool accept = pairs || accept_hit(a, h, qi, true);
 		if (accept) {
 			if (local_emit_runs(a, w, np, h)) {
 				uint32_t slot = 0;
@@ -1068,8 +1071,11 @@ __device__ void local_job(const LocalArgs &a, const LocalShared &S, LocalWs &w, 
 		const uint32_t L = (uint32_t)(a.q_off[qi + 1] - q0);
 		local_load_query(a, S, w, a.q + q0, L, strand);
 		uint32_t acc = 0, rej = 0;
+		bool stopped = pairs;
 		for (uint32_t k = 0; k < ncand; ++k) {
 			const uint32_t t = pairs ? a.pair_t[job] : a.cand_t[(uint64_t)job * a.k_max + k];
+			// (Accepter::RejectPair rules are refused on the host for local searches: the reference applies them
+			// per AR inside IsAccept, searcher.cpp:26-49, and crashes when one rejects a pair)
 			local_load_target(a, w, t);
 			++st.n_tried;
 			st.seq_bytes += w.LA + w.LB;
@@ -1083,11 +1089,13 @@ __device__ void local_job(const LocalArgs &a, const LocalShared &S, LocalWs &w, 
 				++acc;
 			else
 				++rej;
-			if (a.P.maxaccepts > 0 && acc == a.P.maxaccepts)
+			if ((a.P.maxaccepts > 0 && acc == a.P.maxaccepts) || (a.P.maxrejects > 0 && rej == a.P.maxrejects)) {
+				stopped = true;
 				break;
-			if (a.P.maxrejects > 0 && rej == a.P.maxrejects)
-				break;
+			}
 		}
+		if (!stopped && a.n_cand_all && a.n_cand_all[job] > ncand && lane == 0)
+			atomicOr(&a.ctr->err, ERR_KCAP);
 	}
 	if (lane == 0 && a.qstat)
 		a.qstat[job] = st;

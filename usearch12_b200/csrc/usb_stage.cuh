@@ -29,7 +29,6 @@ namespace usb {
 
 #define ERR_REC_FULL 256u
 #define ERR_HSPARENA_FULL 512u
-#define ERR_KCAP 1024u
 
 #define STAGE_MAX 20          // stages per batch: [0,1), then ranges of STAGE_WIDTH candidates
 #define STAGE_WIDTH 64
@@ -142,89 +141,6 @@ __global__ void k_stage_prep(const StageArgs S)
 		if (act)
 			S.items[base + __popc(m & ((1u << lane) - 1))] = job;
 	}
-}
-
-// ------------------------------------------------------------------ Accepter rules
-#define ACC_PAIR_FLAGS (USB_ACC_SELF | USB_ACC_NOTSELF | USB_ACC_SELFID | USB_ACC_MIN_SIZERATIO | USB_ACC_MINQT | \
-                        USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)
-
-// Accepter::RejectPair (accepter.cpp:145-197): rules on the pair itself, before any alignment.
-// Q = raw query letters, L its length; the target's raw (masked) letters come from the database.
-__device__ bool reject_pair(const AlignArgs &a, uint32_t qi, uint32_t strand, uint32_t t, const uint8_t *Q, uint32_t L)
-{
-	const DevParams &P = a.P;
-	const uint32_t f = P.accept_flags;
-	if ((f & USB_ACC_SELF) && a.q_label[qi] == a.t_label[t])
-		return true;
-	if ((f & USB_ACC_NOTSELF) && a.q_label[qi] != a.t_label[t])
-		return true;
-	const uint32_t TL = a.db_len[t];
-	if ((f & USB_ACC_SELFID) && TL == L) { // same length and the same letters, byte for byte
-		const uint8_t *T = a.db_seq + a.db_off[t];
-		bool diff = false;
-		for (uint32_t i = lane_id(); i < L; i += 32) {
-			const uint32_t c = strand ? (uint32_t)c_comp[Q[L - 1 - i]] : (uint32_t)Q[i];
-			diff |= c != (uint32_t)T[i];
-		}
-		if (!__any_sync(USB_FULL, diff))
-			return true;
-	}
-	if (f & USB_ACC_MIN_SIZERATIO) {
-		const double Ratio = (double)a.t_size[t] / (double)a.q_size[qi];
-		if (Ratio < P.min_sizeratio_d)
-			return true;
-	}
-	if (f & (USB_ACC_MINQT | USB_ACC_MAXQT | USB_ACC_MINSL | USB_ACC_MAXSL)) {
-		const double q = (double)L, tt = (double)TL;
-		const double s = (double)min(L, TL), l = (double)max(L, TL);
-		const double qt = q / tt, sl = s / l;
-		if ((f & USB_ACC_MINQT) && qt < P.minqt_d)
-			return true;
-		if ((f & USB_ACC_MAXQT) && qt > P.maxqt_d)
-			return true;
-		if ((f & USB_ACC_MINSL) && sl < P.minsl_d)
-			return true;
-		if ((f & USB_ACC_MAXSL) && sl > P.maxsl_d)
-			return true;
-	}
-	return false;
-}
-
-// Accepter::IsAcceptLo (accepter.cpp:41-94) on the statistics of an alignment.
-__device__ __forceinline__ bool accept_hit(const AlignArgs &a, const usb_hit &h, uint32_t qi)
-{
-	const DevParams &P = a.P;
-	const uint32_t f = P.accept_flags;
-	const double fid = h.alnlen == 0 ? 0.0 : (double)h.ids / (double)h.alnlen;
-	if (fid < P.id_d)
-		return false;
-	if ((f & USB_ACC_MAXID) && fid > P.maxid_d)
-		return false;
-	if ((f & USB_ACC_MINCOLS) && h.alnlen < P.mincols)
-		return false;
-	if ((f & USB_ACC_MAXGAPS) && h.intgaps > P.maxgaps)
-		return false;
-	if (f & (USB_ACC_QUERY_COV | USB_ACC_MAX_QUERY_COV)) {
-		const double cov = (double)(h.last_mq - h.first_mq + 1) / (double)h.ql; // arscorer.cpp:122-137
-		if ((f & USB_ACC_QUERY_COV) && cov < P.query_cov_d)
-			return false;
-		if ((f & USB_ACC_MAX_QUERY_COV) && cov > P.max_query_cov_d)
-			return false;
-	}
-	if (f & (USB_ACC_TARGET_COV | USB_ACC_MAX_TARGET_COV)) {
-		const double cov = (double)(h.ids + h.mism) / (double)h.tl; // arscorer.cpp:139-154
-		if ((f & USB_ACC_TARGET_COV) && cov < P.target_cov_d)
-			return false;
-		if ((f & USB_ACC_MAX_TARGET_COV) && cov > P.max_target_cov_d)
-			return false;
-	}
-	if ((f & USB_ACC_MAXDIFFS) && h.mism + h.intgaps > P.maxdiffs)
-		return false;
-	if ((f & USB_ACC_MINDIFFS) && h.mism + h.intgaps < P.mindiffs)
-		return false;
-	if ((f & USB_ACC_ABSKEW) && (double)a.t_size[h.target] / (double)a.q_size[qi] < P.abskew_d)
-		return false;
-	return true;
 }
 
 // ------------------------------------------------------------------ gate kernel
