@@ -121,3 +121,38 @@ def test_udb_read_rejects_hostile_sizes(tmp_path):
     open(p3, "wb").write(raw[: len(raw) // 2])
     rc = capi.lib().usb_udb_read(p3.encode(), C.byref(h))
     assert rc != 0
+
+
+def test_parallel_fasta_parse_equals_serial(tmp_path):
+    """SeqDB::FromFasta cuts large files at '>' lines and parses the pieces in threads: the .udb written
+    from the result and the warnings must not depend on the number of pieces."""
+    import random
+    import subprocess
+    from usearch12_b200 import build
+    rng = random.Random(12)
+    lines = []
+    for i in range(3000):
+        L = rng.choice([0, 1, 7, 8, 60, 61, 200, 900]) if i % 50 == 7 else rng.randrange(30, 400)
+        s = "".join(rng.choice("ACGT") for _ in range(L))
+        if i % 11 == 0:
+            s = s.lower()
+        if i % 13 == 0 and L > 10:
+            s = s[:5] + "N-.*1" + s[5:]
+        lines.append(">seq%d some text; with >inside\r" % i if i % 17 == 0 else ">seq%d" % i)
+        w = rng.choice([60, 80, 10 ** 6])
+        for k in range(0, len(s), w):
+            lines.append(s[k:k + w] + ("\r" if i % 17 == 0 else ""))
+        if i % 29 == 0:
+            lines.append("")
+    fa = tmp_path / "in.fa"
+    fa.write_text("\n".join(lines) + ("\n" if rng.random() < 0.5 else ""))
+    cli = build.build_cli()
+    outs = []
+    for t in ("1", "2", "7", "33"):
+        udb = tmp_path / ("o%s.udb" % t)
+        r = subprocess.run([cli, "-makeudb_usearch", str(fa), "-output", str(udb)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, env=dict(os.environ, USB_FASTA_THREADS=t))
+        assert r.returncode == 0, r.stdout
+        outs.append((udb.read_bytes(), [l for l in r.stdout.splitlines() if "WARNING" in l.upper() or "Empty sequence" in l]))
+    assert all(o == outs[0] for o in outs[1:])
+    assert len(outs[0][0]) > 100000 and any("Empty sequence" in l for l in outs[0][1])

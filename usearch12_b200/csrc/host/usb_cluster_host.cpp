@@ -420,34 +420,49 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 			Die("Cannot create %s", Opts.centroids.c_str());
 		std::vector<unsigned> COrder;
 		QuickSortOrderDesc(ClusterSizes, COrder);
-		std::string out;
-		unsigned RelabelCounter = 0;
-		for (unsigned k = 0; k < ClusterCount; ++k) {
-			const unsigned r = CentroidRead[COrder[k]];
-			if (ClusterSizes[COrder[k]] < Opts.minsize)
-				break; // clustersink.cpp:245-246 (sizes descend)
-			// ClusterSink::MakeCentroidLabel (clustersink.cpp:217-241)
-			std::string Label = Input.GetLabel(r);
-			if (Opts.sizein || Opts.sizeout)
-				StripAnnot(Label, "size=");
-			if (!Opts.relabel.empty())
-				Label = Opts.relabel + std::to_string(++RelabelCounter);
-			if (Opts.sizeout)
-				AppendSize(Label, ClusterSizes[COrder[k]]);
-			out += '>';
-			out += Label;
-			out += '\n';
-			const uint8_t *s = Input.GetSeq(r);
-			const unsigned L = Input.GetSeqLength(r);
-			for (unsigned i = 0; i < L; i += 80) {
-				out.append((const char *)s + i, std::min(80u, L - i));
-				out += '\n';
+		// clustersink.cpp:245-246: sizes descend, the output stops at the first cluster below -minsize
+		unsigned NOut = ClusterCount;
+		for (unsigned k = 0; k < ClusterCount; ++k)
+			if (ClusterSizes[COrder[k]] < Opts.minsize) {
+				NOut = k;
+				break;
 			}
-			if (out.size() > (1u << 20)) {
-				fwrite(out.data(), 1, out.size(), f);
-				out.clear();
-			}
+		// formatted by several threads (one string per slice), written in order
+		const unsigned T = std::max(1u, std::min(16u, std::min(std::thread::hardware_concurrency(), NOut / 4096 + 1)));
+		std::vector<std::string> parts(T);
+		{
+			std::vector<std::thread> th;
+			for (unsigned j = 0; j < T; ++j)
+				th.emplace_back([&, j]() {
+					const unsigned k0 = (unsigned)((uint64_t)NOut * j / T), k1 = (unsigned)((uint64_t)NOut * (j + 1) / T);
+					std::string &out = parts[j];
+					for (unsigned k = k0; k < k1; ++k) {
+						const unsigned r = CentroidRead[COrder[k]];
+						// ClusterSink::MakeCentroidLabel (clustersink.cpp:217-241); the relabel counter follows the output order
+						std::string Label = Input.GetLabel(r);
+						if (Opts.sizein || Opts.sizeout)
+							StripAnnot(Label, "size=");
+						if (!Opts.relabel.empty())
+							Label = Opts.relabel + std::to_string(k + 1);
+						if (Opts.sizeout)
+							AppendSize(Label, ClusterSizes[COrder[k]]);
+						out += '>';
+						out += Label;
+						out += '\n';
+						const uint8_t *sq = Input.GetSeq(r);
+						const unsigned L = Input.GetSeqLength(r);
+						for (unsigned i = 0; i < L; i += 80) {
+							out.append((const char *)sq + i, std::min(80u, L - i));
+							out += '\n';
+						}
+					}
+				});
+			for (auto &t : th)
+				t.join();
 		}
+		for (const std::string &out : parts)
+			fwrite(out.data(), 1, out.size(), f);
+		std::string out;
 		fwrite(out.data(), 1, out.size(), f);
 		fclose(f);
 	}

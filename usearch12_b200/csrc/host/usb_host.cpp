@@ -46,6 +46,80 @@ static void CheckUsb(int rc, const char *what)
 // fastaseqsource.cpp:25-124: label = everything after '>', letters = isalpha characters, white
 // space skipped, gap characters stripped, other bytes reported and skipped, empty sequences
 // dropped with a warning.
+namespace {
+// One piece of a FASTA file (it starts at a '>' line, or at the top of the file) parsed on its own.
+struct FastaPiece {
+	std::vector<uint8_t> letters;
+	std::vector<uint64_t> offsets{0};
+	std::vector<std::string> labels;
+	std::vector<std::pair<unsigned, std::string>> empty; // (line inside the piece, label) of empty sequences
+	unsigned lines = 0, bad_bytes = 0;
+	bool no_label = false;   // letters before the first '>' (only an error at the top of the file)
+	unsigned no_label_line = 0;
+};
+
+void ParseFastaPiece(const char *p, const char *end, FastaPiece &P)
+{
+	P.letters.reserve((size_t)(end - p));
+	bool have_label = false;
+	std::string label;
+	uint64_t start = 0;
+	auto close_record = [&]() {
+		if (!have_label)
+			return;
+		if (P.letters.size() > start) {
+			P.labels.push_back(label);
+			P.offsets.push_back(P.letters.size());
+		} else
+			P.empty.emplace_back(P.lines, label);
+		start = P.letters.size();
+	};
+	while (p < end) {
+		const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+		if (!eol)
+			eol = end;
+		const char *q = eol;
+		while (q > p && (q[-1] == '\r' || q[-1] == '\n'))
+			--q;
+		++P.lines;
+		if (q > p && *p == '>') {
+			close_record();
+			label.assign(p + 1, q);
+			have_label = true;
+		} else if (q > p) {
+			if (!have_label) {
+				if (!P.no_label) {
+					P.no_label = true;
+					P.no_label_line = P.lines;
+				}
+			} else {
+				// lines of letters only (the normal case) are appended in one piece
+				const char *c = p;
+				while (c < q && (((unsigned char)*c | 0x20u) - 'a') < 26u)
+					++c;
+				if (c == q)
+					P.letters.insert(P.letters.end(), (const uint8_t *)p, (const uint8_t *)q);
+				else
+					for (c = p; c < q; ++c) {
+						unsigned char ch = (unsigned char)*c;
+						if (isalpha(ch))
+							P.letters.push_back(ch);
+						else if (isspace(ch) || ch == '-' || ch == '.')
+							continue;
+						else
+							++P.bad_bytes;
+					}
+			}
+		}
+		p = eol + 1;
+	}
+	close_record();
+}
+} // namespace
+
+// fastaseqsource.cpp:25-124 semantics (labels without '>', letters only, blank lines and white space
+// skipped, empty sequences dropped with a warning).  Large files are cut at '>' lines and the pieces
+// parsed by several threads; the result does not depend on the cut.
 void SeqDB::FromFasta(const std::string &FileName)
 {
 	FILE *f = fopen(FileName.c_str(), "rb");
@@ -59,58 +133,89 @@ void SeqDB::FromFasta(const std::string &FileName)
 		Die("Read error on %s", FileName.c_str());
 	fclose(f);
 	buf[sz] = '\n';
-	m_Letters.clear();
-	m_Letters.reserve((size_t)sz);
-	m_Offsets.assign(1, 0);
-	m_Labels.clear();
-	const char *p = buf.data(), *end = buf.data() + sz;
-	unsigned line_nr = 0, bad_bytes = 0;
-	bool have_label = false;
-	std::string label;
-	uint64_t start = 0;
-	auto close_record = [&]() {
-		if (!have_label)
-			return;
-		if (m_Letters.size() > start) {
-			m_Labels.push_back(label);
-			m_Offsets.push_back(m_Letters.size());
-		} else
-			Warning("Empty sequence at line %u in FASTA file %s, label >%s", line_nr, FileName.c_str(), label.c_str());
-		start = m_Letters.size();
-	};
-	while (p < end) {
-		const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p + 1));
-		const char *q = eol;
-		while (q > p && (q[-1] == '\r' || q[-1] == '\n'))
-			--q;
-		++line_nr;
-		if (q > p && *p == '>') {
-			close_record();
-			label.assign(p + 1, q);
-			have_label = true;
-		} else if (q > p) {
-			if (!have_label)
-				Die("Bad FASTA file %s, expected '>' in line %u", FileName.c_str(), line_nr);
-			// lines of letters only (the normal case) are appended in one piece
-			const char *c = p;
-			while (c < q && (((unsigned char)*c | 0x20u) - 'a') < 26u)
-				++c;
-			if (c == q)
-				m_Letters.insert(m_Letters.end(), (const uint8_t *)p, (const uint8_t *)q);
-			else
-				for (c = p; c < q; ++c) {
-					unsigned char ch = (unsigned char)*c;
-					if (isalpha(ch))
-						m_Letters.push_back(ch);
-					else if (isspace(ch) || ch == '-' || ch == '.')
-						continue;
-					else
-						++bad_bytes;
-				}
+	const char *base = buf.data(), *end = buf.data() + sz;
+	unsigned T = 1;
+	if (sz > (8 << 20))
+		T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	if (const char *e = getenv("USB_FASTA_THREADS")) // test knob: any file, any number of pieces
+		T = (unsigned)std::max(1, std::min(64, atoi(e)));
+	// piece k starts at the first '>' at the beginning of a line at or after k * sz / T
+	std::vector<const char *> cut(T + 1, end);
+	cut[0] = base;
+	for (unsigned k = 1; k < T; ++k) {
+		const char *p = base + (size_t)sz * k / T;
+		if (p < cut[k - 1])
+			p = cut[k - 1];
+		const char *hit = end;
+		while (p < end) {
+			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+			if (!nl || nl + 1 >= end)
+				break;
+			if (nl[1] == '>') {
+				hit = nl + 1;
+				break;
+			}
+			p = nl + 1;
 		}
-		p = eol + 1;
+		cut[k] = hit;
 	}
-	close_record();
+	std::vector<FastaPiece> pieces(T);
+	if (T == 1)
+		ParseFastaPiece(base, end, pieces[0]);
+	else {
+		std::vector<std::thread> th;
+		for (unsigned k = 0; k < T; ++k)
+			th.emplace_back([&, k]() {
+				if (cut[k] < cut[k + 1])
+					ParseFastaPiece(cut[k], cut[k + 1], pieces[k]);
+			});
+		for (auto &t : th)
+			t.join();
+	}
+	// messages in file order, with line numbers of the whole file
+	unsigned line0 = 0, bad_bytes = 0;
+	uint64_t total = 0;
+	size_t n_seqs = 0;
+	for (unsigned k = 0; k < T; ++k) {
+		const FastaPiece &P = pieces[k];
+		if (P.no_label) // only piece 0 can begin without a label: the others start at a '>' line
+			Die("Bad FASTA file %s, expected '>' in line %u", FileName.c_str(), line0 + P.no_label_line);
+		for (const auto &e : P.empty)
+			Warning("Empty sequence at line %u in FASTA file %s, label >%s", line0 + e.first, FileName.c_str(), e.second.c_str());
+		line0 += P.lines;
+		bad_bytes += P.bad_bytes;
+		total += P.letters.size();
+		n_seqs += P.labels.size();
+	}
+	if (T == 1) {
+		m_Letters.swap(pieces[0].letters);
+		m_Offsets.swap(pieces[0].offsets);
+		m_Labels.swap(pieces[0].labels);
+	} else {
+		m_Letters.resize(total);
+		m_Offsets.assign(n_seqs + 1, 0);
+		m_Labels.clear();
+		m_Labels.resize(n_seqs);
+		std::vector<uint64_t> l0(T + 1, 0);
+		std::vector<size_t> s0(T + 1, 0);
+		for (unsigned k = 0; k < T; ++k) {
+			l0[k + 1] = l0[k] + pieces[k].letters.size();
+			s0[k + 1] = s0[k] + pieces[k].labels.size();
+		}
+		std::vector<std::thread> th;
+		for (unsigned k = 0; k < T; ++k)
+			th.emplace_back([&, k]() {
+				FastaPiece &P = pieces[k];
+				if (!P.letters.empty())
+					memcpy(m_Letters.data() + l0[k], P.letters.data(), P.letters.size());
+				for (size_t i = 0; i < P.labels.size(); ++i) {
+					m_Offsets[s0[k] + i + 1] = l0[k] + P.offsets[i + 1];
+					m_Labels[s0[k] + i].swap(P.labels[i]);
+				}
+			});
+		for (auto &t : th)
+			t.join();
+	}
 	if (bad_bytes)
 		Warning("%u invalid bytes in FASTA file %s ignored", bad_bytes, FileName.c_str());
 }
