@@ -279,6 +279,8 @@ int usb_cluster_round(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_o
 /* Karlin-Altschul statistics of a local hit (estats.cpp:73-96, gapped): E-value and bit score of
  * raw score `raw` for a query of ql letters, with the searcher's -ka_dbsize. */
 int usb_local_evalue(const usb_searcher *s, int32_t raw, uint32_t ql, double *evalue, double *bits);
+/* The same from a parameter block alone (usb_set_local); host only, needs no device. */
+int usb_params_evalue(const usb_params *p, int32_t raw, uint32_t ql, double *evalue, double *bits);
 
 /* a18/a19: LocalAligner2::AlignMulti for explicit (query, target) pairs (localmulti.cpp:9-118).
  * Every AR of pair i becomes a hit with rank = i and sub = its index among the pair's ARs

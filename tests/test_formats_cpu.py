@@ -1,0 +1,92 @@
+"""Output formats of the host mirror (OutputSink / DBHitSink in usearch12_b200/csrc/host) against files
+written by the unmodified reference binary, WITHOUT a GPU: tools/format_replay.cpp feeds the reference's
+own hit table (tests/golden/fmt_*.hits.gz = its -userout with the fields of a usb_hit) to the sinks, and
+every file they write must be the reference's byte for byte: -alnout (alnout.cpp:45-171 and the per-query
+report outputsink.cpp:237-356), -fastapairs / -qsegout / -tsegout (outputsink.cpp:17-44,197-235), -matched /
+-notmatched (:383-400), -dbmatched / -dbnotmatched (dbhitsink.cpp:108-159), -uc, -blast6out, and -userout
+with 66 userfields (userout.cpp:126-352).  Fixtures: tools/make_golden_formats.py."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import util
+
+sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+import make_golden_formats as M  # noqa: E402
+
+REPLAY_OPTS = {
+    "fmt_nt": [],
+    "fmt_sz": ["-sizein", "-sizeout"],
+    "fmt_aag": ["-amino", "1"],
+    "fmt_aal": ["-amino", "1", "-local", "1", "-evalue", "10"],
+    "fmt_ntl": ["-local", "1", "-evalue", "1e-3"],
+}
+OUT_FLAGS = dict(M.FLAGS, user="-userout")
+
+
+def golden_bytes(name, kind):
+    with gzip.open(os.path.join(util.GOLDEN, "%s.%s.gz" % (name, kind)), "rb") as f:
+        return f.read()
+
+
+def check_outputs(name, paths):
+    """paths: kind -> file written by the product; compares with the reference's files."""
+    sums = json.load(open(os.path.join(util.GOLDEN, "fmt_db_sha256.json")))
+    for kind, path in paths.items():
+        got = open(path, "rb").read()
+        if kind in ("dbm", "dbnm"):
+            want = sums["%s.%s" % (name, kind)]
+            assert (len(got), got.count(b">")) == (want["bytes"], want["seqs"]), (name, kind)
+            assert hashlib.sha256(got).hexdigest() == want["sha256"], (name, kind)
+            continue
+        if kind == "aln":  # line 1 = command line, line 2 = program / host line
+            head = got.split(b"\n")[:2]
+            assert len(head) == 2 and head[0] and head[1], "alnout header lines"
+            got = b"\n".join(got.split(b"\n")[2:])
+        want = golden_bytes(name, kind)
+        if got != want:
+            d = util.first_diff(got.decode().splitlines(), want.decode().splitlines())
+            raise AssertionError("%s %s differs from the reference\n%s" % (name, kind, d))
+        assert len(want) > 0 or kind == "notmatched"
+
+
+@pytest.mark.parametrize("chunk", ["", "16"])
+@pytest.mark.parametrize("name", list(M.VARIANTS))
+def test_sinks_write_the_reference_files(name, chunk, tmp_path):
+    from usearch12_b200 import build
+    cli, replay = build.build_cli(), build.build_format_replay()
+    tmp = str(tmp_path)
+    q, d = M.write_inputs(name, tmp)
+    # the letters the reference's database holds are masked (loaddb.cpp:117-118): -makeudb_usearch is host only
+    udb = os.path.join(tmp, "db.udb")
+    subprocess.run([cli, "-makeudb_usearch", d, "-output", udb, "-quiet"], check=True)
+    hits = os.path.join(tmp, "hits.tsv")
+    open(hits, "wb").write(golden_bytes(name, "hits"))
+    paths = {k: os.path.join(tmp, "o." + k) for k in OUT_FLAGS}
+    cmd = [replay, "-query", q, "-db", udb, "-hits", hits, "-userfields", M.VARIANTS[name][5]] + REPLAY_OPTS[name]
+    for k, flag in OUT_FLAGS.items():
+        cmd += [flag, paths[k]]
+    env = dict(os.environ)
+    if chunk:  # several formatting threads per batch, chunks written in input order
+        env["USB_FORMAT_CHUNK"] = chunk
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    check_outputs(name, paths)
+
+
+def test_global_segment_fields_are_refused(tmp_path):
+    """qseg / tseg / gc read m_HSP.Leni letters from the first M position (alignresult.h:173): for a global
+    alignment that runs past the end of the sequence in the reference, so the mirror refuses them."""
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    q, d = M.write_inputs("fmt_sz", str(tmp_path))
+    hits = os.path.join(str(tmp_path), "hits.tsv")
+    open(hits, "wb").write(b"")
+    r = subprocess.run([replay, "-query", q, "-db", d, "-hits", hits, "-userout", os.path.join(str(tmp_path), "u"),
+                        "-userfields", "query+qseg"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "only supported with -usearch_local" in r.stdout

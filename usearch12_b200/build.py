@@ -66,6 +66,27 @@ def build_cli(force=False):
     return CLI
 
 
+REPLAY = os.path.join(HERE, "format_replay")
+
+
+def build_format_replay(force=False):
+    """tools/format_replay.cpp: test tool that feeds hit tables to the host sinks (no device needed)."""
+    host = os.path.join(CSRC, "host")
+    srcs = [os.path.join(os.path.dirname(HERE), "tools", "format_replay.cpp")] + [
+        os.path.join(host, f) for f in ("usb_host.cpp", "usb_cluster_host.cpp")]
+    newest = max(os.path.getmtime(x) for x in srcs + [os.path.join(host, "usb_host.h")])
+    if not force and os.path.exists(REPLAY) and os.path.getmtime(REPLAY) >= newest:
+        return REPLAY
+    build()
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", REPLAY] + srcs + [
+        "-L" + HERE, "-lusb200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building tools/format_replay.cpp")
+    return REPLAY
+
+
 if __name__ == "__main__":
     build_cli(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose=True))

@@ -65,7 +65,7 @@ SYMBOLS = [
     "usb_searcher_launch_count", "usb_batch_export_hits_device",
     "usb_result_hit_count", "usb_result_hits", "usb_result_runs", "usb_result_query_offsets",
     "usb_result_qstats", "usb_result_free", "usb_result_path", "usb_rank_batch", "usb_align_pairs",
-    "usb_viterbi_batch", "usb_set_local", "usb_set_amino", "usb_local_evalue", "usb_local_pairs",
+    "usb_viterbi_batch", "usb_set_local", "usb_set_amino", "usb_local_evalue", "usb_params_evalue", "usb_local_pairs",
     "usb_udb_write", "usb_udb_probe", "usb_udb_read", "usb_udb_free", "usb_udb_seq_count", "usb_udb_is_nucleo",
     "usb_udb_word_length", "usb_udb_seqs", "usb_udb_label", "usb_udb_row", "usb_debug_half_row", "usb_derep_full",
 ]
@@ -160,6 +160,7 @@ def lib():
     L.usb_set_amino.argtypes = [C.POINTER(Params)]
     L.usb_set_amino.restype = None
     L.usb_local_evalue.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.usb_params_evalue.argtypes = [C.POINTER(Params), C.c_int32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.usb_local_pairs.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(vp)]
     _lib = L
     return L

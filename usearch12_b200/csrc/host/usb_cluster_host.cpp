@@ -109,7 +109,7 @@ static void DerepFullDevice(const SeqDB &Input, std::vector<unsigned> &UniqOf, s
 }
 
 // label.cpp:47-75 StripAnnot
-static void StripAnnot(std::string &Label, const std::string &NameEq)
+void StripAnnot(std::string &Label, const std::string &NameEq)
 {
 	if (Label.find(NameEq) == std::string::npos)
 		return;
@@ -147,7 +147,7 @@ static unsigned GetSizeFromLabel(const char *Label, unsigned Default)
 }
 
 // label.cpp:88-91 AppendSize -> AppendIntField (myutils.cpp:824-839 Psasc)
-static void AppendSize(std::string &Label, unsigned Size)
+void AppendSize(std::string &Label, unsigned Size)
 {
 	if (!Label.empty() && Label.back() != ';')
 		Label += ';';

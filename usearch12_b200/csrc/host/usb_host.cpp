@@ -1,11 +1,13 @@
 // usb_host.cpp -- see usb_host.h
 #include "usb_host.h"
+#include "../usb_tables.h"
 
 #include <algorithm>
 #include <cctype>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <chrono>
 #include <condition_variable>
@@ -306,14 +308,180 @@ enum UserField {
 	UF_query, UF_target, UF_clusternr, UF_id, UF_fractid, UF_dist, UF_pairs, UF_gaps, UF_allgaps, UF_qlo, UF_qhi,
 	UF_tlo, UF_thi, UF_qlot, UF_qhit, UF_qunt, UF_tlot, UF_thit, UF_tunt, UF_ql, UF_tl, UF_alnlen, UF_opens,
 	UF_exts, UF_aln, UF_caln, UF_qstrand, UF_tstrand, UF_mism, UF_ids, UF_diffs, UF_evalue, UF_bits, UF_raw, UF_qlor,
-	UF_qhir, UF_tlor, UF_thir, UF_COUNT
+	UF_qhir, UF_tlor, UF_thir,
+	// the fields that read the letters (rows, segments, substitution scores) and the derived ratios
+	UF_mid, UF_pctpv, UF_pctgaps, UF_pv, UF_qs, UF_ts, UF_qseq, UF_tseq, UF_qseg, UF_tseg, UF_qsegf, UF_qrow, UF_trow,
+	UF_qrowdots, UF_trowdots, UF_qframe, UF_tframe, UF_qcov, UF_tcov, UF_diffsa, UF_editdiffs, UF_abskew, UF_orflo,
+	UF_orfhi, UF_orfframe, UF_gc, UF_kmerid, UF_COUNT
 };
 static const char *g_UserFieldNames[UF_COUNT] = {
 	"query", "target", "clusternr", "id", "fractid", "dist", "pairs", "gaps", "allgaps", "qlo", "qhi", "tlo",
 	"thi", "qlot", "qhit", "qunt", "tlot", "thit", "tunt", "ql", "tl", "alnlen", "opens", "exts", "aln", "caln",
-	"qstrand", "tstrand", "mism", "ids", "diffs", "evalue", "bits", "raw", "qlor", "qhir", "tlor", "thir"};
+	"qstrand", "tstrand", "mism", "ids", "diffs", "evalue", "bits", "raw", "qlor", "qhir", "tlor", "thir",
+	"mid", "pctpv", "pctgaps", "pv", "qs", "ts", "qseq", "tseq", "qseg", "tseg", "qsegf", "qrow", "trow",
+	"qrowdots", "trowdots", "qframe", "tframe", "qcov", "tcov", "diffsa", "editdiffs", "abskew", "orflo",
+	"orfhi", "orfframe", "gc", "kmerid"};
 
-OutputSink::OutputSink(const OutputOpts &O)
+// g_MatchMxNucleo / g_MatchMxAmino (alpha2.cpp:220-279) and g_SubstMx by raw character, from the
+// same table builder the kernels use (usb_tables.h)
+struct FormatTables {
+	usb::LocalTables L;
+	bool Match(uint8_t a, uint8_t b) const { return (L.match[L.code[a]] >> L.code[b]) & 1; }
+	int Score(uint8_t a, uint8_t b) const { return L.score[L.code[a]][L.code[b]]; }
+};
+
+const uint8_t *AlignResult::GetQSeq(std::string &Buf) const
+{
+	if (!m_Hit.strand)
+		return m_Query.m_Seq;
+	static const usb::CharTables *T = []() {
+		usb::CharTables *t = new usb::CharTables;
+		usb::build_char_tables(*t);
+		return t;
+	}();
+	Buf.resize(m_Query.m_L);
+	for (uint32_t i = 0; i < m_Query.m_L; ++i)
+		Buf[i] = (char)T->comp[m_Query.m_Seq[m_Query.m_L - 1 - i]];
+	return (const uint8_t *)Buf.data();
+}
+
+namespace {
+// The columns between the first and the last M of an alignment with the letters under them: what
+// AlignResult::GetQueryRow / GetTargetRow / GetAnnotRow / Get*RowDots / GetPositiveCount / FillLo's
+// m_DiffCountA / GetKmerId walk (arscorer.cpp:201-296,305-564,882-930).
+struct RowWalk {
+	std::string path, qbuf;
+	const uint8_t *Q = nullptr, *T = nullptr; // first letters under the first M column
+	size_t c0 = 0, c1 = 0;                    // [c0, c1) = columns m_FirstMCol .. m_LastMCol
+	explicit RowWalk(const AlignResult &AR)
+	{
+		AR.GetPath(path);
+		c0 = AR.m_Hit.first_mcol;
+		c1 = c0 + AR.m_Hit.alnlen;
+		Q = AR.GetQSeq(qbuf) + AR.m_Hit.first_mq;
+		T = AR.m_Target.m_Seq + AR.m_Hit.first_mt;
+	}
+	// fn(op, q, t): q / t = raw letter, or 0 where the row has a gap
+	template <class F> void Each(F fn) const
+	{
+		const uint8_t *q = Q, *t = T;
+		for (size_t c = c0; c < c1; ++c) {
+			const char op = path[c];
+			const uint8_t qc = (op == 'M' || op == 'D') ? *q++ : 0;
+			const uint8_t tc = (op == 'M' || op == 'I') ? *t++ : 0;
+			fn(op, qc, tc);
+		}
+	}
+};
+
+char AnnotSym(const FormatTables &FT, bool Nucleo, uint8_t a, uint8_t b) // arscorer.cpp:12-46
+{
+	if (Nucleo) {
+		if (toupper(a) == toupper(b) && strchr("ACGTUacgtu", a) && strchr("ACGTUacgtu", b))
+			return '|';
+		return FT.Match(a, b) ? '+' : ' ';
+	}
+	if (FT.Match(a, b))
+		return '|';
+	const int s = FT.Score(a, b);
+	return s >= 2 ? ':' : s > 0 ? '.' : ' ';
+}
+
+void QueryRow(const RowWalk &W, std::string &Row)
+{
+	Row.clear();
+	W.Each([&](char, uint8_t q, uint8_t) { Row += q ? (char)toupper(q) : '-'; });
+}
+
+void TargetRow(const RowWalk &W, std::string &Row)
+{
+	Row.clear();
+	W.Each([&](char, uint8_t, uint8_t t) { Row += t ? (char)toupper(t) : '-'; });
+}
+
+void AnnotRow(const RowWalk &W, const FormatTables &FT, bool Nucleo, std::string &Row)
+{
+	Row.clear();
+	W.Each([&](char op, uint8_t q, uint8_t t) { Row += op == 'M' ? AnnotSym(FT, Nucleo, q, t) : ' '; });
+}
+
+// rows with '.' where the upper-cased letters match (a letter never matches the gap symbol)
+void RowDots(const RowWalk &W, const FormatTables &FT, bool QueryRowWanted, std::string &Row)
+{
+	Row.clear();
+	W.Each([&](char, uint8_t q, uint8_t t) {
+		const uint8_t uq = q ? (uint8_t)toupper(q) : (uint8_t)'-', ut = t ? (uint8_t)toupper(t) : (uint8_t)'-';
+		const uint8_t mine = QueryRowWanted ? uq : ut;
+		const bool have = QueryRowWanted ? q != 0 : t != 0;
+		Row += !have ? '-' : FT.Match(uq, ut) ? '.' : (char)mine;
+	});
+}
+
+unsigned PositiveCount(const RowWalk &W, const FormatTables &FT)
+{
+	unsigned n = 0;
+	W.Each([&](char op, uint8_t q, uint8_t t) { n += op == 'M' && FT.Score(q, t) > 0; });
+	return n;
+}
+
+unsigned DiffCountA(const RowWalk &W)
+{
+	unsigned n = 0;
+	W.Each([&](char op, uint8_t q, uint8_t t) { n += op == 'M' && toupper(q) != toupper(t); });
+	return n;
+}
+
+double KmerId(const AlignResult &AR, const RowWalk &W, unsigned w)
+{
+	const unsigned MinL = std::min(AR.m_Hit.ql, AR.m_Hit.tl);
+	if (MinL < w)
+		return 0.0;
+	unsigned run = 0, matches = 0;
+	W.Each([&](char op, uint8_t q, uint8_t t) {
+		run = (op == 'M' && toupper(q) == toupper(t)) ? run + 1 : 0;
+		matches += op == 'M' && run >= w;
+	});
+	return double(matches) / double(MinL - w + 1);
+}
+
+// SeqToFasta (seqdb.cpp:62-95) with the default -fasta_cols 80
+void AppendFasta80(std::string &out, const char *Label, const uint8_t *Seq, size_t L)
+{
+	if (L == 0)
+		return;
+	out += '>';
+	out += Label;
+	out += '\n';
+	for (size_t i = 0; i < L; i += 80) {
+		out.append((const char *)Seq + i, std::min<size_t>(80, L - i));
+		out += '\n';
+	}
+}
+
+// RowToFasta (outputsink.cpp:30-58): the letters of a row; an empty row still gets its newline
+void AppendRowFasta(std::string &out, const char *Label, const std::string &Row)
+{
+	out += '>';
+	out += Label;
+	unsigned n = 0;
+	for (char c : Row) {
+		if (c == '-' || c == '.')
+			continue;
+		if (n % 80 == 0)
+			out += '\n';
+		out += c;
+		++n;
+	}
+	out += '\n';
+}
+
+unsigned NDig(unsigned n) // alnout.cpp:9-24
+{
+	return n < 10 ? 1 : n < 100 ? 2 : n < 1000 ? 3 : n < 10000 ? 4 : n < 100000 ? 5 : n < 1000000 ? 6 : 10;
+}
+} // namespace
+
+OutputSink::OutputSink(const OutputOpts &O) : m_O(O)
 {
 	auto open = [](const std::string &fn) -> FILE * {
 		if (fn.empty())
@@ -323,11 +491,23 @@ OutputSink::OutputSink(const OutputOpts &O)
 			Die("Cannot create %s", fn.c_str());
 		return f;
 	};
-	m_fUC = open(O.uc);
-	m_fB6 = open(O.blast6out);
-	m_fUser = open(O.userout);
+	m_f[O_UC] = open(O.uc);
+	m_f[O_B6] = open(O.blast6out);
+	m_f[O_USER] = open(O.userout);
+	m_f[O_ALN] = open(O.alnout);
+	m_f[O_PAIRS] = open(O.fastapairs);
+	m_f[O_QSEG] = open(O.qsegout);
+	m_f[O_TSEG] = open(O.tsegout);
+	m_f[O_MATCHED] = open(O.matched);
+	m_f[O_NOTMATCHED] = open(O.notmatched);
 	m_OutputNoHits = O.output_no_hits;
-	if (m_fUser) {
+	m_T = std::make_shared<FormatTables>();
+	usb::build_local_tables(O.nucleo, O.match, O.mismatch, m_T->L);
+	if (m_f[O_ALN]) {
+		// outputsink.cpp:142-147: the command line, then the program line (version, memory and cores there)
+		fprintf(m_f[O_ALN], "%s\nusearch12_b200 (B200 hot path of usearch v12.0)\n", O.cmdline.c_str());
+	}
+	if (m_f[O_USER]) {
 		// userout.cpp:20-60: fields separated by '+'; default query+target+id
 		std::string spec = O.userfields.empty() ? "query+target+id" : O.userfields;
 		size_t pos = 0;
@@ -342,6 +522,12 @@ OutputSink::OutputSink(const OutputOpts &O)
 					idx = i;
 			if (idx < 0)
 				Die("Invalid or unsupported userfield name '%s'", name.c_str());
+			// For a global alignment the reference prints m_HSP.Leni letters from the first M position
+			// (alignresult.h:173, userout.cpp:204-207, arscorer.cpp:863-880): past the end of the sequence as soon
+			// as the alignment starts with a terminal gap.  Nothing to be identical to.
+			if (!O.local && (idx == UF_qseg || idx == UF_tseg || idx == UF_gc))
+				Die("userfield %s is only supported with -usearch_local (the reference reads past the end of the "
+				    "sequence for global alignments)", name.c_str());
 			m_UserFields.push_back(idx);
 			pos = e + 1;
 		}
@@ -350,24 +536,23 @@ OutputSink::OutputSink(const OutputOpts &O)
 
 OutputSink::~OutputSink() { OnAllDone(); }
 
-void OutputSink::Flush(FILE *f, std::string &buf, bool force)
+void OutputSink::Flush(int k, std::string &buf, bool force)
 {
-	if (f && (force || buf.size() > (1u << 20))) {
-		fwrite(buf.data(), 1, buf.size(), f);
+	if (m_f[k] && (force || buf.size() > (1u << 20))) {
+		fwrite(buf.data(), 1, buf.size(), m_f[k]);
 		buf.clear();
 	}
 }
 
 void OutputSink::OnAllDone()
 {
-	Flush(m_fUC, m_bUC, true);
-	Flush(m_fB6, m_bB6, true);
-	Flush(m_fUser, m_bUser, true);
-	for (FILE **f : {&m_fUC, &m_fB6, &m_fUser})
-		if (*f) {
-			fclose(*f);
-			*f = nullptr;
+	for (int k = 0; k < O_COUNT; ++k) {
+		Flush(k, m_b[k], true);
+		if (m_f[k]) {
+			fclose(m_f[k]);
+			m_f[k] = nullptr;
 		}
+	}
 }
 
 static void appendf(std::string &s, const char *fmt, ...)
@@ -384,7 +569,7 @@ static void appendf(std::string &s, const char *fmt, ...)
 // outputuc.cpp:19-22,45-69
 void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &m_bUC) const
 {
-	if (!m_fUC)
+	if (!m_f[O_UC])
 		return;
 	std::string cp;
 	if (HM.m_Hits.empty()) {
@@ -408,7 +593,7 @@ void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &m
 // blast6out.cpp:27-80 (global alignments: evalue and bit score print as '*')
 void OutputSink::OutputBlast6(const HitMgr &HM, std::string &m_bB6) const
 {
-	if (!m_fB6)
+	if (!m_f[O_B6])
 		return;
 	if (HM.m_Hits.empty() && m_OutputNoHits) { // blast6out.cpp:82-103
 		m_bB6 += HM.m_Query.m_Label;
@@ -427,10 +612,10 @@ void OutputSink::OutputBlast6(const HitMgr &HM, std::string &m_bB6) const
 	}
 }
 
-// userout.cpp:126-215
+// userout.cpp:126-352
 void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 {
-	if (!m_fUser)
+	if (!m_f[O_USER])
 		return;
 	std::string tmp;
 	if (HM.m_Hits.empty() && m_OutputNoHits) { // userout.cpp:53-124
@@ -445,6 +630,9 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 			case UF_qlor: case UF_qhir: case UF_tlo: case UF_thi: case UF_tlor: case UF_thir: case UF_tl: case UF_alnlen:
 			case UF_opens: case UF_exts: case UF_raw: case UF_bits: case UF_aln: case UF_caln: case UF_qstrand:
 			case UF_tstrand: case UF_mism: case UF_ids: case UF_diffs:
+			case UF_mid: case UF_pctpv: case UF_pctgaps: case UF_pv: case UF_qs: case UF_ts: case UF_qrow: case UF_trow:
+			case UF_qframe: case UF_tframe: case UF_qcov: case UF_tcov: case UF_abskew: case UF_orflo: case UF_orfhi:
+			case UF_qseq: case UF_tseq: case UF_qseg: case UF_tseg:
 				m_bUser += '*';
 				break;
 			default:
@@ -454,6 +642,12 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 		m_bUser += '\n';
 	}
 	for (const AlignResult &AR : HM.m_Hits) {
+		std::unique_ptr<RowWalk> walk; // built on demand, once per hit
+		auto W = [&]() -> const RowWalk & {
+			if (!walk)
+				walk.reset(new RowWalk(AR));
+			return *walk;
+		};
 		for (size_t i = 0; i < m_UserFields.size(); ++i) {
 			if (i)
 				m_bUser += '\t';
@@ -496,54 +690,305 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 			case UF_qhir: appendf(m_bUser, "%u", AR.GetHii()); break;
 			case UF_tlor: appendf(m_bUser, "%u", AR.GetLoj()); break;
 			case UF_thir: appendf(m_bUser, "%u", AR.GetHij()); break;
+			case UF_mid: appendf(m_bUser, "%.1f", 100.0 * AR.GetFractMatchId()); break;
+			case UF_pctpv: {
+				const unsigned L = AR.GetAlnLength();
+				appendf(m_bUser, "%.1f", L == 0 ? 0.0 : 100.0 * (double(PositiveCount(W(), *m_T)) / double(L)));
+				break;
+			}
+			case UF_pctgaps: appendf(m_bUser, "%.1f", AR.GetPctGaps()); break;
+			case UF_pv: appendf(m_bUser, "%u", PositiveCount(W(), *m_T)); break;
+			case UF_qs: appendf(m_bUser, "%u", AR.GetQuerySegLength()); break;
+			case UF_ts: appendf(m_bUser, "%u", AR.GetTargetSegLength()); break;
+			case UF_qseq: m_bUser.append((const char *)AR.GetQSeq(tmp), AR.GetIQL()); break;
+			case UF_tseq: m_bUser.append((const char *)AR.m_Target.m_Seq, AR.GetITL()); break;
+			case UF_qseg: m_bUser.append((const char *)W().Q, AR.GetQuerySegLength()); break;
+			case UF_tseg: m_bUser.append((const char *)W().T, AR.GetTargetSegLength()); break;
+			case UF_qsegf: { // userout.cpp:216-235: the query segment between '-' with up to -flank letters around it
+				const unsigned f = m_O.flank, QL = AR.GetIQL(), Lo = AR.GetLoi(), Hi = AR.GetHii();
+				const unsigned fl = std::min(Lo, f), fr = std::min(QL - Hi - 1, f);
+				const char *Q = (const char *)AR.GetQSeq(tmp);
+				m_bUser.append(Q + Lo - fl, fl);
+				m_bUser += '-';
+				m_bUser.append(Q + Lo, Hi - Lo + 1);
+				m_bUser += '-';
+				m_bUser.append(Q + Hi + 1, fr);
+				break;
+			}
+			case UF_qrow: QueryRow(W(), tmp); m_bUser += tmp; break;
+			case UF_trow: TargetRow(W(), tmp); m_bUser += tmp; break;
+			case UF_qrowdots: RowDots(W(), *m_T, true, tmp); m_bUser += tmp; break;
+			case UF_trowdots: RowDots(W(), *m_T, false, tmp); m_bUser += tmp; break;
+			case UF_qframe: case UF_tframe: case UF_orfframe: m_bUser += "+0"; break; // no ORF queries on this path
+			case UF_orflo: case UF_orfhi: m_bUser += '0'; break;
+			case UF_qcov: appendf(m_bUser, "%.0f", 100.0 * AR.GetQueryCov()); break;
+			case UF_tcov: appendf(m_bUser, "%.0f", 100.0 * AR.GetTargetCov()); break;
+			case UF_diffsa: appendf(m_bUser, "%u", DiffCountA(W()) + 0u); break;
+			case UF_editdiffs: appendf(m_bUser, "%u", AR.GetEditDiffCount()); break;
+			case UF_abskew: { // arscorer.cpp:809-816
+				const unsigned QSize = OtuTabSink::GetSizeFromLabel(AR.GetQueryLabel(), 0xffffffffu);
+				const unsigned TSize = OtuTabSink::GetSizeFromLabel(AR.GetTargetLabel(), 0xffffffffu);
+				appendf(m_bUser, "%.1f", double(TSize) / double(QSize));
+				break;
+			}
+			case UF_gc: { // arscorer.cpp:863-880: C and G (either case) among the letters of the query segment
+				const unsigned L = AR.GetQuerySegLength();
+				unsigned n = 0;
+				for (unsigned k = 0; k < L; ++k)
+					n += strchr("CGcg", W().Q[k]) != nullptr;
+				appendf(m_bUser, "%.1f", L == 0 ? 0.0 : (100.0 * n) / L);
+				break;
+			}
+			case UF_kmerid: appendf(m_bUser, "%.4f", KmerId(AR, W(), m_O.wordlength)); break;
 			}
 		}
 		m_bUser += '\n';
 	}
 }
 
+// The per-query table at the top of a query's -alnout section (outputsink.cpp:237-356)
+void OutputSink::OutputReport(const SeqInfo &Query, const HitMgr &HM, std::string &out) const
+{
+	if (!m_f[O_ALN] || HM.m_Hits.empty())
+		return;
+	out += "\nQuery >";
+	out += Query.m_Label;
+	out += '\n';
+	if (!m_O.local) {
+		out += " %Id   TLen  Target\n";
+		for (const AlignResult &AR : HM.m_Hits) {
+			appendf(out, "%3.0f%%  %5u  ", AR.GetPctId(), AR.GetITL());
+			out += AR.GetTargetLabel();
+			out += '\n';
+		}
+		return;
+	}
+	out += " Score     Evalue   %Id    QueryLo-Hi(Un)   TargetLo-Hi(Un)";
+	if (m_O.nucleo)
+		out += "  +";
+	out += "  Target\n";
+	for (const AlignResult &AR : HM.m_Hits) {
+		char seg[64];
+		appendf(out, "%6.0f  %9.1g  %3.0f%%", AR.GetRawScore(), AR.GetEvalue(), AR.GetPctId());
+		snprintf(seg, sizeof seg, "%u-%u(%u)", AR.GetIQLo() + 1, AR.GetIQHi() + 1, AR.GetIQL() - AR.GetIQHi() - 1);
+		appendf(out, "  %16s", seg);
+		snprintf(seg, sizeof seg, "%u-%u(%u)", AR.GetITLo() + 1, AR.GetITHi() + 1, AR.GetITL() - AR.GetITHi() - 1);
+		appendf(out, "  %16s", seg);
+		if (m_O.nucleo)
+			appendf(out, "  %c", AR.GetQueryStrand());
+		out += "  ";
+		out += AR.GetTargetLabel();
+		out += '\n';
+	}
+}
+
+// alnout.cpp:45-171 WriteAln
+void OutputSink::OutputAln(const AlignResult &AR, std::string &out) const
+{
+	const RowWalk W(AR);
+	std::string QRow, TRow, ARow;
+	QueryRow(W, QRow);
+	TargetRow(W, TRow);
+	AnnotRow(W, *m_T, m_O.nucleo, ARow);
+	const unsigned IQL = AR.GetIQL(), ITL = AR.GetITL();
+	const unsigned w = NDig(std::max(IQL, ITL));
+	const char *ntaa = m_O.nucleo ? "nt" : "aa";
+	out += '\n';
+	appendf(out, " Query %*u%s >", (int)w, IQL, ntaa);
+	out += AR.GetQueryLabel();
+	appendf(out, "\nTarget %*u%s >", (int)w, ITL, ntaa);
+	out += AR.GetTargetLabel();
+	out += "\n\n";
+	const char QueryStrand = AR.GetQueryStrand(), TargetStrand = AR.GetTargetStrand();
+	const bool ShowStrand = QueryStrand != '.';
+	const unsigned AlnLength = (unsigned)QRow.size();
+	const unsigned RowLen = m_O.rowlen;
+	// positions of the letters at the two ends of each block; a block that is all gaps in one
+	// sequence repeats the position without the +1 (alnout.cpp:26-43,104-126, alignresult.cpp:365-379)
+	unsigned QPos = AR.m_Hit.first_mq, TPos = AR.m_Hit.first_mt;
+	bool QAllGaps = false, TAllGaps = false;
+	auto ipos_q = [&](unsigned Pos, bool AllGaps) { return (AR.m_Hit.strand ? IQL - Pos - 1 : Pos) + (AllGaps ? 0u : 1u); };
+	auto ipos_t = [&](unsigned Pos, bool AllGaps) { return Pos + (AllGaps ? 0u : 1u); };
+	auto advance = [](unsigned Pos, const char *Row, unsigned n, bool &AllGaps) {
+		bool got = false;
+		for (unsigned i = 0; i < n; ++i)
+			if (Row[i] != '-') {
+				if (got)
+					++Pos;
+				got = true;
+			}
+		AllGaps = !got;
+		return Pos;
+	};
+	for (unsigned From = 0; From < AlnLength; From += RowLen) {
+		const unsigned n = std::min(RowLen, AlnLength - From);
+		const unsigned QFrom = ipos_q(QPos, QAllGaps), TFrom = ipos_t(TPos, TAllGaps);
+		QPos = advance(QPos, QRow.data() + From, n, QAllGaps);
+		TPos = advance(TPos, TRow.data() + From, n, TAllGaps);
+		const unsigned QTo = ipos_q(QPos, QAllGaps), TTo = ipos_t(TPos, TAllGaps);
+		if (!QAllGaps)
+			++QPos;
+		if (!TAllGaps)
+			++TPos;
+		appendf(out, "Qry %*u", (int)w, QFrom);
+		if (ShowStrand)
+			appendf(out, " %c", QueryStrand);
+		out += ' ';
+		out.append(QRow, From, n);
+		appendf(out, " %u\n", QTo);
+		out.append(4 + w + (ShowStrand ? 2 : 0) + 1, ' ');
+		out.append(ARow, From, n);
+		out += '\n';
+		appendf(out, "Tgt %*u", (int)w, TFrom);
+		if (ShowStrand)
+			appendf(out, " %c", TargetStrand);
+		out += ' ';
+		out.append(TRow, From, n);
+		appendf(out, " %u\n\n", TTo);
+	}
+	const unsigned Ids = AR.GetIdCount(), Gaps = AR.GetGapCount();
+	appendf(out, "%u cols, %u ids (%.1f%%), %u gaps (%.1f%%)", AlnLength, Ids, AlnLength ? 100.0 * (double(Ids) / double(AlnLength)) : 0.0,
+	  Gaps, AlnLength ? 100.0 * (double(Gaps) / double(AlnLength)) : 0.0);
+	if (AR.IsLocal())
+		appendf(out, ", score %.1f (%.1f bits), Evalue %.2g", AR.GetRawScore(), AR.GetBitScore(), AR.GetEvalue());
+	out += '\n';
+}
+
+// OutputSink::OnQueryDone (outputsink.cpp:358-400): the report, every hit through every per-hit file,
+// then the query into -matched or -notmatched
+void OutputSink::FormatQuery(const SeqInfo &Query, const HitMgr &HM, Bufs &out) const
+{
+	OutputUC(Query, HM, out[O_UC]);
+	OutputBlast6(HM, out[O_B6]);
+	OutputUser(HM, out[O_USER]);
+	OutputReport(Query, HM, out[O_ALN]);
+	if (m_f[O_ALN] || m_f[O_PAIRS] || m_f[O_QSEG] || m_f[O_TSEG]) {
+		std::string QRow, TRow;
+		for (const AlignResult &AR : HM.m_Hits) {
+			if (m_f[O_ALN])
+				OutputAln(AR, out[O_ALN]);
+			if (!(m_f[O_PAIRS] || m_f[O_QSEG] || m_f[O_TSEG]))
+				continue;
+			const RowWalk W(AR);
+			QueryRow(W, QRow);
+			TargetRow(W, TRow);
+			if (m_f[O_PAIRS]) { // outputsink.cpp:223-235
+				std::string &o = out[O_PAIRS];
+				o += '>';
+				o += AR.GetQueryLabel();
+				o += '\n';
+				o += QRow;
+				o += "\n>";
+				o += AR.GetTargetLabel();
+				o += '\n';
+				o += TRow;
+				o += "\n\n";
+			}
+			if (m_f[O_QSEG])
+				AppendRowFasta(out[O_QSEG], AR.GetQueryLabel(), QRow);
+			if (m_f[O_TSEG])
+				AppendRowFasta(out[O_TSEG], AR.GetTargetLabel(), TRow);
+		}
+	}
+	if (m_f[O_MATCHED] && !HM.m_Hits.empty())
+		AppendFasta80(out[O_MATCHED], Query.m_Label, Query.m_Seq, Query.m_L);
+	if (m_f[O_NOTMATCHED] && HM.m_Hits.empty())
+		AppendFasta80(out[O_NOTMATCHED], Query.m_Label, Query.m_Seq, Query.m_L);
+}
+
 void OutputSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)
 {
-	OutputUC(Query, HM, m_bUC);
-	OutputBlast6(HM, m_bB6);
-	OutputUser(HM, m_bUser);
-	Flush(m_fUC, m_bUC, false);
-	Flush(m_fB6, m_bB6, false);
-	Flush(m_fUser, m_bUser, false);
+	FormatQuery(Query, HM, m_b);
+	for (int k = 0; k < O_COUNT; ++k)
+		Flush(k, m_b[k], false);
 }
 
 void OutputSink::OnBatchDone(const std::vector<HitMgr> &Batch)
 {
 	const size_t n = Batch.size();
-	const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, n / 4096}));
+	// queries per formatting thread; USB_FORMAT_CHUNK lowers it so that small tests reach the threaded path
+	const char *env = getenv("USB_FORMAT_CHUNK");
+	const size_t per = env && atoi(env) > 0 ? (size_t)atoi(env) : 4096;
+	const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, n / per}));
 	if (T <= 1) {
 		for (const HitMgr &HM : Batch)
 			OnQueryDone(HM.m_Query, HM);
 		return;
 	}
 	struct Chunk {
-		std::string uc, b6, user;
+		Bufs b;
 	};
 	std::vector<Chunk> chunks(T);
 	std::vector<std::thread> th;
 	for (unsigned k = 0; k < T; ++k)
 		th.emplace_back([&, k]() {
 			Chunk &c = chunks[k];
-			for (size_t i = n * k / T; i < n * (k + 1) / T; ++i) {
-				OutputUC(Batch[i].m_Query, Batch[i], c.uc);
-				OutputBlast6(Batch[i], c.b6);
-				OutputUser(Batch[i], c.user);
-			}
+			for (size_t i = n * k / T; i < n * (k + 1) / T; ++i)
+				FormatQuery(Batch[i].m_Query, Batch[i], c.b);
 		});
 	for (auto &t : th)
 		t.join();
-	Flush(m_fUC, m_bUC, true);
-	Flush(m_fB6, m_bB6, true);
-	Flush(m_fUser, m_bUser, true);
-	for (Chunk &c : chunks) {
-		Flush(m_fUC, c.uc, true);
-		Flush(m_fB6, c.b6, true);
-		Flush(m_fUser, c.user, true);
+	for (int k = 0; k < O_COUNT; ++k) {
+		Flush(k, m_b[k], true);
+		for (Chunk &c : chunks)
+			Flush(k, c.b[k], true);
+	}
+}
+
+// ------------------------------------------------------------------ DBHitSink
+DBHitSink::DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut)
+  : m_DB(DB), m_DbMatched(DbMatched), m_DbNotMatched(DbNotMatched), m_SizeIn(SizeIn), m_SizeOut(SizeOut),
+    m_HitCounts(DB.GetSeqCount(), 0)
+{
+}
+
+DBHitSink::~DBHitSink() { OnAllDone(); }
+
+void DBHitSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM) // dbhitsink.cpp:132-159
+{
+	if (HM.m_Hits.empty())
+		return;
+	const unsigned N = m_SizeIn ? OtuTabSink::GetSizeFromLabel(Query.m_Label, 1) : 1;
+	for (const AlignResult &AR : HM.m_Hits)
+		m_HitCounts[AR.GetTargetIndex()] += N;
+}
+
+void DBHitSink::OnAllDone() // dbhitsink.cpp:42-50,108-130
+{
+	if (m_Done)
+		return;
+	m_Done = true;
+	std::string Stored;
+	for (int Matched = 1; Matched >= 0; --Matched) {
+		const std::string &FileName = Matched ? m_DbMatched : m_DbNotMatched;
+		if (FileName.empty())
+			continue;
+		FILE *f = fopen(FileName.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", FileName.c_str());
+		std::string out;
+		for (uint32_t i = 0; i < m_DB.GetSeqCount(); ++i) {
+			if ((Matched != 0) != (m_HitCounts[i] > 0))
+				continue;
+			std::string Label = m_DB.GetLabel(i);
+			if (m_SizeOut && Matched) {
+				StripAnnot(Label, "size=");
+				AppendSize(Label, m_HitCounts[i]);
+			}
+			// the letters as the database stores them: masked by LoadDB (loaddb.cpp:117-118)
+			const uint8_t *Seq = m_DB.GetSeq(i);
+			if (m_Searcher) {
+				m_Searcher->GetStoredTarget(i, Stored);
+				Seq = (const uint8_t *)Stored.data();
+			}
+			AppendFasta80(out, Label.c_str(), Seq, m_DB.GetSeqLength(i));
+			if (out.size() > (1u << 20)) {
+				fwrite(out.data(), 1, out.size(), f);
+				out.clear();
+			}
+		}
+		fwrite(out.data(), 1, out.size(), f);
+		fclose(f);
 	}
 }
 
@@ -580,6 +1025,8 @@ static void GetStrField(const std::string &Label, const std::string &NameEq, std
 unsigned OtuTabSink::GetSizeFromLabel(const std::string &Label, unsigned Default)
 {
 	const char *p = strstr(Label.c_str(), ";size="); // label.cpp:152-161
+	if (!p && Default == 0xffffffffu)
+		Die("Missing size= in >%s", Label.c_str());
 	return p ? (unsigned)atoi(p + 6) : Default;
 }
 
@@ -920,6 +1367,14 @@ void GpuSearcher::BuildHitMgrs(const std::shared_ptr<void> &Result, const SeqDB 
 				AR.m_Query = HM.m_Query;
 				AR.m_Query.m_RevComp = hits[k].strand != 0;
 				m_DB.GetSI(hits[k].target, AR.m_Target);
+				{
+					// the target as the database stores it: masked letters, like m_Target->m_Seq of the
+					// reference after LoadDB (loaddb.cpp:117-118); the formats upper-case where the reference does
+					const uint8_t *stored = nullptr;
+					uint32_t slen = 0;
+					if (usb_index_seq(m_Index, hits[k].target, &stored, &slen) == 0 && slen == AR.m_Target.m_L)
+						AR.m_Target.m_Seq = stored;
+				}
 				AR.m_Runs = runs + hits[k].run_off;
 				AR.m_Nucleo = m_P.is_nucleo != 0;
 				AR.m_Local = m_P.local != 0;
@@ -1085,7 +1540,19 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	const double t_ready = now();
 	if (!Opts.quiet)
 		fprintf(stderr, "%u db seqs, %u query seqs, %d GPU(s)\n", DB.GetSeqCount(), Q.GetSeqCount(), gpus);
-	OutputSink Sink(Opts.Out);
+	OutputOpts OO = Opts.Out;
+	OO.nucleo = P.is_nucleo != 0;
+	OO.local = P.local != 0;
+	OO.match = (int)P.match;
+	OO.mismatch = (int)P.mismatch;
+	OutputSink Sink(OO);
+	std::vector<HitSink *> ExtraSinks = Opts.ExtraSinks;
+	std::unique_ptr<DBHitSink> dbhits;
+	if (!Opts.dbmatched.empty() || !Opts.dbnotmatched.empty()) {
+		dbhits.reset(new DBHitSink(DB, Opts.dbmatched, Opts.dbnotmatched, Opts.sizein, Opts.sizeout));
+		dbhits->SetSearcher(searchers[0]);
+		ExtraSinks.push_back(dbhits.get());
+	}
 	const uint32_t NQ = Q.GetSeqCount();
 	const uint32_t nbatch = (NQ + Opts.batch - 1) / Opts.batch;
 	uint64_t queries_with_hits = 0;
@@ -1134,7 +1601,7 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		r.reset();
 		const double t2 = now();
 		Sink.OnBatchDone(batch);
-		for (HitSink *x : Opts.ExtraSinks)
+		for (HitSink *x : ExtraSinks)
 			x->OnBatchDone(batch);
 		for (const HitMgr &HM : batch)
 			queries_with_hits += HM.GetHitCount() > 0;
@@ -1152,7 +1619,7 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	for (auto &t : submit)
 		t.join();
 	Sink.OnAllDone();
-	for (HitSink *x : Opts.ExtraSinks)
+	for (HitSink *x : ExtraSinks)
 		x->OnAllDone();
 	for (GpuSearcher *s : searchers)
 		delete s;

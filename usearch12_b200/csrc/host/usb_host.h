@@ -22,6 +22,8 @@ namespace usbhost {
 
 [[noreturn]] void Die(const char *fmt, ...);
 void Warning(const char *fmt, ...);
+void StripAnnot(std::string &Label, const std::string &NameEq); // label.cpp:47-75
+void AppendSize(std::string &Label, unsigned Size);             // label.cpp:88-91
 
 struct SeqInfo {
 	const char *m_Label = nullptr;
@@ -107,6 +109,24 @@ public:
 	unsigned GetTUnT() const { return m_Hit.tl - m_Hit.last_mt - 1; }
 	char GetQueryStrand() const { return !m_Nucleo ? '.' : m_Hit.strand ? '-' : '+'; } // arscorer.cpp:156-176
 	char GetTargetStrand() const { return m_Nucleo ? '+' : '.'; }
+	// segment lengths m_HSP.Leni / Lenj: the whole sequences for a global alignment (alignresult.cpp:137-145)
+	unsigned GetQuerySegLength() const { return m_Local ? m_Hit.last_mq - m_Hit.first_mq + 1 : m_Hit.ql; }
+	unsigned GetTargetSegLength() const { return m_Local ? m_Hit.last_mt - m_Hit.first_mt + 1 : m_Hit.tl; }
+	unsigned GetTermGapCount() const { return GetPathLength() - m_Hit.alnlen; }
+	unsigned GetEditDiffCount() const { return m_Hit.mism + m_Hit.intgaps + GetTermGapCount(); } // alignresult.h:160
+	double GetFractMatchId() const { return m_Hit.ids == 0 ? 0.0 : double(m_Hit.ids) / double(m_Hit.ids + m_Hit.mism); }
+	double GetPctGaps() const { return m_Hit.alnlen == 0 ? 0.0 : 100.0 * (double(m_Hit.intgaps) / double(m_Hit.alnlen)); }
+	double GetQueryCov() const // arscorer.cpp:122-137
+	{
+		return m_Local ? double(GetQuerySegLength()) / double(m_Hit.ql) : double(m_Hit.last_mq - m_Hit.first_mq + 1) / m_Hit.ql;
+	}
+	double GetTargetCov() const // arscorer.cpp:139-154
+	{
+		return m_Local ? double(GetTargetSegLength()) / double(m_Hit.tl) : double(m_Hit.ids + m_Hit.mism) / double(m_Hit.tl);
+	}
+	// letters of the query as aligned: reverse-complemented for a minus-strand hit (the reference aligns a
+	// second SeqInfo made by SeqInfo::GetRevComp, seqinfo.cpp:292-325); Buf is used only in that case
+	const uint8_t *GetQSeq(std::string &Buf) const;
 	void GetPath(std::string &Path) const;           // pathinfo.cpp:37-214
 	void GetCompressedPath(std::string &CPath) const; // comppath.cpp:7-48
 };
@@ -134,9 +154,21 @@ public:
 	virtual void OnAllDone() {}
 };
 
+class GpuSearcher;
+
 struct OutputOpts {
 	std::string uc, blast6out, userout, userfields;
+	// outputsink.cpp:135-195 OpenOutputFiles: the other per-hit and per-query files
+	std::string alnout, fastapairs, qsegout, tsegout, matched, notmatched;
+	std::string cmdline;           // first line of -alnout (PrintCmdLine, myutils.cpp:1667)
+	unsigned rowlen = 80;          // -rowlen (o_defaults.inc:53)
+	unsigned flank = 8;            // -flank (o_defaults.inc:39), userfield qsegf
+	unsigned wordlength = 8;       // -wordlength as the userfield kmerid reads it (arscorer.cpp:886)
 	bool output_no_hits = false;
+	// alphabet and substitution scores behind the annotation row and the positives count
+	// (g_SubstMx: setnucmx.cpp:33-87 with -match/-mismatch, or BLOSUM62 blosum62.cpp:17-96)
+	bool nucleo = true, local = false;
+	int match = 1, mismatch = -2;
 };
 
 // HitMgr::GetHitCount / GetHit (hitmgr.cpp:367-398,466-475): which of a query's hits the sinks see
@@ -147,9 +179,14 @@ struct HitSelection {
 	bool Any() const { return maxhits != 0 || top_hit_only || top_hits_only; }
 };
 
-// outputsink.cpp:358-381; formats of outputuc.cpp:19-69, blast6out.cpp:27-80, userout.cpp:126-215
+struct FormatTables; // identity / substitution tables of the row formats (usb_host.cpp)
+
+// outputsink.cpp:358-381; formats of outputuc.cpp:19-69, blast6out.cpp:27-80, userout.cpp:126-352,
+// alnout.cpp:45-171 (+ the per-query report outputsink.cpp:237-356), fastapairs / qsegout / tsegout
+// outputsink.cpp:17-44,197-235, matched / notmatched outputsink.cpp:383-400
 class OutputSink : public HitSink {
 public:
+	enum Stream { O_UC, O_B6, O_USER, O_ALN, O_PAIRS, O_QSEG, O_TSEG, O_MATCHED, O_NOTMATCHED, O_COUNT };
 	explicit OutputSink(const OutputOpts &O);
 	~OutputSink() override;
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
@@ -159,14 +196,39 @@ public:
 	void OnAllDone() override;
 
 private:
-	void Flush(FILE *f, std::string &buf, bool force);
+	typedef std::string Bufs[O_COUNT];
+	void FormatQuery(const SeqInfo &Query, const HitMgr &HM, Bufs &out) const;
+	void Flush(int k, std::string &buf, bool force);
 	void OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &out) const;
 	void OutputBlast6(const HitMgr &HM, std::string &out) const;
 	void OutputUser(const HitMgr &HM, std::string &out) const;
-	FILE *m_fUC = nullptr, *m_fB6 = nullptr, *m_fUser = nullptr;
+	void OutputReport(const SeqInfo &Query, const HitMgr &HM, std::string &out) const;
+	void OutputAln(const AlignResult &AR, std::string &out) const;
+	FILE *m_f[O_COUNT] = {};
+	Bufs m_b;
+	OutputOpts m_O;
 	bool m_OutputNoHits = false;
-	std::string m_bUC, m_bB6, m_bUser;
 	std::vector<int> m_UserFields;
+	std::shared_ptr<FormatTables> m_T;
+};
+
+// -dbmatched / -dbnotmatched (dbhitsink.cpp:42-159): the database sequences with / without hits, in
+// database order, written when the search is over.  The letters are the ones the database stores
+// (masked); with -sizeout the matched labels get the number of hits (query size= with -sizein).
+class DBHitSink : public HitSink {
+public:
+	DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut);
+	~DBHitSink() override;
+	void SetSearcher(const GpuSearcher *S) { m_Searcher = S; }
+	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
+	void OnAllDone() override;
+
+private:
+	const SeqDB &m_DB;
+	const GpuSearcher *m_Searcher = nullptr;
+	std::string m_DbMatched, m_DbNotMatched;
+	bool m_SizeIn, m_SizeOut, m_Done = false;
+	std::vector<unsigned> m_HitCounts;
 };
 
 // OTU table of -otutab (otutabsink.cpp:25-76, otutab.cpp:247-310,444-556, label.cpp:152-234): every
@@ -264,6 +326,8 @@ struct SearchOpts {
 	OutputOpts Out;
 	std::vector<HitSink *> ExtraSinks; // run after the OutputSink for every batch (not owned)
 	ClosedRefSink *ClosedRef = nullptr; // one of ExtraSinks: gets the searcher for the stored target letters
+	std::string dbmatched, dbnotmatched; // -dbmatched / -dbnotmatched: Search() adds a DBHitSink
+	bool sizein = false, sizeout = false; // -sizein / -sizeout as -dbmatched reads them
 	int gpus = 1;
 	uint32_t batch = 1u << 18;
 	bool quiet = false;

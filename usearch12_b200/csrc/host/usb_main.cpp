@@ -231,6 +231,27 @@ int main(int argc, char **argv)
 	O.Out.userout = take("userout", nullptr);
 	O.Out.userfields = take("userfields", nullptr);
 	O.Out.output_no_hits = !take("output_no_hits", nullptr).empty();
+	// the other files of OutputSink::OpenOutputFiles (outputsink.cpp:135-195) and of DBHitSink (dbhitsink.cpp:42-50)
+	O.Out.alnout = take("alnout", nullptr);
+	O.Out.fastapairs = take("fastapairs", nullptr);
+	O.Out.qsegout = take("qsegout", nullptr);
+	O.Out.tsegout = take("tsegout", nullptr);
+	O.Out.matched = take("matched", nullptr);
+	O.Out.notmatched = take("notmatched", nullptr);
+	O.Out.rowlen = (unsigned)atoi(take("rowlen", "80").c_str());
+	if (O.Out.rowlen == 0)
+		Die("-rowlen must be positive");
+	O.Out.flank = (unsigned)atoi(take("flank", "8").c_str());
+	O.dbmatched = take("dbmatched", nullptr);
+	O.dbnotmatched = take("dbnotmatched", nullptr);
+	if (oquery.empty() && cquery.empty()) { // -otutab reads -sizein itself; cmd_closed_ref has no size options here
+		O.sizein = !take("sizein", nullptr).empty();
+		O.sizeout = !take("sizeout", nullptr).empty();
+	}
+	for (int i = 0; i < argc; ++i) { // PrintCmdLine (myutils.cpp:1667-1674): every argument followed by a blank
+		O.Out.cmdline += argv[i];
+		O.Out.cmdline += ' ';
+	}
 	// Accepter / Terminator / HitMgr options (accepter.cpp:41-94,145-197; terminator.cpp:66-86;
 	// hitmgr.cpp:367-398)
 	{

@@ -2357,6 +2357,19 @@ extern "C" int usb_local_evalue(const usb_searcher *s, int32_t raw, uint32_t ql,
 	return 0;
 }
 
+extern "C" int usb_params_evalue(const usb_params *p, int32_t raw, uint32_t ql, double *evalue, double *bits)
+{
+	if (!p || p->struct_size != sizeof(usb_params) || !p->local)
+		return fail(USB_EINVAL, "usb_params_evalue: not a -usearch_local parameter block");
+	EStats es;
+	es.init(*p);
+	if (evalue)
+		*evalue = es.raw_to_evalue((double)raw, ql);
+	if (bits)
+		*bits = es.raw_to_bits((double)raw);
+	return 0;
+}
+
 extern "C" int usb_local_pairs(usb_searcher *s, const uint8_t *qseqs, const uint64_t *q_off, uint32_t n_q,
   const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_pairs, usb_result **out)
 {
