@@ -90,3 +90,51 @@ def test_global_segment_fields_are_refused(tmp_path):
     r = subprocess.run([replay, "-query", q, "-db", d, "-hits", hits, "-userout", os.path.join(str(tmp_path), "u"),
                         "-userfields", "query+qseg"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "only supported with -usearch_local" in r.stdout
+
+
+def test_fastq_queries_and_fastq_outputs(tmp_path):
+    """FASTQ query files (fastqseqsource.cpp:8-115: CR LF line ends, '+label' lines, blank lines at the end of the
+    file) and -matchedfq / -notmatchedfq (seqdb.cpp:14-28) against the reference binary's files; the hits, -matched
+    and -uc are those of the same reads given as FASTA (checked when the fixtures were made)."""
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    tmp = str(tmp_path)
+    _, d = M.write_inputs("fmt_nt", tmp)
+    q = os.path.join(tmp, "q.fq")
+    M.write_fastq(q)
+    hits = os.path.join(tmp, "hits.tsv")
+    open(hits, "wb").write(golden_bytes("fmt_nt", "hits"))
+    outs = {k: os.path.join(tmp, "o." + k) for k in ("matchedfq", "notmatchedfq", "matched", "uc")}
+    cmd = [replay, "-query", q, "-db", d, "-hits", hits]
+    for k, path in outs.items():
+        cmd += ["-" + k, path]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for k, path in outs.items():
+        assert open(path, "rb").read() == golden_bytes("fmt_fq" if k.endswith("fq") else "fmt_nt", k), k
+    # FASTA queries have no qualities (seqdb.cpp:19-20)
+    qa, _ = M.write_inputs("fmt_nt", tmp)
+    r = subprocess.run([replay, "-query", qa, "-db", d, "-hits", hits, "-matchedfq", outs["matchedfq"]],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "Cannot convert FASTA to FASTQ" in r.stdout
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("@a\nACGT\n+\nIII\n", "Bad FASTQ record: 4 bases, 3 quals"),
+    ("@a\nAC-T\n+\nIIII\n", "Invalid sequence letter '-'"),
+    ("@a\nACGT\n+\nIIII\n\n@b\nAC\n+\nII\n", "Empty line nr 5"),
+    ("@a\nACGT\n+\nIIII\nb\nAC\n+\nII\n", "Bad line 5"),
+    ("@a\nACGT\n", "Unexpected end-of-file"),
+])
+def test_fastq_errors_are_the_reference_messages(text, msg, tmp_path):
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    q = tmp_path / "bad.fq"
+    q.write_text(text)
+    d = tmp_path / "db.fa"
+    d.write_text(">t\nACGTACGTACGT\n")
+    h = tmp_path / "h.tsv"
+    h.write_text("")
+    r = subprocess.run([replay, "-query", str(q), "-db", str(d), "-hits", str(h)], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and msg in r.stdout, r.stdout

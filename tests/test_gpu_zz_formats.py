@@ -31,3 +31,22 @@ def test_cli_writes_the_reference_files(name, tmp_path):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_outputs(name, paths)
+
+
+def test_cli_fastq_queries(tmp_path):
+    """FASTQ reads as queries: same hits as the FASTA form, -matchedfq / -notmatchedfq as the reference writes them."""
+    from usearch12_b200 import build
+    from tests.test_formats_cpu import golden_bytes
+    cli = build.build_cli()
+    tmp = str(tmp_path)
+    _, d = M.write_inputs("fmt_nt", tmp)
+    q = os.path.join(tmp, "q.fq")
+    M.write_fastq(q)
+    outs = {k: os.path.join(tmp, "o." + k) for k in ("matchedfq", "notmatchedfq", "matched", "uc")}
+    cmd = [cli, "-usearch_global", q, "-db", d, "-quiet"] + M.VARIANTS["fmt_nt"][4]
+    for k, path in outs.items():
+        cmd += ["-" + k, path]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for k, path in outs.items():
+        assert open(path, "rb").read() == golden_bytes("fmt_fq" if k.endswith("fq") else "fmt_nt", k), k

@@ -10,7 +10,7 @@
 //
 //   format_replay -query Q.fa -db DB.udb|DB.fa -hits HITS.tsv [-local 1 -evalue E] [-amino 1]
 //                 [-uc f] [-blast6out f] [-userout f -userfields a+b] [-alnout f] [-fastapairs f] [-qsegout f]
-//                 [-tsegout f] [-matched f] [-notmatched f] [-dbmatched f] [-dbnotmatched f] [-sizein] [-sizeout]
+//                 [-tsegout f] [-matched f] [-notmatched f] [-matchedfq f] [-notmatchedfq f] [-dbmatched f] [-dbnotmatched f] [-sizein] [-sizeout]
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -140,6 +140,8 @@ int main(int argc, char **argv)
 	O.tsegout = get("tsegout");
 	O.matched = get("matched");
 	O.notmatched = get("notmatched");
+	O.matchedfq = get("matchedfq");
+	O.notmatchedfq = get("notmatchedfq");
 	O.output_no_hits = !get("output_no_hits").empty();
 	O.cmdline = "format_replay ";
 	O.nucleo = !amino;

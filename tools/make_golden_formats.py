@@ -78,6 +78,40 @@ def write_inputs(name, tmp):
     return q, d
 
 
+def write_fastq(path):
+    """FASTQ form of fmt_nt's queries: deterministic qualities, CR LF line ends in every fifth record,
+    blank lines at the end of the file (fastqseqsource.cpp:28-41 allows them only there)."""
+    with open(path, "wb") as f:
+        for i, (lab, s) in enumerate(query_subset("fmt_nt")):
+            qual = "".join(chr(33 + (i * 7 + j * 13) % 41) for j in range(len(s)))
+            eol = "\r\n" if i % 5 == 0 else "\n"
+            f.write(("@%s%s%s%s+%s%s%s%s" % (lab[1:], eol, s, eol, lab[1:] if i % 2 else "", eol, qual, eol)).encode())
+        f.write(b"\n\n")
+
+
+def main_fastq():
+    """fmt_fq: the fmt_nt command on FASTQ queries, plus -matchedfq / -notmatchedfq."""
+    opts = VARIANTS["fmt_nt"][4]
+    with tempfile.TemporaryDirectory() as tmp:
+        _, d = write_inputs("fmt_nt", tmp)
+        q = os.path.join(tmp, "q.fq")
+        write_fastq(q)
+        outs = {k: os.path.join(tmp, "o." + k) for k in ("hits", "matchedfq", "notmatchedfq", "matched", "uc")}
+        subprocess.run([REF, "-usearch_global", q, "-db", d, "-threads", "1", "-quiet"] + opts + [
+            "-userout", outs["hits"], "-userfields", HITFIELDS, "-matchedfq", outs["matchedfq"], "-notmatchedfq",
+            outs["notmatchedfq"], "-matched", outs["matched"], "-uc", outs["uc"]], check=True, stdout=subprocess.DEVNULL,
+            stderr=subprocess.DEVNULL)
+        for k, path in outs.items():
+            data = open(path, "rb").read()
+            if k in ("hits", "matched", "uc"):  # the same queries: nothing new to store
+                with gzip.open(os.path.join(OUT, "fmt_nt.%s.gz" % k), "rb") as f:
+                    assert f.read() == data, "FASTQ and FASTA queries gave different " + k
+                continue
+            with gzip.GzipFile(os.path.join(OUT, "fmt_fq.%s.gz" % k), "wb", compresslevel=9, mtime=0) as f:
+                f.write(data)
+            print("golden fmt_fq", k, data.count(b"\n"), "lines")
+
+
 def main():
     sums = {}
     for name, (cmd, _, _, _, opts, fields) in VARIANTS.items():
@@ -105,6 +139,7 @@ def main():
     with open(os.path.join(OUT, "fmt_db_sha256.json"), "w") as f:
         json.dump(sums, f, indent=1, sort_keys=True)
         f.write("\n")
+    main_fastq()
 
 
 if __name__ == "__main__":

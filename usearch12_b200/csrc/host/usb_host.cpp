@@ -136,6 +136,10 @@ void SeqDB::FromFasta(const std::string &FileName)
 	fclose(f);
 	buf[sz] = '\n';
 	const char *base = buf.data(), *end = buf.data() + sz;
+	if (sz > 0 && base[0] == '@') { // filetype.cpp:20-29: the first byte decides between FASTA and FASTQ
+		FromFastq(base, end, FileName);
+		return;
+	}
 	unsigned T = 1;
 	if (sz > (8 << 20))
 		T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -222,6 +226,73 @@ void SeqDB::FromFasta(const std::string &FileName)
 		Warning("%u invalid bytes in FASTA file %s ignored", bad_bytes, FileName.c_str());
 }
 
+// fastqseqsource.cpp:8-115: four lines per record -- "@label", letters, "+anything", qualities of the same
+// length; carriage returns are dropped wherever they stand (linereader.cpp:116-117); empty lines are only
+// allowed at the end of the file.  A record without letters is dropped with a warning, as in FASTA input.
+void SeqDB::FromFastq(const char *p, const char *end, const std::string &FileName)
+{
+	const char *fn = FileName.c_str();
+	unsigned line_nr = 0;
+	std::string line, label;
+	bool eof = false;
+	// LineReader::ReadLine (linereader.cpp:90-133): false at the end of the file; a last line without '\n' counts
+	auto read_line = [&]() -> bool {
+		if (p >= end) {
+			eof = true;
+			return false;
+		}
+		const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+		if (!eol)
+			eol = end;
+		line.assign(p, eol);
+		p = eol + 1;
+		if (line.find('\r') != std::string::npos)
+			line.erase(std::remove(line.begin(), line.end(), '\r'), line.end());
+		++line_nr;
+		return true;
+	};
+	m_Letters.reserve((size_t)(end - p) / 2);
+	m_Quals.reserve((size_t)(end - p) / 2);
+	m_HasQual = true;
+	while (read_line()) {
+		if (line.empty()) {
+			for (;;) {
+				const unsigned nr = line_nr;
+				if (!read_line())
+					return;
+				if (!line.empty())
+					Die("Empty line nr %u in FASTQ file '%s'", nr, fn);
+			}
+		}
+		if (line[0] != '@')
+			Die("Bad line %u in FASTQ file '%s': expected '@'", line_nr, fn);
+		label.assign(line, 1, std::string::npos);
+		if (!read_line())
+			Die("Unexpected end-of-file in FASTQ file %s", fn);
+		for (unsigned char c : line)
+			if (!isalpha(c)) {
+				if (isprint(c))
+					Die("Invalid sequence letter '%c' in FASTQ, line %u file %s", c, line_nr, fn);
+				Die("Non-printing byte 0x%02x in FASTQ sequence line %u file %s label %s", c, line_nr, fn, label.c_str());
+			}
+		const size_t L = line.size();
+		m_Letters.insert(m_Letters.end(), line.begin(), line.end());
+		read_line(); // "+[label]": contents ignored
+		if (!read_line())
+			Die("Unexpected end-of-file in FASTQ file %s", fn);
+		if (line.size() != L)
+			Die("Bad FASTQ record: %u bases, %u quals line %u file %s label %s", (unsigned)L, (unsigned)line.size(), line_nr, fn,
+			    label.c_str());
+		m_Quals.insert(m_Quals.end(), line.begin(), line.end());
+		if (L == 0) {
+			Warning("Empty sequence at line %u in FASTQ file %s, label @%s", line_nr - 2, fn, label.c_str());
+			continue;
+		}
+		m_Labels.push_back(label);
+		m_Offsets.push_back(m_Letters.size());
+	}
+}
+
 void SeqDB::FromUDB(const std::string &FileName, bool &IsNucleo, uint32_t &WordLength)
 {
 	usb_udb *u = nullptr;
@@ -269,6 +340,7 @@ void SeqDB::GetSI(uint32_t Index, SeqInfo &SI) const
 	SI.m_L = GetSeqLength(Index);
 	SI.m_Index = Index;
 	SI.m_RevComp = false;
+	SI.m_Qual = m_HasQual ? m_Quals.data() + m_Offsets[Index] : nullptr;
 }
 
 // ------------------------------------------------------------------ AlignResult
@@ -500,6 +572,8 @@ OutputSink::OutputSink(const OutputOpts &O) : m_O(O)
 	m_f[O_TSEG] = open(O.tsegout);
 	m_f[O_MATCHED] = open(O.matched);
 	m_f[O_NOTMATCHED] = open(O.notmatched);
+	m_f[O_MATCHEDFQ] = open(O.matchedfq);
+	m_f[O_NOTMATCHEDFQ] = open(O.notmatchedfq);
 	m_OutputNoHits = O.output_no_hits;
 	m_T = std::make_shared<FormatTables>();
 	usb::build_local_tables(O.nucleo, O.match, O.mismatch, m_T->L);
@@ -894,6 +968,19 @@ void OutputSink::FormatQuery(const SeqInfo &Query, const HitMgr &HM, Bufs &out) 
 		AppendFasta80(out[O_MATCHED], Query.m_Label, Query.m_Seq, Query.m_L);
 	if (m_f[O_NOTMATCHED] && HM.m_Hits.empty())
 		AppendFasta80(out[O_NOTMATCHED], Query.m_Label, Query.m_Seq, Query.m_L);
+	const int fq = HM.m_Hits.empty() ? O_NOTMATCHEDFQ : O_MATCHEDFQ;
+	if (m_f[fq]) { // SeqToFastq (seqdb.cpp:14-28)
+		if (!Query.m_Qual)
+			Die("Cannot convert FASTA to FASTQ");
+		std::string &o = out[fq];
+		o += '@';
+		o += Query.m_Label;
+		o += '\n';
+		o.append((const char *)Query.m_Seq, Query.m_L);
+		o += "\n+\n";
+		o.append(Query.m_Qual, Query.m_L);
+		o += '\n';
+	}
 }
 
 void OutputSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM)

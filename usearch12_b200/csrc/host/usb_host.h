@@ -31,11 +31,13 @@ struct SeqInfo {
 	uint32_t m_L = 0;
 	uint32_t m_Index = 0;
 	bool m_RevComp = false;
+	const char *m_Qual = nullptr; // FASTQ input only: quality characters, one per letter
 };
 
 // In-memory sequence set (seqdb.h); letters are kept exactly as read.
 class SeqDB {
 public:
+	// FASTA, or FASTQ when the file starts with '@' (MakeSeqSource seqsource.cpp:37-61, GetFileType filetype.cpp:7-47)
 	void FromFasta(const std::string &FileName);
 	// SeqDB part of a .udb file (UDBData::FromUDBFile, udbio.cpp:242-279): letters come back masked
 	// as stored; returns the alphabet and word width of the file's header
@@ -49,7 +51,10 @@ public:
 	const uint64_t *Offsets() const { return m_Offsets.data(); }
 
 private:
+	void FromFastq(const char *p, const char *end, const std::string &FileName);
 	std::vector<uint8_t> m_Letters;
+	std::vector<char> m_Quals; // FASTQ input: same offsets as the letters
+	bool m_HasQual = false;
 	std::vector<uint64_t> m_Offsets{0};
 	std::vector<std::string> m_Labels;
 };
@@ -159,7 +164,7 @@ class GpuSearcher;
 struct OutputOpts {
 	std::string uc, blast6out, userout, userfields;
 	// outputsink.cpp:135-195 OpenOutputFiles: the other per-hit and per-query files
-	std::string alnout, fastapairs, qsegout, tsegout, matched, notmatched;
+	std::string alnout, fastapairs, qsegout, tsegout, matched, notmatched, matchedfq, notmatchedfq;
 	std::string cmdline;           // first line of -alnout (PrintCmdLine, myutils.cpp:1667)
 	unsigned rowlen = 80;          // -rowlen (o_defaults.inc:53)
 	unsigned flank = 8;            // -flank (o_defaults.inc:39), userfield qsegf
@@ -186,7 +191,7 @@ struct FormatTables; // identity / substitution tables of the row formats (usb_h
 // outputsink.cpp:17-44,197-235, matched / notmatched outputsink.cpp:383-400
 class OutputSink : public HitSink {
 public:
-	enum Stream { O_UC, O_B6, O_USER, O_ALN, O_PAIRS, O_QSEG, O_TSEG, O_MATCHED, O_NOTMATCHED, O_COUNT };
+	enum Stream { O_UC, O_B6, O_USER, O_ALN, O_PAIRS, O_QSEG, O_TSEG, O_MATCHED, O_NOTMATCHED, O_MATCHEDFQ, O_NOTMATCHEDFQ, O_COUNT };
 	explicit OutputSink(const OutputOpts &O);
 	~OutputSink() override;
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
