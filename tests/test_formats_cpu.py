@@ -21,12 +21,21 @@ import make_golden_formats as M  # noqa: E402
 
 REPLAY_OPTS = {
     "fmt_nt": [],
+    "fmt_nh": ["-output_no_hits"],
     "fmt_sz": ["-sizein", "-sizeout"],
     "fmt_aag": ["-amino", "1"],
     "fmt_aal": ["-amino", "1", "-local", "1", "-evalue", "10"],
     "fmt_ntl": ["-local", "1", "-evalue", "1e-3"],
 }
 OUT_FLAGS = dict(M.FLAGS, user="-userout")
+
+
+def out_paths(name, tmp):
+    """kind -> output file for the kinds a variant stores (plus the two database files when it stores them)."""
+    kinds = [k for k in M.kinds_of(name) if k != "hits"]
+    if len(M.VARIANTS[name]) == 6:
+        kinds += ["dbm", "dbnm"]
+    return {k: os.path.join(tmp, "o." + k) for k in kinds}
 
 
 def golden_bytes(name, kind):
@@ -67,10 +76,10 @@ def test_sinks_write_the_reference_files(name, chunk, tmp_path):
     subprocess.run([cli, "-makeudb_usearch", d, "-output", udb, "-quiet"], check=True)
     hits = os.path.join(tmp, "hits.tsv")
     open(hits, "wb").write(golden_bytes(name, "hits"))
-    paths = {k: os.path.join(tmp, "o." + k) for k in OUT_FLAGS}
+    paths = out_paths(name, tmp)
     cmd = [replay, "-query", q, "-db", udb, "-hits", hits, "-userfields", M.VARIANTS[name][5]] + REPLAY_OPTS[name]
-    for k, flag in OUT_FLAGS.items():
-        cmd += [flag, paths[k]]
+    for k, path in paths.items():
+        cmd += [OUT_FLAGS[k], path]
     env = dict(os.environ)
     if chunk:  # several formatting threads per batch, chunks written in input order
         env["USB_FORMAT_CHUNK"] = chunk

@@ -9,7 +9,7 @@ import sys
 import pytest
 
 from tests import util
-from tests.test_formats_cpu import OUT_FLAGS, check_outputs
+from tests.test_formats_cpu import OUT_FLAGS, check_outputs, out_paths
 
 sys.path.insert(0, os.path.join(util.ROOT, "tools"))
 import make_golden_formats as M  # noqa: E402
@@ -23,11 +23,11 @@ def test_cli_writes_the_reference_files(name, tmp_path):
     cli = build.build_cli()
     tmp = str(tmp_path)
     q, d = M.write_inputs(name, tmp)
-    cmd_name, _, _, _, opts, fields = M.VARIANTS[name]
-    paths = {k: os.path.join(tmp, "o." + k) for k in OUT_FLAGS}
+    cmd_name, opts, fields = M.VARIANTS[name][0], M.VARIANTS[name][4], M.VARIANTS[name][5]
+    paths = out_paths(name, tmp)
     cmd = [cli, "-" + cmd_name, q, "-db", d, "-quiet", "-userfields", fields] + opts
-    for k, flag in OUT_FLAGS.items():
-        cmd += [flag, paths[k]]
+    for k, path in paths.items():
+        cmd += [OUT_FLAGS[k], path]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_outputs(name, paths)

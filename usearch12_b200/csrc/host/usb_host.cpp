@@ -705,10 +705,10 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 			case UF_opens: case UF_exts: case UF_raw: case UF_bits: case UF_aln: case UF_caln: case UF_qstrand:
 			case UF_tstrand: case UF_mism: case UF_ids: case UF_diffs:
 			case UF_mid: case UF_pctpv: case UF_pctgaps: case UF_pv: case UF_qs: case UF_ts: case UF_qrow: case UF_trow:
-			case UF_qframe: case UF_tframe: case UF_qcov: case UF_tcov: case UF_abskew: case UF_orflo: case UF_orfhi:
-			case UF_qseq: case UF_tseq: case UF_qseg: case UF_tseg:
+			case UF_qframe: case UF_tframe: case UF_qcov: case UF_tcov: case UF_diffsa: case UF_abskew: case UF_tseq:
 				m_bUser += '*';
 				break;
+			case UF_qseq: m_bUser.append((const char *)HM.m_Query.m_Seq, HM.m_Query.m_L); break;
 			default:
 				Die("Invalid user field index %u (-output_no_hits)", (unsigned)m_UserFields[i]);
 			}
