@@ -50,3 +50,31 @@ def test_cli_fastq_queries(tmp_path):
     assert r.returncode == 0, r.stdout
     for k, path in outs.items():
         assert open(path, "rb").read() == golden_bytes("fmt_fq" if k.endswith("fq") else "fmt_nt", k), k
+
+
+@pytest.mark.parametrize("name", ["sc_a", "sc_b", "sc_c", "sc_d", "sc_e"])
+def test_score_options_match_reference(name, tmp_path):
+    """-match / -mismatch / -minhsp / -xdrop_nw: the C ABI with the options in usb_params and the CLI with the
+    reference's option names, against the reference binary's files (tools/make_golden_scores.py)."""
+    import make_golden_scores as S
+    from usearch12_b200 import build, capi
+    recs = M.query_subset("fmt_nt")
+    qlab, qs = [r[0][1:] for r in recs], [r[1] for r in recs]
+    dlab, db = util.read_fasta(os.path.join(util.GOLDEN, "db.fa.gz"))
+    g = util.Golden()
+    p = capi.default_params(**dict(S.PARAMS, **S.VARIANTS[name][1]))
+    s = capi.Searcher(capi.Index(db, p), p)
+    got = util.product_lines(s.search(qs), qlab, qs, dlab)
+    for lines, kind in zip(got, ("user", "uc", "b6")):
+        d = util.first_diff(lines, g.lines(name, kind))
+        assert d is None, "C ABI %s %s\n%s" % (name, kind, d)
+    tmp = str(tmp_path)
+    q, d = M.write_inputs("fmt_nt", tmp)
+    outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc", "b6")}
+    cmd = [build.build_cli(), "-usearch_global", q, "-db", d, "-quiet"] + S.BASE + S.VARIANTS[name][0] + [
+        "-userout", outs["user"], "-userfields", S.USERFIELDS, "-uc", outs["uc"], "-blast6out", outs["b6"]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for kind, path in outs.items():
+        dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
+        assert dd is None, "CLI %s %s\n%s" % (name, kind, dd)

@@ -134,3 +134,24 @@ def test_oracle_cluster_fast_matches_reference_golden(tmp_path):
         for got, name in ((uc, "cluster_%s.uc.gz" % sort), (cen, "cluster_%s.centroids.fa.gz" % sort)):
             with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
                 assert util.first_diff(open(got).read().splitlines(), f.read().splitlines()) is None, name
+
+
+@pytest.mark.parametrize("name", ["sc_a", "sc_b", "sc_c", "sc_d", "sc_e"])
+def test_oracle_score_options_match_reference_golden(name):
+    """-match / -mismatch / -minhsp / -xdrop_nw (alnparams.cpp:330-334, alnheuristics.cpp:26-44): the oracle
+    with the same options against the reference binary's files (tools/make_golden_scores.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    import make_golden_formats as M
+    import make_golden_scores as S
+    from oracle import uso_py as O
+    recs = M.query_subset("fmt_nt")
+    qlab, qs = [r[0][1:] for r in recs], [r[1] for r in recs]
+    dlab, db = util.read_fasta(os.path.join(util.GOLDEN, "db.fa.gz"))
+    op = O.default_params(**dict(S.PARAMS, **S.VARIANTS[name][1]))
+    want = util.oracle_lines(O.Searcher(O.DB(db, op, dlab), op), qlab, qs, dlab)
+    g = util.Golden()
+    for got, kind in zip(want, ("user", "uc", "b6")):
+        d = util.first_diff(got, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)

@@ -220,6 +220,18 @@ int main(int argc, char **argv)
 	O.P.strand_both = nucleo && strand == "both";
 	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", dflt_ma).c_str());
 	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", dflt_mr).c_str());
+	if (lquery.empty() && nucleo) {
+		// nucleotide substitution scores (alnparams.cpp:330-334 SetNucSubstMx) and the HSP heuristics of the
+		// global aligner (alnheuristics.cpp:26-44); a local search keeps its defaults here
+		O.P.match = (float)atof(take("match", "1").c_str());
+		O.P.mismatch = (float)atof(take("mismatch", "-2").c_str());
+		O.P.minhsp = (uint32_t)atoi(take("minhsp", "16").c_str());
+		O.P.xdrop_nw = (float)atof(take("xdrop_nw", "8").c_str());
+		const std::string hw = take("hspw", nullptr); // alnheuristics.cpp:60-61
+		if (!hw.empty())
+			O.P.hspw = (uint32_t)atoi(hw.c_str());
+	}
+	O.P.bump = (uint32_t)atoi(take("bump", "50").c_str()); // udbusortedsearcher.cpp:269-282
 	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
 	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
 	const std::string dbmask = take("dbmask", nucleo ? "fastnucleo" : "fastamino");
