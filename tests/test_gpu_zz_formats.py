@@ -78,3 +78,37 @@ def test_score_options_match_reference(name, tmp_path):
     for kind, path in outs.items():
         dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
         assert dd is None, "CLI %s %s\n%s" % (name, kind, dd)
+
+
+@pytest.mark.parametrize("name", ["exh_00", "exh_0r", "exh_a0"])
+def test_exhaustive_search_matches_reference(name, tmp_path):
+    """-maxaccepts 0 / -maxrejects 0 against 3 000 targets (tools/make_golden_exhaustive.py): the candidate loop
+    runs over whole U-sorted lists made by k_usort_full (up to 2 331 candidates here, more than the 1 024 k_rank
+    materialises); hits identical to the reference binary's, through the C ABI and through the CLI in small
+    batches."""
+    import make_golden_exhaustive as X
+    from usearch12_b200 import build, capi
+    db, dlab, qs, qlab = X.inputs()
+    g = util.Golden()
+    p = capi.default_params(**X.VARIANTS[name][1])
+    s = capi.Searcher(capi.Index(db, p), p)
+    res = s.search(qs)
+    got = util.product_lines(res, qlab, qs, dlab)
+    for lines, kind in zip(got[:2], ("user", "uc")):
+        d = util.first_diff(lines, g.lines(name, kind))
+        assert d is None, "C ABI %s %s\n%s" % (name, kind, d)
+    assert int(res.qstat["n_cand"].max()) > 1024
+    if name != "exh_00":
+        return
+    tmp = str(tmp_path)
+    q, d = os.path.join(tmp, "q.fa"), os.path.join(tmp, "db.fa")
+    open(q, "w").write("".join(">%s\n%s\n" % x for x in zip(qlab, qs)))
+    open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
+    outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
+    cmd = [build.build_cli(), "-usearch_global", q, "-db", d, "-quiet", "-batch", "100"] + X.VARIANTS[name][0] + [
+        "-userout", outs["user"], "-userfields", X.USERFIELDS, "-uc", outs["uc"]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for kind, path in outs.items():
+        dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
+        assert dd is None, "CLI %s %s\n%s" % (name, kind, dd)

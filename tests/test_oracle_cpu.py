@@ -155,3 +155,23 @@ def test_oracle_score_options_match_reference_golden(name):
     for got, kind in zip(want, ("user", "uc", "b6")):
         d = util.first_diff(got, g.lines(name, kind))
         assert d is None, "%s %s\n%s" % (name, kind, d)
+
+
+@pytest.mark.parametrize("name", ["exh_00", "exh_0r", "exh_a0"])
+def test_oracle_exhaustive_search_matches_reference_golden(name):
+    """-maxaccepts 0 / -maxrejects 0 (terminator.cpp:23-31) on 3 000 targets: the oracle's candidate loop runs
+    through whole U-sorted lists (up to ~2 500 candidates for the random reads) like the reference binary
+    (tools/make_golden_exhaustive.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    import make_golden_exhaustive as X
+    from oracle import uso_py as O
+    db, dlab, qs, qlab = X.inputs()
+    op = O.default_params(**X.VARIANTS[name][1])
+    srch = O.Searcher(O.DB(db, op, dlab), op)
+    want = util.oracle_lines(srch, qlab, qs, dlab)
+    g = util.Golden()
+    for got, kind in zip(want[:2], ("user", "uc")):
+        d = util.first_diff(got, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)

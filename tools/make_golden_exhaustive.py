@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Golden fixtures for exhaustive searches (tests/golden/exh_*): -maxaccepts 0 and/or -maxrejects 0
+(terminator.cpp:23-31) against a database of 3 000 targets, where the candidate list of a query is longer than
+the 1 024 candidates the U-sort kernel materialises.  Written by the UNMODIFIED reference binary
+(oracle/_ref/usearch12); the inputs are regenerated from a seed (tools/gen_synth.py), only the outputs are
+stored.   Usage: python tools/make_golden_exhaustive.py"""
+import gzip
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(HERE, "tools"))
+from gen_synth import generate  # noqa: E402
+
+REF = os.path.join(HERE, "oracle", "_ref", "usearch12")
+OUT = os.path.join(HERE, "tests", "golden")
+USERFIELDS = "query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+caln+qstrand"
+# name -> (options, usb_params / oracle fields)
+VARIANTS = {
+    "exh_00": (["-id", "0.9", "-strand", "both", "-maxaccepts", "0", "-maxrejects", "0"],
+               dict(id=0.9, strand_both=1, maxaccepts=0, maxrejects=0)),
+    "exh_0r": (["-id", "0.93", "-strand", "plus", "-maxaccepts", "0", "-maxrejects", "24"],
+               dict(id=0.93, strand_both=0, maxaccepts=0, maxrejects=24)),
+    "exh_a0": (["-id", "0.95", "-strand", "plus", "-maxaccepts", "5", "-maxrejects", "0"],
+               dict(id=0.95, strand_both=0, maxaccepts=5, maxrejects=0)),
+}
+
+
+def inputs():
+    """3 000 targets of 600 letters in 30 families, 240 reads of 200 letters (12 of them random)."""
+    db, reads = generate(ndb=3000, dblen=600, nq=240, qlen=200, seed=29, nroot=30)
+    return db, ["db%d" % i for i in range(len(db))], [r[1] for r in reads], [r[0][1:] for r in reads]
+
+
+def main():
+    db, dlab, qs, qlab = inputs()
+    with tempfile.TemporaryDirectory() as tmp:
+        q, d = os.path.join(tmp, "q.fa"), os.path.join(tmp, "db.fa")
+        open(q, "w").write("".join(">%s\n%s\n" % x for x in zip(qlab, qs)))
+        open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
+        for name, (opts, _) in VARIANTS.items():
+            outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
+            subprocess.run([REF, "-usearch_global", q, "-db", d, "-threads", "1", "-quiet"] + opts + [
+                "-userout", outs["user"], "-userfields", USERFIELDS, "-uc", outs["uc"]], check=True,
+                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for k, path in outs.items():
+                data = open(path, "rb").read()
+                with gzip.GzipFile(os.path.join(OUT, "%s.%s.gz" % (name, k)), "wb", compresslevel=9, mtime=0) as f:
+                    f.write(data)
+                print("golden", name, k, data.count(b"\n"), "lines", os.path.getsize(os.path.join(OUT, "%s.%s.gz" % (name, k))))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

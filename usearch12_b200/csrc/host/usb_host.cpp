@@ -1641,7 +1641,12 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 		ExtraSinks.push_back(dbhits.get());
 	}
 	const uint32_t NQ = Q.GetSeqCount();
-	const uint32_t nbatch = (NQ + Opts.batch - 1) / Opts.batch;
+	// an exhaustive search (-maxaccepts 0 / -maxrejects 0) keeps whole candidate lists on the device: the library
+	// takes at most 2^29 (query-strand, target) pairs per batch
+	uint32_t BatchSize = Opts.batch;
+	if ((P.maxaccepts == 0 || P.maxrejects == 0) && DB.GetSeqCount() > 1024)
+		BatchSize = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(BatchSize, (1ull << 29) / DB.GetSeqCount() / (P.strand_both ? 2 : 1)));
+	const uint32_t nbatch = (NQ + BatchSize - 1) / BatchSize;
 	uint64_t queries_with_hits = 0;
 	// Three overlapped stages.  (1) One submitting thread per device runs usb_search_batch on the
 	// batches dealt to it round-robin, at most two ahead of the consumer.  (2) The consumer takes
@@ -1661,8 +1666,8 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 					std::unique_lock<std::mutex> lk(mu);
 					cv.wait(lk, [&]() { return b < consumed + 2u * (uint32_t)gpus; });
 				}
-				const uint32_t first = b * Opts.batch;
-				std::shared_ptr<void> r = searchers[d]->SearchRaw(Q, first, std::min<uint32_t>(Opts.batch, NQ - first));
+				const uint32_t first = b * BatchSize;
+				std::shared_ptr<void> r = searchers[d]->SearchRaw(Q, first, std::min<uint32_t>(BatchSize, NQ - first));
 				{
 					std::lock_guard<std::mutex> lk(mu);
 					raw[b] = std::move(r);
@@ -1683,7 +1688,7 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 			r = std::move(raw[b]);
 		}
 		const double t1 = now();
-		const uint32_t first = b * Opts.batch, count = std::min<uint32_t>(Opts.batch, NQ - first);
+		const uint32_t first = b * BatchSize, count = std::min<uint32_t>(BatchSize, NQ - first);
 		searchers[b % gpus]->BuildHitMgrs(r, Q, first, count, batch, host_threads);
 		r.reset();
 		const double t2 = now();

@@ -19,6 +19,7 @@
 #include "usb_hostindex.h"
 #include "usb_rank.cuh"
 #include "usb_rankbig.cuh"
+#include "usb_usortfull.cuh"
 
 using namespace usb;
 
@@ -425,6 +426,7 @@ struct usb_searcher {
 	DevBuf<uint8_t> d_q;
 	DevBuf<uint64_t> d_qoff;
 	DevBuf<uint32_t> d_cand_t, d_cand_u, d_ncand, d_nemit, d_runs, d_uout, d_aux;
+	DevBuf<uint32_t> d_cand_full, d_scratch_full; // exhaustive searches: whole candidate lists (usb_usortfull.cuh)
 	DevBuf<usb_hit> d_hits;
 	DevBuf<usb_qstat> d_qstat;
 	DevBuf<DevCounters> d_ctr;
@@ -462,6 +464,9 @@ struct usb_searcher {
 	std::vector<float> es_min_ungapped; // per query length, NAN = not computed yet
 	std::vector<int> es_min_gapped;     // per query length, INT_MIN = not computed yet
 };
+
+// exhaustive searches: (query-strand, target) pairs per batch -- 16 bytes of lists each
+static const uint64_t EXHAUSTIVE_MAX_CELLS = 1ull << 29;
 
 static bool is_int2(float x) { return std::floor(2.0 * (double)x) == 2.0 * (double)x; }
 
@@ -966,6 +971,7 @@ extern "C" void usb_searcher_free(usb_searcher *s)
 		cudaStreamSynchronize(s->stream);
 	s->d_q.release(); s->d_qoff.release(); s->d_cand_t.release(); s->d_cand_u.release();
 	s->d_ncand.release(); s->d_nemit.release(); s->d_runs.release(); s->d_uout.release(); s->d_aux.release();
+	s->d_cand_full.release(); s->d_scratch_full.release();
 	s->d_grp_cnt.release(); s->d_grp_off.release(); s->d_hits_grp.release();
 	s->d_hits.release(); s->d_qstat.release(); s->d_ctr.release(); s->d_slab.release(); s->d_uarena.release();
 	s->d_ltab.release(); s->d_min_ungapped.release(); s->d_min_gapped.release(); s->d_atab.release();
@@ -1729,10 +1735,23 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 		k_max = std::min<uint32_t>(N, RANK_KCAP);
 	if (k_max == 0)
 		k_max = 1;
-	if (k_max > RANK_KCAP)
-		return fail(USB_ELIMIT,
-		  "maxaccepts/maxrejects allow up to %u candidates per query; this build materialises at most %u (set both > 0)",
-		  k_max, RANK_KCAP);
+	// -maxaccepts 0 or -maxrejects 0 on more than RANK_KCAP targets: the candidate loop may walk the whole U-sorted
+	// list.  k_rank then also writes its counters to global memory and k_usort_full (usb_usortfull.cuh) makes the
+	// complete list from them; the loop kernels take it with a stride of N candidates per job.
+	const bool exhaustive = k_max > RANK_KCAP;
+	if (exhaustive) {
+		if (s->big || N > s->P.big)
+			return fail(USB_ELIMIT, "exhaustive searches (-maxaccepts 0 / -maxrejects 0) are not built for databases above -big "
+			                        "(%u targets): set both options > 0", s->P.big);
+		if (s->P.cluster_mode)
+			return fail(USB_EINVAL, "cluster rounds need -maxaccepts 1 and -maxrejects > 0");
+		// counters, scratch list, candidate list and verdicts: 16 bytes per (query-strand, target)
+		if ((uint64_t)s->n_jobs * N > EXHAUSTIVE_MAX_CELLS)
+			return fail(USB_ELIMIT, "exhaustive search: %u query-strands x %u targets exceed %llu list entries per batch; "
+			                        "search batches of at most %llu queries", s->n_jobs, N, (unsigned long long)EXHAUSTIVE_MAX_CELLS,
+			            (unsigned long long)std::max<uint64_t>(1, EXHAUSTIVE_MAX_CELLS / N / s->strands));
+	}
+	const uint32_t k_rank_max = exhaustive ? (uint32_t)RANK_KCAP : k_max;
 	s->k_max = k_max;
 	const uint32_t hsp_cap = std::max<uint32_t>(64, ix->S.max_len / 8 + 16);
 	const bool local = s->P.local != 0;
@@ -1748,7 +1767,8 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 	caps.recs = s->D.fulldp ? (uint64_t)s->n_jobs * k_max + 1024 : (uint64_t)s->n_jobs * 2 + 4096;
 	caps.recs = std::max<uint64_t>(caps.recs, s->d_recs.cap);
 	caps.hsp_words = std::max<uint64_t>(caps.recs * 12, s->d_hsp_arena.cap);
-	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : k_max;
+	// (an exhaustive search starts with room for 64 hits per job; a full buffer is grown and the batch repeated)
+	const uint64_t per_job_hits = s->P.maxaccepts > 0 ? s->P.maxaccepts : exhaustive ? 64 : k_max;
 	// a local target can contribute several ARs (localmulti.cpp): start with room for two per
 	// accepted target and grow on demand
 	uint64_t hits_cap = std::max<uint64_t>(1, (uint64_t)s->n_jobs * per_job_hits * (local ? 2 : 1) + (local ? 1024 : 0));
@@ -1763,15 +1783,33 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			return rc;
 		CK(cudaMemsetAsync(s->d_ctr.p, 0, sizeof(DevCounters), s->stream));
 		CK(cudaEventRecord(s->ev[0], s->stream));
-		if ((rc = launch_rank(s, s->n_jobs, s->strands, k_max, false)))
+		if ((rc = launch_rank(s, s->n_jobs, s->strands, k_rank_max, exhaustive)))
 			return rc;
+		const uint32_t *cand_list = s->d_cand_t.p;
+		if (exhaustive && s->n_jobs) {
+			if ((rc = s->d_cand_full.reserve((size_t)s->n_jobs * N)) || (rc = s->d_scratch_full.reserve((size_t)s->n_jobs * N)))
+				return rc;
+			UsortFullArgs f;
+			f.u = s->d_uout.p;
+			f.scratch = s->d_scratch_full.p;
+			f.cand_t = s->d_cand_full.p;
+			f.n_emit = s->d_nemit.p;
+			f.n_jobs = s->n_jobs;
+			f.n_seq = N;
+			f.bump_d = s->P.bump / 100.0;
+			f.ctr = s->d_ctr.p;
+			k_usort_full<<<(s->n_jobs + USORTFULL_WARPS - 1) / USORTFULL_WARPS, USORTFULL_WARPS * 32, 0, s->stream>>>(f);
+			CK(cudaGetLastError());
+			++s->launches;
+			cand_list = s->d_cand_full.p;
+		}
 		CK(cudaEventRecord(s->ev[1], s->stream));
 		if (s->n_jobs && local) {
 			LocalArgs a;
 			fill_local_args(s, lg, a);
 			a.n_jobs = s->n_jobs;
 			a.strands = s->strands;
-			a.cand_t = s->d_cand_t.p;
+			a.cand_t = cand_list;
 			a.n_emit = s->d_nemit.p;
 			a.k_max = k_max;
 			a.hits = s->d_hits.p;
@@ -1818,7 +1856,7 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 				fill_align_args(s, g, hsp_cap, a);
 			a.n_jobs = s->n_jobs;
 			a.strands = s->strands;
-			a.cand_t = s->d_cand_t.p;
+			a.cand_t = cand_list;
 			a.n_emit = s->d_nemit.p;
 			a.k_max = k_max;
 			a.hits = s->d_hits.p;
