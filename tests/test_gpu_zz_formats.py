@@ -112,3 +112,38 @@ def test_exhaustive_search_matches_reference(name, tmp_path):
     for kind, path in outs.items():
         dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
         assert dd is None, "CLI %s %s\n%s" % (name, kind, dd)
+
+
+def test_exhaustive_local_search_matches_reference():
+    """-usearch_local -maxaccepts 0 -maxrejects 0: k_local walks the whole candidate lists of k_usort_full."""
+    import make_golden_exhaustive as X
+    from usearch12_b200 import capi
+    db, dlab, qs, qlab = X.inputs()
+    name, _, kw, ev = X.LOCAL
+    p = util.product_local_params(True, ev, **kw)
+    s = capi.Searcher(capi.Index(db, p), p)
+    res = s.search(qs)
+    got = util.product_lines_local(res, s, qlab, qs, dlab, True)
+    g = util.Golden()
+    for lines, kind in zip(got[:2], ("user", "uc")):
+        d = util.first_diff(lines, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)
+    assert int(res.qstat["n_cand"].max()) > 1024
+
+
+def test_exhaustive_amino_search_matches_reference():
+    """Amino acid -usearch_global -maxaccepts 0 -maxrejects 0 on 1 500 proteins: k_align takes its candidates
+    from k_usort_full's lists (stride of N candidates per query)."""
+    import ctypes as C
+    import make_golden_exhaustive as X
+    from usearch12_b200 import capi
+    db, dlab, qs, qlab = X.inputs_aa()
+    name, _, kw = X.AMINO
+    p = capi.default_params(**kw)
+    capi.lib().usb_set_amino(C.byref(p))
+    s = capi.Searcher(capi.Index(db, p), p)
+    got = util.product_lines(s.search(qs), qlab, qs, dlab, nucleo=False)
+    g = util.Golden()
+    for lines, kind in zip(got[:2], ("user", "uc")):
+        d = util.first_diff(lines, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)

@@ -175,3 +175,37 @@ def test_oracle_exhaustive_search_matches_reference_golden(name):
     for got, kind in zip(want[:2], ("user", "uc")):
         d = util.first_diff(got, g.lines(name, kind))
         assert d is None, "%s %s\n%s" % (name, kind, d)
+
+
+def test_oracle_exhaustive_local_search_matches_reference_golden():
+    """-usearch_local -maxaccepts 0 -maxrejects 0 on the same 3 000 targets (tests/golden/exh_loc.*)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    import make_golden_exhaustive as X
+    from oracle import uso_py as O
+    db, dlab, qs, qlab = X.inputs()
+    name, _, kw, ev = X.LOCAL
+    op = util.oracle_local_params(True, evalue=ev, **kw)
+    want = util.oracle_lines_local(O.Searcher(O.DB(db, op, dlab), op), qlab, qs, dlab, True)
+    g = util.Golden()
+    for got, kind in zip(want[:2], ("user", "uc")):
+        d = util.first_diff(got, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)
+
+
+def test_oracle_exhaustive_amino_search_matches_reference_golden():
+    """Amino acid -usearch_global -maxaccepts 0 -maxrejects 0 on 1 500 proteins (tests/golden/exh_aa.*)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    import make_golden_exhaustive as X
+    from oracle import uso_py as O
+    db, dlab, qs, qlab = X.inputs_aa()
+    name, _, kw = X.AMINO
+    op = O.default_params(amino=True, **kw)
+    want = util.oracle_lines(O.Searcher(O.DB(db, op, dlab), op), qlab, qs, dlab, nucleo=False)
+    g = util.Golden()
+    for got, kind in zip(want[:2], ("user", "uc")):
+        d = util.first_diff(got, g.lines(name, kind))
+        assert d is None, "%s %s\n%s" % (name, kind, d)

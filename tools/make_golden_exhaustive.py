@@ -28,6 +28,22 @@ VARIANTS = {
 }
 
 
+# -usearch_local with the same inputs: LocalAligner2 against every candidate of the list
+LOCAL_USERFIELDS = "query+target+id+alnlen+mism+opens+qlo+qhi+tlo+thi+evalue+bits+raw+caln+qstrand"
+LOCAL = ("exh_loc", ["-id", "0.93", "-evalue", "1e-3", "-strand", "plus", "-maxaccepts", "0", "-maxrejects", "0"],
+         dict(id=0.93, maxaccepts=0, maxrejects=0), 1e-3)
+
+
+# amino acid -usearch_global (k_align): 1 500 proteins in 30 families, 150 queries
+AMINO = ("exh_aa", ["-id", "0.6", "-maxaccepts", "0", "-maxrejects", "0"], dict(id=0.6, maxaccepts=0, maxrejects=0))
+
+
+def inputs_aa():
+    import gen_synth_aa
+    db, qs = gen_synth_aa.generate(ndb=1500, length=300, nq=150, seed=31, nroot=30)
+    return db, ["p%d" % i for i in range(len(db))], [r[1] for r in qs], [r[0] for r in qs]
+
+
 def inputs():
     """3 000 targets of 600 letters in 30 families, 240 reads of 200 letters (12 of them random)."""
     db, reads = generate(ndb=3000, dblen=600, nq=240, qlen=200, seed=29, nroot=30)
@@ -40,16 +56,32 @@ def main():
         q, d = os.path.join(tmp, "q.fa"), os.path.join(tmp, "db.fa")
         open(q, "w").write("".join(">%s\n%s\n" % x for x in zip(qlab, qs)))
         open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
-        for name, (opts, _) in VARIANTS.items():
+        runs = [(name, "-usearch_global", opts, USERFIELDS) for name, (opts, _) in VARIANTS.items()]
+        runs.append((LOCAL[0], "-usearch_local", LOCAL[1], LOCAL_USERFIELDS))
+        for name, cmd, opts, fields in runs:
             outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
-            subprocess.run([REF, "-usearch_global", q, "-db", d, "-threads", "1", "-quiet"] + opts + [
-                "-userout", outs["user"], "-userfields", USERFIELDS, "-uc", outs["uc"]], check=True,
+            subprocess.run([REF, cmd, q, "-db", d, "-threads", "1", "-quiet"] + opts + [
+                "-userout", outs["user"], "-userfields", fields, "-uc", outs["uc"]], check=True,
                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             for k, path in outs.items():
                 data = open(path, "rb").read()
                 with gzip.GzipFile(os.path.join(OUT, "%s.%s.gz" % (name, k)), "wb", compresslevel=9, mtime=0) as f:
                     f.write(data)
                 print("golden", name, k, data.count(b"\n"), "lines", os.path.getsize(os.path.join(OUT, "%s.%s.gz" % (name, k))))
+    db, dlab, qs, qlab = inputs_aa()
+    with tempfile.TemporaryDirectory() as tmp:
+        q, d = os.path.join(tmp, "q.fa"), os.path.join(tmp, "db.fa")
+        open(q, "w").write("".join(">%s\n%s\n" % x for x in zip(qlab, qs)))
+        open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
+        outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
+        subprocess.run([REF, "-usearch_global", q, "-db", d, "-threads", "1", "-quiet"] + AMINO[1] + [
+            "-userout", outs["user"], "-userfields", USERFIELDS, "-uc", outs["uc"]], check=True,
+            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for k, path in outs.items():
+            data = open(path, "rb").read()
+            with gzip.GzipFile(os.path.join(OUT, "%s.%s.gz" % (AMINO[0], k)), "wb", compresslevel=9, mtime=0) as f:
+                f.write(data)
+            print("golden", AMINO[0], k, data.count(b"\n"), "lines", os.path.getsize(os.path.join(OUT, "%s.%s.gz" % (AMINO[0], k))))
 
 
 if __name__ == "__main__":
