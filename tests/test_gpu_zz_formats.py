@@ -147,3 +147,27 @@ def test_exhaustive_amino_search_matches_reference():
     for lines, kind in zip(got[:2], ("user", "uc")):
         d = util.first_diff(lines, g.lines(name, kind))
         assert d is None, "%s %s\n%s" % (name, kind, d)
+
+
+@pytest.mark.parametrize("name", ["exh_qt5", "exh_qt3"])
+def test_skipped_pairs_walk_whole_candidate_lists(name, tmp_path):
+    """RejectPair rules skip pairs without a Terminator call (searcher.cpp:63-67).  With -minqt 0.5 every pair of
+    these inputs is skipped and two queries walk lists of 1 363 and 2 331 candidates: the batch runs out of the
+    1 024 candidates k_rank materialises and is repeated with the whole lists (k_usort_full).  Files identical to
+    the reference binary's (tools/make_golden_exhaustive.py)."""
+    import make_golden_exhaustive as X
+    from usearch12_b200 import build
+    db, dlab, qs, qlab = X.inputs()
+    g = util.Golden()
+    tmp = str(tmp_path)
+    q, d = os.path.join(tmp, "q.fa"), os.path.join(tmp, "db.fa")
+    open(q, "w").write("".join(">%s\n%s\n" % x for x in zip(qlab, qs)))
+    open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
+    outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
+    cmd = [build.build_cli(), "-usearch_global", q, "-db", d, "-quiet"] + X.SKIPS[name] + [
+        "-userout", outs["user"], "-userfields", X.USERFIELDS, "-uc", outs["uc"]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for kind, path in outs.items():
+        dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
+        assert dd is None, "%s %s\n%s" % (name, kind, dd)

@@ -38,6 +38,15 @@ LOCAL = ("exh_loc", ["-id", "0.93", "-evalue", "1e-3", "-strand", "plus", "-maxa
 AMINO = ("exh_aa", ["-id", "0.6", "-maxaccepts", "0", "-maxrejects", "0"], dict(id=0.6, maxaccepts=0, maxrejects=0))
 
 
+# RejectPair rules skip pairs without a Terminator call (searcher.cpp:63-67): with -minqt 0.5 every pair of these
+# inputs is skipped (200 / 600 letters), so a query walks its whole list -- more than the 1 024 candidates of
+# k_rank for two of them; with -minqt 0.335 about half of the targets are skipped
+SKIPS = {
+    "exh_qt5": ["-id", "0.9", "-strand", "plus", "-maxaccepts", "2", "-maxrejects", "8", "-minqt", "0.5"],
+    "exh_qt3": ["-id", "0.9", "-strand", "plus", "-maxaccepts", "2", "-maxrejects", "8", "-minqt", "0.335"],
+}
+
+
 def inputs_aa():
     import gen_synth_aa
     db, qs = gen_synth_aa.generate(ndb=1500, length=300, nq=150, seed=31, nroot=30)
@@ -58,6 +67,7 @@ def main():
         open(d, "w").write("".join(">%s\n%s\n" % x for x in zip(dlab, db)))
         runs = [(name, "-usearch_global", opts, USERFIELDS) for name, (opts, _) in VARIANTS.items()]
         runs.append((LOCAL[0], "-usearch_local", LOCAL[1], LOCAL_USERFIELDS))
+        runs += [(name, "-usearch_global", opts, USERFIELDS) for name, opts in SKIPS.items()]
         for name, cmd, opts, fields in runs:
             outs = {k: os.path.join(tmp, "o." + k) for k in ("user", "uc")}
             subprocess.run([REF, cmd, q, "-db", d, "-threads", "1", "-quiet"] + opts + [

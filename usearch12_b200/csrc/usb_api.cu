@@ -435,6 +435,7 @@ struct usb_searcher {
 	void *h_stage = nullptr;
 	size_t h_stage_cap = 0;
 	bool big = false;       // UDBSearchBig path (sticky, udbusortedsearcher.cpp:39-58)
+	bool kcap_retry = false; // the batch is being repeated with whole candidate lists (ERR_KCAP)
 	// -usearch_local
 	DevBuf<LocalDevTables> d_ltab;
 	DevBuf<float> d_min_ungapped;
@@ -1731,8 +1732,11 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 	// the build allows; a query that runs out of them unterminated is reported (ERR_KCAP)
 	// (a local search never skips: its rejected pairs are rejects, searcher.cpp:26-49)
 	const bool pair_skips = (s->D.accept_flags & ACC_PAIR_FLAGS) != 0 && !(s->big || N > s->P.big) && !s->P.local;
+	// (after such a batch ran out of candidates it is repeated with the whole lists, see below)
+	const bool pair_skips_all = pair_skips && s->kcap_retry;
+	s->kcap_retry = false;
 	if (pair_skips)
-		k_max = std::min<uint32_t>(N, RANK_KCAP);
+		k_max = pair_skips_all ? N : std::min<uint32_t>(N, RANK_KCAP);
 	if (k_max == 0)
 		k_max = 1;
 	// -maxaccepts 0 or -maxrejects 0 on more than RANK_KCAP targets: the candidate loop may walk the whole U-sorted
@@ -1904,6 +1908,12 @@ extern "C" int usb_batch_run(usb_searcher *s, float *ms)
 			if (c.err & (ERR_REC_FULL | ERR_HSPARENA_FULL))
 				caps.hsp_words = std::max<uint64_t>(caps.hsp_words * 4, caps.recs * 12);
 			continue;
+		}
+		if ((c.err & ERR_KCAP) && !(c.err & ~(ERR_KCAP | ERR_RUNS_FULL | ERR_HITS_FULL | ERR_REC_FULL | ERR_HSPARENA_FULL)) && !exhaustive &&
+		    N > RANK_KCAP && (uint64_t)s->n_jobs * N <= EXHAUSTIVE_MAX_CELLS) {
+			// skipped pairs used up the 1 024 materialised candidates: once more with the whole lists (k_usort_full)
+			s->kcap_retry = true;
+			return usb_batch_run(s, ms);
 		}
 		if (c.err)
 			return fail(USB_ELIMIT, "%s", err_text(c.err));
