@@ -33,7 +33,8 @@ typedef struct usb_params {
 	uint32_t struct_size;   /* = sizeof(usb_params), ABI check */
 	int32_t is_nucleo;      /* 1 = nucleotide DB; 0 = amino acid DB (only with local = 1) */
 	float id;               /* -id */
-	uint32_t maxaccepts;    /* -maxaccepts (terminator.cpp:23-31), default 1 */
+	uint32_t maxaccepts;    /* -maxaccepts (terminator.cpp:23-31), default 1; 0 = no limit: with more than 1 024 targets the
+	                           candidate loop then walks whole U-sorted lists (at most 2^29 query-strand x target pairs per batch) */
 	uint32_t maxrejects;    /* -maxrejects, default 32 (8 for cluster_fast) */
 	int32_t strand_both;    /* -strand both (searcher.cpp:144-158) */
 	uint32_t word_length;   /* UDB word length, nt 8 (udbparams.cpp:246-250) */
