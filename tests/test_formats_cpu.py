@@ -22,6 +22,7 @@ import make_golden_formats as M  # noqa: E402
 REPLAY_OPTS = {
     "fmt_nt": [],
     "fmt_nh": ["-output_no_hits"],
+    "fmt_ms": ["-minsize", "5", "-uc_hitsonly"],
     "fmt_sz": ["-sizein", "-sizeout"],
     "fmt_aag": ["-amino", "1"],
     "fmt_aal": ["-amino", "1", "-local", "1", "-evalue", "10"],

@@ -46,7 +46,7 @@ int main(int argc, char **argv)
 		const char *a = argv[i];
 		while (*a == '-')
 			++a;
-		if (!strcmp(a, "sizein") || !strcmp(a, "sizeout") || !strcmp(a, "output_no_hits"))
+		if (!strcmp(a, "sizein") || !strcmp(a, "sizeout") || !strcmp(a, "output_no_hits") || !strcmp(a, "uc_hitsonly"))
 			opt[a] = "1";
 		else if (i + 1 < argc)
 			opt[a] = argv[++i];
@@ -64,6 +64,7 @@ int main(int argc, char **argv)
 
 	SeqDB Q, DB;
 	Q.FromFasta(get("query"));
+	Q.DropSmallerThan((unsigned)atoi(get("minsize").c_str())); // as Search() does before the first batch
 	if (IsUDBFile(get("db"))) {
 		bool nucleo = true;
 		uint32_t wl = 0;
@@ -143,6 +144,7 @@ int main(int argc, char **argv)
 	O.matchedfq = get("matchedfq");
 	O.notmatchedfq = get("notmatchedfq");
 	O.output_no_hits = !get("output_no_hits").empty();
+	O.uc_hitsonly = !get("uc_hitsonly").empty();
 	O.cmdline = "format_replay ";
 	O.nucleo = !amino;
 	O.local = local;

@@ -37,6 +37,10 @@ VARIANTS = {
     "fmt_nh": ("usearch_global", "q.fa.gz", "db.fa.gz", lambda i: i < 20 or i >= 2400,
                ["-id", "0.97", "-strand", "plus", "-output_no_hits"],
                "query+target+id+mid+qs+ts+qrow+qcov+diffsa+qseq+tseq+ql+clusternr", ("hits", "user", "b6", "uc")),
+    # -minsize: smaller queries are not searched and reach no sink (search.cpp:59-82); -uc_hitsonly (outputuc.cpp:14-15)
+    "fmt_ms": ("usearch_global", "acc_q.fa.gz", "acc_db.fa.gz", lambda i: i % 4 == 1,
+               ["-id", "0.9", "-strand", "plus", "-minsize", "5", "-uc_hitsonly"], "query+target+id",
+               ("hits", "user", "uc", "matched", "notmatched")),
     "fmt_sz": ("usearch_global", "acc_q.fa.gz", "acc_db.fa.gz", lambda i: i % 8 == 0,
                ["-id", "0.9", "-strand", "plus", "-maxaccepts", "3", "-maxrejects", "16", "-sizein", "-sizeout"],
                "query+target+id+abskew+qcov+tcov"),

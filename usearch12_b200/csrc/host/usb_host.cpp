@@ -293,6 +293,36 @@ void SeqDB::FromFastq(const char *p, const char *end, const std::string &FileNam
 	}
 }
 
+void SeqDB::DropSmallerThan(unsigned MinSize)
+{
+	if (MinSize == 0)
+		return;
+	const uint32_t n = GetSeqCount();
+	uint32_t kept = 0;
+	uint64_t w = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (OtuTabSink::GetSizeFromLabel(m_Labels[i], 0xffffffffu) < MinSize)
+			continue;
+		const uint64_t b = m_Offsets[i], L = m_Offsets[i + 1] - b;
+		if (w != b) {
+			memmove(m_Letters.data() + w, m_Letters.data() + b, L);
+			if (m_HasQual)
+				memmove(m_Quals.data() + w, m_Quals.data() + b, L);
+		}
+		if (kept != i)
+			m_Labels[kept].swap(m_Labels[i]);
+		m_Offsets[kept] = w;
+		w += L;
+		++kept;
+	}
+	m_Offsets[kept] = w;
+	m_Offsets.resize(kept + 1);
+	m_Labels.resize(kept);
+	m_Letters.resize(w);
+	if (m_HasQual)
+		m_Quals.resize(w);
+}
+
 void SeqDB::FromUDB(const std::string &FileName, bool &IsNucleo, uint32_t &WordLength)
 {
 	usb_udb *u = nullptr;
@@ -646,7 +676,7 @@ void OutputSink::OutputUC(const SeqInfo &Query, const HitMgr &HM, std::string &m
 	if (!m_f[O_UC])
 		return;
 	std::string cp;
-	if (HM.m_Hits.empty()) {
+	if (HM.m_Hits.empty() && !m_O.uc_hitsonly) {
 		appendf(m_bUC, "N\t*\t%u\t*\t.\t*\t*\t*\t", Query.m_L);
 		m_bUC += Query.m_Label;
 		m_bUC += "\t*\n";
@@ -1585,6 +1615,7 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 			t.join();
 	}
 	parse_q.join();
+	Q.DropSmallerThan(Opts.minsize);
 	// Accepter rules that read labels: identities of equal labels, size= annotations
 	std::vector<uint32_t> q_label, t_label, q_size, t_size;
 	if (P.accept_flags & USB_ACC_NEEDS_LABELS) {

@@ -44,6 +44,9 @@ public:
 	void FromUDB(const std::string &FileName, bool &IsNucleo, uint32_t &WordLength);
 	uint32_t GetSeqCount() const { return (uint32_t)m_Offsets.size() - 1; }
 	void GetSI(uint32_t Index, SeqInfo &SI) const;
+	// Drops the sequences whose size= annotation is below MinSize (the query loop of Thread(), search.cpp:59-82,
+	// skips them before the search: they reach no sink); a label without size= is an error (label.cpp:152-161)
+	void DropSmallerThan(unsigned MinSize);
 	const uint8_t *GetSeq(uint32_t i) const { return m_Letters.data() + m_Offsets[i]; }
 	uint32_t GetSeqLength(uint32_t i) const { return (uint32_t)(m_Offsets[i + 1] - m_Offsets[i]); }
 	const char *GetLabel(uint32_t i) const { return m_Labels[i].c_str(); }
@@ -170,6 +173,7 @@ struct OutputOpts {
 	unsigned flank = 8;            // -flank (o_defaults.inc:39), userfield qsegf
 	unsigned wordlength = 8;       // -wordlength as the userfield kmerid reads it (arscorer.cpp:886)
 	bool output_no_hits = false;
+	bool uc_hitsonly = false;      // -uc_hitsonly: no N records (outputuc.cpp:14-15)
 	// alphabet and substitution scores behind the annotation row and the positives count
 	// (g_SubstMx: setnucmx.cpp:33-87 with -match/-mismatch, or BLOSUM62 blosum62.cpp:17-96)
 	bool nucleo = true, local = false;
@@ -333,6 +337,7 @@ struct SearchOpts {
 	ClosedRefSink *ClosedRef = nullptr; // one of ExtraSinks: gets the searcher for the stored target letters
 	std::string dbmatched, dbnotmatched; // -dbmatched / -dbnotmatched: Search() adds a DBHitSink
 	bool sizein = false, sizeout = false; // -sizein / -sizeout as -dbmatched reads them
+	unsigned minsize = 0;                 // -minsize: queries with a smaller size= annotation are not searched (search.cpp:59-82)
 	int gpus = 1;
 	uint32_t batch = 1u << 18;
 	bool quiet = false;

@@ -26,7 +26,7 @@ int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
 	static const char *flags[] = {"quiet", "output_no_hits", "fulldp", "sizeout", "sizein", "self", "notself", "selfid", "top_hit_only",
-	                              "top_hits_only", nullptr};
+	                              "top_hits_only", "uc_hitsonly", nullptr};
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
 		if (a[0] != '-')
@@ -243,6 +243,8 @@ int main(int argc, char **argv)
 	O.Out.userout = take("userout", nullptr);
 	O.Out.userfields = take("userfields", nullptr);
 	O.Out.output_no_hits = !take("output_no_hits", nullptr).empty();
+	O.Out.uc_hitsonly = !take("uc_hitsonly", nullptr).empty();
+	O.minsize = (unsigned)atoi(take("minsize", "0").c_str());
 	// the other files of OutputSink::OpenOutputFiles (outputsink.cpp:135-195) and of DBHitSink (dbhitsink.cpp:42-50)
 	O.Out.alnout = take("alnout", nullptr);
 	O.Out.fastapairs = take("fastapairs", nullptr);
