@@ -44,7 +44,7 @@ def main():
     out = ["SASS excerpts of usearch12_b200/libusb200.so (sm_100a), made by tools/sass_excerpts.py from cuobjdump -sass", ""]
     counts = {}
     for n, b in fn.items():
-        for op in ("UBLKCP", "SYNCS", "ATOMS", "LDG.E.NA.128", "SHFL.UP", "VIMNMX", "UTMALDG", "TCGEN05"):
+        for op in ("UBLKCP", "SYNCS", "ATOMS", "LDG.E.NA.128", "SHFL.UP", "VIMNMX", "MATCH.ANY", "VOTE", "UTMALDG", "TCGEN05"):
             c = sum(op in l for l in b)
             if c:
                 counts.setdefault(demangled(n), {})[op] = c
@@ -93,6 +93,15 @@ def main():
             out.append("   row, match state from the packed letters, serial insert state inside the lane, max-plus scan over lanes (SHFL.UP),")
             out.append("   four trace bytes in one 32-bit store, 128-bit stores of the new row")
             out += ["   " + l for l in b[max(0, pick[0] - 4):pick[1] + 3]]
+            out.append("")
+
+    for n, b in find(fn, "k_usort_full"):
+        ix = [i for i, l in enumerate(b) if "MATCH.ANY" in l]
+        if ix:
+            out.append("== %s: stable placement step of the whole-list counting sort: MATCH.ANY groups the lanes of one" % demangled(n))
+            out.append("   counter value, the group's first lane takes its slots from the shared-memory offset table, SHFL hands the base out")
+            i0 = ix[-1]
+            out += ["   " + l for l in b[max(0, i0 - 10):i0 + 28]]
             out.append("")
 
     path = os.path.join(ROOT, "profiles", "%s_sass_excerpts.txt" % tag)
