@@ -148,3 +148,33 @@ def test_fastq_errors_are_the_reference_messages(text, msg, tmp_path):
     r = subprocess.run([replay, "-query", str(q), "-db", str(d), "-hits", str(h)], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and msg in r.stdout, r.stdout
+
+
+UNIQUES_OLD = {"uniq_sizeout": ["-sizeout"], "uniq_relabel": ["-sizeout", "-relabel", "Uniq", "-minuniquesize", "2"], "uniq_plain": []}
+
+
+@pytest.mark.parametrize("name", sorted(UNIQUES_OLD) + ["uniq2_" + k for k in sorted(util.UNIQUES2_VARIANTS)])
+def test_uniques_writer_matches_reference(name, tmp_path):
+    """DerepResult::Write for -fastx_uniques (derepresult.cpp:255-284,689-775,822-844: size order by the reference's
+    own quicksort, -sizein sums, -topn, -minuniquesize, -relabel) behind a grouping made on the host by the test tool;
+    the product groups on the device (tests/test_gpu_uniques.py)."""
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    src = str(tmp_path / "in.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "uniq_in.fa.gz"), "rb") as f, open(src, "wb") as g:
+        g.write(f.read())
+    dst = str(tmp_path / "out.fa")
+    extra = UNIQUES_OLD[name] if name in UNIQUES_OLD else util.UNIQUES2_VARIANTS[name[6:]]
+    cmd = [replay, "-uniques", src, "-fastaout", dst]
+    i = 0
+    while i < len(extra):  # the test tool takes "-flag 1" for flags
+        if extra[i] in ("-sizein", "-sizeout"):
+            cmd += [extra[i]]
+            i += 1
+        else:
+            cmd += extra[i:i + 2]
+            i += 2
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    with gzip.open(os.path.join(util.GOLDEN, name + ".fa.gz"), "rb") as f:
+        assert open(dst, "rb").read() == f.read()

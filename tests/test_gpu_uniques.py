@@ -14,6 +14,8 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 VARIANTS = {
+    "uniq2_sizein": util.UNIQUES2_VARIANTS["sizein"],
+    "uniq2_topn": util.UNIQUES2_VARIANTS["topn"],
     "uniq_sizeout": ["-sizeout"],
     "uniq_relabel": ["-sizeout", "-relabel", "Uniq", "-minuniquesize", "2"],
     "uniq_plain": [],

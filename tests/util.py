@@ -301,3 +301,11 @@ def smallmem_reads(path, order):
     with open(path, "w") as f:
         for lab, s, _ in recs:
             f.write(">%s\n%s\n" % (lab, s))
+
+
+# -fastx_uniques with -sizein / -topn: option sets of tests/golden/uniq2_<name>.fa.gz
+# (tools/make_golden_uniques.py, reference binary)
+UNIQUES2_VARIANTS = {
+    "sizein": ["-sizein", "-sizeout", "-relabel", "U"],
+    "topn": ["-sizeout", "-topn", "40", "-minuniquesize", "2"],
+}

@@ -11,6 +11,7 @@
 //   format_replay -query Q.fa -db DB.udb|DB.fa -hits HITS.tsv [-local 1 -evalue E] [-amino 1]
 //                 [-uc f] [-blast6out f] [-userout f -userfields a+b] [-alnout f] [-fastapairs f] [-qsegout f]
 //                 [-tsegout f] [-matched f] [-notmatched f] [-matchedfq f] [-notmatchedfq f] [-dbmatched f] [-dbnotmatched f] [-sizein] [-sizeout]
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -54,6 +55,29 @@ int main(int argc, char **argv)
 			Die("Missing value for -%s", a);
 	}
 	auto get = [&](const char *k) { return opt.count(k) ? opt[k] : std::string(); };
+	if (!get("uniques").empty()) {
+		// -uniques IN.fa: the writers of -fastx_uniques (WriteUniques) behind a grouping made here with a map
+		// (test only; the product groups on the device: usb_derep_full)
+		SeqDB In;
+		In.FromFasta(get("uniques"));
+		std::unordered_map<std::string, unsigned> seen;
+		std::vector<unsigned> UniqOf(In.GetSeqCount());
+		for (uint32_t i = 0; i < In.GetSeqCount(); ++i) {
+			std::string s((const char *)In.GetSeq(i), In.GetSeqLength(i));
+			for (char &c : s)
+				c = (char)toupper((unsigned char)c);
+			UniqOf[i] = seen.emplace(s, (unsigned)seen.size()).first->second;
+		}
+		UniquesOpts U;
+		U.fastaout = get("fastaout");
+		U.relabel = get("relabel");
+		U.sizein = !get("sizein").empty();
+		U.sizeout = !get("sizeout").empty();
+		U.topn = (unsigned)atoi(get("topn").c_str());
+		U.minuniquesize = (unsigned)atoi(get("minuniquesize").c_str());
+		WriteUniques(In, UniqOf, (unsigned)seen.size(), U);
+		return 0;
+	}
 	const bool local = get("local") == "1", amino = get("amino") == "1";
 	usb_params P;
 	usb_default_params(&P, 0);

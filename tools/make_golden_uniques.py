@@ -40,3 +40,11 @@ with tempfile.TemporaryDirectory() as tmp:
         with open(dst, "rb") as f, gzip.open(os.path.join(G, name + ".fa.gz"), "wb") as g:
             g.write(f.read())
         print(name, sum(1 for x in open(dst) if x.startswith(">")), "uniques")
+    # -sizein / -topn (derepresult.cpp:705-707,822-844): tests/golden/uniq2_<name>.fa.gz
+    for name, extra in util.UNIQUES2_VARIANTS.items():
+        dst = os.path.join(tmp, "o.fa")
+        subprocess.run([REF, "-fastx_uniques", src, "-fastaout", dst, "-threads", "1", "-quiet"] + extra, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with open(dst, "rb") as f, gzip.GzipFile(os.path.join(G, "uniq2_%s.fa.gz" % name), "wb", mtime=0) as g:
+            g.write(f.read())
+        print("uniq2", name, sum(1 for x in open(dst) if x.startswith(">")), "uniques")

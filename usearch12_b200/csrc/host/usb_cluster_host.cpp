@@ -154,54 +154,91 @@ void AppendSize(std::string &Label, unsigned Size)
 	Label += "size=" + std::to_string(Size) + ";";
 }
 
-// -fastx_uniques (derepfull.cpp:214-236, derepresult.cpp:255-284,689-775,811-820): uniques in order
-// of decreasing size (the reference's own quicksort, not stable), labelled with the first member's
-// label, optionally relabelled and annotated with ;size=N;
+// DerepResult::Write (derepresult.cpp:878-895): -fastaout (ToFastx :689-775: uniques in order of decreasing size --
+// the reference's own quicksort, not stable --, labelled with the first member's label, optionally relabelled and
+// annotated with ;size=N;).  -uc and -tabbedout are not offered: the reference binary stops with an assert before it
+// writes them (progress.cpp:496, nested ProgressStartOther in DerepResult::Write), so there is nothing to match.
+void WriteUniques(const SeqDB &Input, const std::vector<unsigned> &UniqOf, unsigned UniqueCount, const UniquesOpts &Opts)
+{
+	const unsigned SeqCount = Input.GetSeqCount();
+	// members of every unique in input order (DerepResult::GetSeqIndex)
+	std::vector<unsigned> MemberOff(UniqueCount + 1, 0), Members(SeqCount);
+	for (unsigned i = 0; i < SeqCount; ++i)
+		++MemberOff[UniqOf[i] + 1];
+	for (unsigned u = 0; u < UniqueCount; ++u)
+		MemberOff[u + 1] += MemberOff[u];
+	{
+		std::vector<unsigned> cur(MemberOff.begin(), MemberOff.end() - 1);
+		for (unsigned i = 0; i < SeqCount; ++i)
+			Members[cur[UniqOf[i]]++] = i;
+	}
+	// SetSizes (derepresult.cpp:822-844): member counts, or the sums of the size= annotations with -sizein
+	std::vector<unsigned> Sizes(UniqueCount), Order;
+	for (unsigned u = 0; u < UniqueCount; ++u) {
+		unsigned Size = MemberOff[u + 1] - MemberOff[u];
+		if (Opts.sizein) {
+			Size = 0;
+			for (unsigned m = MemberOff[u]; m < MemberOff[u + 1]; ++m)
+				Size += GetSizeFromLabel(Input.GetLabel(Members[m]), 1);
+		}
+		Sizes[u] = Size;
+	}
+	QuickSortOrderDesc(Sizes, Order);
+	auto open = [](const std::string &fn) {
+		FILE *f = fopen(fn.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", fn.c_str());
+		return f;
+	};
+	auto flush = [](FILE *f, std::string &out, bool force) {
+		if (force || out.size() > (1u << 20)) {
+			fwrite(out.data(), 1, out.size(), f);
+			out.clear();
+		}
+	};
+	std::string out;
+	if (!Opts.fastaout.empty()) {
+		FILE *f = open(Opts.fastaout);
+		unsigned N = UniqueCount, counter = 0;
+		if (Opts.topn != 0 && N > Opts.topn)
+			N = Opts.topn;
+		for (unsigned k = 0; k < N; ++k) {
+			const unsigned u = Order[k], Size = Sizes[u], r = Members[MemberOff[u]];
+			if (Size < Opts.minuniquesize)
+				break;
+			std::string Label = Input.GetLabel(r); // DerepResult::MakeLabel (derepresult.cpp:255-284)
+			if (!Opts.relabel.empty())
+				Label = Opts.relabel + std::to_string(++counter);
+			if (Opts.sizeout) {
+				StripAnnot(Label, "size=");
+				AppendSize(Label, Size);
+			}
+			const uint8_t *s = Input.GetSeq(r);
+			const unsigned L = Input.GetSeqLength(r);
+			out += '>';
+			out += Label;
+			out += '\n';
+			for (unsigned i = 0; i < L; i += 80) {
+				out.append((const char *)s + i, std::min(80u, L - i));
+				out += '\n';
+			}
+			flush(f, out, false);
+		}
+		flush(f, out, true);
+		fclose(f);
+	}
+}
+
+// -fastx_uniques (derepfull.cpp:214-236): the grouping runs on the device, the files are written on the host
 uint64_t FastxUniques(const std::string &InputFileName, const UniquesOpts &Opts)
 {
 	SeqDB Input;
 	Input.FromFasta(InputFileName);
-	std::vector<unsigned> UniqOf, First, USize, Order;
+	std::vector<unsigned> UniqOf, First, USize;
 	if (usb_device_count() <= 0)
 		Die("No CUDA device available: this build has no CPU path");
 	DerepFullDevice(Input, UniqOf, First, USize);
-	QuickSortOrderDesc(USize, Order);
-	if (Opts.fastaout.empty())
-		return First.size();
-	FILE *f = fopen(Opts.fastaout.c_str(), "wb");
-	if (!f)
-		Die("Cannot create %s", Opts.fastaout.c_str());
-	std::string out;
-	unsigned counter = 0;
-	for (unsigned k = 0; k < Order.size(); ++k) {
-		const unsigned u = Order[k], Size = USize[u];
-		if (Size < Opts.minuniquesize)
-			break;
-		std::string Label = Input.GetLabel(First[u]);
-		if (!Opts.relabel.empty())
-			Label = Opts.relabel + std::to_string(++counter);
-		if (Opts.sizeout) {
-			StripAnnot(Label, "size=");
-			if (!Label.empty() && Label.back() != ';') // myutils.cpp:824-839 Psasc
-				Label += ';';
-			Label += "size=" + std::to_string(Size) + ";";
-		}
-		const uint8_t *s = Input.GetSeq(First[u]);
-		const unsigned L = Input.GetSeqLength(First[u]);
-		out += '>';
-		out += Label;
-		out += '\n';
-		for (unsigned i = 0; i < L; i += 80) {
-			out.append((const char *)s + i, std::min(80u, L - i));
-			out += '\n';
-		}
-		if (out.size() > (1u << 20)) {
-			fwrite(out.data(), 1, out.size(), f);
-			out.clear();
-		}
-	}
-	fwrite(out.data(), 1, out.size(), f);
-	fclose(f);
+	WriteUniques(Input, UniqOf, (unsigned)First.size(), Opts);
 	return First.size();
 }
 

@@ -365,9 +365,15 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts);
 struct UniquesOpts {
 	std::string fastaout, relabel;
 	bool sizeout = false;
+	bool sizein = false;       // sizes = sums of the members' size= annotations (derepresult.cpp:211-225,822-844)
 	unsigned minuniquesize = 0;
+	unsigned topn = 0;         // -topn: at most this many uniques in -fastaout (derepresult.cpp:705-707), 0 = all
 };
-// -fastx_uniques (derepfull.cpp:214-236): full-length dereplication, host only; returns the number of uniques.
+// DerepResult::Write (derepresult.cpp:878-895) for a finished grouping: UniqOf[i] = unique of input sequence i,
+// uniques numbered in order of first occurrence.  Host only.
+void WriteUniques(const SeqDB &Input, const std::vector<unsigned> &UniqOf, unsigned UniqueCount, const UniquesOpts &Opts);
+// -fastx_uniques (derepfull.cpp:214-236): full-length dereplication on the device (usb_derep_full), output on the
+// host; returns the number of uniques.
 uint64_t FastxUniques(const std::string &InputFileName, const UniquesOpts &Opts);
 
 // SeqDB::GetIsNucleo (seqdb.cpp:268-310): a database is nucleotide when more than 80 of 100 sampled

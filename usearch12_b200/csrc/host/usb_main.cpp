@@ -96,6 +96,8 @@ int main(int argc, char **argv)
 		U.fastaout = take("fastaout", nullptr);
 		U.relabel = take("relabel", nullptr);
 		U.sizeout = !take("sizeout", nullptr).empty();
+		U.sizein = !take("sizein", nullptr).empty();
+		U.topn = (unsigned)atoi(take("topn", "0").c_str());
 		U.minuniquesize = (unsigned)atoi(take("minuniquesize", "0").c_str());
 		const bool quiet = !take("quiet", nullptr).empty();
 		take("threads", nullptr); // the unique order follows the reference's -threads 1 behaviour
