@@ -178,3 +178,36 @@ def test_uniques_writer_matches_reference(name, tmp_path):
     assert r.returncode == 0, r.stdout
     with gzip.open(os.path.join(util.GOLDEN, name + ".fa.gz"), "rb") as f:
         assert open(dst, "rb").read() == f.read()
+
+
+def _otutab_inputs(tmp):
+    for n in ("otutab_reads", "otutab_otus"):
+        with gzip.open(os.path.join(util.GOLDEN, n + ".fa.gz"), "rb") as f, open(os.path.join(tmp, n + ".fa"), "wb") as g:
+            g.write(f.read())
+
+
+def check_otutab_outputs(tmp):
+    import make_golden_otutab2 as T
+    for got, want in (("tab.txt", "otutab.tab.gz"), ("map.txt", "otutab.map.gz"), ("o.biom", "otutab.biom.gz")):
+        data = open(os.path.join(tmp, got), "rb").read()
+        if got == "o.biom":
+            assert b'"date": "' in data and b'"date": ""' not in data
+            data = T.blank_date(data)
+        with gzip.open(os.path.join(util.GOLDEN, want), "rb") as f:
+            assert data == f.read(), want
+
+
+def test_otutab_sink_writes_the_reference_files(tmp_path):
+    """OtuTabSink (otutabsink.cpp:25-76; OTUTable::ToTabbedFile otutab.cpp:247-310, ToJsonFile json.cpp:32-110, the
+    -mapout lines) behind the reference's own hit table (tests/golden/otutab.hits.gz): -otutabout, -mapout and
+    -biomout byte-identical to the reference binary's files, without a GPU."""
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    tmp = str(tmp_path)
+    _otutab_inputs(tmp)
+    open(os.path.join(tmp, "hits.tsv"), "wb").write(golden_bytes("otutab", "hits"))
+    r = subprocess.run([replay, "-query", "otutab_reads.fa", "-db", "otutab_otus.fa", "-hits", "hits.tsv", "-otutabout",
+                        "tab.txt", "-mapout", "map.txt", "-biomout", "o.biom"], cwd=tmp, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    check_otutab_outputs(tmp)

@@ -171,3 +171,16 @@ def test_skipped_pairs_walk_whole_candidate_lists(name, tmp_path):
     for kind, path in outs.items():
         dd = util.first_diff(open(path).read().splitlines(), g.lines(name, kind))
         assert dd is None, "%s %s\n%s" % (name, kind, dd)
+
+
+def test_cli_otutab_with_biom(tmp_path):
+    """-otutab with -biomout through the CLI on the device (the table, the map and the BIOM file of the reference)."""
+    from usearch12_b200 import build
+    from tests.test_formats_cpu import _otutab_inputs, check_otutab_outputs
+    tmp = str(tmp_path)
+    _otutab_inputs(tmp)
+    r = subprocess.run([build.build_cli(), "-otutab", "otutab_reads.fa", "-otus", "otutab_otus.fa", "-otutabout", "tab.txt",
+                        "-mapout", "map.txt", "-biomout", "o.biom", "-quiet"], cwd=tmp, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    check_otutab_outputs(tmp)

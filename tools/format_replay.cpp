@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <unordered_map>
@@ -176,6 +177,10 @@ int main(int argc, char **argv)
 	O.mismatch = (int)P.mismatch;
 	OutputSink Sink(O);
 	DBHitSink DbSink(DB, get("dbmatched"), get("dbnotmatched"), !get("sizein").empty(), !get("sizeout").empty());
+	// -otutab: the OTU table sink behind the same hit lists (otutabsink.cpp:25-76)
+	std::unique_ptr<OtuTabSink> OtuSink;
+	if (!get("otutabout").empty() || !get("mapout").empty() || !get("biomout").empty())
+		OtuSink.reset(new OtuTabSink(get("otutabout"), get("mapout"), get("sample_delim"), true, get("biomout")));
 
 	// batches of 5000 queries, so that both the serial and the threaded formatting paths run
 	const uint32_t NQ = Q.GetSeqCount(), B = (uint32_t)std::max(1, atoi(get("batch").empty() ? "5000" : get("batch").c_str()));
@@ -201,8 +206,12 @@ int main(int argc, char **argv)
 		}
 		Sink.OnBatchDone(batch);
 		DbSink.OnBatchDone(batch);
+		if (OtuSink)
+			OtuSink->OnBatchDone(batch);
 	}
 	Sink.OnAllDone();
 	DbSink.OnAllDone();
+	if (OtuSink)
+		OtuSink->OnAllDone();
 	return 0;
 }

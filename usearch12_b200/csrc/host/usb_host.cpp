@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <chrono>
@@ -1186,8 +1187,9 @@ void OtuTabSink::GetSampleNameFromLabel(const std::string &Label, std::string &S
 	}
 }
 
-OtuTabSink::OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet)
-  : m_OtuTabOut(OtuTabOut), m_SampleDelim(SampleDelim), m_Quiet(Quiet)
+OtuTabSink::OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet,
+  const std::string &BiomOut)
+  : m_OtuTabOut(OtuTabOut), m_SampleDelim(SampleDelim), m_BiomOut(BiomOut), m_Quiet(Quiet)
 {
 	if (!MapOut.empty()) {
 		m_fMap = fopen(MapOut.c_str(), "wb");
@@ -1255,25 +1257,52 @@ void OtuTabSink::OnAllDone()
 		fclose(m_fMap);
 		m_fMap = nullptr;
 	}
-	if (m_OtuTabOut.empty())
-		return;
-	// OTUTable::ToTabbedFile (otutab.cpp:247-310)
-	FILE *f = fopen(m_OtuTabOut.c_str(), "wb");
-	if (!f)
-		Die("Cannot create %s", m_OtuTabOut.c_str());
-	fprintf(f, "#OTU ID");
-	for (const std::string &sn : m_SampleNames) {
-		fputc('\t', f);
-		fputs(sn.c_str(), f);
-	}
-	fputc('\n', f);
-	for (size_t o = 0; o < m_OTUNames.size(); ++o) {
-		fputs(m_OTUNames[o].c_str(), f);
-		for (size_t k = 0; k < m_SampleNames.size(); ++k)
-			fprintf(f, "\t%u", m_Counts[o][k]);
+	if (!m_OtuTabOut.empty()) {
+		// OTUTable::ToTabbedFile (otutab.cpp:247-310)
+		FILE *f = fopen(m_OtuTabOut.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", m_OtuTabOut.c_str());
+		fprintf(f, "#OTU ID");
+		for (const std::string &sn : m_SampleNames) {
+			fputc('\t', f);
+			fputs(sn.c_str(), f);
+		}
 		fputc('\n', f);
+		for (size_t o = 0; o < m_OTUNames.size(); ++o) {
+			fputs(m_OTUNames[o].c_str(), f);
+			for (size_t k = 0; k < m_SampleNames.size(); ++k)
+				fprintf(f, "\t%u", m_Counts[o][k]);
+			fputc('\n', f);
+		}
+		fclose(f);
 	}
-	fclose(f);
+	if (!m_BiomOut.empty()) {
+		// OTUTable::ToJsonFile (json.cpp:32-110): BIOM 1.0, sparse; an entry is followed by a comma unless it is the
+		// cell of the last OTU and the last sample, whether or not that cell is written
+		FILE *f = fopen(m_BiomOut.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", m_BiomOut.c_str());
+		const size_t NO = m_OTUNames.size(), NS = m_SampleNames.size();
+		time_t now = time(nullptr);
+		char when[32];
+		snprintf(when, sizeof when, "%.24s", asctime(localtime(&now)));
+		fprintf(f, "{\n\t\"id\":\"%s\",\n\t\"format\": \"Biological Observation Matrix 1.0\",\n", m_BiomOut.c_str());
+		fprintf(f, "\t\"format_url\": \"http://biom-format.org\",\n\t\"generated_by\": \"usearch\",\n\t\"type\": \"OTU table\",\n");
+		fprintf(f, "\t\"date\": \"%s\",\n\t\"matrix_type\": \"sparse\",\n\t\"matrix_element_type\": \"float\",\n", when);
+		fprintf(f, "\t\"shape\": [%u,%u],\n\t\"rows\":[\n", (unsigned)NO, (unsigned)NS);
+		for (size_t o = 0; o < NO; ++o)
+			fprintf(f, "\t\t{\"id\":\"%s\", \"metadata\":null}%s\n", m_OTUNames[o].c_str(), o + 1 != NO ? "," : "");
+		fprintf(f, "\t],\n\t\"columns\":[\n");
+		for (size_t k = 0; k < NS; ++k)
+			fprintf(f, "\t\t{\"id\":\"%s\", \"metadata\":null}%s\n", m_SampleNames[k].c_str(), k + 1 != NS ? "," : "");
+		fprintf(f, "\t],\n\t\"data\": [\n");
+		for (size_t o = 0; o < NO; ++o)
+			for (size_t k = 0; k < NS; ++k)
+				if (m_Counts[o][k] != 0)
+					fprintf(f, "\t\t[%u,%u,%u]%s\n", (unsigned)o, (unsigned)k, m_Counts[o][k], (o + 1 < NO || k + 1 < NS) ? "," : "");
+		fprintf(f, "\t]\n}\n");
+		fclose(f);
+	}
 }
 
 // ------------------------------------------------------------------ ClosedRefSink

@@ -246,7 +246,8 @@ private:
 // reference's order for -threads 1.
 class OtuTabSink : public HitSink {
 public:
-	OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet);
+	OtuTabSink(const std::string &OtuTabOut, const std::string &MapOut, const std::string &SampleDelim, bool Quiet,
+	  const std::string &BiomOut = std::string()); // -biomout: OTUTable::ToJsonFile (json.cpp:32-110)
 	~OtuTabSink() override;
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
 	void OnAllDone() override;
@@ -255,7 +256,7 @@ public:
 	void GetSampleNameFromLabel(const std::string &Label, std::string &SampleName) const;
 
 private:
-	std::string m_OtuTabOut, m_SampleDelim;
+	std::string m_OtuTabOut, m_SampleDelim, m_BiomOut;
 	FILE *m_fMap = nullptr;
 	bool m_Quiet = false, m_Done = false;
 	std::vector<std::string> m_OTUNames, m_SampleNames;

@@ -173,7 +173,8 @@ int main(int argc, char **argv)
 		if (db.empty())
 			Die("Must specify OTU FASTA -db, -otus or -zotus");
 		const std::string tab = take("otutabout", nullptr), mapout = take("mapout", nullptr);
-		otusink.reset(new OtuTabSink(tab, mapout, take("sample_delim", nullptr), opt.count("quiet") != 0));
+		const std::string biom = take("biomout", nullptr);
+		otusink.reset(new OtuTabSink(tab, mapout, take("sample_delim", nullptr), opt.count("quiet") != 0, biom));
 		O.ExtraSinks.push_back(otusink.get());
 	}
 	if (id.empty())
