@@ -23,6 +23,7 @@ REPLAY_OPTS = {
     "fmt_nt": [],
     "fmt_nh": ["-output_no_hits"],
     "fmt_ms": ["-minsize", "5", "-uc_hitsonly"],
+    "fmt_rl": ["-rowlen", "50", "-flank", "3"],
     "fmt_sz": ["-sizein", "-sizeout"],
     "fmt_aag": ["-amino", "1"],
     "fmt_aal": ["-amino", "1", "-local", "1", "-evalue", "10"],

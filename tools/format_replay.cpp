@@ -168,6 +168,10 @@ int main(int argc, char **argv)
 	O.notmatched = get("notmatched");
 	O.matchedfq = get("matchedfq");
 	O.notmatchedfq = get("notmatchedfq");
+	if (!get("rowlen").empty())
+		O.rowlen = (unsigned)atoi(get("rowlen").c_str());
+	if (!get("flank").empty())
+		O.flank = (unsigned)atoi(get("flank").c_str());
 	O.output_no_hits = !get("output_no_hits").empty();
 	O.uc_hitsonly = !get("uc_hitsonly").empty();
 	O.cmdline = "format_replay ";

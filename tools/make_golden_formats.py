@@ -41,6 +41,10 @@ VARIANTS = {
     "fmt_ms": ("usearch_global", "acc_q.fa.gz", "acc_db.fa.gz", lambda i: i % 4 == 1,
                ["-id", "0.9", "-strand", "plus", "-minsize", "5", "-uc_hitsonly"], "query+target+id",
                ("hits", "user", "uc", "matched", "notmatched")),
+    # -rowlen / -flank (alnout.cpp:93-99, userout.cpp:216-235)
+    "fmt_rl": ("usearch_global", "q.fa.gz", "db.fa.gz", lambda i: i >= 2560,
+               ["-id", "0.9", "-strand", "both", "-maxaccepts", "2", "-maxrejects", "16", "-rowlen", "50", "-flank", "3"],
+               "query+target+qsegf+qlo+qhi", ("hits", "user", "aln")),
     "fmt_sz": ("usearch_global", "acc_q.fa.gz", "acc_db.fa.gz", lambda i: i % 8 == 0,
                ["-id", "0.9", "-strand", "plus", "-maxaccepts", "3", "-maxrejects", "16", "-sizein", "-sizeout"],
                "query+target+id+abskew+qcov+tcov"),
