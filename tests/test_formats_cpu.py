@@ -36,7 +36,7 @@ def out_paths(name, tmp):
     """kind -> output file for the kinds a variant stores (plus the two database files when it stores them)."""
     kinds = [k for k in M.kinds_of(name) if k != "hits"]
     if len(M.VARIANTS[name]) == 6:
-        kinds += ["dbm", "dbnm"]
+        kinds += ["dbm", "dbnm", "dbcut"]
     return {k: os.path.join(tmp, "o." + k) for k in kinds}
 
 
@@ -50,7 +50,7 @@ def check_outputs(name, paths):
     sums = json.load(open(os.path.join(util.GOLDEN, "fmt_db_sha256.json")))
     for kind, path in paths.items():
         got = open(path, "rb").read()
-        if kind in ("dbm", "dbnm"):
+        if kind in ("dbm", "dbnm", "dbcut"):
             want = sums["%s.%s" % (name, kind)]
             assert (len(got), got.count(b">")) == (want["bytes"], want["seqs"]), (name, kind)
             assert hashlib.sha256(got).hexdigest() == want["sha256"], (name, kind)

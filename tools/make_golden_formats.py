@@ -58,7 +58,8 @@ VARIANTS = {
 }
 KINDS = ("hits", "user", "aln", "pairs", "qseg", "tseg", "matched", "notmatched", "uc", "b6")
 FLAGS = {"aln": "-alnout", "pairs": "-fastapairs", "qseg": "-qsegout", "tseg": "-tsegout", "matched": "-matched",
-         "notmatched": "-notmatched", "uc": "-uc", "b6": "-blast6out", "dbm": "-dbmatched", "dbnm": "-dbnotmatched"}
+         "notmatched": "-notmatched", "uc": "-uc", "b6": "-blast6out", "dbm": "-dbmatched", "dbnm": "-dbnotmatched",
+         "dbcut": "-dbcutout"}
 
 
 def read_fasta(path):
@@ -137,7 +138,7 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             q, d = write_inputs(name, tmp)
             base = [REF, "-" + cmd, q, "-db", d, "-threads", "1", "-quiet"] + opts
-            outs = {k: os.path.join(tmp, "o." + k) for k in KINDS + ("dbm", "dbnm")}
+            outs = {k: os.path.join(tmp, "o." + k) for k in KINDS + ("dbm", "dbnm", "dbcut")}
             run = base + ["-userout", outs["user"], "-userfields", fields]
             for k, flag in FLAGS.items():
                 run += [flag, outs[k]]
@@ -152,7 +153,7 @@ def main():
                 with gzip.GzipFile(os.path.join(OUT, "%s.%s.gz" % (name, k)), "wb", compresslevel=9, mtime=0) as f:
                     f.write(data)
                 print("golden", name, k, data.count(b"\n"), "lines")
-            for k in ("dbm", "dbnm") if len(VARIANTS[name]) == 6 else ():  # the database split in two: kept as digests
+            for k in ("dbm", "dbnm", "dbcut") if len(VARIANTS[name]) == 6 else ():  # database files: kept as digests
                 data = open(outs[k], "rb").read()
                 sums["%s.%s" % (name, k)] = {"sha256": hashlib.sha256(data).hexdigest(), "bytes": len(data),
                                              "seqs": data.count(b">")}

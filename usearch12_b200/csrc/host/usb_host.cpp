@@ -1054,10 +1054,15 @@ void OutputSink::OnBatchDone(const std::vector<HitMgr> &Batch)
 }
 
 // ------------------------------------------------------------------ DBHitSink
-DBHitSink::DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut)
-  : m_DB(DB), m_DbMatched(DbMatched), m_DbNotMatched(DbNotMatched), m_SizeIn(SizeIn), m_SizeOut(SizeOut),
+DBHitSink::DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut,
+  const std::string &DbCutOut)
+  : m_DB(DB), m_DbMatched(DbMatched), m_DbNotMatched(DbNotMatched), m_DbCutOut(DbCutOut), m_SizeIn(SizeIn), m_SizeOut(SizeOut),
     m_HitCounts(DB.GetSeqCount(), 0)
 {
+	if (!m_DbCutOut.empty()) {
+		m_Los.resize(DB.GetSeqCount());
+		m_His.resize(DB.GetSeqCount());
+	}
 }
 
 DBHitSink::~DBHitSink() { OnAllDone(); }
@@ -1067,8 +1072,13 @@ void DBHitSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM) // dbhitsink
 	if (HM.m_Hits.empty())
 		return;
 	const unsigned N = m_SizeIn ? OtuTabSink::GetSizeFromLabel(Query.m_Label, 1) : 1;
-	for (const AlignResult &AR : HM.m_Hits)
+	for (const AlignResult &AR : HM.m_Hits) {
 		m_HitCounts[AR.GetTargetIndex()] += N;
+		if (!m_DbCutOut.empty()) { // GetTLo / GetTHi: first and last target letter under an M column
+			m_Los[AR.GetTargetIndex()].insert(m_Los[AR.GetTargetIndex()].end(), N, AR.m_Hit.first_mt);
+			m_His[AR.GetTargetIndex()].insert(m_His[AR.GetTargetIndex()].end(), N, AR.m_Hit.last_mt);
+		}
+	}
 }
 
 void DBHitSink::OnAllDone() // dbhitsink.cpp:42-50,108-130
@@ -1077,6 +1087,31 @@ void DBHitSink::OnAllDone() // dbhitsink.cpp:42-50,108-130
 		return;
 	m_Done = true;
 	std::string Stored;
+	if (!m_DbCutOut.empty()) {
+		// CutToFASTA (dbhitsink.cpp:52-106): every target with hits, from the median first to the median last aligned
+		// position of its hits (element N/2 of the sorted positions)
+		FILE *f = fopen(m_DbCutOut.c_str(), "wb");
+		if (!f)
+			Die("Cannot create %s", m_DbCutOut.c_str());
+		std::string out;
+		for (uint32_t i = 0; i < m_DB.GetSeqCount(); ++i) {
+			if (m_HitCounts[i] == 0)
+				continue;
+			std::sort(m_Los[i].begin(), m_Los[i].end());
+			std::sort(m_His[i].begin(), m_His[i].end());
+			const unsigned Lo = m_Los[i][m_Los[i].size() / 2], Hi = m_His[i][m_His[i].size() / 2];
+			if (!(Lo < Hi && Hi < m_DB.GetSeqLength(i)))
+				Die("-dbcutout: segment %u-%u of >%s", Lo, Hi, m_DB.GetLabel(i)); // asserta(Lo < Hi && Hi < L)
+			const uint8_t *Seq = m_DB.GetSeq(i);
+			if (m_Searcher) {
+				m_Searcher->GetStoredTarget(i, Stored);
+				Seq = (const uint8_t *)Stored.data();
+			}
+			AppendFasta80(out, m_DB.GetLabel(i), Seq + Lo, Hi - Lo + 1);
+		}
+		fwrite(out.data(), 1, out.size(), f);
+		fclose(f);
+	}
 	for (int Matched = 1; Matched >= 0; --Matched) {
 		const std::string &FileName = Matched ? m_DbMatched : m_DbNotMatched;
 		if (FileName.empty())
@@ -1695,8 +1730,8 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	OutputSink Sink(OO);
 	std::vector<HitSink *> ExtraSinks = Opts.ExtraSinks;
 	std::unique_ptr<DBHitSink> dbhits;
-	if (!Opts.dbmatched.empty() || !Opts.dbnotmatched.empty()) {
-		dbhits.reset(new DBHitSink(DB, Opts.dbmatched, Opts.dbnotmatched, Opts.sizein, Opts.sizeout));
+	if (!Opts.dbmatched.empty() || !Opts.dbnotmatched.empty() || !Opts.dbcutout.empty()) {
+		dbhits.reset(new DBHitSink(DB, Opts.dbmatched, Opts.dbnotmatched, Opts.sizein, Opts.sizeout, Opts.dbcutout));
 		dbhits->SetSearcher(searchers[0]);
 		ExtraSinks.push_back(dbhits.get());
 	}

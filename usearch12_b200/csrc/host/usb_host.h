@@ -226,7 +226,8 @@ private:
 // (masked); with -sizeout the matched labels get the number of hits (query size= with -sizein).
 class DBHitSink : public HitSink {
 public:
-	DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut);
+	DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut,
+	  const std::string &DbCutOut = std::string()); // -dbcutout: the hit segments (dbhitsink.cpp:52-106)
 	~DBHitSink() override;
 	void SetSearcher(const GpuSearcher *S) { m_Searcher = S; }
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
@@ -235,7 +236,8 @@ public:
 private:
 	const SeqDB &m_DB;
 	const GpuSearcher *m_Searcher = nullptr;
-	std::string m_DbMatched, m_DbNotMatched;
+	std::string m_DbMatched, m_DbNotMatched, m_DbCutOut;
+	std::vector<std::vector<unsigned>> m_Los, m_His; // -dbcutout: first / last aligned target position of every hit
 	bool m_SizeIn, m_SizeOut, m_Done = false;
 	std::vector<unsigned> m_HitCounts;
 };
@@ -336,7 +338,7 @@ struct SearchOpts {
 	OutputOpts Out;
 	std::vector<HitSink *> ExtraSinks; // run after the OutputSink for every batch (not owned)
 	ClosedRefSink *ClosedRef = nullptr; // one of ExtraSinks: gets the searcher for the stored target letters
-	std::string dbmatched, dbnotmatched; // -dbmatched / -dbnotmatched: Search() adds a DBHitSink
+	std::string dbmatched, dbnotmatched, dbcutout; // -dbmatched / -dbnotmatched / -dbcutout: Search() adds a DBHitSink
 	bool sizein = false, sizeout = false; // -sizein / -sizeout as -dbmatched reads them
 	unsigned minsize = 0;                 // -minsize: queries with a smaller size= annotation are not searched (search.cpp:59-82)
 	int gpus = 1;

@@ -263,6 +263,7 @@ int main(int argc, char **argv)
 	O.Out.flank = (unsigned)atoi(take("flank", "8").c_str());
 	O.dbmatched = take("dbmatched", nullptr);
 	O.dbnotmatched = take("dbnotmatched", nullptr);
+	O.dbcutout = take("dbcutout", nullptr);
 	if (oquery.empty() && cquery.empty()) { // -otutab reads -sizein itself; cmd_closed_ref has no size options here
 		O.sizein = !take("sizein", nullptr).empty();
 		O.sizeout = !take("sizeout", nullptr).empty();
