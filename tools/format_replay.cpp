@@ -166,6 +166,7 @@ int main(int argc, char **argv)
 	O.tsegout = get("tsegout");
 	O.matched = get("matched");
 	O.notmatched = get("notmatched");
+	O.trimout = get("trimout");
 	O.matchedfq = get("matchedfq");
 	O.notmatchedfq = get("notmatchedfq");
 	if (!get("rowlen").empty())

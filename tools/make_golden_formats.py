@@ -44,7 +44,7 @@ VARIANTS = {
     # -rowlen / -flank (alnout.cpp:93-99, userout.cpp:216-235)
     "fmt_rl": ("usearch_global", "q.fa.gz", "db.fa.gz", lambda i: i >= 2560,
                ["-id", "0.9", "-strand", "both", "-maxaccepts", "2", "-maxrejects", "16", "-rowlen", "50", "-flank", "3"],
-               "query+target+qsegf+qlo+qhi", ("hits", "user", "aln")),
+               "query+target+qsegf+qlo+qhi+qtrimlo+qtrimhi+qtrimseq", ("hits", "user", "aln", "trim")),
     "fmt_sz": ("usearch_global", "acc_q.fa.gz", "acc_db.fa.gz", lambda i: i % 8 == 0,
                ["-id", "0.9", "-strand", "plus", "-maxaccepts", "3", "-maxrejects", "16", "-sizein", "-sizeout"],
                "query+target+id+abskew+qcov+tcov"),
@@ -59,7 +59,7 @@ VARIANTS = {
 KINDS = ("hits", "user", "aln", "pairs", "qseg", "tseg", "matched", "notmatched", "uc", "b6")
 FLAGS = {"aln": "-alnout", "pairs": "-fastapairs", "qseg": "-qsegout", "tseg": "-tsegout", "matched": "-matched",
          "notmatched": "-notmatched", "uc": "-uc", "b6": "-blast6out", "dbm": "-dbmatched", "dbnm": "-dbnotmatched",
-         "dbcut": "-dbcutout"}
+         "dbcut": "-dbcutout", "trim": "-trimout"}
 
 
 def read_fasta(path):
@@ -138,7 +138,7 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             q, d = write_inputs(name, tmp)
             base = [REF, "-" + cmd, q, "-db", d, "-threads", "1", "-quiet"] + opts
-            outs = {k: os.path.join(tmp, "o." + k) for k in KINDS + ("dbm", "dbnm", "dbcut")}
+            outs = {k: os.path.join(tmp, "o." + k) for k in KINDS + ("dbm", "dbnm", "dbcut", "trim")}
             run = base + ["-userout", outs["user"], "-userfields", fields]
             for k, flag in FLAGS.items():
                 run += [flag, outs[k]]

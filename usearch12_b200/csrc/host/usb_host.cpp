@@ -415,7 +415,7 @@ enum UserField {
 	// the fields that read the letters (rows, segments, substitution scores) and the derived ratios
 	UF_mid, UF_pctpv, UF_pctgaps, UF_pv, UF_qs, UF_ts, UF_qseq, UF_tseq, UF_qseg, UF_tseg, UF_qsegf, UF_qrow, UF_trow,
 	UF_qrowdots, UF_trowdots, UF_qframe, UF_tframe, UF_qcov, UF_tcov, UF_diffsa, UF_editdiffs, UF_abskew, UF_orflo,
-	UF_orfhi, UF_orfframe, UF_gc, UF_kmerid, UF_COUNT
+	UF_orfhi, UF_orfframe, UF_gc, UF_kmerid, UF_qtrimlo, UF_qtrimhi, UF_qtrimseq, UF_COUNT
 };
 static const char *g_UserFieldNames[UF_COUNT] = {
 	"query", "target", "clusternr", "id", "fractid", "dist", "pairs", "gaps", "allgaps", "qlo", "qhi", "tlo",
@@ -423,7 +423,7 @@ static const char *g_UserFieldNames[UF_COUNT] = {
 	"qstrand", "tstrand", "mism", "ids", "diffs", "evalue", "bits", "raw", "qlor", "qhir", "tlor", "thir",
 	"mid", "pctpv", "pctgaps", "pv", "qs", "ts", "qseq", "tseq", "qseg", "tseg", "qsegf", "qrow", "trow",
 	"qrowdots", "trowdots", "qframe", "tframe", "qcov", "tcov", "diffsa", "editdiffs", "abskew", "orflo",
-	"orfhi", "orfframe", "gc", "kmerid"};
+	"orfhi", "orfframe", "gc", "kmerid", "qtrimlo", "qtrimhi", "qtrimseq"};
 
 // g_MatchMxNucleo / g_MatchMxAmino (alpha2.cpp:220-279) and g_SubstMx by raw character, from the
 // same table builder the kernels use (usb_tables.h)
@@ -578,6 +578,30 @@ void AppendRowFasta(std::string &out, const char *Label, const std::string &Row)
 	out += '\n';
 }
 
+// AlignResult::GetTrimInfo (arscorer.cpp:932-970): the query without the letters under a leading / trailing run of D
+// columns; the loop that copies the letters stops one short of QHi, as in the reference
+void TrimInfo(const AlignResult &AR, unsigned &QLo, unsigned &QHi, std::string &QSeg)
+{
+	const unsigned QL = AR.m_Hit.ql;
+	QLo = 0;
+	QHi = QL ? QL - 1 : 0;
+	QSeg.clear();
+	if (QL == 0)
+		return;
+	const uint32_t n = AR.m_Hit.run_cnt;
+	if (n > 0 && (AR.m_Runs[0] & 3) == 1)
+		QLo = AR.m_Runs[0] >> 2;
+	if (n > 0 && (AR.m_Runs[n - 1] & 3) == 1) {
+		const unsigned NewQHi = QL - (AR.m_Runs[n - 1] >> 2) - 1;
+		if (NewQHi > QLo)
+			QHi = NewQHi;
+	}
+	std::string buf;
+	const uint8_t *Q = AR.GetQSeq(buf);
+	if (QHi > QLo)
+		QSeg.assign((const char *)Q + QLo, QHi - QLo);
+}
+
 unsigned NDig(unsigned n) // alnout.cpp:9-24
 {
 	return n < 10 ? 1 : n < 100 ? 2 : n < 1000 ? 3 : n < 10000 ? 4 : n < 100000 ? 5 : n < 1000000 ? 6 : 10;
@@ -603,6 +627,7 @@ OutputSink::OutputSink(const OutputOpts &O) : m_O(O)
 	m_f[O_TSEG] = open(O.tsegout);
 	m_f[O_MATCHED] = open(O.matched);
 	m_f[O_NOTMATCHED] = open(O.notmatched);
+	m_f[O_TRIM] = open(O.trimout);
 	m_f[O_MATCHEDFQ] = open(O.matchedfq);
 	m_f[O_NOTMATCHEDFQ] = open(O.notmatchedfq);
 	m_OutputNoHits = O.output_no_hits;
@@ -845,6 +870,15 @@ void OutputSink::OutputUser(const HitMgr &HM, std::string &m_bUser) const
 				break;
 			}
 			case UF_kmerid: appendf(m_bUser, "%.4f", KmerId(AR, W(), m_O.wordlength)); break;
+			case UF_qtrimlo: case UF_qtrimhi: case UF_qtrimseq: {
+				unsigned Lo, Hi;
+				TrimInfo(AR, Lo, Hi, tmp);
+				if (m_UserFields[i] == UF_qtrimseq)
+					m_bUser += tmp;
+				else
+					appendf(m_bUser, "%u", (m_UserFields[i] == UF_qtrimlo ? Lo : Hi) + 1);
+				break;
+			}
 			}
 		}
 		m_bUser += '\n';
@@ -967,11 +1001,19 @@ void OutputSink::FormatQuery(const SeqInfo &Query, const HitMgr &HM, Bufs &out) 
 	OutputBlast6(HM, out[O_B6]);
 	OutputUser(HM, out[O_USER]);
 	OutputReport(Query, HM, out[O_ALN]);
-	if (m_f[O_ALN] || m_f[O_PAIRS] || m_f[O_QSEG] || m_f[O_TSEG]) {
+	if (m_f[O_ALN] || m_f[O_PAIRS] || m_f[O_QSEG] || m_f[O_TSEG] || m_f[O_TRIM]) {
 		std::string QRow, TRow;
 		for (const AlignResult &AR : HM.m_Hits) {
 			if (m_f[O_ALN])
 				OutputAln(AR, out[O_ALN]);
+			if (m_f[O_TRIM]) { // OutputSink::OutputTrim (outputsink.cpp:402-417): label:lo-hi
+				unsigned Lo, Hi;
+				std::string Seq;
+				TrimInfo(AR, Lo, Hi, Seq);
+				std::string Label = AR.GetQueryLabel();
+				appendf(Label, ":%u-%u", Lo + 1, Hi + 1);
+				AppendFasta80(out[O_TRIM], Label.c_str(), (const uint8_t *)Seq.data(), Seq.size());
+			}
 			if (!(m_f[O_PAIRS] || m_f[O_QSEG] || m_f[O_TSEG]))
 				continue;
 			const RowWalk W(AR);

@@ -167,7 +167,7 @@ class GpuSearcher;
 struct OutputOpts {
 	std::string uc, blast6out, userout, userfields;
 	// outputsink.cpp:135-195 OpenOutputFiles: the other per-hit and per-query files
-	std::string alnout, fastapairs, qsegout, tsegout, matched, notmatched, matchedfq, notmatchedfq;
+	std::string alnout, fastapairs, qsegout, tsegout, matched, notmatched, matchedfq, notmatchedfq, trimout;
 	std::string cmdline;           // first line of -alnout (PrintCmdLine, myutils.cpp:1667)
 	unsigned rowlen = 80;          // -rowlen (o_defaults.inc:53)
 	unsigned flank = 8;            // -flank (o_defaults.inc:39), userfield qsegf
@@ -195,7 +195,7 @@ struct FormatTables; // identity / substitution tables of the row formats (usb_h
 // outputsink.cpp:17-44,197-235, matched / notmatched outputsink.cpp:383-400
 class OutputSink : public HitSink {
 public:
-	enum Stream { O_UC, O_B6, O_USER, O_ALN, O_PAIRS, O_QSEG, O_TSEG, O_MATCHED, O_NOTMATCHED, O_MATCHEDFQ, O_NOTMATCHEDFQ, O_COUNT };
+	enum Stream { O_UC, O_B6, O_USER, O_ALN, O_PAIRS, O_QSEG, O_TSEG, O_MATCHED, O_NOTMATCHED, O_MATCHEDFQ, O_NOTMATCHEDFQ, O_TRIM, O_COUNT };
 	explicit OutputSink(const OutputOpts &O);
 	~OutputSink() override;
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;

@@ -255,6 +255,7 @@ int main(int argc, char **argv)
 	O.Out.tsegout = take("tsegout", nullptr);
 	O.Out.matched = take("matched", nullptr);
 	O.Out.notmatched = take("notmatched", nullptr);
+	O.Out.trimout = take("trimout", nullptr);
 	O.Out.matchedfq = take("matchedfq", nullptr);
 	O.Out.notmatchedfq = take("notmatchedfq", nullptr);
 	O.Out.rowlen = (unsigned)atoi(take("rowlen", "80").c_str());
