@@ -184,3 +184,31 @@ def test_cli_otutab_with_biom(tmp_path):
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_otutab_outputs(tmp)
+
+
+def test_cluster_fast_writes_the_output_sink_files(tmp_path):
+    """-cluster_fast with the per-hit files of its OutputSink (-userout, -blast6out, -alnout, -fastapairs, -matched,
+    -notmatched) next to the .uc: the reference binary's files (tools/make_golden_cluster_outputs.py)."""
+    import gzip
+    import json
+    import make_golden_cluster_outputs as C
+    from usearch12_b200 import build
+    tmp = str(tmp_path)
+    reads = os.path.join(tmp, "r.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "cluster_reads.fa.gz"), "rb") as f, open(reads, "wb") as g:
+        g.write(f.read())
+    outs = {k: os.path.join(tmp, "o." + k) for k in C.FLAGS}
+    cmd = [build.build_cli(), "-cluster_fast", reads, "-quiet", "-userfields", C.USERFIELDS] + C.OPTS
+    for k, flag in C.FLAGS.items():
+        cmd += [flag, outs[k]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    g = util.Golden()
+    for kind in ("user", "b6"):
+        d = util.first_diff(open(outs[kind]).read().splitlines(), g.lines("cluster_out", kind))
+        assert d is None, "%s\n%s" % (kind, d)
+    d = util.first_diff(open(outs["uc"]).read().splitlines(), g.lines("cluster_length", "uc"))
+    assert d is None, d
+    sums = json.load(open(os.path.join(util.GOLDEN, "cluster_out_sha256.json")))
+    for kind, want in sums.items():
+        assert C.digest_of(kind, open(outs[kind], "rb").read()) == want, kind

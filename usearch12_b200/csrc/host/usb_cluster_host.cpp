@@ -17,6 +17,8 @@
 
 #include "usb_host.h"
 
+#include <memory>
+
 #include <chrono>
 #include <climits>
 #include <thread>
@@ -366,6 +368,22 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 	if (!Opts.uc.empty() && !(fUC = fopen(Opts.uc.c_str(), "wb")))
 		Die("Cannot create %s", Opts.uc.c_str());
 	std::string buf, cp;
+	// OutputSink of the cluster searcher: every unique goes through it in search order, with its hit or without one
+	std::unique_ptr<OutputSink> Sink;
+	{
+		const OutputOpts &O = Opts.Out;
+		if (!O.userout.empty() || !O.blast6out.empty() || !O.alnout.empty() || !O.fastapairs.empty() || !O.qsegout.empty() ||
+		    !O.tsegout.empty() || !O.matched.empty() || !O.notmatched.empty()) {
+			OutputOpts OO = O;
+			OO.uc.clear();
+			OO.nucleo = Opts.P.is_nucleo != 0;
+			OO.local = false;
+			OO.match = (int)Opts.P.match;
+			OO.mismatch = (int)Opts.P.mismatch;
+			Sink.reset(new OutputSink(OO));
+		}
+	}
+	HitMgr SinkHM;
 	std::vector<unsigned> ClusterSizes, CentroidRead;
 	std::vector<uint32_t> cidx;
 	unsigned pos = 0;
@@ -390,6 +408,22 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 			const unsigned r0 = First[u];
 			const unsigned L = Input.GetSeqLength(r0);
 			const unsigned c = cidx[q];
+			if (Sink) {
+				Input.GetSI(r0, SinkHM.m_Query);
+				SinkHM.m_Hits.clear();
+				if (qoff[q + 1] != qoff[q]) {
+					AlignResult AR;
+					AR.m_Hit = hits[qoff[q]];
+					AR.m_Hit.target = c; // the centroid database is numbered by cluster (userfield clusternr)
+					AR.m_Runs = runs + AR.m_Hit.run_off;
+					AR.m_Query = SinkHM.m_Query;
+					Input.GetSI(CentroidRead[c], AR.m_Target);
+					AR.m_Target.m_Index = c;
+					AR.m_Nucleo = Opts.P.is_nucleo != 0;
+					SinkHM.m_Hits.push_back(AR);
+				}
+				Sink->OnQueryDone(SinkHM.m_Query, SinkHM);
+			}
 			if (qoff[q + 1] == qoff[q]) {
 				// ClusterSink::OnQueryDone, no hit: new centroid (clustersink.cpp:318-329)
 				if (c != ClusterSizes.size())
@@ -440,6 +474,8 @@ uint64_t ClusterFast(const std::string &ReadsFileName, const ClusterOpts &Opts)
 		else
 			B = std::max<uint32_t>(64, std::min<uint32_t>(B, 2 * ncom));
 	}
+	if (Sink)
+		Sink->OnAllDone();
 	const double t_loop = now();
 	const unsigned ClusterCount = (unsigned)ClusterSizes.size();
 	if (fUC) {

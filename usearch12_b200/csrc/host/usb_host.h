@@ -350,6 +350,10 @@ struct SearchOpts {
 struct ClusterOpts {
 	usb_params P;             // usb_default_params(&P, 1) + -id
 	std::string uc, centroids, sort, relabel;
+	// the per-hit files of the OutputSink that MakeClusterSearcher puts behind the searcher next to the ClusterSink
+	// (-userout, -blast6out, -alnout, -fastapairs, -qsegout, -tsegout, -matched, -notmatched); Out.uc stays empty, the
+	// .uc file is written by the cluster loop itself
+	OutputOpts Out;
 	uint32_t max_block = 1u << 16;
 	unsigned minsize = 0;     // -minsize: centroids of smaller clusters are not written
 	bool minsize_filled = false;

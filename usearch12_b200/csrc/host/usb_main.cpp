@@ -76,6 +76,22 @@ int main(int argc, char **argv)
 		C.uc = take("uc", nullptr);
 		C.centroids = take("centroids", nullptr);
 		C.sort = take("sort", nullptr);
+		C.Out.userout = take("userout", nullptr);
+		C.Out.userfields = take("userfields", nullptr);
+		C.Out.blast6out = take("blast6out", nullptr);
+		C.Out.alnout = take("alnout", nullptr);
+		C.Out.fastapairs = take("fastapairs", nullptr);
+		C.Out.qsegout = take("qsegout", nullptr);
+		C.Out.tsegout = take("tsegout", nullptr);
+		C.Out.matched = take("matched", nullptr);
+		C.Out.notmatched = take("notmatched", nullptr);
+		C.Out.rowlen = (unsigned)atoi(take("rowlen", "80").c_str());
+		if (C.Out.rowlen == 0)
+			Die("-rowlen must be positive");
+		for (int i = 0; i < argc; ++i) {
+			C.Out.cmdline += argv[i];
+			C.Out.cmdline += ' ';
+		}
 		C.sizein = !take("sizein", nullptr).empty();
 		C.sizeout = !take("sizeout", nullptr).empty();
 		C.relabel = take("relabel", nullptr);
