@@ -196,6 +196,11 @@ def check_otutab_outputs(tmp):
             data = T.blank_date(data)
         with gzip.open(os.path.join(util.GOLDEN, want), "rb") as f:
             assert data == f.read(), want
+    # DBHitSink behind -otutab counts one hit per query (dbhitsink.cpp:138-139); -sizeout writes the counts
+    sums = json.load(open(os.path.join(util.GOLDEN, "otutab_sha256.json")))
+    for k, want in sums.items():
+        data = open(os.path.join(tmp, k), "rb").read()
+        assert (hashlib.sha256(data).hexdigest(), data.count(b">")) == (want["sha256"], want["seqs"]), k
 
 
 def test_otutab_sink_writes_the_reference_files(tmp_path):
@@ -207,8 +212,10 @@ def test_otutab_sink_writes_the_reference_files(tmp_path):
     tmp = str(tmp_path)
     _otutab_inputs(tmp)
     open(os.path.join(tmp, "hits.tsv"), "wb").write(golden_bytes("otutab", "hits"))
-    r = subprocess.run([replay, "-query", "otutab_reads.fa", "-db", "otutab_otus.fa", "-hits", "hits.tsv", "-otutabout",
-                        "tab.txt", "-mapout", "map.txt", "-biomout", "o.biom"], cwd=tmp, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True)
+    # -dbmatched writes the letters the database holds: masked (loaddb.cpp:117-118)
+    subprocess.run([build.build_cli(), "-makeudb_usearch", "otutab_otus.fa", "-output", "otus.udb", "-quiet"], cwd=tmp, check=True)
+    r = subprocess.run([replay, "-query", "otutab_reads.fa", "-db", "otus.udb", "-hits", "hits.tsv", "-otutabout",
+                        "tab.txt", "-mapout", "map.txt", "-biomout", "o.biom", "-dbmatched", "dbm.fa", "-dbnotmatched", "dbnm.fa",
+                        "-notmatched", "nm.fa", "-sizeout"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_otutab_outputs(tmp)

@@ -180,7 +180,8 @@ def test_cli_otutab_with_biom(tmp_path):
     tmp = str(tmp_path)
     _otutab_inputs(tmp)
     r = subprocess.run([build.build_cli(), "-otutab", "otutab_reads.fa", "-otus", "otutab_otus.fa", "-otutabout", "tab.txt",
-                        "-mapout", "map.txt", "-biomout", "o.biom", "-quiet"], cwd=tmp, stdout=subprocess.PIPE,
+                        "-mapout", "map.txt", "-biomout", "o.biom", "-dbmatched", "dbm.fa", "-dbnotmatched", "dbnm.fa",
+                        "-notmatched", "nm.fa", "-sizeout", "-quiet"], cwd=tmp, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_otutab_outputs(tmp)

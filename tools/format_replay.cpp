@@ -181,7 +181,8 @@ int main(int argc, char **argv)
 	O.match = (int)P.match;
 	O.mismatch = (int)P.mismatch;
 	OutputSink Sink(O);
-	DBHitSink DbSink(DB, get("dbmatched"), get("dbnotmatched"), !get("sizein").empty(), !get("sizeout").empty(), get("dbcutout"));
+	DBHitSink DbSink(DB, get("dbmatched"), get("dbnotmatched"), !get("sizein").empty(), !get("sizeout").empty(), get("dbcutout"),
+	  !get("otutabout").empty() || !get("mapout").empty() || !get("biomout").empty());
 	// -otutab: the OTU table sink behind the same hit lists (otutabsink.cpp:25-76)
 	std::unique_ptr<OtuTabSink> OtuSink;
 	if (!get("otutabout").empty() || !get("mapout").empty() || !get("biomout").empty())

@@ -27,7 +27,8 @@ def main():
             with gzip.open(os.path.join(G, n + ".fa.gz"), "rb") as f, open(os.path.join(tmp, n + ".fa"), "wb") as g:
                 g.write(f.read())
         subprocess.run([M.REF, "-otutab", "otutab_reads.fa", "-otus", "otutab_otus.fa", "-otutabout", "tab.txt", "-mapout",
-                        "map.txt", "-biomout", "o.biom", "-userout", "hits.txt", "-userfields", M.HITFIELDS, "-threads", "1",
+                        "map.txt", "-biomout", "o.biom", "-dbmatched", "dbm.fa", "-dbnotmatched", "dbnm.fa", "-notmatched", "nm.fa", "-sizeout",
+                        "-userout", "hits.txt", "-userfields", M.HITFIELDS, "-threads", "1",
                         "-quiet"], check=True, cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         for src, dst in (("tab.txt", "otutab.tab.gz"), ("map.txt", "otutab.map.gz")):  # unchanged by the extra outputs
             with gzip.open(os.path.join(G, dst), "rb") as g:
@@ -37,6 +38,14 @@ def main():
             with gzip.GzipFile(os.path.join(G, dst), "wb", compresslevel=9, mtime=0) as g:
                 g.write(data)
             print(dst, data.count(b"\n"), "lines")
+        # DBHitSink counts one hit per query in -otutab (dbhitsink.cpp:138-139); digests of the three FASTA files
+        import hashlib
+        import json
+        sums = {k: {"sha256": hashlib.sha256(open(os.path.join(tmp, k), "rb").read()).hexdigest(),
+                    "seqs": open(os.path.join(tmp, k), "rb").read().count(b">")} for k in ("dbm.fa", "dbnm.fa", "nm.fa")}
+        with open(os.path.join(G, "otutab_sha256.json"), "w") as f:
+            json.dump(sums, f, indent=1, sort_keys=True)
+            f.write("\n")
 
 
 if __name__ == "__main__":

@@ -1097,9 +1097,9 @@ void OutputSink::OnBatchDone(const std::vector<HitMgr> &Batch)
 
 // ------------------------------------------------------------------ DBHitSink
 DBHitSink::DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut,
-  const std::string &DbCutOut)
+  const std::string &DbCutOut, bool TopHitOnly)
   : m_DB(DB), m_DbMatched(DbMatched), m_DbNotMatched(DbNotMatched), m_DbCutOut(DbCutOut), m_SizeIn(SizeIn), m_SizeOut(SizeOut),
-    m_HitCounts(DB.GetSeqCount(), 0)
+    m_TopHitOnly(TopHitOnly), m_HitCounts(DB.GetSeqCount(), 0)
 {
 	if (!m_DbCutOut.empty()) {
 		m_Los.resize(DB.GetSeqCount());
@@ -1120,6 +1120,8 @@ void DBHitSink::OnQueryDone(const SeqInfo &Query, const HitMgr &HM) // dbhitsink
 			m_Los[AR.GetTargetIndex()].insert(m_Los[AR.GetTargetIndex()].end(), N, AR.m_Hit.first_mt);
 			m_His[AR.GetTargetIndex()].insert(m_His[AR.GetTargetIndex()].end(), N, AR.m_Hit.last_mt);
 		}
+		if (m_TopHitOnly)
+			break;
 	}
 }
 
@@ -1773,7 +1775,7 @@ uint64_t Search(const std::string &QueryFileName, const std::string &DBFileName,
 	std::vector<HitSink *> ExtraSinks = Opts.ExtraSinks;
 	std::unique_ptr<DBHitSink> dbhits;
 	if (!Opts.dbmatched.empty() || !Opts.dbnotmatched.empty() || !Opts.dbcutout.empty()) {
-		dbhits.reset(new DBHitSink(DB, Opts.dbmatched, Opts.dbnotmatched, Opts.sizein, Opts.sizeout, Opts.dbcutout));
+		dbhits.reset(new DBHitSink(DB, Opts.dbmatched, Opts.dbnotmatched, Opts.sizein, Opts.sizeout, Opts.dbcutout, Opts.otutab));
 		dbhits->SetSearcher(searchers[0]);
 		ExtraSinks.push_back(dbhits.get());
 	}

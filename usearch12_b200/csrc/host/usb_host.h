@@ -227,7 +227,8 @@ private:
 class DBHitSink : public HitSink {
 public:
 	DBHitSink(const SeqDB &DB, const std::string &DbMatched, const std::string &DbNotMatched, bool SizeIn, bool SizeOut,
-	  const std::string &DbCutOut = std::string()); // -dbcutout: the hit segments (dbhitsink.cpp:52-106)
+	  const std::string &DbCutOut = std::string(), // -dbcutout: the hit segments (dbhitsink.cpp:52-106)
+	  bool TopHitOnly = false);                    // -otutab counts only a query's first hit (dbhitsink.cpp:138-139)
 	~DBHitSink() override;
 	void SetSearcher(const GpuSearcher *S) { m_Searcher = S; }
 	void OnQueryDone(const SeqInfo &Query, const HitMgr &HM) override;
@@ -238,7 +239,7 @@ private:
 	const GpuSearcher *m_Searcher = nullptr;
 	std::string m_DbMatched, m_DbNotMatched, m_DbCutOut;
 	std::vector<std::vector<unsigned>> m_Los, m_His; // -dbcutout: first / last aligned target position of every hit
-	bool m_SizeIn, m_SizeOut, m_Done = false;
+	bool m_SizeIn, m_SizeOut, m_TopHitOnly = false, m_Done = false;
 	std::vector<unsigned> m_HitCounts;
 };
 
@@ -340,6 +341,7 @@ struct SearchOpts {
 	ClosedRefSink *ClosedRef = nullptr; // one of ExtraSinks: gets the searcher for the stored target letters
 	std::string dbmatched, dbnotmatched, dbcutout; // -dbmatched / -dbnotmatched / -dbcutout: Search() adds a DBHitSink
 	bool sizein = false, sizeout = false; // -sizein / -sizeout as -dbmatched reads them
+	bool otutab = false;                  // cmd_otutab: the DBHitSink counts one hit per query
 	unsigned minsize = 0;                 // -minsize: queries with a smaller size= annotation are not searched (search.cpp:59-82)
 	int gpus = 1;
 	uint32_t batch = 1u << 18;

@@ -192,6 +192,7 @@ int main(int argc, char **argv)
 		const std::string biom = take("biomout", nullptr);
 		otusink.reset(new OtuTabSink(tab, mapout, take("sample_delim", nullptr), opt.count("quiet") != 0, biom));
 		O.ExtraSinks.push_back(otusink.get());
+		O.otutab = true;
 	}
 	if (id.empty())
 		Die("--id not set"); // udbusortedsearcher.cpp:99-100: mandatory for both commands
@@ -281,7 +282,7 @@ int main(int argc, char **argv)
 	O.dbmatched = take("dbmatched", nullptr);
 	O.dbnotmatched = take("dbnotmatched", nullptr);
 	O.dbcutout = take("dbcutout", nullptr);
-	if (oquery.empty() && cquery.empty()) { // -otutab reads -sizein itself; cmd_closed_ref has no size options here
+	if (cquery.empty()) { // DBHitSink: -sizein weighs a hit with the query's size=, -sizeout annotates the matched targets
 		O.sizein = !take("sizein", nullptr).empty();
 		O.sizeout = !take("sizeout", nullptr).empty();
 	}
