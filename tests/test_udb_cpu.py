@@ -28,19 +28,30 @@ def params_for(name):
 
 @pytest.mark.parametrize("name", sorted(DIGESTS))
 def test_udb_write_is_byte_identical_to_the_reference(name, tmp_path):
-    labels, seqs = util.read_fasta(os.path.join(GOLDEN, name))
+    """Keys "<file>:w<n>" are written with -wordlength n (udbparams.cpp:58-81)."""
+    fname, _, wl = name.partition(":w")
+    labels, seqs = util.read_fasta(os.path.join(GOLDEN, fname))
     path = str(tmp_path / "ours.udb")
-    capi.udb_write(path, labels, seqs, params_for(name))
+    p = params_for(fname)
+    if wl:
+        p.word_length = int(wl)
+    capi.udb_write(path, labels, seqs, p)
     ours = open(path, "rb").read()
     assert len(ours) == DIGESTS[name]["bytes"]
     assert hashlib.sha256(ours).hexdigest() == DIGESTS[name]["sha256"]
     assert capi.lib().usb_udb_probe(path.encode()) == 1
+    fa = str(tmp_path / "in.fa")
+    with gzip.open(os.path.join(GOLDEN, fname), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    extra = ["-wordlength", wl] if wl else []
+    if wl:  # the command line of the host driver writes the same file
+        from usearch12_b200 import build
+        cli_out = str(tmp_path / "cli.udb")
+        subprocess.run([build.build_cli(), "-makeudb_usearch", fa, "-output", cli_out, "-quiet"] + extra, check=True)
+        assert open(cli_out, "rb").read() == ours
     if os.path.exists(REF):  # this container: the reference binary itself, byte by byte
-        fa = str(tmp_path / "in.fa")
-        with gzip.open(os.path.join(GOLDEN, name), "rb") as f, open(fa, "wb") as g:
-            g.write(f.read())
         ref = str(tmp_path / "ref.udb")
-        subprocess.run([REF, "-makeudb_usearch", fa, "-output", ref, "-quiet"], check=True, stdout=subprocess.DEVNULL,
+        subprocess.run([REF, "-makeudb_usearch", fa, "-output", ref, "-quiet"] + extra, check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL)
         assert open(ref, "rb").read() == ours
 

@@ -24,5 +24,13 @@ with tempfile.TemporaryDirectory() as tmp:
                        stderr=subprocess.DEVNULL)
         b = open(udb, "rb").read()
         out[name] = {"bytes": len(b), "sha256": hashlib.sha256(b).hexdigest()}
+    # -wordlength (udbparams.cpp:58-81): keys "<file>:w<length>"
+    for name, w in (("db.fa.gz", 6), ("loc_aa_db.fa.gz", 4)):
+        fa = os.path.join(tmp, name[:-3])
+        udb = fa + ".w.udb"
+        subprocess.run([REF, "-makeudb_usearch", fa, "-output", udb, "-wordlength", str(w), "-quiet"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        b = open(udb, "rb").read()
+        out["%s:w%d" % (name, w)] = {"bytes": len(b), "sha256": hashlib.sha256(b).hexdigest()}
 json.dump(out, open(os.path.join(ROOT, "tests", "golden", "udb_sha256.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -138,6 +138,12 @@ int main(int argc, char **argv)
 		if (mask != (nt ? "fastnucleo" : "fastamino") && mask != "none")
 			Die("-dbmask %s not supported (%s|none)", mask.c_str(), nt ? "fastnucleo" : "fastamino");
 		P.dbmask = mask != "none";
+		const std::string wl = take("wordlength", nullptr); // udbparams.cpp:58-81: index words of another length
+		if (!wl.empty()) {
+			P.word_length = (uint32_t)atoi(wl.c_str());
+			if (P.word_length < 2 || P.word_length > (nt ? 8u : 5u))
+				Die("-wordlength %s not supported (%s)", wl.c_str(), nt ? "2..8" : "2..5");
+		}
 		const std::string out = take("output", nullptr);
 		take("quiet", nullptr);
 		take("threads", nullptr);
