@@ -2,8 +2,12 @@
 // commands on the path (usearch_main.cpp:19-71, opts.cpp:272-362: "-opt value" or "--opt value").
 //
 //   usearch12_b200 -usearch_global Q.fa -db DB.fa -id 0.97 -strand plus|both
-//        [-maxaccepts n] [-maxrejects n] [-uc f] [-blast6out f] [-userout f] [-userfields a+b+..]
-//        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]
+//        [-maxaccepts n] [-maxrejects n] (0 = no limit) [-uc f] [-blast6out f] [-userout f] [-userfields a+b+..]
+//        [-alnout f] [-fastapairs f] [-qsegout f] [-tsegout f] [-matched f] [-notmatched f] [-matchedfq f]
+//        [-notmatchedfq f] [-trimout f] [-dbmatched f] [-dbnotmatched f] [-dbcutout f] [-sizein] [-sizeout]
+//        [-rowlen n] [-flank n] [-uc_hitsonly] [-output_no_hits] [-minsize n]
+//        [-match x] [-mismatch x] [-minhsp n] [-xdrop_nw x] [-hspw n] [-band n] [-bump n] [-fulldp]
+//        [-dbmask fastnucleo|none] [-gpus n] [-threads n] [-quiet]      (queries: FASTA or FASTQ)
 //   usearch12_b200 -otutab READS.fa -otus|-zotus|-db OTUS.fa -otutabout TABLE.txt [-mapout MAP.txt]
 //        [-sample_delim s] (searchcmd.cpp:21-40: -id 0.97 -strand both -maxaccepts 3 -maxrejects 32)
 //   usearch12_b200 -fastx_uniques IN.fa -fastaout OUT.fa [-sizeout] [-relabel prefix] [-minuniquesize n]
