@@ -1693,8 +1693,9 @@ static const char *err_text(uint32_t e)
 	static thread_local char buf[400];
 	if (e & ERR_KCAP) {
 		snprintf(buf, sizeof buf, "a query ran through all %u materialised candidates without terminating because pairs were "
-		                          "skipped (-self / -notself / -selfid / size and length ratio rules): the candidate list is longer "
-		                          "than this build materialises", (unsigned)RANK_KCAP);
+		                          "skipped (-self / -notself / -selfid / size and length ratio rules), and the whole lists do not fit: "
+		                          "search smaller batches (at most 2^29 query-strand x target pairs), or a database below -big",
+		         (unsigned)RANK_KCAP);
 		return buf;
 	}
 	snprintf(buf, sizeof buf, "device error flags 0x%x:%s%s%s%s%s%s%s%s%s%s", e, e & ERR_REC_FULL ? " gate record list full" : "",
