@@ -614,19 +614,36 @@ def main():
             return t["dram_bytes"]
 
         bounds = {
-            "k_rank": "hbm during the posting walk; about a third of the launch is the serial scan/select tail",
+            "k_rank": "hbm during the posting walk, whose rate is set by one shared-memory atomic per posting (see "
+                      "shared_atomic_floor); about a third of the launch is the serial scan/select tail",
             "k_gate": "instruction issue (ncu: issue slots 71 % busy in the stage that holds 86 % of its time, DRAM < 1 % of "
                       "peak): integer/bit work on packed letters in shared memory; its HBM fraction is small by construction",
             "k_dp": "shared-memory latency / issue (ncu: issue slots 46-62 % busy at 16 warps/SM); writes one trace byte per "
                     "cell to HBM",
             "k_align": "instruction issue / latency"}
 
+        def shared_atomic_floor():
+            """k_rank counts every posting with one shared-memory atomic; tools/ubench_smem.cu measured 3.85 cycles per
+            warp-wide random atomic per SM on B200 (profiles/r2_ubench_smem.txt).  Time the launch would take if it did
+            nothing but those atomics at that rate on all SMs -- the floor of this counting design."""
+            try:
+                n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+                mhz = float((P1["clocks"] or {}).get("sm_mhz") or 1965.0)
+                ms = float(P1["ctr"]["postings"]) * (3.85 / 32.0) / (n_sm * mhz * 1e6) * 1e3
+                return {"ms": ms, "frac": ms / ms_k["k_rank"] if ms_k.get("k_rank") else None,
+                        "cycles_per_warp_atomic": 3.85, "source": "profiles/r2_ubench_smem.txt"}
+            except Exception:  # explanatory key only: never take the line down
+                return None
+
         def kernel_line(name):
             ms = ms_k[name]
             gbps = alg[name] / (ms / 1000.0) / 1e9 if ms else None
-            return {"ms": ms, "share_of_step": ms / max(sum(ms_k.values()), 1e-9), "algorithmic_bytes_per_launch": alg[name],
+            line = {"ms": ms, "share_of_step": ms / max(sum(ms_k.values()), 1e-9), "algorithmic_bytes_per_launch": alg[name],
                     "achieved_GBps": gbps, "frac_of_hbm_peak": gbps / peak if gbps else None, "traffic": traffic_of(name),
                     "bound": bounds[name]}
+            if name == "k_rank":
+                line["shared_atomic_floor"] = shared_atomic_floor()
+            return line
         achieved = alg[dom] / (ms_k[dom] / 1000.0) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "query-seqs/s", "n_gpus": world, "steps": a.steps,
