@@ -219,3 +219,15 @@ def test_otutab_sink_writes_the_reference_files(tmp_path):
                         "-notmatched", "nm.fa", "-sizeout"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     check_otutab_outputs(tmp)
+
+
+def test_userout_needs_userfields(tmp_path):
+    """outputsink.cpp:149-156: Die("--userout requires --userfields")."""
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    q, d = M.write_inputs("fmt_sz", str(tmp_path))
+    hits = os.path.join(str(tmp_path), "hits.tsv")
+    open(hits, "wb").write(b"")
+    r = subprocess.run([replay, "-query", q, "-db", d, "-hits", hits, "-userout", os.path.join(str(tmp_path), "u")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "--userout requires --userfields" in r.stdout

@@ -673,8 +673,10 @@ OutputSink::OutputSink(const OutputOpts &O) : m_O(O)
 		fprintf(m_f[O_ALN], "%s\nusearch12_b200 (B200 hot path of usearch v12.0)\n", O.cmdline.c_str());
 	}
 	if (m_f[O_USER]) {
-		// userout.cpp:20-60: fields separated by '+'; default query+target+id
-		std::string spec = O.userfields.empty() ? "query+target+id" : O.userfields;
+		// outputsink.cpp:149-156: -userout needs -userfields; userout.cpp:20-60: fields separated by '+'
+		if (O.userfields.empty())
+			Die("--userout requires --userfields");
+		const std::string &spec = O.userfields;
 		size_t pos = 0;
 		while (pos <= spec.size()) {
 			size_t e = spec.find('+', pos);
