@@ -262,6 +262,7 @@ int main(int argc, char **argv)
 			O.P.hspw = (uint32_t)atoi(hw.c_str());
 	}
 	O.P.bump = (uint32_t)atoi(take("bump", "50").c_str()); // udbusortedsearcher.cpp:269-282
+	O.P.big = (uint32_t)atoi(take("big", "100000").c_str()); // udbusortedsearcher.cpp:39-58: UDBSearchBig above this many targets
 	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
 	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
 	const std::string dbmask = take("dbmask", nucleo ? "fastnucleo" : "fastamino");
