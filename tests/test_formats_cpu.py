@@ -231,3 +231,24 @@ def test_userout_needs_userfields(tmp_path):
     r = subprocess.run([replay, "-query", q, "-db", d, "-hits", hits, "-userout", os.path.join(str(tmp_path), "u")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "--userout requires --userfields" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["acc_maxhits", "acc_tophit", "acc_tophits"])
+def test_hit_selection_matches_reference(name, tmp_path):
+    """-maxhits / -top_hit_only / -top_hits_only (HitMgr::GetHitCount / GetHit / GetTopHit, hitmgr.cpp:367-420,466-475):
+    SelectHits applied to the reference's unselected hit lists (tests/golden/acc_sel.hits.gz) gives the files the
+    reference wrote with the option (tools/make_golden_accept.py)."""
+    import make_golden_selection as S
+    from usearch12_b200 import build
+    replay = build.build_format_replay()
+    tmp = str(tmp_path)
+    for n in ("acc_q", "acc_db"):
+        with gzip.open(os.path.join(util.GOLDEN, n + ".fa.gz"), "rb") as f, open(os.path.join(tmp, n + ".fa"), "wb") as g:
+            g.write(f.read())
+    open(os.path.join(tmp, "hits.tsv"), "wb").write(golden_bytes("acc_sel", "hits"))
+    r = subprocess.run([replay, "-query", "acc_q.fa", "-db", "acc_db.fa", "-hits", "hits.tsv", "-userout", "o.user",
+                        "-userfields", S.USERFIELDS, "-uc", "o.uc", "-blast6out", "o.b6"] + S.SELECTIONS[name], cwd=tmp,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    for kind in ("user", "uc", "b6"):
+        assert open(os.path.join(tmp, "o." + kind), "rb").read() == golden_bytes(name, kind), kind

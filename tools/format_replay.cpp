@@ -11,6 +11,7 @@
 //   format_replay -query Q.fa -db DB.udb|DB.fa -hits HITS.tsv [-local 1 -evalue E] [-amino 1]
 //                 [-uc f] [-blast6out f] [-userout f -userfields a+b] [-alnout f] [-fastapairs f] [-qsegout f]
 //                 [-tsegout f] [-matched f] [-notmatched f] [-matchedfq f] [-notmatchedfq f] [-dbmatched f] [-dbnotmatched f] [-sizein] [-sizeout]
+#include <algorithm>
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +49,7 @@ int main(int argc, char **argv)
 		const char *a = argv[i];
 		while (*a == '-')
 			++a;
-		if (!strcmp(a, "sizein") || !strcmp(a, "sizeout") || !strcmp(a, "output_no_hits") || !strcmp(a, "uc_hitsonly"))
+		if (!strcmp(a, "sizein") || !strcmp(a, "sizeout") || !strcmp(a, "output_no_hits") || !strcmp(a, "uc_hitsonly") || !strcmp(a, "top_hit_only") || !strcmp(a, "top_hits_only"))
 			opt[a] = "1";
 		else if (i + 1 < argc)
 			opt[a] = argv[++i];
@@ -96,9 +97,13 @@ int main(int argc, char **argv)
 		DB.FromUDB(get("db"), nucleo, wl); // letters masked as the reference's database holds them
 	} else
 		DB.FromFasta(get("db"));
-	std::unordered_map<std::string, uint32_t> qidx, tidx;
+	// query labels need not be unique: the table is in query order (the reference ran with one thread), so a hit
+	// belongs to the first query of that label at or behind the query of the hit before it
+	std::unordered_map<std::string, std::vector<uint32_t>> qidx;
+	std::unordered_map<std::string, uint32_t> tidx;
+	uint32_t cursor = 0;
 	for (uint32_t i = 0; i < Q.GetSeqCount(); ++i)
-		qidx.emplace(Q.GetLabel(i), i);
+		qidx[Q.GetLabel(i)].push_back(i);
 	for (uint32_t i = 0; i < DB.GetSeqCount(); ++i)
 		tidx.emplace(DB.GetLabel(i), i);
 
@@ -125,7 +130,13 @@ int main(int argc, char **argv)
 		Row r;
 		memset(&r.h, 0, sizeof r.h);
 		usb_hit &h = r.h;
-		h.query = qi->second;
+		{
+			const std::vector<uint32_t> &ids = qi->second;
+			auto it = std::lower_bound(ids.begin(), ids.end(), cursor);
+			if (it == ids.end())
+				Die("hit table: hits of %s are not in query order", f[0].c_str());
+			h.query = cursor = *it;
+		}
 		h.target = ti->second;
 		h.strand = f[2] == "-";
 		h.ids = (uint32_t)atoi(f[3].c_str());
@@ -180,6 +191,10 @@ int main(int argc, char **argv)
 	O.local = local;
 	O.match = (int)P.match;
 	O.mismatch = (int)P.mismatch;
+	HitSelection Sel;
+	Sel.maxhits = (unsigned)atoi(get("maxhits").c_str());
+	Sel.top_hit_only = !get("top_hit_only").empty();
+	Sel.top_hits_only = !get("top_hits_only").empty();
 	OutputSink Sink(O);
 	DBHitSink DbSink(DB, get("dbmatched"), get("dbnotmatched"), !get("sizein").empty(), !get("sizeout").empty(), get("dbcutout"),
 	  !get("otutabout").empty() || !get("mapout").empty() || !get("biomout").empty());
@@ -209,6 +224,7 @@ int main(int argc, char **argv)
 					Die("usb_params_evalue: %s", usb_last_error());
 				HM.m_Hits.push_back(AR);
 			}
+			SelectHits(HM.m_Hits, Sel); // -maxhits / -top_hit_only / -top_hits_only, as BuildHitMgrs does
 		}
 		Sink.OnBatchDone(batch);
 		DbSink.OnBatchDone(batch);

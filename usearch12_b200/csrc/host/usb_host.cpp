@@ -1593,6 +1593,37 @@ void GpuSearcher::SetTargetAttrs(const uint32_t *LabelIds, const uint32_t *Sizes
 	CheckUsb(usb_index_set_attrs(m_Index, 0, m_DB.GetSeqCount(), LabelIds, Sizes), "usb_index_set_attrs");
 }
 
+// HitMgr::GetHitCount / GetHit (hitmgr.cpp:367-398,466-475): which hits of a query the sinks see with -maxhits,
+// -top_hit_only, -top_hits_only.  Hits is in HitMgr::Sort order.
+void SelectHits(std::vector<AlignResult> &H, const HitSelection &Sel)
+{
+	if (!Sel.Any() || H.empty())
+		return;
+	auto score = [&](const AlignResult &AR) { return AR.IsLocal() ? (float)AR.GetRawScore() : (float)AR.GetFractId(); };
+	size_t n = H.size();
+	if (Sel.maxhits && n > Sel.maxhits)
+		n = Sel.maxhits;
+	if (Sel.top_hit_only) {
+		size_t top = 0; // GetTopHit over every hit (hitmgr.cpp:400-420)
+		for (size_t i = 1; i < H.size(); ++i)
+			if (score(H[i]) > score(H[top]) || (score(H[i]) == score(H[top]) && H[i].GetTargetIndex() < H[top].GetTargetIndex()))
+				top = i;
+		const AlignResult keep = H[top];
+		H.assign(1, keep);
+	} else {
+		if (Sel.top_hits_only) {
+			float best = score(H[0]);
+			for (const AlignResult &AR : H)
+				best = std::max(best, score(AR));
+			size_t i = 1;
+			while (i < n && !(score(H[i]) < best))
+				++i;
+			n = i;
+		}
+		H.resize(n);
+	}
+}
+
 // Replaces the loop "SS->GetNext(Query); searcher->Search(Query)" of Thread() (search.cpp:63-86)
 // for a batch: one C-ABI call, then one HitMgr per query holding AlignResults in output order.
 std::shared_ptr<void> GpuSearcher::SearchRaw(const SeqDB &Queries, uint32_t First, uint32_t Count)
@@ -1645,34 +1676,7 @@ void GpuSearcher::BuildHitMgrs(const std::shared_ptr<void> &Result, const SeqDB 
 					  "usb_local_evalue");
 				HM.m_Hits.push_back(AR);
 			}
-			if (m_Sel.Any() && !HM.m_Hits.empty()) {
-				// HitMgr::GetHitCount / GetHit (hitmgr.cpp:367-398,466-475); m_Hits is in HitMgr::Sort order
-				std::vector<AlignResult> &H = HM.m_Hits;
-				auto score = [&](const AlignResult &AR) { return AR.IsLocal() ? (float)AR.GetRawScore() : (float)AR.GetFractId(); };
-				size_t n = H.size();
-				if (m_Sel.maxhits && n > m_Sel.maxhits)
-					n = m_Sel.maxhits;
-				if (m_Sel.top_hit_only) {
-					size_t top = 0; // GetTopHit over every hit (hitmgr.cpp:400-420)
-					for (size_t i = 1; i < H.size(); ++i)
-						if (score(H[i]) > score(H[top]) ||
-						    (score(H[i]) == score(H[top]) && H[i].GetTargetIndex() < H[top].GetTargetIndex()))
-							top = i;
-					const AlignResult keep = H[top];
-					H.assign(1, keep);
-				} else {
-					if (m_Sel.top_hits_only) {
-						float best = score(H[0]);
-						for (const AlignResult &AR : H)
-							best = std::max(best, score(AR));
-						size_t i = 1;
-						while (i < n && !(score(H[i]) < best))
-							++i;
-						n = i;
-					}
-					H.resize(n);
-				}
-			}
+			SelectHits(HM.m_Hits, m_Sel);
 		}
 	};
 	const unsigned T = std::max(1u, std::min(Threads, Count / 4096));

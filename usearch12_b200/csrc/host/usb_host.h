@@ -188,6 +188,9 @@ struct HitSelection {
 	bool Any() const { return maxhits != 0 || top_hit_only || top_hits_only; }
 };
 
+// applies a HitSelection to a query's hit list (used by GpuSearcher::BuildHitMgrs)
+void SelectHits(std::vector<AlignResult> &Hits, const HitSelection &Sel);
+
 struct FormatTables; // identity / substitution tables of the row formats (usb_host.cpp)
 
 // outputsink.cpp:358-381; formats of outputuc.cpp:19-69, blast6out.cpp:27-80, userout.cpp:126-352,
