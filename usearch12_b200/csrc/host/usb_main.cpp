@@ -26,6 +26,23 @@
 
 using namespace usbhost;
 
+// StrToUint / StrToFloat (myutils.cpp:1148-1155,1217-1231): a malformed number stops the program
+static unsigned ToUint(const std::string &s)
+{
+	if (s.empty() || s.find_first_not_of("0123456789") != std::string::npos)
+		Die("Invalid integer '%s'", s.c_str());
+	return (unsigned)strtoul(s.c_str(), nullptr, 10);
+}
+
+static double ToFloat(const std::string &s)
+{
+	char *end = nullptr;
+	const double d = strtod(s.c_str(), &end);
+	if (s.empty() || !end || *end != 0)
+		Die("Invalid floating-point number '%s'", s.c_str());
+	return d;
+}
+
 int main(int argc, char **argv)
 {
 	std::map<std::string, std::string> opt;
@@ -72,11 +89,11 @@ int main(int argc, char **argv)
 		const std::string cid = take("id", nullptr);
 		if (cid.empty())
 			Die("Must specify -id"); // makeclustersearcher.cpp:30-31
-		C.P.id = (float)atof(cid.c_str());
+		C.P.id = (float)ToFloat(cid);
 		const std::string cstrand = take("strand", "plus");
 		if (cstrand != "plus")
 			Die("-cluster_fast -strand %s is not supported by this build", cstrand.c_str());
-		C.P.maxrejects = (uint32_t)atoi(take("maxrejects", C.smallmem ? "32" : "8").c_str()); // terminator.cpp:10-31
+		C.P.maxrejects = (uint32_t)ToUint(take("maxrejects", C.smallmem ? "32" : "8")); // terminator.cpp:10-31
 		C.uc = take("uc", nullptr);
 		C.centroids = take("centroids", nullptr);
 		C.sort = take("sort", nullptr);
@@ -89,7 +106,7 @@ int main(int argc, char **argv)
 		C.Out.tsegout = take("tsegout", nullptr);
 		C.Out.matched = take("matched", nullptr);
 		C.Out.notmatched = take("notmatched", nullptr);
-		C.Out.rowlen = (unsigned)atoi(take("rowlen", "80").c_str());
+		C.Out.rowlen = (unsigned)ToUint(take("rowlen", "80"));
 		if (C.Out.rowlen == 0)
 			Die("-rowlen must be positive");
 		for (int i = 0; i < argc; ++i) {
@@ -100,8 +117,8 @@ int main(int argc, char **argv)
 		C.sizeout = !take("sizeout", nullptr).empty();
 		C.relabel = take("relabel", nullptr);
 		C.minsize_filled = opt.count("minsize") != 0;
-		C.minsize = (unsigned)atoi(take("minsize", "0").c_str());
-		C.max_block = (uint32_t)atoi(take("batch", "65536").c_str());
+		C.minsize = (unsigned)ToUint(take("minsize", "0"));
+		C.max_block = (uint32_t)ToUint(take("batch", "65536"));
 		C.quiet = !take("quiet", nullptr).empty();
 		take("threads", nullptr); // derep/cluster order follow the reference's -threads 1 behaviour
 		if (!opt.empty())
@@ -117,8 +134,8 @@ int main(int argc, char **argv)
 		U.relabel = take("relabel", nullptr);
 		U.sizeout = !take("sizeout", nullptr).empty();
 		U.sizein = !take("sizein", nullptr).empty();
-		U.topn = (unsigned)atoi(take("topn", "0").c_str());
-		U.minuniquesize = (unsigned)atoi(take("minuniquesize", "0").c_str());
+		U.topn = (unsigned)ToUint(take("topn", "0"));
+		U.minuniquesize = (unsigned)ToUint(take("minuniquesize", "0"));
 		const bool quiet = !take("quiet", nullptr).empty();
 		take("threads", nullptr); // the unique order follows the reference's -threads 1 behaviour
 		if (opt.count("output"))
@@ -144,7 +161,7 @@ int main(int argc, char **argv)
 		P.dbmask = mask != "none";
 		const std::string wl = take("wordlength", nullptr); // udbparams.cpp:58-81: index words of another length
 		if (!wl.empty()) {
-			P.word_length = (uint32_t)atoi(wl.c_str());
+			P.word_length = (uint32_t)ToUint(wl);
 			if (P.word_length < 2 || P.word_length > (nt ? 8u : 5u))
 				Die("-wordlength %s not supported (%s)", wl.c_str(), nt ? "2..8" : "2..5");
 		}
@@ -206,7 +223,7 @@ int main(int argc, char **argv)
 	}
 	if (id.empty())
 		Die("--id not set"); // udbusortedsearcher.cpp:99-100: mandatory for both commands
-	O.P.id = (float)atof(id.c_str());
+	O.P.id = (float)ToFloat(id);
 	bool nucleo = true;
 	if (!lquery.empty()) {
 		// searchcmd.cpp:42 cmd_usearch_local; the DB alphabet is guessed from its letters like
@@ -216,22 +233,22 @@ int main(int argc, char **argv)
 		if (ev.empty())
 			Die("Must set -evalue"); // accepter.cpp / search.cpp: mandatory for local searches
 		nucleo = IsUDBFile(db) ? UDBIsNucleo(db) : GuessIsNucleo(db);
-		usb_set_local(&O.P, nucleo ? 1 : 0, (float)atof(ev.c_str()));
-		O.P.xdrop_u = (float)atof(take("xdrop_u", "16").c_str());
-		O.P.xdrop_g = (float)atof(take("xdrop_g", "32").c_str());
+		usb_set_local(&O.P, nucleo ? 1 : 0, (float)ToFloat(ev));
+		O.P.xdrop_u = (float)ToFloat(take("xdrop_u", "16"));
+		O.P.xdrop_g = (float)ToFloat(take("xdrop_g", "32"));
 		const std::string lo = take("lopen", nullptr), le = take("lext", nullptr);
 		if (lo.empty() != le.empty())
 			Die("Must set both --lopen and --lext"); // alnparams.cpp:362-366
 		if (!lo.empty()) {
-			if (atof(lo.c_str()) < 0.0 || atof(le.c_str()) < 0.0)
+			if (ToFloat(lo) < 0.0 || ToFloat(le) < 0.0)
 				Die("Invalid --lopen/--lext, gap penalties must be >= 0");
-			O.P.lopen = -(float)atof(lo.c_str());
-			O.P.lext = -(float)atof(le.c_str());
+			O.P.lopen = -(float)ToFloat(lo);
+			O.P.lext = -(float)ToFloat(le);
 		}
-		O.P.ka_dbsize = (float)atof(take("ka_dbsize", "1e9").c_str());
+		O.P.ka_dbsize = (float)ToFloat(take("ka_dbsize", "1e9"));
 		const std::string hw = take("hspw", nullptr);
 		if (!hw.empty())
-			O.P.hspw = (uint32_t)atoi(hw.c_str());
+			O.P.hspw = (uint32_t)ToUint(hw);
 	} else if (oquery.empty()) {
 		// -usearch_global takes either alphabet (makedbsearcher.cpp:132-140); amino acid databases
 		// switch to BLOSUM62, gap open -17 and HSP words of 3 letters
@@ -248,22 +265,22 @@ int main(int argc, char **argv)
 	if (nucleo && strand != "plus" && strand != "both")
 		Die("Must specify -strand plus or both with nt db"); // search.cpp:23-34
 	O.P.strand_both = nucleo && strand == "both";
-	O.P.maxaccepts = (uint32_t)atoi(take("maxaccepts", dflt_ma).c_str());
-	O.P.maxrejects = (uint32_t)atoi(take("maxrejects", dflt_mr).c_str());
+	O.P.maxaccepts = (uint32_t)ToUint(take("maxaccepts", dflt_ma));
+	O.P.maxrejects = (uint32_t)ToUint(take("maxrejects", dflt_mr));
 	if (lquery.empty() && nucleo) {
 		// nucleotide substitution scores (alnparams.cpp:330-334 SetNucSubstMx) and the HSP heuristics of the
 		// global aligner (alnheuristics.cpp:26-44); a local search keeps its defaults here
-		O.P.match = (float)atof(take("match", "1").c_str());
-		O.P.mismatch = (float)atof(take("mismatch", "-2").c_str());
-		O.P.minhsp = (uint32_t)atoi(take("minhsp", "16").c_str());
-		O.P.xdrop_nw = (float)atof(take("xdrop_nw", "8").c_str());
+		O.P.match = (float)ToFloat(take("match", "1"));
+		O.P.mismatch = (float)ToFloat(take("mismatch", "-2"));
+		O.P.minhsp = (uint32_t)ToUint(take("minhsp", "16"));
+		O.P.xdrop_nw = (float)ToFloat(take("xdrop_nw", "8"));
 		const std::string hw = take("hspw", nullptr); // alnheuristics.cpp:60-61
 		if (!hw.empty())
-			O.P.hspw = (uint32_t)atoi(hw.c_str());
+			O.P.hspw = (uint32_t)ToUint(hw);
 	}
-	O.P.bump = (uint32_t)atoi(take("bump", "50").c_str()); // udbusortedsearcher.cpp:269-282
-	O.P.big = (uint32_t)atoi(take("big", "100000").c_str()); // udbusortedsearcher.cpp:39-58: UDBSearchBig above this many targets
-	O.P.band = (uint32_t)atoi(take("band", "16").c_str());   // alnheuristics.cpp:33
+	O.P.bump = (uint32_t)ToUint(take("bump", "50")); // udbusortedsearcher.cpp:269-282
+	O.P.big = (uint32_t)ToUint(take("big", "100000")); // udbusortedsearcher.cpp:39-58: UDBSearchBig above this many targets
+	O.P.band = (uint32_t)ToUint(take("band", "16"));   // alnheuristics.cpp:33
 	O.P.fulldp = !take("fulldp", nullptr).empty();            // alnheuristics.cpp:64-76
 	const std::string dbmask = take("dbmask", nucleo ? "fastnucleo" : "fastamino");
 	if (dbmask != (nucleo ? "fastnucleo" : "fastamino") && dbmask != "none")
@@ -275,7 +292,7 @@ int main(int argc, char **argv)
 	O.Out.userfields = take("userfields", nullptr);
 	O.Out.output_no_hits = !take("output_no_hits", nullptr).empty();
 	O.Out.uc_hitsonly = !take("uc_hitsonly", nullptr).empty();
-	O.minsize = (unsigned)atoi(take("minsize", "0").c_str());
+	O.minsize = (unsigned)ToUint(take("minsize", "0"));
 	// the other files of OutputSink::OpenOutputFiles (outputsink.cpp:135-195) and of DBHitSink (dbhitsink.cpp:42-50)
 	O.Out.alnout = take("alnout", nullptr);
 	O.Out.fastapairs = take("fastapairs", nullptr);
@@ -286,10 +303,10 @@ int main(int argc, char **argv)
 	O.Out.trimout = take("trimout", nullptr);
 	O.Out.matchedfq = take("matchedfq", nullptr);
 	O.Out.notmatchedfq = take("notmatchedfq", nullptr);
-	O.Out.rowlen = (unsigned)atoi(take("rowlen", "80").c_str());
+	O.Out.rowlen = (unsigned)ToUint(take("rowlen", "80"));
 	if (O.Out.rowlen == 0)
 		Die("-rowlen must be positive");
-	O.Out.flank = (unsigned)atoi(take("flank", "8").c_str());
+	O.Out.flank = (unsigned)ToUint(take("flank", "8"));
 	O.dbmatched = take("dbmatched", nullptr);
 	O.dbnotmatched = take("dbnotmatched", nullptr);
 	O.dbcutout = take("dbcutout", nullptr);
@@ -311,14 +328,14 @@ int main(int argc, char **argv)
 		auto flt = [&](const char *name, uint32_t bit, float &dst) {
 			const std::string v = take(name, nullptr);
 			if (!v.empty()) {
-				dst = (float)atof(v.c_str());
+				dst = (float)ToFloat(v);
 				O.P.accept_flags |= bit;
 			}
 		};
 		auto uns = [&](const char *name, uint32_t bit, uint32_t &dst) {
 			const std::string v = take(name, nullptr);
 			if (!v.empty()) {
-				dst = (uint32_t)atoi(v.c_str());
+				dst = (uint32_t)ToUint(v);
 				O.P.accept_flags |= bit;
 			}
 		};
@@ -344,12 +361,12 @@ int main(int argc, char **argv)
 		flt("termidd", USB_ACC_TERMIDD, O.P.termidd);
 		const std::string mh = take("maxhits", nullptr);
 		if (!mh.empty())
-			O.Sel.maxhits = (unsigned)atoi(mh.c_str());
+			O.Sel.maxhits = (unsigned)ToUint(mh);
 		O.Sel.top_hit_only = !take("top_hit_only", nullptr).empty();
 		O.Sel.top_hits_only = !take("top_hits_only", nullptr).empty();
 	}
-	O.gpus = atoi(take("gpus", "1").c_str());
-	O.batch = (uint32_t)atoi(take("batch", "262144").c_str());
+	O.gpus = ToUint(take("gpus", "1"));
+	O.batch = (uint32_t)ToUint(take("batch", "262144"));
 	O.quiet = !take("quiet", nullptr).empty();
 	take("threads", nullptr); // host threads are not on the search path here
 	if (!opt.empty())
