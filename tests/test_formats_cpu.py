@@ -252,3 +252,16 @@ def test_hit_selection_matches_reference(name, tmp_path):
     assert r.returncode == 0, r.stdout
     for kind in ("user", "uc", "b6"):
         assert open(os.path.join(tmp, "o." + kind), "rb").read() == golden_bytes(name, kind), kind
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-id", "0.9x", "-strand", "plus"], "Invalid floating-point number '0.9x'"),
+    (["-id", "0.9", "-strand", "plus", "-maxaccepts", "abc"], "Invalid integer 'abc'"),
+    (["-id", "0.9", "-strand", "plus", "-maxrejects", "-1"], "Invalid integer '-1'"),
+])
+def test_cli_rejects_malformed_numbers(args, msg):
+    """StrToUint / StrToFloat (myutils.cpp:1148-1155,1217-1231) stop the program; no device is needed to get there."""
+    from usearch12_b200 import build
+    r = subprocess.run([build.build_cli(), "-usearch_global", "x.fa", "-db", "y.fa"] + args, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and msg in r.stdout, r.stdout
