@@ -131,6 +131,8 @@ void SeqDB::FromFasta(const std::string &FileName)
 	fseek(f, 0, SEEK_END);
 	long sz = ftell(f);
 	fseek(f, 0, SEEK_SET);
+	if (sz == 0)
+		Die("Empty file %s", FileName.c_str()); // filetype.cpp:14-15
 	// (not a std::vector: its zero fill touches every page once more, 0.15 s per 200 MB)
 	std::unique_ptr<char[]> buf(new char[(size_t)sz + 1]);
 	if (sz > 0 && fread(buf.get(), 1, (size_t)sz, f) != (size_t)sz)
